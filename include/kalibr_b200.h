@@ -1,0 +1,187 @@
+/*
+ * kalibr_b200.h — C ABI of the B200-native batch-calibration hot path.
+ *
+ * This is the drop-in boundary.  Every entry point names the
+ * reference interface it replaces; file:line citations are relative to the
+ * reference tree (ToyotaResearchInstitute/kalibr), abbreviations:
+ *   BE  = aslam_optimizer/aslam_backend
+ *   BX  = aslam_optimizer/aslam_backend_expressions
+ *   CAM = aslam_cv/aslam_cameras
+ *   K2  = aslam_offline_calibration/kalibr2
+ *
+ * Conventions: opaque handle, int status (0 = OK, negative = error, message
+ * via kb_last_error), no exceptions cross the boundary, one caller thread per
+ * handle (BE/src/Optimizer2.cpp:183-273 drives a solver from one thread).
+ * All pointers in the signatures are caller-owned HOST pointers (FP64 /
+ * int32 / int64, SoA); the library owns every device buffer.  There is no CPU
+ * fallback: kb_create fails with KB_ERR_NO_DEVICE when no sm_100 device is
+ * usable.
+ */
+#ifndef KALIBR_B200_H_
+#define KALIBR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_API __attribute__((visibility("default")))
+
+/* ---- status codes ------------------------------------------------------- */
+typedef int32_t kb_status;
+#define KB_OK 0
+#define KB_ERR_INVALID_ARGUMENT (-1)
+#define KB_ERR_NO_DEVICE (-2)
+#define KB_ERR_CUDA (-3)
+#define KB_ERR_NCCL (-4)
+#define KB_ERR_STATE (-5)      /* call sequence violated (e.g. solve before build) */
+#define KB_ERR_ALLOC (-6)
+
+/* ---- camera models: K2/include/kalibr2/CameraCalibrator.hpp:421-441 ------ */
+typedef enum {
+  KB_PINHOLE_RADTAN = 0, /* PinholeProjection<RadialTangentialDistortion>  P=4 (fu,fv,cu,cv)            D=4 (k1,k2,p1,p2) */
+  KB_PINHOLE_EQUI = 1,   /* PinholeProjection<EquidistantDistortion>       P=4                          D=4 (k1..k4)      */
+  KB_OMNI_RADTAN = 2,    /* OmniProjection<RadialTangentialDistortion>     P=5 (xi,fu,fv,cu,cv)         D=4               */
+  KB_EUCM_NONE = 3,      /* ExtendedUnifiedProjection<NoDistortion>        P=6 (alpha,beta,fu,fv,cu,cv) D=0 (active, 0-dim) */
+  KB_DS_NONE = 4,        /* DoubleSphereProjection<NoDistortion>           P=6 (xi,alpha,fu,fv,cu,cv)   D=0 (active, 0-dim) */
+  KB_NUM_MODELS = 5
+} kb_camera_model;
+
+/* Design-variable insertion order of the three batch drivers
+ * (K2/include/kalibr2/CalibrationTools.hpp:93-144, 183-300, 376-428).  It
+ * fixes blockIndex / columnBase (BE/src/Optimizer2.cpp:110-124). */
+typedef enum {
+  KB_ORDER_SINGLE = 0, /* proj, dist ; per set q_v, t_v                                  */
+  KB_ORDER_STEREO = 1, /* baseline q,t ; per set q_v,t_v ; proj0,dist0, proj1,dist1      */
+  KB_ORDER_RIG = 2     /* per cam proj,dist ; per baseline q,t ; per set q_v,t_v         */
+} kb_driver_order;
+
+#define KB_CAM_PARAM_STRIDE 10 /* per camera: P projection params then D distortion params, zero padded */
+#define KB_POSE_STRIDE 7       /* q[4] (x,y,z,w; sm_kinematics JPL, scalar last) then t[3] */
+
+/*
+ * Problem description = what K2's drivers hand to Optimizer2 as an
+ * OptimizationProblem, flattened.  A "view" is one (synced set, camera) image:
+ * the run of ReprojectionError terms added by one AddReprojectionErrorsForView
+ * call (K2/include/kalibr2/CameraCalibrator.hpp:238-265).  Terms (observed
+ * corners) are listed in the reference's error-term insertion order, so term
+ * index i has rowBase 2*i (BE/src/Optimizer2.cpp:130-135); views index
+ * contiguous runs of it.
+ */
+typedef struct {
+  int32_t driver_order;        /* kb_driver_order */
+  int32_t n_cams;
+  const int32_t* cam_model;    /* [n_cams] kb_camera_model */
+  const double* cam_params;    /* [n_cams][KB_CAM_PARAM_STRIDE] initial intrinsics */
+  const double* baselines;     /* [n_cams-1][KB_POSE_STRIDE]  T_cam(k+1)_cam(k) initial guess */
+  int32_t n_sets;
+  const double* set_poses;     /* [n_sets][KB_POSE_STRIDE]    T_target_cam0 initial guess (pose DV; the term uses its inverse) */
+  int32_t n_target_points;
+  const double* target_points; /* [n_target_points][3] */
+  int32_t n_views;
+  const int32_t* view_set;     /* [n_views] */
+  const int32_t* view_cam;     /* [n_views] */
+  const int64_t* view_begin;   /* [n_views+1] term range of each view */
+  int64_t n_terms;
+  const double* y_u;           /* [n_terms] measured corner, pixels */
+  const double* y_v;           /* [n_terms] */
+  const int32_t* corner_id;    /* [n_terms] index into target_points */
+  /* multi-GPU: sets are sharded by contiguous ranges over n_ranks; NCCL id from kb_nccl_unique_id */
+  int32_t n_ranks;
+  int32_t rank;
+  const char* nccl_id;         /* 128 bytes, NULL when n_ranks == 1 */
+  int32_t device;              /* CUDA device ordinal */
+} kb_problem_desc;
+
+typedef struct kb_handle kb_handle;
+
+/* ---- life cycle ---------------------------------------------------------- */
+/* ≙ Optimizer2::initialize + LinearSystemSolver::initMatrixStructure
+ *   (BE/src/Optimizer2.cpp:95-151, BE/src/LinearSystemSolver.cpp:117-138,
+ *    BE/src/BlockCholeskyLinearSystemSolver.cpp:34-55).  Uploads the problem. */
+KB_API kb_status kb_create(const kb_problem_desc* desc, kb_handle** out);
+KB_API void kb_destroy(kb_handle* h);
+KB_API const char* kb_last_error(const kb_handle* h); /* h may be NULL: last create error */
+KB_API kb_status kb_nccl_unique_id(char out[128]);     /* rank 0 calls, caller broadcasts */
+
+/* sizes: ≙ LinearSystemSolver::JRows/JCols (BE/include/aslam/backend/LinearSystemSolver.hpp:62-66) */
+KB_API int64_t kb_jrows(const kb_handle* h);  /* 2 * GLOBAL number of terms */
+KB_API int64_t kb_jcols(const kb_handle* h);  /* sum of active DV dimensions */
+KB_API int32_t kb_num_design_variables(const kb_handle* h); /* active DVs incl. 0-dim ones */
+/* ≙ DesignVariable::blockIndex/columnBase/minimalDimensions (BE/include/aslam/backend/DesignVariable.hpp:18-145) */
+KB_API kb_status kb_get_dv_layout(const kb_handle* h, int32_t* column_base /*[n_dv]*/, int32_t* dims /*[n_dv]*/);
+
+/* ---- per-iteration hot path ---------------------------------------------- */
+/* ≙ LinearSystemSolver::evaluateError (BE/src/LinearSystemSolver.cpp:81-92): returns J = sum e^T invR e
+ *   over ALL ranks and fills the device copy of e().  use_m_estimator must be 0 (NoMEstimator only). */
+KB_API kb_status kb_evaluate_error(kb_handle* h, int32_t use_m_estimator, double* out_cost);
+/* ≙ BlockCholeskyLinearSystemSolver::buildSystem (BE/src/BlockCholeskyLinearSystemSolver.cpp:58-72):
+ *   linearise every term at the current state and assemble H, rhs. */
+KB_API kb_status kb_build_system(kb_handle* h, int32_t use_m_estimator);
+/* ≙ LinearSystemSolver::setConstantConditioner (BE/src/LinearSystemSolver.cpp:111-114); squared when applied */
+KB_API kb_status kb_set_constant_conditioner(kb_handle* h, double lambda);
+/* ≙ BlockCholeskyLinearSystemSolver::solveSystem (BE/src/BlockCholeskyLinearSystemSolver.cpp:74-106), including
+ *   the λ² augment / λ un-augment asymmetry.  dx has kb_jcols entries (this rank's poses + shared block; poses of
+ *   other ranks' sets are returned as 0 unless gather_dx != 0).  *pos_def = 0 ≙ solveSystem returning false. */
+KB_API kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* pos_def);
+/* dx^T (lambda dx + rhs) on the device: the denominator of LevenbergMarquardtTrustRegionPolicy::getLmRho
+ *   (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:107-113) for the dx of the last kb_solve_system. */
+KB_API kb_status kb_lm_rho_denominator(kb_handle* h, double lambda, double* out);
+/* ≙ Optimizer2::applyStateUpdate (BE/src/Optimizer2.cpp:290-307) with the dx of the last solve; returns max|dx| */
+KB_API kb_status kb_apply_state_update(kb_handle* h, double* out_max_abs_dx);
+/* ≙ Optimizer2::revertLastStateUpdate (BE/src/Optimizer2.cpp:313-318) */
+KB_API kb_status kb_revert_last_state_update(kb_handle* h);
+
+/* One whole Optimizer2::optimize() (BE/src/Optimizer2.cpp:183-273) with LevenbergMarquardtTrustRegionPolicy
+ * (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:50-113) driven by the host C++ mirror; state stays on the device. */
+typedef struct {
+  double convergence_delta_x; /* 1e-3  K2 CalibrationTools.hpp:57-66 */
+  double convergence_delta_j; /* 1.0   */
+  int32_t max_iterations;     /* 200   */
+  double lm_lambda_init;      /* 10.0  */
+  int32_t verbose;
+} kb_optimizer_options;
+typedef struct { /* ≙ SolutionReturnValue, BE/include/aslam/backend/backend.hpp:14-27 */
+  double j_start, j_final, dx_final, dj_final;
+  int32_t iterations, failed_iterations, linear_solver_failure;
+} kb_solution;
+KB_API void kb_default_optimizer_options(kb_optimizer_options* o);
+KB_API kb_status kb_optimize(kb_handle* h, const kb_optimizer_options* o, kb_solution* out);
+
+/* ---- read-back (parity / results) ----------------------------------------- */
+KB_API kb_status kb_get_error_vector(kb_handle* h, double* e /*[2*local terms]*/);      /* ≙ LinearSystemSolver::e() : -sqrtInvR^T e */
+KB_API kb_status kb_get_rhs(kb_handle* h, double* rhs /*[jcols]*/);                     /* ≙ LinearSystemSolver::rhs() */
+/* Materialised Jacobians of every local term at the current state: J[term][2][width] row-major, width =
+ * kb_jacobian_width(); column layout [pose q(3) t(3) | baselines 0..C-2 (q,t) | proj(6, padded) | dist(4, padded)];
+ * ≙ ErrorTerm::evaluateJacobians → JacobianContainer (CVE .../ReprojectionError.hpp:63-77). */
+KB_API int32_t kb_jacobian_width(const kb_handle* h);
+KB_API kb_status kb_get_jacobians(kb_handle* h, double* J);
+/* Upper-triangular block pattern of H exactly as SparseBlockMatrix holds it after buildSystem+solveSystem
+ * (sparse_block_matrix.hpp:121-143; JacobianContainer.cpp:112-126): for block column c, block_row[col_ptr[c]..col_ptr[c+1])
+ * ascending.  values are the blocks column-major one after another (value_ptr[k] offsets).  Call with NULL arrays to query counts. */
+KB_API kb_status kb_get_hessian_blocks(kb_handle* h, int64_t* n_blocks, int64_t* n_values, int64_t* col_ptr /*[n_dv+1]*/,
+                                       int32_t* block_row, int64_t* value_ptr, double* values);
+/* current state ≙ DesignVariable::getParameters */
+KB_API kb_status kb_get_camera_params(kb_handle* h, double* cam_params /*[n_cams][KB_CAM_PARAM_STRIDE]*/);
+KB_API kb_status kb_get_baselines(kb_handle* h, double* baselines /*[n_cams-1][7]*/);
+KB_API kb_status kb_get_set_poses(kb_handle* h, double* set_poses /*[n_sets][7]; other ranks' sets untouched*/);
+/* replace the measurements (same structure) — used by the end-to-end bench leg to time host→device per step */
+KB_API kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v);
+/* reset state to the initial guess given at kb_create */
+KB_API kb_status kb_reset_state(kb_handle* h);
+
+/* ---- instrumentation ------------------------------------------------------ */
+/* number of this library's kernels launched since creation (bench.py's gpu_launches) */
+KB_API int64_t kb_kernel_launches(const kb_handle* h);
+/* device time in ms of the last call's stages measured with CUDA events on the library's stream:
+ *  [0] evaluate  [1] linearise+assemble  [2] expand  [3] schur  [4] reduced solve  [5] backsub  [6] update */
+#define KB_NUM_STAGES 8
+KB_API kb_status kb_get_stage_ms(kb_handle* h, double* ms /*[KB_NUM_STAGES]*/);
+KB_API kb_status kb_enable_stage_timing(kb_handle* h, int32_t on);
+KB_API void* kb_cuda_stream(kb_handle* h); /* cudaStream_t the library launches on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KALIBR_B200_H_ */

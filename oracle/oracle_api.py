@@ -1,0 +1,228 @@
+"""ctypes binding of the CPU oracle (oracle/libkalibr_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs, never by
+kalibr_b200/.  PARITY UNPINNED (see oracle/ko_math.hpp).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libkalibr_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("kalibr_oracle.cpp", "ko_backend.hpp", "ko_cameras.hpp", "ko_math.hpp")]
+    srcs.append(os.path.join(_HERE, "..", "include", "kalibr_b200.h"))
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "libkalibr_oracle.so"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        L.ko_last_error.restype = C.c_char_p
+        L.ko_create.restype = C.c_void_p
+        L.ko_create.argtypes = [C.c_void_p, C.c_int]
+        L.ko_destroy.argtypes = [C.c_void_p]
+        for name in ("ko_jrows", "ko_jcols"):
+            getattr(L, name).restype = C.c_int64
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.ko_num_design_variables.restype = C.c_int32
+        L.ko_num_design_variables.argtypes = [C.c_void_p]
+        L.ko_get_dv_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ko_evaluate_error.restype = C.c_double
+        L.ko_evaluate_error.argtypes = [C.c_void_p, C.c_int]
+        L.ko_get_error_vector.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_build_system.argtypes = [C.c_void_p, C.c_int]
+        L.ko_set_constant_conditioner.argtypes = [C.c_void_p, C.c_double]
+        L.ko_solve_system.restype = C.c_int32
+        L.ko_solve_system.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_get_rhs.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_apply_state_update.restype = C.c_double
+        L.ko_apply_state_update.argtypes = [C.c_void_p]
+        L.ko_revert_last_state_update.argtypes = [C.c_void_p]
+        L.ko_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ko_get_trace.restype = C.c_int32
+        L.ko_get_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.ko_get_jacobian_ccs.restype = C.c_int64
+        L.ko_get_jacobian_ccs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ko_get_hessian_blocks.restype = C.c_int32
+        L.ko_get_hessian_blocks.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.ko_get_camera_params.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_get_baselines.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_get_set_poses.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_camera_project.restype = C.c_int32
+        L.ko_camera_project.argtypes = [C.c_int32] + [C.c_void_p] * 6
+        L.ko_quat2r.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_update_quat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ko_inverse4.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_time_iteration.restype = C.c_int32
+        L.ko_time_iteration.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+BLOCK_CHOLESKY, SPARSE_CHOLESKY, BLOCK_CHOLESKY_DENSE = 0, 1, 2
+
+
+class OracleProblem:
+    """CPU restatement of Optimizer2 + LinearSystemSolver on a kalibr_b200.problem.Problem."""
+
+    def __init__(self, problem, solver_kind: int = BLOCK_CHOLESKY, n_threads: int = 4):
+        self._problem = problem  # keep arrays alive
+        self._desc = problem.desc()
+        self.n_threads = n_threads
+        self._h = lib().ko_create(C.byref(self._desc), solver_kind)
+        if not self._h:
+            raise RuntimeError("ko_create failed: " + lib().ko_last_error().decode())
+        self.jrows = lib().ko_jrows(self._h)
+        self.jcols = lib().ko_jcols(self._h)
+        self.n_dv = lib().ko_num_design_variables(self._h)
+
+    def close(self):
+        if self._h:
+            lib().ko_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def dv_layout(self):
+        col = np.zeros(self.n_dv, np.int32)
+        dims = np.zeros(self.n_dv, np.int32)
+        lib().ko_get_dv_layout(self._h, _p(col), _p(dims))
+        return col, dims
+
+    def evaluate_error(self) -> float:
+        return lib().ko_evaluate_error(self._h, self.n_threads)
+
+    def error_vector(self) -> np.ndarray:
+        e = np.zeros(self.jrows)
+        lib().ko_get_error_vector(self._h, _p(e))
+        return e
+
+    def build_system(self):
+        lib().ko_build_system(self._h, self.n_threads)
+
+    def set_constant_conditioner(self, lam: float):
+        lib().ko_set_constant_conditioner(self._h, lam)
+
+    def solve_system(self):
+        dx = np.zeros(self.jcols)
+        ok = lib().ko_solve_system(self._h, _p(dx))
+        return dx, bool(ok)
+
+    def rhs(self) -> np.ndarray:
+        r = np.zeros(self.jcols)
+        lib().ko_get_rhs(self._h, _p(r))
+        return r
+
+    def apply_state_update(self) -> float:
+        return lib().ko_apply_state_update(self._h)
+
+    def revert_last_state_update(self):
+        lib().ko_revert_last_state_update(self._h)
+
+    def optimize(self, options=None):
+        from kalibr_b200.problem import KbOptimizerOptions, KbSolution
+
+        options = options or KbOptimizerOptions.kalibr2_default()
+        sol = KbSolution()
+        lib().ko_optimize(self._h, C.byref(options), self.n_threads, C.byref(sol))
+        n = lib().ko_get_trace(self._h, None, 0)
+        tr = np.zeros((n, 3))
+        if n:
+            lib().ko_get_trace(self._h, _p(tr), n)
+        return sol, tr
+
+    def jacobian_ccs(self):
+        nnz = lib().ko_get_jacobian_ccs(self._h, self.n_threads, None, None, None)
+        col_ptr = np.zeros(self.jrows + 1, np.int64)
+        row_idx = np.zeros(nnz, np.int32)
+        vals = np.zeros(nnz)
+        lib().ko_get_jacobian_ccs(self._h, self.n_threads, _p(col_ptr), _p(row_idx), _p(vals))
+        return col_ptr, row_idx, vals
+
+    def hessian_blocks(self):
+        nb = C.c_int64()
+        nv = C.c_int64()
+        lib().ko_get_hessian_blocks(self._h, C.byref(nb), C.byref(nv), None, None, None, None)
+        col_ptr = np.zeros(self.n_dv + 1, np.int64)
+        block_row = np.zeros(nb.value, np.int32)
+        value_ptr = np.zeros(nb.value, np.int64)
+        values = np.zeros(nv.value)
+        lib().ko_get_hessian_blocks(self._h, C.byref(nb), C.byref(nv), _p(col_ptr), _p(block_row), _p(value_ptr), _p(values))
+        return col_ptr, block_row, value_ptr, values
+
+    def camera_params(self) -> np.ndarray:
+        out = np.zeros((self._problem.n_cams, 10))
+        lib().ko_get_camera_params(self._h, _p(out))
+        return out
+
+    def baselines(self) -> np.ndarray:
+        out = np.zeros((max(self._problem.n_cams - 1, 0), 7))
+        if out.size:
+            lib().ko_get_baselines(self._h, _p(out))
+        return out
+
+    def set_poses(self) -> np.ndarray:
+        out = np.zeros((self._problem.n_sets, 7))
+        lib().ko_get_set_poses(self._h, _p(out))
+        return out
+
+    def time_iteration(self, lam: float = 10.0):
+        t = np.zeros(3)
+        ok = lib().ko_time_iteration(self._h, self.n_threads, lam, _p(t))
+        return t, bool(ok)
+
+
+def camera_project(model: int, params, ph):
+    params = np.ascontiguousarray(np.pad(np.asarray(params, np.float64), (0, 10 - len(params))))
+    ph = np.ascontiguousarray(ph, np.float64)
+    y = np.zeros(2)
+    Jp = np.zeros((2, 4))
+    Ji = np.zeros((2, 6))
+    Jd = np.zeros((2, 4))
+    ok = lib().ko_camera_project(model, _p(params), _p(ph), _p(y), _p(Jp), _p(Ji), _p(Jd))
+    return y, Jp, Ji, Jd, ok
+
+
+def quat2r(q):
+    q = np.ascontiguousarray(q, np.float64)
+    R = np.zeros((3, 3))
+    lib().ko_quat2r(_p(q), _p(R))
+    return R
+
+
+def update_quat(q, dq):
+    q = np.ascontiguousarray(q, np.float64)
+    dq = np.ascontiguousarray(dq, np.float64)
+    out = np.zeros(4)
+    lib().ko_update_quat(_p(q), _p(dq), _p(out))
+    return out
+
+
+def inverse4(M):
+    M = np.ascontiguousarray(M, np.float64)
+    out = np.zeros((4, 4))
+    lib().ko_inverse4(_p(M), _p(out))
+    return out
