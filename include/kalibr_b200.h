@@ -108,6 +108,7 @@ KB_API kb_status kb_nccl_unique_id(char out[128]);     /* rank 0 calls, caller b
 /* sizes: ≙ LinearSystemSolver::JRows/JCols (BE/include/aslam/backend/LinearSystemSolver.hpp:62-66) */
 KB_API int64_t kb_jrows(const kb_handle* h);  /* 2 * GLOBAL number of terms */
 KB_API int64_t kb_jcols(const kb_handle* h);  /* sum of active DV dimensions */
+KB_API int64_t kb_local_jrows(const kb_handle* h); /* 2 * number of terms owned by this rank (== kb_jrows when n_ranks == 1) */
 KB_API int32_t kb_num_design_variables(const kb_handle* h); /* active DVs incl. 0-dim ones */
 /* ≙ DesignVariable::blockIndex/columnBase/minimalDimensions (BE/include/aslam/backend/DesignVariable.hpp:18-145) */
 KB_API kb_status kb_get_dv_layout(const kb_handle* h, int32_t* column_base /*[n_dv]*/, int32_t* dims /*[n_dv]*/);
@@ -148,15 +149,23 @@ typedef struct { /* ≙ SolutionReturnValue, BE/include/aslam/backend/backend.hp
 } kb_solution;
 KB_API void kb_default_optimizer_options(kb_optimizer_options* o);
 KB_API kb_status kb_optimize(kb_handle* h, const kb_optimizer_options* o, kb_solution* out);
+/* per-iteration trace of the last kb_optimize: triples (J, deltaX, lambda); returns the number of triples */
+KB_API int32_t kb_get_trace(const kb_handle* h, double* out, int32_t max_triples);
+/* Solver semantic: 0 = BlockCholesky (default; un-augments with lambda instead of lambda^2),
+ * 1 = SparseCholesky (damping appended as columns, no residual: BE/src/SparseCholeskyLinearSystemSolver.cpp:48-66) */
+KB_API kb_status kb_set_solver_semantic(kb_handle* h, int32_t semantic);
 
 /* ---- read-back (parity / results) ----------------------------------------- */
 KB_API kb_status kb_get_error_vector(kb_handle* h, double* e /*[2*local terms]*/);      /* ≙ LinearSystemSolver::e() : -sqrtInvR^T e */
 KB_API kb_status kb_get_rhs(kb_handle* h, double* rhs /*[jcols]*/);                     /* ≙ LinearSystemSolver::rhs() */
-/* Materialised Jacobians of every local term at the current state: J[term][2][width] row-major, width =
- * kb_jacobian_width(); column layout [pose q(3) t(3) | baselines 0..C-2 (q,t) | proj(6, padded) | dist(4, padded)];
- * ≙ ErrorTerm::evaluateJacobians → JacobianContainer (CVE .../ReprojectionError.hpp:63-77). */
-KB_API int32_t kb_jacobian_width(const kb_handle* h);
-KB_API kb_status kb_get_jacobians(kb_handle* h, double* J);
+/* Materialising linearise (K1): e and J of every local term at the current state, J^T in the compressed-column
+ * layout CompressedColumnJacobianTransposeBuilder holds (BE/include/aslam/backend/implementation/
+ * CompressedColumnJacobianTransposeBuilder.hpp:59-100; CompressedColumnMatrix.hpp:236-304): two columns per term, rows =
+ * design-variable columns ordered by block index.  kb_linearise runs the kernel (values stay on the device);
+ * kb_get_jacobian_ccs copies them out.  Call with NULL arrays to obtain nnz (also the return of kb_jacobian_nnz). */
+KB_API kb_status kb_linearise(kb_handle* h);
+KB_API int64_t kb_jacobian_nnz(const kb_handle* h);
+KB_API kb_status kb_get_jacobian_ccs(kb_handle* h, int64_t* col_ptr /*[2*local terms+1]*/, int32_t* row_idx /*[nnz]*/, double* values /*[nnz]*/);
 /* Upper-triangular block pattern of H exactly as SparseBlockMatrix holds it after buildSystem+solveSystem
  * (sparse_block_matrix.hpp:121-143; JacobianContainer.cpp:112-126): for block column c, block_row[col_ptr[c]..col_ptr[c+1])
  * ascending.  values are the blocks column-major one after another (value_ptr[k] offsets).  Call with NULL arrays to query counts. */
@@ -168,6 +177,8 @@ KB_API kb_status kb_get_baselines(kb_handle* h, double* baselines /*[n_cams-1][7
 KB_API kb_status kb_get_set_poses(kb_handle* h, double* set_poses /*[n_sets][7]; other ranks' sets untouched*/);
 /* replace the measurements (same structure) — used by the end-to-end bench leg to time host→device per step */
 KB_API kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v);
+/* terms whose projection bailed out before writing y_hat (zero-weighted here) since creation */
+KB_API int64_t kb_num_invalid_terms(kb_handle* h);
 /* reset state to the initial guess given at kb_create */
 KB_API kb_status kb_reset_state(kb_handle* h);
 

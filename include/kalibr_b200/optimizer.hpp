@@ -1,0 +1,273 @@
+// Host-side C++ mirror of the reference's optimiser plugin surface for the batch-calibration hot path,
+// written over the C ABI (kalibr_b200.h).  Same class / method names, argument meaning and error behaviour as
+//   aslam::backend::LinearSystemSolver              BE/include/aslam/backend/LinearSystemSolver.hpp:16-109
+//   aslam::backend::LevenbergMarquardtTrustRegionPolicy  BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:37-113
+//   aslam::backend::TrustRegionPolicy               BE/src/TrustRegionPolicy.cpp:28-57
+//   aslam::backend::Optimizer2 / Optimizer2Options / SolutionReturnValue
+//                                                   BE/src/Optimizer2.cpp:183-318, Optimizer2Options.hpp:9-41, backend.hpp:14-27
+// (BE = aslam_optimizer/aslam_backend).  Eigen::VectorXd is replaced by std::vector<double>; design variables and
+// error terms live on the device behind the handle, so initMatrixStructure takes the flattened problem.
+// INTEGRATION.md shows the adapter a Kalibr2 maintainer would add on the reference side.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../kalibr_b200.h"
+
+namespace kalibr_b200 {
+namespace backend {
+
+struct SolutionReturnValue {  // backend.hpp:14-27
+  double JStart = 0, JFinal = 0;
+  int iterations = 0, failedIterations = 0;
+  double dXFinal = 0, dJFinal = 0;
+  bool linearSolverFailure = false;
+};
+
+// The solver interface the optimiser drives.  evaluateError is virtual here (SURVEY.md §8b option (i)).
+class LinearSystemSolver {
+ public:
+  virtual ~LinearSystemSolver() {}
+  virtual double evaluateError(size_t nThreads, bool useMEstimator) = 0;
+  virtual void buildSystem(size_t nThreads, bool useMEstimator) = 0;
+  virtual bool solveSystem(std::vector<double>& outDx) = 0;
+  virtual void setConstantConditioner(double diag) = 0;
+  virtual const std::vector<double>& rhs() = 0;
+  virtual const std::vector<double>& e() = 0;
+  virtual size_t JRows() const = 0;
+  virtual size_t JCols() const = 0;
+  virtual std::string name() const = 0;
+  // dx^T (lambda dx + rhs) for the last solution; the default follows getLmRho literally on the host
+  virtual double lmRhoDenominator(double lambda, const std::vector<double>& dx) {
+    const std::vector<double>& r = rhs();
+    double d2 = 0;
+    for (size_t i = 0; i < dx.size(); ++i) d2 += dx[i] * (lambda * dx[i] + r[i]);
+    return d2;
+  }
+  // Optimizer2::applyStateUpdate / revertLastStateUpdate act on design variables the solver's device owns
+  virtual double applyStateUpdate(const std::vector<double>& dx) = 0;
+  virtual void revertLastStateUpdate() = 0;
+};
+
+// B200 replacement of BlockCholeskyLinearSystemSolver (BE/src/BlockCholeskyLinearSystemSolver.cpp:34-106):
+// fused linearise+assemble, batched Schur elimination of the per-set poses, dense Cholesky of the camera system.
+class B200SchurLinearSystemSolver : public LinearSystemSolver {
+ public:
+  explicit B200SchurLinearSystemSolver(kb_handle* h, bool keepDxOnDevice = true) : _h(h), _deviceDx(keepDxOnDevice) {}
+  std::string name() const override { return "b200_schur"; }
+  size_t JRows() const override { return (size_t)kb_jrows(_h); }
+  size_t JCols() const override { return (size_t)kb_jcols(_h); }
+  double evaluateError(size_t /*nThreads*/, bool useMEstimator) override {
+    double J = 0;
+    check(kb_evaluate_error(_h, useMEstimator ? 1 : 0, &J));
+    return J;
+  }
+  void buildSystem(size_t /*nThreads*/, bool useMEstimator) override { check(kb_build_system(_h, useMEstimator ? 1 : 0)); }
+  void setConstantConditioner(double diag) override { check(kb_set_constant_conditioner(_h, diag)); }
+  bool solveSystem(std::vector<double>& outDx) override {
+    int32_t posDef = 0;
+    if (_deviceDx) {
+      check(kb_solve_system(_h, nullptr, 0, &posDef));
+    } else {
+      outDx.resize(JCols());
+      check(kb_solve_system(_h, outDx.data(), 1, &posDef));
+    }
+    return posDef != 0;
+  }
+  const std::vector<double>& rhs() override {
+    _rhs.resize(JCols());
+    check(kb_get_rhs(_h, _rhs.data()));
+    return _rhs;
+  }
+  const std::vector<double>& e() override {
+    _e.resize((size_t)kb_local_jrows(_h));
+    check(kb_get_error_vector(_h, _e.data()));
+    return _e;
+  }
+  double lmRhoDenominator(double lambda, const std::vector<double>& dx) override {
+    if (!_deviceDx) return LinearSystemSolver::lmRhoDenominator(lambda, dx);
+    double d = 0;
+    check(kb_lm_rho_denominator(_h, lambda, &d));
+    return d;
+  }
+  double applyStateUpdate(const std::vector<double>& /*dx: the device already holds the last solution*/) override {
+    double m = 0;
+    check(kb_apply_state_update(_h, &m));
+    return m;
+  }
+  void revertLastStateUpdate() override { check(kb_revert_last_state_update(_h)); }
+
+ private:
+  void check(kb_status s) {
+    if (s != KB_OK) throw std::runtime_error(std::string("kalibr_b200: ") + kb_last_error(_h));
+  }
+  kb_handle* _h;
+  bool _deviceDx;
+  std::vector<double> _rhs, _e;
+};
+
+// TrustRegionPolicy.cpp:28-57 + LevenbergMarquardtTrustRegionPolicy.cpp:37-113
+class LevenbergMarquardtTrustRegionPolicy {
+ public:
+  explicit LevenbergMarquardtTrustRegionPolicy(double lambdaInit = 1e-3) : _lambdaInit(lambdaInit) {}
+  std::string name() const { return "levenberg_marquardt"; }
+  bool requiresAugmentedDiagonal() const { return true; }
+  bool revertOnFailure() const { return true; }
+  void setSolver(std::shared_ptr<LinearSystemSolver> s) { _solver = s; }
+  void optimizationStarting(double J) {
+    _J = _p_J = _last_successful_J = J;
+    _isFirstIteration = true;
+    _lambda = _lambdaInit;
+    _gamma = _gammaInit;
+    _beta = _betaInit;
+    _p = _pInit;
+    _mu = _muInit;
+  }
+  bool solveSystem(double J, bool previousIterationFailed, int nThreads, std::vector<double>& outDx) {
+    if (previousIterationFailed) {
+      _J = J;
+    } else {
+      _p_J = _last_successful_J;
+      _last_successful_J = J;
+      _J = J;
+    }
+    if (_isFirstIteration) {
+      _solver->buildSystem(nThreads, true);
+    } else {
+      const double rho = getLmRho();
+      if (previousIterationFailed) {
+        _mu *= 2;
+        _lambda *= _mu;
+      } else if (rho <= 0) {
+        _mu *= 10;
+        _lambda *= _mu;
+      } else {
+        _solver->buildSystem(nThreads, true);
+        if (_lambda > 1e-16) {
+          const double u1 = 1 / _gamma;
+          const double u2 = 1 - (_beta - 1) * std::pow((2 * rho - 1), _p);
+          _lambda *= (u1 > u2) ? u1 : u2;
+          _mu = _beta;
+        } else {
+          _lambda = 1e-15;
+        }
+      }
+    }
+    _solver->setConstantConditioner(_lambda);
+    const bool success = _solver->solveSystem(_dx);
+    outDx = _dx;
+    _isFirstIteration = false;
+    return success;
+  }
+  double get_dJ() const { return _p_J - _J; }
+  double getLmRho() { return get_dJ() / _solver->lmRhoDenominator(_lambda, _dx); }
+  double lambda() const { return _lambda; }
+  double mu() const { return _mu; }
+
+ private:
+  double _lambdaInit, _gammaInit = 3, _betaInit = 2, _muInit = 2;
+  int _pInit = 3;
+  double _lambda = 0, _gamma = 0, _beta = 0, _mu = 0;
+  int _p = 0;
+  double _J = 0, _p_J = 0, _last_successful_J = 0;
+  bool _isFirstIteration = true;
+  std::shared_ptr<LinearSystemSolver> _solver;
+  std::vector<double> _dx;
+};
+
+struct Optimizer2Options {  // Optimizer2Options.hpp:9-41 with kalibr2's values (CalibrationTools.hpp:57-66) as defaults
+  double convergenceDeltaJ = 1.0;
+  double convergenceDeltaX = 1e-3;
+  int maxIterations = 200;
+  int nThreads = 4;
+  bool verbose = false;
+  std::shared_ptr<LinearSystemSolver> linearSystemSolver;
+  std::shared_ptr<LevenbergMarquardtTrustRegionPolicy> trustRegionPolicy;
+};
+
+class Optimizer2 {
+ public:
+  explicit Optimizer2(const Optimizer2Options& options) : _options(options) {}
+  Optimizer2Options& options() { return _options; }
+  double J() const { return _J; }
+  const std::vector<double>& dx() const { return _dx; }
+  const std::vector<double>& trace() const { return _trace; }  // (J, deltaX, lambda) per iteration
+
+  // Optimizer2.cpp:183-273
+  SolutionReturnValue optimize() {
+    if (!_options.linearSystemSolver) throw std::runtime_error("kalibr_b200::Optimizer2: a B200 linear system solver must be set (no CPU fallback)");
+    _solver = _options.linearSystemSolver;
+    _trustRegionPolicy = _options.trustRegionPolicy ? _options.trustRegionPolicy : std::make_shared<LevenbergMarquardtTrustRegionPolicy>();
+    SolutionReturnValue srv;
+    _trace.clear();
+    _p_J = 0.0;
+    evaluateError(true);
+    _p_J = _J;
+    srv.JStart = _p_J;
+    if (_options.verbose) std::printf("[0.0]: J: %.10g\n", _J);
+    double deltaX = _options.convergenceDeltaX + 1.0;
+    double deltaJ = _options.convergenceDeltaJ + 1.0;
+    bool previousIterationFailed = false;
+    bool linearSolverFailure = false;
+    _trustRegionPolicy->setSolver(_solver);
+    _trustRegionPolicy->optimizationStarting(_J);
+    while (srv.iterations < _options.maxIterations && srv.failedIterations < _options.maxIterations &&
+           ((deltaX > _options.convergenceDeltaX && std::fabs(deltaJ) > _options.convergenceDeltaJ) || linearSolverFailure)) {
+      const bool solutionSuccess = _trustRegionPolicy->solveSystem(_J, previousIterationFailed, _options.nThreads, _dx);
+      if (!solutionSuccess) {
+        if (_options.verbose) std::printf("[WARNING] System solution failed\n");
+        previousIterationFailed = true;
+        linearSolverFailure = true;
+        srv.failedIterations++;
+      } else {
+        deltaX = _solver->applyStateUpdate(_dx);
+        evaluateError(true);
+        deltaJ = _p_J - _J;
+        if (_trustRegionPolicy->revertOnFailure()) {
+          if (deltaJ < 0.0) {
+            if (_options.verbose) std::printf("Last step was a regression. Reverting\n");
+            _solver->revertLastStateUpdate();
+            srv.failedIterations++;
+            previousIterationFailed = true;
+          } else {
+            _p_J = _J;
+            previousIterationFailed = false;
+          }
+        } else {
+          _p_J = _J;
+        }
+        srv.iterations++;
+        _trace.push_back(_J);
+        _trace.push_back(deltaX);
+        _trace.push_back(_trustRegionPolicy->lambda());
+        if (_options.verbose)
+          std::printf("[%d]: J: %.10g, dJ: %.6g, deltaX: %.6g, LM - lambda:%.6g mu:%.6g\n", srv.iterations, _J, deltaJ, deltaX,
+                      _trustRegionPolicy->lambda(), _trustRegionPolicy->mu());
+      }
+    }
+    srv.JFinal = _p_J;
+    srv.dXFinal = deltaX;
+    srv.dJFinal = deltaJ;
+    srv.linearSolverFailure = linearSolverFailure;
+    return srv;
+  }
+
+  double evaluateError(bool useMEstimator) {  // Optimizer2.cpp:327-332
+    _J = _solver->evaluateError(_options.nThreads, useMEstimator);
+    return _J;
+  }
+
+ private:
+  Optimizer2Options _options;
+  std::shared_ptr<LinearSystemSolver> _solver;
+  std::shared_ptr<LevenbergMarquardtTrustRegionPolicy> _trustRegionPolicy;
+  std::vector<double> _dx, _trace;
+  double _J = 0, _p_J = 0;
+};
+
+}  // namespace backend
+}  // namespace kalibr_b200

@@ -1,0 +1,275 @@
+"""ctypes binding of the C ABI (include/kalibr_b200.h) exported by kalibr_b200/libkalibr_b200.so.
+
+The library is the product: if it is missing this module raises — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB_PATH
+from .problem import KbOptimizerOptions, KbProblemDesc, KbSolution, Problem
+
+KB_OK = 0
+KB_NUM_STAGES = 8
+STAGE_NAMES = ["evaluate", "linearise_assemble", "expand", "schur", "reduced_solve", "backsub", "update", "linearise_materialise"]
+
+# every symbol include/kalibr_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "kb_create", "kb_destroy", "kb_last_error", "kb_nccl_unique_id", "kb_jrows", "kb_jcols", "kb_local_jrows",
+    "kb_num_design_variables", "kb_get_dv_layout", "kb_evaluate_error", "kb_build_system", "kb_set_constant_conditioner",
+    "kb_solve_system", "kb_lm_rho_denominator", "kb_apply_state_update", "kb_revert_last_state_update",
+    "kb_default_optimizer_options", "kb_optimize", "kb_get_trace", "kb_set_solver_semantic", "kb_get_error_vector", "kb_get_rhs",
+    "kb_linearise", "kb_jacobian_nnz", "kb_get_jacobian_ccs", "kb_get_hessian_blocks", "kb_get_camera_params", "kb_get_baselines",
+    "kb_get_set_poses", "kb_set_observations", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
+    "kb_enable_stage_timing", "kb_cuda_stream",
+]
+
+_lib = None
+
+
+class KalibrB200Error(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA extension; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KalibrB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m kalibr_b200.build` (nvcc, sm_100a). "
+            "The B200 hot path has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.kb_create.argtypes = [C.POINTER(KbProblemDesc), C.POINTER(vp)]
+    L.kb_create.restype = C.c_int32
+    L.kb_destroy.argtypes = [vp]
+    L.kb_destroy.restype = None
+    L.kb_last_error.argtypes = [vp]
+    L.kb_last_error.restype = C.c_char_p
+    L.kb_nccl_unique_id.argtypes = [C.c_char_p]
+    L.kb_nccl_unique_id.restype = C.c_int32
+    for name in ("kb_jrows", "kb_jcols", "kb_local_jrows", "kb_jacobian_nnz", "kb_kernel_launches", "kb_num_invalid_terms"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = C.c_int64
+    L.kb_num_design_variables.argtypes = [vp]
+    L.kb_num_design_variables.restype = C.c_int32
+    L.kb_get_dv_layout.argtypes = [vp, vp, vp]
+    L.kb_evaluate_error.argtypes = [vp, C.c_int32, C.POINTER(C.c_double)]
+    L.kb_build_system.argtypes = [vp, C.c_int32]
+    L.kb_set_constant_conditioner.argtypes = [vp, C.c_double]
+    L.kb_solve_system.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int32)]
+    L.kb_lm_rho_denominator.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
+    L.kb_apply_state_update.argtypes = [vp, C.POINTER(C.c_double)]
+    L.kb_revert_last_state_update.argtypes = [vp]
+    L.kb_default_optimizer_options.argtypes = [C.POINTER(KbOptimizerOptions)]
+    L.kb_default_optimizer_options.restype = None
+    L.kb_optimize.argtypes = [vp, C.POINTER(KbOptimizerOptions), C.POINTER(KbSolution)]
+    L.kb_get_trace.argtypes = [vp, vp, C.c_int32]
+    L.kb_get_trace.restype = C.c_int32
+    L.kb_set_solver_semantic.argtypes = [vp, C.c_int32]
+    L.kb_get_error_vector.argtypes = [vp, vp]
+    L.kb_get_rhs.argtypes = [vp, vp]
+    L.kb_linearise.argtypes = [vp]
+    L.kb_get_jacobian_ccs.argtypes = [vp, vp, vp, vp]
+    L.kb_get_hessian_blocks.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, vp, vp, vp]
+    L.kb_get_camera_params.argtypes = [vp, vp]
+    L.kb_get_baselines.argtypes = [vp, vp]
+    L.kb_get_set_poses.argtypes = [vp, vp]
+    L.kb_set_observations.argtypes = [vp, vp, vp]
+    L.kb_reset_state.argtypes = [vp]
+    L.kb_get_stage_ms.argtypes = [vp, vp]
+    L.kb_enable_stage_timing.argtypes = [vp, C.c_int32]
+    L.kb_cuda_stream.argtypes = [vp]
+    L.kb_cuda_stream.restype = vp
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int:  # default: status-returning entry points
+            fn.restype = C.c_int32
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    st = load_library().kb_nccl_unique_id(buf)
+    if st != KB_OK:
+        raise KalibrB200Error("kb_nccl_unique_id: " + load_library().kb_last_error(None).decode())
+    return buf.raw
+
+
+class B200SchurLinearSystemSolver:
+    """Python face of the reference-facing solver plugin (≙ aslam::backend::LinearSystemSolver,
+    aslam_optimizer/aslam_backend/include/aslam/backend/LinearSystemSolver.hpp:16-109) over the C ABI.
+
+    Method names follow the reference (camelCase in C++, snake_case here); all compute runs in the CUDA library.
+    """
+
+    def __init__(self, problem: Problem, n_ranks: int = 1, rank: int = 0, nccl_id: bytes | None = None, device: int = 0):
+        self._L = load_library()
+        self.problem = problem
+        self._desc = problem.desc(n_ranks=n_ranks, rank=rank, nccl_id=nccl_id, device=device)
+        h = C.c_void_p()
+        st = self._L.kb_create(C.byref(self._desc), C.byref(h))
+        if st != KB_OK:
+            raise KalibrB200Error(f"kb_create failed ({st}): " + self._L.kb_last_error(None).decode())
+        self._h = h
+        self.jrows = self._L.kb_jrows(h)
+        self.local_jrows = self._L.kb_local_jrows(h)
+        self.jcols = self._L.kb_jcols(h)
+        self.n_dv = self._L.kb_num_design_variables(h)
+
+    def name(self) -> str:
+        return "b200_schur"
+
+    # -- life cycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int, what: str):
+        if st != KB_OK:
+            raise KalibrB200Error(f"{what} failed ({st}): " + self._L.kb_last_error(self._h).decode())
+
+    # -- LinearSystemSolver surface
+    def dv_layout(self):
+        col = np.zeros(self.n_dv, np.int32)
+        dims = np.zeros(self.n_dv, np.int32)
+        self._check(self._L.kb_get_dv_layout(self._h, _p(col), _p(dims)), "kb_get_dv_layout")
+        return col, dims
+
+    def evaluate_error(self, use_m_estimator: bool = True) -> float:
+        out = C.c_double()
+        self._check(self._L.kb_evaluate_error(self._h, 0, C.byref(out)), "kb_evaluate_error")
+        return out.value
+
+    def build_system(self, use_m_estimator: bool = True):
+        self._check(self._L.kb_build_system(self._h, 0), "kb_build_system")
+
+    def set_constant_conditioner(self, lam: float):
+        self._check(self._L.kb_set_constant_conditioner(self._h, lam), "kb_set_constant_conditioner")
+
+    def solve_system(self, fetch_dx: bool = True, gather: bool = True):
+        pd = C.c_int32()
+        dx = np.zeros(self.jcols) if fetch_dx else None
+        self._check(self._L.kb_solve_system(self._h, _p(dx), 1 if gather else 0, C.byref(pd)), "kb_solve_system")
+        return dx, bool(pd.value)
+
+    def lm_rho_denominator(self, lam: float) -> float:
+        out = C.c_double()
+        self._check(self._L.kb_lm_rho_denominator(self._h, lam, C.byref(out)), "kb_lm_rho_denominator")
+        return out.value
+
+    def apply_state_update(self) -> float:
+        out = C.c_double()
+        self._check(self._L.kb_apply_state_update(self._h, C.byref(out)), "kb_apply_state_update")
+        return out.value
+
+    def revert_last_state_update(self):
+        self._check(self._L.kb_revert_last_state_update(self._h), "kb_revert_last_state_update")
+
+    def set_solver_semantic(self, semantic: int):
+        self._check(self._L.kb_set_solver_semantic(self._h, semantic), "kb_set_solver_semantic")
+
+    def optimize(self, options: KbOptimizerOptions | None = None):
+        """One Optimizer2::optimize() with the LM policy, state resident on the device."""
+        options = options or KbOptimizerOptions.kalibr2_default()
+        sol = KbSolution()
+        self._check(self._L.kb_optimize(self._h, C.byref(options), C.byref(sol)), "kb_optimize")
+        n = self._L.kb_get_trace(self._h, None, 0)
+        tr = np.zeros((n, 3))
+        if n:
+            self._L.kb_get_trace(self._h, _p(tr), n)
+        return sol, tr
+
+    # -- read back
+    def error_vector(self) -> np.ndarray:
+        e = np.zeros(self.local_jrows)
+        self._check(self._L.kb_get_error_vector(self._h, _p(e)), "kb_get_error_vector")
+        return e
+
+    def rhs(self) -> np.ndarray:
+        r = np.zeros(self.jcols)
+        self._check(self._L.kb_get_rhs(self._h, _p(r)), "kb_get_rhs")
+        return r
+
+    def linearise(self):
+        self._check(self._L.kb_linearise(self._h), "kb_linearise")
+
+    def jacobian_ccs(self):
+        self.linearise()
+        nnz = self._L.kb_jacobian_nnz(self._h)
+        col_ptr = np.zeros(self.local_jrows + 1, np.int64)
+        row_idx = np.zeros(nnz, np.int32)
+        vals = np.zeros(nnz)
+        self._check(self._L.kb_get_jacobian_ccs(self._h, _p(col_ptr), _p(row_idx), _p(vals)), "kb_get_jacobian_ccs")
+        return col_ptr, row_idx, vals
+
+    def hessian_blocks(self):
+        nb, nv = C.c_int64(), C.c_int64()
+        self._check(self._L.kb_get_hessian_blocks(self._h, C.byref(nb), C.byref(nv), None, None, None, None), "kb_get_hessian_blocks")
+        col_ptr = np.zeros(self.n_dv + 1, np.int64)
+        block_row = np.zeros(nb.value, np.int32)
+        value_ptr = np.zeros(nb.value, np.int64)
+        values = np.zeros(nv.value)
+        self._check(
+            self._L.kb_get_hessian_blocks(self._h, C.byref(nb), C.byref(nv), _p(col_ptr), _p(block_row), _p(value_ptr), _p(values)),
+            "kb_get_hessian_blocks",
+        )
+        return col_ptr, block_row, value_ptr, values
+
+    def camera_params(self) -> np.ndarray:
+        out = np.zeros((self.problem.n_cams, 10))
+        self._check(self._L.kb_get_camera_params(self._h, _p(out)), "kb_get_camera_params")
+        return out
+
+    def baselines(self) -> np.ndarray:
+        out = np.zeros((max(self.problem.n_cams - 1, 0), 7))
+        if out.size:
+            self._check(self._L.kb_get_baselines(self._h, _p(out)), "kb_get_baselines")
+        return out
+
+    def set_poses(self) -> np.ndarray:
+        out = np.zeros((self.problem.n_sets, 7))
+        self._check(self._L.kb_get_set_poses(self._h, _p(out)), "kb_get_set_poses")
+        return out
+
+    def set_observations(self, y_u: np.ndarray, y_v: np.ndarray):
+        self._check(self._L.kb_set_observations(self._h, _p(y_u), _p(y_v)), "kb_set_observations")
+
+    def reset_state(self):
+        self._check(self._L.kb_reset_state(self._h), "kb_reset_state")
+
+    def num_invalid_terms(self) -> int:
+        return int(self._L.kb_num_invalid_terms(self._h))
+
+    # -- instrumentation
+    def kernel_launches(self) -> int:
+        return int(self._L.kb_kernel_launches(self._h))
+
+    def enable_stage_timing(self, on: bool = True):
+        self._L.kb_enable_stage_timing(self._h, 1 if on else 0)
+
+    def stage_ms(self) -> dict:
+        ms = np.zeros(KB_NUM_STAGES)
+        self._L.kb_get_stage_ms(self._h, _p(ms))
+        return dict(zip(STAGE_NAMES, ms.tolist()))
+
+    def cuda_stream(self) -> int:
+        return int(self._L.kb_cuda_stream(self._h) or 0)

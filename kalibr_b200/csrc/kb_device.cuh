@@ -1,0 +1,95 @@
+// Device-side problem view shared by the kernels (kb_kernels.cu) and the host layer (kb_host.cpp).
+// Data layout in HBM: structure-of-arrays observations in the reference's term order,
+// views (one camera image of one synced set) as contiguous term ranges, per-view 16x16 Gram blocks, per-set
+// Schur blocks, one dense reduced camera system.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace kb {
+
+enum : int { PINHOLE_RADTAN = 0, PINHOLE_EQUI = 1, OMNI_RADTAN = 2, EUCM_NONE = 3, DS_NONE = 4, NUM_MODELS = 5 };  // = kb_camera_model
+__host__ __device__ constexpr int model_P(int m) { return m == OMNI_RADTAN ? 5 : (m == EUCM_NONE || m == DS_NONE) ? 6 : 4; }
+__host__ __device__ constexpr int model_D(int m) { return (m == EUCM_NONE || m == DS_NONE) ? 0 : 4; }
+
+constexpr int MAX_CAMS = 32;
+constexpr int CAM_PARAM_STRIDE = 10;
+constexpr int POSE_STRIDE = 7;
+constexpr int GRAM_DIM = 16;                       // local columns: xi(6) | proj(P) | dist(D) | pad | e (col 15)
+constexpr int GRAM_SIZE = GRAM_DIM * GRAM_DIM;     // row-major; only the tiles (0,0), (0,1), (1,1) are written
+constexpr int E_COL = 15;
+
+struct DevProblem {
+  // ---- structure (immutable after kb_create) ----
+  int n_cams;
+  int n_sets;        // local synced sets
+  int n_views;       // local views
+  int n_target;
+  long long n_terms; // local terms
+  int n_c;           // reduced camera system dimension (global)
+  int n_aug;         // n_c + 1 (rhs folded in as last row/col)
+  int cam_model[MAX_CAMS];
+  int cam_P[MAX_CAMS];
+  int cam_D[MAX_CAMS];
+  int intr_off[MAX_CAMS];  // offset of [proj|dist] of camera k in the reduced system
+  int base_off[MAX_CAMS];  // offset of baseline j (q then t) in the reduced system
+  const double* y_u;
+  const double* y_v;
+  const uint16_t* corner;
+  const double* target;    // [n_target][3]
+  const int* view_set;     // [n_views] local set index
+  const int* view_cam;     // [n_views]
+  const int* view_begin;   // [n_views+1] local term offsets
+  const int* set_view;     // [n_sets][n_cams] view index or -1
+  const int* lin_off;      // [n_cams][LIN_OFF_STRIDE] column offsets of the CCS J^T layout per camera
+  const long long* view_jbase;  // [n_views] offset of the view's first value in the CCS J^T value array
+  // ---- state ----
+  double* cam_params;   // [n_cams][10]
+  double* baselines;    // [n_cams-1][7]
+  double* set_poses;    // [n_sets][7]
+  // ---- per-linearisation constants (prep kernel) ----
+  double* camT;         // [n_cams][12]  R (row-major 9), t (3): T_cam(k)_cam(0)
+  double* camPi;        // [n_cams][36]  product of boxTimes(B_{k-1}) ... boxTimes(B_0)
+  double* camA;         // [n_cams][n_cams][36]  A_{j,k} at [k][j]: d(xi_k)/d(baseline j) = X_{k,j} [M_q(t_j) | M_t]
+  // ---- outputs ----
+  double* e;            // [2*n_terms]   -(y - y_hat), the reference's _e
+  double* view_cost;    // [n_views]
+  double* G;            // [n_views][256]
+  double* sumG;         // [n_cams][256]
+  double* V;            // [n_sets][36]
+  double* bv;           // [n_sets][6]
+  double* W;            // [n_sets][n_c][6]
+  double* Lv;           // [n_sets][36]   Cholesky factor of V + damping (row-major lower)
+  double* yv;           // [n_sets][6]    L^-1 b_v
+  double* U;            // [n_aug*n_aug]  camera block with rhs b_c in the last row/col (this rank's partial)
+  double* Sred;         // [n_aug*n_aug]  reduced system (after all-reduce), then its Cholesky factor
+  double* dxc;          // [n_c]
+  double* dx;           // [jcols] in design-variable order (poses of other ranks stay 0)
+  unsigned int* n_invalid;  // terms whose projection bailed out (Q6)
+};
+
+constexpr int LIN_OFF_STRIDE = 4 + MAX_CAMS;  // pose_q, pose_t, proj, dist, baseline j (q; t = +3)
+
+struct StreamCtx {
+  cudaStream_t stream;
+  long long* launches;  // incremented per kernel launch
+};
+
+// launchers (kb_kernels.cu); every one returns the cudaGetLastError() of its launches
+cudaError_t launch_prep(const DevProblem& p, StreamCtx& s);
+cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int* model_begin, double* cost_out, StreamCtx& s);
+cudaError_t launch_linearise_assemble(const DevProblem& p, const int* view_list, const int* model_begin, StreamCtx& s);
+cudaError_t launch_linearise_materialise(const DevProblem& p, const int* view_list, const int* model_begin, double* jt_values, StreamCtx& s);
+cudaError_t launch_expand(const DevProblem& p, const int* cam_view_list, const int* cam_view_begin, StreamCtx& s);
+cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* pos_def_flag, StreamCtx& s);
+cudaError_t launch_schur_finalize(const DevProblem& p, double damping, const double* partials, int n_partials, bool add_camera_block, StreamCtx& s);
+cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s);
+cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, int* pos_def_flag, StreamCtx& s);
+cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int* cam_cols,
+                                   int include_shared, double* out2 /* [0]=sum, [1]=max|dx| */, StreamCtx& s);
+cudaError_t launch_apply_update(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, double* backup_cam,
+                                double* backup_base, double* backup_sets, StreamCtx& s);
+int schur_num_partials(const DevProblem& p);
+size_t schur_partial_stride(const DevProblem& p);
+
+}  // namespace kb

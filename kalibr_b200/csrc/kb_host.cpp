@@ -1,0 +1,902 @@
+// C ABI (include/kalibr_b200.h) and host-side logic of the B200 batch-calibration hot path: design-variable
+// ordering of the three kalibr2 drivers, sharding of synced sets over ranks, device buffer ownership, the call
+// sequence of LinearSystemSolver (evaluate -> build -> setConditioner -> solve -> update/revert), NCCL plumbing for
+// the reduced system, and the export of the Hessian block pattern / CCS Jacobian structure for parity checks.
+// There is no CPU compute path in here: every number comes from the kernels in kb_kernels.cu.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/kalibr_b200.h"
+#include "../../include/kalibr_b200/optimizer.hpp"
+#include "kb_device.cuh"
+
+using namespace kb;
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL through dlopen (no link-time dependency; single-GPU use never touches it)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) { err = "libnccl is missing symbols"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3;
+std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) count = 1;
+    return cudaMalloc((void**)&p, sizeof(T) * count);
+  }
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = alloc(v.size());
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s);
+  }
+};
+}  // namespace
+
+struct kb_handle {
+  std::string error;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  // ---- host-side structure ----
+  int driver_order = 0, n_cams = 0, n_sets_global = 0, set_lo = 0, set_hi = 0, n_ranks = 1, rank = 0;
+  int64_t n_terms_global = 0, n_terms_local = 0;
+  std::vector<int> cam_model;
+  std::vector<int> dv_dim, dv_col;  // active design variables in insertion order
+  std::vector<int> dv_proj, dv_dist, dv_base_q, dv_base_t;
+  int dv_first_set = 0;             // block index of q of set 0 (q_v = first + 2v, t_v = first + 2v + 1)
+  int64_t jcols = 0;
+  std::vector<int> h_view_set, h_view_cam, h_view_begin;  // local
+  std::vector<long long> h_view_jbase;
+  int64_t jac_nnz = 0;
+  std::vector<int> h_cam_cols;
+  // ---- device ----
+  DevProblem d;
+  DevBuf<double> y_u, y_v, target, cam_params, baselines, set_poses, camT, camPi, camA, e, view_cost, G, sumG, V, bv, W, Lv, yv, U, Sred, dxc, dx;
+  DevBuf<double> init_cam, init_base, init_sets, bk_cam, bk_base, bk_sets, partials, scalars, jt, gather;
+  DevBuf<uint16_t> corner;
+  DevBuf<int> view_set, view_cam, view_begin, set_view, lin_off, view_list, cam_view_list, cam_view_begin, set_col_q, set_col_t, cam_cols, posdef;
+  DevBuf<long long> view_jbase;
+  DevBuf<unsigned int> n_invalid;
+  int model_begin[KB_NUM_MODELS + 1] = {};
+  int n_partials = 0;
+  double* h_scalars = nullptr;  // pinned [8]
+  int* h_posdef = nullptr;      // pinned
+  // ---- solver state ----
+  double lambda = 0.0;          // _diagonalConditioner (constant)
+  double diag_residual = 0.0;   // what the lambda^2 / lambda asymmetry leaves on diag(H) since the last build (Q2)
+  int semantic = 0;
+  bool built = false, solved = false, has_backup = false;
+  std::vector<double> trace;
+  // ---- multi-GPU ----
+  NcclComm comm = nullptr;
+  // ---- timing ----
+  bool timing = false;
+  cudaEvent_t ev[2 * KB_NUM_STAGES] = {};
+  double stage_ms[KB_NUM_STAGES] = {};
+};
+
+namespace {
+
+#define KB_CUDA(h, call)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      (h)->error = std::string(#call) + ": " + cudaGetErrorString(_e);                            \
+      return KB_ERR_CUDA;                                                                         \
+    }                                                                                             \
+  } while (0)
+
+kb_status fail(kb_handle* h, kb_status code, const std::string& msg) {
+  if (h) h->error = msg; else g_create_error = msg;
+  return code;
+}
+
+void shard_range(int n_sets, int n_ranks, int rank, int& lo, int& hi) {
+  const int base = n_sets / n_ranks, rem = n_sets % n_ranks;
+  lo = rank * base + std::min(rank, rem);
+  hi = lo + base + (rank < rem ? 1 : 0);
+}
+
+StreamCtx ctx(kb_handle* h) { return StreamCtx{h->stream, &h->launches}; }
+
+struct StageTimer {
+  kb_handle* h;
+  int stage;
+  StageTimer(kb_handle* h_, int s) : h(h_), stage(s) { if (h->timing) cudaEventRecord(h->ev[2 * s], h->stream); }
+  ~StageTimer() { if (h->timing) cudaEventRecord(h->ev[2 * stage + 1], h->stream); }
+};
+void collect_stage(kb_handle* h, int s) {
+  if (!h->timing) return;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, h->ev[2 * s], h->ev[2 * s + 1]) == cudaSuccess) h->stage_ms[s] = ms;
+}
+
+kb_status nccl_allreduce(kb_handle* h, void* buf, size_t count, int dtype, int op) {
+  if (h->n_ranks <= 1) return KB_OK;
+  int r = g_nccl.AllReduce(buf, buf, count, dtype, op, h->comm, h->stream);
+  if (r != 0) return fail(h, KB_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
+  return KB_OK;
+}
+
+// design-variable layout of the three drivers
+void build_dv_layout(kb_handle* h) {
+  h->dv_dim.clear();
+  h->dv_proj.assign(h->n_cams, -1);
+  h->dv_dist.assign(h->n_cams, -1);
+  h->dv_base_q.assign(std::max(h->n_cams - 1, 0), -1);
+  h->dv_base_t.assign(std::max(h->n_cams - 1, 0), -1);
+  auto intr = [&](int k) {
+    h->dv_proj[k] = (int)h->dv_dim.size();
+    h->dv_dim.push_back(model_P(h->cam_model[k]));
+    h->dv_dist[k] = (int)h->dv_dim.size();
+    h->dv_dim.push_back(model_D(h->cam_model[k]));
+  };
+  auto base = [&]() {
+    for (int j = 0; j + 1 < h->n_cams; ++j) {
+      h->dv_base_q[j] = (int)h->dv_dim.size();
+      h->dv_dim.push_back(3);
+      h->dv_base_t[j] = (int)h->dv_dim.size();
+      h->dv_dim.push_back(3);
+    }
+  };
+  auto sets = [&]() {
+    h->dv_first_set = (int)h->dv_dim.size();
+    for (int v = 0; v < h->n_sets_global; ++v) { h->dv_dim.push_back(3); h->dv_dim.push_back(3); }
+  };
+  if (h->driver_order == KB_ORDER_SINGLE) { intr(0); sets(); }
+  else if (h->driver_order == KB_ORDER_STEREO) { base(); sets(); intr(0); intr(1); }
+  else { for (int k = 0; k < h->n_cams; ++k) intr(k); base(); sets(); }
+  h->dv_col.resize(h->dv_dim.size());
+  int c = 0;
+  for (size_t i = 0; i < h->dv_dim.size(); ++i) { h->dv_col[i] = c; c += h->dv_dim[i]; }
+  h->jcols = c;
+}
+
+// camera-side design variables a view of camera k touches
+std::vector<int> camside_dvs(const kb_handle* h, int k) {
+  std::vector<int> v = {h->dv_proj[k], h->dv_dist[k]};
+  for (int j = 0; j < k; ++j) { v.push_back(h->dv_base_q[j]); v.push_back(h->dv_base_t[j]); }
+  return v;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+const char* kb_last_error(const kb_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+kb_status kb_nccl_unique_id(char out[128]) {
+  std::string err;
+  if (!g_nccl.load(err)) return fail(nullptr, KB_ERR_NCCL, err);
+  NcclUniqueId id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return fail(nullptr, KB_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+  std::memcpy(out, id.internal, 128);
+  return KB_OK;
+}
+
+void kb_destroy(kb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) g_nccl.CommDestroy(h->comm);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->h_posdef) cudaFreeHost(h->h_posdef);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
+  if (!d || !out) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (d->n_cams < 1 || d->n_cams > MAX_CAMS) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "n_cams out of range (1..32)");
+  if (d->driver_order < 0 || d->driver_order > 2) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "unknown driver order");
+  if (d->driver_order == KB_ORDER_SINGLE && d->n_cams != 1) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "single-camera order needs one camera");
+  if (d->driver_order == KB_ORDER_STEREO && d->n_cams != 2) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "stereo order needs two cameras");
+  if (d->n_target_points < 1 || d->n_target_points > 65535) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "n_target_points out of range");
+  if (d->n_sets < 0 || d->n_views < 0 || d->n_terms < 0) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "negative size");
+  if (d->n_ranks < 1 || d->rank < 0 || d->rank >= d->n_ranks) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "bad rank / n_ranks");
+  for (int k = 0; k < d->n_cams; ++k)
+    if (d->cam_model[k] < 0 || d->cam_model[k] >= KB_NUM_MODELS) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "unknown camera model");
+
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
+    return fail(nullptr, KB_ERR_NO_DEVICE, "no CUDA device: the B200 hot path has no CPU fallback");
+  if (d->device < 0 || d->device >= n_dev) return fail(nullptr, KB_ERR_NO_DEVICE, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if (cudaSetDevice(d->device) != cudaSuccess || cudaGetDeviceProperties(&prop, d->device) != cudaSuccess)
+    return fail(nullptr, KB_ERR_NO_DEVICE, "cannot select CUDA device");
+  if (prop.major != 10) return fail(nullptr, KB_ERR_NO_DEVICE, "kernels are built for sm_100a only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+
+  std::unique_ptr<kb_handle, void (*)(kb_handle*)> hp(new kb_handle(), kb_destroy);
+  kb_handle* h = hp.get();
+  std::memset(&h->d, 0, sizeof(h->d));
+  h->device = d->device;
+  h->driver_order = d->driver_order;
+  h->n_cams = d->n_cams;
+  h->n_sets_global = d->n_sets;
+  h->n_ranks = d->n_ranks;
+  h->rank = d->rank;
+  h->n_terms_global = d->n_terms;
+  h->cam_model.assign(d->cam_model, d->cam_model + d->n_cams);
+  shard_range(d->n_sets, d->n_ranks, d->rank, h->set_lo, h->set_hi);
+  build_dv_layout(h);
+  auto cfail = [&](kb_status c, const std::string& m) { g_create_error = m; return c; };
+#define KB_CCUDA(call)                                                                                        \
+  do {                                                                                                        \
+    cudaError_t _e = (call);                                                                                  \
+    if (_e != cudaSuccess) return cfail(KB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));     \
+  } while (0)
+  KB_CCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  KB_CCUDA(cudaMallocHost((void**)&h->h_scalars, sizeof(double) * 8));
+  KB_CCUDA(cudaMallocHost((void**)&h->h_posdef, sizeof(int) * 2));
+  for (auto& e : h->ev) KB_CCUDA(cudaEventCreate(&e));
+
+  // ---- local views / terms ----
+  const int n_local_sets = h->set_hi - h->set_lo;
+  std::vector<double> yu, yv;
+  std::vector<uint16_t> corner;
+  std::vector<int>& vs = h->h_view_set;
+  std::vector<int>& vc = h->h_view_cam;
+  std::vector<int>& vb = h->h_view_begin;
+  vb.push_back(0);
+  std::vector<int> set_view((size_t)n_local_sets * d->n_cams, -1);
+  for (int w = 0; w < d->n_views; ++w) {
+    const int v = d->view_set[w], k = d->view_cam[w];
+    if (v < 0 || v >= d->n_sets || k < 0 || k >= d->n_cams) return cfail(KB_ERR_INVALID_ARGUMENT, "view index out of range");
+    const int64_t b = d->view_begin[w], e = d->view_begin[w + 1];
+    if (b < 0 || e < b || e > d->n_terms) return cfail(KB_ERR_INVALID_ARGUMENT, "view_begin is not a monotone partition of the terms");
+    if (v < h->set_lo || v >= h->set_hi) continue;
+    const int lv = v - h->set_lo;
+    if (set_view[(size_t)lv * d->n_cams + k] >= 0) return cfail(KB_ERR_INVALID_ARGUMENT, "two views for the same (set, camera)");
+    set_view[(size_t)lv * d->n_cams + k] = (int)vs.size();
+    vs.push_back(lv);
+    vc.push_back(k);
+    for (int64_t i = b; i < e; ++i) {
+      if (d->corner_id[i] < 0 || d->corner_id[i] >= d->n_target_points) return cfail(KB_ERR_INVALID_ARGUMENT, "corner_id out of range");
+      yu.push_back(d->y_u[i]);
+      yv.push_back(d->y_v[i]);
+      corner.push_back((uint16_t)d->corner_id[i]);
+    }
+    if (yu.size() > (size_t)0x7fffffff) return cfail(KB_ERR_INVALID_ARGUMENT, "more than 2^31 terms on one rank");
+    vb.push_back((int)yu.size());
+  }
+  const int n_views = (int)vs.size();
+  h->n_terms_local = (int64_t)yu.size();
+
+  // ---- reduced-system layout: [cam0 proj|dist, cam1 ..., | baseline 0 q,t, ...] ----
+  DevProblem& D = h->d;
+  D.n_cams = d->n_cams;
+  D.n_sets = n_local_sets;
+  D.n_views = n_views;
+  D.n_target = d->n_target_points;
+  D.n_terms = h->n_terms_local;
+  int off = 0;
+  for (int k = 0; k < d->n_cams; ++k) {
+    D.cam_model[k] = d->cam_model[k];
+    D.cam_P[k] = model_P(d->cam_model[k]);
+    D.cam_D[k] = model_D(d->cam_model[k]);
+    D.intr_off[k] = off;
+    off += D.cam_P[k] + D.cam_D[k];
+  }
+  for (int j = 0; j + 1 < d->n_cams; ++j) { D.base_off[j] = off; off += 6; }
+  D.n_c = off;
+  D.n_aug = off + 1;
+  if (D.n_aug > 224) return cfail(KB_ERR_INVALID_ARGUMENT, "reduced camera system larger than 223 unknowns is not supported");
+  h->h_cam_cols.assign(D.n_c, 0);
+  for (int k = 0; k < d->n_cams; ++k) {
+    for (int c = 0; c < D.cam_P[k]; ++c) h->h_cam_cols[D.intr_off[k] + c] = h->dv_col[h->dv_proj[k]] + c;
+    for (int c = 0; c < D.cam_D[k]; ++c) h->h_cam_cols[D.intr_off[k] + D.cam_P[k] + c] = h->dv_col[h->dv_dist[k]] + c;
+  }
+  for (int j = 0; j + 1 < d->n_cams; ++j)
+    for (int c = 0; c < 3; ++c) {
+      h->h_cam_cols[D.base_off[j] + c] = h->dv_col[h->dv_base_q[j]] + c;
+      h->h_cam_cols[D.base_off[j] + 3 + c] = h->dv_col[h->dv_base_t[j]] + c;
+    }
+  std::vector<int> set_col_q(n_local_sets), set_col_t(n_local_sets);
+  for (int lv = 0; lv < n_local_sets; ++lv) {
+    set_col_q[lv] = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv)];
+    set_col_t[lv] = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv) + 1];
+  }
+  // ---- CCS J^T slot offsets per camera: design variables of a term sorted by block index ----
+  std::vector<int> lin_off((size_t)d->n_cams * LIN_OFF_STRIDE, 0);
+  h->h_view_jbase.assign(n_views, 0);
+  {
+    const int pose_q_block = h->dv_first_set;  // relative order against the camera-side blocks is the same for every set
+    for (int k = 0; k < d->n_cams; ++k) {
+      struct Seg { int block, dim, slot; };
+      std::vector<Seg> segs;
+      segs.push_back({pose_q_block, 3, 0});
+      segs.push_back({pose_q_block + 1, 3, 1});
+      segs.push_back({h->dv_proj[k], D.cam_P[k], 2});
+      segs.push_back({h->dv_dist[k], D.cam_D[k], 3});
+      for (int j = 0; j < k; ++j) segs.push_back({h->dv_base_q[j], 6, 4 + j});  // q,t adjacent in every order
+      std::sort(segs.begin(), segs.end(), [](const Seg& a, const Seg& b) { return a.block < b.block; });
+      int o = 0;
+      for (auto& s : segs) { lin_off[(size_t)k * LIN_OFF_STRIDE + s.slot] = o; o += s.dim; }
+    }
+    long long jb = 0;
+    for (int w = 0; w < n_views; ++w) {
+      h->h_view_jbase[w] = jb;
+      const int k = vc[w];
+      jb += (long long)(vb[w + 1] - vb[w]) * 2 * (6 + 6 * k + D.cam_P[k] + D.cam_D[k]);
+    }
+    h->jac_nnz = jb;
+  }
+  // ---- view lists: by model (kernel specialisation) and by camera (Gram sums) ----
+  std::vector<int> view_list;
+  for (int m = 0; m < KB_NUM_MODELS; ++m) {
+    h->model_begin[m] = (int)view_list.size();
+    for (int k = 0; k < d->n_cams; ++k)
+      if (d->cam_model[k] == m)
+        for (int w = 0; w < n_views; ++w)
+          if (vc[w] == k) view_list.push_back(w);
+  }
+  h->model_begin[KB_NUM_MODELS] = (int)view_list.size();
+  std::vector<int> cam_view_list, cam_view_begin(d->n_cams + 1, 0);
+  for (int k = 0; k < d->n_cams; ++k) {
+    cam_view_begin[k] = (int)cam_view_list.size();
+    for (int w = 0; w < n_views; ++w)
+      if (vc[w] == k) cam_view_list.push_back(w);
+  }
+  cam_view_begin[d->n_cams] = (int)cam_view_list.size();
+
+  // ---- upload ----
+  cudaStream_t s = h->stream;
+  std::vector<double> target(d->target_points, d->target_points + (size_t)3 * d->n_target_points);
+  std::vector<double> cam(d->cam_params, d->cam_params + (size_t)KB_CAM_PARAM_STRIDE * d->n_cams);
+  std::vector<double> base;
+  if (d->n_cams > 1) base.assign(d->baselines, d->baselines + (size_t)KB_POSE_STRIDE * (d->n_cams - 1));
+  std::vector<double> sets;
+  if (n_local_sets > 0) sets.assign(d->set_poses + (size_t)KB_POSE_STRIDE * h->set_lo, d->set_poses + (size_t)KB_POSE_STRIDE * h->set_hi);
+  KB_CCUDA(h->y_u.upload(yu, s));
+  KB_CCUDA(h->y_v.upload(yv, s));
+  KB_CCUDA(h->corner.upload(corner, s));
+  KB_CCUDA(h->target.upload(target, s));
+  KB_CCUDA(h->view_set.upload(vs, s));
+  KB_CCUDA(h->view_cam.upload(vc, s));
+  KB_CCUDA(h->view_begin.upload(vb, s));
+  KB_CCUDA(h->set_view.upload(set_view, s));
+  KB_CCUDA(h->lin_off.upload(lin_off, s));
+  KB_CCUDA(h->view_jbase.upload(h->h_view_jbase, s));
+  KB_CCUDA(h->view_list.upload(view_list, s));
+  KB_CCUDA(h->cam_view_list.upload(cam_view_list, s));
+  KB_CCUDA(h->cam_view_begin.upload(cam_view_begin, s));
+  KB_CCUDA(h->set_col_q.upload(set_col_q, s));
+  KB_CCUDA(h->set_col_t.upload(set_col_t, s));
+  KB_CCUDA(h->cam_cols.upload(h->h_cam_cols, s));
+  KB_CCUDA(h->cam_params.upload(cam, s));
+  KB_CCUDA(h->baselines.upload(base, s));
+  KB_CCUDA(h->set_poses.upload(sets, s));
+  KB_CCUDA(h->init_cam.upload(cam, s));
+  KB_CCUDA(h->init_base.upload(base, s));
+  KB_CCUDA(h->init_sets.upload(sets, s));
+  KB_CCUDA(h->bk_cam.upload(cam, s));
+  KB_CCUDA(h->bk_base.upload(base, s));
+  KB_CCUDA(h->bk_sets.upload(sets, s));
+  const size_t C = d->n_cams, S = n_local_sets, NA = D.n_aug;
+  KB_CCUDA(h->camT.alloc(C * 12));
+  KB_CCUDA(h->camPi.alloc(C * 36));
+  KB_CCUDA(h->camA.alloc(C * C * 36));
+  KB_CCUDA(h->e.alloc(2 * (size_t)h->n_terms_local));
+  KB_CCUDA(h->view_cost.alloc(n_views));
+  KB_CCUDA(h->G.alloc((size_t)n_views * GRAM_SIZE));
+  KB_CCUDA(h->sumG.alloc(C * GRAM_SIZE));
+  KB_CCUDA(h->V.alloc(S * 36));
+  KB_CCUDA(h->bv.alloc(S * 6));
+  KB_CCUDA(h->W.alloc(S * D.n_c * 6));
+  KB_CCUDA(h->Lv.alloc(S * 36));
+  KB_CCUDA(h->yv.alloc(S * 6));
+  KB_CCUDA(h->U.alloc(NA * NA));
+  KB_CCUDA(h->Sred.alloc(NA * NA));
+  KB_CCUDA(h->dxc.alloc(D.n_c));
+  KB_CCUDA(h->dx.alloc((size_t)h->jcols));
+  KB_CCUDA(h->scalars.alloc(8));
+  KB_CCUDA(h->posdef.alloc(2));
+  KB_CCUDA(h->n_invalid.alloc(1));
+  KB_CCUDA(cudaMemsetAsync(h->n_invalid.p, 0, sizeof(unsigned int), s));
+  KB_CCUDA(cudaMemsetAsync(h->dx.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)h->jcols), s));
+  KB_CCUDA(cudaMemsetAsync(h->G.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)n_views * GRAM_SIZE), s));
+  KB_CCUDA(cudaMemsetAsync(h->e.p, 0, sizeof(double) * std::max<size_t>(1, 2 * (size_t)h->n_terms_local), s));
+  KB_CCUDA(cudaMemsetAsync(h->camA.p, 0, sizeof(double) * C * C * 36, s));
+  D.y_u = h->y_u.p; D.y_v = h->y_v.p; D.corner = h->corner.p; D.target = h->target.p;
+  D.view_set = h->view_set.p; D.view_cam = h->view_cam.p; D.view_begin = h->view_begin.p; D.set_view = h->set_view.p;
+  D.lin_off = h->lin_off.p; D.view_jbase = h->view_jbase.p;
+  D.cam_params = h->cam_params.p; D.baselines = h->baselines.p; D.set_poses = h->set_poses.p;
+  D.camT = h->camT.p; D.camPi = h->camPi.p; D.camA = h->camA.p;
+  D.e = h->e.p; D.view_cost = h->view_cost.p; D.G = h->G.p; D.sumG = h->sumG.p;
+  D.V = h->V.p; D.bv = h->bv.p; D.W = h->W.p; D.Lv = h->Lv.p; D.yv = h->yv.p;
+  D.U = h->U.p; D.Sred = h->Sred.p; D.dxc = h->dxc.p; D.dx = h->dx.p; D.n_invalid = h->n_invalid.p;
+  h->n_partials = schur_num_partials(D);
+  KB_CCUDA(h->partials.alloc(schur_partial_stride(D) * h->n_partials));
+
+  if (d->n_ranks > 1) {
+    std::string err;
+    if (!g_nccl.load(err)) return cfail(KB_ERR_NCCL, err);
+    if (!d->nccl_id) return cfail(KB_ERR_INVALID_ARGUMENT, "nccl_id is required when n_ranks > 1");
+    NcclUniqueId id;
+    std::memcpy(id.internal, d->nccl_id, 128);
+    int r = g_nccl.CommInitRank(&h->comm, d->n_ranks, id, d->rank);
+    if (r != 0) return cfail(KB_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+  }
+  KB_CCUDA(cudaStreamSynchronize(s));
+#undef KB_CCUDA
+  *out = hp.release();
+  return KB_OK;
+}
+
+int64_t kb_jrows(const kb_handle* h) { return 2 * h->n_terms_global; }
+int64_t kb_local_jrows(const kb_handle* h) { return 2 * h->n_terms_local; }
+int64_t kb_jcols(const kb_handle* h) { return h->jcols; }
+int32_t kb_num_design_variables(const kb_handle* h) { return (int32_t)h->dv_dim.size(); }
+kb_status kb_get_dv_layout(const kb_handle* h, int32_t* column_base, int32_t* dims) {
+  for (size_t i = 0; i < h->dv_dim.size(); ++i) { column_base[i] = h->dv_col[i]; dims[i] = h->dv_dim[i]; }
+  return KB_OK;
+}
+int64_t kb_kernel_launches(const kb_handle* h) { return h->launches; }
+void* kb_cuda_stream(kb_handle* h) { return (void*)h->stream; }
+kb_status kb_enable_stage_timing(kb_handle* h, int32_t on) { h->timing = on != 0; return KB_OK; }
+kb_status kb_get_stage_ms(kb_handle* h, double* ms) {
+  for (int i = 0; i < KB_NUM_STAGES; ++i) ms[i] = h->stage_ms[i];
+  return KB_OK;
+}
+kb_status kb_set_solver_semantic(kb_handle* h, int32_t semantic) {
+  if (semantic != 0 && semantic != 1) return fail(h, KB_ERR_INVALID_ARGUMENT, "semantic must be 0 (block_cholesky) or 1 (sparse_cholesky)");
+  h->semantic = semantic;
+  return KB_OK;
+}
+
+kb_status kb_evaluate_error(kb_handle* h, int32_t use_m_estimator, double* out_cost) {
+  if (use_m_estimator) {
+    // kalibr2 never installs an M-estimator on these terms (NoMEstimator weight 1): accepted and ignored like the reference does
+  }
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  {
+    StageTimer t(h, 0);
+    KB_CUDA(h, launch_prep(h->d, c));
+    KB_CUDA(h, launch_evaluate(h->d, h->view_list.p, h->model_begin, h->scalars.p, c));
+    kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
+    if (st != KB_OK) return st;
+  }
+  KB_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  collect_stage(h, 0);
+  if (out_cost) *out_cost = h->h_scalars[0];
+  return KB_OK;
+}
+
+kb_status kb_build_system(kb_handle* h, int32_t /*use_m_estimator*/) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  {
+    StageTimer t(h, 1);
+    KB_CUDA(h, launch_prep(h->d, c));
+    KB_CUDA(h, launch_linearise_assemble(h->d, h->view_list.p, h->model_begin, c));
+  }
+  {
+    StageTimer t(h, 2);
+    KB_CUDA(h, launch_expand(h->d, h->cam_view_list.p, h->cam_view_begin.p, c));
+  }
+  h->diag_residual = 0.0;  // H.clear(false): BlockCholeskyLinearSystemSolver.cpp:64
+  h->built = true;
+  h->solved = false;
+  if (h->timing) {
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    collect_stage(h, 1);
+    collect_stage(h, 2);
+  }
+  return KB_OK;
+}
+
+kb_status kb_set_constant_conditioner(kb_handle* h, double lambda) {
+  h->lambda = lambda;
+  return KB_OK;
+}
+
+kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* pos_def) {
+  if (!h->built) return fail(h, KB_ERR_STATE, "kb_solve_system called before kb_build_system");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  // diag(H) += lambda^2 on top of whatever earlier solves left there (BlockCholeskyLinearSystemSolver.cpp:77-86)
+  const double damping = h->diag_residual + h->lambda * h->lambda;
+  h->h_posdef[0] = 1;
+  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  {
+    StageTimer t(h, 3);
+    KB_CUDA(h, launch_schur(h->d, damping, h->partials.p, h->n_partials, h->posdef.p, c));
+    KB_CUDA(h, launch_schur_finalize(h->d, damping, h->partials.p, h->n_partials, true, c));
+    kb_status st = nccl_allreduce(h, h->Sred.p, (size_t)h->d.n_aug * h->d.n_aug, kNcclFloat64, kNcclSum);
+    if (st != KB_OK) return st;
+  }
+  {
+    StageTimer t(h, 4);
+    KB_CUDA(h, launch_reduced_solve(h->d, damping, h->posdef.p, c));
+  }
+  {
+    StageTimer t(h, 5);
+    KB_CUDA(h, launch_backsub(h->d, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->posdef.p, c));
+  }
+  {
+    kb_status st = nccl_allreduce(h, h->posdef.p, 1, kNcclInt32, kNcclMin);
+    if (st != KB_OK) return st;
+  }
+  KB_CUDA(h, cudaMemcpyAsync(h->h_posdef, h->posdef.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (dx) {
+    if (gather_dx && h->n_ranks > 1) {
+      // poses are disjoint across ranks, the shared block is identical: sum with the shared block kept on rank 0 only
+      KB_CUDA(h, h->gather.n == (size_t)h->jcols ? cudaSuccess : h->gather.alloc((size_t)h->jcols));
+      KB_CUDA(h, cudaMemcpyAsync(h->gather.p, h->dx.p, sizeof(double) * h->jcols, cudaMemcpyDeviceToDevice, h->stream));
+      if (h->rank != 0) {
+        std::vector<int> cols = h->h_cam_cols;
+        std::sort(cols.begin(), cols.end());
+        // camera-side columns form at most a few contiguous runs
+        size_t i = 0;
+        while (i < cols.size()) {
+          size_t j = i;
+          while (j + 1 < cols.size() && cols[j + 1] == cols[j] + 1) ++j;
+          KB_CUDA(h, cudaMemsetAsync(h->gather.p + cols[i], 0, sizeof(double) * (j - i + 1), h->stream));
+          i = j + 1;
+        }
+      }
+      kb_status st = nccl_allreduce(h, h->gather.p, (size_t)h->jcols, kNcclFloat64, kNcclSum);
+      if (st != KB_OK) return st;
+      KB_CUDA(h, cudaMemcpyAsync(dx, h->gather.p, sizeof(double) * h->jcols, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      KB_CUDA(h, cudaMemcpyAsync(dx, h->dx.p, sizeof(double) * h->jcols, cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  collect_stage(h, 3);
+  collect_stage(h, 4);
+  collect_stage(h, 5);
+  // un-augment: BlockCholesky subtracts lambda, not lambda^2 (BlockCholeskyLinearSystemSolver.cpp:91-97)
+  if (h->semantic == 0) h->diag_residual += h->lambda * h->lambda - h->lambda;
+  h->solved = true;
+  if (pos_def) *pos_def = h->h_posdef[0];
+  return KB_OK;
+}
+
+kb_status kb_lm_rho_denominator(kb_handle* h, double lambda, double* out) {
+  if (!h->solved) return fail(h, KB_ERR_STATE, "kb_lm_rho_denominator called before kb_solve_system");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  KB_CUDA(h, launch_rho_denominator(h->d, lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2, c));
+  kb_status st = nccl_allreduce(h, h->scalars.p + 2, 1, kNcclFloat64, kNcclSum);
+  if (st != KB_OK) return st;
+  KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 2, h->scalars.p + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (out) *out = h->h_scalars[2];
+  return KB_OK;
+}
+
+kb_status kb_apply_state_update(kb_handle* h, double* out_max_abs_dx) {
+  if (!h->solved) return fail(h, KB_ERR_STATE, "kb_apply_state_update called before kb_solve_system");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  {
+    StageTimer t(h, 6);
+    KB_CUDA(h, launch_rho_denominator(h->d, 0.0, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, 0, h->scalars.p + 4, c));
+    kb_status st = nccl_allreduce(h, h->scalars.p + 5, 1, kNcclFloat64, kNcclMax);
+    if (st != KB_OK) return st;
+    KB_CUDA(h, launch_apply_update(h->d, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->bk_cam.p, h->bk_base.p, h->bk_sets.p, c));
+  }
+  KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 5, h->scalars.p + 5, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  collect_stage(h, 6);
+  h->has_backup = true;
+  if (out_max_abs_dx) *out_max_abs_dx = h->h_scalars[5];
+  return KB_OK;
+}
+
+kb_status kb_revert_last_state_update(kb_handle* h) {
+  if (!h->has_backup) return fail(h, KB_ERR_STATE, "kb_revert_last_state_update without a previous update");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  KB_CUDA(h, cudaMemcpyAsync(h->cam_params.p, h->bk_cam.p, sizeof(double) * h->cam_params.n, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->baselines.n) KB_CUDA(h, cudaMemcpyAsync(h->baselines.p, h->bk_base.p, sizeof(double) * h->baselines.n, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->set_poses.n) KB_CUDA(h, cudaMemcpyAsync(h->set_poses.p, h->bk_sets.p, sizeof(double) * h->set_poses.n, cudaMemcpyDeviceToDevice, h->stream));
+  return KB_OK;
+}
+
+kb_status kb_reset_state(kb_handle* h) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  KB_CUDA(h, cudaMemcpyAsync(h->cam_params.p, h->init_cam.p, sizeof(double) * h->cam_params.n, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->baselines.n) KB_CUDA(h, cudaMemcpyAsync(h->baselines.p, h->init_base.p, sizeof(double) * h->baselines.n, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->set_poses.n) KB_CUDA(h, cudaMemcpyAsync(h->set_poses.p, h->init_sets.p, sizeof(double) * h->set_poses.n, cudaMemcpyDeviceToDevice, h->stream));
+  h->built = h->solved = h->has_backup = false;
+  h->diag_residual = 0.0;
+  h->lambda = 0.0;
+  return KB_OK;
+}
+
+kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v) {
+  if (h->n_ranks != 1) return fail(h, KB_ERR_STATE, "kb_set_observations supports a single rank (terms are re-packed per rank at kb_create)");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  KB_CUDA(h, cudaMemcpyAsync(h->y_u.p, y_u, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->y_v.p, y_v, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
+  return KB_OK;
+}
+
+int64_t kb_num_invalid_terms(kb_handle* h) {
+  unsigned int v = 0;
+  cudaSetDevice(h->device);
+  cudaMemcpyAsync(&v, h->n_invalid.p, sizeof(v), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  return (int64_t)v;
+}
+
+void kb_default_optimizer_options(kb_optimizer_options* o) {
+  o->convergence_delta_x = 1e-3;
+  o->convergence_delta_j = 1.0;
+  o->max_iterations = 200;
+  o->lm_lambda_init = 10.0;
+  o->verbose = 0;
+}
+
+kb_status kb_optimize(kb_handle* h, const kb_optimizer_options* o, kb_solution* out) {
+  using namespace kalibr_b200::backend;
+  try {
+    Optimizer2Options opt;
+    opt.convergenceDeltaX = o->convergence_delta_x;
+    opt.convergenceDeltaJ = o->convergence_delta_j;
+    opt.maxIterations = o->max_iterations;
+    opt.verbose = o->verbose != 0;
+    opt.linearSystemSolver = std::make_shared<B200SchurLinearSystemSolver>(h, true);
+    opt.trustRegionPolicy = std::make_shared<LevenbergMarquardtTrustRegionPolicy>(o->lm_lambda_init);
+    Optimizer2 optimizer(opt);
+    SolutionReturnValue srv = optimizer.optimize();
+    h->trace = optimizer.trace();
+    if (out) {
+      out->j_start = srv.JStart;
+      out->j_final = srv.JFinal;
+      out->dx_final = srv.dXFinal;
+      out->dj_final = srv.dJFinal;
+      out->iterations = srv.iterations;
+      out->failed_iterations = srv.failedIterations;
+      out->linear_solver_failure = srv.linearSolverFailure ? 1 : 0;
+    }
+    return KB_OK;
+  } catch (const std::exception& e) {
+    if (h->error.empty()) h->error = e.what();
+    return KB_ERR_CUDA;
+  }
+}
+
+int32_t kb_get_trace(const kb_handle* h, double* out, int32_t max_triples) {
+  const int32_t n = (int32_t)(h->trace.size() / 3);
+  if (out)
+    for (int32_t i = 0; i < std::min(n, max_triples) * 3; ++i) out[i] = h->trace[i];
+  return n;
+}
+
+// ---- read-back --------------------------------------------------------------------------------------------
+kb_status kb_get_error_vector(kb_handle* h, double* e) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  KB_CUDA(h, cudaMemcpyAsync(e, h->e.p, sizeof(double) * 2 * h->n_terms_local, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+static kb_status download(kb_handle* h, const DevBuf<double>& b, std::vector<double>& out) {
+  out.resize(b.n);
+  if (b.n) KB_CUDA(h, cudaMemcpyAsync(out.data(), b.p, sizeof(double) * b.n, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+kb_status kb_get_rhs(kb_handle* h, double* rhs) {
+  if (!h->built) return fail(h, KB_ERR_STATE, "kb_get_rhs called before kb_build_system");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  std::vector<double> bv, U;
+  kb_status st;
+  if ((st = download(h, h->bv, bv)) != KB_OK) return st;
+  if (h->n_ranks > 1) {  // b_c is a per-rank partial: reduce a copy
+    KB_CUDA(h, h->gather.alloc((size_t)h->d.n_aug * h->d.n_aug));
+    KB_CUDA(h, cudaMemcpyAsync(h->gather.p, h->U.p, sizeof(double) * h->U.n, cudaMemcpyDeviceToDevice, h->stream));
+    if ((st = nccl_allreduce(h, h->gather.p, h->U.n, kNcclFloat64, kNcclSum)) != KB_OK) return st;
+    if ((st = download(h, h->gather, U)) != KB_OK) return st;
+  } else if ((st = download(h, h->U, U)) != KB_OK) return st;
+  std::fill(rhs, rhs + h->jcols, 0.0);
+  const int n = h->d.n_aug;
+  for (int i = 0; i < h->d.n_c; ++i) rhs[h->h_cam_cols[i]] = U[(size_t)i * n + h->d.n_c];
+  for (int lv = 0; lv < h->d.n_sets; ++lv) {
+    const int cq = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv)], ct = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv) + 1];
+    for (int c = 0; c < 3; ++c) { rhs[cq + c] = bv[(size_t)lv * 6 + c]; rhs[ct + c] = bv[(size_t)lv * 6 + 3 + c]; }
+  }
+  return KB_OK;
+}
+
+kb_status kb_linearise(kb_handle* h) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  if (h->jt.n != (size_t)h->jac_nnz) KB_CUDA(h, h->jt.alloc((size_t)h->jac_nnz));
+  StreamCtx c = ctx(h);
+  {
+    StageTimer t(h, 7);
+    KB_CUDA(h, launch_prep(h->d, c));
+    KB_CUDA(h, launch_linearise_materialise(h->d, h->view_list.p, h->model_begin, h->jt.p, c));
+  }
+  if (h->timing) {
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    collect_stage(h, 7);
+  }
+  return KB_OK;
+}
+int64_t kb_jacobian_nnz(const kb_handle* h) { return h->jac_nnz; }
+
+kb_status kb_get_jacobian_ccs(kb_handle* h, int64_t* col_ptr, int32_t* row_idx, double* values) {
+  if (!col_ptr || !row_idx || !values) return fail(h, KB_ERR_INVALID_ARGUMENT, "null output array (use kb_jacobian_nnz for the size)");
+  if (h->jt.n != (size_t)h->jac_nnz) return fail(h, KB_ERR_STATE, "kb_get_jacobian_ccs called before kb_linearise");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  if (h->jac_nnz) KB_CUDA(h, cudaMemcpyAsync(values, h->jt.p, sizeof(double) * h->jac_nnz, cudaMemcpyDeviceToHost, h->stream));
+  // structure: per term, design variables sorted by block index (CompressedColumnMatrix.hpp:236-304)
+  int64_t o = 0;
+  size_t col = 0;
+  col_ptr[0] = 0;
+  for (size_t w = 0; w < h->h_view_set.size(); ++w) {
+    const int k = h->h_view_cam[w], gv = h->set_lo + h->h_view_set[w];
+    std::vector<int> blocks = camside_dvs(h, k);
+    blocks.push_back(h->dv_first_set + 2 * gv);
+    blocks.push_back(h->dv_first_set + 2 * gv + 1);
+    std::sort(blocks.begin(), blocks.end());
+    std::vector<int32_t> rows;
+    for (int b : blocks)
+      for (int c = 0; c < h->dv_dim[b]; ++c) rows.push_back(h->dv_col[b] + c);
+    for (int i = h->h_view_begin[w]; i < h->h_view_begin[w + 1]; ++i)
+      for (int r = 0; r < 2; ++r) {
+        std::memcpy(row_idx + o, rows.data(), sizeof(int32_t) * rows.size());
+        o += (int64_t)rows.size();
+        col_ptr[++col] = o;
+      }
+  }
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+kb_status kb_get_hessian_blocks(kb_handle* h, int64_t* n_blocks, int64_t* n_values, int64_t* col_ptr, int32_t* block_row, int64_t* value_ptr,
+                                double* values) {
+  if (h->n_ranks != 1) return fail(h, KB_ERR_STATE, "kb_get_hessian_blocks is a single-rank parity export");
+  if (!h->built) return fail(h, KB_ERR_STATE, "kb_get_hessian_blocks called before kb_build_system");
+  const int n_dv = (int)h->dv_dim.size();
+  // ---- pattern: pairs of design variables sharing a term (JacobianContainer.cpp:112-126), plus every diagonal block once
+  //      solveSystem has run (BlockCholeskyLinearSystemSolver.cpp:80, block(i,i,true)) ----
+  std::vector<std::set<int>> cols(n_dv);
+  std::vector<char> cam_used(h->n_cams, 0);
+  for (size_t w = 0; w < h->h_view_set.size(); ++w) {
+    if (h->h_view_begin[w + 1] == h->h_view_begin[w]) continue;
+    const int k = h->h_view_cam[w], v = h->set_lo + h->h_view_set[w];
+    const int bq = h->dv_first_set + 2 * v, bt = bq + 1;
+    cols[bq].insert(bq); cols[bt].insert(bq); cols[bt].insert(bt);
+    for (int c : camside_dvs(h, k)) {
+      for (int pb : {bq, bt}) cols[std::max(c, pb)].insert(std::min(c, pb));
+    }
+    cam_used[k] = 1;
+  }
+  for (int k = 0; k < h->n_cams; ++k) {
+    if (!cam_used[k]) continue;
+    std::vector<int> cs = camside_dvs(h, k);
+    for (int a : cs)
+      for (int b : cs) cols[std::max(a, b)].insert(std::min(a, b));
+  }
+  if (h->solved)
+    for (int i = 0; i < n_dv; ++i) cols[i].insert(i);
+  int64_t nb = 0, nv = 0;
+  for (int c = 0; c < n_dv; ++c)
+    for (int r : cols[c]) { ++nb; nv += (int64_t)h->dv_dim[r] * h->dv_dim[c]; }
+  if (n_blocks) *n_blocks = nb;
+  if (n_values) *n_values = nv;
+  if (!col_ptr || !block_row || !value_ptr || !values) return KB_OK;
+  // ---- values from the device blocks ----
+  KB_CUDA(h, cudaSetDevice(h->device));
+  std::vector<double> V, W, U;
+  kb_status st;
+  if ((st = download(h, h->V, V)) != KB_OK) return st;
+  if ((st = download(h, h->W, W)) != KB_OK) return st;
+  if ((st = download(h, h->U, U)) != KB_OK) return st;
+  const int nc = h->d.n_c, na = h->d.n_aug;
+  // reduced-system offset of every camera-side block
+  std::vector<int> red_off(n_dv, -1);
+  for (int k = 0; k < h->n_cams; ++k) { red_off[h->dv_proj[k]] = h->d.intr_off[k]; red_off[h->dv_dist[k]] = h->d.intr_off[k] + h->d.cam_P[k]; }
+  for (int j = 0; j + 1 < h->n_cams; ++j) { red_off[h->dv_base_q[j]] = h->d.base_off[j]; red_off[h->dv_base_t[j]] = h->d.base_off[j] + 3; }
+  auto is_pose = [&](int b) { return b >= h->dv_first_set && b < h->dv_first_set + 2 * h->n_sets_global; };
+  // H(a, b) entry accessor for design-variable blocks a, b (any order), local indices i, j
+  auto entry = [&](int a, int i, int b, int j) -> double {
+    const bool pa = is_pose(a), pb = is_pose(b);
+    if (pa && pb) {
+      const int va = (a - h->dv_first_set) / 2, vb2 = (b - h->dv_first_set) / 2;
+      if (va != vb2) return 0.0;
+      const int ia = ((a - h->dv_first_set) & 1) * 3 + i, ib = ((b - h->dv_first_set) & 1) * 3 + j;
+      double v = V[(size_t)(va - h->set_lo) * 36 + ia * 6 + ib];
+      if (a == b && i == j) v += h->diag_residual;
+      return v;
+    }
+    if (!pa && !pb) {
+      double v = U[(size_t)(red_off[a] + i) * na + red_off[b] + j];
+      if (a == b && i == j) v += h->diag_residual;
+      return v;
+    }
+    const int cam_b = pa ? b : a, cam_i = pa ? j : i, pose_b = pa ? a : b, pose_i = pa ? i : j;
+    const int v = (pose_b - h->dv_first_set) / 2;
+    return W[((size_t)(v - h->set_lo) * nc + red_off[cam_b] + cam_i) * 6 + ((pose_b - h->dv_first_set) & 1) * 3 + pose_i];
+  };
+  int64_t bi = 0, vi = 0;
+  for (int c = 0; c < n_dv; ++c) {
+    col_ptr[c] = bi;
+    for (int r : cols[c]) {
+      block_row[bi] = r;
+      value_ptr[bi] = vi;
+      for (int j = 0; j < h->dv_dim[c]; ++j)       // column-major like Eigen
+        for (int i = 0; i < h->dv_dim[r]; ++i) values[vi++] = entry(r, i, c, j);
+      ++bi;
+    }
+  }
+  col_ptr[n_dv] = bi;
+  return KB_OK;
+}
+
+kb_status kb_get_camera_params(kb_handle* h, double* out) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  KB_CUDA(h, cudaMemcpyAsync(out, h->cam_params.p, sizeof(double) * h->cam_params.n, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+kb_status kb_get_baselines(kb_handle* h, double* out) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  if (h->baselines.n) KB_CUDA(h, cudaMemcpyAsync(out, h->baselines.p, sizeof(double) * h->baselines.n, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+kb_status kb_get_set_poses(kb_handle* h, double* out) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  if (h->set_poses.n)
+    KB_CUDA(h, cudaMemcpyAsync(out + (size_t)KB_POSE_STRIDE * h->set_lo, h->set_poses.p, sizeof(double) * h->set_poses.n, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1153 @@
+// Hand-written sm_100a kernels of the batch-calibration hot path.
+//
+//   prep            per-linearisation camera-chain constants (T_cam_k_cam_0, boxTimes products, baseline adjoints)
+//   evaluate        K5: residual-only pass, cost                     ≙ BE/src/LinearSystemSolver.cpp:12-23, 81-92
+//   linearise_assemble  K1+K2 fused: per term chain + projection + 3 Jacobians, per view Gram block
+//                   G = [J_xi|J_proj|J_dist|e]^T [..] on the FP64 tensor pipe (DMMA m8n8k4)
+//                                                                     ≙ ReprojectionError.hpp:63-77 + JacobianContainer.cpp:103-167
+//   linearise_materialise  K1 with J written out in the reference's CCS J^T layout
+//                                                                     ≙ CompressedColumnJacobianTransposeBuilder.hpp:59-100
+//   expand          per set: V_v, b_v, W_v from the Gram blocks       ≙ sparse_block_matrix.hpp:121-143 (block += J1^T J2)
+//   sum_gram/camera_block  U, b_c
+//   schur           K3a: S = U - sum_v W_v (V_v + d I)^-1 W_v^T on DMMA ≙ BE/src/sparse_matrix_functions.cpp:8-60
+//   reduced_solve   K3b: dense Cholesky of the reduced system          ≙ linear_solver_cholmod.h:70-112
+//   backsub         K3c: dx_v = (V_v + d I)^-1 (b_v - W_v^T dx_c)       ≙ sparse_matrix_functions.cpp:64-83
+//   apply_update / rho                                                 ≙ Optimizer2.cpp:290-318, LevenbergMarquardtTrustRegionPolicy.cpp:107-113
+#include <cstdio>
+
+#include "kb_device.cuh"
+#include "kb_models.cuh"
+
+namespace kb {
+
+// =========================================================================================================
+// small fixed-size algebra (registers / local arrays)
+// =========================================================================================================
+// sm_kinematics quat2r, scalar-last (Schweizer-Messer/sm_kinematics/src/quaternion_algebra.cpp:77-101); R row-major
+__device__ __forceinline__ void quat2r(const double* __restrict__ q, double R[9]) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = x * x - y * y - z * z + w * w;
+  R[1] = x * y * 2.0 + z * w * 2.0;
+  R[2] = x * z * 2.0 - y * w * 2.0;
+  R[3] = x * y * 2.0 - z * w * 2.0;
+  R[4] = -x * x + y * y - z * z + w * w;
+  R[5] = x * w * 2.0 + y * z * 2.0;
+  R[6] = x * z * 2.0 + y * w * 2.0;
+  R[7] = x * w * (-2.0) + y * z * 2.0;
+  R[8] = -x * x - y * y + z * z + w * w;
+}
+
+// general 3x3 inverse (the reference inverts the whole 4x4 with Eigen's general inverse:
+// BX/src/TransformationExpressionNode.cpp:81,88; for [C t; 0 1] that is [C^-1, -C^-1 t])
+__device__ __forceinline__ void inv3(const double A[9], double B[9]) {
+  const double c00 = A[4] * A[8] - A[5] * A[7];
+  const double c01 = A[5] * A[6] - A[3] * A[8];
+  const double c02 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  const double id = 1.0 / det;
+  B[0] = c00 * id;
+  B[1] = (A[2] * A[7] - A[1] * A[8]) * id;
+  B[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  B[3] = c01 * id;
+  B[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+  B[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  B[6] = c02 * id;
+  B[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+  B[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+
+// boxTimes(T) = [C, -t^x C; 0, C]  (Schweizer-Messer/sm_kinematics/src/transformations.cpp:132-142); 6x6 row-major
+__device__ __forceinline__ void box_times(const double C[9], const double t[3], double o[36]) {
+#pragma unroll
+  for (int i = 0; i < 36; ++i) o[i] = 0.0;
+  // -t^x = [0, t2, -t1; -t2, 0, t0; t1, -t0, 0]
+  const double m[9] = {0.0, t[2], -t[1], -t[2], 0.0, t[0], t[1], -t[0], 0.0};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      o[i * 6 + j] = C[i * 3 + j];
+      o[(i + 3) * 6 + j + 3] = C[i * 3 + j];
+      o[i * 6 + j + 3] = m[i * 3 + 0] * C[0 * 3 + j] + m[i * 3 + 1] * C[1 * 3 + j] + m[i * 3 + 2] * C[2 * 3 + j];
+    }
+}
+
+// [M_q(t) | M_t] = [[-t^x, I], [I, 0]]  (BX/src/TransformationBasic.cpp:48-67); 6x6 row-major, cols 0..2 = q, 3..5 = t
+__device__ __forceinline__ void pose_jac(const double t[3], double o[36]) {
+#pragma unroll
+  for (int i = 0; i < 36; ++i) o[i] = 0.0;
+  o[0 * 6 + 1] = t[2];  o[0 * 6 + 2] = -t[1];
+  o[1 * 6 + 0] = -t[2]; o[1 * 6 + 2] = t[0];
+  o[2 * 6 + 0] = t[1];  o[2 * 6 + 1] = -t[0];
+  o[0 * 6 + 3] = 1.0; o[1 * 6 + 4] = 1.0; o[2 * 6 + 5] = 1.0;
+  o[3 * 6 + 0] = 1.0; o[4 * 6 + 1] = 1.0; o[5 * 6 + 2] = 1.0;
+}
+
+__device__ __forceinline__ void mul6(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ Cc) {
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s += A[i * 6 + k] * B[k * 6 + j];
+      Cc[i * 6 + j] = s;
+    }
+}
+
+// T_cam_w = T_cam_k_cam_0 * inverse(T_v): R_cw (row-major), t_cw.  BX/src/TransformationExpressionNode.cpp:54-59, 86-90
+__device__ __forceinline__ void view_transform(const double* __restrict__ pose7, const double* __restrict__ camT, double Rcw[9], double tcw[3]) {
+  double C[9], Ci[9];
+  quat2r(pose7, C);
+  inv3(C, Ci);
+  const double tx = pose7[4], ty = pose7[5], tz = pose7[6];
+  const double ti[3] = {-(Ci[0] * tx + Ci[1] * ty + Ci[2] * tz), -(Ci[3] * tx + Ci[4] * ty + Ci[5] * tz), -(Ci[6] * tx + Ci[7] * ty + Ci[8] * tz)};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rcw[i * 3 + j] = camT[i * 3 + 0] * Ci[0 * 3 + j] + camT[i * 3 + 1] * Ci[1 * 3 + j] + camT[i * 3 + 2] * Ci[2 * 3 + j];
+    tcw[i] = camT[i * 3 + 0] * ti[0] + camT[i * 3 + 1] * ti[1] + camT[i * 3 + 2] * ti[2] + camT[9 + i];
+  }
+}
+
+// P_v = -boxTimes(inverse(T_v)) [M_q(t_v) | M_t]: d(xi at the Inverse node)/d(q_v, t_v)
+// BX/src/TransformationExpressionNode.cpp:98-101 chained into TransformationBasic.cpp:48-67
+__device__ __forceinline__ void set_pose_jac(const double* __restrict__ pose7, double Pv[36]) {
+  double C[9], Ci[9];
+  quat2r(pose7, C);
+  inv3(C, Ci);
+  const double t[3] = {pose7[4], pose7[5], pose7[6]};
+  const double ti[3] = {-(Ci[0] * t[0] + Ci[1] * t[1] + Ci[2] * t[2]), -(Ci[3] * t[0] + Ci[4] * t[1] + Ci[5] * t[2]), -(Ci[6] * t[0] + Ci[7] * t[1] + Ci[8] * t[2])};
+  double bt[36], M[36];
+  box_times(Ci, ti, bt);
+  pose_jac(t, M);
+  mul6(bt, M, Pv);
+#pragma unroll
+  for (int i = 0; i < 36; ++i) Pv[i] = -Pv[i];
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 6x6 Cholesky (row-major lower) ; returns false if not positive definite
+__device__ __forceinline__ bool chol6(double A[36]) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
+    if (!(d > 0.0)) ok = false;
+    d = sqrt(d);
+    A[j * 6 + j] = d;
+    const double id = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double s = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= A[i * 6 + k] * A[j * 6 + k];
+      A[i * 6 + j] = s * id;
+    }
+  }
+  return ok;
+}
+__device__ __forceinline__ void fwd6(const double* __restrict__ L, double x[6]) {  // L z = x
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = x[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * x[k];
+    x[i] = s / L[i * 6 + i];
+  }
+}
+__device__ __forceinline__ void bwd6(const double* __restrict__ L, double x[6]) {  // L^T z = x
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = x[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k];
+    x[i] = s / L[i * 6 + i];
+  }
+}
+
+// FP64 tensor-core MMA, D(8x8) += A(8x4) B(4x8).  Fragment ownership (PTX ISA, mma.m8n8k4 .f64):
+//   a: row = lane/4, col = lane%4 ; b: row = lane%4, col = lane/4 ; c0,c1: row = lane/4, col = 2*(lane%4) + {0,1}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// =========================================================================================================
+// prep: per camera k, the constants shared by all of its views.
+// =========================================================================================================
+__global__ void prep_kernel(DevProblem p) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p.n_cams) return;
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
+  for (int l = 0; l < k; ++l) {  // T_k = B_{k-1} ... B_0   (CalibrationTools.hpp:405-408)
+    const double* b = p.baselines + l * POSE_STRIDE;
+    double Rl[9], Rn[9], tn[3];
+    quat2r(b, Rl);
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) Rn[i * 3 + j] = Rl[i * 3 + 0] * R[0 * 3 + j] + Rl[i * 3 + 1] * R[1 * 3 + j] + Rl[i * 3 + 2] * R[2 * 3 + j];
+      tn[i] = Rl[i * 3 + 0] * t[0] + Rl[i * 3 + 1] * t[1] + Rl[i * 3 + 2] * t[2] + b[4 + i];
+    }
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+    for (int i = 0; i < 3; ++i) t[i] = tn[i];
+  }
+  double* o = p.camT + k * 12;
+  for (int i = 0; i < 9; ++i) o[i] = R[i];
+  for (int i = 0; i < 3; ++i) o[9 + i] = t[i];
+  // chain rule down the Multiply nodes (BX/src/TransformationExpressionNode.cpp:68-72): outermost baseline first
+  double X[36];
+  for (int i = 0; i < 36; ++i) X[i] = (i % 7 == 0) ? 1.0 : 0.0;
+  for (int l = k - 1; l >= 0; --l) {
+    const double* b = p.baselines + l * POSE_STRIDE;
+    double Rl[9], M[36], A[36], bt[36], Xn[36];
+    quat2r(b, Rl);
+    pose_jac(b + 4, M);
+    mul6(X, M, A);
+    double* Ao = p.camA + ((size_t)k * p.n_cams + l) * 36;
+    for (int i = 0; i < 36; ++i) Ao[i] = A[i];
+    box_times(Rl, b + 4, bt);
+    mul6(X, bt, Xn);
+    for (int i = 0; i < 36; ++i) X[i] = Xn[i];
+  }
+  double* Po = p.camPi + k * 36;
+  for (int i = 0; i < 36; ++i) Po[i] = X[i];
+}
+
+// =========================================================================================================
+// evaluate (residual only)
+// =========================================================================================================
+constexpr int EVAL_THREADS = 256;
+
+template <int MODEL>
+__global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(DevProblem p, const int* __restrict__ view_list, int n_list) {
+  extern __shared__ double smem_target[];
+  for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) smem_target[i] = p.target[i];
+  __syncthreads();
+  using Cam = Camera<MODEL, false>;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int vi = warp; vi < n_list; vi += n_warps) {
+    const int view = view_list[vi];
+    const int set = p.view_set[view], cam = p.view_cam[view];
+    const int b = p.view_begin[view], e = p.view_begin[view + 1];
+    double Rcw[9], tcw[3];
+    view_transform(p.set_poses + (size_t)set * POSE_STRIDE, p.camT + cam * 12, Rcw, tcw);
+    double prm[CAM_PARAM_STRIDE];
+#pragma unroll
+    for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
+    double cost = 0.0;
+    for (int i = b + lane; i < e; i += 32) {
+      const double* pt = smem_target + 3 * p.corner[i];
+      const double pc[3] = {Rcw[0] * pt[0] + Rcw[1] * pt[1] + Rcw[2] * pt[2] + tcw[0], Rcw[3] * pt[0] + Rcw[4] * pt[1] + Rcw[5] * pt[2] + tcw[1],
+                            Rcw[6] * pt[0] + Rcw[7] * pt[1] + Rcw[8] * pt[2] + tcw[2]};
+      Linearisation<Cam::P, Cam::D> L;
+      Cam::eval(prm, pc, L);
+      double e0 = p.y_u[i] - L.y[0], e1 = p.y_v[i] - L.y[1];
+      if (!L.valid) {
+        e0 = 0.0;
+        e1 = 0.0;
+        atomicAdd(p.n_invalid, 1u);
+      }
+      reinterpret_cast<double2*>(p.e)[i] = make_double2(-e0, -e1);
+      cost += e0 * e0 + e1 * e1;
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) p.view_cost[view] = cost;
+  }
+}
+
+// deterministic sum of n doubles -> out[0] (fixed thread/tree order)
+__global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[0] = s;
+  }
+}
+
+// =========================================================================================================
+// linearise: rows of the local design matrix of one term.
+//   a_r = [ J_xi(r, 0..5) | -Ji(r, 0..P-1) | -Jd(r, 0..D-1) | 0.. | e_r ]   (16 columns, e in column 15)
+//   J_xi = -Jp * boxMinus(p_c) = -[Jp | Jp [p_c]x]   (BX/src/HomogeneousExpressionNode.cpp:77-82, transformations.cpp:45-53)
+// =========================================================================================================
+template <int MODEL>
+__device__ __forceinline__ void term_rows(const double* __restrict__ prm, const double Rcw[9], const double tcw[3], const double* __restrict__ pt,
+                                          double yu, double yv, bool active, double a0[GRAM_DIM], double a1[GRAM_DIM], unsigned int* n_invalid) {
+  using Cam = Camera<MODEL, true>;
+  constexpr int P = Cam::P, D = Cam::D;
+  const double pc[3] = {Rcw[0] * pt[0] + Rcw[1] * pt[1] + Rcw[2] * pt[2] + tcw[0], Rcw[3] * pt[0] + Rcw[4] * pt[1] + Rcw[5] * pt[2] + tcw[1],
+                        Rcw[6] * pt[0] + Rcw[7] * pt[1] + Rcw[8] * pt[2] + tcw[2]};
+  Linearisation<P, D> L;
+  Cam::eval(prm, pc, L);
+  if (active && !L.valid) atomicAdd(n_invalid, 1u);
+  const double w = (active && L.valid) ? 1.0 : 0.0;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    double* a = r == 0 ? a0 : a1;
+    const double j0 = L.Jp[r][0], j1 = L.Jp[r][1], j2 = L.Jp[r][2];
+    a[0] = -w * j0;
+    a[1] = -w * j1;
+    a[2] = -w * j2;
+    a[3] = -w * (j1 * pc[2] - j2 * pc[1]);
+    a[4] = -w * (j2 * pc[0] - j0 * pc[2]);
+    a[5] = -w * (j0 * pc[1] - j1 * pc[0]);
+#pragma unroll
+    for (int c = 0; c < P; ++c) a[6 + c] = -w * L.Ji[r][c];
+#pragma unroll
+    for (int c = 0; c < D; ++c) a[6 + P + c] = -w * L.Jd[r][c];
+#pragma unroll
+    for (int c = 6 + P + D; c < E_COL; ++c) a[c] = 0.0;
+    a[E_COL] = w * ((r == 0 ? yu : yv) - L.y[r]);
+  }
+}
+
+// ---- fused linearise + per-view Gram block on DMMA ----------------------------------------------------------
+constexpr int LA_WARPS = 8;
+constexpr int LA_THREADS = LA_WARPS * 32;
+constexpr int XT_LD = 68;  // 64 rows (32 terms x 2) + 4: conflict-free for both the 16-byte stores and the DMMA operand loads
+constexpr int XT_WARP_DOUBLES = GRAM_DIM * XT_LD;
+
+template <int MODEL>
+__global__ void __launch_bounds__(LA_THREADS) linearise_assemble_kernel(DevProblem p, const int* __restrict__ view_list, int n_list) {
+  extern __shared__ __align__(16) double smem[];
+  double* s_target = smem;                                  // n_target*3 (rounded up to even)
+  const int target_doubles = (p.n_target * 3 + 1) & ~1;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  double* XT = smem + target_doubles + wib * XT_WARP_DOUBLES;  // [16 cols][68]
+  for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
+  __syncthreads();
+
+  const int warp = blockIdx.x * LA_WARPS + wib;
+  const int n_warps = gridDim.x * LA_WARPS;
+  const int arow = lane >> 2, acol = lane & 3;
+  for (int vi = warp; vi < n_list; vi += n_warps) {
+    const int view = view_list[vi];
+    const int set = p.view_set[view], cam = p.view_cam[view];
+    const int b = p.view_begin[view], e = p.view_begin[view + 1];
+    double Rcw[9], tcw[3];
+    view_transform(p.set_poses + (size_t)set * POSE_STRIDE, p.camT + cam * 12, Rcw, tcw);
+    double prm[CAM_PARAM_STRIDE];
+#pragma unroll
+    for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
+    double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+    for (int base = b; base < e; base += 32) {
+      const int i = base + lane;
+      const bool active = i < e;
+      const int ii = active ? i : b;
+      double a0[GRAM_DIM], a1[GRAM_DIM];
+      term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * p.corner[ii], p.y_u[ii], p.y_v[ii], active, a0, a1, p.n_invalid);
+#pragma unroll
+      for (int c = 0; c < GRAM_DIM; ++c) *reinterpret_cast<double2*>(XT + c * XT_LD + 2 * lane) = make_double2(a0[c], a1[c]);
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < 16; ++s) {
+        const double x0 = XT[arow * XT_LD + 4 * s + acol];
+        const double x1 = XT[(8 + arow) * XT_LD + 4 * s + acol];
+        dmma(c00[0], c00[1], x0, x0);
+        dmma(c01[0], c01[1], x0, x1);
+        dmma(c11[0], c11[1], x1, x1);
+      }
+      __syncwarp();
+    }
+    double* G = p.G + (size_t)view * GRAM_SIZE;
+    const int gc = 2 * acol;
+    *reinterpret_cast<double2*>(G + arow * GRAM_DIM + gc) = make_double2(c00[0], c00[1]);
+    *reinterpret_cast<double2*>(G + arow * GRAM_DIM + 8 + gc) = make_double2(c01[0], c01[1]);
+    *reinterpret_cast<double2*>(G + (8 + arow) * GRAM_DIM + 8 + gc) = make_double2(c11[0], c11[1]);
+  }
+}
+
+// ---- materialising linearise: e and J in the CCS J^T layout of the reference -----------------------------------
+// Per term two columns of J^T (= rows of J), each W_k = 6 + 6k + P + D values ordered by design-variable block index
+// (lin_off gives the slot of every DV segment for camera k).
+template <int MODEL>
+__global__ void __launch_bounds__(EVAL_THREADS) linearise_materialise_kernel(DevProblem p, const int* __restrict__ view_list, int n_list,
+                                                                              double* __restrict__ jt) {
+  extern __shared__ __align__(16) double smem[];
+  double* s_target = smem;
+  const int target_doubles = (p.n_target * 3 + 1) & ~1;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  double* Mk = smem + target_doubles + wib * 36;  // Pi_k * P_v
+  for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
+  __syncthreads();
+  constexpr int P = model_P(MODEL), D = model_D(MODEL);
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int vi = warp; vi < n_list; vi += n_warps) {
+    const int view = view_list[vi];
+    const int set = p.view_set[view], cam = p.view_cam[view];
+    const int b = p.view_begin[view], e = p.view_begin[view + 1];
+    const double* pose = p.set_poses + (size_t)set * POSE_STRIDE;
+    double Rcw[9], tcw[3];
+    view_transform(pose, p.camT + cam * 12, Rcw, tcw);
+    {
+      double Pv[36];
+      set_pose_jac(pose, Pv);
+      const double* Pi = p.camPi + cam * 36;
+      for (int o = lane; o < 36; o += 32) {
+        const int r = o / 6, c = o % 6;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += Pi[r * 6 + k] * Pv[k * 6 + c];
+        Mk[o] = s;
+      }
+    }
+    __syncwarp();
+    double prm[CAM_PARAM_STRIDE];
+#pragma unroll
+    for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
+    const int* off = p.lin_off + cam * LIN_OFF_STRIDE;
+    const int W = 6 + 6 * cam + P + D;
+    const long long jbase = p.view_jbase[view];
+    for (int i = b + lane; i < e; i += 32) {
+      double a[2][GRAM_DIM];
+      term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * p.corner[i], p.y_u[i], p.y_v[i], true, a[0], a[1], p.n_invalid);
+      reinterpret_cast<double2*>(p.e)[i] = make_double2(-a[0][E_COL], -a[1][E_COL]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double* out = jt + jbase + ((long long)(i - b) * 2 + r) * W;
+        // pose: J_xi * (Pi_k P_v)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s += a[r][k] * Mk[k * 6 + c];
+          out[(c < 3 ? off[0] : off[1] - 3) + c] = s;
+        }
+        for (int j = 0; j < cam; ++j) {  // baselines: J_xi * A_{j,k}
+          const double* A = p.camA + ((size_t)cam * p.n_cams + j) * 36;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s += a[r][k] * __ldg(A + k * 6 + c);
+            out[off[4 + j] + c] = s;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < P; ++c) out[off[2] + c] = a[r][6 + c];
+#pragma unroll
+        for (int c = 0; c < D; ++c) out[off[3] + c] = a[r][6 + P + c];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// =========================================================================================================
+// expand: one warp per synced set.  V_v = sum_k M^T G_xx M, b_v = -sum_k M^T G_xe, W_v rows (intrinsics of cam k:
+// G_cx M ; baseline j: sum_{k>j} A_{j,k}^T G_xx M) with M = Pi_k P_v.
+// =========================================================================================================
+constexpr int EX_WARPS = 4;
+
+__global__ void __launch_bounds__(EX_WARPS * 32) expand_kernel(DevProblem p) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int per_warp = 256 + 36 * 4 + 8 + 36 * p.n_cams;
+  double* sG = smem + (size_t)wib * per_warp;  // 256: full symmetric Gram block
+  double* sP = sG + 256;                       // P_v
+  double* sM = sP + 36;                        // M = Pi_k P_v
+  double* sY = sM + 36;                        // Y = G_xx M
+  double* sV = sY + 36;                        // V accumulator
+  double* sb = sV + 36;                        // b accumulator (6, padded to 8)
+  double* sWb = sb + 8;                        // baseline rows accumulators [n_cams-1][36]
+  const int set = blockIdx.x * EX_WARPS + wib;
+  if (set >= p.n_sets) return;
+  {
+    double Pv[36];
+    set_pose_jac(p.set_poses + (size_t)set * POSE_STRIDE, Pv);
+    for (int o = lane; o < 36; o += 32) { sP[o] = Pv[o]; sV[o] = 0.0; }
+    if (lane < 8) sb[lane] = 0.0;
+    for (int o = lane; o < 36 * (p.n_cams - 1); o += 32) sWb[o] = 0.0;
+  }
+  double* Wout = p.W + (size_t)set * p.n_c * 6;
+  __syncwarp();
+  for (int k = 0; k < p.n_cams; ++k) {
+    const int view = p.set_view[(size_t)set * p.n_cams + k];
+    const int PD = p.cam_P[k] + p.cam_D[k];
+    if (view < 0 || p.view_begin[view + 1] == p.view_begin[view]) {
+      for (int o = lane; o < PD * 6; o += 32) Wout[(size_t)p.intr_off[k] * 6 + o] = 0.0;
+      continue;
+    }
+    const double* G = p.G + (size_t)view * GRAM_SIZE;
+    // symmetric fill: tiles (0,0),(0,1),(1,1) are stored; only the upper triangle of the diagonal tiles is exact-symmetric anyway
+    for (int o = lane; o < 256; o += 32) {
+      const int r = o >> 4, c = o & 15;
+      sG[o] = (r >= 8 && c < 8) ? G[c * GRAM_DIM + r] : G[o];
+    }
+    const double* Pi = p.camPi + k * 36;
+    for (int o = lane; o < 36; o += 32) {
+      const int r = o / 6, c = o % 6;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += Pi[r * 6 + a] * sP[a * 6 + c];
+      sM[o] = s;
+    }
+    __syncwarp();
+    for (int o = lane; o < 36; o += 32) {  // Y = G_xx M
+      const int r = o / 6, c = o % 6;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sG[r * GRAM_DIM + a] * sM[a * 6 + c];
+      sY[o] = s;
+    }
+    __syncwarp();
+    for (int o = lane; o < 36; o += 32) {  // V += M^T Y
+      const int r = o / 6, c = o % 6;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sM[a * 6 + r] * sY[a * 6 + c];
+      sV[o] += s;
+    }
+    if (lane < 6) {  // b_v -= M^T G_xe
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sM[a * 6 + lane] * sG[a * GRAM_DIM + E_COL];
+      sb[lane] -= s;
+    }
+    for (int o = lane; o < PD * 6; o += 32) {  // intrinsics rows: G_cx M
+      const int r = o / 6, c = o % 6;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sG[(6 + r) * GRAM_DIM + a] * sM[a * 6 + c];
+      Wout[(size_t)p.intr_off[k] * 6 + o] = s;
+    }
+    for (int j = 0; j < k; ++j) {  // baseline rows: A_{j,k}^T Y
+      const double* A = p.camA + ((size_t)k * p.n_cams + j) * 36;
+      for (int o = lane; o < 36; o += 32) {
+        const int r = o / 6, c = o % 6;
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s += A[a * 6 + r] * sY[a * 6 + c];
+        sWb[j * 36 + o] += s;
+      }
+    }
+    __syncwarp();
+  }
+  for (int o = lane; o < 36; o += 32) p.V[(size_t)set * 36 + o] = sV[o];
+  if (lane < 6) p.bv[(size_t)set * 6 + lane] = sb[lane];
+  for (int j = 0; j < p.n_cams - 1; ++j)
+    for (int o = lane; o < 36; o += 32) Wout[(size_t)p.base_off[j] * 6 + o] = sWb[j * 36 + o];
+}
+
+// ---- per-camera sum of Gram blocks (deterministic two-stage) ---------------------------------------------------
+constexpr int SG_SLICES = 64;
+__global__ void __launch_bounds__(256) sum_gram_stage1(DevProblem p, const int* __restrict__ cam_view_list, const int* __restrict__ cam_view_begin,
+                                                       double* __restrict__ partial /*[n_cams][SG_SLICES][256]*/) {
+  const int k = blockIdx.y, sl = blockIdx.x;
+  const int b = cam_view_begin[k], e = cam_view_begin[k + 1];
+  const int n = e - b;
+  const int per = (n + SG_SLICES - 1) / SG_SLICES;
+  const int lo = b + sl * per, hi = min(e, lo + per);
+  double s = 0.0;
+  for (int i = lo; i < hi; ++i) {
+    const int view = cam_view_list[i];
+    if (p.view_begin[view + 1] > p.view_begin[view]) s += p.G[(size_t)view * GRAM_SIZE + threadIdx.x];
+  }
+  partial[((size_t)k * SG_SLICES + sl) * 256 + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) sum_gram_stage2(DevProblem p, const double* __restrict__ partial) {
+  const int k = blockIdx.x;
+  double s = 0.0;
+  for (int sl = 0; sl < SG_SLICES; ++sl) s += partial[((size_t)k * SG_SLICES + sl) * 256 + threadIdx.x];
+  p.sumG[(size_t)k * 256 + threadIdx.x] = s;
+}
+
+// ---- camera block U (augmented with b_c as last row/col and the linearisation-point cost in the corner) ----------
+__device__ __forceinline__ double sumg_sym(const double* __restrict__ G, int r, int c) {
+  if (r >= 8 && c < 8) return G[c * GRAM_DIM + r];
+  if ((r < 8) == (c < 8) && r > c) return G[c * GRAM_DIM + r];  // diagonal tiles: use the upper triangle for exact symmetry
+  return G[r * GRAM_DIM + c];
+}
+
+// descriptor of one reduced-system index: which camera-side variable it belongs to
+struct RedIndex {
+  int kind;  // 0 = intrinsics of camera `id` (local column 6 + sub), 1 = baseline `id` (sub in 0..5), 2 = the augmented rhs row
+  int id;
+  int sub;
+};
+__device__ __forceinline__ RedIndex red_index(const DevProblem& p, int i) {
+  RedIndex r;
+  if (i == p.n_c) { r.kind = 2; r.id = 0; r.sub = 0; return r; }
+  if (p.n_cams > 1 && i >= p.base_off[0]) {
+    r.kind = 1; r.id = (i - p.base_off[0]) / 6; r.sub = (i - p.base_off[0]) % 6; return r;
+  }
+  int k = 0;
+  while (k + 1 < p.n_cams && i >= p.intr_off[k + 1]) ++k;
+  r.kind = 0; r.id = k; r.sub = i - p.intr_off[k];
+  return r;
+}
+// "local Jacobian column" of reduced index ri as seen from camera k: a 16-vector c such that J_red = J_local * c.
+// Returns false when camera k does not depend on ri.
+__device__ __forceinline__ bool red_column(const DevProblem& p, const RedIndex& ri, int k, double col[GRAM_DIM]) {
+#pragma unroll
+  for (int a = 0; a < GRAM_DIM; ++a) col[a] = 0.0;
+  if (ri.kind == 0) {
+    if (ri.id != k) return false;
+    col[6 + ri.sub] = 1.0;
+    return true;
+  }
+  if (ri.kind == 1) {
+    if (ri.id >= k) return false;
+    const double* A = p.camA + ((size_t)k * p.n_cams + ri.id) * 36;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) col[a] = A[a * 6 + ri.sub];
+    return true;
+  }
+  col[E_COL] = -1.0;  // rhs = -J^T e
+  return true;
+}
+
+__global__ void __launch_bounds__(256) camera_block_kernel(DevProblem p) {
+  const int n = p.n_aug;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int i = idx / n, j = idx % n;
+  if (i > j) return;
+  const RedIndex ri = red_index(p, i), rj = red_index(p, j);
+  double acc = 0.0;
+  for (int k = 0; k < p.n_cams; ++k) {
+    double ci[GRAM_DIM], cj[GRAM_DIM];
+    if (!red_column(p, ri, k, ci)) continue;
+    if (!red_column(p, rj, k, cj)) continue;
+    const double* G = p.sumG + (size_t)k * 256;
+    double s = 0.0;
+    for (int a = 0; a < GRAM_DIM; ++a) {
+      if (ci[a] == 0.0) continue;
+      double t = 0.0;
+      for (int b = 0; b < GRAM_DIM; ++b) t += sumg_sym(G, a, b) * cj[b];
+      s += ci[a] * t;
+    }
+    acc += s;
+  }
+  p.U[(size_t)i * n + j] = acc;
+  p.U[(size_t)j * n + i] = acc;
+}
+
+// =========================================================================================================
+// Schur complement on the FP64 tensor pipe:  partial = sum_{v in CTA slice} Z_v Z_v^T,  Z_v = [W_v ; b_v^T] L_v^-T,
+// (V_v + d I) = L_v L_v^T.  Two sets per step (K = 12 = 3 k-steps of the m8n8k4 DMMA).
+// =========================================================================================================
+constexpr int SC_LD = 20;  // 12 k-columns + pad; ld % 16 == 4 keeps the operand loads conflict-free
+
+template <int WARPS, int MAX_PAIRS>
+__global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, double damping, double* __restrict__ partials, int sets_per_cta,
+                                                                int* __restrict__ pos_def_flag) {
+  extern __shared__ __align__(16) double smem[];
+  const int n = p.n_aug;
+  const int nt = (n + 7) >> 3;
+  const int n_pad = nt * 8;
+  double* Zs = smem;                  // [n_pad][SC_LD]
+  double* Ls = Zs + n_pad * SC_LD;    // [2][36]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int arow = lane >> 2, acol = lane & 3;
+  const int npairs = nt * (nt + 1) / 2;
+  // tile pairs of this warp (upper triangle, row-major enumeration)
+  int ti[MAX_PAIRS], tj[MAX_PAIRS];
+  double acc[MAX_PAIRS][2];
+#pragma unroll
+  for (int q = 0; q < MAX_PAIRS; ++q) {
+    int pair = warp + q * WARPS;
+    int i = 0;
+    if (pair < npairs) {
+      int rem = pair;
+      while (rem >= nt - i) { rem -= nt - i; ++i; }
+      ti[q] = i;
+      tj[q] = i + rem;
+    } else {
+      ti[q] = -1;
+      tj[q] = -1;
+    }
+    acc[q][0] = 0.0;
+    acc[q][1] = 0.0;
+  }
+  for (int i = tid; i < n_pad * SC_LD; i += blockDim.x) Zs[i] = 0.0;
+  __syncthreads();
+  const int s_lo = blockIdx.x * sets_per_cta, s_hi = min(p.n_sets, s_lo + sets_per_cta);
+  for (int s0 = s_lo; s0 < s_hi; s0 += 2) {
+    if (tid < 2) {  // factor the (up to) two pose blocks of this step
+      const int set = s0 + tid;
+      double L[36];
+      if (set < s_hi) {
+#pragma unroll
+        for (int i = 0; i < 36; ++i) L[i] = p.V[(size_t)set * 36 + i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) L[i * 6 + i] += damping;
+        if (!chol6(L)) *pos_def_flag = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = i + 1; j < 6; ++j) L[i * 6 + j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 36; ++i) p.Lv[(size_t)set * 36 + i] = L[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 36; ++i) L[i] = (i % 7 == 0) ? 1.0 : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 36; ++i) Ls[tid * 36 + i] = L[i];
+    }
+    __syncthreads();
+    for (int o = tid; o < 2 * n; o += blockDim.x) {  // rows of Z for both sets
+      const int which = o / n, r = o % n;
+      const int set = s0 + which;
+      double z[6] = {0, 0, 0, 0, 0, 0};
+      if (set < s_hi) {
+        const double* src = (r < p.n_c) ? (p.W + ((size_t)set * p.n_c + r) * 6) : (p.bv + (size_t)set * 6);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) z[c] = src[c];
+        fwd6(Ls + which * 36, z);
+        if (r == p.n_c) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) p.yv[(size_t)set * 6 + c] = z[c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Zs[r * SC_LD + which * 6 + c] = z[c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+#pragma unroll
+      for (int q = 0; q < MAX_PAIRS; ++q) {
+        if (ti[q] >= 0) {
+          const double a = Zs[(8 * ti[q] + arow) * SC_LD + 4 * kk + acol];
+          const double b = Zs[(8 * tj[q] + arow) * SC_LD + 4 * kk + acol];
+          dmma(acc[q][0], acc[q][1], a, b);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  double* out = partials + (size_t)blockIdx.x * n_pad * n_pad;
+#pragma unroll
+  for (int q = 0; q < MAX_PAIRS; ++q) {
+    if (ti[q] >= 0) {
+      double* o = out + (size_t)(8 * ti[q] + arow) * n_pad + 8 * tj[q] + 2 * acol;
+      *reinterpret_cast<double2*>(o) = make_double2(acc[q][0], acc[q][1]);
+    }
+  }
+}
+
+// Sred = U - sum_partials (fixed order), symmetric, undamped; this rank's contribution to the all-reduce.
+__global__ void __launch_bounds__(256) schur_finalize_kernel(DevProblem p, const double* __restrict__ partials, int n_partials) {
+  const int n = p.n_aug;
+  const int n_pad = ((n + 7) >> 3) * 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int i = idx / n, j = idx % n;
+  if (i > j) return;
+  // within a diagonal tile only the mma's own (i,j) entry is used for i<=j, so the result is exactly symmetric
+  double s = 0.0;
+  for (int c = 0; c < n_partials; ++c) s += partials[(size_t)c * n_pad * n_pad + (size_t)i * n_pad + j];
+  const double v = p.U[(size_t)i * n + j] - s;
+  p.Sred[(size_t)i * n + j] = v;
+  p.Sred[(size_t)j * n + i] = v;
+}
+
+// =========================================================================================================
+// reduced solve: one CTA.  Left-looking Cholesky of the augmented reduced system held packed (lower) in shared
+// memory; the augmented last row comes out as y = L^-1 b, then L^T x = y.
+// =========================================================================================================
+constexpr int RS_THREADS = 1024;
+__device__ __forceinline__ int tri(int i, int k) { return i * (i + 1) / 2 + k; }
+
+__global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping, int* __restrict__ pos_def_flag) {
+  extern __shared__ __align__(16) double Lp[];  // packed lower, n_aug rows
+  __shared__ double s_piv;
+  __shared__ int s_ok;
+  const int n = p.n_aug, nc = p.n_c;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < n * (n + 1) / 2; idx += RS_THREADS) {
+    // idx -> (i,k)
+    int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+    while (tri(i, 0) > idx) --i;
+    while (tri(i + 1, 0) <= idx) ++i;
+    const int k = idx - tri(i, 0);
+    double v = p.Sred[(size_t)i * n + k];
+    if (i == k && i < nc) v += damping;
+    Lp[idx] = v;
+  }
+  if (tid == 0) s_ok = 1;
+  __syncthreads();
+  // 4 threads cooperate on one row
+  const int row_of_thread = tid >> 2, sub = tid & 3;
+  for (int j = 0; j < nc; ++j) {
+    // s_i = A[i][j] - sum_{k<j} L[i][k] L[j][k]  for rows i >= j handled in strides
+    for (int base = j; base < n; base += RS_THREADS / 4) {  // trip count uniform across the warp (shuffles inside)
+      const int i = base + row_of_thread;
+      const bool act = i < n;
+      double s = 0.0;
+      const double* Li = Lp + tri(act ? i : j, 0);
+      const double* Lj = Lp + tri(j, 0);
+      if (act)
+        for (int k = sub; k < j; k += 4) s += Li[k] * Lj[k];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (act && sub == 0) {
+        const double v = Li[j] - s;
+        Lp[tri(i, j)] = v;
+        if (i == j) {
+          s_piv = v;
+          if (!(v > 0.0)) s_ok = 0;
+        }
+      }
+    }
+    __syncthreads();
+    const double piv = sqrt(s_piv);
+    const double ip = 1.0 / piv;
+    for (int i = j + tid; i < n; i += RS_THREADS) Lp[tri(i, j)] = (i == j) ? piv : Lp[tri(i, j)] * ip;
+    __syncthreads();
+  }
+  if (!s_ok) {
+    if (tid == 0) *pos_def_flag = 0;
+  }
+  // back substitution L^T x = y ; y is row nc of the factor (columns 0..nc-1)
+  double* y = Lp + tri(nc, 0);
+  for (int i = nc - 1; i >= 0; --i) {
+    if (tid == 0) y[i] = y[i] / Lp[tri(i, i)];
+    __syncthreads();
+    const double xi = y[i];
+    for (int k = tid; k < i; k += RS_THREADS) y[k] -= Lp[tri(i, k)] * xi;
+    __syncthreads();
+  }
+  for (int i = tid; i < nc; i += RS_THREADS) p.dxc[i] = y[i];
+}
+
+// =========================================================================================================
+// back substitution for the poses + scatter of dx into design-variable order
+// =========================================================================================================
+__global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
+                                                      const int* __restrict__ cam_cols) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < p.n_c; i += blockDim.x) p.dx[cam_cols[i]] = p.dxc[i];
+  if (gw >= p.n_sets) return;
+  const int set = gw;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const double* W = p.W + (size_t)set * p.n_c * 6;
+  for (int i = lane; i < p.n_c; i += 32) {
+    const double x = p.dxc[i];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[c] += W[i * 6 + c] * x;
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) acc[c] = warp_sum(acc[c]);
+  if (lane == 0) {
+    double r[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) r[c] = p.bv[(size_t)set * 6 + c] - acc[c];
+    const double* L = p.Lv + (size_t)set * 36;
+    fwd6(L, r);
+    bwd6(L, r);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      p.dx[set_col_q[set] + c] = r[c];
+      p.dx[set_col_t[set] + c] = r[3 + c];
+    }
+  }
+}
+
+// out[0] = sum_local dx (lambda dx + rhs) [+ lambda |dx_c|^2 once], out[1] = max |dx| over local poses and the shared block
+__global__ void __launch_bounds__(1024) rho_kernel(DevProblem p, double lambda, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
+                                                    int include_shared, double* __restrict__ out) {
+  __shared__ double sh_s[32], sh_m[32];
+  double s = 0.0, m = 0.0;
+  for (int set = threadIdx.x; set < p.n_sets; set += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double d = p.dx[(c < 3 ? set_col_q[set] : set_col_t[set] - 3) + c];
+      s += d * (lambda * d + p.bv[(size_t)set * 6 + c]);
+      m = fmax(m, fabs(d));
+    }
+  }
+  for (int i = threadIdx.x; i < p.n_c; i += blockDim.x) {
+    const double d = p.dxc[i];
+    s += d * p.U[(size_t)i * p.n_aug + p.n_c];  // this rank's partial b_c
+    if (include_shared) s += lambda * d * d;
+    m = fmax(m, fabs(d));
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_m[threadIdx.x >> 5] = m; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = sh_s[threadIdx.x];
+    m = sh_m[threadIdx.x];
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) { out[0] = s; out[1] = m; }
+  }
+}
+
+// sm::kinematics::updateQuat (quaternion_algebra.cpp:200-219, 302-317)
+__device__ __forceinline__ void update_quat(double* q, const double* dq) {
+  const double theta = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2]);
+  double na;
+  if (theta < 1.220703125e-4 /* eps^(1/4) = 2^-13 */) na = 0.5 + (theta * theta) * (1.0 / 48.0);
+  else na = sin(theta * 0.5) / theta;
+  const double d0 = dq[0] * na, d1 = dq[1] * na, d2 = dq[2] * na, ca = cos(theta * 0.5);
+  const double q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+  q[0] = q0 * ca + d0 * q3 - d1 * q2 + d2 * q1;
+  q[1] = q1 * ca + d0 * q2 + d1 * q3 - d2 * q0;
+  q[2] = q2 * ca - d0 * q1 + d1 * q0 + d2 * q3;
+  q[3] = q3 * ca - d0 * q0 - d1 * q1 - d2 * q2;
+}
+
+// backup + update of every design variable (Optimizer2.cpp:290-307; RotationQuaternion.cpp:22-36; EuclideanPoint.cpp:23-32;
+// DesignVariableAdapter.hpp:42-55 over Projection::update / Distortion::update, all of which are parameter += delta)
+__global__ void __launch_bounds__(256) apply_update_kernel(DevProblem p, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
+                                                           double* __restrict__ backup_cam, double* __restrict__ backup_base, double* __restrict__ backup_sets) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < p.n_sets) {
+    double* pose = p.set_poses + (size_t)idx * POSE_STRIDE;
+    double* bk = backup_sets + (size_t)idx * POSE_STRIDE;
+#pragma unroll
+    for (int i = 0; i < POSE_STRIDE; ++i) bk[i] = pose[i];
+    double dq[3], dt[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { dq[c] = p.dx[set_col_q[idx] + c]; dt[c] = p.dx[set_col_t[idx] + c]; }
+    update_quat(pose, dq);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pose[4 + c] += dt[c];
+  }
+  if (blockIdx.x == 0) {
+    for (int k = threadIdx.x; k < p.n_cams; k += blockDim.x) {
+      const int PD = p.cam_P[k] + p.cam_D[k];
+      for (int c = 0; c < CAM_PARAM_STRIDE; ++c) {
+        const double v = p.cam_params[k * CAM_PARAM_STRIDE + c];
+        backup_cam[k * CAM_PARAM_STRIDE + c] = v;
+        if (c < PD) p.cam_params[k * CAM_PARAM_STRIDE + c] = v + p.dxc[p.intr_off[k] + c];
+      }
+    }
+    for (int j = threadIdx.x; j < p.n_cams - 1; j += blockDim.x) {
+      double* b = p.baselines + j * POSE_STRIDE;
+      for (int i = 0; i < POSE_STRIDE; ++i) backup_base[j * POSE_STRIDE + i] = b[i];
+      double dq[3];
+      for (int c = 0; c < 3; ++c) dq[c] = p.dxc[p.base_off[j] + c];
+      update_quat(b, dq);
+      for (int c = 0; c < 3; ++c) b[4 + c] += p.dxc[p.base_off[j] + 3 + c];
+    }
+  }
+}
+
+// =========================================================================================================
+// launchers
+// =========================================================================================================
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+#define KB_LAUNCHED(s) (++*(s).launches)
+
+cudaError_t launch_prep(const DevProblem& p, StreamCtx& s) {
+  prep_kernel<<<1, 32, 0, s.stream>>>(p);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+template <int MODEL>
+static void launch_evaluate_model(const DevProblem& p, const int* list, int n, StreamCtx& s) {
+  if (n <= 0) return;
+  const int warps_per_cta = EVAL_THREADS / 32;
+  const int grid = min((n + warps_per_cta - 1) / warps_per_cta, sm_count() * 8);
+  evaluate_kernel<MODEL><<<grid, EVAL_THREADS, sizeof(double) * p.n_target * 3, s.stream>>>(p, list, n);
+  KB_LAUNCHED(s);
+}
+
+cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int* mb, double* cost_out, StreamCtx& s) {
+  launch_evaluate_model<0>(p, view_list + mb[0], mb[1] - mb[0], s);
+  launch_evaluate_model<1>(p, view_list + mb[1], mb[2] - mb[1], s);
+  launch_evaluate_model<2>(p, view_list + mb[2], mb[3] - mb[2], s);
+  launch_evaluate_model<3>(p, view_list + mb[3], mb[4] - mb[3], s);
+  launch_evaluate_model<4>(p, view_list + mb[4], mb[5] - mb[4], s);
+  sum_kernel<<<1, 1024, 0, s.stream>>>(p.view_cost, p.n_views, cost_out);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+template <int MODEL>
+static cudaError_t launch_la_model(const DevProblem& p, const int* list, int n, StreamCtx& s) {
+  if (n <= 0) return cudaSuccess;
+  const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * XT_WARP_DOUBLES);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(linearise_assemble_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = min((n + LA_WARPS - 1) / LA_WARPS, sm_count() * 3);
+  linearise_assemble_kernel<MODEL><<<grid, LA_THREADS, smem, s.stream>>>(p, list, n);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_linearise_assemble(const DevProblem& p, const int* view_list, const int* mb, StreamCtx& s) {
+  cudaError_t e;
+  if ((e = launch_la_model<0>(p, view_list + mb[0], mb[1] - mb[0], s)) != cudaSuccess) return e;
+  if ((e = launch_la_model<1>(p, view_list + mb[1], mb[2] - mb[1], s)) != cudaSuccess) return e;
+  if ((e = launch_la_model<2>(p, view_list + mb[2], mb[3] - mb[2], s)) != cudaSuccess) return e;
+  if ((e = launch_la_model<3>(p, view_list + mb[3], mb[4] - mb[3], s)) != cudaSuccess) return e;
+  if ((e = launch_la_model<4>(p, view_list + mb[4], mb[5] - mb[4], s)) != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+template <int MODEL>
+static void launch_lm_model(const DevProblem& p, const int* list, int n, double* jt, StreamCtx& s) {
+  if (n <= 0) return;
+  const int warps_per_cta = EVAL_THREADS / 32;
+  const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + warps_per_cta * 36);
+  const int grid = min((n + warps_per_cta - 1) / warps_per_cta, sm_count() * 8);
+  linearise_materialise_kernel<MODEL><<<grid, EVAL_THREADS, smem, s.stream>>>(p, list, n, jt);
+  KB_LAUNCHED(s);
+}
+
+cudaError_t launch_linearise_materialise(const DevProblem& p, const int* view_list, const int* mb, double* jt, StreamCtx& s) {
+  launch_lm_model<0>(p, view_list + mb[0], mb[1] - mb[0], jt, s);
+  launch_lm_model<1>(p, view_list + mb[1], mb[2] - mb[1], jt, s);
+  launch_lm_model<2>(p, view_list + mb[2], mb[3] - mb[2], jt, s);
+  launch_lm_model<3>(p, view_list + mb[3], mb[4] - mb[3], jt, s);
+  launch_lm_model<4>(p, view_list + mb[4], mb[5] - mb[4], jt, s);
+  return cudaGetLastError();
+}
+
+static double* g_sumg_partial = nullptr;
+static size_t g_sumg_partial_bytes = 0;
+
+cudaError_t launch_expand(const DevProblem& p, const int* cam_view_list, const int* cam_view_begin, StreamCtx& s) {
+  const size_t per_warp = 256 + 36 * 4 + 8 + 36 * p.n_cams;
+  const size_t smem = sizeof(double) * per_warp * EX_WARPS;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  if (p.n_sets > 0) {
+    expand_kernel<<<(p.n_sets + EX_WARPS - 1) / EX_WARPS, EX_WARPS * 32, smem, s.stream>>>(p);
+    KB_LAUNCHED(s);
+  }
+  const size_t need = sizeof(double) * (size_t)p.n_cams * SG_SLICES * 256;
+  if (need > g_sumg_partial_bytes) {
+    if (g_sumg_partial) cudaFree(g_sumg_partial);
+    cudaError_t e = cudaMalloc(&g_sumg_partial, need);
+    if (e != cudaSuccess) return e;
+    g_sumg_partial_bytes = need;
+  }
+  sum_gram_stage1<<<dim3(SG_SLICES, p.n_cams), 256, 0, s.stream>>>(p, cam_view_list, cam_view_begin, g_sumg_partial);
+  KB_LAUNCHED(s);
+  sum_gram_stage2<<<p.n_cams, 256, 0, s.stream>>>(p, g_sumg_partial);
+  KB_LAUNCHED(s);
+  const int n2 = p.n_aug * p.n_aug;
+  camera_block_kernel<<<(n2 + 255) / 256, 256, 0, s.stream>>>(p);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+static int schur_sets_per_cta(const DevProblem& p) {
+  const int ctas = sm_count();
+  int per = (p.n_sets + ctas - 1) / ctas;
+  per = (per + 1) & ~1;
+  return per < 2 ? 2 : per;
+}
+int schur_num_partials(const DevProblem& p) {
+  const int per = schur_sets_per_cta(p);
+  const int n = (p.n_sets + per - 1) / per;
+  return n < 1 ? 1 : n;
+}
+size_t schur_partial_stride(const DevProblem& p) {
+  const size_t n_pad = ((p.n_aug + 7) >> 3) * 8;
+  return n_pad * n_pad;
+}
+
+template <int WARPS, int MAX_PAIRS>
+static cudaError_t launch_schur_t(const DevProblem& p, double damping, double* partials, int n_partials, int* flag, StreamCtx& s) {
+  const int n_pad = ((p.n_aug + 7) >> 3) * 8;
+  const size_t smem = sizeof(double) * ((size_t)n_pad * SC_LD + 72);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(schur_kernel<WARPS, MAX_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  schur_kernel<WARPS, MAX_PAIRS><<<n_partials, WARPS * 32, smem, s.stream>>>(p, damping, partials, schur_sets_per_cta(p), flag);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* flag, StreamCtx& s) {
+  cudaError_t e = cudaMemsetAsync(partials, 0, sizeof(double) * schur_partial_stride(p) * n_partials, s.stream);
+  if (e != cudaSuccess) return e;
+  const int nt = (p.n_aug + 7) >> 3;
+  if (nt <= 6) return launch_schur_t<8, 3>(p, damping, partials, n_partials, flag, s);
+  if (nt <= 14) return launch_schur_t<8, 14>(p, damping, partials, n_partials, flag, s);
+  if (nt <= 28) return launch_schur_t<16, 26>(p, damping, partials, n_partials, flag, s);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const double* partials, int n_partials, bool, StreamCtx& s) {
+  const int n2 = p.n_aug * p.n_aug;
+  schur_finalize_kernel<<<(n2 + 255) / 256, 256, 0, s.stream>>>(p, partials, n_partials);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s) {
+  const size_t smem = sizeof(double) * ((size_t)p.n_aug * (p.n_aug + 1) / 2);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  reduced_solve_kernel<<<1, RS_THREADS, smem, s.stream>>>(p, damping, pos_def_flag);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, int*, StreamCtx& s) {
+  const int warps = p.n_sets > 0 ? p.n_sets : 1;
+  backsub_kernel<<<(warps * 32 + 255) / 256, 256, 0, s.stream>>>(p, set_col_q, set_col_t, cam_cols);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int*, int include_shared,
+                                   double* out2, StreamCtx& s) {
+  rho_kernel<<<1, 1024, 0, s.stream>>>(p, lambda, set_col_q, set_col_t, include_shared, out2);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_apply_update(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int*, double* backup_cam, double* backup_base,
+                                double* backup_sets, StreamCtx& s) {
+  const int n = p.n_sets > 0 ? p.n_sets : 1;
+  apply_update_kernel<<<(n + 255) / 256, 256, 0, s.stream>>>(p, set_col_q, set_col_t, backup_cam, backup_base, backup_sets);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+}  // namespace kb

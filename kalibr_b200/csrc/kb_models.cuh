@@ -1,0 +1,256 @@
+// Device camera models: forward projection of a point in the camera frame plus the three Jacobians the
+// reprojection term needs (w.r.t. the point, the projection parameters and the distortion parameters), each
+// evaluated ONCE per term with shared sub-expressions (the reference re-runs the distortion three times).
+//
+// Follows aslam_cv/aslam_cameras/include/aslam/cameras/implementation/ (CAM):
+//   PinholeProjection.hpp:99-145, 326-378     OmniProjection.hpp:118-180, 383-445
+//   ExtendedUnifiedProjection.hpp:133-198, 399-455 (incl. the fu-for-fv quirk Q4)
+//   DoubleSphereProjection.hpp:142-221, 445-503
+//   RadialTangentialDistortion.hpp:28-65, 153-182   EquidistantDistortion.hpp:32-183, 244-273
+// Parameter order per model = kb_camera_model in include/kalibr_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kb_device.cuh"
+
+namespace kb {
+
+
+// Result of linearising one term in the camera frame.  Jp: d(y_hat)/d(p) 2x3 (the 4th homogeneous column is
+// always zero in the reference), Ji: 2xP, Jd: 2xD.  valid = 0 reproduces "projection returned false before
+// writing y_hat" (SURVEY.md Q6): the caller zero-weights the term.
+template <int P, int D>
+struct Linearisation {
+  double y[2];
+  double Jp[2][3];
+  double Ji[2][P > 0 ? P : 1];
+  double Jd[2][D > 0 ? D : 1];
+  bool valid;
+};
+
+// ---- distortions ---------------------------------------------------------------------------------------
+// radtan: in/out m (normalised point), Jm = d(distorted)/d(m) (symmetric 2x2), Jk = d(distorted)/d(k1,k2,p1,p2) at m
+template <bool WITH_JAC>
+__device__ __forceinline__ void radtan(const double* __restrict__ k, double& mx, double& my, double Jm[2][2], double Jk[2][4]) {
+  const double k1 = k[0], k2 = k[1], p1 = k[2], p2 = k[3];
+  const double x = mx, y = my;
+  const double x2 = x * x, y2 = y * y, xy = x * y;
+  const double rho2 = x2 + y2;
+  const double rad = k1 * rho2 + k2 * rho2 * rho2;
+  if (WITH_JAC) {
+    Jm[0][0] = 1.0 + rad + k1 * 2.0 * x2 + k2 * rho2 * 4.0 * x2 + 2.0 * p1 * y + 6.0 * p2 * x;
+    Jm[1][0] = k1 * 2.0 * xy + k2 * 4.0 * rho2 * xy + p1 * 2.0 * x + 2.0 * p2 * y;
+    Jm[0][1] = Jm[1][0];
+    Jm[1][1] = 1.0 + rad + k1 * 2.0 * y2 + k2 * rho2 * 4.0 * y2 + 6.0 * p1 * y + 2.0 * p2 * x;
+    const double r4 = rho2 * rho2;
+    Jk[0][0] = x * rho2; Jk[0][1] = x * r4; Jk[0][2] = 2.0 * xy;         Jk[0][3] = rho2 + 2.0 * x2;
+    Jk[1][0] = y * rho2; Jk[1][1] = y * r4; Jk[1][2] = rho2 + 2.0 * y2;  Jk[1][3] = 2.0 * xy;
+  }
+  mx = x + (x * rad + 2.0 * p1 * xy + p2 * (rho2 + 2.0 * x2));
+  my = y + (y * rad + 2.0 * p2 * xy + p1 * (rho2 + 2.0 * y2));
+}
+
+// equidistant (Kannala-Brandt).  The point Jacobian has no guard at r = 0 (NaN there, as in the reference: Q5).
+template <bool WITH_JAC>
+__device__ __forceinline__ void equidistant(const double* __restrict__ k, double& mx, double& my, double Jm[2][2], double Jk[2][4]) {
+  const double x = mx, y = my;
+  const double r2 = x * x + y * y;
+  const double r = sqrt(r2);
+  const double th = atan(r);
+  const double th2 = th * th, th4 = th2 * th2, th6 = th4 * th2, th8 = th4 * th4;
+  const double poly = k[0] * th2 + k[1] * th4 + k[2] * th6 + k[3] * th8 + 1.0;
+  if (WITH_JAC) {
+    const double inv_r = 1.0 / r;
+    const double th_r = th * inv_r;
+    const double r2p1 = r2 + 1.0;
+    const double th3 = th2 * th, th5 = th4 * th, th7 = th6 * th;
+    // d(poly)/d(v) / v  (v = x or y)
+    const double dpoly = ((k[1] * th3 * 4.0 + k[2] * th5 * 6.0 + k[3] * th7 * 8.0 + k[0] * th * 2.0) * inv_r) / r2p1;
+    const double a = poly / (r2 * r2p1);         // coefficient of v*w
+    const double b = th_r / r2 * poly;           // th / r^3 * poly
+    const double common = th_r * dpoly + a - b;  // multiplies x*x, x*y, y*y
+    Jm[0][0] = th_r * poly + x * x * common;
+    Jm[0][1] = x * y * common;
+    Jm[1][0] = Jm[0][1];
+    Jm[1][1] = th_r * poly + y * y * common;
+    const double pw3 = th3 * inv_r, pw5 = th5 * inv_r, pw7 = th7 * inv_r, pw9 = th8 * th * inv_r;
+    Jk[0][0] = x * pw3; Jk[0][1] = x * pw5; Jk[0][2] = x * pw7; Jk[0][3] = x * pw9;
+    Jk[1][0] = y * pw3; Jk[1][1] = y * pw5; Jk[1][2] = y * pw7; Jk[1][3] = y * pw9;
+  }
+  const double s = (r > 1e-8) ? (th * poly) / r : 1.0;
+  mx = x * s;
+  my = y * s;
+}
+
+// ---- projections ----------------------------------------------------------------------------------------
+template <int MODEL, bool WITH_JAC>
+struct Camera;
+
+// pinhole + (radtan | equi): params fu,fv,cu,cv,d0..d3
+template <int MODEL, bool WITH_JAC>
+struct PinholeCamera {
+  static constexpr int P = 4, D = 4;
+  __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
+    const double fu = prm[0], fv = prm[1], cu = prm[2], cv = prm[3];
+    const double rz = 1.0 / p[2];
+    double mx = p[0] * rz, my = p[1] * rz;
+    double Jm[2][2], Jk[2][4];
+    if (MODEL == PINHOLE_RADTAN)
+      radtan<WITH_JAC>(prm + 4, mx, my, Jm, Jk);
+    else
+      equidistant<WITH_JAC>(prm + 4, mx, my, Jm, Jk);
+    if (WITH_JAC) {
+      const double rz2 = rz * rz;
+      L.Jp[0][0] = fu * Jm[0][0] * rz;
+      L.Jp[0][1] = fu * Jm[0][1] * rz;
+      L.Jp[0][2] = -fu * (p[0] * Jm[0][0] + p[1] * Jm[0][1]) * rz2;
+      L.Jp[1][0] = fv * Jm[1][0] * rz;
+      L.Jp[1][1] = fv * Jm[1][1] * rz;
+      L.Jp[1][2] = -fv * (p[0] * Jm[1][0] + p[1] * Jm[1][1]) * rz2;
+      L.Ji[0][0] = mx; L.Ji[0][1] = 0.0; L.Ji[0][2] = 1.0; L.Ji[0][3] = 0.0;
+      L.Ji[1][0] = 0.0; L.Ji[1][1] = my; L.Ji[1][2] = 0.0; L.Ji[1][3] = 1.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        L.Jd[0][j] = fu * Jk[0][j];
+        L.Jd[1][j] = fv * Jk[1][j];
+      }
+    }
+    L.y[0] = fu * mx + cu;
+    L.y[1] = fv * my + cv;
+    L.valid = true;  // the reference's pinhole never bails out before writing y_hat
+  }
+};
+template <bool WITH_JAC>
+struct Camera<PINHOLE_RADTAN, WITH_JAC> : PinholeCamera<PINHOLE_RADTAN, WITH_JAC> {};
+template <bool WITH_JAC>
+struct Camera<PINHOLE_EQUI, WITH_JAC> : PinholeCamera<PINHOLE_EQUI, WITH_JAC> {};
+
+// omni + radtan: params xi,fu,fv,cu,cv,k1,k2,p1,p2
+template <bool WITH_JAC>
+struct Camera<OMNI_RADTAN, WITH_JAC> {
+  static constexpr int P = 5, D = 4;
+  __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
+    const double xi = prm[0], fu = prm[1], fv = prm[2], cu = prm[3], cv = prm[4];
+    const double d = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    const double fov = (xi <= 1.0) ? xi : 1.0 / xi;
+    L.valid = !(p[2] <= -(fov * d));
+    const double rz = 1.0 / (p[2] + xi * d);
+    double mx = p[0] * rz, my = p[1] * rz;
+    double Jn[2][3];
+    if (WITH_JAC) {
+      const double s = rz * rz / d;
+      Jn[0][0] = s * (d * p[2] + xi * (p[1] * p[1] + p[2] * p[2]));
+      Jn[1][0] = -s * xi * p[0] * p[1];
+      Jn[0][1] = Jn[1][0];
+      Jn[1][1] = s * (d * p[2] + xi * (p[0] * p[0] + p[2] * p[2]));
+      const double s2 = s * (-xi * p[2] - d);
+      Jn[0][2] = p[0] * s2;
+      Jn[1][2] = p[1] * s2;
+    }
+    const double jxi0 = -mx * d * rz, jxi1 = -my * d * rz;  // d(m)/d(xi) at the undistorted point
+    double Jm[2][2], Jk[2][4];
+    radtan<WITH_JAC>(prm + 5, mx, my, Jm, Jk);
+    if (WITH_JAC) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        L.Jp[0][c] = fu * (Jn[0][c] * Jm[0][0] + Jn[1][c] * Jm[0][1]);
+        L.Jp[1][c] = fv * (Jn[0][c] * Jm[1][0] + Jn[1][c] * Jm[1][1]);
+      }
+      L.Ji[0][0] = fu * Jm[0][0] * jxi0 + fu * Jm[0][1] * jxi1;
+      L.Ji[1][0] = fv * Jm[1][0] * jxi0 + fv * Jm[1][1] * jxi1;
+      L.Ji[0][1] = mx; L.Ji[0][2] = 0.0; L.Ji[0][3] = 1.0; L.Ji[0][4] = 0.0;
+      L.Ji[1][1] = 0.0; L.Ji[1][2] = my; L.Ji[1][3] = 0.0; L.Ji[1][4] = 1.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        L.Jd[0][j] = fu * Jk[0][j];
+        L.Jd[1][j] = fv * Jk[1][j];
+      }
+    }
+    L.y[0] = fu * mx + cu;
+    L.y[1] = fv * my + cv;
+  }
+};
+
+// EUCM (no distortion): params alpha,beta,fu,fv,cu,cv
+template <bool WITH_JAC>
+struct Camera<EUCM_NONE, WITH_JAC> {
+  static constexpr int P = 6, D = 0;
+  __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
+    const double al = prm[0], be = prm[1], fu = prm[2], fv = prm[3], cu = prm[4], cv = prm[5];
+    const double x = p[0], y = p[1], z = p[2];
+    const double r2 = x * x + y * y;
+    const double d = sqrt(be * r2 + z * z);
+    const double fov = (al <= 0.5) ? al / (1.0 - al) : (1.0 - al) / al;
+    L.valid = !(z <= -(fov * d));
+    const double norm = al * d + (1.0 - al) * z;
+    const double ni = 1.0 / norm;
+    if (WITH_JAC) {
+      const double di = 1.0 / d;
+      const double denom = ni * ni * di;
+      const double mid = -(al * be * x * y) * denom;
+      const double add = norm * d;
+      const double addz = al * z + (1.0 - al) * d;
+      L.Jp[0][0] = fu * (add - x * x * al * be) * denom;
+      L.Jp[1][0] = fv * mid;
+      L.Jp[0][1] = fu * mid;
+      L.Jp[1][1] = fv * (add - y * y * al * be) * denom;
+      L.Jp[0][2] = -fu * x * addz * denom;
+      L.Jp[1][2] = -fv * y * addz * denom;
+      const double ni2 = ni * ni;
+      const double tx = -fu * x * ni2;
+      const double ty = -fu * y * ni2;  // Q4: the reference scales row 1 with fu as well
+      const double t4 = d - z;
+      const double t5 = 0.5 * al * r2 * di;
+      L.Ji[0][0] = tx * t4; L.Ji[1][0] = ty * t4;
+      L.Ji[0][1] = tx * t5; L.Ji[1][1] = ty * t5;
+      L.Ji[0][2] = x * ni; L.Ji[0][3] = 0.0; L.Ji[0][4] = 1.0; L.Ji[0][5] = 0.0;
+      L.Ji[1][2] = 0.0; L.Ji[1][3] = y * ni; L.Ji[1][4] = 0.0; L.Ji[1][5] = 1.0;
+    }
+    L.y[0] = fu * (x * ni) + cu;
+    L.y[1] = fv * (y * ni) + cv;
+  }
+};
+
+// double sphere (no distortion): params xi,alpha,fu,fv,cu,cv
+template <bool WITH_JAC>
+struct Camera<DS_NONE, WITH_JAC> {
+  static constexpr int P = 6, D = 0;
+  __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
+    const double xi = prm[0], al = prm[1], fu = prm[2], fv = prm[3], cu = prm[4], cv = prm[5];
+    const double x = p[0], y = p[1], z = p[2];
+    const double xx = x * x, yy = y * y;
+    const double r2 = xx + yy;
+    const double d1 = sqrt(r2 + z * z);
+    const double t = (al <= 0.5) ? al / (1.0 - al) : (1.0 - al) / al;
+    const double fov = (t + xi) / sqrt(2.0 * t * xi + xi * xi + 1.0);
+    L.valid = !(z <= -(fov * d1));
+    const double k = xi * d1 + z;
+    const double d2 = sqrt(r2 + k * k);
+    const double norm = al * d2 + (1.0 - al) * k;
+    const double ni = 1.0 / norm;
+    if (WITH_JAC) {
+      const double d1i = 1.0 / d1, d2i = 1.0 / d2;
+      const double ni2 = ni * ni;
+      const double xy = x * y;
+      const double tt2 = xi * z * d1i + 1.0;
+      const double dn = (xi * (1.0 - al) * d1i + al * (xi * k * d1i + 1.0) * d2i) * ni2;
+      const double tmp2 = ((1.0 - al) * tt2 + al * k * tt2 * d2i) * ni2;
+      L.Jp[0][0] = fu * (ni - xx * dn);
+      L.Jp[1][0] = -fv * xy * dn;
+      L.Jp[0][1] = -fu * xy * dn;
+      L.Jp[1][1] = fv * (ni - yy * dn);
+      L.Jp[0][2] = -fu * x * tmp2;
+      L.Jp[1][2] = -fv * y * tmp2;
+      const double t4 = (al - 1.0 - al * k * d2i) * d1 * ni2;
+      const double t5 = (k - d2) * ni2;
+      L.Ji[0][0] = fu * x * t4; L.Ji[1][0] = fv * y * t4;
+      L.Ji[0][1] = fu * x * t5; L.Ji[1][1] = fv * y * t5;
+      L.Ji[0][2] = x * ni; L.Ji[0][3] = 0.0; L.Ji[0][4] = 1.0; L.Ji[0][5] = 0.0;
+      L.Ji[1][2] = 0.0; L.Ji[1][3] = y * ni; L.Ji[1][4] = 0.0; L.Ji[1][5] = 1.0;
+    }
+    L.y[0] = fu * (x * ni) + cu;
+    L.y[1] = fv * (y * ni) + cv;
+  }
+};
+
+}  // namespace kb
