@@ -92,6 +92,11 @@ typedef struct {
   int32_t rank;
   const char* nccl_id;         /* 128 bytes, NULL when n_ranks == 1 */
   int32_t device;              /* CUDA device ordinal */
+  /* pre-sharded input (optional): when n_sets_total > 0 this description holds ONLY this rank's sets, which are the
+   * global sets [set_offset, set_offset + n_sets) of a problem with n_sets_total sets; view_set is local (0-based). */
+  int32_t n_sets_total;
+  int32_t set_offset;
+  int64_t n_terms_total;       /* global number of terms when pre-sharded (for kb_jrows) */
 } kb_problem_desc;
 
 typedef struct kb_handle kb_handle;
@@ -186,9 +191,12 @@ KB_API kb_status kb_reset_state(kb_handle* h);
 /* number of this library's kernels launched since creation (bench.py's gpu_launches) */
 KB_API int64_t kb_kernel_launches(const kb_handle* h);
 /* device time in ms of the last call's stages measured with CUDA events on the library's stream:
- *  [0] evaluate  [1] linearise+assemble  [2] expand  [3] schur  [4] reduced solve  [5] backsub  [6] update */
+ *  [0] evaluate  [1] linearise+assemble  [2] expand  [3] schur  [4] reduced solve  [5] backsub  [6] update
+ *  [7] materialising linearise */
 #define KB_NUM_STAGES 8
 KB_API kb_status kb_get_stage_ms(kb_handle* h, double* ms /*[KB_NUM_STAGES]*/);
+/* accumulated since the last kb_enable_stage_timing(h, 1): total ms and number of timed calls per stage */
+KB_API kb_status kb_get_stage_totals(kb_handle* h, double* total_ms /*[KB_NUM_STAGES]*/, int64_t* calls /*[KB_NUM_STAGES]*/);
 KB_API kb_status kb_enable_stage_timing(kb_handle* h, int32_t on);
 KB_API void* kb_cuda_stream(kb_handle* h); /* cudaStream_t the library launches on */
 

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "kb_default_optimizer_options", "kb_optimize", "kb_get_trace", "kb_set_solver_semantic", "kb_get_error_vector", "kb_get_rhs",
     "kb_linearise", "kb_jacobian_nnz", "kb_get_jacobian_ccs", "kb_get_hessian_blocks", "kb_get_camera_params", "kb_get_baselines",
     "kb_get_set_poses", "kb_set_observations", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
-    "kb_enable_stage_timing", "kb_cuda_stream",
+    "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     L.kb_reset_state.argtypes = [vp]
     L.kb_get_stage_ms.argtypes = [vp, vp]
     L.kb_enable_stage_timing.argtypes = [vp, C.c_int32]
+    L.kb_get_stage_totals.argtypes = [vp, vp, vp]
     L.kb_cuda_stream.argtypes = [vp]
     L.kb_cuda_stream.restype = vp
     for name in EXPORTED_SYMBOLS:
@@ -114,10 +115,12 @@ class B200SchurLinearSystemSolver:
     Method names follow the reference (camelCase in C++, snake_case here); all compute runs in the CUDA library.
     """
 
-    def __init__(self, problem: Problem, n_ranks: int = 1, rank: int = 0, nccl_id: bytes | None = None, device: int = 0):
+    def __init__(self, problem: Problem, n_ranks: int = 1, rank: int = 0, nccl_id: bytes | None = None, device: int = 0,
+                 n_sets_total: int = 0, set_offset: int = 0, n_terms_total: int = 0):
         self._L = load_library()
         self.problem = problem
-        self._desc = problem.desc(n_ranks=n_ranks, rank=rank, nccl_id=nccl_id, device=device)
+        self._desc = problem.desc(n_ranks=n_ranks, rank=rank, nccl_id=nccl_id, device=device,
+                                  n_sets_total=n_sets_total, set_offset=set_offset, n_terms_total=n_terms_total)
         h = C.c_void_p()
         st = self._L.kb_create(C.byref(self._desc), C.byref(h))
         if st != KB_OK:
@@ -270,6 +273,13 @@ class B200SchurLinearSystemSolver:
         ms = np.zeros(KB_NUM_STAGES)
         self._L.kb_get_stage_ms(self._h, _p(ms))
         return dict(zip(STAGE_NAMES, ms.tolist()))
+
+    def stage_totals(self) -> dict:
+        """{stage: (total_ms, calls)} accumulated since enable_stage_timing(True)."""
+        ms = np.zeros(KB_NUM_STAGES)
+        calls = np.zeros(KB_NUM_STAGES, np.int64)
+        self._L.kb_get_stage_totals(self._h, _p(ms), _p(calls))
+        return {n: (float(m), int(k)) for n, m, k in zip(STAGE_NAMES, ms, calls)}
 
     def cuda_stream(self) -> int:
         return int(self._L.kb_cuda_stream(self._h) or 0)

@@ -109,7 +109,7 @@ struct kb_handle {
   double lambda = 0.0;          // _diagonalConditioner (constant)
   double diag_residual = 0.0;   // what the lambda^2 / lambda asymmetry leaves on diag(H) since the last build (Q2)
   int semantic = 0;
-  bool built = false, solved = false, has_backup = false;
+  bool built = false, solved = false, has_backup = false, presharded = false;
   std::vector<double> trace;
   // ---- multi-GPU ----
   NcclComm comm = nullptr;
@@ -117,6 +117,9 @@ struct kb_handle {
   bool timing = false;
   cudaEvent_t ev[2 * KB_NUM_STAGES] = {};
   double stage_ms[KB_NUM_STAGES] = {};
+  double stage_total[KB_NUM_STAGES] = {};
+  long long stage_calls[KB_NUM_STAGES] = {};
+  bool stage_pending[KB_NUM_STAGES] = {};
 };
 
 namespace {
@@ -147,12 +150,26 @@ struct StageTimer {
   kb_handle* h;
   int stage;
   StageTimer(kb_handle* h_, int s) : h(h_), stage(s) { if (h->timing) cudaEventRecord(h->ev[2 * s], h->stream); }
-  ~StageTimer() { if (h->timing) cudaEventRecord(h->ev[2 * stage + 1], h->stream); }
+  ~StageTimer() {
+    if (h->timing) {
+      cudaEventRecord(h->ev[2 * stage + 1], h->stream);
+      h->stage_pending[stage] = true;
+    }
+  }
 };
-void collect_stage(kb_handle* h, int s) {
+// call after a stream synchronisation: folds every finished stage measurement into the totals
+void collect_stages(kb_handle* h) {
   if (!h->timing) return;
-  float ms = 0;
-  if (cudaEventElapsedTime(&ms, h->ev[2 * s], h->ev[2 * s + 1]) == cudaSuccess) h->stage_ms[s] = ms;
+  for (int s = 0; s < KB_NUM_STAGES; ++s) {
+    if (!h->stage_pending[s]) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev[2 * s], h->ev[2 * s + 1]) == cudaSuccess) {
+      h->stage_ms[s] = ms;
+      h->stage_total[s] += ms;
+      h->stage_calls[s] += 1;
+    }
+    h->stage_pending[s] = false;
+  }
 }
 
 kb_status nccl_allreduce(kb_handle* h, void* buf, size_t count, int dtype, int op) {
@@ -260,12 +277,18 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   h->device = d->device;
   h->driver_order = d->driver_order;
   h->n_cams = d->n_cams;
-  h->n_sets_global = d->n_sets;
+  const bool presharded = d->n_sets_total > 0;
+  if (presharded && (d->set_offset < 0 || d->set_offset + d->n_sets > d->n_sets_total))
+    return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "pre-sharded set range outside [0, n_sets_total)");
+  h->n_sets_global = presharded ? d->n_sets_total : d->n_sets;
   h->n_ranks = d->n_ranks;
   h->rank = d->rank;
-  h->n_terms_global = d->n_terms;
+  h->n_terms_global = presharded ? std::max<int64_t>(d->n_terms_total, d->n_terms) : d->n_terms;
+  h->presharded = presharded;
   h->cam_model.assign(d->cam_model, d->cam_model + d->n_cams);
-  shard_range(d->n_sets, d->n_ranks, d->rank, h->set_lo, h->set_hi);
+  if (presharded) { h->set_lo = d->set_offset; h->set_hi = d->set_offset + d->n_sets; }
+  else shard_range(d->n_sets, d->n_ranks, d->rank, h->set_lo, h->set_hi);
+  const int in_set_shift = presharded ? d->set_offset : 0;  // input view_set is local when pre-sharded
   build_dv_layout(h);
   auto cfail = [&](kb_status c, const std::string& m) { g_create_error = m; return c; };
 #define KB_CCUDA(call)                                                                                        \
@@ -288,8 +311,9 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   vb.push_back(0);
   std::vector<int> set_view((size_t)n_local_sets * d->n_cams, -1);
   for (int w = 0; w < d->n_views; ++w) {
-    const int v = d->view_set[w], k = d->view_cam[w];
-    if (v < 0 || v >= d->n_sets || k < 0 || k >= d->n_cams) return cfail(KB_ERR_INVALID_ARGUMENT, "view index out of range");
+    const int k = d->view_cam[w];
+    if (d->view_set[w] < 0 || d->view_set[w] >= d->n_sets || k < 0 || k >= d->n_cams) return cfail(KB_ERR_INVALID_ARGUMENT, "view index out of range");
+    const int v = d->view_set[w] + in_set_shift;
     const int64_t b = d->view_begin[w], e = d->view_begin[w + 1];
     if (b < 0 || e < b || e > d->n_terms) return cfail(KB_ERR_INVALID_ARGUMENT, "view_begin is not a monotone partition of the terms");
     if (v < h->set_lo || v >= h->set_hi) continue;
@@ -394,7 +418,10 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   std::vector<double> base;
   if (d->n_cams > 1) base.assign(d->baselines, d->baselines + (size_t)KB_POSE_STRIDE * (d->n_cams - 1));
   std::vector<double> sets;
-  if (n_local_sets > 0) sets.assign(d->set_poses + (size_t)KB_POSE_STRIDE * h->set_lo, d->set_poses + (size_t)KB_POSE_STRIDE * h->set_hi);
+  if (n_local_sets > 0) {
+    const double* sp = d->set_poses + (presharded ? 0 : (size_t)KB_POSE_STRIDE * h->set_lo);
+    sets.assign(sp, sp + (size_t)KB_POSE_STRIDE * n_local_sets);
+  }
   KB_CCUDA(h->y_u.upload(yu, s));
   KB_CCUDA(h->y_v.upload(yv, s));
   KB_CCUDA(h->corner.upload(corner, s));
@@ -481,7 +508,16 @@ kb_status kb_get_dv_layout(const kb_handle* h, int32_t* column_base, int32_t* di
 }
 int64_t kb_kernel_launches(const kb_handle* h) { return h->launches; }
 void* kb_cuda_stream(kb_handle* h) { return (void*)h->stream; }
-kb_status kb_enable_stage_timing(kb_handle* h, int32_t on) { h->timing = on != 0; return KB_OK; }
+kb_status kb_enable_stage_timing(kb_handle* h, int32_t on) {
+  h->timing = on != 0;
+  if (on)
+    for (int i = 0; i < KB_NUM_STAGES; ++i) { h->stage_total[i] = 0.0; h->stage_calls[i] = 0; h->stage_pending[i] = false; }
+  return KB_OK;
+}
+kb_status kb_get_stage_totals(kb_handle* h, double* total_ms, int64_t* calls) {
+  for (int i = 0; i < KB_NUM_STAGES; ++i) { total_ms[i] = h->stage_total[i]; calls[i] = h->stage_calls[i]; }
+  return KB_OK;
+}
 kb_status kb_get_stage_ms(kb_handle* h, double* ms) {
   for (int i = 0; i < KB_NUM_STAGES; ++i) ms[i] = h->stage_ms[i];
   return KB_OK;
@@ -507,7 +543,7 @@ kb_status kb_evaluate_error(kb_handle* h, int32_t use_m_estimator, double* out_c
   }
   KB_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
-  collect_stage(h, 0);
+  collect_stages(h);
   if (out_cost) *out_cost = h->h_scalars[0];
   return KB_OK;
 }
@@ -527,12 +563,7 @@ kb_status kb_build_system(kb_handle* h, int32_t /*use_m_estimator*/) {
   h->diag_residual = 0.0;  // H.clear(false): BlockCholeskyLinearSystemSolver.cpp:64
   h->built = true;
   h->solved = false;
-  if (h->timing) {
-    KB_CUDA(h, cudaStreamSynchronize(h->stream));
-    collect_stage(h, 1);
-    collect_stage(h, 2);
-  }
-  return KB_OK;
+  return KB_OK;  // stage times are collected at the next synchronising call
 }
 
 kb_status kb_set_constant_conditioner(kb_handle* h, double lambda) {
@@ -593,9 +624,7 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
     }
   }
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
-  collect_stage(h, 3);
-  collect_stage(h, 4);
-  collect_stage(h, 5);
+  collect_stages(h);
   // un-augment: BlockCholesky subtracts lambda, not lambda^2 (BlockCholeskyLinearSystemSolver.cpp:91-97)
   if (h->semantic == 0) h->diag_residual += h->lambda * h->lambda - h->lambda;
   h->solved = true;
@@ -629,7 +658,7 @@ kb_status kb_apply_state_update(kb_handle* h, double* out_max_abs_dx) {
   }
   KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 5, h->scalars.p + 5, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
-  collect_stage(h, 6);
+  collect_stages(h);
   h->has_backup = true;
   if (out_max_abs_dx) *out_max_abs_dx = h->h_scalars[5];
   return KB_OK;
@@ -656,7 +685,8 @@ kb_status kb_reset_state(kb_handle* h) {
 }
 
 kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v) {
-  if (h->n_ranks != 1) return fail(h, KB_ERR_STATE, "kb_set_observations supports a single rank (terms are re-packed per rank at kb_create)");
+  if (h->n_ranks != 1 && !h->presharded)
+    return fail(h, KB_ERR_STATE, "kb_set_observations needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
   KB_CUDA(h, cudaSetDevice(h->device));
   KB_CUDA(h, cudaMemcpyAsync(h->y_u.p, y_u, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(h->y_v.p, y_v, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
@@ -763,7 +793,7 @@ kb_status kb_linearise(kb_handle* h) {
   }
   if (h->timing) {
     KB_CUDA(h, cudaStreamSynchronize(h->stream));
-    collect_stage(h, 7);
+    collect_stages(h);
   }
   return KB_OK;
 }
@@ -894,7 +924,7 @@ kb_status kb_get_baselines(kb_handle* h, double* out) {
 kb_status kb_get_set_poses(kb_handle* h, double* out) {
   KB_CUDA(h, cudaSetDevice(h->device));
   if (h->set_poses.n)
-    KB_CUDA(h, cudaMemcpyAsync(out + (size_t)KB_POSE_STRIDE * h->set_lo, h->set_poses.p, sizeof(double) * h->set_poses.n, cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaMemcpyAsync(out + (h->presharded ? 0 : (size_t)KB_POSE_STRIDE * h->set_lo), h->set_poses.p, sizeof(double) * h->set_poses.n, cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   return KB_OK;
 }

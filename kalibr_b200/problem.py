@@ -46,6 +46,9 @@ class KbProblemDesc(C.Structure):
         ("rank", C.c_int32),
         ("nccl_id", C.c_char_p),
         ("device", C.c_int32),
+        ("n_sets_total", C.c_int32),
+        ("set_offset", C.c_int32),
+        ("n_terms_total", C.c_int64),
     ]
 
 
@@ -136,7 +139,8 @@ class Problem:
         """Dimension of the reduced camera system (intrinsics + baselines)."""
         return int(sum(MODEL_P[m] + MODEL_D[m] for m in self.cam_model) + 6 * (self.n_cams - 1))
 
-    def desc(self, n_ranks: int = 1, rank: int = 0, nccl_id: bytes | None = None, device: int = 0) -> KbProblemDesc:
+    def desc(self, n_ranks: int = 1, rank: int = 0, nccl_id: bytes | None = None, device: int = 0,
+             n_sets_total: int = 0, set_offset: int = 0, n_terms_total: int = 0) -> KbProblemDesc:
         """ctypes view; keeps `self` arrays alive only as long as `self` lives."""
         d = KbProblemDesc()
         d.driver_order = self.driver_order
@@ -160,6 +164,9 @@ class Problem:
         d.rank = rank
         d.nccl_id = nccl_id
         d.device = device
+        d.n_sets_total = n_sets_total
+        d.set_offset = set_offset
+        d.n_terms_total = n_terms_total
         return d
 
     def dv_layout(self):

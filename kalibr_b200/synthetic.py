@@ -178,10 +178,17 @@ def make_problem(
     dropout: float = 0.0,
     perturb: bool = True,
     name: str = "",
+    set_seed: int | None = None,
 ) -> Problem:
     """Generate one problem: dense observations of the 120-corner aprilgrid by every camera in every synced set
-    (optionally with per-corner dropout), measurement noise, and a perturbed initial guess."""
+    (optionally with per-corner dropout), measurement noise, and a perturbed initial guess.
+
+    The rig (baselines, intrinsics and their initial guess) is drawn from `seed`; the synced sets (poses, noise)
+    from `set_seed` (default: seed + 7919), so that ranks of a pre-sharded multi-GPU problem can generate their own
+    sets while sharing the same cameras."""
     rng = np.random.default_rng(seed)
+    rng_cam_guess = np.random.default_rng([seed, 1])
+    set_rng = np.random.default_rng(seed + 7919 if set_seed is None else set_seed)
     models = [int(m) for m in models]
     Cn = len(models)
     pts = aprilgrid_points()
@@ -214,9 +221,9 @@ def make_problem(
     margin = 4.0
     while need > 0:
         B = max(256, int(need * 2.5))
-        depth = rng.uniform(0.4, 0.9, size=B)
-        aa = np.deg2rad(rng.uniform(-25, 25, size=(B, 3)))
-        lat = rng.uniform(-0.35, 0.35, size=(B, 2)) * depth[:, None]
+        depth = set_rng.uniform(0.4, 0.9, size=B)
+        aa = np.deg2rad(set_rng.uniform(-25, 25, size=(B, 3)))
+        lat = set_rng.uniform(-0.35, 0.35, size=(B, 2)) * depth[:, None]
         q_ct = axis_angle_to_quat(aa)  # rotation target -> cam0
         R_ct = quat2r(q_ct)
         # place the target centre at (lat, depth) in cam0
@@ -261,10 +268,10 @@ def make_problem(
             u, v, _ = project(m, truth_params[k], pk)
             u_all[w] = u
             v_all[w] = v
-    u_all += rng.normal(0.0, noise_px, size=u_all.shape)
-    v_all += rng.normal(0.0, noise_px, size=v_all.shape)
+    u_all += set_rng.normal(0.0, noise_px, size=u_all.shape)
+    v_all += set_rng.normal(0.0, noise_px, size=v_all.shape)
     if dropout > 0:
-        keep = rng.uniform(size=(V, T)) >= dropout
+        keep = set_rng.uniform(size=(V, T)) >= dropout
         keep[:, 0] = True  # never an empty view unless asked for explicitly
     else:
         keep = np.ones((V, T), bool)
@@ -282,14 +289,14 @@ def make_problem(
         for k, m in enumerate(models):
             P, D = MODEL_P[m], MODEL_D[m]
             n_shape = {OMNI_RADTAN: 1, EUCM_NONE: 2, DS_NONE: 2}.get(m, 0)  # xi / alpha,beta / xi,alpha lead the vector
-            cam0[k, :n_shape] += rng.normal(0, 0.01, size=n_shape)
-            cam0[k, n_shape:P] *= 1 + rng.uniform(-0.02, 0.02, size=P - n_shape)
-            cam0[k, P : P + D] += rng.normal(0, 0.01, size=D)
+            cam0[k, :n_shape] += rng_cam_guess.normal(0, 0.01, size=n_shape)
+            cam0[k, n_shape:P] *= 1 + rng_cam_guess.uniform(-0.02, 0.02, size=P - n_shape)
+            cam0[k, P : P + D] += rng_cam_guess.normal(0, 0.01, size=D)
         if Cn > 1:
-            base_q0 = quat_mul_update(base_q0, rng.normal(0, np.deg2rad(0.5), size=base_q0[:, :3].shape))
-            base_t0 = base_t0 + rng.normal(0, 0.005, size=base_t0.shape)
-        q0 = quat_mul_update(q0, rng.normal(0, np.deg2rad(0.5), size=q0[:, :3].shape))
-        t0 = t0 + rng.normal(0, 0.005, size=t0.shape)
+            base_q0 = quat_mul_update(base_q0, rng_cam_guess.normal(0, np.deg2rad(0.5), size=base_q0[:, :3].shape))
+            base_t0 = base_t0 + rng_cam_guess.normal(0, 0.005, size=base_t0.shape)
+        q0 = quat_mul_update(q0, set_rng.normal(0, np.deg2rad(0.5), size=q0[:, :3].shape))
+        t0 = t0 + set_rng.normal(0, 0.005, size=t0.shape)
 
     truth = {
         "cam_params": truth_params,
