@@ -146,6 +146,17 @@ struct CameraDesignVariable {
 };
 
 // ---- BX transformation expression nodes -----------------------------------------------------------
+// The reference's nodes cache fixed-size Eigen::Matrix4d members that worker threads of evaluateError overwrite
+// concurrently with identical values (terms of one view share their transformation nodes).  The caches here are
+// heap-backed, so they are overwritten element-wise in place: never re-allocated after construction.
+inline void storeCache(Mat& dst, const Mat& src) {
+  if (dst.r != src.r || dst.c != src.c) {
+    dst = src;
+    return;
+  }
+  for (size_t i = 0; i < src.d.size(); ++i) dst.d[i] = src.d[i];
+}
+
 struct TransformationExpressionNode {
   virtual ~TransformationExpressionNode() {}
   virtual Mat toTransformationMatrix() = 0;
@@ -189,9 +200,11 @@ struct TransformationExpressionNodeMultiply : TransformationExpressionNode {
     T_rhs = rhs->toTransformationMatrix();
   }
   Mat toTransformationMatrix() override {
-    T_lhs = lhs->toTransformationMatrix();
-    T_rhs = rhs->toTransformationMatrix();
-    return T_lhs * T_rhs;
+    const Mat l = lhs->toTransformationMatrix();
+    const Mat r = rhs->toTransformationMatrix();
+    storeCache(T_lhs, l);
+    storeCache(T_rhs, r);
+    return l * r;
   }
   void evaluateJacobians(JacobianContainer& out, const Mat& chain) const override {
     rhs->evaluateJacobians(out, chain * boxTimes(T_lhs));
@@ -207,8 +220,9 @@ struct TransformationExpressionNodeInverse : TransformationExpressionNode {
     T = inverse4(dvTransformation->toTransformationMatrix());
   }
   Mat toTransformationMatrix() override {
-    T = inverse4(dvTransformation->toTransformationMatrix());
-    return T;
+    const Mat inv = inverse4(dvTransformation->toTransformationMatrix());
+    storeCache(T, inv);
+    return inv;
   }
   void evaluateJacobians(JacobianContainer& out, const Mat& chain) const override {
     dvTransformation->evaluateJacobians(out, chain * (-boxTimes(T)));
@@ -225,10 +239,11 @@ struct HomogeneousExpressionNodeMultiply {
     T_lhs = lhs->toTransformationMatrix();
   }
   void toHomogeneous(double out[4]) const {
-    T_lhs = lhs->toTransformationMatrix();
+    const Mat Tl = lhs->toTransformationMatrix();
+    storeCache(T_lhs, Tl);
     for (int i = 0; i < 4; ++i) {
       double s = 0;
-      for (int j = 0; j < 4; ++j) s += T_lhs(i, j) * p_rhs[j];
+      for (int j = 0; j < 4; ++j) s += Tl(i, j) * p_rhs[j];
       out[i] = s;
     }
   }
