@@ -55,7 +55,7 @@ def peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region through NVML (the same counters nvidia-smi's
-    clocks.sm / clocks_event_reasons.* print), every 50 ms from a thread."""
+    clocks.sm / clocks_event_reasons.* print), every 2 ms from a thread."""
 
     def __init__(self, index: int):
         self.index = index
@@ -97,7 +97,7 @@ class ClockSampler:
             except Exception as ex:
                 self.err = str(ex)
                 break
-            self._stop.wait(0.05)
+            self._stop.wait(0.002)
 
     def stop(self):
         self._stop.set()

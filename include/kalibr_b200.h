@@ -159,6 +159,10 @@ KB_API int32_t kb_get_trace(const kb_handle* h, double* out, int32_t max_triples
 /* Solver semantic: 0 = BlockCholesky (default; un-augments with lambda instead of lambda^2),
  * 1 = SparseCholesky (damping appended as columns, no residual: BE/src/SparseCholeskyLinearSystemSolver.cpp:48-66) */
 KB_API kb_status kb_set_solver_semantic(kb_handle* h, int32_t semantic);
+/* Speculative linearisation (default on): kb_evaluate_error runs the fused linearise+assemble kernel (its Gram block yields
+ * the cost, e() is written too), so that a kb_build_system at the same state — the accepted-step case of the LM loop —
+ * only has to reduce the view blocks.  Off: kb_evaluate_error runs the residual-only kernel. Results are identical. */
+KB_API kb_status kb_set_speculative_linearise(kb_handle* h, int32_t on);
 
 /* ---- read-back (parity / results) ----------------------------------------- */
 KB_API kb_status kb_get_error_vector(kb_handle* h, double* e /*[2*local terms]*/);      /* ≙ LinearSystemSolver::e() : -sqrtInvR^T e */

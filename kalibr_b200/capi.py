@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "kb_create", "kb_destroy", "kb_last_error", "kb_nccl_unique_id", "kb_jrows", "kb_jcols", "kb_local_jrows",
     "kb_num_design_variables", "kb_get_dv_layout", "kb_evaluate_error", "kb_build_system", "kb_set_constant_conditioner",
     "kb_solve_system", "kb_lm_rho_denominator", "kb_apply_state_update", "kb_revert_last_state_update",
-    "kb_default_optimizer_options", "kb_optimize", "kb_get_trace", "kb_set_solver_semantic", "kb_get_error_vector", "kb_get_rhs",
+    "kb_default_optimizer_options", "kb_optimize", "kb_get_trace", "kb_set_solver_semantic", "kb_set_speculative_linearise", "kb_get_error_vector", "kb_get_rhs",
     "kb_linearise", "kb_jacobian_nnz", "kb_get_jacobian_ccs", "kb_get_hessian_blocks", "kb_get_camera_params", "kb_get_baselines",
     "kb_get_set_poses", "kb_set_observations", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
@@ -73,6 +73,7 @@ def load_library() -> C.CDLL:
     L.kb_get_trace.argtypes = [vp, vp, C.c_int32]
     L.kb_get_trace.restype = C.c_int32
     L.kb_set_solver_semantic.argtypes = [vp, C.c_int32]
+    L.kb_set_speculative_linearise.argtypes = [vp, C.c_int32]
     L.kb_get_error_vector.argtypes = [vp, vp]
     L.kb_get_rhs.argtypes = [vp, vp]
     L.kb_linearise.argtypes = [vp]
@@ -189,6 +190,9 @@ class B200SchurLinearSystemSolver:
 
     def set_solver_semantic(self, semantic: int):
         self._check(self._L.kb_set_solver_semantic(self._h, semantic), "kb_set_solver_semantic")
+
+    def set_speculative_linearise(self, on: bool):
+        self._check(self._L.kb_set_speculative_linearise(self._h, 1 if on else 0), "kb_set_speculative_linearise")
 
     def optimize(self, options: KbOptimizerOptions | None = None):
         """One Optimizer2::optimize() with the LM policy, state resident on the device."""

@@ -18,6 +18,14 @@ constexpr int POSE_STRIDE = 7;
 constexpr int GRAM_DIM = 16;                       // local columns: xi(6) | proj(P) | dist(D) | pad | e (col 15)
 constexpr int GRAM_SIZE = GRAM_DIM * GRAM_DIM;     // row-major; only the tiles (0,0), (0,1), (1,1) are written
 constexpr int E_COL = 15;
+constexpr int GRAM_TILES = 192;                    // the three stored 8x8 tiles (0,0), (0,1), (1,1) in mma C-fragment order
+constexpr int SETPREP_STRIDE = 48;                 // per set: C^-1 (9), -C^-1 t (3), P_v (36)
+// per-view block written by the fused kernel's epilogue
+constexpr int VB_V = 0;                            // V_k = M^T G_xx M   (36)
+constexpr int VB_B = 36;                           // b_k = -M^T G_xe    (6, padded to 12)
+constexpr int VB_Y = 48;                           // Y_k = G_xx M       (36)
+constexpr int VB_W = 84;                           // W_k = G_cx M       (up to 10 x 6)
+constexpr int VB_STRIDE = 144;
 
 struct DevProblem {
   // ---- structure (immutable after kb_create) ----
@@ -51,11 +59,15 @@ struct DevProblem {
   double* camT;         // [n_cams][12]  R (row-major 9), t (3): T_cam(k)_cam(0)
   double* camPi;        // [n_cams][36]  product of boxTimes(B_{k-1}) ... boxTimes(B_0)
   double* camA;         // [n_cams][n_cams][36]  A_{j,k} at [k][j]: d(xi_k)/d(baseline j) = X_{k,j} [M_q(t_j) | M_t]
+  double* baseBt;       // [n_cams-1][36]  boxTimes(B_j)
+  double* baseM;        // [n_cams-1][36]  [M_q(t_j) | M_t]
   // ---- outputs ----
   double* e;            // [2*n_terms]   -(y - y_hat), the reference's _e
   double* view_cost;    // [n_views]
-  double* G;            // [n_views][256]
-  double* sumG;         // [n_cams][256]
+  double* set_prep;     // [n_sets][48]
+  double* VB;           // [n_views][144] view blocks
+  double* gram_partial; // [n_slices][192]
+  double* sumG;         // [n_cams][256] full symmetric
   double* V;            // [n_sets][36]
   double* bv;           // [n_sets][6]
   double* W;            // [n_sets][n_c][6]
@@ -78,9 +90,12 @@ struct StreamCtx {
 // launchers (kb_kernels.cu); every one returns the cudaGetLastError() of its launches
 cudaError_t launch_prep(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int* model_begin, double* cost_out, StreamCtx& s);
-cudaError_t launch_linearise_assemble(const DevProblem& p, const int* view_list, const int* model_begin, StreamCtx& s);
+int la_grid_warps();
+cudaError_t launch_linearise_assemble(const DevProblem& p, const int* view_list, const int4* slices, const int* slice_model_begin, bool write_e,
+                                      StreamCtx& s);
+cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, double* cost_out, StreamCtx& s);
+cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_linearise_materialise(const DevProblem& p, const int* view_list, const int* model_begin, double* jt_values, StreamCtx& s);
-cudaError_t launch_expand(const DevProblem& p, const int* cam_view_list, const int* cam_view_begin, StreamCtx& s);
 cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_schur_finalize(const DevProblem& p, double damping, const double* partials, int n_partials, bool add_camera_block, StreamCtx& s);
 cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s);

@@ -95,11 +95,14 @@ struct kb_handle {
   std::vector<int> h_cam_cols;
   // ---- device ----
   DevProblem d;
-  DevBuf<double> y_u, y_v, target, cam_params, baselines, set_poses, camT, camPi, camA, e, view_cost, G, sumG, V, bv, W, Lv, yv, U, Sred, dxc, dx;
+  DevBuf<double> y_u, y_v, target, cam_params, baselines, set_poses, camT, camPi, camA, baseBt, baseM, e, view_cost, set_prep, VB, gram_partial, sumG, V, bv, W, Lv, yv, U, Sred, dxc, dx;
   DevBuf<double> init_cam, init_base, init_sets, bk_cam, bk_base, bk_sets, partials, scalars, jt, gather;
   DevBuf<uint16_t> corner;
   DevBuf<int> view_set, view_cam, view_begin, set_view, lin_off, view_list, cam_view_list, cam_view_begin, set_col_q, set_col_t, cam_cols, posdef;
   DevBuf<long long> view_jbase;
+  DevBuf<int4> slices;
+  DevBuf<int> cam_slice_range;
+  int slice_model_begin[KB_NUM_MODELS + 1] = {};
   DevBuf<unsigned int> n_invalid;
   int model_begin[KB_NUM_MODELS + 1] = {};
   int n_partials = 0;
@@ -107,9 +110,13 @@ struct kb_handle {
   int* h_posdef = nullptr;      // pinned
   // ---- solver state ----
   double lambda = 0.0;          // _diagonalConditioner (constant)
+  double rho_lambda = -1.0;     // lambda the cached dx^T(lambda dx + rhs) of the last solve was computed with
   double diag_residual = 0.0;   // what the lambda^2 / lambda asymmetry leaves on diag(H) since the last build (Q2)
   int semantic = 0;
   bool built = false, solved = false, has_backup = false, presharded = false;
+  bool speculative = true;       // kb_evaluate_error linearises too, so that a build at the same state is free
+  long long state_version = 0;   // bumped whenever design variables or observations change
+  long long la_version = -1;     // state the view blocks / Gram sums were computed at
   std::vector<double> trace;
   // ---- multi-GPU ----
   NcclComm comm = nullptr;
@@ -410,6 +417,25 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
       if (vc[w] == k) cam_view_list.push_back(w);
   }
   cam_view_begin[d->n_cams] = (int)cam_view_list.size();
+  // ---- slices of the model/camera-sorted view list: one warp of the fused kernel per slice, never crossing a camera ----
+  std::vector<int4> slices;
+  std::vector<int> cam_slice_range(2 * (size_t)d->n_cams, 0);
+  {
+    const int per = std::max(1, (n_views + la_grid_warps() - 1) / la_grid_warps());
+    int pos = 0;  // position in view_list
+    for (int m = 0; m < KB_NUM_MODELS; ++m) {
+      h->slice_model_begin[m] = (int)slices.size();
+      for (int k = 0; k < d->n_cams; ++k) {
+        if (d->cam_model[k] != m) continue;
+        const int nk = cam_view_begin[k + 1] - cam_view_begin[k];
+        cam_slice_range[2 * k] = (int)slices.size();
+        for (int a = 0; a < nk; a += per) slices.push_back(make_int4(pos + a, pos + std::min(nk, a + per), k, 0));
+        cam_slice_range[2 * k + 1] = (int)slices.size();
+        pos += nk;
+      }
+    }
+    h->slice_model_begin[KB_NUM_MODELS] = (int)slices.size();
+  }
 
   // ---- upload ----
   cudaStream_t s = h->stream;
@@ -435,6 +461,8 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->view_list.upload(view_list, s));
   KB_CCUDA(h->cam_view_list.upload(cam_view_list, s));
   KB_CCUDA(h->cam_view_begin.upload(cam_view_begin, s));
+  KB_CCUDA(h->slices.upload(slices, s));
+  KB_CCUDA(h->cam_slice_range.upload(cam_slice_range, s));
   KB_CCUDA(h->set_col_q.upload(set_col_q, s));
   KB_CCUDA(h->set_col_t.upload(set_col_t, s));
   KB_CCUDA(h->cam_cols.upload(h->h_cam_cols, s));
@@ -451,9 +479,13 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->camT.alloc(C * 12));
   KB_CCUDA(h->camPi.alloc(C * 36));
   KB_CCUDA(h->camA.alloc(C * C * 36));
+  KB_CCUDA(h->baseBt.alloc(C * 36));
+  KB_CCUDA(h->baseM.alloc(C * 36));
   KB_CCUDA(h->e.alloc(2 * (size_t)h->n_terms_local));
   KB_CCUDA(h->view_cost.alloc(n_views));
-  KB_CCUDA(h->G.alloc((size_t)n_views * GRAM_SIZE));
+  KB_CCUDA(h->set_prep.alloc(S * SETPREP_STRIDE));
+  KB_CCUDA(h->VB.alloc((size_t)n_views * VB_STRIDE));
+  KB_CCUDA(h->gram_partial.alloc(slices.size() * GRAM_TILES));
   KB_CCUDA(h->sumG.alloc(C * GRAM_SIZE));
   KB_CCUDA(h->V.alloc(S * 36));
   KB_CCUDA(h->bv.alloc(S * 6));
@@ -469,15 +501,15 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->n_invalid.alloc(1));
   KB_CCUDA(cudaMemsetAsync(h->n_invalid.p, 0, sizeof(unsigned int), s));
   KB_CCUDA(cudaMemsetAsync(h->dx.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)h->jcols), s));
-  KB_CCUDA(cudaMemsetAsync(h->G.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)n_views * GRAM_SIZE), s));
+  KB_CCUDA(cudaMemsetAsync(h->VB.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)n_views * VB_STRIDE), s));
   KB_CCUDA(cudaMemsetAsync(h->e.p, 0, sizeof(double) * std::max<size_t>(1, 2 * (size_t)h->n_terms_local), s));
   KB_CCUDA(cudaMemsetAsync(h->camA.p, 0, sizeof(double) * C * C * 36, s));
   D.y_u = h->y_u.p; D.y_v = h->y_v.p; D.corner = h->corner.p; D.target = h->target.p;
   D.view_set = h->view_set.p; D.view_cam = h->view_cam.p; D.view_begin = h->view_begin.p; D.set_view = h->set_view.p;
   D.lin_off = h->lin_off.p; D.view_jbase = h->view_jbase.p;
   D.cam_params = h->cam_params.p; D.baselines = h->baselines.p; D.set_poses = h->set_poses.p;
-  D.camT = h->camT.p; D.camPi = h->camPi.p; D.camA = h->camA.p;
-  D.e = h->e.p; D.view_cost = h->view_cost.p; D.G = h->G.p; D.sumG = h->sumG.p;
+  D.camT = h->camT.p; D.camPi = h->camPi.p; D.camA = h->camA.p; D.baseBt = h->baseBt.p; D.baseM = h->baseM.p;
+  D.e = h->e.p; D.view_cost = h->view_cost.p; D.set_prep = h->set_prep.p; D.VB = h->VB.p; D.gram_partial = h->gram_partial.p; D.sumG = h->sumG.p;
   D.V = h->V.p; D.bv = h->bv.p; D.W = h->W.p; D.Lv = h->Lv.p; D.yv = h->yv.p;
   D.U = h->U.p; D.Sred = h->Sred.p; D.dxc = h->dxc.p; D.dx = h->dx.p; D.n_invalid = h->n_invalid.p;
   h->n_partials = schur_num_partials(D);
@@ -528,16 +560,33 @@ kb_status kb_set_solver_semantic(kb_handle* h, int32_t semantic) {
   return KB_OK;
 }
 
-kb_status kb_evaluate_error(kb_handle* h, int32_t use_m_estimator, double* out_cost) {
-  if (use_m_estimator) {
-    // kalibr2 never installs an M-estimator on these terms (NoMEstimator weight 1): accepted and ignored like the reference does
+// fused linearise+assemble at the current state: view blocks, per-camera Gram sums, cost (-> scalars[slot]) and, if asked, e()
+static kb_status run_linearise_assemble(kb_handle* h, bool write_e, int cost_slot) {
+  StreamCtx c = ctx(h);
+  KB_CUDA(h, launch_prep(h->d, c));
+  {
+    StageTimer t(h, 1);
+    KB_CUDA(h, launch_linearise_assemble(h->d, h->view_list.p, h->slices.p, h->slice_model_begin, write_e, c));
   }
+  KB_CUDA(h, launch_finalize_gram(h->d, h->cam_slice_range.p, h->scalars.p + cost_slot, c));
+  h->la_version = h->state_version;
+  return KB_OK;
+}
+
+kb_status kb_evaluate_error(kb_handle* h, int32_t /*use_m_estimator: kalibr2 installs none on these terms (weight 1)*/, double* out_cost) {
   KB_CUDA(h, cudaSetDevice(h->device));
   StreamCtx c = ctx(h);
   {
     StageTimer t(h, 0);
-    KB_CUDA(h, launch_prep(h->d, c));
-    KB_CUDA(h, launch_evaluate(h->d, h->view_list.p, h->model_begin, h->scalars.p, c));
+    if (h->speculative) {
+      // The LM loop evaluates the cost of a trial state and, when the step is accepted, linearises at that same state
+      // (Optimizer2.cpp:237 then LevenbergMarquardtTrustRegionPolicy.cpp:72): do both now, the Gram column of e gives the cost.
+      kb_status st = run_linearise_assemble(h, true, 0);
+      if (st != KB_OK) return st;
+    } else {
+      KB_CUDA(h, launch_prep(h->d, c));
+      KB_CUDA(h, launch_evaluate(h->d, h->view_list.p, h->model_begin, h->scalars.p, c));
+    }
     kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
     if (st != KB_OK) return st;
   }
@@ -551,19 +600,23 @@ kb_status kb_evaluate_error(kb_handle* h, int32_t use_m_estimator, double* out_c
 kb_status kb_build_system(kb_handle* h, int32_t /*use_m_estimator*/) {
   KB_CUDA(h, cudaSetDevice(h->device));
   StreamCtx c = ctx(h);
-  {
-    StageTimer t(h, 1);
-    KB_CUDA(h, launch_prep(h->d, c));
-    KB_CUDA(h, launch_linearise_assemble(h->d, h->view_list.p, h->model_begin, c));
+  if (h->la_version != h->state_version) {
+    kb_status st = run_linearise_assemble(h, false, 6);
+    if (st != KB_OK) return st;
   }
   {
     StageTimer t(h, 2);
-    KB_CUDA(h, launch_expand(h->d, h->cam_view_list.p, h->cam_view_begin.p, c));
+    KB_CUDA(h, launch_set_reduce(h->d, c));
   }
   h->diag_residual = 0.0;  // H.clear(false): BlockCholeskyLinearSystemSolver.cpp:64
   h->built = true;
   h->solved = false;
   return KB_OK;  // stage times are collected at the next synchronising call
+}
+
+kb_status kb_set_speculative_linearise(kb_handle* h, int32_t on) {
+  h->speculative = on != 0;
+  return KB_OK;
 }
 
 kb_status kb_set_constant_conditioner(kb_handle* h, double lambda) {
@@ -595,10 +648,15 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
     KB_CUDA(h, launch_backsub(h->d, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->posdef.p, c));
   }
   {
+    // dx^T (lambda dx + rhs) and max|dx| of this solution, so that getLmRho / applyStateUpdate need no further launch
+    KB_CUDA(h, launch_rho_denominator(h->d, h->lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2, c));
     kb_status st = nccl_allreduce(h, h->posdef.p, 1, kNcclInt32, kNcclMin);
     if (st != KB_OK) return st;
+    if ((st = nccl_allreduce(h, h->scalars.p + 2, 1, kNcclFloat64, kNcclSum)) != KB_OK) return st;
+    if ((st = nccl_allreduce(h, h->scalars.p + 3, 1, kNcclFloat64, kNcclMax)) != KB_OK) return st;
   }
   KB_CUDA(h, cudaMemcpyAsync(h->h_posdef, h->posdef.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 2, h->scalars.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (dx) {
     if (gather_dx && h->n_ranks > 1) {
       // poses are disjoint across ranks, the shared block is identical: sum with the shared block kept on rank 0 only
@@ -628,19 +686,24 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
   // un-augment: BlockCholesky subtracts lambda, not lambda^2 (BlockCholeskyLinearSystemSolver.cpp:91-97)
   if (h->semantic == 0) h->diag_residual += h->lambda * h->lambda - h->lambda;
   h->solved = true;
+  h->rho_lambda = h->lambda;
   if (pos_def) *pos_def = h->h_posdef[0];
   return KB_OK;
 }
 
 kb_status kb_lm_rho_denominator(kb_handle* h, double lambda, double* out) {
   if (!h->solved) return fail(h, KB_ERR_STATE, "kb_lm_rho_denominator called before kb_solve_system");
-  KB_CUDA(h, cudaSetDevice(h->device));
-  StreamCtx c = ctx(h);
-  KB_CUDA(h, launch_rho_denominator(h->d, lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2, c));
-  kb_status st = nccl_allreduce(h, h->scalars.p + 2, 1, kNcclFloat64, kNcclSum);
-  if (st != KB_OK) return st;
-  KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 2, h->scalars.p + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (lambda != h->rho_lambda) {  // the solve already computed it for its own lambda (the LM policy's case)
+    KB_CUDA(h, cudaSetDevice(h->device));
+    StreamCtx c = ctx(h);
+    KB_CUDA(h, launch_rho_denominator(h->d, lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 6, c));
+    kb_status st = nccl_allreduce(h, h->scalars.p + 6, 1, kNcclFloat64, kNcclSum);
+    if (st != KB_OK) return st;
+    KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 6, h->scalars.p + 6, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (out) *out = h->h_scalars[6];
+    return KB_OK;
+  }
   if (out) *out = h->h_scalars[2];
   return KB_OK;
 }
@@ -651,16 +714,12 @@ kb_status kb_apply_state_update(kb_handle* h, double* out_max_abs_dx) {
   StreamCtx c = ctx(h);
   {
     StageTimer t(h, 6);
-    KB_CUDA(h, launch_rho_denominator(h->d, 0.0, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, 0, h->scalars.p + 4, c));
-    kb_status st = nccl_allreduce(h, h->scalars.p + 5, 1, kNcclFloat64, kNcclMax);
-    if (st != KB_OK) return st;
     KB_CUDA(h, launch_apply_update(h->d, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->bk_cam.p, h->bk_base.p, h->bk_sets.p, c));
   }
-  KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 5, h->scalars.p + 5, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  KB_CUDA(h, cudaStreamSynchronize(h->stream));
-  collect_stages(h);
+  // no synchronisation needed: max|dx| came back with the solve; the next call on this stream sees the updated state
   h->has_backup = true;
-  if (out_max_abs_dx) *out_max_abs_dx = h->h_scalars[5];
+  ++h->state_version;
+  if (out_max_abs_dx) *out_max_abs_dx = h->h_scalars[3];
   return KB_OK;
 }
 
@@ -670,6 +729,7 @@ kb_status kb_revert_last_state_update(kb_handle* h) {
   KB_CUDA(h, cudaMemcpyAsync(h->cam_params.p, h->bk_cam.p, sizeof(double) * h->cam_params.n, cudaMemcpyDeviceToDevice, h->stream));
   if (h->baselines.n) KB_CUDA(h, cudaMemcpyAsync(h->baselines.p, h->bk_base.p, sizeof(double) * h->baselines.n, cudaMemcpyDeviceToDevice, h->stream));
   if (h->set_poses.n) KB_CUDA(h, cudaMemcpyAsync(h->set_poses.p, h->bk_sets.p, sizeof(double) * h->set_poses.n, cudaMemcpyDeviceToDevice, h->stream));
+  ++h->state_version;
   return KB_OK;
 }
 
@@ -679,6 +739,7 @@ kb_status kb_reset_state(kb_handle* h) {
   if (h->baselines.n) KB_CUDA(h, cudaMemcpyAsync(h->baselines.p, h->init_base.p, sizeof(double) * h->baselines.n, cudaMemcpyDeviceToDevice, h->stream));
   if (h->set_poses.n) KB_CUDA(h, cudaMemcpyAsync(h->set_poses.p, h->init_sets.p, sizeof(double) * h->set_poses.n, cudaMemcpyDeviceToDevice, h->stream));
   h->built = h->solved = h->has_backup = false;
+  ++h->state_version;
   h->diag_residual = 0.0;
   h->lambda = 0.0;
   return KB_OK;
@@ -690,6 +751,7 @@ kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v
   KB_CUDA(h, cudaSetDevice(h->device));
   KB_CUDA(h, cudaMemcpyAsync(h->y_u.p, y_u, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(h->y_v.p, y_v, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
+  ++h->state_version;
   return KB_OK;
 }
 
@@ -774,10 +836,18 @@ kb_status kb_get_rhs(kb_handle* h, double* rhs) {
   } else if ((st = download(h, h->U, U)) != KB_OK) return st;
   std::fill(rhs, rhs + h->jcols, 0.0);
   const int n = h->d.n_aug;
-  for (int i = 0; i < h->d.n_c; ++i) rhs[h->h_cam_cols[i]] = U[(size_t)i * n + h->d.n_c];
+  if (h->rank == 0 || h->n_ranks == 1)
+    for (int i = 0; i < h->d.n_c; ++i) rhs[h->h_cam_cols[i]] = U[(size_t)i * n + h->d.n_c];
   for (int lv = 0; lv < h->d.n_sets; ++lv) {
     const int cq = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv)], ct = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv) + 1];
     for (int c = 0; c < 3; ++c) { rhs[cq + c] = bv[(size_t)lv * 6 + c]; rhs[ct + c] = bv[(size_t)lv * 6 + 3 + c]; }
+  }
+  if (h->n_ranks > 1) {  // pose segments are disjoint across ranks, the camera segment was kept on rank 0 only: sum = full vector
+    KB_CUDA(h, h->gather.alloc((size_t)h->jcols));
+    KB_CUDA(h, cudaMemcpyAsync(h->gather.p, rhs, sizeof(double) * h->jcols, cudaMemcpyHostToDevice, h->stream));
+    if ((st = nccl_allreduce(h, h->gather.p, (size_t)h->jcols, kNcclFloat64, kNcclSum)) != KB_OK) return st;
+    KB_CUDA(h, cudaMemcpyAsync(rhs, h->gather.p, sizeof(double) * h->jcols, cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   return KB_OK;
 }

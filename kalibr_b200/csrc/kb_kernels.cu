@@ -7,8 +7,8 @@
 //                                                                     ≙ ReprojectionError.hpp:63-77 + JacobianContainer.cpp:103-167
 //   linearise_materialise  K1 with J written out in the reference's CCS J^T layout
 //                                                                     ≙ CompressedColumnJacobianTransposeBuilder.hpp:59-100
-//   expand          per set: V_v, b_v, W_v from the Gram blocks       ≙ sparse_block_matrix.hpp:121-143 (block += J1^T J2)
-//   sum_gram/camera_block  U, b_c
+//   set_reduce      per set: V_v, b_v, W_v from the view blocks       ≙ sparse_block_matrix.hpp:121-143 (block += J1^T J2)
+//   finalize_gram/camera_block  U, b_c, cost
 //   schur           K3a: S = U - sum_v W_v (V_v + d I)^-1 W_v^T on DMMA ≙ BE/src/sparse_matrix_functions.cpp:8-60
 //   reduced_solve   K3b: dense Cholesky of the reduced system          ≙ linear_solver_cholmod.h:70-112
 //   backsub         K3c: dx_v = (V_v + d I)^-1 (b_v - W_v^T dx_c)       ≙ sparse_matrix_functions.cpp:64-83
@@ -215,6 +215,47 @@ __global__ void prep_kernel(DevProblem p) {
   }
   double* Po = p.camPi + k * 36;
   for (int i = 0; i < 36; ++i) Po[i] = X[i];
+  if (k + 1 < p.n_cams) {  // per baseline k: boxTimes(B_k) and [M_q(t_k) | M_t] for the set reduction's recurrence
+    const double* b = p.baselines + k * POSE_STRIDE;
+    double Rl[9], M[36], bt[36];
+    quat2r(b, Rl);
+    pose_jac(b + 4, M);
+    box_times(Rl, b + 4, bt);
+    for (int i = 0; i < 36; ++i) {
+      p.baseBt[k * 36 + i] = bt[i];
+      p.baseM[k * 36 + i] = M[i];
+    }
+  }
+}
+
+// per synced set: inverse pose (C^-1, -C^-1 t) and P_v, shared by the views of every camera of the set
+__global__ void __launch_bounds__(128) set_prep_kernel(DevProblem p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.n_sets) return;
+  const double* pose = p.set_poses + (size_t)s * POSE_STRIDE;
+  double C[9], Ci[9];
+  quat2r(pose, C);
+  inv3(C, Ci);
+  const double t[3] = {pose[4], pose[5], pose[6]};
+  const double ti[3] = {-(Ci[0] * t[0] + Ci[1] * t[1] + Ci[2] * t[2]), -(Ci[3] * t[0] + Ci[4] * t[1] + Ci[5] * t[2]), -(Ci[6] * t[0] + Ci[7] * t[1] + Ci[8] * t[2])};
+  double* o = p.set_prep + (size_t)s * SETPREP_STRIDE;
+  for (int i = 0; i < 9; ++i) o[i] = Ci[i];
+  for (int i = 0; i < 3; ++i) o[9 + i] = ti[i];
+  double bt[36], M[36], Pv[36];
+  box_times(Ci, ti, bt);
+  pose_jac(t, M);
+  mul6(bt, M, Pv);
+  for (int i = 0; i < 36; ++i) o[12 + i] = -Pv[i];
+}
+
+// T_cam_w from the per-set inverse pose and the per-camera chain
+__device__ __forceinline__ void view_transform_prepped(const double* __restrict__ sp, const double* __restrict__ camT, double Rcw[9], double tcw[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rcw[i * 3 + j] = camT[i * 3 + 0] * sp[0 * 3 + j] + camT[i * 3 + 1] * sp[1 * 3 + j] + camT[i * 3 + 2] * sp[2 * 3 + j];
+    tcw[i] = camT[i * 3 + 0] * sp[9] + camT[i * 3 + 1] * sp[10] + camT[i * 3 + 2] * sp[11] + camT[9 + i];
+  }
 }
 
 // =========================================================================================================
@@ -284,88 +325,180 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ v,
 template <int MODEL>
 __device__ __forceinline__ void term_rows(const double* __restrict__ prm, const double Rcw[9], const double tcw[3], const double* __restrict__ pt,
                                           double yu, double yv, bool active, double a0[GRAM_DIM], double a1[GRAM_DIM], unsigned int* n_invalid) {
-  using Cam = Camera<MODEL, true>;
+  using Cam = Camera<MODEL, true, true>;  // negated Jacobians: e = y - y_hat
   constexpr int P = Cam::P, D = Cam::D;
   const double pc[3] = {Rcw[0] * pt[0] + Rcw[1] * pt[1] + Rcw[2] * pt[2] + tcw[0], Rcw[3] * pt[0] + Rcw[4] * pt[1] + Rcw[5] * pt[2] + tcw[1],
                         Rcw[6] * pt[0] + Rcw[7] * pt[1] + Rcw[8] * pt[2] + tcw[2]};
   Linearisation<P, D> L;
   Cam::eval(prm, pc, L);
   if (active && !L.valid) atomicAdd(n_invalid, 1u);
-  const double w = (active && L.valid) ? 1.0 : 0.0;
+  const bool keep = active && L.valid;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     double* a = r == 0 ? a0 : a1;
-    const double j0 = L.Jp[r][0], j1 = L.Jp[r][1], j2 = L.Jp[r][2];
-    a[0] = -w * j0;
-    a[1] = -w * j1;
-    a[2] = -w * j2;
-    a[3] = -w * (j1 * pc[2] - j2 * pc[1]);
-    a[4] = -w * (j2 * pc[0] - j0 * pc[2]);
-    a[5] = -w * (j0 * pc[1] - j1 * pc[0]);
+    const double j0 = L.Jp[r][0], j1 = L.Jp[r][1], j2 = L.Jp[r][2];  // = -Jp
+    a[0] = j0;
+    a[1] = j1;
+    a[2] = j2;
+    a[3] = j1 * pc[2] - j2 * pc[1];
+    a[4] = j2 * pc[0] - j0 * pc[2];
+    a[5] = j0 * pc[1] - j1 * pc[0];
 #pragma unroll
-    for (int c = 0; c < P; ++c) a[6 + c] = -w * L.Ji[r][c];
+    for (int c = 0; c < P; ++c) a[6 + c] = L.Ji[r][c];
 #pragma unroll
-    for (int c = 0; c < D; ++c) a[6 + P + c] = -w * L.Jd[r][c];
+    for (int c = 0; c < D; ++c) a[6 + P + c] = L.Jd[r][c];
 #pragma unroll
     for (int c = 6 + P + D; c < E_COL; ++c) a[c] = 0.0;
-    a[E_COL] = w * ((r == 0 ? yu : yv) - L.y[r]);
+    a[E_COL] = (r == 0 ? yu : yv) - L.y[r];
+#pragma unroll
+    for (int c = 0; c < GRAM_DIM; ++c) a[c] = keep ? a[c] : 0.0;  // zero weight: selects, no FP64 work
   }
 }
 
-// ---- fused linearise + per-view Gram block on DMMA ----------------------------------------------------------
+// ---- fused linearise + assemble on DMMA ----------------------------------------------------------------------
+// One warp walks a slice of the camera-sorted view list (a slice never crosses a camera).  Per view: 32-term chunks are
+// linearised (lane per term), staged transposed in shared memory and reduced into the 16x16 Gram block G with
+// mma.sync.m8n8k4.f64; the next chunk's observations are prefetched before the DMMA phase.  The epilogue turns G into the
+// view block the set reduction needs (V_k = M^T G_xx M, b_k = -M^T G_xe, Y_k = G_xx M, W_k = G_cx M with M = Pi_k P_v)
+// and adds G to the slice's per-camera Gram sum, so G itself never goes to HBM.
 constexpr int LA_WARPS = 8;
 constexpr int LA_THREADS = LA_WARPS * 32;
 constexpr int XT_LD = 68;  // 64 rows (32 terms x 2) + 4: conflict-free for both the 16-byte stores and the DMMA operand loads
 constexpr int XT_WARP_DOUBLES = GRAM_DIM * XT_LD;
+constexpr int LA_WARP_DOUBLES = XT_WARP_DOUBLES + GRAM_TILES + 4 * 36;  // XT | slice Gram sum | Pi, P_v, M, Y
 
-template <int MODEL>
-__global__ void __launch_bounds__(LA_THREADS) linearise_assemble_kernel(DevProblem p, const int* __restrict__ view_list, int n_list) {
+template <int MODEL, bool WRITE_E>
+__global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevProblem p, const int* __restrict__ view_list,
+                                                                            const int4* __restrict__ slices, int slice_lo, int slice_hi) {
   extern __shared__ __align__(16) double smem[];
   double* s_target = smem;                                  // n_target*3 (rounded up to even)
   const int target_doubles = (p.n_target * 3 + 1) & ~1;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  double* XT = smem + target_doubles + wib * XT_WARP_DOUBLES;  // [16 cols][68]
+  double* XT = smem + target_doubles + wib * LA_WARP_DOUBLES;  // [16 cols][68]; reused as G[16][16] in the epilogue
+  double* sG = XT + XT_WARP_DOUBLES;                           // [3][64] slice sum of the three stored tiles
+  double* sPi = sG + GRAM_TILES;
+  double* sP = sPi + 36;
+  double* sM = sP + 36;
+  double* sY = sM + 36;
   for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
   __syncthreads();
+  constexpr int PD = model_P(MODEL) + model_D(MODEL);
 
   const int warp = blockIdx.x * LA_WARPS + wib;
   const int n_warps = gridDim.x * LA_WARPS;
   const int arow = lane >> 2, acol = lane & 3;
-  for (int vi = warp; vi < n_list; vi += n_warps) {
-    const int view = view_list[vi];
-    const int set = p.view_set[view], cam = p.view_cam[view];
-    const int b = p.view_begin[view], e = p.view_begin[view + 1];
-    double Rcw[9], tcw[3];
-    view_transform(p.set_poses + (size_t)set * POSE_STRIDE, p.camT + cam * 12, Rcw, tcw);
+  const int gc = 2 * acol;
+  for (int sl = slice_lo + warp; sl < slice_hi; sl += n_warps) {
+    const int4 S = slices[sl];
+    const int cam = S.z;
     double prm[CAM_PARAM_STRIDE];
 #pragma unroll
     for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
-    double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
-    for (int base = b; base < e; base += 32) {
-      const int i = base + lane;
-      const bool active = i < e;
-      const int ii = active ? i : b;
-      double a0[GRAM_DIM], a1[GRAM_DIM];
-      term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * p.corner[ii], p.y_u[ii], p.y_v[ii], active, a0, a1, p.n_invalid);
+    double camT[12];
 #pragma unroll
-      for (int c = 0; c < GRAM_DIM; ++c) *reinterpret_cast<double2*>(XT + c * XT_LD + 2 * lane) = make_double2(a0[c], a1[c]);
+    for (int i = 0; i < 12; ++i) camT[i] = p.camT[cam * 12 + i];
+    for (int o = lane; o < 36; o += 32) sPi[o] = p.camPi[cam * 36 + o];
+    for (int o = lane; o < GRAM_TILES; o += 32) sG[o] = 0.0;
+    __syncwarp();
+    for (int vi = S.x; vi < S.y; ++vi) {
+      const int view = view_list[vi];
+      const int set = p.view_set[view];
+      const int b = p.view_begin[view], e = p.view_begin[view + 1];
+      const double* sp = p.set_prep + (size_t)set * SETPREP_STRIDE;
+      double Rcw[9], tcw[3];
+      view_transform_prepped(sp, camT, Rcw, tcw);
+      double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+      // software prefetch of the chunk's observations
+      int i = b + lane;
+      bool active = i < e;
+      int ii = active ? i : b;
+      double yu = 0.0, yv = 0.0;
+      int cid = 0;
+      if (b < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+      for (int base = b; base < e; base += 32) {
+        const double cyu = yu, cyv = yv;
+        const int ccid = cid;
+        const bool cactive = active;
+        const int ci = i;
+        i = base + 32 + lane;
+        active = i < e;
+        ii = active ? i : b;
+        if (base + 32 < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+        double a0[GRAM_DIM], a1[GRAM_DIM];
+        term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, cactive, a0, a1, p.n_invalid);
+        if (WRITE_E && cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-a0[E_COL], -a1[E_COL]);
+#pragma unroll
+        for (int c = 0; c < GRAM_DIM; ++c) *reinterpret_cast<double2*>(XT + c * XT_LD + 2 * lane) = make_double2(a0[c], a1[c]);
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+          const double x0 = XT[arow * XT_LD + 4 * s + acol];
+          const double x1 = XT[(8 + arow) * XT_LD + 4 * s + acol];
+          dmma(c00[0], c00[1], x0, x0);
+          dmma(c01[0], c01[1], x0, x1);
+          dmma(c11[0], c11[1], x1, x1);
+        }
+        __syncwarp();
+      }
+      // ---- epilogue: G (full symmetric 16x16, ld 16) in shared memory, slice sum, view block ----
+      double* G = XT;
+      *reinterpret_cast<double2*>(G + arow * GRAM_DIM + gc) = make_double2(c00[0], c00[1]);
+      *reinterpret_cast<double2*>(G + arow * GRAM_DIM + 8 + gc) = make_double2(c01[0], c01[1]);
+      G[(8 + gc) * GRAM_DIM + arow] = c01[0];
+      G[(8 + gc + 1) * GRAM_DIM + arow] = c01[1];
+      *reinterpret_cast<double2*>(G + (8 + arow) * GRAM_DIM + 8 + gc) = make_double2(c11[0], c11[1]);
+      {
+        double2* g2 = reinterpret_cast<double2*>(sG);
+        double2 t0 = g2[lane], t1 = g2[32 + lane], t2 = g2[64 + lane];
+        t0.x += c00[0]; t0.y += c00[1]; t1.x += c01[0]; t1.y += c01[1]; t2.x += c11[0]; t2.y += c11[1];
+        g2[lane] = t0; g2[32 + lane] = t1; g2[64 + lane] = t2;
+      }
+      for (int o = lane; o < 36; o += 32) sP[o] = sp[12 + o];
       __syncwarp();
+      for (int o = lane; o < 36; o += 32) {  // M = Pi_k P_v
+        const int r = o / 6, c = o % 6;
+        double s = 0.0;
 #pragma unroll
-      for (int s = 0; s < 16; ++s) {
-        const double x0 = XT[arow * XT_LD + 4 * s + acol];
-        const double x1 = XT[(8 + arow) * XT_LD + 4 * s + acol];
-        dmma(c00[0], c00[1], x0, x0);
-        dmma(c01[0], c01[1], x0, x1);
-        dmma(c11[0], c11[1], x1, x1);
+        for (int a = 0; a < 6; ++a) s += sPi[r * 6 + a] * sP[a * 6 + c];
+        sM[o] = s;
+      }
+      __syncwarp();
+      double* vb = p.VB + (size_t)view * VB_STRIDE;
+      for (int o = lane; o < 36; o += 32) {  // Y = G_xx M
+        const int r = o / 6, c = o % 6;
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s += G[r * GRAM_DIM + a] * sM[a * 6 + c];
+        sY[o] = s;
+        vb[VB_Y + o] = s;
+      }
+      for (int o = lane; o < PD * 6; o += 32) {  // W_k = G_cx M
+        const int r = o / 6, c = o % 6;
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s += G[(6 + r) * GRAM_DIM + a] * sM[a * 6 + c];
+        vb[VB_W + o] = s;
+      }
+      if (lane < 6) {  // b_k = -M^T G_xe
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s += sM[a * 6 + lane] * G[a * GRAM_DIM + E_COL];
+        vb[VB_B + lane] = -s;
+      }
+      __syncwarp();
+      for (int o = lane; o < 36; o += 32) {  // V_k = M^T Y
+        const int r = o / 6, c = o % 6;
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s += sM[a * 6 + r] * sY[a * 6 + c];
+        vb[VB_V + o] = s;
       }
       __syncwarp();
     }
-    double* G = p.G + (size_t)view * GRAM_SIZE;
-    const int gc = 2 * acol;
-    *reinterpret_cast<double2*>(G + arow * GRAM_DIM + gc) = make_double2(c00[0], c00[1]);
-    *reinterpret_cast<double2*>(G + arow * GRAM_DIM + 8 + gc) = make_double2(c01[0], c01[1]);
-    *reinterpret_cast<double2*>(G + (8 + arow) * GRAM_DIM + 8 + gc) = make_double2(c11[0], c11[1]);
+    double* out = p.gram_partial + (size_t)sl * GRAM_TILES;
+    for (int o = lane; o < GRAM_TILES; o += 32) out[o] = sG[o];
+    __syncwarp();
   }
 }
 
@@ -448,123 +581,101 @@ __global__ void __launch_bounds__(EVAL_THREADS) linearise_materialise_kernel(Dev
 }
 
 // =========================================================================================================
-// expand: one warp per synced set.  V_v = sum_k M^T G_xx M, b_v = -sum_k M^T G_xe, W_v rows (intrinsics of cam k:
-// G_cx M ; baseline j: sum_{k>j} A_{j,k}^T G_xx M) with M = Pi_k P_v.
+// set reduction: one warp per synced set.  V_v = sum_k V_k, b_v = sum_k b_k, W_v rows: intrinsics of camera k = W_k,
+// baseline j = sum_{k>j} A_{j,k}^T Y_k.                                  ≙ SparseBlockMatrix::block(r,c) += J1^T J2
 // =========================================================================================================
-constexpr int EX_WARPS = 4;
+constexpr int SR_WARPS = 8;
 
-__global__ void __launch_bounds__(EX_WARPS * 32) expand_kernel(DevProblem p) {
+// Baseline rows by a backward recurrence along the chain instead of the O(C^2) sum over (j,k) pairs:
+//   W_base(j) = sum_{k>j} A_{j,k}^T Y_k,  A_{j,k} = X_{k,j} M_j,  X_{k,j} = X_{k,j+1} boxTimes(B_{j+1})
+//   =>  Z_j := sum_{k>j} X_{k,j}^T Y_k = Y_{j+1} + boxTimes(B_{j+1})^T Z_{j+1},  Z_{C-1} = 0,  W_base(j) = M_j^T Z_j.
+__global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int per_warp = 256 + 36 * 4 + 8 + 36 * p.n_cams;
-  double* sG = smem + (size_t)wib * per_warp;  // 256: full symmetric Gram block
-  double* sP = sG + 256;                       // P_v
-  double* sM = sP + 36;                        // M = Pi_k P_v
-  double* sY = sM + 36;                        // Y = G_xx M
-  double* sV = sY + 36;                        // V accumulator
-  double* sb = sV + 36;                        // b accumulator (6, padded to 8)
-  double* sWb = sb + 8;                        // baseline rows accumulators [n_cams-1][36]
-  const int set = blockIdx.x * EX_WARPS + wib;
-  if (set >= p.n_sets) return;
-  {
-    double Pv[36];
-    set_pose_jac(p.set_poses + (size_t)set * POSE_STRIDE, Pv);
-    for (int o = lane; o < 36; o += 32) { sP[o] = Pv[o]; sV[o] = 0.0; }
-    if (lane < 8) sb[lane] = 0.0;
-    for (int o = lane; o < 36 * (p.n_cams - 1); o += 32) sWb[o] = 0.0;
+  const int nb = p.n_cams - 1;
+  double* sBt = smem;                       // [nb][36]
+  double* sMj = sBt + 36 * nb;              // [nb][36]
+  double* sY = sMj + 36 * nb + (size_t)wib * (36 * p.n_cams + 72);  // per warp: Y_k of every camera, Z, T
+  double* sZ = sY + 36 * p.n_cams;
+  double* sT = sZ + 36;
+  for (int i = threadIdx.x; i < 36 * nb; i += blockDim.x) {
+    sBt[i] = p.baseBt[i];
+    sMj[i] = p.baseM[i];
   }
-  double* Wout = p.W + (size_t)set * p.n_c * 6;
-  __syncwarp();
-  for (int k = 0; k < p.n_cams; ++k) {
-    const int view = p.set_view[(size_t)set * p.n_cams + k];
-    const int PD = p.cam_P[k] + p.cam_D[k];
-    if (view < 0 || p.view_begin[view + 1] == p.view_begin[view]) {
-      for (int o = lane; o < PD * 6; o += 32) Wout[(size_t)p.intr_off[k] * 6 + o] = 0.0;
-      continue;
+  __syncthreads();
+  for (int set = blockIdx.x * SR_WARPS + wib; set < p.n_sets; set += gridDim.x * SR_WARPS) {
+    double* Wout = p.W + (size_t)set * p.n_c * 6;
+    double v0 = 0.0, v1 = 0.0, bb = 0.0;  // lane o and o + 32 of V, lane < 6 of b
+    for (int k = 0; k < p.n_cams; ++k) {
+      const int view = p.set_view[(size_t)set * p.n_cams + k];
+      const int PD = p.cam_P[k] + p.cam_D[k];
+      const bool present = view >= 0 && p.view_begin[view + 1] > p.view_begin[view];
+      if (!present) {
+        for (int o = lane; o < PD * 6; o += 32) Wout[(size_t)p.intr_off[k] * 6 + o] = 0.0;
+        for (int o = lane; o < 36; o += 32) sY[k * 36 + o] = 0.0;
+        continue;
+      }
+      const double* vb = p.VB + (size_t)view * VB_STRIDE;
+      v0 += vb[VB_V + lane];
+      if (lane < 4) v1 += vb[VB_V + 32 + lane];
+      if (lane < 6) bb += vb[VB_B + lane];
+      for (int o = lane; o < 36; o += 32) sY[k * 36 + o] = vb[VB_Y + o];
+      for (int o = lane; o < PD * 6; o += 32) Wout[(size_t)p.intr_off[k] * 6 + o] = vb[VB_W + o];
     }
-    const double* G = p.G + (size_t)view * GRAM_SIZE;
-    // symmetric fill: tiles (0,0),(0,1),(1,1) are stored; only the upper triangle of the diagonal tiles is exact-symmetric anyway
-    for (int o = lane; o < 256; o += 32) {
-      const int r = o >> 4, c = o & 15;
-      sG[o] = (r >= 8 && c < 8) ? G[c * GRAM_DIM + r] : G[o];
-    }
-    const double* Pi = p.camPi + k * 36;
-    for (int o = lane; o < 36; o += 32) {
-      const int r = o / 6, c = o % 6;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += Pi[r * 6 + a] * sP[a * 6 + c];
-      sM[o] = s;
-    }
+    p.V[(size_t)set * 36 + lane] = v0;
+    if (lane < 4) p.V[(size_t)set * 36 + 32 + lane] = v1;
+    if (lane < 6) p.bv[(size_t)set * 6 + lane] = bb;
+    for (int o = lane; o < 36; o += 32) sZ[o] = 0.0;
     __syncwarp();
-    for (int o = lane; o < 36; o += 32) {  // Y = G_xx M
-      const int r = o / 6, c = o % 6;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sG[r * GRAM_DIM + a] * sM[a * 6 + c];
-      sY[o] = s;
-    }
-    __syncwarp();
-    for (int o = lane; o < 36; o += 32) {  // V += M^T Y
-      const int r = o / 6, c = o % 6;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sM[a * 6 + r] * sY[a * 6 + c];
-      sV[o] += s;
-    }
-    if (lane < 6) {  // b_v -= M^T G_xe
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sM[a * 6 + lane] * sG[a * GRAM_DIM + E_COL];
-      sb[lane] -= s;
-    }
-    for (int o = lane; o < PD * 6; o += 32) {  // intrinsics rows: G_cx M
-      const int r = o / 6, c = o % 6;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sG[(6 + r) * GRAM_DIM + a] * sM[a * 6 + c];
-      Wout[(size_t)p.intr_off[k] * 6 + o] = s;
-    }
-    for (int j = 0; j < k; ++j) {  // baseline rows: A_{j,k}^T Y
-      const double* A = p.camA + ((size_t)k * p.n_cams + j) * 36;
+    for (int j = nb - 1; j >= 0; --j) {
+      // Z_j = Y_{j+1} + boxTimes(B_{j+1})^T Z_{j+1}
       for (int o = lane; o < 36; o += 32) {
+        const int r = o / 6, c = o % 6;
+        double s = sY[(j + 1) * 36 + o];
+        if (j + 1 < nb) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) s += sBt[(j + 1) * 36 + a * 6 + r] * sZ[a * 6 + c];
+        }
+        sT[o] = s;
+      }
+      __syncwarp();
+      for (int o = lane; o < 36; o += 32) sZ[o] = sT[o];
+      __syncwarp();
+      for (int o = lane; o < 36; o += 32) {  // W_base(j) = M_j^T Z_j
         const int r = o / 6, c = o % 6;
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) s += A[a * 6 + r] * sY[a * 6 + c];
-        sWb[j * 36 + o] += s;
+        for (int a = 0; a < 6; ++a) s += sMj[j * 36 + a * 6 + r] * sZ[a * 6 + c];
+        Wout[(size_t)p.base_off[j] * 6 + o] = s;
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
-  for (int o = lane; o < 36; o += 32) p.V[(size_t)set * 36 + o] = sV[o];
-  if (lane < 6) p.bv[(size_t)set * 6 + lane] = sb[lane];
-  for (int j = 0; j < p.n_cams - 1; ++j)
-    for (int o = lane; o < 36; o += 32) Wout[(size_t)p.base_off[j] * 6 + o] = sWb[j * 36 + o];
 }
 
-// ---- per-camera sum of Gram blocks (deterministic two-stage) ---------------------------------------------------
-constexpr int SG_SLICES = 64;
-__global__ void __launch_bounds__(256) sum_gram_stage1(DevProblem p, const int* __restrict__ cam_view_list, const int* __restrict__ cam_view_begin,
-                                                       double* __restrict__ partial /*[n_cams][SG_SLICES][256]*/) {
-  const int k = blockIdx.y, sl = blockIdx.x;
-  const int b = cam_view_begin[k], e = cam_view_begin[k + 1];
-  const int n = e - b;
-  const int per = (n + SG_SLICES - 1) / SG_SLICES;
-  const int lo = b + sl * per, hi = min(e, lo + per);
+// ---- per-camera Gram sums from the slice partials (fixed order) -------------------------------------------------
+constexpr int FG_GROUPS = 5;
+__global__ void __launch_bounds__(GRAM_TILES * FG_GROUPS) finalize_gram_kernel(DevProblem p, const int* __restrict__ cam_slice_range /*[n_cams][2]*/) {
+  __shared__ double sh[FG_GROUPS][GRAM_TILES];
+  const int k = blockIdx.x, t = threadIdx.x % GRAM_TILES, g = threadIdx.x / GRAM_TILES;
+  const int lo = cam_slice_range[2 * k], hi = cam_slice_range[2 * k + 1];
+  const int per = (hi - lo + FG_GROUPS - 1) / FG_GROUPS;
+  const int a = lo + g * per, b = min(hi, a + per);
   double s = 0.0;
-  for (int i = lo; i < hi; ++i) {
-    const int view = cam_view_list[i];
-    if (p.view_begin[view + 1] > p.view_begin[view]) s += p.G[(size_t)view * GRAM_SIZE + threadIdx.x];
-  }
-  partial[((size_t)k * SG_SLICES + sl) * 256 + threadIdx.x] = s;
-}
-__global__ void __launch_bounds__(256) sum_gram_stage2(DevProblem p, const double* __restrict__ partial) {
-  const int k = blockIdx.x;
-  double s = 0.0;
-  for (int sl = 0; sl < SG_SLICES; ++sl) s += partial[((size_t)k * SG_SLICES + sl) * 256 + threadIdx.x];
-  p.sumG[(size_t)k * 256 + threadIdx.x] = s;
+#pragma unroll 8
+  for (int sl = a; sl < b; ++sl) s += p.gram_partial[(size_t)sl * GRAM_TILES + t];
+  sh[g][t] = s;
+  __syncthreads();
+  if (g != 0) return;
+#pragma unroll
+  for (int q = 1; q < FG_GROUPS; ++q) s += sh[q][t];
+  // tile t/64: 0 -> (0,0), 1 -> (0,1), 2 -> (1,1); within a tile the mma C layout: lane = (t%64)/2, element = t%2
+  const int tile = t >> 6, lane = (t & 63) >> 1, el = t & 1;
+  const int r = (tile == 2 ? 8 : 0) + (lane >> 2), c = (tile >= 1 ? 8 : 0) + 2 * (lane & 3) + el;
+  double* G = p.sumG + (size_t)k * GRAM_SIZE;
+  G[r * GRAM_DIM + c] = s;
+  if (tile == 1) G[c * GRAM_DIM + r] = s;
 }
 
 // ---- camera block U (augmented with b_c as last row/col and the linearisation-point cost in the corner) ----------
@@ -636,6 +747,15 @@ __global__ void __launch_bounds__(256) camera_block_kernel(DevProblem p) {
   }
   p.U[(size_t)i * n + j] = acc;
   p.U[(size_t)j * n + i] = acc;
+}
+
+// cost at the linearisation point = sum_k G_k[e][e]
+__global__ void gram_cost_kernel(DevProblem p, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < p.n_cams; ++k) s += p.sumG[(size_t)k * GRAM_SIZE + E_COL * GRAM_DIM + E_COL];
+    out[0] = s;
+  }
 }
 
 // =========================================================================================================
@@ -863,12 +983,29 @@ __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* _
   }
 }
 
-// out[0] = sum_local dx (lambda dx + rhs) [+ lambda |dx_c|^2 once], out[1] = max |dx| over local poses and the shared block
-__global__ void __launch_bounds__(1024) rho_kernel(DevProblem p, double lambda, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
-                                                    int include_shared, double* __restrict__ out) {
+// out[0] = sum_local dx (lambda dx + rhs) [+ lambda |dx_c|^2 once], out[1] = max |dx| over local poses and the shared block.
+// Two stages with fixed order: per-block partials, then one block.
+constexpr int RHO_BLOCKS = 64;
+__device__ __forceinline__ void block_sum_max(double& s, double& m, double* sh_s, double* sh_m) {
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_m[threadIdx.x >> 5] = m; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    s = threadIdx.x < nw ? sh_s[threadIdx.x] : 0.0;
+    m = threadIdx.x < nw ? sh_m[threadIdx.x] : 0.0;
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+}
+__global__ void __launch_bounds__(256) rho_stage1_kernel(DevProblem p, double lambda, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
+                                                           int include_shared, double* __restrict__ partial /*[RHO_BLOCKS][2]*/) {
   __shared__ double sh_s[32], sh_m[32];
   double s = 0.0, m = 0.0;
-  for (int set = threadIdx.x; set < p.n_sets; set += blockDim.x) {
+  for (int set = blockIdx.x * blockDim.x + threadIdx.x; set < p.n_sets; set += gridDim.x * blockDim.x) {
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       const double d = p.dx[(c < 3 ? set_col_q[set] : set_col_t[set] - 3) + c];
@@ -876,25 +1013,23 @@ __global__ void __launch_bounds__(1024) rho_kernel(DevProblem p, double lambda, 
       m = fmax(m, fabs(d));
     }
   }
-  for (int i = threadIdx.x; i < p.n_c; i += blockDim.x) {
-    const double d = p.dxc[i];
-    s += d * p.U[(size_t)i * p.n_aug + p.n_c];  // this rank's partial b_c
-    if (include_shared) s += lambda * d * d;
-    m = fmax(m, fabs(d));
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < p.n_c; i += blockDim.x) {
+      const double d = p.dxc[i];
+      s += d * p.U[(size_t)i * p.n_aug + p.n_c];  // this rank's partial b_c
+      if (include_shared) s += lambda * d * d;
+      m = fmax(m, fabs(d));
+    }
   }
-  s = warp_sum(s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_m[threadIdx.x >> 5] = m; }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    s = sh_s[threadIdx.x];
-    m = sh_m[threadIdx.x];
-    s = warp_sum(s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) { out[0] = s; out[1] = m; }
-  }
+  block_sum_max(s, m, sh_s, sh_m);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s; partial[2 * blockIdx.x + 1] = m; }
+}
+__global__ void __launch_bounds__(RHO_BLOCKS) rho_stage2_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ double sh_s[32], sh_m[32];
+  double s = threadIdx.x < n ? partial[2 * threadIdx.x] : 0.0;
+  double m = threadIdx.x < n ? partial[2 * threadIdx.x + 1] : 0.0;
+  block_sum_max(s, m, sh_s, sh_m);
+  if (threadIdx.x == 0) { out[0] = s; out[1] = m; }
 }
 
 // sm::kinematics::updateQuat (quaternion_algebra.cpp:200-219, 302-317)
@@ -989,29 +1124,45 @@ cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int
   return cudaGetLastError();
 }
 
-template <int MODEL>
-static cudaError_t launch_la_model(const DevProblem& p, const int* list, int n, StreamCtx& s) {
-  if (n <= 0) return cudaSuccess;
-  const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * XT_WARP_DOUBLES);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(linearise_assemble_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+int la_grid_warps() { return sm_count() * 2 * LA_WARPS; }
+
+template <int MODEL, bool WRITE_E>
+static cudaError_t launch_la_model(const DevProblem& p, const int* view_list, const int4* slices, int lo, int hi, StreamCtx& s) {
+  if (hi <= lo) return cudaSuccess;
+  const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(linearise_assemble_kernel<MODEL, WRITE_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_smem = smem;
   }
-  const int grid = min((n + LA_WARPS - 1) / LA_WARPS, sm_count() * 3);
-  linearise_assemble_kernel<MODEL><<<grid, LA_THREADS, smem, s.stream>>>(p, list, n);
+  const int grid = min((hi - lo + LA_WARPS - 1) / LA_WARPS, sm_count() * 2);
+  linearise_assemble_kernel<MODEL, WRITE_E><<<grid, LA_THREADS, smem, s.stream>>>(p, view_list, slices, lo, hi);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
 
-cudaError_t launch_linearise_assemble(const DevProblem& p, const int* view_list, const int* mb, StreamCtx& s) {
+// slice_model_begin[m] .. [m+1]: slices of camera model m
+cudaError_t launch_linearise_assemble(const DevProblem& p, const int* view_list, const int4* slices, const int* smb, bool write_e, StreamCtx& s) {
   cudaError_t e;
-  if ((e = launch_la_model<0>(p, view_list + mb[0], mb[1] - mb[0], s)) != cudaSuccess) return e;
-  if ((e = launch_la_model<1>(p, view_list + mb[1], mb[2] - mb[1], s)) != cudaSuccess) return e;
-  if ((e = launch_la_model<2>(p, view_list + mb[2], mb[3] - mb[2], s)) != cudaSuccess) return e;
-  if ((e = launch_la_model<3>(p, view_list + mb[3], mb[4] - mb[3], s)) != cudaSuccess) return e;
-  if ((e = launch_la_model<4>(p, view_list + mb[4], mb[5] - mb[4], s)) != cudaSuccess) return e;
+  if (p.n_sets > 0) {
+    set_prep_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p);
+    KB_LAUNCHED(s);
+  }
+#define KB_LA(M)                                                                                      \
+  if ((e = write_e ? launch_la_model<M, true>(p, view_list, slices, smb[M], smb[M + 1], s)            \
+                   : launch_la_model<M, false>(p, view_list, slices, smb[M], smb[M + 1], s)) != cudaSuccess) return e;
+  KB_LA(0) KB_LA(1) KB_LA(2) KB_LA(3) KB_LA(4)
+#undef KB_LA
+  return cudaGetLastError();
+}
+
+// per-camera Gram sums + cost of the linearisation point (-> cost_out[0])
+cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, double* cost_out, StreamCtx& s) {
+  finalize_gram_kernel<<<p.n_cams, GRAM_TILES * FG_GROUPS, 0, s.stream>>>(p, cam_slice_range);
+  KB_LAUNCHED(s);
+  gram_cost_kernel<<<1, 32, 0, s.stream>>>(p, cost_out);
+  KB_LAUNCHED(s);
   return cudaGetLastError();
 }
 
@@ -1034,33 +1185,20 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int* view_li
   return cudaGetLastError();
 }
 
-static double* g_sumg_partial = nullptr;
-static size_t g_sumg_partial_bytes = 0;
-
-cudaError_t launch_expand(const DevProblem& p, const int* cam_view_list, const int* cam_view_begin, StreamCtx& s) {
-  const size_t per_warp = 256 + 36 * 4 + 8 + 36 * p.n_cams;
-  const size_t smem = sizeof(double) * per_warp * EX_WARPS;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_smem = smem;
-  }
+// V_v, b_v, W_v from the view blocks; U, b_c from the per-camera Gram sums
+cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s) {
+  const size_t smem = sizeof(double) * (72 * (size_t)(p.n_cams - 1) + SR_WARPS * (36 * (size_t)p.n_cams + 72));
   if (p.n_sets > 0) {
-    expand_kernel<<<(p.n_sets + EX_WARPS - 1) / EX_WARPS, EX_WARPS * 32, smem, s.stream>>>(p);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem && smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(set_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_smem = smem;
+    }
+    const int grid = min((p.n_sets + SR_WARPS - 1) / SR_WARPS, sm_count() * 4);
+    set_reduce_kernel<<<grid, SR_WARPS * 32, smem, s.stream>>>(p);
     KB_LAUNCHED(s);
   }
-  const size_t need = sizeof(double) * (size_t)p.n_cams * SG_SLICES * 256;
-  if (need > g_sumg_partial_bytes) {
-    if (g_sumg_partial) cudaFree(g_sumg_partial);
-    cudaError_t e = cudaMalloc(&g_sumg_partial, need);
-    if (e != cudaSuccess) return e;
-    g_sumg_partial_bytes = need;
-  }
-  sum_gram_stage1<<<dim3(SG_SLICES, p.n_cams), 256, 0, s.stream>>>(p, cam_view_list, cam_view_begin, g_sumg_partial);
-  KB_LAUNCHED(s);
-  sum_gram_stage2<<<p.n_cams, 256, 0, s.stream>>>(p, g_sumg_partial);
-  KB_LAUNCHED(s);
   const int n2 = p.n_aug * p.n_aug;
   camera_block_kernel<<<(n2 + 255) / 256, 256, 0, s.stream>>>(p);
   KB_LAUNCHED(s);
@@ -1137,7 +1275,15 @@ cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int*
 
 cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int*, int include_shared,
                                    double* out2, StreamCtx& s) {
-  rho_kernel<<<1, 1024, 0, s.stream>>>(p, lambda, set_col_q, set_col_t, include_shared, out2);
+  static double* partial = nullptr;
+  if (!partial) {
+    cudaError_t e = cudaMalloc(&partial, sizeof(double) * 2 * RHO_BLOCKS);
+    if (e != cudaSuccess) return e;
+  }
+  const int blocks = max(1, min(RHO_BLOCKS, (p.n_sets + 255) / 256));
+  rho_stage1_kernel<<<blocks, 256, 0, s.stream>>>(p, lambda, set_col_q, set_col_t, include_shared, partial);
+  KB_LAUNCHED(s);
+  rho_stage2_kernel<<<1, RHO_BLOCKS, 0, s.stream>>>(partial, blocks, out2);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }

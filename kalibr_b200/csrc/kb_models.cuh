@@ -83,11 +83,13 @@ __device__ __forceinline__ void equidistant(const double* __restrict__ k, double
 }
 
 // ---- projections ----------------------------------------------------------------------------------------
-template <int MODEL, bool WITH_JAC>
+// NEG = true returns the NEGATED Jacobians (-Jp, -Ji, -Jd): what the error term e = y - y_hat needs, with the sign folded
+// into the focal-length factors instead of a separate pass over the rows.
+template <int MODEL, bool WITH_JAC, bool NEG = false>
 struct Camera;
 
 // pinhole + (radtan | equi): params fu,fv,cu,cv,d0..d3
-template <int MODEL, bool WITH_JAC>
+template <int MODEL, bool WITH_JAC, bool NEG>
 struct PinholeCamera {
   static constexpr int P = 4, D = 4;
   __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
@@ -100,19 +102,21 @@ struct PinholeCamera {
     else
       equidistant<WITH_JAC>(prm + 4, mx, my, Jm, Jk);
     if (WITH_JAC) {
+      const double ju = NEG ? -fu : fu, jv = NEG ? -fv : fv;
+      const double one = NEG ? -1.0 : 1.0;
       const double rz2 = rz * rz;
-      L.Jp[0][0] = fu * Jm[0][0] * rz;
-      L.Jp[0][1] = fu * Jm[0][1] * rz;
-      L.Jp[0][2] = -fu * (p[0] * Jm[0][0] + p[1] * Jm[0][1]) * rz2;
-      L.Jp[1][0] = fv * Jm[1][0] * rz;
-      L.Jp[1][1] = fv * Jm[1][1] * rz;
-      L.Jp[1][2] = -fv * (p[0] * Jm[1][0] + p[1] * Jm[1][1]) * rz2;
-      L.Ji[0][0] = mx; L.Ji[0][1] = 0.0; L.Ji[0][2] = 1.0; L.Ji[0][3] = 0.0;
-      L.Ji[1][0] = 0.0; L.Ji[1][1] = my; L.Ji[1][2] = 0.0; L.Ji[1][3] = 1.0;
+      L.Jp[0][0] = ju * Jm[0][0] * rz;
+      L.Jp[0][1] = ju * Jm[0][1] * rz;
+      L.Jp[0][2] = -ju * (p[0] * Jm[0][0] + p[1] * Jm[0][1]) * rz2;
+      L.Jp[1][0] = jv * Jm[1][0] * rz;
+      L.Jp[1][1] = jv * Jm[1][1] * rz;
+      L.Jp[1][2] = -jv * (p[0] * Jm[1][0] + p[1] * Jm[1][1]) * rz2;
+      L.Ji[0][0] = NEG ? -mx : mx; L.Ji[0][1] = 0.0; L.Ji[0][2] = one; L.Ji[0][3] = 0.0;
+      L.Ji[1][0] = 0.0; L.Ji[1][1] = NEG ? -my : my; L.Ji[1][2] = 0.0; L.Ji[1][3] = one;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        L.Jd[0][j] = fu * Jk[0][j];
-        L.Jd[1][j] = fv * Jk[1][j];
+        L.Jd[0][j] = ju * Jk[0][j];
+        L.Jd[1][j] = jv * Jk[1][j];
       }
     }
     L.y[0] = fu * mx + cu;
@@ -120,14 +124,14 @@ struct PinholeCamera {
     L.valid = true;  // the reference's pinhole never bails out before writing y_hat
   }
 };
-template <bool WITH_JAC>
-struct Camera<PINHOLE_RADTAN, WITH_JAC> : PinholeCamera<PINHOLE_RADTAN, WITH_JAC> {};
-template <bool WITH_JAC>
-struct Camera<PINHOLE_EQUI, WITH_JAC> : PinholeCamera<PINHOLE_EQUI, WITH_JAC> {};
+template <bool WITH_JAC, bool NEG>
+struct Camera<PINHOLE_RADTAN, WITH_JAC, NEG> : PinholeCamera<PINHOLE_RADTAN, WITH_JAC, NEG> {};
+template <bool WITH_JAC, bool NEG>
+struct Camera<PINHOLE_EQUI, WITH_JAC, NEG> : PinholeCamera<PINHOLE_EQUI, WITH_JAC, NEG> {};
 
 // omni + radtan: params xi,fu,fv,cu,cv,k1,k2,p1,p2
-template <bool WITH_JAC>
-struct Camera<OMNI_RADTAN, WITH_JAC> {
+template <bool WITH_JAC, bool NEG>
+struct Camera<OMNI_RADTAN, WITH_JAC, NEG> {
   static constexpr int P = 5, D = 4;
   __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
     const double xi = prm[0], fu = prm[1], fv = prm[2], cu = prm[3], cv = prm[4];
@@ -151,19 +155,21 @@ struct Camera<OMNI_RADTAN, WITH_JAC> {
     double Jm[2][2], Jk[2][4];
     radtan<WITH_JAC>(prm + 5, mx, my, Jm, Jk);
     if (WITH_JAC) {
+      const double ju = NEG ? -fu : fu, jv = NEG ? -fv : fv;
+      const double one = NEG ? -1.0 : 1.0;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        L.Jp[0][c] = fu * (Jn[0][c] * Jm[0][0] + Jn[1][c] * Jm[0][1]);
-        L.Jp[1][c] = fv * (Jn[0][c] * Jm[1][0] + Jn[1][c] * Jm[1][1]);
+        L.Jp[0][c] = ju * (Jn[0][c] * Jm[0][0] + Jn[1][c] * Jm[0][1]);
+        L.Jp[1][c] = jv * (Jn[0][c] * Jm[1][0] + Jn[1][c] * Jm[1][1]);
       }
-      L.Ji[0][0] = fu * Jm[0][0] * jxi0 + fu * Jm[0][1] * jxi1;
-      L.Ji[1][0] = fv * Jm[1][0] * jxi0 + fv * Jm[1][1] * jxi1;
-      L.Ji[0][1] = mx; L.Ji[0][2] = 0.0; L.Ji[0][3] = 1.0; L.Ji[0][4] = 0.0;
-      L.Ji[1][1] = 0.0; L.Ji[1][2] = my; L.Ji[1][3] = 0.0; L.Ji[1][4] = 1.0;
+      L.Ji[0][0] = ju * Jm[0][0] * jxi0 + ju * Jm[0][1] * jxi1;
+      L.Ji[1][0] = jv * Jm[1][0] * jxi0 + jv * Jm[1][1] * jxi1;
+      L.Ji[0][1] = NEG ? -mx : mx; L.Ji[0][2] = 0.0; L.Ji[0][3] = one; L.Ji[0][4] = 0.0;
+      L.Ji[1][1] = 0.0; L.Ji[1][2] = NEG ? -my : my; L.Ji[1][3] = 0.0; L.Ji[1][4] = one;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        L.Jd[0][j] = fu * Jk[0][j];
-        L.Jd[1][j] = fv * Jk[1][j];
+        L.Jd[0][j] = ju * Jk[0][j];
+        L.Jd[1][j] = jv * Jk[1][j];
       }
     }
     L.y[0] = fu * mx + cu;
@@ -172,8 +178,8 @@ struct Camera<OMNI_RADTAN, WITH_JAC> {
 };
 
 // EUCM (no distortion): params alpha,beta,fu,fv,cu,cv
-template <bool WITH_JAC>
-struct Camera<EUCM_NONE, WITH_JAC> {
+template <bool WITH_JAC, bool NEG>
+struct Camera<EUCM_NONE, WITH_JAC, NEG> {
   static constexpr int P = 6, D = 0;
   __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
     const double al = prm[0], be = prm[1], fu = prm[2], fv = prm[3], cu = prm[4], cv = prm[5];
@@ -185,26 +191,28 @@ struct Camera<EUCM_NONE, WITH_JAC> {
     const double norm = al * d + (1.0 - al) * z;
     const double ni = 1.0 / norm;
     if (WITH_JAC) {
+      const double ju = NEG ? -fu : fu, jv = NEG ? -fv : fv;
+      const double one = NEG ? -1.0 : 1.0;
       const double di = 1.0 / d;
       const double denom = ni * ni * di;
       const double mid = -(al * be * x * y) * denom;
       const double add = norm * d;
       const double addz = al * z + (1.0 - al) * d;
-      L.Jp[0][0] = fu * (add - x * x * al * be) * denom;
-      L.Jp[1][0] = fv * mid;
-      L.Jp[0][1] = fu * mid;
-      L.Jp[1][1] = fv * (add - y * y * al * be) * denom;
-      L.Jp[0][2] = -fu * x * addz * denom;
-      L.Jp[1][2] = -fv * y * addz * denom;
+      L.Jp[0][0] = ju * (add - x * x * al * be) * denom;
+      L.Jp[1][0] = jv * mid;
+      L.Jp[0][1] = ju * mid;
+      L.Jp[1][1] = jv * (add - y * y * al * be) * denom;
+      L.Jp[0][2] = -ju * x * addz * denom;
+      L.Jp[1][2] = -jv * y * addz * denom;
       const double ni2 = ni * ni;
-      const double tx = -fu * x * ni2;
-      const double ty = -fu * y * ni2;  // Q4: the reference scales row 1 with fu as well
+      const double tx = -ju * x * ni2;
+      const double ty = -ju * y * ni2;  // Q4: the reference scales row 1 with fu as well
       const double t4 = d - z;
       const double t5 = 0.5 * al * r2 * di;
       L.Ji[0][0] = tx * t4; L.Ji[1][0] = ty * t4;
       L.Ji[0][1] = tx * t5; L.Ji[1][1] = ty * t5;
-      L.Ji[0][2] = x * ni; L.Ji[0][3] = 0.0; L.Ji[0][4] = 1.0; L.Ji[0][5] = 0.0;
-      L.Ji[1][2] = 0.0; L.Ji[1][3] = y * ni; L.Ji[1][4] = 0.0; L.Ji[1][5] = 1.0;
+      L.Ji[0][2] = (NEG ? -x : x) * ni; L.Ji[0][3] = 0.0; L.Ji[0][4] = one; L.Ji[0][5] = 0.0;
+      L.Ji[1][2] = 0.0; L.Ji[1][3] = (NEG ? -y : y) * ni; L.Ji[1][4] = 0.0; L.Ji[1][5] = one;
     }
     L.y[0] = fu * (x * ni) + cu;
     L.y[1] = fv * (y * ni) + cv;
@@ -212,8 +220,8 @@ struct Camera<EUCM_NONE, WITH_JAC> {
 };
 
 // double sphere (no distortion): params xi,alpha,fu,fv,cu,cv
-template <bool WITH_JAC>
-struct Camera<DS_NONE, WITH_JAC> {
+template <bool WITH_JAC, bool NEG>
+struct Camera<DS_NONE, WITH_JAC, NEG> {
   static constexpr int P = 6, D = 0;
   __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
     const double xi = prm[0], al = prm[1], fu = prm[2], fv = prm[3], cu = prm[4], cv = prm[5];
@@ -229,24 +237,26 @@ struct Camera<DS_NONE, WITH_JAC> {
     const double norm = al * d2 + (1.0 - al) * k;
     const double ni = 1.0 / norm;
     if (WITH_JAC) {
+      const double ju = NEG ? -fu : fu, jv = NEG ? -fv : fv;
+      const double one = NEG ? -1.0 : 1.0;
       const double d1i = 1.0 / d1, d2i = 1.0 / d2;
       const double ni2 = ni * ni;
       const double xy = x * y;
       const double tt2 = xi * z * d1i + 1.0;
       const double dn = (xi * (1.0 - al) * d1i + al * (xi * k * d1i + 1.0) * d2i) * ni2;
       const double tmp2 = ((1.0 - al) * tt2 + al * k * tt2 * d2i) * ni2;
-      L.Jp[0][0] = fu * (ni - xx * dn);
-      L.Jp[1][0] = -fv * xy * dn;
-      L.Jp[0][1] = -fu * xy * dn;
-      L.Jp[1][1] = fv * (ni - yy * dn);
-      L.Jp[0][2] = -fu * x * tmp2;
-      L.Jp[1][2] = -fv * y * tmp2;
+      L.Jp[0][0] = ju * (ni - xx * dn);
+      L.Jp[1][0] = -jv * xy * dn;
+      L.Jp[0][1] = -ju * xy * dn;
+      L.Jp[1][1] = jv * (ni - yy * dn);
+      L.Jp[0][2] = -ju * x * tmp2;
+      L.Jp[1][2] = -jv * y * tmp2;
       const double t4 = (al - 1.0 - al * k * d2i) * d1 * ni2;
       const double t5 = (k - d2) * ni2;
-      L.Ji[0][0] = fu * x * t4; L.Ji[1][0] = fv * y * t4;
-      L.Ji[0][1] = fu * x * t5; L.Ji[1][1] = fv * y * t5;
-      L.Ji[0][2] = x * ni; L.Ji[0][3] = 0.0; L.Ji[0][4] = 1.0; L.Ji[0][5] = 0.0;
-      L.Ji[1][2] = 0.0; L.Ji[1][3] = y * ni; L.Ji[1][4] = 0.0; L.Ji[1][5] = 1.0;
+      L.Ji[0][0] = ju * x * t4; L.Ji[1][0] = jv * y * t4;
+      L.Ji[0][1] = ju * x * t5; L.Ji[1][1] = jv * y * t5;
+      L.Ji[0][2] = (NEG ? -x : x) * ni; L.Ji[0][3] = 0.0; L.Ji[0][4] = one; L.Ji[0][5] = 0.0;
+      L.Ji[1][2] = 0.0; L.Ji[1][3] = (NEG ? -y : y) * ni; L.Ji[1][4] = 0.0; L.Ji[1][5] = one;
     }
     L.y[0] = fu * (x * ni) + cu;
     L.y[1] = fv * (y * ni) + cv;
