@@ -71,7 +71,7 @@ struct DevProblem {
   double* V;            // [n_sets][36]
   double* bv;           // [n_sets][6]
   double* W;            // [n_sets][n_c][6]
-  double* Lv;           // [n_sets][36]   Cholesky factor of V + damping (row-major lower)
+  double* Lv;           // [n_sets][36]   inverse of the Cholesky factor of V + damping (row-major lower)
   double* yv;           // [n_sets][6]    L^-1 b_v
   double* U;            // [n_aug*n_aug]  camera block with rhs b_c in the last row/col (this rank's partial)
   double* Sred;         // [n_aug*n_aug]  reduced system (after all-reduce), then its Cholesky factor
@@ -91,7 +91,8 @@ struct StreamCtx {
 cudaError_t launch_prep(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int* model_begin, double* cost_out, StreamCtx& s);
 int la_grid_warps();
-cudaError_t launch_linearise_assemble(const DevProblem& p, const int* view_list, const int4* slices, const int* slice_model_begin, bool write_e,
+cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta /*(view,set,begin,end) in view-list order*/, const int4* slices,
+                                      const int* slice_model_begin, bool write_e,
                                       StreamCtx& s);
 cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, double* cost_out, StreamCtx& s);
 cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s);

@@ -100,7 +100,7 @@ struct kb_handle {
   DevBuf<uint16_t> corner;
   DevBuf<int> view_set, view_cam, view_begin, set_view, lin_off, view_list, cam_view_list, cam_view_begin, set_col_q, set_col_t, cam_cols, posdef;
   DevBuf<long long> view_jbase;
-  DevBuf<int4> slices;
+  DevBuf<int4> slices, vmeta;
   DevBuf<int> cam_slice_range;
   int slice_model_begin[KB_NUM_MODELS + 1] = {};
   DevBuf<unsigned int> n_invalid;
@@ -462,6 +462,14 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->cam_view_list.upload(cam_view_list, s));
   KB_CCUDA(h->cam_view_begin.upload(cam_view_begin, s));
   KB_CCUDA(h->slices.upload(slices, s));
+  {
+    std::vector<int4> vmeta(view_list.size());
+    for (size_t i = 0; i < view_list.size(); ++i) {
+      const int w = view_list[i];
+      vmeta[i] = make_int4(w, vs[w], vb[w], vb[w + 1]);
+    }
+    KB_CCUDA(h->vmeta.upload(vmeta, s));
+  }
   KB_CCUDA(h->cam_slice_range.upload(cam_slice_range, s));
   KB_CCUDA(h->set_col_q.upload(set_col_q, s));
   KB_CCUDA(h->set_col_t.upload(set_col_t, s));
@@ -566,7 +574,7 @@ static kb_status run_linearise_assemble(kb_handle* h, bool write_e, int cost_slo
   KB_CUDA(h, launch_prep(h->d, c));
   {
     StageTimer t(h, 1);
-    KB_CUDA(h, launch_linearise_assemble(h->d, h->view_list.p, h->slices.p, h->slice_model_begin, write_e, c));
+    KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->slices.p, h->slice_model_begin, write_e, c));
   }
   KB_CUDA(h, launch_finalize_gram(h->d, h->cam_slice_range.p, h->scalars.p + cost_slot, c));
   h->la_version = h->state_version;

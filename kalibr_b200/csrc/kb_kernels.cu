@@ -14,6 +14,7 @@
 //   backsub         K3c: dx_v = (V_v + d I)^-1 (b_v - W_v^T dx_c)       ≙ sparse_matrix_functions.cpp:64-83
 //   apply_update / rho                                                 ≙ Optimizer2.cpp:290-318, LevenbergMarquardtTrustRegionPolicy.cpp:107-113
 #include <cstdio>
+#include <cstdlib>
 
 #include "kb_device.cuh"
 #include "kb_models.cuh"
@@ -365,22 +366,31 @@ constexpr int LA_WARPS = 8;
 constexpr int LA_THREADS = LA_WARPS * 32;
 constexpr int XT_LD = 68;  // 64 rows (32 terms x 2) + 4: conflict-free for both the 16-byte stores and the DMMA operand loads
 constexpr int XT_WARP_DOUBLES = GRAM_DIM * XT_LD;
-constexpr int LA_WARP_DOUBLES = XT_WARP_DOUBLES + GRAM_TILES + 4 * 36;  // XT | slice Gram sum | Pi, P_v, M, Y
+constexpr int LA_WARP_DOUBLES = XT_WARP_DOUBLES + GRAM_TILES + 3 * 36 + 2 * SETPREP_STRIDE;  // XT | slice Gram sum | Pi, M, Y | set constants x2
 
-template <int MODEL, bool WRITE_E>
-__global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevProblem p, const int* __restrict__ view_list,
+constexpr int G_LD = 17;  // epilogue copy of the Gram block: odd stride, conflict-free for the row-strided reads
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int MODEL, bool WRITE_E, int VARIANT = 0>
+__global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevProblem p, const int4* __restrict__ vmeta,
                                                                             const int4* __restrict__ slices, int slice_lo, int slice_hi) {
   extern __shared__ __align__(16) double smem[];
   double* s_target = smem;                                  // n_target*3 (rounded up to even)
   const int target_doubles = (p.n_target * 3 + 1) & ~1;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  double* XT = smem + target_doubles + wib * LA_WARP_DOUBLES;  // [16 cols][68]; reused as G[16][16] in the epilogue
+  double* XT = smem + target_doubles + wib * LA_WARP_DOUBLES;  // [16 cols][68]; reused as G[16][17] in the epilogue
   double* sG = XT + XT_WARP_DOUBLES;                           // [3][64] slice sum of the three stored tiles
   double* sPi = sG + GRAM_TILES;
-  double* sP = sPi + 36;
-  double* sM = sP + 36;
+  double* sM = sPi + 36;
   double* sY = sM + 36;
+  double* sSP = sY + 36;                                       // [2][48] per-set constants of the current / next view (cp.async)
   for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
   __syncthreads();
   constexpr int PD = model_P(MODEL) + model_D(MODEL);
@@ -400,22 +410,32 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
     for (int i = 0; i < 12; ++i) camT[i] = p.camT[cam * 12 + i];
     for (int o = lane; o < 36; o += 32) sPi[o] = p.camPi[cam * 36 + o];
     for (int o = lane; o < GRAM_TILES; o += 32) sG[o] = 0.0;
-    __syncwarp();
+    // pipeline: metadata two views ahead (registers), per-set constants one view ahead (cp.async into shared memory)
+    int4 m_cur = vmeta[S.x];                                   // (view, set, begin, end)
+    int4 m_nxt = (S.x + 1 < S.y) ? vmeta[S.x + 1] : m_cur;
+    if (lane < 24) cp_async_16(sSP + 2 * lane, p.set_prep + (size_t)m_cur.y * SETPREP_STRIDE + 2 * lane);
+    cp_async_commit();
     for (int vi = S.x; vi < S.y; ++vi) {
-      const int view = view_list[vi];
-      const int set = p.view_set[view];
-      const int b = p.view_begin[view], e = p.view_begin[view + 1];
-      const double* sp = p.set_prep + (size_t)set * SETPREP_STRIDE;
-      double Rcw[9], tcw[3];
-      view_transform_prepped(sp, camT, Rcw, tcw);
-      double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
-      // software prefetch of the chunk's observations
+      const int buf = (vi - S.x) & 1;
+      const int view = m_cur.x;
+      const int b = m_cur.z, e = m_cur.w;
+      // observations of the first chunk: issued before anything waits
       int i = b + lane;
       bool active = i < e;
       int ii = active ? i : b;
       double yu = 0.0, yv = 0.0;
       int cid = 0;
       if (b < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+      const int4 m_nn = (vi + 2 < S.y) ? vmeta[vi + 2] : m_nxt;
+      cp_async_wait_all();
+      __syncwarp();
+      if (vi + 1 < S.y && lane < 24) cp_async_16(sSP + (buf ^ 1) * SETPREP_STRIDE + 2 * lane, p.set_prep + (size_t)m_nxt.y * SETPREP_STRIDE + 2 * lane);
+      cp_async_commit();
+      const double* sp = sSP + buf * SETPREP_STRIDE;
+      double Rcw[9], tcw[3];
+      view_transform_prepped(sp, camT, Rcw, tcw);
+      double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+      double d00[2] = {0.0, 0.0}, d01[2] = {0.0, 0.0}, d11[2] = {0.0, 0.0};
       for (int base = b; base < e; base += 32) {
         const double cyu = yu, cyv = yv;
         const int ccid = cid;
@@ -426,41 +446,58 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
         ii = active ? i : b;
         if (base + 32 < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
         double a0[GRAM_DIM], a1[GRAM_DIM];
-        term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, cactive, a0, a1, p.n_invalid);
+        if (VARIANT == 2) {  // timing experiment: no projection math
+#pragma unroll
+          for (int c = 0; c < GRAM_DIM; ++c) { a0[c] = cyu + c; a1[c] = cyv * ccid; }
+        } else {
+          term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, cactive, a0, a1, p.n_invalid);
+        }
         if (WRITE_E && cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-a0[E_COL], -a1[E_COL]);
 #pragma unroll
         for (int c = 0; c < GRAM_DIM; ++c) *reinterpret_cast<double2*>(XT + c * XT_LD + 2 * lane) = make_double2(a0[c], a1[c]);
         __syncwarp();
+        if (VARIANT == 1) {  // timing experiment: no tensor work
+          c00[0] += XT[arow * XT_LD + acol]; c01[0] += XT[(8 + arow) * XT_LD + acol]; c11[1] += XT[lane];
+        } else {
+          // two independent accumulator sets (even / odd k-steps): six DMMA dependency chains per warp instead of three
 #pragma unroll
-        for (int s = 0; s < 16; ++s) {
-          const double x0 = XT[arow * XT_LD + 4 * s + acol];
-          const double x1 = XT[(8 + arow) * XT_LD + 4 * s + acol];
-          dmma(c00[0], c00[1], x0, x0);
-          dmma(c01[0], c01[1], x0, x1);
-          dmma(c11[0], c11[1], x1, x1);
+          for (int s = 0; s < 16; s += 2) {
+            const double x0 = XT[arow * XT_LD + 4 * s + acol];
+            const double x1 = XT[(8 + arow) * XT_LD + 4 * s + acol];
+            const double z0 = XT[arow * XT_LD + 4 * s + 4 + acol];
+            const double z1 = XT[(8 + arow) * XT_LD + 4 * s + 4 + acol];
+            dmma(c00[0], c00[1], x0, x0);
+            dmma(d00[0], d00[1], z0, z0);
+            dmma(c01[0], c01[1], x0, x1);
+            dmma(d01[0], d01[1], z0, z1);
+            dmma(c11[0], c11[1], x1, x1);
+            dmma(d11[0], d11[1], z1, z1);
+          }
         }
         __syncwarp();
       }
-      // ---- epilogue: G (full symmetric 16x16, ld 16) in shared memory, slice sum, view block ----
+      c00[0] += d00[0]; c00[1] += d00[1]; c01[0] += d01[0]; c01[1] += d01[1]; c11[0] += d11[0]; c11[1] += d11[1];
+      // ---- epilogue: G (full symmetric 16x16, ld 17) in shared memory, slice sum, view block ----
       double* G = XT;
-      *reinterpret_cast<double2*>(G + arow * GRAM_DIM + gc) = make_double2(c00[0], c00[1]);
-      *reinterpret_cast<double2*>(G + arow * GRAM_DIM + 8 + gc) = make_double2(c01[0], c01[1]);
-      G[(8 + gc) * GRAM_DIM + arow] = c01[0];
-      G[(8 + gc + 1) * GRAM_DIM + arow] = c01[1];
-      *reinterpret_cast<double2*>(G + (8 + arow) * GRAM_DIM + 8 + gc) = make_double2(c11[0], c11[1]);
+      G[arow * G_LD + gc] = c00[0];
+      G[arow * G_LD + gc + 1] = c00[1];
+      G[arow * G_LD + 8 + gc] = c01[0];
+      G[arow * G_LD + 8 + gc + 1] = c01[1];
+      G[(8 + gc) * G_LD + arow] = c01[0];
+      G[(8 + gc + 1) * G_LD + arow] = c01[1];
+      G[(8 + arow) * G_LD + 8 + gc] = c11[0];
+      G[(8 + arow) * G_LD + 8 + gc + 1] = c11[1];
       {
         double2* g2 = reinterpret_cast<double2*>(sG);
         double2 t0 = g2[lane], t1 = g2[32 + lane], t2 = g2[64 + lane];
         t0.x += c00[0]; t0.y += c00[1]; t1.x += c01[0]; t1.y += c01[1]; t2.x += c11[0]; t2.y += c11[1];
         g2[lane] = t0; g2[32 + lane] = t1; g2[64 + lane] = t2;
       }
-      for (int o = lane; o < 36; o += 32) sP[o] = sp[12 + o];
-      __syncwarp();
       for (int o = lane; o < 36; o += 32) {  // M = Pi_k P_v
         const int r = o / 6, c = o % 6;
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) s += sPi[r * 6 + a] * sP[a * 6 + c];
+        for (int a = 0; a < 6; ++a) s += sPi[r * 6 + a] * sp[12 + a * 6 + c];
         sM[o] = s;
       }
       __syncwarp();
@@ -469,7 +506,7 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
         const int r = o / 6, c = o % 6;
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) s += G[r * GRAM_DIM + a] * sM[a * 6 + c];
+        for (int a = 0; a < 6; ++a) s += G[r * G_LD + a] * sM[a * 6 + c];
         sY[o] = s;
         vb[VB_Y + o] = s;
       }
@@ -477,13 +514,13 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
         const int r = o / 6, c = o % 6;
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) s += G[(6 + r) * GRAM_DIM + a] * sM[a * 6 + c];
+        for (int a = 0; a < 6; ++a) s += G[(6 + r) * G_LD + a] * sM[a * 6 + c];
         vb[VB_W + o] = s;
       }
       if (lane < 6) {  // b_k = -M^T G_xe
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) s += sM[a * 6 + lane] * G[a * GRAM_DIM + E_COL];
+        for (int a = 0; a < 6; ++a) s += sM[a * 6 + lane] * G[a * G_LD + E_COL];
         vb[VB_B + lane] = -s;
       }
       __syncwarp();
@@ -495,7 +532,10 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
         vb[VB_V + o] = s;
       }
       __syncwarp();
+      m_cur = m_nxt;
+      m_nxt = m_nn;
     }
+    cp_async_wait_all();
     double* out = p.gram_partial + (size_t)sl * GRAM_TILES;
     for (int o = lane; o < GRAM_TILES; o += 32) out[o] = sG[o];
     __syncwarp();
@@ -605,23 +645,37 @@ __global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p)
   }
   __syncthreads();
   for (int set = blockIdx.x * SR_WARPS + wib; set < p.n_sets; set += gridDim.x * SR_WARPS) {
-    double* Wout = p.W + (size_t)set * p.n_c * 6;
+    double* __restrict__ Wout = p.W + (size_t)set * p.n_c * 6;
     double v0 = 0.0, v1 = 0.0, bb = 0.0;  // lane o and o + 32 of V, lane < 6 of b
+    // lane k fetches the view of camera k (n_cams <= 32), so that the view-block loads below have no dependent address chain
+    int my_view = -1;
+    if (lane < p.n_cams) {
+      const int w = p.set_view[(size_t)set * p.n_cams + lane];
+      if (w >= 0 && p.view_begin[w + 1] > p.view_begin[w]) my_view = w;
+    }
     for (int k = 0; k < p.n_cams; ++k) {
-      const int view = p.set_view[(size_t)set * p.n_cams + k];
+      const int view = __shfl_sync(0xffffffffu, my_view, k);
       const int PD = p.cam_P[k] + p.cam_D[k];
-      const bool present = view >= 0 && p.view_begin[view + 1] > p.view_begin[view];
-      if (!present) {
+      if (view < 0) {
         for (int o = lane; o < PD * 6; o += 32) Wout[(size_t)p.intr_off[k] * 6 + o] = 0.0;
         for (int o = lane; o < 36; o += 32) sY[k * 36 + o] = 0.0;
         continue;
       }
-      const double* vb = p.VB + (size_t)view * VB_STRIDE;
-      v0 += vb[VB_V + lane];
-      if (lane < 4) v1 += vb[VB_V + 32 + lane];
-      if (lane < 6) bb += vb[VB_B + lane];
-      for (int o = lane; o < 36; o += 32) sY[k * 36 + o] = vb[VB_Y + o];
-      for (int o = lane; o < PD * 6; o += 32) Wout[(size_t)p.intr_off[k] * 6 + o] = vb[VB_W + o];
+      const double* __restrict__ vb = p.VB + (size_t)view * VB_STRIDE;
+      const double a0 = vb[VB_V + lane];
+      const double a1 = lane < 4 ? vb[VB_V + 32 + lane] : 0.0;
+      const double a2 = lane < 6 ? vb[VB_B + lane] : 0.0;
+      const double y0 = vb[VB_Y + lane];
+      const double y1 = lane < 4 ? vb[VB_Y + 32 + lane] : 0.0;
+      const double w0 = lane < PD * 6 ? vb[VB_W + lane] : 0.0;
+      const double w1 = lane + 32 < PD * 6 ? vb[VB_W + 32 + lane] : 0.0;
+      v0 += a0;
+      v1 += a1;
+      bb += a2;
+      sY[k * 36 + lane] = y0;
+      if (lane < 4) sY[k * 36 + 32 + lane] = y1;
+      if (lane < PD * 6) Wout[(size_t)p.intr_off[k] * 6 + lane] = w0;
+      if (lane + 32 < PD * 6) Wout[(size_t)p.intr_off[k] * 6 + 32 + lane] = w1;
     }
     p.V[(size_t)set * 36 + lane] = v0;
     if (lane < 4) p.V[(size_t)set * 36 + 32 + lane] = v1;
@@ -760,19 +814,48 @@ __global__ void gram_cost_kernel(DevProblem p, double* __restrict__ out) {
 
 // =========================================================================================================
 // Schur complement on the FP64 tensor pipe:  partial = sum_{v in CTA slice} Z_v Z_v^T,  Z_v = [W_v ; b_v^T] L_v^-T,
-// (V_v + d I) = L_v L_v^T.  Two sets per step (K = 12 = 3 k-steps of the m8n8k4 DMMA).
+// (V_v + d I) = L_v L_v^T.  pose_factor_kernel inverts the 6x6 factors (thread per set); schur_kernel then turns the rows
+// of [W_v ; b_v^T] into Z rows with a 6x6 triangular product and accumulates Z Z^T with DMMA, SC_SETS sets per step.
 // =========================================================================================================
-constexpr int SC_LD = 20;  // 12 k-columns + pad; ld % 16 == 4 keeps the operand loads conflict-free
+__global__ void __launch_bounds__(128) pose_factor_kernel(DevProblem p, double damping, int* __restrict__ pos_def_flag) {
+  const int set = blockIdx.x * blockDim.x + threadIdx.x;
+  if (set >= p.n_sets) return;
+  double L[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) L[i] = p.V[(size_t)set * 36 + i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) L[i * 6 + i] += damping;
+  if (!chol6(L)) *pos_def_flag = 0;
+  // Li = L^-1 (lower triangular), column by column
+  double Li[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) Li[i] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    Li[c * 6 + c] = 1.0 / L[c * 6 + c];
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = c; k < r; ++k) s -= L[r * 6 + k] * Li[k * 6 + c];
+      Li[r * 6 + c] = s / L[r * 6 + r];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 36; ++i) p.Lv[(size_t)set * 36 + i] = Li[i];
+}
+
+constexpr int SC_SETS = 4;              // sets per step: K = 24 = 6 k-steps of the m8n8k4 DMMA
+constexpr int SC_K = SC_SETS * 6;
+constexpr int SC_LD = 36;               // ld % 16 == 4 keeps the operand loads conflict-free
 
 template <int WARPS, int MAX_PAIRS>
-__global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, double damping, double* __restrict__ partials, int sets_per_cta,
-                                                                int* __restrict__ pos_def_flag) {
+__global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, double* __restrict__ partials, int sets_per_cta) {
   extern __shared__ __align__(16) double smem[];
   const int n = p.n_aug;
   const int nt = (n + 7) >> 3;
   const int n_pad = nt * 8;
-  double* Zs = smem;                  // [n_pad][SC_LD]
-  double* Ls = Zs + n_pad * SC_LD;    // [2][36]
+  double* Zbuf = smem;  // [2][n_pad][SC_LD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int arow = lane >> 2, acol = lane & 3;
   const int npairs = nt * (nt + 1) / 2;
@@ -795,42 +878,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
     acc[q][0] = 0.0;
     acc[q][1] = 0.0;
   }
-  for (int i = tid; i < n_pad * SC_LD; i += blockDim.x) Zs[i] = 0.0;
-  __syncthreads();
+  for (int i = tid; i < 2 * n_pad * SC_LD; i += blockDim.x) Zbuf[i] = 0.0;
   const int s_lo = blockIdx.x * sets_per_cta, s_hi = min(p.n_sets, s_lo + sets_per_cta);
-  for (int s0 = s_lo; s0 < s_hi; s0 += 2) {
-    if (tid < 2) {  // factor the (up to) two pose blocks of this step
-      const int set = s0 + tid;
-      double L[36];
-      if (set < s_hi) {
-#pragma unroll
-        for (int i = 0; i < 36; ++i) L[i] = p.V[(size_t)set * 36 + i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) L[i * 6 + i] += damping;
-        if (!chol6(L)) *pos_def_flag = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = i + 1; j < 6; ++j) L[i * 6 + j] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 36; ++i) p.Lv[(size_t)set * 36 + i] = L[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < 36; ++i) L[i] = (i % 7 == 0) ? 1.0 : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < 36; ++i) Ls[tid * 36 + i] = L[i];
-    }
-    __syncthreads();
-    for (int o = tid; o < 2 * n; o += blockDim.x) {  // rows of Z for both sets
+  // rows of Z for the sets [s0, s0 + SC_SETS): z = Linv * w (lower triangular 6x6 product)
+  auto fill = [&](double* Zs, int s0) {
+    for (int o = tid; o < SC_SETS * n; o += blockDim.x) {
       const int which = o / n, r = o % n;
       const int set = s0 + which;
       double z[6] = {0, 0, 0, 0, 0, 0};
       if (set < s_hi) {
         const double* src = (r < p.n_c) ? (p.W + ((size_t)set * p.n_c + r) * 6) : (p.bv + (size_t)set * 6);
+        const double* Li = p.Lv + (size_t)set * 36;
+        double w[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) z[c] = src[c];
-        fwd6(Ls + which * 36, z);
+        for (int c = 0; c < 6; ++c) w[c] = src[c];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k <= i; ++k) s += __ldg(Li + i * 6 + k) * w[k];
+          z[i] = s;
+        }
         if (r == p.n_c) {
 #pragma unroll
           for (int c = 0; c < 6; ++c) p.yv[(size_t)set * 6 + c] = z[c];
@@ -839,9 +907,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
 #pragma unroll
       for (int c = 0; c < 6; ++c) Zs[r * SC_LD + which * 6 + c] = z[c];
     }
-    __syncthreads();
+  };
+  __syncthreads();
+  if (s_lo < s_hi) fill(Zbuf, s_lo);
+  __syncthreads();
+  int buf = 0;
+  for (int s0 = s_lo; s0 < s_hi; s0 += SC_SETS) {
+    const double* Zs = Zbuf + (size_t)buf * n_pad * SC_LD;
+    if (s0 + SC_SETS < s_hi) fill(Zbuf + (size_t)(buf ^ 1) * n_pad * SC_LD, s0 + SC_SETS);  // overlaps the DMMA phase below
 #pragma unroll
-    for (int kk = 0; kk < 3; ++kk) {
+    for (int kk = 0; kk < SC_K / 4; ++kk) {
 #pragma unroll
       for (int q = 0; q < MAX_PAIRS; ++q) {
         if (ti[q] >= 0) {
@@ -852,6 +927,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
       }
     }
     __syncthreads();
+    buf ^= 1;
   }
   double* out = partials + (size_t)blockIdx.x * n_pad * n_pad;
 #pragma unroll
@@ -873,6 +949,7 @@ __global__ void __launch_bounds__(256) schur_finalize_kernel(DevProblem p, const
   if (i > j) return;
   // within a diagonal tile only the mma's own (i,j) entry is used for i<=j, so the result is exactly symmetric
   double s = 0.0;
+#pragma unroll 8
   for (int c = 0; c < n_partials; ++c) s += partials[(size_t)c * n_pad * n_pad + (size_t)i * n_pad + j];
   const double v = p.U[(size_t)i * n + j] - s;
   p.Sred[(size_t)i * n + j] = v;
@@ -883,69 +960,168 @@ __global__ void __launch_bounds__(256) schur_finalize_kernel(DevProblem p, const
 // reduced solve: one CTA.  Left-looking Cholesky of the augmented reduced system held packed (lower) in shared
 // memory; the augmented last row comes out as y = L^-1 b, then L^T x = y.
 // =========================================================================================================
-constexpr int RS_THREADS = 1024;
+constexpr int RS_THREADS = 256;
+constexpr int RS_NB = 8;  // panel width = DMMA tile
 __device__ __forceinline__ int tri(int i, int k) { return i * (i + 1) / 2 + k; }
 
+// Cholesky of the W x W diagonal block at (j0, j0) of the packed matrix and the inverse of its factor; fully unrolled so that
+// the block lives in registers.  Returns false if a pivot is not positive.
+template <int W>
+__device__ __forceinline__ bool diag_block(double* __restrict__ Lp, int j0, double* __restrict__ s_Linv) {
+  double L[W][W], Li[W][W], rd[W];
+  bool ok = true;
+#pragma unroll
+  for (int r = 0; r < W; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) L[r][c] = Lp[(j0 + r) * (j0 + r + 1) / 2 + j0 + c];
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    double d = L[c][c];
+#pragma unroll
+    for (int k = 0; k < c; ++k) d -= L[c][k] * L[c][k];
+    if (!(d > 0.0)) ok = false;
+    d = sqrt(d);
+    L[c][c] = d;
+    rd[c] = 1.0 / d;
+#pragma unroll
+    for (int r = c + 1; r < W; ++r) {
+      double v = L[r][c];
+#pragma unroll
+      for (int k = 0; k < c; ++k) v -= L[r][k] * L[c][k];
+      L[r][c] = v * rd[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    Li[c][c] = rd[c];
+#pragma unroll
+    for (int r = c + 1; r < W; ++r) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = c; k < r; ++k) v -= L[r][k] * Li[k][c];
+      Li[r][c] = v * rd[r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < W; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) {
+      Lp[(j0 + r) * (j0 + r + 1) / 2 + j0 + c] = L[r][c];
+      s_Linv[r * 8 + c] = Li[r][c];
+    }
+  return ok;
+}
+template <int W>
+__device__ __forceinline__ void panel_rows(double* __restrict__ Lp, int j0, int n, const double* __restrict__ s_Linv, int tid, int nthreads) {
+  for (int row = j0 + W + tid; row < n; row += nthreads) {
+    double a[W], x[W];
+    double* base = Lp + row * (row + 1) / 2 + j0;
+#pragma unroll
+    for (int c = 0; c < W; ++c) a[c] = base[c];
+#pragma unroll
+    for (int c = 0; c < W; ++c) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k <= c; ++k) v += a[k] * s_Linv[c * 8 + k];
+      x[c] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < W; ++c) base[c] = x[c];
+  }
+}
+
+// Blocked left-looking Cholesky of the augmented reduced system (n_aug = n_c + 1 rows; the last row carries the rhs and
+// comes out as y = L^-1 b), packed lower triangle in shared memory.  Per 8-column panel:
+//   1. all warps: A[rows >= j0][panel] -= L[rows][0:j0] L[panel][0:j0]^T with DMMA m8n8k4 (operands straight from the packed rows),
+//   2. thread 0: Cholesky of the 8x8 diagonal block and its inverse,
+//   3. thread per row: L[row][panel] = A[row][panel] Ldd^-T.
+// Then L^T x = y with one barrier per unknown.
 __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping, int* __restrict__ pos_def_flag) {
-  extern __shared__ __align__(16) double Lp[];  // packed lower, n_aug rows
-  __shared__ double s_piv;
+  extern __shared__ __align__(16) double Lp[];  // packed lower triangle, n_rows rows (zero padded)
+  __shared__ double s_Ldd[RS_NB * RS_NB], s_Linv[RS_NB * RS_NB];
+  __shared__ double s_slot[2];
   __shared__ int s_ok;
   const int n = p.n_aug, nc = p.n_c;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < n * (n + 1) / 2; idx += RS_THREADS) {
-    // idx -> (i,k)
-    int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-    while (tri(i, 0) > idx) --i;
-    while (tri(i + 1, 0) <= idx) ++i;
-    const int k = idx - tri(i, 0);
-    double v = p.Sred[(size_t)i * n + k];
+  const int n_rows = ((n + RS_NB - 1) / RS_NB) * RS_NB + RS_NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < n_rows * (n_rows + 1) / 2; idx += RS_THREADS) Lp[idx] = 0.0;
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += RS_THREADS) {
+    const int i = idx / n, k = idx % n;
+    if (k > i) continue;
+    double v = p.Sred[idx];
     if (i == k && i < nc) v += damping;
-    Lp[idx] = v;
+    Lp[tri(i, k)] = v;
   }
   if (tid == 0) s_ok = 1;
   __syncthreads();
-  // 4 threads cooperate on one row
-  const int row_of_thread = tid >> 2, sub = tid & 3;
-  for (int j = 0; j < nc; ++j) {
-    // s_i = A[i][j] - sum_{k<j} L[i][k] L[j][k]  for rows i >= j handled in strides
-    for (int base = j; base < n; base += RS_THREADS / 4) {  // trip count uniform across the warp (shuffles inside)
-      const int i = base + row_of_thread;
-      const bool act = i < n;
-      double s = 0.0;
-      const double* Li = Lp + tri(act ? i : j, 0);
-      const double* Lj = Lp + tri(j, 0);
-      if (act)
-        for (int k = sub; k < j; k += 4) s += Li[k] * Lj[k];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (act && sub == 0) {
-        const double v = Li[j] - s;
-        Lp[tri(i, j)] = v;
-        if (i == j) {
-          s_piv = v;
-          if (!(v > 0.0)) s_ok = 0;
+  const int arow = lane >> 2, acol = lane & 3;
+  for (int j0 = 0; j0 < nc; j0 += RS_NB) {
+    const int w = min(RS_NB, nc - j0);
+    // ---- 1. panel update on the tensor pipe ----
+    if (j0 > 0) {
+      const int first_tile = j0 / RS_NB, n_tiles = (n + RS_NB - 1) / RS_NB;
+      const double* Bbase = Lp + tri(j0 + arow, 0);  // B fragment: L[j0 + lane/4][k0 + lane%4]
+      for (int t = first_tile + warp; t < n_tiles; t += RS_THREADS / 32) {
+        const double* Abase = Lp + tri(RS_NB * t + arow, 0);
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+        for (int k0 = 0; k0 < j0; k0 += 8) {  // two independent chains
+          dmma(c0, c1, Abase[k0 + acol], Bbase[k0 + acol]);
+          dmma(e0, e1, Abase[k0 + 4 + acol], Bbase[k0 + 4 + acol]);
+        }
+        c0 += e0;
+        c1 += e1;
+        const int row = RS_NB * t + arow, col = j0 + 2 * acol;
+        if (row < n) {
+          if (col <= row && col < j0 + w) Lp[tri(row, col)] -= c0;
+          if (col + 1 <= row && col + 1 < j0 + w) Lp[tri(row, col + 1)] -= c1;
         }
       }
+      __syncthreads();
+    }
+    // ---- 2. diagonal block: Cholesky and inverse (one thread, registers) ----
+    if (tid == 0) {
+      bool ok = true;
+      switch (w) {
+        case 8: ok = diag_block<8>(Lp, j0, s_Linv); break;
+        case 7: ok = diag_block<7>(Lp, j0, s_Linv); break;
+        case 6: ok = diag_block<6>(Lp, j0, s_Linv); break;
+        case 5: ok = diag_block<5>(Lp, j0, s_Linv); break;
+        case 4: ok = diag_block<4>(Lp, j0, s_Linv); break;
+        case 3: ok = diag_block<3>(Lp, j0, s_Linv); break;
+        case 2: ok = diag_block<2>(Lp, j0, s_Linv); break;
+        default: ok = diag_block<1>(Lp, j0, s_Linv); break;
+      }
+      if (!ok) s_ok = 0;
     }
     __syncthreads();
-    const double piv = sqrt(s_piv);
-    const double ip = 1.0 / piv;
-    for (int i = j + tid; i < n; i += RS_THREADS) Lp[tri(i, j)] = (i == j) ? piv : Lp[tri(i, j)] * ip;
+    // ---- 3. rows below the block: x = a Ldd^-T ----
+    switch (w) {
+      case 8: panel_rows<8>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
+      case 7: panel_rows<7>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
+      case 6: panel_rows<6>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
+      case 5: panel_rows<5>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
+      case 4: panel_rows<4>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
+      case 3: panel_rows<3>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
+      case 2: panel_rows<2>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
+      default: panel_rows<1>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
+    }
     __syncthreads();
   }
-  if (!s_ok) {
-    if (tid == 0) *pos_def_flag = 0;
-  }
-  // back substitution L^T x = y ; y is row nc of the factor (columns 0..nc-1)
-  double* y = Lp + tri(nc, 0);
+  if (tid == 0 && !s_ok) *pos_def_flag = 0;
+  // back substitution L^T x = y ; y is row nc of the factor.  Thread k owns x_k; one barrier per step.
+  double yk = (tid < nc) ? Lp[tri(nc, tid)] : 0.0;
   for (int i = nc - 1; i >= 0; --i) {
-    if (tid == 0) y[i] = y[i] / Lp[tri(i, i)];
+    if (tid == i) {
+      yk = yk / Lp[tri(i, i)];
+      s_slot[i & 1] = yk;
+    }
     __syncthreads();
-    const double xi = y[i];
-    for (int k = tid; k < i; k += RS_THREADS) y[k] -= Lp[tri(i, k)] * xi;
-    __syncthreads();
+    const double xi = s_slot[i & 1];
+    if (tid < i) yk -= Lp[tri(i, tid)] * xi;
   }
-  for (int i = tid; i < nc; i += RS_THREADS) p.dxc[i] = y[i];
+  if (tid < nc) p.dxc[tid] = yk;
+  (void)s_Ldd;
 }
 
 // =========================================================================================================
@@ -972,9 +1148,23 @@ __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* _
     double r[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) r[c] = p.bv[(size_t)set * 6 + c] - acc[c];
-    const double* L = p.Lv + (size_t)set * 36;
-    fwd6(L, r);
-    bwd6(L, r);
+    // (V + dI)^-1 r = Linv^T (Linv r)
+    const double* Li = p.Lv + (size_t)set * 36;
+    double t[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k <= i; ++k) s += Li[i * 6 + k] * r[k];
+      t[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = i; k < 6; ++k) s += Li[k * 6 + i] * t[k];
+      r[i] = s;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       p.dx[set_col_q[set] + c] = r[c];
@@ -1127,7 +1317,7 @@ cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int
 int la_grid_warps() { return sm_count() * 2 * LA_WARPS; }
 
 template <int MODEL, bool WRITE_E>
-static cudaError_t launch_la_model(const DevProblem& p, const int* view_list, const int4* slices, int lo, int hi, StreamCtx& s) {
+static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const int4* slices, int lo, int hi, StreamCtx& s) {
   if (hi <= lo) return cudaSuccess;
   const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
   static size_t attr_smem = 0;
@@ -1137,21 +1327,30 @@ static cudaError_t launch_la_model(const DevProblem& p, const int* view_list, co
     attr_smem = smem;
   }
   const int grid = min((hi - lo + LA_WARPS - 1) / LA_WARPS, sm_count() * 2);
-  linearise_assemble_kernel<MODEL, WRITE_E><<<grid, LA_THREADS, smem, s.stream>>>(p, view_list, slices, lo, hi);
+  static int variant = -1;
+  if (variant < 0) variant = getenv("KB_LA_VARIANT") ? atoi(getenv("KB_LA_VARIANT")) : 0;  // timing experiments only (wrong results)
+  if (MODEL == 0 && WRITE_E && variant == 1) {
+    cudaFuncSetAttribute(linearise_assemble_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    linearise_assemble_kernel<0, true, 1><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
+  } else if (MODEL == 0 && WRITE_E && variant == 2) {
+    cudaFuncSetAttribute(linearise_assemble_kernel<0, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    linearise_assemble_kernel<0, true, 2><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
+  } else
+  linearise_assemble_kernel<MODEL, WRITE_E><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
 
 // slice_model_begin[m] .. [m+1]: slices of camera model m
-cudaError_t launch_linearise_assemble(const DevProblem& p, const int* view_list, const int4* slices, const int* smb, bool write_e, StreamCtx& s) {
+cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, const int4* slices, const int* smb, bool write_e, StreamCtx& s) {
   cudaError_t e;
   if (p.n_sets > 0) {
     set_prep_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p);
     KB_LAUNCHED(s);
   }
 #define KB_LA(M)                                                                                      \
-  if ((e = write_e ? launch_la_model<M, true>(p, view_list, slices, smb[M], smb[M + 1], s)            \
-                   : launch_la_model<M, false>(p, view_list, slices, smb[M], smb[M + 1], s)) != cudaSuccess) return e;
+  if ((e = write_e ? launch_la_model<M, true>(p, vmeta, slices, smb[M], smb[M + 1], s)                \
+                   : launch_la_model<M, false>(p, vmeta, slices, smb[M], smb[M + 1], s)) != cudaSuccess) return e;
   KB_LA(0) KB_LA(1) KB_LA(2) KB_LA(3) KB_LA(4)
 #undef KB_LA
   return cudaGetLastError();
@@ -1208,8 +1407,8 @@ cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s) {
 static int schur_sets_per_cta(const DevProblem& p) {
   const int ctas = sm_count();
   int per = (p.n_sets + ctas - 1) / ctas;
-  per = (per + 1) & ~1;
-  return per < 2 ? 2 : per;
+  per = ((per + SC_SETS - 1) / SC_SETS) * SC_SETS;
+  return per < SC_SETS ? SC_SETS : per;
 }
 int schur_num_partials(const DevProblem& p) {
   const int per = schur_sets_per_cta(p);
@@ -1222,16 +1421,16 @@ size_t schur_partial_stride(const DevProblem& p) {
 }
 
 template <int WARPS, int MAX_PAIRS>
-static cudaError_t launch_schur_t(const DevProblem& p, double damping, double* partials, int n_partials, int* flag, StreamCtx& s) {
+static cudaError_t launch_schur_t(const DevProblem& p, double* partials, int n_partials, StreamCtx& s) {
   const int n_pad = ((p.n_aug + 7) >> 3) * 8;
-  const size_t smem = sizeof(double) * ((size_t)n_pad * SC_LD + 72);
+  const size_t smem = sizeof(double) * (2 * (size_t)n_pad * SC_LD);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(schur_kernel<WARPS, MAX_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  schur_kernel<WARPS, MAX_PAIRS><<<n_partials, WARPS * 32, smem, s.stream>>>(p, damping, partials, schur_sets_per_cta(p), flag);
+  schur_kernel<WARPS, MAX_PAIRS><<<n_partials, WARPS * 32, smem, s.stream>>>(p, partials, schur_sets_per_cta(p));
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -1239,10 +1438,14 @@ static cudaError_t launch_schur_t(const DevProblem& p, double damping, double* p
 cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* flag, StreamCtx& s) {
   cudaError_t e = cudaMemsetAsync(partials, 0, sizeof(double) * schur_partial_stride(p) * n_partials, s.stream);
   if (e != cudaSuccess) return e;
+  if (p.n_sets > 0) {
+    pose_factor_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p, damping, flag);
+    KB_LAUNCHED(s);
+  }
   const int nt = (p.n_aug + 7) >> 3;
-  if (nt <= 6) return launch_schur_t<8, 3>(p, damping, partials, n_partials, flag, s);
-  if (nt <= 14) return launch_schur_t<8, 14>(p, damping, partials, n_partials, flag, s);
-  if (nt <= 28) return launch_schur_t<16, 26>(p, damping, partials, n_partials, flag, s);
+  if (nt <= 6) return launch_schur_t<8, 3>(p, partials, n_partials, s);
+  if (nt <= 14) return launch_schur_t<8, 14>(p, partials, n_partials, s);
+  if (nt <= 28) return launch_schur_t<16, 26>(p, partials, n_partials, s);
   return cudaErrorInvalidValue;
 }
 
@@ -1254,7 +1457,8 @@ cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const
 }
 
 cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s) {
-  const size_t smem = sizeof(double) * ((size_t)p.n_aug * (p.n_aug + 1) / 2);
+  const size_t n_rows = ((p.n_aug + RS_NB - 1) / RS_NB) * RS_NB + RS_NB;
+  const size_t smem = sizeof(double) * (n_rows * (n_rows + 1) / 2);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
