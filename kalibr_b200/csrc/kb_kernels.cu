@@ -459,9 +459,11 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
         if (VARIANT == 1) {  // timing experiment: no tensor work
           c00[0] += XT[arow * XT_LD + acol]; c01[0] += XT[(8 + arow) * XT_LD + acol]; c11[1] += XT[lane];
         } else {
-          // two independent accumulator sets (even / odd k-steps): six DMMA dependency chains per warp instead of three
+          // two independent accumulator sets (even / odd k-steps); a partial last chunk only spends DMMAs on rows that exist
+          const int ksteps = (min(32, e - base) + 1) >> 1;  // 2 rows per term, 4 rows per k-step
 #pragma unroll
           for (int s = 0; s < 16; s += 2) {
+            if (s >= ksteps) break;
             const double x0 = XT[arow * XT_LD + 4 * s + acol];
             const double x1 = XT[(8 + arow) * XT_LD + 4 * s + acol];
             const double z0 = XT[arow * XT_LD + 4 * s + 4 + acol];
@@ -542,18 +544,275 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
   }
 }
 
+// ---- warp-specialised variant of the fused kernel ------------------------------------------------------------
+// One persistent 16-warp CTA per SM: 12 PRODUCER warps linearise 32-term chunks (lane per term, FP64 scalar pipe) into
+// their own shared-memory row buffer, 4 CONSUMER warps (one per SM sub-partition) do nothing but the DMMA Gram
+// accumulation, each serving 3 producers through mbarrier full/empty hand-offs.  When a view's last chunk has been
+// accumulated the consumer drops the 16x16 Gram block into the producer's G buffer and the PRODUCER runs the view
+// epilogue (view block + slice Gram sum), deferred until after it has submitted the next view's first chunk, so that
+// neither role waits on the other in steady state and the tensor pipe is fed continuously.
+constexpr int WS_CONSUMERS = 4;
+constexpr int WS_PRODUCERS = 12;
+constexpr int WS_THREADS = 32 * (WS_CONSUMERS + WS_PRODUCERS);
+constexpr int WS_G_DOUBLES = GRAM_DIM * G_LD;  // 272
+constexpr int WS_PROD_DOUBLES = XT_WARP_DOUBLES + 2 * WS_G_DOUBLES + 3 * 36 + 3 * SETPREP_STRIDE;  // XT | Gbuf | slice sum | Pi,M,Y | set consts x3
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+
+template <int MODEL, bool WRITE_E>
+__global__ void __launch_bounds__(WS_THREADS, 1) linearise_assemble_ws_kernel(DevProblem p, const int4* __restrict__ vmeta,
+                                                                                const int4* __restrict__ slices, int slice_lo, int slice_hi) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ unsigned long long bar_full[WS_PRODUCERS], bar_empty[WS_PRODUCERS], bar_g[WS_PRODUCERS];
+  __shared__ int s_info[WS_PRODUCERS];  // bits 0-7: DMMA k-steps of the chunk, bit 8: last chunk of the view; -1: producer finished
+  double* s_target = smem;
+  const int target_doubles = (p.n_target * 3 + 1) & ~1;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
+  if (threadIdx.x < WS_PRODUCERS) {
+    mbar_init(&bar_full[threadIdx.x], 1);
+    mbar_init(&bar_empty[threadIdx.x], 1);
+    mbar_init(&bar_g[threadIdx.x], 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncthreads();
+  const int arow = lane >> 2, acol = lane & 3;
+  const int gc = 2 * acol;
+  double* prod_base = smem + target_doubles;
+
+  if (wib < WS_CONSUMERS) {
+    // =============================== consumer: DMMA only ===============================
+    double acc[3][6];
+    unsigned ph[3] = {0u, 0u, 0u};
+    bool done[3] = {false, false, false};
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int t = 0; t < 6; ++t) acc[q][t] = 0.0;
+    int n_done = 0;
+    while (n_done < 3) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int pr = wib + WS_CONSUMERS * q;  // producers served by this consumer
+        if (done[q] || !mbar_try_wait(&bar_full[pr], ph[q])) continue;
+        ph[q] ^= 1u;
+        const int info = s_info[pr];
+        if (info < 0) {
+          done[q] = true;
+          ++n_done;
+          continue;
+        }
+        const double* XT = prod_base + (size_t)pr * WS_PROD_DOUBLES;
+        const int ksteps = info & 0xff;  // a partial last chunk only spends DMMAs on rows that exist
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+          if (s >= ksteps) break;
+          const double x0 = XT[arow * XT_LD + 4 * s + acol];
+          const double x1 = XT[(8 + arow) * XT_LD + 4 * s + acol];
+          dmma(acc[q][0], acc[q][1], x0, x0);
+          dmma(acc[q][2], acc[q][3], x0, x1);
+          dmma(acc[q][4], acc[q][5], x1, x1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[pr]);  // every lane's operand loads have been consumed by its DMMAs
+        if (info & 0x100) {
+          double* G = prod_base + (size_t)pr * WS_PROD_DOUBLES + XT_WARP_DOUBLES;
+          G[arow * G_LD + gc] = acc[q][0];
+          G[arow * G_LD + gc + 1] = acc[q][1];
+          G[arow * G_LD + 8 + gc] = acc[q][2];
+          G[arow * G_LD + 8 + gc + 1] = acc[q][3];
+          G[(8 + gc) * G_LD + arow] = acc[q][2];
+          G[(8 + gc + 1) * G_LD + arow] = acc[q][3];
+          G[(8 + arow) * G_LD + 8 + gc] = acc[q][4];
+          G[(8 + arow) * G_LD + 8 + gc + 1] = acc[q][5];
+#pragma unroll
+          for (int t = 0; t < 6; ++t) acc[q][t] = 0.0;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_g[pr]);
+        }
+      }
+    }
+    return;
+  }
+
+  // =============================== producer ===============================
+  const int me = wib - WS_CONSUMERS;
+  double* XT = prod_base + (size_t)me * WS_PROD_DOUBLES;
+  double* G = XT + XT_WARP_DOUBLES;
+  double* sG = G + WS_G_DOUBLES;  // slice sum, same full layout as G
+  double* sPi = sG + WS_G_DOUBLES;
+  double* sM = sPi + 36;
+  double* sY = sM + 36;
+  double* sSP = sY + 36;          // [3][48]
+  constexpr int PD = model_P(MODEL) + model_D(MODEL);
+  unsigned ph_empty = 1u, ph_g = 0u;  // a fresh barrier reports the "previous" phase (parity 1) as complete
+  const int pw = blockIdx.x * WS_PRODUCERS + me;
+  const int n_pw = gridDim.x * WS_PRODUCERS;
+
+  // view epilogue from the Gram block the consumer left in G
+  auto epilogue = [&](int view, const double* sp) {
+    mbar_wait(&bar_g[me], ph_g);
+    ph_g ^= 1u;
+    for (int o = lane; o < 36; o += 32) {  // M = Pi_k P_v
+      const int r = o / 6, c = o % 6;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sPi[r * 6 + a] * sp[12 + a * 6 + c];
+      sM[o] = s;
+    }
+    for (int o = lane; o < WS_G_DOUBLES; o += 32) sG[o] += G[o];
+    __syncwarp();
+    double* vb = p.VB + (size_t)view * VB_STRIDE;
+    for (int o = lane; o < 36; o += 32) {  // Y = G_xx M
+      const int r = o / 6, c = o % 6;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += G[r * G_LD + a] * sM[a * 6 + c];
+      sY[o] = s;
+      vb[VB_Y + o] = s;
+    }
+    for (int o = lane; o < PD * 6; o += 32) {  // W_k = G_cx M
+      const int r = o / 6, c = o % 6;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += G[(6 + r) * G_LD + a] * sM[a * 6 + c];
+      vb[VB_W + o] = s;
+    }
+    if (lane < 6) {  // b_k = -M^T G_xe
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sM[a * 6 + lane] * G[a * G_LD + E_COL];
+      vb[VB_B + lane] = -s;
+    }
+    __syncwarp();
+    for (int o = lane; o < 36; o += 32) {  // V_k = M^T Y
+      const int r = o / 6, c = o % 6;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sM[a * 6 + r] * sY[a * 6 + c];
+      vb[VB_V + o] = s;
+    }
+    __syncwarp();
+  };
+
+  for (int sl = slice_lo + pw; sl < slice_hi; sl += n_pw) {
+    const int4 S = slices[sl];
+    const int cam = S.z;
+    double prm[CAM_PARAM_STRIDE];
+#pragma unroll
+    for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
+    double camT[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) camT[i] = p.camT[cam * 12 + i];
+    for (int o = lane; o < 36; o += 32) sPi[o] = p.camPi[cam * 36 + o];
+    for (int o = lane; o < WS_G_DOUBLES; o += 32) sG[o] = 0.0;
+    int4 m_cur = vmeta[S.x];
+    int4 m_nxt = (S.x + 1 < S.y) ? vmeta[S.x + 1] : m_cur;
+    if (lane < 24) cp_async_16(sSP + 2 * lane, p.set_prep + (size_t)m_cur.y * SETPREP_STRIDE + 2 * lane);
+    cp_async_commit();
+    int pend_view = -1;
+    const double* pend_sp = sSP;
+    for (int vi = S.x; vi < S.y; ++vi) {
+      const int buf = (vi - S.x) % 3;
+      const int view = m_cur.x;
+      const int b = m_cur.z, e = m_cur.w;
+      int i = b + lane;
+      bool active = i < e;
+      int ii = active ? i : b;
+      double yu = 0.0, yv = 0.0;
+      int cid = 0;
+      if (b < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+      const int4 m_nn = (vi + 2 < S.y) ? vmeta[vi + 2] : m_nxt;
+      cp_async_wait_all();
+      __syncwarp();
+      if (b >= e && pend_view >= 0) { epilogue(pend_view, pend_sp); pend_view = -1; }  // an empty view has no chunk to hide it behind
+      if (vi + 1 < S.y && lane < 24)
+        cp_async_16(sSP + ((buf + 1) % 3) * SETPREP_STRIDE + 2 * lane, p.set_prep + (size_t)m_nxt.y * SETPREP_STRIDE + 2 * lane);
+      cp_async_commit();
+      const double* sp = sSP + buf * SETPREP_STRIDE;
+      double Rcw[9], tcw[3];
+      view_transform_prepped(sp, camT, Rcw, tcw);
+      for (int base = b; base < e; base += 32) {
+        const double cyu = yu, cyv = yv;
+        const int ccid = cid;
+        const bool cactive = active;
+        const int ci = i;
+        const bool last = base + 32 >= e;
+        i = base + 32 + lane;
+        active = i < e;
+        ii = active ? i : b;
+        if (!last) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+        double a0[GRAM_DIM], a1[GRAM_DIM];
+        term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, cactive, a0, a1, p.n_invalid);
+        if (WRITE_E && cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-a0[E_COL], -a1[E_COL]);
+        // the G buffer must be free before a 'last' chunk is handed over
+        if (pend_view >= 0 && last) { epilogue(pend_view, pend_sp); pend_view = -1; }
+        mbar_wait(&bar_empty[me], ph_empty);
+        ph_empty ^= 1u;
+#pragma unroll
+        for (int c = 0; c < GRAM_DIM; ++c) *reinterpret_cast<double2*>(XT + c * XT_LD + 2 * lane) = make_double2(a0[c], a1[c]);
+        if (lane == 0) s_info[me] = ((min(32, e - base) + 1) >> 1) | (last ? 0x100 : 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[me]);
+        if (pend_view >= 0) { epilogue(pend_view, pend_sp); pend_view = -1; }
+      }
+      if (b < e) { pend_view = view; pend_sp = sp; }
+      m_cur = m_nxt;
+      m_nxt = m_nn;
+    }
+    if (pend_view >= 0) epilogue(pend_view, pend_sp);
+    cp_async_wait_all();
+    // slice Gram sum in the tile order finalize_gram_kernel expects
+    double* out = p.gram_partial + (size_t)sl * GRAM_TILES;
+    for (int t = lane; t < GRAM_TILES; t += 32) {
+      const int tile = t >> 6, ln = (t & 63) >> 1, el = t & 1;
+      const int r = (tile == 2 ? 8 : 0) + (ln >> 2), c = (tile >= 1 ? 8 : 0) + 2 * (ln & 3) + el;
+      out[t] = sG[r * G_LD + c];
+    }
+    __syncwarp();
+  }
+  // tell the consumer this producer is finished
+  mbar_wait(&bar_empty[me], ph_empty);
+  if (lane == 0) {
+    s_info[me] = -1;
+    mbar_arrive(&bar_full[me]);
+  }
+}
+
 // ---- materialising linearise: e and J in the CCS J^T layout of the reference -----------------------------------
 // Per term two columns of J^T (= rows of J), each W_k = 6 + 6k + P + D values ordered by design-variable block index
 // (lin_off gives the slot of every DV segment for camera k).
+constexpr int LM_WARPS = 4;
+constexpr int LM_THREADS = LM_WARPS * 32;
+constexpr int LM_STAGE_TERMS = 16;  // rows of 16 terms are staged in shared memory, then written to HBM fully coalesced
+
 template <int MODEL>
-__global__ void __launch_bounds__(EVAL_THREADS) linearise_materialise_kernel(DevProblem p, const int* __restrict__ view_list, int n_list,
-                                                                              double* __restrict__ jt) {
+__global__ void __launch_bounds__(LM_THREADS) linearise_materialise_kernel(DevProblem p, const int* __restrict__ view_list, int n_list,
+                                                                            double* __restrict__ jt, int stage_doubles) {
   extern __shared__ __align__(16) double smem[];
   double* s_target = smem;
   const int target_doubles = (p.n_target * 3 + 1) & ~1;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  double* Mk = smem + target_doubles + wib * 36;  // Pi_k * P_v
+  double* Mk = smem + target_doubles + wib * (36 + stage_doubles);  // Pi_k * P_v
+  double* stage = Mk + 36;                                          // [16 terms][2][W]
   for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
   __syncthreads();
   constexpr int P = model_P(MODEL), D = model_D(MODEL);
@@ -585,38 +844,54 @@ __global__ void __launch_bounds__(EVAL_THREADS) linearise_materialise_kernel(Dev
     const int* off = p.lin_off + cam * LIN_OFF_STRIDE;
     const int W = 6 + 6 * cam + P + D;
     const long long jbase = p.view_jbase[view];
-    for (int i = b + lane; i < e; i += 32) {
+    for (int base = b; base < e; base += 32) {
+      const int i = base + lane;
+      const bool active = i < e;
+      const int ii = active ? i : b;
       double a[2][GRAM_DIM];
-      term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * p.corner[i], p.y_u[i], p.y_v[i], true, a[0], a[1], p.n_invalid);
-      reinterpret_cast<double2*>(p.e)[i] = make_double2(-a[0][E_COL], -a[1][E_COL]);
+      term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * p.corner[ii], p.y_u[ii], p.y_v[ii], active, a[0], a[1], p.n_invalid);
+      if (active) reinterpret_cast<double2*>(p.e)[i] = make_double2(-a[0][E_COL], -a[1][E_COL]);
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        double* out = jt + jbase + ((long long)(i - b) * 2 + r) * W;
-        // pose: J_xi * (Pi_k P_v)
+      for (int pass = 0; pass < 2; ++pass) {
+        if ((lane >> 4) == pass) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          double s = 0.0;
+          for (int r = 0; r < 2; ++r) {
+            double* out = stage + ((lane & 15) * 2 + r) * W;
+            // pose: J_xi * (Pi_k P_v)
 #pragma unroll
-          for (int k = 0; k < 6; ++k) s += a[r][k] * Mk[k * 6 + c];
-          out[(c < 3 ? off[0] : off[1] - 3) + c] = s;
-        }
-        for (int j = 0; j < cam; ++j) {  // baselines: J_xi * A_{j,k}
-          const double* A = p.camA + ((size_t)cam * p.n_cams + j) * 36;
+            for (int c = 0; c < 6; ++c) {
+              double s = 0.0;
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            double s = 0.0;
+              for (int k = 0; k < 6; ++k) s += a[r][k] * Mk[k * 6 + c];
+              out[(c < 3 ? off[0] : off[1] - 3) + c] = s;
+            }
+            for (int j = 0; j < cam; ++j) {  // baselines: J_xi * A_{j,k}
+              const double* A = p.camA + ((size_t)cam * p.n_cams + j) * 36;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) s += a[r][k] * __ldg(A + k * 6 + c);
-            out[off[4 + j] + c] = s;
+              for (int c = 0; c < 6; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s += a[r][k] * __ldg(A + k * 6 + c);
+                out[off[4 + j] + c] = s;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < P; ++c) out[off[2] + c] = a[r][6 + c];
+#pragma unroll
+            for (int c = 0; c < D; ++c) out[off[3] + c] = a[r][6 + P + c];
           }
         }
-#pragma unroll
-        for (int c = 0; c < P; ++c) out[off[2] + c] = a[r][6 + c];
-#pragma unroll
-        for (int c = 0; c < D; ++c) out[off[3] + c] = a[r][6 + P + c];
+        __syncwarp();
+        const int first = base + LM_STAGE_TERMS * pass;
+        const int n_valid = min(LM_STAGE_TERMS, e - first);
+        if (n_valid > 0) {
+          double* dst = jt + jbase + (long long)(first - b) * 2 * W;
+          const int n_out = n_valid * 2 * W;
+          for (int o = lane; o < n_out; o += 32) dst[o] = stage[o];
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
   }
 }
 
@@ -1314,11 +1589,29 @@ cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int
   return cudaGetLastError();
 }
 
-int la_grid_warps() { return sm_count() * 2 * LA_WARPS; }
+static bool la_use_ws() {
+  static int v = -1;
+  if (v < 0) v = getenv("KB_LA_WS") ? atoi(getenv("KB_LA_WS")) : 0;  // measured equal-or-slower than the symmetric kernel
+  return v != 0;
+}
+int la_grid_warps() { return la_use_ws() ? sm_count() * WS_PRODUCERS : sm_count() * 2 * LA_WARPS; }
 
 template <int MODEL, bool WRITE_E>
 static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const int4* slices, int lo, int hi, StreamCtx& s) {
   if (hi <= lo) return cudaSuccess;
+  if (la_use_ws()) {
+    const size_t smem_ws = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + (size_t)WS_PRODUCERS * WS_PROD_DOUBLES);
+    static size_t attr_ws = 0;
+    if (smem_ws > attr_ws) {
+      cudaError_t e = cudaFuncSetAttribute(linearise_assemble_ws_kernel<MODEL, WRITE_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
+      if (e != cudaSuccess) return e;
+      attr_ws = smem_ws;
+    }
+    const int grid_ws = min((hi - lo + WS_PRODUCERS - 1) / WS_PRODUCERS, sm_count());
+    linearise_assemble_ws_kernel<MODEL, WRITE_E><<<grid_ws, WS_THREADS, smem_ws, s.stream>>>(p, vmeta, slices, lo, hi);
+    KB_LAUNCHED(s);
+    return cudaGetLastError();
+  }
   const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -1366,21 +1659,32 @@ cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range
 }
 
 template <int MODEL>
-static void launch_lm_model(const DevProblem& p, const int* list, int n, double* jt, StreamCtx& s) {
-  if (n <= 0) return;
-  const int warps_per_cta = EVAL_THREADS / 32;
-  const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + warps_per_cta * 36);
-  const int grid = min((n + warps_per_cta - 1) / warps_per_cta, sm_count() * 8);
-  linearise_materialise_kernel<MODEL><<<grid, EVAL_THREADS, smem, s.stream>>>(p, list, n, jt);
+static cudaError_t launch_lm_model(const DevProblem& p, const int* list, int n, double* jt, StreamCtx& s) {
+  if (n <= 0) return cudaSuccess;
+  int w_max = 0;
+  for (int k = 0; k < p.n_cams; ++k)
+    if (p.cam_model[k] == MODEL) w_max = max(w_max, 6 + 6 * k + p.cam_P[k] + p.cam_D[k]);
+  const int stage_doubles = LM_STAGE_TERMS * 2 * w_max;
+  const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + (size_t)LM_WARPS * (36 + stage_doubles));
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(linearise_materialise_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  const int grid = min((n + LM_WARPS - 1) / LM_WARPS, sm_count() * 6);
+  linearise_materialise_kernel<MODEL><<<grid, LM_THREADS, smem, s.stream>>>(p, list, n, jt, stage_doubles);
   KB_LAUNCHED(s);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_linearise_materialise(const DevProblem& p, const int* view_list, const int* mb, double* jt, StreamCtx& s) {
-  launch_lm_model<0>(p, view_list + mb[0], mb[1] - mb[0], jt, s);
-  launch_lm_model<1>(p, view_list + mb[1], mb[2] - mb[1], jt, s);
-  launch_lm_model<2>(p, view_list + mb[2], mb[3] - mb[2], jt, s);
-  launch_lm_model<3>(p, view_list + mb[3], mb[4] - mb[3], jt, s);
-  launch_lm_model<4>(p, view_list + mb[4], mb[5] - mb[4], jt, s);
+  cudaError_t e;
+  if ((e = launch_lm_model<0>(p, view_list + mb[0], mb[1] - mb[0], jt, s)) != cudaSuccess) return e;
+  if ((e = launch_lm_model<1>(p, view_list + mb[1], mb[2] - mb[1], jt, s)) != cudaSuccess) return e;
+  if ((e = launch_lm_model<2>(p, view_list + mb[2], mb[3] - mb[2], jt, s)) != cudaSuccess) return e;
+  if ((e = launch_lm_model<3>(p, view_list + mb[3], mb[4] - mb[3], jt, s)) != cudaSuccess) return e;
+  if ((e = launch_lm_model<4>(p, view_list + mb[4], mb[5] - mb[4], jt, s)) != cudaSuccess) return e;
   return cudaGetLastError();
 }
 
