@@ -99,12 +99,15 @@ class OracleProblem:
         self.n_dv = lib().ko_num_design_variables(self._h)
 
     def close(self):
-        if self._h:
-            lib().ko_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ko_destroy(self._h)
             self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def dv_layout(self):
         col = np.zeros(self.n_dv, np.int32)

@@ -154,3 +154,43 @@ def test_optimize_converges_like_oracle(capi, oracle_lib, cfg, n_sets):
     # and both recover the ground truth to the noise level
     truth = p.truth["cam_params"]
     assert np.abs(g.camera_params()[:, :4] - truth[:, :4]).max() < 5.0
+
+
+@pytest.mark.parametrize("cfg,n_sets", [(2, 30), (3, 24)])
+def test_speculative_and_plain_evaluate_agree(capi, cfg, n_sets):
+    """kb_evaluate_error through the fused kernel (default) and through the residual-only kernel give the same cost, e()
+    and the same LM trajectory."""
+    p = make(cfg, n_sets)
+    a = capi.B200SchurLinearSystemSolver(p)
+    b = capi.B200SchurLinearSystemSolver(p)
+    b.set_speculative_linearise(False)
+    Ja, Jb = a.evaluate_error(), b.evaluate_error()
+    assert abs(Ja - Jb) <= 1e-12 * Jb
+    assert rel_err(a.error_vector(), b.error_vector()) < 1e-13
+    sa, ta = a.optimize(KbOptimizerOptions.kalibr2_default())
+    sb, tb = b.optimize(KbOptimizerOptions.kalibr2_default())
+    assert sa.iterations == sb.iterations and sa.failed_iterations == sb.failed_iterations
+    assert rel_err(ta[:, 0], tb[:, 0]) < 1e-12
+    assert rel_err(a.camera_params(), b.camera_params()) < 1e-12
+
+
+def test_rejected_step_keeps_the_built_system(capi, oracle_lib):
+    """After a rejected step (update, evaluate, revert) the next solve must use the system built BEFORE the step, although the
+    speculative evaluate has linearised at the trial state in between."""
+    p = make(2, 20)
+    g = capi.B200SchurLinearSystemSolver(p)
+    o = oracle_lib.OracleProblem(p)
+    for s in (g, o):
+        s.evaluate_error()
+        s.build_system()
+        s.set_constant_conditioner(0.5)
+        s.solve_system()
+        s.apply_state_update()
+        s.evaluate_error()            # trial state (speculative linearisation happens here on the GPU)
+        s.revert_last_state_update()
+        s.set_constant_conditioner(5.0)
+    gdx, gok = g.solve_system()
+    odx, ook = o.solve_system()
+    assert gok == ook
+    assert rel_err(gdx, odx) < 1e-7
+    assert rel_err(g.rhs(), o.rhs()) < 1e-9
