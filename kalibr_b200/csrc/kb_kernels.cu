@@ -1139,7 +1139,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
   double acc[MAX_PAIRS][2];
 #pragma unroll
   for (int q = 0; q < MAX_PAIRS; ++q) {
-    int pair = warp + q * WARPS;
+    int pair = warp + q * WARPS + blockIdx.y * (WARPS * MAX_PAIRS);  // gridDim.y splits the tile pairs of large systems
     int i = 0;
     if (pair < npairs) {
       int rem = pair;
@@ -1174,7 +1174,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
           for (int k = 0; k <= i; ++k) s += __ldg(Li + i * 6 + k) * w[k];
           z[i] = s;
         }
-        if (r == p.n_c) {
+        if (r == p.n_c && blockIdx.y == 0) {
 #pragma unroll
           for (int c = 0; c < 6; ++c) p.yv[(size_t)set * 6 + c] = z[c];
         }
@@ -1734,7 +1734,10 @@ static cudaError_t launch_schur_t(const DevProblem& p, double* partials, int n_p
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  schur_kernel<WARPS, MAX_PAIRS><<<n_partials, WARPS * 32, smem, s.stream>>>(p, partials, schur_sets_per_cta(p));
+  const int nt = (p.n_aug + 7) >> 3;
+  const int npairs = nt * (nt + 1) / 2;
+  const int gy = (npairs + WARPS * MAX_PAIRS - 1) / (WARPS * MAX_PAIRS);
+  schur_kernel<WARPS, MAX_PAIRS><<<dim3(n_partials, gy), WARPS * 32, smem, s.stream>>>(p, partials, schur_sets_per_cta(p));
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -1748,9 +1751,7 @@ cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, 
   }
   const int nt = (p.n_aug + 7) >> 3;
   if (nt <= 6) return launch_schur_t<8, 3>(p, partials, n_partials, s);
-  if (nt <= 14) return launch_schur_t<8, 14>(p, partials, n_partials, s);
-  if (nt <= 28) return launch_schur_t<16, 26>(p, partials, n_partials, s);
-  return cudaErrorInvalidValue;
+  return launch_schur_t<8, 14>(p, partials, n_partials, s);  // nt <= 14: one CTA per slice; larger systems: tile pairs split over gridDim.y
 }
 
 cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const double* partials, int n_partials, bool, StreamCtx& s) {
