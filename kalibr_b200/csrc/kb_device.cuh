@@ -51,6 +51,9 @@ struct DevProblem {
   const int* set_view;     // [n_sets][n_cams] view index or -1
   const int* lin_off;      // [n_cams][LIN_OFF_STRIDE] column offsets of the CCS J^T layout per camera
   const long long* view_jbase;  // [n_views] offset of the view's first value in the CCS J^T value array
+  const int* col_desc;     // [n_cams][col_desc_stride] per CCS J^T column of camera k: kind << 16 | j << 8 | sub
+                           //   kind 0 = set pose (sub 0..5), 1 = baseline j (sub 0..5), 2 = intrinsics (sub = local column - 6)
+  int col_desc_stride;
   // ---- state ----
   double* cam_params;   // [n_cams][10]
   double* baselines;    // [n_cams-1][7]
@@ -96,7 +99,9 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta /*(
                                       StreamCtx& s);
 cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, double* cost_out, StreamCtx& s);
 cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s);
-cudaError_t launch_linearise_materialise(const DevProblem& p, const int* view_list, const int* model_begin, double* jt_values, StreamCtx& s);
+cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta, const int4* slices, const int* slice_model_begin,
+                                         const int* bfrag_pairs /*[NUM_MODELS]*/, unsigned int* counters /*[NUM_MODELS], device*/, double* jt_values,
+                                         StreamCtx& s);
 cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_schur_finalize(const DevProblem& p, double damping, const double* partials, int n_partials, bool add_camera_block, StreamCtx& s);
 cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s);

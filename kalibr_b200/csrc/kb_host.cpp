@@ -103,7 +103,9 @@ struct kb_handle {
   DevBuf<int4> slices, vmeta;
   DevBuf<int> cam_slice_range;
   int slice_model_begin[KB_NUM_MODELS + 1] = {};
-  DevBuf<unsigned int> n_invalid;
+  DevBuf<unsigned int> n_invalid, lm_counters;
+  DevBuf<int> col_desc;
+  int lm_bfrag_pairs[KB_NUM_MODELS] = {};
   int model_begin[KB_NUM_MODELS + 1] = {};
   int n_partials = 0;
   double* h_scalars = nullptr;  // pinned [8]
@@ -392,6 +394,31 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
       int o = 0;
       for (auto& s : segs) { lin_off[(size_t)k * LIN_OFF_STRIDE + s.slot] = o; o += s.dim; }
     }
+    // per-column descriptors of the CCS J^T layout and the DMMA B-fragment slots the materialising kernel needs per model
+    const int desc_stride = 6 * d->n_cams + KB_CAM_PARAM_STRIDE;
+    std::vector<int> col_desc((size_t)d->n_cams * desc_stride, 3 << 16);
+    for (int k = 0; k < d->n_cams; ++k) {
+      const int* off = &lin_off[(size_t)k * LIN_OFF_STRIDE];
+      int* cd = &col_desc[(size_t)k * desc_stride];
+      for (int c = 0; c < 3; ++c) { cd[off[0] + c] = (0 << 16) | c; cd[off[1] + c] = (0 << 16) | (3 + c); }
+      for (int c = 0; c < D.cam_P[k]; ++c) cd[off[2] + c] = (2 << 16) | c;
+      for (int c = 0; c < D.cam_D[k]; ++c) cd[off[3] + c] = (2 << 16) | (D.cam_P[k] + c);
+      for (int j = 0; j < k; ++j)
+        for (int c = 0; c < 6; ++c) cd[off[4 + j] + c] = (1 << 16) | (j << 8) | c;
+      const int Wk = 6 + 6 * k + D.cam_P[k] + D.cam_D[k];
+      int pairs = 0;
+      for (int n0 = 0; n0 < Wk; n0 += 8) {
+        unsigned need = 0;
+        for (int c = n0; c < std::min(Wk, n0 + 8); ++c) {
+          const int kind = cd[c] >> 16, sub = cd[c] & 0xff;
+          need |= kind == 2 ? 1u << ((6 + sub) >> 2) : 3u;
+        }
+        for (int ks = 0; ks < 4; ++ks) pairs += (need >> ks) & 1;
+      }
+      h->lm_bfrag_pairs[d->cam_model[k]] = std::max(h->lm_bfrag_pairs[d->cam_model[k]], pairs);
+    }
+    KB_CCUDA(h->col_desc.upload(col_desc, h->stream));
+    D.col_desc_stride = desc_stride;
     long long jb = 0;
     for (int w = 0; w < n_views; ++w) {
       h->h_view_jbase[w] = jb;
@@ -507,6 +534,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->scalars.alloc(8));
   KB_CCUDA(h->posdef.alloc(2));
   KB_CCUDA(h->n_invalid.alloc(1));
+  KB_CCUDA(h->lm_counters.alloc(KB_NUM_MODELS));
   KB_CCUDA(cudaMemsetAsync(h->n_invalid.p, 0, sizeof(unsigned int), s));
   KB_CCUDA(cudaMemsetAsync(h->dx.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)h->jcols), s));
   KB_CCUDA(cudaMemsetAsync(h->VB.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)n_views * VB_STRIDE), s));
@@ -514,7 +542,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(cudaMemsetAsync(h->camA.p, 0, sizeof(double) * C * C * 36, s));
   D.y_u = h->y_u.p; D.y_v = h->y_v.p; D.corner = h->corner.p; D.target = h->target.p;
   D.view_set = h->view_set.p; D.view_cam = h->view_cam.p; D.view_begin = h->view_begin.p; D.set_view = h->set_view.p;
-  D.lin_off = h->lin_off.p; D.view_jbase = h->view_jbase.p;
+  D.lin_off = h->lin_off.p; D.view_jbase = h->view_jbase.p; D.col_desc = h->col_desc.p;
   D.cam_params = h->cam_params.p; D.baselines = h->baselines.p; D.set_poses = h->set_poses.p;
   D.camT = h->camT.p; D.camPi = h->camPi.p; D.camA = h->camA.p; D.baseBt = h->baseBt.p; D.baseM = h->baseM.p;
   D.e = h->e.p; D.view_cost = h->view_cost.p; D.set_prep = h->set_prep.p; D.VB = h->VB.p; D.gram_partial = h->gram_partial.p; D.sumG = h->sumG.p;
@@ -867,7 +895,7 @@ kb_status kb_linearise(kb_handle* h) {
   {
     StageTimer t(h, 7);
     KB_CUDA(h, launch_prep(h->d, c));
-    KB_CUDA(h, launch_linearise_materialise(h->d, h->view_list.p, h->model_begin, h->jt.p, c));
+    KB_CUDA(h, launch_linearise_materialise(h->d, h->vmeta.p, h->slices.p, h->slice_model_begin, h->lm_bfrag_pairs, h->lm_counters.p, h->jt.p, c));
   }
   if (h->timing) {
     KB_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -797,97 +797,166 @@ __global__ void __launch_bounds__(WS_THREADS, 1) linearise_assemble_ws_kernel(De
 }
 
 // ---- materialising linearise: e and J in the CCS J^T layout of the reference -----------------------------------
-// Per term two columns of J^T (= rows of J), each W_k = 6 + 6k + P + D values ordered by design-variable block index
-// (lin_off gives the slot of every DV segment for camera k).
+// Per term two columns of J^T (= rows of J), each W_k = 6 + 6k + P + D values ordered by design-variable block index, so
+// the Jacobian of one view is a dense row-major [2 * terms][W_k] array: the product of the local rows
+// a = [J_xi | -J_i | -J_d | . | e] (16 columns, lane per term) with a 16 x W_k matrix B that holds Pi_k P_v under the set-pose
+// columns, A_{j,k} under the baseline columns and unit vectors under the intrinsics columns (col_desc says which).
+// That product runs on the FP64 tensor pipe: the rows of a 32-term chunk are staged transposed in shared memory (same
+// layout as the fused kernel), B lives in shared memory in DMMA fragment order (only the k-steps that are structurally
+// non-zero per 8-column tile), and every 8x8 output tile goes from the accumulator registers straight to HBM.
+// Work is handed out in sub-slices of the camera-sorted view list through an atomic counter (scheduling only: every
+// value is computed the same way wherever it runs).
 constexpr int LM_WARPS = 4;
 constexpr int LM_THREADS = LM_WARPS * 32;
-constexpr int LM_STAGE_TERMS = 16;  // rows of 16 terms are staged in shared memory, then written to HBM fully coalesced
+constexpr int LM_SUB = 4;  // sub-slices per slice of the fused kernel's slice table
+
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream2(double* p, double v0, double v1) { __stcs(reinterpret_cast<double2*>(p), make_double2(v0, v1)); }
 
 template <int MODEL>
-__global__ void __launch_bounds__(LM_THREADS) linearise_materialise_kernel(DevProblem p, const int* __restrict__ view_list, int n_list,
-                                                                            double* __restrict__ jt, int stage_doubles) {
+__global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(DevProblem p, const int4* __restrict__ vmeta, const int4* __restrict__ slices,
+                                                                               int slice_lo, int slice_hi, double* __restrict__ jt, int bfrag_pairs,
+                                                                               unsigned int* __restrict__ work_counter) {
   extern __shared__ __align__(16) double smem[];
   double* s_target = smem;
   const int target_doubles = (p.n_target * 3 + 1) & ~1;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  double* Mk = smem + target_doubles + wib * (36 + stage_doubles);  // Pi_k * P_v
-  double* stage = Mk + 36;                                          // [16 terms][2][W]
+  const int warp_doubles = XT_WARP_DOUBLES + bfrag_pairs * 32 + 36 + SETPREP_STRIDE;
+  double* XT = smem + target_doubles + (size_t)wib * warp_doubles;  // [16 cols][68]
+  double* Bf = XT + XT_WARP_DOUBLES;                                  // [pairs][32] B fragments
+  double* sM = Bf + bfrag_pairs * 32;                                 // Pi_k P_v
+  double* sSP = sM + 36;                                              // per-set constants
   for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
+  for (int o = lane; o < XT_LD; o += 32) XT[E_COL * XT_LD + o] = 0.0;  // the e column never enters J: its k-row stays zero
   __syncthreads();
   constexpr int P = model_P(MODEL), D = model_D(MODEL);
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int vi = warp; vi < n_list; vi += n_warps) {
-    const int view = view_list[vi];
-    const int set = p.view_set[view], cam = p.view_cam[view];
-    const int b = p.view_begin[view], e = p.view_begin[view + 1];
-    const double* pose = p.set_poses + (size_t)set * POSE_STRIDE;
-    double Rcw[9], tcw[3];
-    view_transform(pose, p.camT + cam * 12, Rcw, tcw);
-    {
-      double Pv[36];
-      set_pose_jac(pose, Pv);
-      const double* Pi = p.camPi + cam * 36;
-      for (int o = lane; o < 36; o += 32) {
-        const int r = o / 6, c = o % 6;
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s += Pi[r * 6 + k] * Pv[k * 6 + c];
-        Mk[o] = s;
-      }
-    }
-    __syncwarp();
+  const int arow = lane >> 2, acol = lane & 3;
+  const int n_work = (slice_hi - slice_lo) * LM_SUB;
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = (int)atomicAdd(work_counter, 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= n_work) break;
+    const int4 S = slices[slice_lo + w / LM_SUB];
+    const int part = w % LM_SUB, nv = S.y - S.x;
+    const int v_lo = S.x + (int)((long long)nv * part / LM_SUB), v_hi = S.x + (int)((long long)nv * (part + 1) / LM_SUB);
+    if (v_lo >= v_hi) continue;
+    const int cam = S.z;
     double prm[CAM_PARAM_STRIDE];
 #pragma unroll
     for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
-    const int* off = p.lin_off + cam * LIN_OFF_STRIDE;
+    double camT[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) camT[i] = p.camT[cam * 12 + i];
     const int W = 6 + 6 * cam + P + D;
-    const long long jbase = p.view_jbase[view];
-    for (int base = b; base < e; base += 32) {
-      const int i = base + lane;
-      const bool active = i < e;
-      const int ii = active ? i : b;
-      double a[2][GRAM_DIM];
-      term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * p.corner[ii], p.y_u[ii], p.y_v[ii], active, a[0], a[1], p.n_invalid);
-      if (active) reinterpret_cast<double2*>(p.e)[i] = make_double2(-a[0][E_COL], -a[1][E_COL]);
+    const int ntiles = (W + 7) >> 3;
+    const bool w_even = (W & 1) == 0;
+    const int* __restrict__ desc = p.col_desc + (size_t)cam * p.col_desc_stride;
+    for (int vi = v_lo; vi < v_hi; ++vi) {
+      const int4 m = vmeta[vi];  // (view, set, begin, end)
+      const int b = m.z, e = m.w;
+      // first chunk's observations: in flight while the per-view constants are set up
+      int i = b + lane;
+      bool active = i < e;
+      int ii = active ? i : b;
+      double yu = 0.0, yv = 0.0;
+      int cid = 0;
+      if (b < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+      const double* sp_g = p.set_prep + (size_t)m.y * SETPREP_STRIDE;
+      sSP[lane] = sp_g[lane];
+      if (lane < SETPREP_STRIDE - 32) sSP[32 + lane] = sp_g[32 + lane];
+      __syncwarp();
+      double Rcw[9], tcw[3];
+      view_transform_prepped(sSP, camT, Rcw, tcw);
+      for (int o = lane; o < 36; o += 32) {  // M = Pi_k P_v
+        const int r = o / 6, c = o % 6;
+        double s = 0.0;
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        if ((lane >> 4) == pass) {
+        for (int a = 0; a < 6; ++a) s += __ldg(p.camPi + cam * 36 + r * 6 + a) * sSP[12 + a * 6 + c];
+        sM[o] = s;
+      }
+      __syncwarp();
+      // B fragments (b: row k = lane % 4, col n = lane / 4) of the structurally non-zero (tile, k-step) pairs
+      unsigned long long kmask = 0ull;
+      {
+        int np = 0;
+        for (int nt = 0; nt < ntiles; ++nt) {
+          const int c = 8 * nt + arow;
+          const int d = (c < W) ? desc[c] : (3 << 16);
+          const int kind = d >> 16, j = (d >> 8) & 0xff, sub = d & 0xff;
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            double* out = stage + ((lane & 15) * 2 + r) * W;
-            // pose: J_xi * (Pi_k P_v)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-              double s = 0.0;
-#pragma unroll
-              for (int k = 0; k < 6; ++k) s += a[r][k] * Mk[k * 6 + c];
-              out[(c < 3 ? off[0] : off[1] - 3) + c] = s;
+          for (int ks = 0; ks < 4; ++ks) {
+            const int kr = 4 * ks + acol;
+            bool need = false;
+            double val = 0.0;
+            if (kind == 0) {
+              need = ks < 2;
+              if (kr < 6) val = sM[kr * 6 + sub];
+            } else if (kind == 1) {
+              need = ks < 2;
+              if (kr < 6) val = __ldg(p.camA + ((size_t)cam * p.n_cams + j) * 36 + kr * 6 + sub);
+            } else if (kind == 2) {
+              need = ks == ((6 + sub) >> 2);
+              val = (kr == 6 + sub) ? 1.0 : 0.0;
             }
-            for (int j = 0; j < cam; ++j) {  // baselines: J_xi * A_{j,k}
-              const double* A = p.camA + ((size_t)cam * p.n_cams + j) * 36;
-#pragma unroll
-              for (int c = 0; c < 6; ++c) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) s += a[r][k] * __ldg(A + k * 6 + c);
-                out[off[4 + j] + c] = s;
-              }
+            if (__any_sync(0xffffffffu, need)) {
+              Bf[np * 32 + lane] = val;
+              kmask |= 1ull << (4 * nt + ks);
+              ++np;
             }
-#pragma unroll
-            for (int c = 0; c < P; ++c) out[off[2] + c] = a[r][6 + c];
-#pragma unroll
-            for (int c = 0; c < D; ++c) out[off[3] + c] = a[r][6 + P + c];
           }
         }
+      }
+      __syncwarp();
+      double* __restrict__ dst_view = jt + p.view_jbase[m.x];
+      for (int base = b; base < e; base += 32) {
+        const double cyu = yu, cyv = yv;
+        const int ccid = cid;
+        const bool cactive = active;
+        const int ci = i;
+        i = base + 32 + lane;
+        active = i < e;
+        ii = active ? i : b;
+        if (base + 32 < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+        {
+          double a0[GRAM_DIM], a1[GRAM_DIM];
+          term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, cactive, a0, a1, p.n_invalid);
+          if (cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-a0[E_COL], -a1[E_COL]);
+#pragma unroll
+          for (int c = 0; c < E_COL; ++c) *reinterpret_cast<double2*>(XT + c * XT_LD + 2 * lane) = make_double2(a0[c], a1[c]);
+        }
         __syncwarp();
-        const int first = base + LM_STAGE_TERMS * pass;
-        const int n_valid = min(LM_STAGE_TERMS, e - first);
-        if (n_valid > 0) {
-          double* dst = jt + jbase + (long long)(first - b) * 2 * W;
-          const int n_out = n_valid * 2 * W;
-          for (int o = lane; o < n_out; o += 32) dst[o] = stage[o];
+        const int rows_valid = 2 * min(32, e - base);
+        const int mtiles = (rows_valid + 7) >> 3;
+        double* __restrict__ dst_chunk = dst_view + (long long)(base - b) * 2 * W;
+        for (int mt = 0; mt < mtiles; ++mt) {
+          double a[4];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) a[ks] = XT[(4 * ks + acol) * XT_LD + 8 * mt + arow];
+          const int row = 8 * mt + arow;
+          const bool row_ok = row < rows_valid;
+          double* __restrict__ drow = dst_chunk + (long long)row * W + 2 * acol;
+          const double* bf = Bf + lane;
+          unsigned long long km = kmask;
+          for (int nt = 0; nt < ntiles; ++nt, km >>= 4) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (km & (1ull << ks)) {
+                dmma(c0, c1, a[ks], *bf);
+                bf += 32;
+              }
+            const int col = 8 * nt + 2 * acol;
+            if (row_ok) {
+              if (w_even) {
+                if (col < W) st_stream2(drow + 8 * nt, c0, c1);
+              } else {
+                if (col < W) st_stream(drow + 8 * nt, c0);
+                if (col + 1 < W) st_stream(drow + 8 * nt + 1, c1);
+              }
+            }
+          }
         }
         __syncwarp();
       }
@@ -1659,32 +1728,37 @@ cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range
 }
 
 template <int MODEL>
-static cudaError_t launch_lm_model(const DevProblem& p, const int* list, int n, double* jt, StreamCtx& s) {
-  if (n <= 0) return cudaSuccess;
-  int w_max = 0;
-  for (int k = 0; k < p.n_cams; ++k)
-    if (p.cam_model[k] == MODEL) w_max = max(w_max, 6 + 6 * k + p.cam_P[k] + p.cam_D[k]);
-  const int stage_doubles = LM_STAGE_TERMS * 2 * w_max;
-  const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + (size_t)LM_WARPS * (36 + stage_doubles));
+static cudaError_t launch_lm_model(const DevProblem& p, const int4* vmeta, const int4* slices, int lo, int hi, double* jt, int bfrag_pairs,
+                                   unsigned int* counter, StreamCtx& s) {
+  if (hi <= lo) return cudaSuccess;
+  const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + (size_t)LM_WARPS * (XT_WARP_DOUBLES + bfrag_pairs * 32 + 36 + SETPREP_STRIDE));
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(linearise_materialise_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  const int grid = min((n + LM_WARPS - 1) / LM_WARPS, sm_count() * 6);
-  linearise_materialise_kernel<MODEL><<<grid, LM_THREADS, smem, s.stream>>>(p, list, n, jt, stage_doubles);
+  const int ctas_per_sm = (int)max((size_t)1, min((size_t)4, (size_t)(220 * 1024) / (smem + 1024)));
+  const int grid = min(((hi - lo) * LM_SUB + LM_WARPS - 1) / LM_WARPS, sm_count() * ctas_per_sm);
+  linearise_materialise_kernel<MODEL><<<grid, LM_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi, jt, bfrag_pairs, counter);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
 
-cudaError_t launch_linearise_materialise(const DevProblem& p, const int* view_list, const int* mb, double* jt, StreamCtx& s) {
-  cudaError_t e;
-  if ((e = launch_lm_model<0>(p, view_list + mb[0], mb[1] - mb[0], jt, s)) != cudaSuccess) return e;
-  if ((e = launch_lm_model<1>(p, view_list + mb[1], mb[2] - mb[1], jt, s)) != cudaSuccess) return e;
-  if ((e = launch_lm_model<2>(p, view_list + mb[2], mb[3] - mb[2], jt, s)) != cudaSuccess) return e;
-  if ((e = launch_lm_model<3>(p, view_list + mb[3], mb[4] - mb[3], jt, s)) != cudaSuccess) return e;
-  if ((e = launch_lm_model<4>(p, view_list + mb[4], mb[5] - mb[4], jt, s)) != cudaSuccess) return e;
+// slice_model_begin[m] .. [m+1]: slices of camera model m; bfrag_pairs[m]: B-fragment slots a camera of model m needs at most;
+// counters: KB_NUM_MODELS work counters (zeroed here)
+cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta, const int4* slices, const int* smb, const int* bfrag_pairs,
+                                         unsigned int* counters, double* jt, StreamCtx& s) {
+  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * NUM_MODELS, s.stream);
+  if (e != cudaSuccess) return e;
+  if (p.n_sets > 0) {
+    set_prep_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p);
+    KB_LAUNCHED(s);
+  }
+#define KB_LM(M) \
+  if ((e = launch_lm_model<M>(p, vmeta, slices, smb[M], smb[M + 1], jt, bfrag_pairs[M], counters + M, s)) != cudaSuccess) return e;
+  KB_LM(0) KB_LM(1) KB_LM(2) KB_LM(3) KB_LM(4)
+#undef KB_LM
   return cudaGetLastError();
 }
 
