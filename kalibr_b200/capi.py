@@ -39,12 +39,13 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    lib_path = os.environ.get("KB_LIB_PATH", LIB_PATH)  # kernel-variant experiments (tools/) point this at another build
+    if not os.path.exists(lib_path):
         raise KalibrB200Error(
-            f"{LIB_PATH} is missing: build it with `python -m kalibr_b200.build` (nvcc, sm_100a). "
+            f"{lib_path} is missing: build it with `python -m kalibr_b200.build` (nvcc, sm_100a). "
             "The B200 hot path has no CPU fallback."
         )
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(lib_path)
     vp = C.c_void_p
     L.kb_create.argtypes = [C.POINTER(KbProblemDesc), C.POINTER(vp)]
     L.kb_create.restype = C.c_int32

@@ -20,12 +20,9 @@ constexpr int GRAM_SIZE = GRAM_DIM * GRAM_DIM;     // row-major; only the tiles 
 constexpr int E_COL = 15;
 constexpr int GRAM_TILES = 192;                    // the three stored 8x8 tiles (0,0), (0,1), (1,1) in mma C-fragment order
 constexpr int SETPREP_STRIDE = 48;                 // per set: C^-1 (9), -C^-1 t (3), P_v (36)
-// per-view block written by the fused kernel's epilogue
-constexpr int VB_V = 0;                            // V_k = M^T G_xx M   (36)
-constexpr int VB_B = 36;                           // b_k = -M^T G_xe    (6, padded to 12)
-constexpr int VB_Y = 48;                           // Y_k = G_xx M       (36)
-constexpr int VB_W = 84;                           // W_k = G_cx M       (up to 10 x 6)
-constexpr int VB_STRIDE = 144;
+// per-view block written by the fused kernel: Gram tiles (0,0) and (0,1), each row-major 8x8
+//   tile (0,0): G[0:8][0:8]  (pose x pose, pose x first two intrinsics)      tile (0,1): G[0:8][8:16]  (pose x remaining intrinsics, pose x e)
+constexpr int VB_STRIDE = 128;
 
 struct DevProblem {
   // ---- structure (immutable after kb_create) ----
@@ -68,7 +65,7 @@ struct DevProblem {
   double* e;            // [2*n_terms]   -(y - y_hat), the reference's _e
   double* view_cost;    // [n_views]
   double* set_prep;     // [n_sets][48]
-  double* VB;           // [n_views][144] view blocks
+  double* VB;           // [n_views][128] view blocks (two Gram tiles)
   double* gram_partial; // [n_slices][192]
   double* sumG;         // [n_cams][256] full symmetric
   double* V;            // [n_sets][36]

@@ -323,52 +323,68 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ v,
 //   a_r = [ J_xi(r, 0..5) | -Ji(r, 0..P-1) | -Jd(r, 0..D-1) | 0.. | e_r ]   (16 columns, e in column 15)
 //   J_xi = -Jp * boxMinus(p_c) = -[Jp | Jp [p_c]x]   (BX/src/HomogeneousExpressionNode.cpp:77-82, transformations.cpp:45-53)
 // =========================================================================================================
+// The rows go straight to the warp's staging buffer in shared memory, transposed: column c of the u-row of the term of
+// lane l at xt[c * XT_LD + l], of its v-row at xt[c * XT_LD + 32 + l] (conflict-free stores, and no 32 values to keep
+// live in registers).  Returns the projection's validity flag; e0, e1 = the residuals.
+constexpr int XT_LD = 68;  // 64 rows (32 terms x 2) + 4: conflict-free for the row stores and the DMMA operand loads
+constexpr int XT_WARP_DOUBLES = GRAM_DIM * XT_LD;
+
 template <int MODEL>
-__device__ __forceinline__ void term_rows(const double* __restrict__ prm, const double Rcw[9], const double tcw[3], const double* __restrict__ pt,
-                                          double yu, double yv, bool active, double a0[GRAM_DIM], double a1[GRAM_DIM], unsigned int* n_invalid) {
+__device__ __forceinline__ bool term_rows(const double* __restrict__ prm, const double Rcw[9], const double tcw[3], const double* __restrict__ pt,
+                                          double yu, double yv, double* __restrict__ xt_lane, double& e0, double& e1) {
   using Cam = Camera<MODEL, true, true>;  // negated Jacobians: e = y - y_hat
   constexpr int P = Cam::P, D = Cam::D;
   const double pc[3] = {Rcw[0] * pt[0] + Rcw[1] * pt[1] + Rcw[2] * pt[2] + tcw[0], Rcw[3] * pt[0] + Rcw[4] * pt[1] + Rcw[5] * pt[2] + tcw[1],
                         Rcw[6] * pt[0] + Rcw[7] * pt[1] + Rcw[8] * pt[2] + tcw[2]};
   Linearisation<P, D> L;
   Cam::eval(prm, pc, L);
-  if (active && !L.valid) atomicAdd(n_invalid, 1u);
-  const bool keep = active && L.valid;
+  e0 = yu - L.y[0];
+  e1 = yv - L.y[1];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    double* a = r == 0 ? a0 : a1;
+    double* __restrict__ x = xt_lane + 32 * r;
     const double j0 = L.Jp[r][0], j1 = L.Jp[r][1], j2 = L.Jp[r][2];  // = -Jp
-    a[0] = j0;
-    a[1] = j1;
-    a[2] = j2;
-    a[3] = j1 * pc[2] - j2 * pc[1];
-    a[4] = j2 * pc[0] - j0 * pc[2];
-    a[5] = j0 * pc[1] - j1 * pc[0];
+    x[0 * XT_LD] = j0;
+    x[1 * XT_LD] = j1;
+    x[2 * XT_LD] = j2;
+    x[3 * XT_LD] = j1 * pc[2] - j2 * pc[1];
+    x[4 * XT_LD] = j2 * pc[0] - j0 * pc[2];
+    x[5 * XT_LD] = j0 * pc[1] - j1 * pc[0];
 #pragma unroll
-    for (int c = 0; c < P; ++c) a[6 + c] = L.Ji[r][c];
+    for (int c = 0; c < P; ++c) x[(6 + c) * XT_LD] = L.Ji[r][c];
 #pragma unroll
-    for (int c = 0; c < D; ++c) a[6 + P + c] = L.Jd[r][c];
+    for (int c = 0; c < D; ++c) x[(6 + P + c) * XT_LD] = L.Jd[r][c];
 #pragma unroll
-    for (int c = 6 + P + D; c < E_COL; ++c) a[c] = 0.0;
-    a[E_COL] = (r == 0 ? yu : yv) - L.y[r];
+    for (int c = 6 + P + D; c < E_COL; ++c) x[c * XT_LD] = 0.0;
+    x[E_COL * XT_LD] = r == 0 ? e0 : e1;
+  }
+  return L.valid;
+}
+// zero weight (inactive lane of a partial chunk, or a projection that bailed out: SURVEY.md Q6): the rows become zero.
+// Only reached when some lane of the warp needs it, so the common case spends nothing on it.
+__device__ __forceinline__ void zero_rows(double* __restrict__ xt_lane) {
 #pragma unroll
-    for (int c = 0; c < GRAM_DIM; ++c) a[c] = keep ? a[c] : 0.0;  // zero weight: selects, no FP64 work
+  for (int c = 0; c < GRAM_DIM; ++c) {
+    xt_lane[c * XT_LD] = 0.0;
+    xt_lane[c * XT_LD + 32] = 0.0;
   }
 }
 
 // ---- fused linearise + assemble on DMMA ----------------------------------------------------------------------
 // One warp walks a slice of the camera-sorted view list (a slice never crosses a camera).  Per view: 32-term chunks are
-// linearised (lane per term), staged transposed in shared memory and reduced into the 16x16 Gram block G with
-// mma.sync.m8n8k4.f64; the next chunk's observations are prefetched before the DMMA phase.  The epilogue turns G into the
-// view block the set reduction needs (V_k = M^T G_xx M, b_k = -M^T G_xe, Y_k = G_xx M, W_k = G_cx M with M = Pi_k P_v)
-// and adds G to the slice's per-camera Gram sum, so G itself never goes to HBM.
-constexpr int LA_WARPS = 8;
+// linearised (lane per term), staged transposed in shared memory (u-rows of the 32 terms, then their v-rows) and reduced
+// into the 16x16 Gram block G with mma.sync.m8n8k4.f64 (two accumulator sets: u-rows / v-rows); the next chunk's
+// observations - or the next view's first chunk - are prefetched before the DMMA phase.  Per view the kernel writes only
+// the two Gram tiles the set reduction needs (G[0:8][0:16]: pose x pose, pose x intrinsics, pose x e) straight from the
+// accumulator registers, and adds all three tiles to the slice's per-camera Gram sum; the M = Pi_k P_v products that turn
+// G into V_v / W_v / b_v live in set_reduce_kernel, where the FP64 units are idle.
+#ifndef KB_LA_WARPS
+#define KB_LA_WARPS 8
+#endif
+constexpr int LA_WARPS = KB_LA_WARPS;
 constexpr int LA_THREADS = LA_WARPS * 32;
-constexpr int XT_LD = 68;  // 64 rows (32 terms x 2) + 4: conflict-free for both the 16-byte stores and the DMMA operand loads
-constexpr int XT_WARP_DOUBLES = GRAM_DIM * XT_LD;
-constexpr int LA_WARP_DOUBLES = XT_WARP_DOUBLES + GRAM_TILES + 3 * 36 + 2 * SETPREP_STRIDE;  // XT | slice Gram sum | Pi, M, Y | set constants x2
-
-constexpr int G_LD = 17;  // epilogue copy of the Gram block: odd stride, conflict-free for the row-strided reads
+constexpr int LA_SP_DOUBLES = 16;  // per view: C^-1 (9), -C^-1 t (3) of the set, padded
+constexpr int LA_WARP_DOUBLES = XT_WARP_DOUBLES + GRAM_TILES + 2 * LA_SP_DOUBLES;  // XT | slice Gram sum | set constants x2
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -377,7 +393,7 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-template <int MODEL, bool WRITE_E, int VARIANT = 0>
+template <int MODEL, bool WRITE_E>
 __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevProblem p, const int4* __restrict__ vmeta,
                                                                             const int4* __restrict__ slices, int slice_lo, int slice_hi) {
   extern __shared__ __align__(16) double smem[];
@@ -385,155 +401,116 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
   const int target_doubles = (p.n_target * 3 + 1) & ~1;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  double* XT = smem + target_doubles + wib * LA_WARP_DOUBLES;  // [16 cols][68]; reused as G[16][17] in the epilogue
-  double* sG = XT + XT_WARP_DOUBLES;                           // [3][64] slice sum of the three stored tiles
-  double* sPi = sG + GRAM_TILES;
-  double* sM = sPi + 36;
-  double* sY = sM + 36;
-  double* sSP = sY + 36;                                       // [2][48] per-set constants of the current / next view (cp.async)
+  double* XT = smem + target_doubles + wib * LA_WARP_DOUBLES;  // [16 cols][68]
+  double* sG = XT + XT_WARP_DOUBLES;                           // [3][64] slice sum of the three tiles
+  double* sSP = sG + GRAM_TILES;                               // [2][16] per-set constants of the current / next view (cp.async)
   for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
   __syncthreads();
-  constexpr int PD = model_P(MODEL) + model_D(MODEL);
 
   const int warp = blockIdx.x * LA_WARPS + wib;
   const int n_warps = gridDim.x * LA_WARPS;
   const int arow = lane >> 2, acol = lane & 3;
-  const int gc = 2 * acol;
   for (int sl = slice_lo + warp; sl < slice_hi; sl += n_warps) {
     const int4 S = slices[sl];
     const int cam = S.z;
     double prm[CAM_PARAM_STRIDE];
 #pragma unroll
     for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
-    double camT[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) camT[i] = p.camT[cam * 12 + i];
-    for (int o = lane; o < 36; o += 32) sPi[o] = p.camPi[cam * 36 + o];
     for (int o = lane; o < GRAM_TILES; o += 32) sG[o] = 0.0;
-    // pipeline: metadata two views ahead (registers), per-set constants one view ahead (cp.async into shared memory)
+    // pipeline: metadata two views ahead (registers), per-set constants one view ahead (cp.async into shared memory),
+    // observations one chunk ahead (registers), across view boundaries too
     int4 m_cur = vmeta[S.x];                                   // (view, set, begin, end)
     int4 m_nxt = (S.x + 1 < S.y) ? vmeta[S.x + 1] : m_cur;
-    if (lane < 24) cp_async_16(sSP + 2 * lane, p.set_prep + (size_t)m_cur.y * SETPREP_STRIDE + 2 * lane);
+    if (lane < 6) cp_async_16(sSP + 2 * lane, p.set_prep + (size_t)m_cur.y * SETPREP_STRIDE + 2 * lane);
     cp_async_commit();
+    int i = 0;
+    bool active = false, have_pf = false;
+    double yu = 0.0, yv = 0.0;
+    int cid = 0;
     for (int vi = S.x; vi < S.y; ++vi) {
       const int buf = (vi - S.x) & 1;
       const int view = m_cur.x;
       const int b = m_cur.z, e = m_cur.w;
-      // observations of the first chunk: issued before anything waits
-      int i = b + lane;
-      bool active = i < e;
-      int ii = active ? i : b;
-      double yu = 0.0, yv = 0.0;
-      int cid = 0;
-      if (b < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+      if (!have_pf) {  // first view of the slice, or the previous view was empty
+        i = b + lane;
+        active = i < e;
+        const int ii = active ? i : b;
+        if (b < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+      }
+      have_pf = false;
       const int4 m_nn = (vi + 2 < S.y) ? vmeta[vi + 2] : m_nxt;
       cp_async_wait_all();
       __syncwarp();
-      if (vi + 1 < S.y && lane < 24) cp_async_16(sSP + (buf ^ 1) * SETPREP_STRIDE + 2 * lane, p.set_prep + (size_t)m_nxt.y * SETPREP_STRIDE + 2 * lane);
+      if (vi + 1 < S.y && lane < 6) cp_async_16(sSP + (buf ^ 1) * LA_SP_DOUBLES + 2 * lane, p.set_prep + (size_t)m_nxt.y * SETPREP_STRIDE + 2 * lane);
       cp_async_commit();
-      const double* sp = sSP + buf * SETPREP_STRIDE;
       double Rcw[9], tcw[3];
-      view_transform_prepped(sp, camT, Rcw, tcw);
-      double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
-      double d00[2] = {0.0, 0.0}, d01[2] = {0.0, 0.0}, d11[2] = {0.0, 0.0};
+      {
+        double camT[12];  // per view from L1: not worth 24 registers across the slice
+#pragma unroll
+        for (int q = 0; q < 12; ++q) camT[q] = __ldg(p.camT + cam * 12 + q);
+        view_transform_prepped(sSP + buf * LA_SP_DOUBLES, camT, Rcw, tcw);
+      }
+      double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};  // three independent DMMA chains saturate the pipe
       for (int base = b; base < e; base += 32) {
         const double cyu = yu, cyv = yv;
         const int ccid = cid;
         const bool cactive = active;
         const int ci = i;
-        i = base + 32 + lane;
-        active = i < e;
-        ii = active ? i : b;
-        if (base + 32 < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
-        double a0[GRAM_DIM], a1[GRAM_DIM];
-        if (VARIANT == 2) {  // timing experiment: no projection math
-#pragma unroll
-          for (int c = 0; c < GRAM_DIM; ++c) { a0[c] = cyu + c; a1[c] = cyv * ccid; }
-        } else {
-          term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, cactive, a0, a1, p.n_invalid);
+        if (base + 32 < e) {  // next chunk of this view
+          i = base + 32 + lane;
+          active = i < e;
+          const int ii = active ? i : b;
+          yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii];
+        } else if (vi + 1 < S.y && m_nxt.z < m_nxt.w) {  // first chunk of the next view
+          i = m_nxt.z + lane;
+          active = i < m_nxt.w;
+          const int ii = active ? i : m_nxt.z;
+          yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii];
+          have_pf = true;
         }
-        if (WRITE_E && cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-a0[E_COL], -a1[E_COL]);
-#pragma unroll
-        for (int c = 0; c < GRAM_DIM; ++c) *reinterpret_cast<double2*>(XT + c * XT_LD + 2 * lane) = make_double2(a0[c], a1[c]);
-        __syncwarp();
-        if (VARIANT == 1) {  // timing experiment: no tensor work
-          c00[0] += XT[arow * XT_LD + acol]; c01[0] += XT[(8 + arow) * XT_LD + acol]; c11[1] += XT[lane];
-        } else {
-          // two independent accumulator sets (even / odd k-steps); a partial last chunk only spends DMMAs on rows that exist
-          const int ksteps = (min(32, e - base) + 1) >> 1;  // 2 rows per term, 4 rows per k-step
-#pragma unroll
-          for (int s = 0; s < 16; s += 2) {
-            if (s >= ksteps) break;
-            const double x0 = XT[arow * XT_LD + 4 * s + acol];
-            const double x1 = XT[(8 + arow) * XT_LD + 4 * s + acol];
-            const double z0 = XT[arow * XT_LD + 4 * s + 4 + acol];
-            const double z1 = XT[(8 + arow) * XT_LD + 4 * s + 4 + acol];
-            dmma(c00[0], c00[1], x0, x0);
-            dmma(d00[0], d00[1], z0, z0);
-            dmma(c01[0], c01[1], x0, x1);
-            dmma(d01[0], d01[1], z0, z1);
-            dmma(c11[0], c11[1], x1, x1);
-            dmma(d11[0], d11[1], z1, z1);
+        const int n = min(32, e - base);
+        const int kq = (n + 3) >> 2;  // DMMA k-steps per row half: a partial last chunk only spends DMMAs on rows that exist
+        double e0, e1;
+        const bool valid = term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, XT + lane, e0, e1);
+        if (cactive && !valid) atomicAdd(p.n_invalid, 1u);
+        const bool keep = cactive && valid;
+        if (__any_sync(0xffffffffu, !keep && lane < 4 * kq)) {
+          if (!keep) {
+            zero_rows(XT + lane);
+            e0 = 0.0;
+            e1 = 0.0;
           }
+        }
+        if (WRITE_E && cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-e0, -e1);
+        __syncwarp();
+        // operands of k-step s + 1 are loaded before the DMMAs of k-step s are issued
+        const double* xa = XT + arow * XT_LD + acol;
+        double x0 = xa[0], x1 = xa[8 * XT_LD], z0 = xa[32], z1 = xa[8 * XT_LD + 32];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s >= kq) break;
+          const int sn = s < 7 ? s + 1 : 7;  // rows beyond the chunk are stale but never used
+          const double nx0 = xa[4 * sn], nx1 = xa[8 * XT_LD + 4 * sn], nz0 = xa[32 + 4 * sn], nz1 = xa[8 * XT_LD + 32 + 4 * sn];
+          dmma(c00[0], c00[1], x0, x0);
+          dmma(c01[0], c01[1], x0, x1);
+          dmma(c11[0], c11[1], x1, x1);
+          dmma(c00[0], c00[1], z0, z0);
+          dmma(c01[0], c01[1], z0, z1);
+          dmma(c11[0], c11[1], z1, z1);
+          x0 = nx0; x1 = nx1; z0 = nz0; z1 = nz1;
         }
         __syncwarp();
       }
-      c00[0] += d00[0]; c00[1] += d00[1]; c01[0] += d01[0]; c01[1] += d01[1]; c11[0] += d11[0]; c11[1] += d11[1];
-      // ---- epilogue: G (full symmetric 16x16, ld 17) in shared memory, slice sum, view block ----
-      double* G = XT;
-      G[arow * G_LD + gc] = c00[0];
-      G[arow * G_LD + gc + 1] = c00[1];
-      G[arow * G_LD + 8 + gc] = c01[0];
-      G[arow * G_LD + 8 + gc + 1] = c01[1];
-      G[(8 + gc) * G_LD + arow] = c01[0];
-      G[(8 + gc + 1) * G_LD + arow] = c01[1];
-      G[(8 + arow) * G_LD + 8 + gc] = c11[0];
-      G[(8 + arow) * G_LD + 8 + gc + 1] = c11[1];
+      // ---- per view: tiles (0,0) and (0,1) row-major (the C fragment order is row-major 8x8), slice sum of all three ----
       {
+        double2* vb = reinterpret_cast<double2*>(p.VB + (size_t)view * VB_STRIDE);
+        vb[lane] = make_double2(c00[0], c00[1]);
+        vb[32 + lane] = make_double2(c01[0], c01[1]);
         double2* g2 = reinterpret_cast<double2*>(sG);
         double2 t0 = g2[lane], t1 = g2[32 + lane], t2 = g2[64 + lane];
         t0.x += c00[0]; t0.y += c00[1]; t1.x += c01[0]; t1.y += c01[1]; t2.x += c11[0]; t2.y += c11[1];
         g2[lane] = t0; g2[32 + lane] = t1; g2[64 + lane] = t2;
       }
-      for (int o = lane; o < 36; o += 32) {  // M = Pi_k P_v
-        const int r = o / 6, c = o % 6;
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s += sPi[r * 6 + a] * sp[12 + a * 6 + c];
-        sM[o] = s;
-      }
-      __syncwarp();
-      double* vb = p.VB + (size_t)view * VB_STRIDE;
-      for (int o = lane; o < 36; o += 32) {  // Y = G_xx M
-        const int r = o / 6, c = o % 6;
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s += G[r * G_LD + a] * sM[a * 6 + c];
-        sY[o] = s;
-        vb[VB_Y + o] = s;
-      }
-      for (int o = lane; o < PD * 6; o += 32) {  // W_k = G_cx M
-        const int r = o / 6, c = o % 6;
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s += G[(6 + r) * G_LD + a] * sM[a * 6 + c];
-        vb[VB_W + o] = s;
-      }
-      if (lane < 6) {  // b_k = -M^T G_xe
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s += sM[a * 6 + lane] * G[a * G_LD + E_COL];
-        vb[VB_B + lane] = -s;
-      }
-      __syncwarp();
-      for (int o = lane; o < 36; o += 32) {  // V_k = M^T Y
-        const int r = o / 6, c = o % 6;
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s += sM[a * 6 + r] * sY[a * 6 + c];
-        vb[VB_V + o] = s;
-      }
-      __syncwarp();
       m_cur = m_nxt;
       m_nxt = m_nn;
     }
@@ -541,258 +518,6 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
     double* out = p.gram_partial + (size_t)sl * GRAM_TILES;
     for (int o = lane; o < GRAM_TILES; o += 32) out[o] = sG[o];
     __syncwarp();
-  }
-}
-
-// ---- warp-specialised variant of the fused kernel ------------------------------------------------------------
-// One persistent 16-warp CTA per SM: 12 PRODUCER warps linearise 32-term chunks (lane per term, FP64 scalar pipe) into
-// their own shared-memory row buffer, 4 CONSUMER warps (one per SM sub-partition) do nothing but the DMMA Gram
-// accumulation, each serving 3 producers through mbarrier full/empty hand-offs.  When a view's last chunk has been
-// accumulated the consumer drops the 16x16 Gram block into the producer's G buffer and the PRODUCER runs the view
-// epilogue (view block + slice Gram sum), deferred until after it has submitted the next view's first chunk, so that
-// neither role waits on the other in steady state and the tensor pipe is fed continuously.
-constexpr int WS_CONSUMERS = 4;
-constexpr int WS_PRODUCERS = 12;
-constexpr int WS_THREADS = 32 * (WS_CONSUMERS + WS_PRODUCERS);
-constexpr int WS_G_DOUBLES = GRAM_DIM * G_LD;  // 272
-constexpr int WS_PROD_DOUBLES = XT_WARP_DOUBLES + 2 * WS_G_DOUBLES + 3 * 36 + 3 * SETPREP_STRIDE;  // XT | Gbuf | slice sum | Pi,M,Y | set consts x3
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  while (!mbar_try_wait(bar, parity)) {}
-}
-
-template <int MODEL, bool WRITE_E>
-__global__ void __launch_bounds__(WS_THREADS, 1) linearise_assemble_ws_kernel(DevProblem p, const int4* __restrict__ vmeta,
-                                                                                const int4* __restrict__ slices, int slice_lo, int slice_hi) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ unsigned long long bar_full[WS_PRODUCERS], bar_empty[WS_PRODUCERS], bar_g[WS_PRODUCERS];
-  __shared__ int s_info[WS_PRODUCERS];  // bits 0-7: DMMA k-steps of the chunk, bit 8: last chunk of the view; -1: producer finished
-  double* s_target = smem;
-  const int target_doubles = (p.n_target * 3 + 1) & ~1;
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
-  if (threadIdx.x < WS_PRODUCERS) {
-    mbar_init(&bar_full[threadIdx.x], 1);
-    mbar_init(&bar_empty[threadIdx.x], 1);
-    mbar_init(&bar_g[threadIdx.x], 1);
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  __syncthreads();
-  const int arow = lane >> 2, acol = lane & 3;
-  const int gc = 2 * acol;
-  double* prod_base = smem + target_doubles;
-
-  if (wib < WS_CONSUMERS) {
-    // =============================== consumer: DMMA only ===============================
-    double acc[3][6];
-    unsigned ph[3] = {0u, 0u, 0u};
-    bool done[3] = {false, false, false};
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-#pragma unroll
-      for (int t = 0; t < 6; ++t) acc[q][t] = 0.0;
-    int n_done = 0;
-    while (n_done < 3) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int pr = wib + WS_CONSUMERS * q;  // producers served by this consumer
-        if (done[q] || !mbar_try_wait(&bar_full[pr], ph[q])) continue;
-        ph[q] ^= 1u;
-        const int info = s_info[pr];
-        if (info < 0) {
-          done[q] = true;
-          ++n_done;
-          continue;
-        }
-        const double* XT = prod_base + (size_t)pr * WS_PROD_DOUBLES;
-        const int ksteps = info & 0xff;  // a partial last chunk only spends DMMAs on rows that exist
-#pragma unroll
-        for (int s = 0; s < 16; ++s) {
-          if (s >= ksteps) break;
-          const double x0 = XT[arow * XT_LD + 4 * s + acol];
-          const double x1 = XT[(8 + arow) * XT_LD + 4 * s + acol];
-          dmma(acc[q][0], acc[q][1], x0, x0);
-          dmma(acc[q][2], acc[q][3], x0, x1);
-          dmma(acc[q][4], acc[q][5], x1, x1);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_empty[pr]);  // every lane's operand loads have been consumed by its DMMAs
-        if (info & 0x100) {
-          double* G = prod_base + (size_t)pr * WS_PROD_DOUBLES + XT_WARP_DOUBLES;
-          G[arow * G_LD + gc] = acc[q][0];
-          G[arow * G_LD + gc + 1] = acc[q][1];
-          G[arow * G_LD + 8 + gc] = acc[q][2];
-          G[arow * G_LD + 8 + gc + 1] = acc[q][3];
-          G[(8 + gc) * G_LD + arow] = acc[q][2];
-          G[(8 + gc + 1) * G_LD + arow] = acc[q][3];
-          G[(8 + arow) * G_LD + 8 + gc] = acc[q][4];
-          G[(8 + arow) * G_LD + 8 + gc + 1] = acc[q][5];
-#pragma unroll
-          for (int t = 0; t < 6; ++t) acc[q][t] = 0.0;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_g[pr]);
-        }
-      }
-    }
-    return;
-  }
-
-  // =============================== producer ===============================
-  const int me = wib - WS_CONSUMERS;
-  double* XT = prod_base + (size_t)me * WS_PROD_DOUBLES;
-  double* G = XT + XT_WARP_DOUBLES;
-  double* sG = G + WS_G_DOUBLES;  // slice sum, same full layout as G
-  double* sPi = sG + WS_G_DOUBLES;
-  double* sM = sPi + 36;
-  double* sY = sM + 36;
-  double* sSP = sY + 36;          // [3][48]
-  constexpr int PD = model_P(MODEL) + model_D(MODEL);
-  unsigned ph_empty = 1u, ph_g = 0u;  // a fresh barrier reports the "previous" phase (parity 1) as complete
-  const int pw = blockIdx.x * WS_PRODUCERS + me;
-  const int n_pw = gridDim.x * WS_PRODUCERS;
-
-  // view epilogue from the Gram block the consumer left in G
-  auto epilogue = [&](int view, const double* sp) {
-    mbar_wait(&bar_g[me], ph_g);
-    ph_g ^= 1u;
-    for (int o = lane; o < 36; o += 32) {  // M = Pi_k P_v
-      const int r = o / 6, c = o % 6;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sPi[r * 6 + a] * sp[12 + a * 6 + c];
-      sM[o] = s;
-    }
-    for (int o = lane; o < WS_G_DOUBLES; o += 32) sG[o] += G[o];
-    __syncwarp();
-    double* vb = p.VB + (size_t)view * VB_STRIDE;
-    for (int o = lane; o < 36; o += 32) {  // Y = G_xx M
-      const int r = o / 6, c = o % 6;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += G[r * G_LD + a] * sM[a * 6 + c];
-      sY[o] = s;
-      vb[VB_Y + o] = s;
-    }
-    for (int o = lane; o < PD * 6; o += 32) {  // W_k = G_cx M
-      const int r = o / 6, c = o % 6;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += G[(6 + r) * G_LD + a] * sM[a * 6 + c];
-      vb[VB_W + o] = s;
-    }
-    if (lane < 6) {  // b_k = -M^T G_xe
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sM[a * 6 + lane] * G[a * G_LD + E_COL];
-      vb[VB_B + lane] = -s;
-    }
-    __syncwarp();
-    for (int o = lane; o < 36; o += 32) {  // V_k = M^T Y
-      const int r = o / 6, c = o % 6;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sM[a * 6 + r] * sY[a * 6 + c];
-      vb[VB_V + o] = s;
-    }
-    __syncwarp();
-  };
-
-  for (int sl = slice_lo + pw; sl < slice_hi; sl += n_pw) {
-    const int4 S = slices[sl];
-    const int cam = S.z;
-    double prm[CAM_PARAM_STRIDE];
-#pragma unroll
-    for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
-    double camT[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) camT[i] = p.camT[cam * 12 + i];
-    for (int o = lane; o < 36; o += 32) sPi[o] = p.camPi[cam * 36 + o];
-    for (int o = lane; o < WS_G_DOUBLES; o += 32) sG[o] = 0.0;
-    int4 m_cur = vmeta[S.x];
-    int4 m_nxt = (S.x + 1 < S.y) ? vmeta[S.x + 1] : m_cur;
-    if (lane < 24) cp_async_16(sSP + 2 * lane, p.set_prep + (size_t)m_cur.y * SETPREP_STRIDE + 2 * lane);
-    cp_async_commit();
-    int pend_view = -1;
-    const double* pend_sp = sSP;
-    for (int vi = S.x; vi < S.y; ++vi) {
-      const int buf = (vi - S.x) % 3;
-      const int view = m_cur.x;
-      const int b = m_cur.z, e = m_cur.w;
-      int i = b + lane;
-      bool active = i < e;
-      int ii = active ? i : b;
-      double yu = 0.0, yv = 0.0;
-      int cid = 0;
-      if (b < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
-      const int4 m_nn = (vi + 2 < S.y) ? vmeta[vi + 2] : m_nxt;
-      cp_async_wait_all();
-      __syncwarp();
-      if (b >= e && pend_view >= 0) { epilogue(pend_view, pend_sp); pend_view = -1; }  // an empty view has no chunk to hide it behind
-      if (vi + 1 < S.y && lane < 24)
-        cp_async_16(sSP + ((buf + 1) % 3) * SETPREP_STRIDE + 2 * lane, p.set_prep + (size_t)m_nxt.y * SETPREP_STRIDE + 2 * lane);
-      cp_async_commit();
-      const double* sp = sSP + buf * SETPREP_STRIDE;
-      double Rcw[9], tcw[3];
-      view_transform_prepped(sp, camT, Rcw, tcw);
-      for (int base = b; base < e; base += 32) {
-        const double cyu = yu, cyv = yv;
-        const int ccid = cid;
-        const bool cactive = active;
-        const int ci = i;
-        const bool last = base + 32 >= e;
-        i = base + 32 + lane;
-        active = i < e;
-        ii = active ? i : b;
-        if (!last) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
-        double a0[GRAM_DIM], a1[GRAM_DIM];
-        term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, cactive, a0, a1, p.n_invalid);
-        if (WRITE_E && cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-a0[E_COL], -a1[E_COL]);
-        // the G buffer must be free before a 'last' chunk is handed over
-        if (pend_view >= 0 && last) { epilogue(pend_view, pend_sp); pend_view = -1; }
-        mbar_wait(&bar_empty[me], ph_empty);
-        ph_empty ^= 1u;
-#pragma unroll
-        for (int c = 0; c < GRAM_DIM; ++c) *reinterpret_cast<double2*>(XT + c * XT_LD + 2 * lane) = make_double2(a0[c], a1[c]);
-        if (lane == 0) s_info[me] = ((min(32, e - base) + 1) >> 1) | (last ? 0x100 : 0);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_full[me]);
-        if (pend_view >= 0) { epilogue(pend_view, pend_sp); pend_view = -1; }
-      }
-      if (b < e) { pend_view = view; pend_sp = sp; }
-      m_cur = m_nxt;
-      m_nxt = m_nn;
-    }
-    if (pend_view >= 0) epilogue(pend_view, pend_sp);
-    cp_async_wait_all();
-    // slice Gram sum in the tile order finalize_gram_kernel expects
-    double* out = p.gram_partial + (size_t)sl * GRAM_TILES;
-    for (int t = lane; t < GRAM_TILES; t += 32) {
-      const int tile = t >> 6, ln = (t & 63) >> 1, el = t & 1;
-      const int r = (tile == 2 ? 8 : 0) + (ln >> 2), c = (tile >= 1 ? 8 : 0) + 2 * (ln & 3) + el;
-      out[t] = sG[r * G_LD + c];
-    }
-    __syncwarp();
-  }
-  // tell the consumer this producer is finished
-  mbar_wait(&bar_empty[me], ph_empty);
-  if (lane == 0) {
-    s_info[me] = -1;
-    mbar_arrive(&bar_full[me]);
   }
 }
 
@@ -828,7 +553,6 @@ __global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(De
   double* sM = Bf + bfrag_pairs * 32;                                 // Pi_k P_v
   double* sSP = sM + 36;                                              // per-set constants
   for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
-  for (int o = lane; o < XT_LD; o += 32) XT[E_COL * XT_LD + o] = 0.0;  // the e column never enters J: its k-row stays zero
   __syncthreads();
   constexpr int P = model_P(MODEL), D = model_D(MODEL);
   const int arow = lane >> 2, acol = lane & 3;
@@ -920,11 +644,17 @@ __global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(De
         ii = active ? i : b;
         if (base + 32 < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
         {
-          double a0[GRAM_DIM], a1[GRAM_DIM];
-          term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, cactive, a0, a1, p.n_invalid);
-          if (cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-a0[E_COL], -a1[E_COL]);
-#pragma unroll
-          for (int c = 0; c < E_COL; ++c) *reinterpret_cast<double2*>(XT + c * XT_LD + 2 * lane) = make_double2(a0[c], a1[c]);
+          double e0, e1;
+          const bool valid = term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, XT + lane, e0, e1);
+          if (cactive && !valid) atomicAdd(p.n_invalid, 1u);
+          if (__any_sync(0xffffffffu, cactive && !valid)) {
+            if (cactive && !valid) {
+              zero_rows(XT + lane);
+              e0 = 0.0;
+              e1 = 0.0;
+            }
+          }
+          if (cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-e0, -e1);
         }
         __syncwarp();
         const int rows_valid = 2 * min(32, e - base);
@@ -933,8 +663,9 @@ __global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(De
         for (int mt = 0; mt < mtiles; ++mt) {
           double a[4];
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) a[ks] = XT[(4 * ks + acol) * XT_LD + 8 * mt + arow];
-          const int row = 8 * mt + arow;
+          // fragment row arow = (term 4 * mt + arow % 4, residual arow / 4): conflict-free loads from the u-rows | v-rows staging
+          for (int ks = 0; ks < 4; ++ks) a[ks] = XT[(4 * ks + acol) * XT_LD + 32 * (arow >> 2) + 4 * mt + (arow & 3)];
+          const int row = 8 * mt + 2 * (arow & 3) + (arow >> 2);
           const bool row_ok = row < rows_valid;
           double* __restrict__ drow = dst_chunk + (long long)row * W + 2 * acol;
           const double* bf = Bf + lane;
@@ -965,90 +696,130 @@ __global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(De
 }
 
 // =========================================================================================================
-// set reduction: one warp per synced set.  V_v = sum_k V_k, b_v = sum_k b_k, W_v rows: intrinsics of camera k = W_k,
-// baseline j = sum_{k>j} A_{j,k}^T Y_k.                                  ≙ SparseBlockMatrix::block(r,c) += J1^T J2
+// set reduction: one warp per synced set.  From the two Gram tiles the fused kernel left per view (G_xx = G[0:6][0:6],
+// G_cx = G[6:6+PD][0:6], G_xe = G[0:6][15]) and M = Pi_k P_v:
+//   Y_k = G_xx M,  V_v = sum_k M^T Y_k,  b_v = -sum_k M^T G_xe,  W_v rows: intrinsics of camera k = G_cx M,
+//   baseline j = sum_{k>j} A_{j,k}^T Y_k.                                  ≙ SparseBlockMatrix::block(r,c) += J1^T J2
 // =========================================================================================================
-constexpr int SR_WARPS = 8;
+constexpr int SR_WARPS = 4;
+__host__ __device__ constexpr int sr_warp_doubles(int n_cams) { return 200 * n_cams + 36; }  // tiles (later Z_j) | M | Y | P_v
 
-// Baseline rows by a backward recurrence along the chain instead of the O(C^2) sum over (j,k) pairs:
+// Phases per set, each a flat index space over all cameras so that no lane idles and a phase has many independent
+// products in flight: (1) M_k = Pi_k P_v; (2) Y_k = G_xx M_k, W rows of the intrinsics, b_v; (3) V_v (upper triangle,
+// mirrored); (4) the baseline rows by the backward recurrence
 //   W_base(j) = sum_{k>j} A_{j,k}^T Y_k,  A_{j,k} = X_{k,j} M_j,  X_{k,j} = X_{k,j+1} boxTimes(B_{j+1})
-//   =>  Z_j := sum_{k>j} X_{k,j}^T Y_k = Y_{j+1} + boxTimes(B_{j+1})^T Z_{j+1},  Z_{C-1} = 0,  W_base(j) = M_j^T Z_j.
+//   =>  Z_j := sum_{k>j} X_{k,j}^T Y_k = Y_{j+1} + boxTimes(B_{j+1})^T Z_{j+1},  Z_{C-1} = 0,  W_base(j) = M_j^T Z_j
+// (O(C) instead of the O(C^2) sum over (j,k) pairs; only the Z chain is sequential, the M_j^T Z_j products run together).
 __global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int nb = p.n_cams - 1;
+  const int C = p.n_cams, nb = C - 1;
+  const int n_intr = C > 1 ? p.base_off[0] : p.n_c;  // rows of W_v that belong to intrinsics
   double* sBt = smem;                       // [nb][36]
   double* sMj = sBt + 36 * nb;              // [nb][36]
-  double* sY = sMj + 36 * nb + (size_t)wib * (36 * p.n_cams + 72);  // per warp: Y_k of every camera, Z, T
-  double* sZ = sY + 36 * p.n_cams;
-  double* sT = sZ + 36;
+  double* sPi = sMj + 36 * nb;              // [C][36]
+  int* sRow = reinterpret_cast<int*>(sPi + 36 * C);  // [n_intr] camera << 8 | local parameter index
+  double* sTile = sPi + 36 * C + (((n_intr + 3) >> 2) << 1) + (size_t)wib * sr_warp_doubles(C);  // per warp: [C][128] tiles, later Z_j for all j
+  double* sM = sTile + 128 * C;             // [C][36]
+  double* sY = sM + 36 * C;                 // [C][36]
+  double* sPv = sY + 36 * C;                // [36]
   for (int i = threadIdx.x; i < 36 * nb; i += blockDim.x) {
     sBt[i] = p.baseBt[i];
     sMj[i] = p.baseM[i];
   }
+  for (int i = threadIdx.x; i < 36 * C; i += blockDim.x) sPi[i] = p.camPi[i];
+  for (int k = 0; k < C; ++k)
+    for (int i = threadIdx.x; i < p.cam_P[k] + p.cam_D[k]; i += blockDim.x) sRow[p.intr_off[k] + i] = (k << 8) | i;
   __syncthreads();
   for (int set = blockIdx.x * SR_WARPS + wib; set < p.n_sets; set += gridDim.x * SR_WARPS) {
     double* __restrict__ Wout = p.W + (size_t)set * p.n_c * 6;
-    double v0 = 0.0, v1 = 0.0, bb = 0.0;  // lane o and o + 32 of V, lane < 6 of b
-    // lane k fetches the view of camera k (n_cams <= 32), so that the view-block loads below have no dependent address chain
+    // lane k fetches the view of camera k (n_cams <= 32), so that the tile loads below have no dependent address chain
     int my_view = -1;
-    if (lane < p.n_cams) {
-      const int w = p.set_view[(size_t)set * p.n_cams + lane];
+    if (lane < C) {
+      const int w = p.set_view[(size_t)set * C + lane];
       if (w >= 0 && p.view_begin[w + 1] > p.view_begin[w]) my_view = w;
     }
-    for (int k = 0; k < p.n_cams; ++k) {
-      const int view = __shfl_sync(0xffffffffu, my_view, k);
-      const int PD = p.cam_P[k] + p.cam_D[k];
-      if (view < 0) {
-        for (int o = lane; o < PD * 6; o += 32) Wout[(size_t)p.intr_off[k] * 6 + o] = 0.0;
-        for (int o = lane; o < 36; o += 32) sY[k * 36 + o] = 0.0;
-        continue;
-      }
-      const double* __restrict__ vb = p.VB + (size_t)view * VB_STRIDE;
-      const double a0 = vb[VB_V + lane];
-      const double a1 = lane < 4 ? vb[VB_V + 32 + lane] : 0.0;
-      const double a2 = lane < 6 ? vb[VB_B + lane] : 0.0;
-      const double y0 = vb[VB_Y + lane];
-      const double y1 = lane < 4 ? vb[VB_Y + 32 + lane] : 0.0;
-      const double w0 = lane < PD * 6 ? vb[VB_W + lane] : 0.0;
-      const double w1 = lane + 32 < PD * 6 ? vb[VB_W + 32 + lane] : 0.0;
-      v0 += a0;
-      v1 += a1;
-      bb += a2;
-      sY[k * 36 + lane] = y0;
-      if (lane < 4) sY[k * 36 + 32 + lane] = y1;
-      if (lane < PD * 6) Wout[(size_t)p.intr_off[k] * 6 + lane] = w0;
-      if (lane + 32 < PD * 6) Wout[(size_t)p.intr_off[k] * 6 + 32 + lane] = w1;
+    {
+      const double* sp = p.set_prep + (size_t)set * SETPREP_STRIDE + 12;
+      sPv[lane] = sp[lane];
+      if (lane < 4) sPv[32 + lane] = sp[32 + lane];
     }
-    p.V[(size_t)set * 36 + lane] = v0;
-    if (lane < 4) p.V[(size_t)set * 36 + 32 + lane] = v1;
-    if (lane < 6) p.bv[(size_t)set * 6 + lane] = bb;
-    for (int o = lane; o < 36; o += 32) sZ[o] = 0.0;
+    for (int k = 0; k < C; ++k) {  // all tiles of the set: independent 32-byte loads per lane
+      const int view = __shfl_sync(0xffffffffu, my_view, k);
+      double4 t = make_double4(0.0, 0.0, 0.0, 0.0);  // a camera without a view contributes zeros
+      if (view >= 0) t = reinterpret_cast<const double4*>(p.VB + (size_t)view * VB_STRIDE)[lane];
+      reinterpret_cast<double4*>(sTile + 128 * k)[lane] = t;
+    }
     __syncwarp();
+    for (int q = lane; q < 36 * C; q += 32) {  // (1) M_k = Pi_k P_v
+      const int k = q / 36, o = q - 36 * k, r = o / 6, c = o - 6 * r;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sPi[k * 36 + r * 6 + a] * sPv[a * 6 + c];
+      sM[q] = s;
+    }
+    __syncwarp();
+    for (int q = lane; q < 36 * C; q += 32) {  // (2a) Y_k = G_xx M_k
+      const int k = q / 36, o = q - 36 * k, r = o / 6, c = o - 6 * r;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sTile[128 * k + r * 8 + a] * sM[k * 36 + a * 6 + c];
+      sY[q] = s;
+    }
+    for (int q = lane; q < 6 * n_intr; q += 32) {  // (2b) W rows of the intrinsics: G_cx M ; G_cx[r][a] = G[a][6 + r]
+      const int row = q / 6, c = q - 6 * row;
+      const int k = sRow[row] >> 8, r = sRow[row] & 0xff;
+      const double* g = sTile + 128 * k + (r < 2 ? 6 + r : 64 + (r - 2));
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += g[a * 8] * sM[k * 36 + a * 6 + c];
+      Wout[q] = s;
+    }
+    if (lane < 6) {  // (2c) b_v = -sum_k M_k^T G_xe ; G_xe[a] = tile (0,1) column 7
+      double s = 0.0;
+      for (int k = 0; k < C; ++k) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s += sM[k * 36 + a * 6 + lane] * sTile[128 * k + 64 + a * 8 + 7];
+      }
+      p.bv[(size_t)set * 6 + lane] = -s;
+    }
+    __syncwarp();
+    if (lane < 21) {  // (3) V_v = sum_k M_k^T Y_k, upper triangle
+      int r = 0, rem = lane;
+      while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+      const int c = r + rem;
+      double s = 0.0;
+      for (int k = 0; k < C; ++k) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s += sM[k * 36 + a * 6 + r] * sY[k * 36 + a * 6 + c];
+      }
+      p.V[(size_t)set * 36 + r * 6 + c] = s;
+      p.V[(size_t)set * 36 + c * 6 + r] = s;
+    }
+    // (4) Z chain; Z_j is kept in the tile area (free now), Z_{nb-1} = Y_{nb}
+    double* sZall = sTile;
     for (int j = nb - 1; j >= 0; --j) {
-      // Z_j = Y_{j+1} + boxTimes(B_{j+1})^T Z_{j+1}
+      const double* zp = sZall + 36 * (j + 1);
       for (int o = lane; o < 36; o += 32) {
-        const int r = o / 6, c = o % 6;
+        const int r = o / 6, c = o - 6 * r;
         double s = sY[(j + 1) * 36 + o];
         if (j + 1 < nb) {
 #pragma unroll
-          for (int a = 0; a < 6; ++a) s += sBt[(j + 1) * 36 + a * 6 + r] * sZ[a * 6 + c];
+          for (int a = 0; a < 6; ++a) s += sBt[(j + 1) * 36 + a * 6 + r] * zp[a * 6 + c];
         }
-        sT[o] = s;
-      }
-      __syncwarp();
-      for (int o = lane; o < 36; o += 32) sZ[o] = sT[o];
-      __syncwarp();
-      for (int o = lane; o < 36; o += 32) {  // W_base(j) = M_j^T Z_j
-        const int r = o / 6, c = o % 6;
-        double s = 0.0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s += sMj[j * 36 + a * 6 + r] * sZ[a * 6 + c];
-        Wout[(size_t)p.base_off[j] * 6 + o] = s;
+        sZall[36 * j + o] = s;
       }
       __syncwarp();
     }
+    for (int q = lane; q < 36 * nb; q += 32) {  // W_base(j) = M_j^T Z_j
+      const int j = q / 36, o = q - 36 * j, r = o / 6, c = o - 6 * r;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += sMj[j * 36 + a * 6 + r] * sZall[36 * j + a * 6 + c];
+      Wout[(size_t)6 * n_intr + q] = s;
+    }
+    __syncwarp();
   }
 }
 
@@ -1658,29 +1429,11 @@ cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int
   return cudaGetLastError();
 }
 
-static bool la_use_ws() {
-  static int v = -1;
-  if (v < 0) v = getenv("KB_LA_WS") ? atoi(getenv("KB_LA_WS")) : 0;  // measured equal-or-slower than the symmetric kernel
-  return v != 0;
-}
-int la_grid_warps() { return la_use_ws() ? sm_count() * WS_PRODUCERS : sm_count() * 2 * LA_WARPS; }
+int la_grid_warps() { return sm_count() * 2 * LA_WARPS; }
 
 template <int MODEL, bool WRITE_E>
 static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const int4* slices, int lo, int hi, StreamCtx& s) {
   if (hi <= lo) return cudaSuccess;
-  if (la_use_ws()) {
-    const size_t smem_ws = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + (size_t)WS_PRODUCERS * WS_PROD_DOUBLES);
-    static size_t attr_ws = 0;
-    if (smem_ws > attr_ws) {
-      cudaError_t e = cudaFuncSetAttribute(linearise_assemble_ws_kernel<MODEL, WRITE_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws);
-      if (e != cudaSuccess) return e;
-      attr_ws = smem_ws;
-    }
-    const int grid_ws = min((hi - lo + WS_PRODUCERS - 1) / WS_PRODUCERS, sm_count());
-    linearise_assemble_ws_kernel<MODEL, WRITE_E><<<grid_ws, WS_THREADS, smem_ws, s.stream>>>(p, vmeta, slices, lo, hi);
-    KB_LAUNCHED(s);
-    return cudaGetLastError();
-  }
   const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -1689,15 +1442,6 @@ static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const
     attr_smem = smem;
   }
   const int grid = min((hi - lo + LA_WARPS - 1) / LA_WARPS, sm_count() * 2);
-  static int variant = -1;
-  if (variant < 0) variant = getenv("KB_LA_VARIANT") ? atoi(getenv("KB_LA_VARIANT")) : 0;  // timing experiments only (wrong results)
-  if (MODEL == 0 && WRITE_E && variant == 1) {
-    cudaFuncSetAttribute(linearise_assemble_kernel<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    linearise_assemble_kernel<0, true, 1><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
-  } else if (MODEL == 0 && WRITE_E && variant == 2) {
-    cudaFuncSetAttribute(linearise_assemble_kernel<0, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    linearise_assemble_kernel<0, true, 2><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
-  } else
   linearise_assemble_kernel<MODEL, WRITE_E><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
   KB_LAUNCHED(s);
   return cudaGetLastError();
@@ -1764,7 +1508,8 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
 
 // V_v, b_v, W_v from the view blocks; U, b_c from the per-camera Gram sums
 cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s) {
-  const size_t smem = sizeof(double) * (72 * (size_t)(p.n_cams - 1) + SR_WARPS * (36 * (size_t)p.n_cams + 72));
+  const int n_intr = p.n_cams > 1 ? p.base_off[0] : p.n_c;
+  const size_t smem = sizeof(double) * (72 * (size_t)(p.n_cams - 1) + 36 * (size_t)p.n_cams + (((n_intr + 3) >> 2) << 1) + SR_WARPS * (size_t)sr_warp_doubles(p.n_cams));
   if (p.n_sets > 0) {
     static size_t attr_smem = 0;
     if (smem > attr_smem && smem > 48 * 1024) {
@@ -1772,7 +1517,8 @@ cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s) {
       if (e != cudaSuccess) return e;
       attr_smem = smem;
     }
-    const int grid = min((p.n_sets + SR_WARPS - 1) / SR_WARPS, sm_count() * 4);
+    const int ctas_per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem + 1024)));
+    const int grid = min((p.n_sets + SR_WARPS - 1) / SR_WARPS, sm_count() * ctas_per_sm);
     set_reduce_kernel<<<grid, SR_WARPS * 32, smem, s.stream>>>(p);
     KB_LAUNCHED(s);
   }
