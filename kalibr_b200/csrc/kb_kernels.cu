@@ -701,37 +701,35 @@ __global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(De
 //   Y_k = G_xx M,  V_v = sum_k M^T Y_k,  b_v = -sum_k M^T G_xe,  W_v rows: intrinsics of camera k = G_cx M,
 //   baseline j = sum_{k>j} A_{j,k}^T Y_k.                                  ≙ SparseBlockMatrix::block(r,c) += J1^T J2
 // =========================================================================================================
-constexpr int SR_WARPS = 4;
-__host__ __device__ constexpr int sr_warp_doubles(int n_cams) { return 200 * n_cams + 36; }  // tiles (later Z_j) | M | Y | P_v
+constexpr int SR_WARPS = 8;
 
-// Phases per set, each a flat index space over all cameras so that no lane idles and a phase has many independent
-// products in flight: (1) M_k = Pi_k P_v; (2) Y_k = G_xx M_k, W rows of the intrinsics, b_v; (3) V_v (upper triangle,
-// mirrored); (4) the baseline rows by the backward recurrence
-//   W_base(j) = sum_{k>j} A_{j,k}^T Y_k,  A_{j,k} = X_{k,j} M_j,  X_{k,j} = X_{k,j+1} boxTimes(B_{j+1})
-//   =>  Z_j := sum_{k>j} X_{k,j}^T Y_k = Y_{j+1} + boxTimes(B_{j+1})^T Z_{j+1},  Z_{C-1} = 0,  W_base(j) = M_j^T Z_j
-// (O(C) instead of the O(C^2) sum over (j,k) pairs; only the Z chain is sequential, the M_j^T Z_j products run together).
+// Layout changes between DMMA fragments, by warp shuffles.  X is an 8x8 matrix in C-fragment layout: lane l holds
+// X[l/4][2(l%4)] and X[l/4][2(l%4)+1].  The B fragment of X for k-step ks (b: row k = l%4, col n = l/4) is X[4ks + l%4][l/4];
+// the A fragment of X^T for k-step ks (a: row m = l/4, col k = l%4) is the very same element.
+__device__ __forceinline__ double c_to_b(double c0, double c1, int ks, int arow, int acol) {
+  const int src = 4 * (4 * ks + acol) + (arow >> 1);
+  const double v0 = __shfl_sync(0xffffffffu, c0, src), v1 = __shfl_sync(0xffffffffu, c1, src);
+  return (arow & 1) ? v1 : v0;
+}
+
+// Everything is a chain of 8x8 FP64 tensor-core products held in registers - no shared memory, so the kernel is bounded
+// only by the tile loads.  Cameras are walked from the last to the first so that the baseline rows follow from a running
+//   Z_j := sum_{k>j} X_{k,j}^T Y_k = Y_{j+1} + boxTimes(B_{j+1})^T Z_{j+1},   W_base(j) = M_j^T Z_j
+// (W_base(j) = sum_{k>j} A_{j,k}^T Y_k with A_{j,k} = X_{k,j} M_j, X_{k,j} = X_{k,j+1} boxTimes(B_{j+1}): O(C) instead of O(C^2)).
+// Per camera k with its Gram tiles G = [G00 | G01] (rows: pose 0..5, first two intrinsics; G01 column 7 = e):
+//   M  = Pi_k P_v                                  (2 DMMA)
+//   R0 = G00 M       rows 0..5 = Y_k, rows 6,7 = W rows of the first two intrinsics          (2 DMMA)
+//   R1 = G01^T M     rows 0..PD-3 = W rows of the remaining intrinsics, row 7 = -b_k^T       (2 DMMA)
+//   V += M^T Y_k                                                                              (2 DMMA)
 __global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p) {
-  extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int C = p.n_cams, nb = C - 1;
-  const int n_intr = C > 1 ? p.base_off[0] : p.n_c;  // rows of W_v that belong to intrinsics
-  double* sBt = smem;                       // [nb][36]
-  double* sMj = sBt + 36 * nb;              // [nb][36]
-  double* sPi = sMj + 36 * nb;              // [C][36]
-  int* sRow = reinterpret_cast<int*>(sPi + 36 * C);  // [n_intr] camera << 8 | local parameter index
-  double* sTile = sPi + 36 * C + (((n_intr + 3) >> 2) << 1) + (size_t)wib * sr_warp_doubles(C);  // per warp: [C][128] tiles, later Z_j for all j
-  double* sM = sTile + 128 * C;             // [C][36]
-  double* sY = sM + 36 * C;                 // [C][36]
-  double* sPv = sY + 36 * C;                // [36]
-  for (int i = threadIdx.x; i < 36 * nb; i += blockDim.x) {
-    sBt[i] = p.baseBt[i];
-    sMj[i] = p.baseM[i];
-  }
-  for (int i = threadIdx.x; i < 36 * C; i += blockDim.x) sPi[i] = p.camPi[i];
-  for (int k = 0; k < C; ++k)
-    for (int i = threadIdx.x; i < p.cam_P[k] + p.cam_D[k]; i += blockDim.x) sRow[p.intr_off[k] + i] = (k << 8) | i;
-  __syncthreads();
+  const int arow = lane >> 2, acol = lane & 3;
+  const int C = p.n_cams;
+  // operand element of a 6x6 row-major matrix, zero padded to 8x8:  direct[ks] = X[arow][4ks + acol],  transposed[ks] = X[4ks + acol][arow]
+  const bool in0 = arow < 6, in1 = arow < 6 && acol < 2;  // k-step 0: k = acol < 4 ; k-step 1: k = 4 + acol < 6
+  const int d0 = arow * 6 + acol, d1 = arow * 6 + 4 + acol;
+  const int t0 = acol * 6 + arow, t1 = (4 + acol) * 6 + arow;
   for (int set = blockIdx.x * SR_WARPS + wib; set < p.n_sets; set += gridDim.x * SR_WARPS) {
     double* __restrict__ Wout = p.W + (size_t)set * p.n_c * 6;
     // lane k fetches the view of camera k (n_cams <= 32), so that the tile loads below have no dependent address chain
@@ -740,86 +738,79 @@ __global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p)
       const int w = p.set_view[(size_t)set * C + lane];
       if (w >= 0 && p.view_begin[w + 1] > p.view_begin[w]) my_view = w;
     }
+    const double* pv = p.set_prep + (size_t)set * SETPREP_STRIDE + 12;
+    const double pb0 = in0 ? pv[t0] : 0.0, pb1 = in1 ? pv[t1] : 0.0;  // B fragments of P_v
+    double v0 = 0.0, v1 = 0.0;    // V_v accumulator (C layout)
+    double bs0 = 0.0, bs1 = 0.0;  // running R1 (row 7 = -b_v^T)
+    double z0 = 0.0, z1 = 0.0;    // Z (C layout)
+    double zb0 = 0.0, zb1 = 0.0;  // its B fragments
+    // A fragments of [G00 ; G01^T] of the camera about to be processed (zeros when it has no view in this set)
+    double g00a = 0.0, g00b = 0.0, g01a = 0.0, g01b = 0.0;
     {
-      const double* sp = p.set_prep + (size_t)set * SETPREP_STRIDE + 12;
-      sPv[lane] = sp[lane];
-      if (lane < 4) sPv[32 + lane] = sp[32 + lane];
-    }
-    for (int k = 0; k < C; ++k) {  // all tiles of the set: independent 32-byte loads per lane
-      const int view = __shfl_sync(0xffffffffu, my_view, k);
-      double4 t = make_double4(0.0, 0.0, 0.0, 0.0);  // a camera without a view contributes zeros
-      if (view >= 0) t = reinterpret_cast<const double4*>(p.VB + (size_t)view * VB_STRIDE)[lane];
-      reinterpret_cast<double4*>(sTile + 128 * k)[lane] = t;
-    }
-    __syncwarp();
-    for (int q = lane; q < 36 * C; q += 32) {  // (1) M_k = Pi_k P_v
-      const int k = q / 36, o = q - 36 * k, r = o / 6, c = o - 6 * r;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sPi[k * 36 + r * 6 + a] * sPv[a * 6 + c];
-      sM[q] = s;
-    }
-    __syncwarp();
-    for (int q = lane; q < 36 * C; q += 32) {  // (2a) Y_k = G_xx M_k
-      const int k = q / 36, o = q - 36 * k, r = o / 6, c = o - 6 * r;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sTile[128 * k + r * 8 + a] * sM[k * 36 + a * 6 + c];
-      sY[q] = s;
-    }
-    for (int q = lane; q < 6 * n_intr; q += 32) {  // (2b) W rows of the intrinsics: G_cx M ; G_cx[r][a] = G[a][6 + r]
-      const int row = q / 6, c = q - 6 * row;
-      const int k = sRow[row] >> 8, r = sRow[row] & 0xff;
-      const double* g = sTile + 128 * k + (r < 2 ? 6 + r : 64 + (r - 2));
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += g[a * 8] * sM[k * 36 + a * 6 + c];
-      Wout[q] = s;
-    }
-    if (lane < 6) {  // (2c) b_v = -sum_k M_k^T G_xe ; G_xe[a] = tile (0,1) column 7
-      double s = 0.0;
-      for (int k = 0; k < C; ++k) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s += sM[k * 36 + a * 6 + lane] * sTile[128 * k + 64 + a * 8 + 7];
+      const int view = __shfl_sync(0xffffffffu, my_view, C - 1);
+      if (view >= 0) {
+        const double* t = p.VB + (size_t)view * VB_STRIDE;
+        g00a = t[arow * 8 + acol]; g00b = t[arow * 8 + 4 + acol];
+        g01a = t[64 + acol * 8 + arow]; g01b = t[64 + (4 + acol) * 8 + arow];
       }
-      p.bv[(size_t)set * 6 + lane] = -s;
     }
-    __syncwarp();
-    if (lane < 21) {  // (3) V_v = sum_k M_k^T Y_k, upper triangle
-      int r = 0, rem = lane;
-      while (rem >= 6 - r) { rem -= 6 - r; ++r; }
-      const int c = r + rem;
-      double s = 0.0;
-      for (int k = 0; k < C; ++k) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) s += sM[k * 36 + a * 6 + r] * sY[k * 36 + a * 6 + c];
-      }
-      p.V[(size_t)set * 36 + r * 6 + c] = s;
-      p.V[(size_t)set * 36 + c * 6 + r] = s;
-    }
-    // (4) Z chain; Z_j is kept in the tile area (free now), Z_{nb-1} = Y_{nb}
-    double* sZall = sTile;
-    for (int j = nb - 1; j >= 0; --j) {
-      const double* zp = sZall + 36 * (j + 1);
-      for (int o = lane; o < 36; o += 32) {
-        const int r = o / 6, c = o - 6 * r;
-        double s = sY[(j + 1) * 36 + o];
-        if (j + 1 < nb) {
-#pragma unroll
-          for (int a = 0; a < 6; ++a) s += sBt[(j + 1) * 36 + a * 6 + r] * zp[a * 6 + c];
+    for (int k = C - 1; k >= 0; --k) {
+      const double a00 = g00a, a01 = g00b, a10 = g01a, a11 = g01b;
+      if (k > 0) {  // next camera's tiles: in flight during this camera's products
+        const int view = __shfl_sync(0xffffffffu, my_view, k - 1);
+        g00a = g00b = g01a = g01b = 0.0;
+        if (view >= 0) {
+          const double* t = p.VB + (size_t)view * VB_STRIDE;
+          g00a = t[arow * 8 + acol]; g00b = t[arow * 8 + 4 + acol];
+          g01a = t[64 + acol * 8 + arow]; g01b = t[64 + (4 + acol) * 8 + arow];
         }
-        sZall[36 * j + o] = s;
       }
-      __syncwarp();
+      const int PD = p.cam_P[k] + p.cam_D[k];
+      // M = Pi_k P_v
+      const double* Pi = p.camPi + k * 36;
+      double m0 = 0.0, m1 = 0.0;
+      dmma(m0, m1, in0 ? __ldg(Pi + d0) : 0.0, pb0);
+      dmma(m0, m1, in1 ? __ldg(Pi + d1) : 0.0, pb1);
+      const double mb0 = c_to_b(m0, m1, 0, arow, acol), mb1 = c_to_b(m0, m1, 1, arow, acol);  // B fragments of M = A fragments of M^T
+      double r00 = 0.0, r01 = 0.0, r10 = 0.0, r11 = 0.0;
+      dmma(r00, r01, a00, mb0);
+      dmma(r10, r11, a10, mb0);
+      dmma(r00, r01, a01, mb1);
+      dmma(r10, r11, a11, mb1);
+      // W rows of the intrinsics of camera k (columns 0..5 of R: acol < 3)
+      if (acol < 3) {
+        double* w = Wout + (size_t)p.intr_off[k] * 6 + 2 * acol;
+        if (arow >= 6 && arow - 6 < PD) *reinterpret_cast<double2*>(w + (arow - 6) * 6) = make_double2(r00, r01);
+        if (arow < 7 && arow + 2 < PD) *reinterpret_cast<double2*>(w + (arow + 2) * 6) = make_double2(r10, r11);
+      }
+      bs0 += r10;
+      bs1 += r11;
+      // Y_k = rows 0..5 of R0
+      const double y0 = in0 ? r00 : 0.0, y1 = in0 ? r01 : 0.0;
+      const double yb0 = c_to_b(y0, y1, 0, arow, acol), yb1 = c_to_b(y0, y1, 1, arow, acol);
+      dmma(v0, v1, mb0, yb0);
+      dmma(v0, v1, mb1, yb1);
+      if (k >= 1) {  // baseline j = k - 1
+        const int j = k - 1;
+        double n0 = y0, n1 = y1;
+        if (k < C - 1) {  // Z_j = Y_k + boxTimes(B_k)^T Z_k
+          const double* Bt = p.baseBt + k * 36;
+          dmma(n0, n1, in0 ? __ldg(Bt + t0) : 0.0, zb0);
+          dmma(n0, n1, in1 ? __ldg(Bt + t1) : 0.0, zb1);
+        }
+        z0 = n0;
+        z1 = n1;
+        zb0 = c_to_b(z0, z1, 0, arow, acol);
+        zb1 = c_to_b(z0, z1, 1, arow, acol);
+        const double* Mj = p.baseM + j * 36;
+        double w0 = 0.0, w1 = 0.0;  // W_base(j) = M_j^T Z_j
+        dmma(w0, w1, in0 ? __ldg(Mj + t0) : 0.0, zb0);
+        dmma(w0, w1, in1 ? __ldg(Mj + t1) : 0.0, zb1);
+        if (in0 && acol < 3) *reinterpret_cast<double2*>(Wout + ((size_t)p.base_off[j] + arow) * 6 + 2 * acol) = make_double2(w0, w1);
+      }
     }
-    for (int q = lane; q < 36 * nb; q += 32) {  // W_base(j) = M_j^T Z_j
-      const int j = q / 36, o = q - 36 * j, r = o / 6, c = o - 6 * r;
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) s += sMj[j * 36 + a * 6 + r] * sZall[36 * j + a * 6 + c];
-      Wout[(size_t)6 * n_intr + q] = s;
-    }
-    __syncwarp();
+    if (in0 && acol < 3) *reinterpret_cast<double2*>(p.V + (size_t)set * 36 + arow * 6 + 2 * acol) = make_double2(v0, v1);
+    if (arow == 7 && acol < 3) *reinterpret_cast<double2*>(p.bv + (size_t)set * 6 + 2 * acol) = make_double2(-bs0, -bs1);
   }
 }
 
@@ -1508,18 +1499,9 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
 
 // V_v, b_v, W_v from the view blocks; U, b_c from the per-camera Gram sums
 cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s) {
-  const int n_intr = p.n_cams > 1 ? p.base_off[0] : p.n_c;
-  const size_t smem = sizeof(double) * (72 * (size_t)(p.n_cams - 1) + 36 * (size_t)p.n_cams + (((n_intr + 3) >> 2) << 1) + SR_WARPS * (size_t)sr_warp_doubles(p.n_cams));
   if (p.n_sets > 0) {
-    static size_t attr_smem = 0;
-    if (smem > attr_smem && smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(set_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_smem = smem;
-    }
-    const int ctas_per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem + 1024)));
-    const int grid = min((p.n_sets + SR_WARPS - 1) / SR_WARPS, sm_count() * ctas_per_sm);
-    set_reduce_kernel<<<grid, SR_WARPS * 32, smem, s.stream>>>(p);
+    const int grid = min((p.n_sets + SR_WARPS - 1) / SR_WARPS, sm_count() * 8);
+    set_reduce_kernel<<<grid, SR_WARPS * 32, 0, s.stream>>>(p);
     KB_LAUNCHED(s);
   }
   const int n2 = p.n_aug * p.n_aug;
