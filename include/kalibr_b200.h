@@ -186,6 +186,10 @@ KB_API kb_status kb_get_baselines(kb_handle* h, double* baselines /*[n_cams-1][7
 KB_API kb_status kb_get_set_poses(kb_handle* h, double* set_poses /*[n_sets][7]; other ranks' sets untouched*/);
 /* replace the measurements (same structure) — used by the end-to-end bench leg to time host→device per step */
 KB_API kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v);
+/* kb_set_observations + kb_evaluate_error in one call, with the host->device copy of the measurements (pinned host memory
+ * for real overlap) pipelined against the evaluation: the terms travel in a few chunks and the kernel starts on each chunk
+ * as it lands.  Same results as the two separate calls up to the summation order of the cost. */
+KB_API kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const double* y_v, int32_t use_m_estimator, double* out_cost);
 /* terms whose projection bailed out before writing y_hat (zero-weighted here) since creation */
 KB_API int64_t kb_num_invalid_terms(kb_handle* h);
 /* reset state to the initial guess given at kb_create */

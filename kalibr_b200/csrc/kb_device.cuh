@@ -92,9 +92,9 @@ cudaError_t launch_prep(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int* model_begin, double* cost_out, StreamCtx& s);
 int la_grid_warps();
 cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta /*(view,set,begin,end) in view-list order*/, const int4* slices,
-                                      const int* slice_model_begin, bool write_e,
+                                      const int* slice_model_begin, bool write_e, bool with_set_prep,
                                       StreamCtx& s);
-cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, double* cost_out, StreamCtx& s);
+cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range /*[n_cams][n_ranges][2]*/, int n_ranges, double* cost_out, StreamCtx& s);
 cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta, const int4* slices, const int* slice_model_begin,
                                          const int* bfrag_pairs /*[NUM_MODELS]*/, unsigned int* counters /*[NUM_MODELS], device*/, double* jt_values,

@@ -76,6 +76,8 @@ struct DevBuf {
 };
 }  // namespace
 
+constexpr int KB_STREAM_CHUNKS = 4;
+
 struct kb_handle {
   std::string error;
   int device = 0;
@@ -103,6 +105,14 @@ struct kb_handle {
   DevBuf<int4> slices, vmeta;
   DevBuf<int> cam_slice_range;
   int slice_model_begin[KB_NUM_MODELS + 1] = {};
+  // second slice table for the streamed evaluate: the views are cut into KB_STREAM_CHUNKS contiguous term ranges, slices are
+  // chunk-major and never cross a chunk, so the fused kernel can start on a chunk as soon as its observations have landed
+  DevBuf<int4> st_slices;
+  DevBuf<int> st_cam_slice_range;                       // [n_cams][KB_STREAM_CHUNKS][2]
+  int st_chunk_model_begin[KB_STREAM_CHUNKS][KB_NUM_MODELS + 1] = {};
+  int64_t st_chunk_term[KB_STREAM_CHUNKS + 1] = {};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_chunk[KB_STREAM_CHUNKS] = {}, ev_main = nullptr;
   DevBuf<unsigned int> n_invalid, lm_counters;
   DevBuf<int> col_desc;
   int lm_bfrag_pairs[KB_NUM_MODELS] = {};
@@ -252,6 +262,9 @@ void kb_destroy(kb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) g_nccl.CommDestroy(h->comm);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_chunk) if (e) cudaEventDestroy(e);
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_posdef) cudaFreeHost(h->h_posdef);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -463,6 +476,41 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     }
     h->slice_model_begin[KB_NUM_MODELS] = (int)slices.size();
   }
+  // streamed table: chunk c = local views [cv[c], cv[c+1]) = terms [st_chunk_term[c], st_chunk_term[c+1])
+  std::vector<int4> st_slices;
+  std::vector<int> st_cam_slice_range((size_t)d->n_cams * KB_STREAM_CHUNKS * 2, 0);
+  {
+    int cv[KB_STREAM_CHUNKS + 1];
+    for (int c = 0; c <= KB_STREAM_CHUNKS; ++c) {
+      cv[c] = (int)((long long)n_views * c / KB_STREAM_CHUNKS);
+      h->st_chunk_term[c] = vb[cv[c]];
+    }
+    // position of every camera's first view in the model/camera-sorted list
+    std::vector<int> cam_pos(d->n_cams, 0);
+    {
+      int pos = 0;
+      for (int m = 0; m < KB_NUM_MODELS; ++m)
+        for (int k = 0; k < d->n_cams; ++k)
+          if (d->cam_model[k] == m) { cam_pos[k] = pos; pos += cam_view_begin[k + 1] - cam_view_begin[k]; }
+    }
+    for (int c = 0; c < KB_STREAM_CHUNKS; ++c) {
+      const int per = std::max(1, (cv[c + 1] - cv[c] + la_grid_warps() - 1) / la_grid_warps());
+      for (int m = 0; m < KB_NUM_MODELS; ++m) {
+        h->st_chunk_model_begin[c][m] = (int)st_slices.size();
+        for (int k = 0; k < d->n_cams; ++k) {
+          if (d->cam_model[k] != m) continue;
+          // views of camera k inside the chunk: a contiguous run of its (ascending) view list
+          const int* lst = cam_view_list.data() + cam_view_begin[k];
+          const int nk = cam_view_begin[k + 1] - cam_view_begin[k];
+          const int lo = (int)(std::lower_bound(lst, lst + nk, cv[c]) - lst), hi = (int)(std::lower_bound(lst, lst + nk, cv[c + 1]) - lst);
+          st_cam_slice_range[((size_t)k * KB_STREAM_CHUNKS + c) * 2] = (int)st_slices.size();
+          for (int a = lo; a < hi; a += per) st_slices.push_back(make_int4(cam_pos[k] + a, cam_pos[k] + std::min(hi, a + per), k, 0));
+          st_cam_slice_range[((size_t)k * KB_STREAM_CHUNKS + c) * 2 + 1] = (int)st_slices.size();
+        }
+      }
+      h->st_chunk_model_begin[c][KB_NUM_MODELS] = (int)st_slices.size();
+    }
+  }
 
   // ---- upload ----
   cudaStream_t s = h->stream;
@@ -498,6 +546,11 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     KB_CCUDA(h->vmeta.upload(vmeta, s));
   }
   KB_CCUDA(h->cam_slice_range.upload(cam_slice_range, s));
+  KB_CCUDA(h->st_slices.upload(st_slices, s));
+  KB_CCUDA(h->st_cam_slice_range.upload(st_cam_slice_range, s));
+  KB_CCUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev_chunk) KB_CCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
   KB_CCUDA(h->set_col_q.upload(set_col_q, s));
   KB_CCUDA(h->set_col_t.upload(set_col_t, s));
   KB_CCUDA(h->cam_cols.upload(h->h_cam_cols, s));
@@ -520,7 +573,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->view_cost.alloc(n_views));
   KB_CCUDA(h->set_prep.alloc(S * SETPREP_STRIDE));
   KB_CCUDA(h->VB.alloc((size_t)n_views * VB_STRIDE));
-  KB_CCUDA(h->gram_partial.alloc(slices.size() * GRAM_TILES));
+  KB_CCUDA(h->gram_partial.alloc(std::max(slices.size(), st_slices.size()) * GRAM_TILES));
   KB_CCUDA(h->sumG.alloc(C * GRAM_SIZE));
   KB_CCUDA(h->V.alloc(S * 36));
   KB_CCUDA(h->bv.alloc(S * 6));
@@ -602,10 +655,18 @@ static kb_status run_linearise_assemble(kb_handle* h, bool write_e, int cost_slo
   KB_CUDA(h, launch_prep(h->d, c));
   {
     StageTimer t(h, 1);
-    KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->slices.p, h->slice_model_begin, write_e, c));
+    KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->slices.p, h->slice_model_begin, write_e, true, c));
   }
-  KB_CUDA(h, launch_finalize_gram(h->d, h->cam_slice_range.p, h->scalars.p + cost_slot, c));
+  KB_CUDA(h, launch_finalize_gram(h->d, h->cam_slice_range.p, 1, h->scalars.p + cost_slot, c));
   h->la_version = h->state_version;
+  return KB_OK;
+}
+
+static kb_status finish_evaluate(kb_handle* h, double* out_cost) {
+  KB_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  collect_stages(h);
+  if (out_cost) *out_cost = h->h_scalars[0];
   return KB_OK;
 }
 
@@ -626,11 +687,46 @@ kb_status kb_evaluate_error(kb_handle* h, int32_t /*use_m_estimator: kalibr2 ins
     kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
     if (st != KB_OK) return st;
   }
-  KB_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  KB_CUDA(h, cudaStreamSynchronize(h->stream));
-  collect_stages(h);
-  if (out_cost) *out_cost = h->h_scalars[0];
-  return KB_OK;
+  return finish_evaluate(h, out_cost);
+}
+
+// kb_set_observations + kb_evaluate_error with the upload overlapped: the observations travel in KB_STREAM_CHUNKS pieces on a
+// copy stream and the fused kernel starts on each piece as soon as it has landed.
+kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const double* y_v, int32_t use_m_estimator, double* out_cost) {
+  if (h->n_ranks != 1 && !h->presharded)
+    return fail(h, KB_ERR_STATE, "kb_evaluate_error_streamed needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
+  if (!y_u || !y_v) return fail(h, KB_ERR_INVALID_ARGUMENT, "null observation array");
+  if (!h->speculative) {
+    kb_status st = kb_set_observations(h, y_u, y_v);
+    return st != KB_OK ? st : kb_evaluate_error(h, use_m_estimator, out_cost);
+  }
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  ++h->state_version;
+  // the copies may only overwrite the observations once everything queued so far has read them
+  KB_CUDA(h, cudaEventRecord(h->ev_main, h->stream));
+  KB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
+  for (int k = 0; k < KB_STREAM_CHUNKS; ++k) {
+    const int64_t lo = h->st_chunk_term[k], n = h->st_chunk_term[k + 1] - lo;
+    if (n > 0) {
+      KB_CUDA(h, cudaMemcpyAsync(h->y_u.p + lo, y_u + lo, sizeof(double) * n, cudaMemcpyHostToDevice, h->copy_stream));
+      KB_CUDA(h, cudaMemcpyAsync(h->y_v.p + lo, y_v + lo, sizeof(double) * n, cudaMemcpyHostToDevice, h->copy_stream));
+    }
+    KB_CUDA(h, cudaEventRecord(h->ev_chunk[k], h->copy_stream));
+  }
+  {
+    StageTimer t(h, 0);
+    KB_CUDA(h, launch_prep(h->d, c));
+    for (int k = 0; k < KB_STREAM_CHUNKS; ++k) {
+      KB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[k], 0));
+      KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->st_slices.p, h->st_chunk_model_begin[k], true, k == 0, c));
+    }
+    KB_CUDA(h, launch_finalize_gram(h->d, h->st_cam_slice_range.p, KB_STREAM_CHUNKS, h->scalars.p, c));
+    h->la_version = h->state_version;
+    kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
+    if (st != KB_OK) return st;
+  }
+  return finish_evaluate(h, out_cost);
 }
 
 kb_status kb_build_system(kb_handle* h, int32_t /*use_m_estimator*/) {

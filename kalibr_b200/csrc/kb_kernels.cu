@@ -816,15 +816,18 @@ __global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p)
 
 // ---- per-camera Gram sums from the slice partials (fixed order) -------------------------------------------------
 constexpr int FG_GROUPS = 5;
-__global__ void __launch_bounds__(GRAM_TILES * FG_GROUPS) finalize_gram_kernel(DevProblem p, const int* __restrict__ cam_slice_range /*[n_cams][2]*/) {
+// cam_slice_range: [n_cams][n_ranges][2] slice ranges of camera k (one per chunk of the streamed slice table)
+__global__ void __launch_bounds__(GRAM_TILES * FG_GROUPS) finalize_gram_kernel(DevProblem p, const int* __restrict__ cam_slice_range, int n_ranges) {
   __shared__ double sh[FG_GROUPS][GRAM_TILES];
   const int k = blockIdx.x, t = threadIdx.x % GRAM_TILES, g = threadIdx.x / GRAM_TILES;
-  const int lo = cam_slice_range[2 * k], hi = cam_slice_range[2 * k + 1];
-  const int per = (hi - lo + FG_GROUPS - 1) / FG_GROUPS;
-  const int a = lo + g * per, b = min(hi, a + per);
   double s = 0.0;
+  for (int r = 0; r < n_ranges; ++r) {
+    const int lo = cam_slice_range[(k * n_ranges + r) * 2], hi = cam_slice_range[(k * n_ranges + r) * 2 + 1];
+    const int per = (hi - lo + FG_GROUPS - 1) / FG_GROUPS;
+    const int a = lo + g * per, b = min(hi, a + per);
 #pragma unroll 8
-  for (int sl = a; sl < b; ++sl) s += p.gram_partial[(size_t)sl * GRAM_TILES + t];
+    for (int sl = a; sl < b; ++sl) s += p.gram_partial[(size_t)sl * GRAM_TILES + t];
+  }
   sh[g][t] = s;
   __syncthreads();
   if (g != 0) return;
@@ -1439,9 +1442,10 @@ static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const
 }
 
 // slice_model_begin[m] .. [m+1]: slices of camera model m
-cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, const int4* slices, const int* smb, bool write_e, StreamCtx& s) {
+cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, const int4* slices, const int* smb, bool write_e, bool with_set_prep,
+                                      StreamCtx& s) {
   cudaError_t e;
-  if (p.n_sets > 0) {
+  if (with_set_prep && p.n_sets > 0) {
     set_prep_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p);
     KB_LAUNCHED(s);
   }
@@ -1454,8 +1458,8 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, co
 }
 
 // per-camera Gram sums + cost of the linearisation point (-> cost_out[0])
-cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, double* cost_out, StreamCtx& s) {
-  finalize_gram_kernel<<<p.n_cams, GRAM_TILES * FG_GROUPS, 0, s.stream>>>(p, cam_slice_range);
+cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, int n_ranges, double* cost_out, StreamCtx& s) {
+  finalize_gram_kernel<<<p.n_cams, GRAM_TILES * FG_GROUPS, 0, s.stream>>>(p, cam_slice_range, n_ranges);
   KB_LAUNCHED(s);
   gram_cost_kernel<<<1, 32, 0, s.stream>>>(p, cost_out);
   KB_LAUNCHED(s);

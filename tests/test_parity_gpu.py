@@ -194,3 +194,37 @@ def test_rejected_step_keeps_the_built_system(capi, oracle_lib):
     assert gok == ook
     assert rel_err(gdx, odx) < 1e-7
     assert rel_err(g.rhs(), o.rhs()) < 1e-9
+
+
+@pytest.mark.parametrize("cfg,n_sets", [(1, 40), (3, 24), (4, 37)])
+def test_streamed_evaluate_matches_separate_upload_and_oracle(capi, oracle_lib, cfg, n_sets):
+    """kb_evaluate_error_streamed (chunked upload overlapped with the fused kernel, second slice table) == kb_set_observations +
+    kb_evaluate_error, and the system built from it matches the oracle on the new observations."""
+    p = make(cfg, n_sets)
+    rng = np.random.default_rng(5)
+    yu = np.ascontiguousarray(p.y_u + rng.normal(0.0, 0.2, p.y_u.shape))
+    yv = np.ascontiguousarray(p.y_v + rng.normal(0.0, 0.2, p.y_v.shape))
+    a = capi.B200SchurLinearSystemSolver(p)
+    b = capi.B200SchurLinearSystemSolver(p)
+    a.evaluate_error()  # something queued before the streamed call (write-after-read ordering of the observation buffers)
+    Ja = a.evaluate_error_streamed(yu, yv)
+    b.set_observations(yu, yv)
+    Jb = b.evaluate_error()
+    assert abs(Ja - Jb) <= 1e-13 * Jb
+    assert np.array_equal(a.error_vector(), b.error_vector())
+    p2 = make(cfg, n_sets)
+    p2.y_u[:] = yu
+    p2.y_v[:] = yv
+    o = oracle_lib.OracleProblem(p2)
+    Jo = o.evaluate_error()
+    assert abs(Ja - Jo) <= 1e-10 * Jo
+    for s in (a, b, o):
+        s.build_system()
+        s.set_constant_conditioner(10.0)
+    dxa, oka = a.solve_system()
+    dxb, okb = b.solve_system()
+    dxo, oko = o.solve_system()
+    assert oka and okb and oko
+    assert rel_err(dxa, dxb) < 1e-11
+    assert rel_err(dxa, dxo) < 1e-7
+    assert rel_err(a.rhs(), o.rhs()) < 1e-9
