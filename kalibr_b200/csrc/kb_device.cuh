@@ -105,6 +105,7 @@ cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_d
 cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int* cam_cols,
                                    int include_shared, double* out2 /* [0]=sum, [1]=max|dx| */, StreamCtx& s);
+cudaError_t launch_pack_rank_scalars(double* pk /*[n_ranks][4], device*/, int rank, int n_ranks, const double* rho_max, const int* pos_def, StreamCtx& s);
 cudaError_t launch_apply_update(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, double* backup_cam,
                                 double* backup_base, double* backup_sets, StreamCtx& s);
 int schur_num_partials(const DevProblem& p);

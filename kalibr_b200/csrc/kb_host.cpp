@@ -118,7 +118,8 @@ struct kb_handle {
   int lm_bfrag_pairs[KB_NUM_MODELS] = {};
   int model_begin[KB_NUM_MODELS + 1] = {};
   int n_partials = 0;
-  double* h_scalars = nullptr;  // pinned [8]
+  double* h_scalars = nullptr;  // pinned [8 + 4 * MAX_CAMS]: scalars, then the per-rank slots of the packed all-reduce
+  DevBuf<double> rank_slots;    // [n_ranks][4]
   int* h_posdef = nullptr;      // pinned
   // ---- solver state ----
   double lambda = 0.0;          // _diagonalConditioner (constant)
@@ -319,7 +320,8 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     if (_e != cudaSuccess) return cfail(KB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));     \
   } while (0)
   KB_CCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  KB_CCUDA(cudaMallocHost((void**)&h->h_scalars, sizeof(double) * 8));
+  if (d->n_ranks > MAX_CAMS) return cfail(KB_ERR_INVALID_ARGUMENT, "more than 32 ranks");
+  KB_CCUDA(cudaMallocHost((void**)&h->h_scalars, sizeof(double) * (8 + 4 * MAX_CAMS)));
   KB_CCUDA(cudaMallocHost((void**)&h->h_posdef, sizeof(int) * 2));
   for (auto& e : h->ev) KB_CCUDA(cudaEventCreate(&e));
 
@@ -585,6 +587,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->dxc.alloc(D.n_c));
   KB_CCUDA(h->dx.alloc((size_t)h->jcols));
   KB_CCUDA(h->scalars.alloc(8));
+  KB_CCUDA(h->rank_slots.alloc(4 * (size_t)d->n_ranks));
   KB_CCUDA(h->posdef.alloc(2));
   KB_CCUDA(h->n_invalid.alloc(1));
   KB_CCUDA(h->lm_counters.alloc(KB_NUM_MODELS));
@@ -782,10 +785,12 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
   {
     // dx^T (lambda dx + rhs) and max|dx| of this solution, so that getLmRho / applyStateUpdate need no further launch
     KB_CUDA(h, launch_rho_denominator(h->d, h->lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2, c));
-    kb_status st = nccl_allreduce(h, h->posdef.p, 1, kNcclInt32, kNcclMin);
-    if (st != KB_OK) return st;
-    if ((st = nccl_allreduce(h, h->scalars.p + 2, 1, kNcclFloat64, kNcclSum)) != KB_OK) return st;
-    if ((st = nccl_allreduce(h, h->scalars.p + 3, 1, kNcclFloat64, kNcclMax)) != KB_OK) return st;
+    if (h->n_ranks > 1) {  // one packed all-reduce instead of three (min / sum / max)
+      KB_CUDA(h, launch_pack_rank_scalars(h->rank_slots.p, h->rank, h->n_ranks, h->scalars.p + 2, h->posdef.p, c));
+      kb_status st = nccl_allreduce(h, h->rank_slots.p, 4 * (size_t)h->n_ranks, kNcclFloat64, kNcclSum);
+      if (st != KB_OK) return st;
+      KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 8, h->rank_slots.p, 4 * sizeof(double) * h->n_ranks, cudaMemcpyDeviceToHost, h->stream));
+    }
   }
   KB_CUDA(h, cudaMemcpyAsync(h->h_posdef, h->posdef.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 2, h->scalars.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -815,6 +820,18 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
   }
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   collect_stages(h);
+  if (h->n_ranks > 1) {  // combine the ranks' slots in rank order: identical on every rank
+    double rho = 0.0, mx = 0.0;
+    int pd = 1;
+    for (int r = 0; r < h->n_ranks; ++r) {
+      rho += h->h_scalars[8 + 4 * r];
+      mx = std::max(mx, h->h_scalars[8 + 4 * r + 1]);
+      if (h->h_scalars[8 + 4 * r + 2] < 0.5) pd = 0;
+    }
+    h->h_scalars[2] = rho;
+    h->h_scalars[3] = mx;
+    h->h_posdef[0] = pd;
+  }
   // un-augment: BlockCholesky subtracts lambda, not lambda^2 (BlockCholeskyLinearSystemSolver.cpp:91-97)
   if (h->semantic == 0) h->diag_residual += h->lambda * h->lambda - h->lambda;
   h->solved = true;

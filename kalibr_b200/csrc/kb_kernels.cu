@@ -958,13 +958,17 @@ constexpr int SC_SETS = 4;              // sets per step: K = 24 = 6 k-steps of 
 constexpr int SC_K = SC_SETS * 6;
 constexpr int SC_LD = 36;               // ld % 16 == 4 keeps the operand loads conflict-free
 
+// Per step of SC_SETS sets: the raw rows [W_v ; b_v^T] and the inverse factors L_v^-1 of the NEXT step travel with cp.async
+// straight into the other Z buffer while the DMMA phase runs on the current one; afterwards every thread turns the rows it
+// copied into Z rows in place (z = L^-1 w, a 6x6 triangular product).
 template <int WARPS, int MAX_PAIRS>
 __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, double* __restrict__ partials, int sets_per_cta) {
   extern __shared__ __align__(16) double smem[];
   const int n = p.n_aug;
   const int nt = (n + 7) >> 3;
   const int n_pad = nt * 8;
-  double* Zbuf = smem;  // [2][n_pad][SC_LD]
+  double* Zbuf = smem;                         // [2][n_pad][SC_LD]
+  double* sLi = smem + 2 * n_pad * SC_LD;      // [2][SC_SETS][36]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int arow = lane >> 2, acol = lane & 3;
   const int npairs = nt * (nt + 1) / 2;
@@ -989,41 +993,71 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
   }
   for (int i = tid; i < 2 * n_pad * SC_LD; i += blockDim.x) Zbuf[i] = 0.0;
   const int s_lo = blockIdx.x * sets_per_cta, s_hi = min(p.n_sets, s_lo + sets_per_cta);
-  // rows of Z for the sets [s0, s0 + SC_SETS): z = Linv * w (lower triangular 6x6 product)
-  auto fill = [&](double* Zs, int s0) {
+  __syncthreads();
+  // raw rows of the sets [s0, s0 + SC_SETS) -> Zs, their inverse factors -> Ls  (asynchronous; rows of sets past the end are zeroed)
+  auto fetch = [&](double* Zs, double* Ls, int s0) {
     for (int o = tid; o < SC_SETS * n; o += blockDim.x) {
-      const int which = o / n, r = o % n;
+      const int which = o / n, r = o - which * n;
       const int set = s0 + which;
-      double z[6] = {0, 0, 0, 0, 0, 0};
+      double* dst = Zs + r * SC_LD + which * 6;
       if (set < s_hi) {
         const double* src = (r < p.n_c) ? (p.W + ((size_t)set * p.n_c + r) * 6) : (p.bv + (size_t)set * 6);
-        const double* Li = p.Lv + (size_t)set * 36;
-        double w[6];
+        cp_async_16(dst, src);
+        cp_async_16(dst + 2, src + 2);
+        cp_async_16(dst + 4, src + 4);
+      } else {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) w[c] = src[c];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          double s = 0.0;
-#pragma unroll
-          for (int k = 0; k <= i; ++k) s += __ldg(Li + i * 6 + k) * w[k];
-          z[i] = s;
-        }
-        if (r == p.n_c && blockIdx.y == 0) {
-#pragma unroll
-          for (int c = 0; c < 6; ++c) p.yv[(size_t)set * 6 + c] = z[c];
-        }
+        for (int c = 0; c < 6; ++c) dst[c] = 0.0;
       }
+    }
+    for (int o = tid; o < SC_SETS * 18; o += blockDim.x) {
+      const int which = o / 18, q = o - which * 18;
+      if (s0 + which < s_hi) cp_async_16(Ls + which * 36 + 2 * q, p.Lv + (size_t)(s0 + which) * 36 + 2 * q);
+    }
+    cp_async_commit();
+  };
+  // in place: z = Linv * w for the rows this thread fetched (same index mapping as fetch)
+  auto transform = [&](double* Zs, const double* Ls, int s0) {
+    for (int o = tid; o < SC_SETS * n; o += blockDim.x) {
+      const int which = o / n, r = o - which * n;
+      const int set = s0 + which;
+      if (set >= s_hi) continue;
+      double* zr = Zs + r * SC_LD + which * 6;
+      const double* Li = Ls + which * 36;
+      double w[6], z[6];
+      *reinterpret_cast<double2*>(w) = *reinterpret_cast<const double2*>(zr);
+      *reinterpret_cast<double2*>(w + 2) = *reinterpret_cast<const double2*>(zr + 2);
+      *reinterpret_cast<double2*>(w + 4) = *reinterpret_cast<const double2*>(zr + 4);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) Zs[r * SC_LD + which * 6 + c] = z[c];
+      for (int i = 0; i < 6; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; ++k) t += Li[i * 6 + k] * w[k];
+        z[i] = t;
+      }
+      *reinterpret_cast<double2*>(zr) = make_double2(z[0], z[1]);
+      *reinterpret_cast<double2*>(zr + 2) = make_double2(z[2], z[3]);
+      *reinterpret_cast<double2*>(zr + 4) = make_double2(z[4], z[5]);
+      if (r == p.n_c && blockIdx.y == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) p.yv[(size_t)set * 6 + c] = z[c];
+      }
     }
   };
-  __syncthreads();
-  if (s_lo < s_hi) fill(Zbuf, s_lo);
+  if (s_lo < s_hi) {
+    fetch(Zbuf, sLi, s_lo);
+    cp_async_wait_all();
+    __syncthreads();
+    transform(Zbuf, sLi, s_lo);
+  }
   __syncthreads();
   int buf = 0;
   for (int s0 = s_lo; s0 < s_hi; s0 += SC_SETS) {
     const double* Zs = Zbuf + (size_t)buf * n_pad * SC_LD;
-    if (s0 + SC_SETS < s_hi) fill(Zbuf + (size_t)(buf ^ 1) * n_pad * SC_LD, s0 + SC_SETS);  // overlaps the DMMA phase below
+    double* Zn = Zbuf + (size_t)(buf ^ 1) * n_pad * SC_LD;
+    double* Ln = sLi + (buf ^ 1) * SC_SETS * 36;
+    const bool more = s0 + SC_SETS < s_hi;
+    if (more) fetch(Zn, Ln, s0 + SC_SETS);  // in flight during the DMMA phase below
 #pragma unroll
     for (int kk = 0; kk < SC_K / 4; ++kk) {
 #pragma unroll
@@ -1034,6 +1068,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
           dmma(acc[q][0], acc[q][1], a, b);
         }
       }
+    }
+    if (more) {
+      cp_async_wait_all();
+      __syncthreads();  // every thread's copies (the L factors are shared) have landed
+      transform(Zn, Ln, s0 + SC_SETS);
     }
     __syncthreads();
     buf ^= 1;
@@ -1052,17 +1091,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
 __global__ void __launch_bounds__(256) schur_finalize_kernel(DevProblem p, const double* __restrict__ partials, int n_partials) {
   const int n = p.n_aug;
   const int n_pad = ((n + 7) >> 3) * 8;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * n) return;
-  const int i = idx / n, j = idx % n;
-  if (i > j) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = t >> 2, seg = t & 3;  // four lanes per element, each a quarter of the partials; combined in a fixed order
+  const int i = idx / n, j = idx - i * n;
+  const bool live = idx < n * n && i <= j;
   // within a diagonal tile only the mma's own (i,j) entry is used for i<=j, so the result is exactly symmetric
   double s = 0.0;
+  if (live) {
+    const int per = (n_partials + 3) >> 2;
+    const int c0 = seg * per, c1 = min(n_partials, c0 + per);
+    const double* src = partials + (size_t)i * n_pad + j;
 #pragma unroll 8
-  for (int c = 0; c < n_partials; ++c) s += partials[(size_t)c * n_pad * n_pad + (size_t)i * n_pad + j];
-  const double v = p.U[(size_t)i * n + j] - s;
-  p.Sred[(size_t)i * n + j] = v;
-  p.Sred[(size_t)j * n + i] = v;
+    for (int c = c0; c < c1; ++c) s += src[(size_t)c * n_pad * n_pad];
+  }
+  s += __shfl_down_sync(0xffffffffu, s, 2);
+  s += __shfl_down_sync(0xffffffffu, s, 1);
+  if (live && seg == 0) {
+    const double v = p.U[(size_t)i * n + j] - s;
+    p.Sred[(size_t)i * n + j] = v;
+    p.Sred[(size_t)j * n + i] = v;
+  }
 }
 
 // =========================================================================================================
@@ -1331,6 +1379,16 @@ __global__ void __launch_bounds__(RHO_BLOCKS) rho_stage2_kernel(const double* __
   if (threadIdx.x == 0) { out[0] = s; out[1] = m; }
 }
 
+// Multi-rank: every rank drops (rho partial, max|dx|, pos-def flag) into its own slot of a zeroed [n_ranks][4] array; ONE
+// sum all-reduce then hands every rank all slots, and the host combines them in rank order (sum / max / min).
+__global__ void pack_rank_scalars_kernel(double* __restrict__ pk, int rank, int n_ranks, const double* __restrict__ rho_max, const int* __restrict__ pos_def) {
+  const int i = threadIdx.x;
+  if (i >= 4 * n_ranks) return;
+  double v = 0.0;
+  if ((i >> 2) == rank) v = (i & 3) == 0 ? rho_max[0] : (i & 3) == 1 ? rho_max[1] : (i & 3) == 2 ? (double)pos_def[0] : 0.0;
+  pk[i] = v;
+}
+
 // sm::kinematics::updateQuat (quaternion_algebra.cpp:200-219, 302-317)
 __device__ __forceinline__ void update_quat(double* q, const double* dq) {
   const double theta = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2]);
@@ -1533,7 +1591,7 @@ size_t schur_partial_stride(const DevProblem& p) {
 template <int WARPS, int MAX_PAIRS>
 static cudaError_t launch_schur_t(const DevProblem& p, double* partials, int n_partials, StreamCtx& s) {
   const int n_pad = ((p.n_aug + 7) >> 3) * 8;
-  const size_t smem = sizeof(double) * (2 * (size_t)n_pad * SC_LD);
+  const size_t smem = sizeof(double) * (2 * (size_t)n_pad * SC_LD + 2 * SC_SETS * 36);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(schur_kernel<WARPS, MAX_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1549,8 +1607,7 @@ static cudaError_t launch_schur_t(const DevProblem& p, double* partials, int n_p
 }
 
 cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* flag, StreamCtx& s) {
-  cudaError_t e = cudaMemsetAsync(partials, 0, sizeof(double) * schur_partial_stride(p) * n_partials, s.stream);
-  if (e != cudaSuccess) return e;
+  // every CTA writes all of its tile pairs (zeros when it has no sets), so the partials need no clearing
   if (p.n_sets > 0) {
     pose_factor_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p, damping, flag);
     KB_LAUNCHED(s);
@@ -1562,7 +1619,7 @@ cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, 
 
 cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const double* partials, int n_partials, bool, StreamCtx& s) {
   const int n2 = p.n_aug * p.n_aug;
-  schur_finalize_kernel<<<(n2 + 255) / 256, 256, 0, s.stream>>>(p, partials, n_partials);
+  schur_finalize_kernel<<<(4 * n2 + 255) / 256, 256, 0, s.stream>>>(p, partials, n_partials);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -1599,6 +1656,12 @@ cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int
   rho_stage1_kernel<<<blocks, 256, 0, s.stream>>>(p, lambda, set_col_q, set_col_t, include_shared, partial);
   KB_LAUNCHED(s);
   rho_stage2_kernel<<<1, RHO_BLOCKS, 0, s.stream>>>(partial, blocks, out2);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_rank_scalars(double* pk, int rank, int n_ranks, const double* rho_max, const int* pos_def, StreamCtx& s) {
+  pack_rank_scalars_kernel<<<1, 128, 0, s.stream>>>(pk, rank, n_ranks, rho_max, pos_def);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
