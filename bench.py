@@ -32,7 +32,8 @@ UNIT = "terms/s"
 # algorithmic work of the fused linearise+assemble kernel per term
 FLOP_PER_TERM = 750.0
 BYTES_IN_PER_TERM = 18.0        # y (16 B) + corner id (2 B)
-BYTES_OUT_PER_VIEW = 1536.0     # three 8x8 FP64 tiles of the per-view Gram block
+BYTES_E_PER_TERM = 16.0         # e() written by the evaluate-time launch of the fused kernel
+BYTES_OUT_PER_VIEW = 1024.0     # two 8x8 FP64 tiles of the per-view Gram block (pose x pose|intrinsics|e)
 BYTES_LINEARISE_PER_TERM = lambda W: 18.0 + 16.0 + 16.0 * W  # materialising linearise: ids+y in, e and J (2 x W) out
 
 
@@ -328,7 +329,7 @@ def main():
         la_ms = la_ms / max(la_calls, 1)
         n_views_rank = p.n_views
         flops = FLOP_PER_TERM * terms_rank
-        byts = BYTES_IN_PER_TERM * terms_rank + BYTES_OUT_PER_VIEW * n_views_rank
+        byts = (BYTES_IN_PER_TERM + BYTES_E_PER_TERM) * terms_rank + BYTES_OUT_PER_VIEW * n_views_rank
         traffic = (read_json(os.path.join(ROOT, "profiles", "r01_traffic.json")) or {}).get("linearise_assemble_dram_bytes_per_launch")
         roofline = {"kernel": "linearise_assemble_kernel<pinhole-radtan>", "bound": "tensor",
                     "achieved": flops / (la_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
