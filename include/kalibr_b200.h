@@ -147,6 +147,10 @@ typedef struct {
   int32_t max_iterations;     /* 200   */
   double lm_lambda_init;      /* 10.0  */
   int32_t verbose;
+  int32_t device_loop;        /* 1 (default): the whole LM loop runs on the device - trust-region logic in single-thread control
+                               * kernels, iterations enqueued ahead, the host only polls the "done" flag; 0: the host-side
+                               * Optimizer2 mirror drives the call-by-call entry points (two synchronisations per iteration).
+                               * Same iterations and results.  verbose = 1 or speculative linearisation off imply 0. */
 } kb_optimizer_options;
 typedef struct { /* ≙ SolutionReturnValue, BE/include/aslam/backend/backend.hpp:14-27 */
   double j_start, j_final, dx_final, dj_final;

@@ -24,6 +24,32 @@ constexpr int SETPREP_STRIDE = 48;                 // per set: C^-1 (9), -C^-1 t
 //   tile (0,0): G[0:8][0:8]  (pose x pose, pose x first two intrinsics)      tile (0,1): G[0:8][8:16]  (pose x remaining intrinsics, pose x e)
 constexpr int VB_STRIDE = 128;
 
+// Control block of the device-resident Levenberg-Marquardt loop (kb_optimize): the optimiser / trust-region state of
+// Optimizer2 + LevenbergMarquardtTrustRegionPolicy and the flags that make an enqueued kernel a no-op when the iteration it
+// belongs to does not need it.  In the call-by-call API (kb_evaluate_error, kb_build_system, ...) the flags stay neutral
+// (done = 0, need_build = 1, skip_eval = 0, revert = 0) and the scalar parameters travel as kernel arguments.
+struct LmCtrl {
+  // flags read by the kernels
+  int done;        // the loop has ended: everything still enqueued exits at once
+  int need_build;  // this iteration rebuilds the normal equations (first iteration, or the last step was accepted with rho > 0)
+  int skip_eval;   // the solve failed (not positive definite): no update, no evaluation this iteration
+  int revert;      // the step was a regression: restore the backup of the design variables
+  // parameters read by the kernels when their argument is negative
+  double damping;  // added to every diagonal entry of H for this solve (residual + lambda^2)
+  double lambda;
+  // results written by kernels
+  double cost_new;  // cost of the trial state
+  // Optimizer2 state (BE/src/Optimizer2.cpp:183-273)
+  double J, pJ, deltaX, deltaJ, JStart;
+  int iterations, failed, prev_failed, solver_failure;
+  // LevenbergMarquardtTrustRegionPolicy state (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:37-113)
+  double mu, gamma, beta, polJ, pol_pJ, pol_lastJ, rho_den, max_dx;
+  int p_exp, first;
+  // solver state / options
+  double diag_residual, conv_dx, conv_dj;
+  int semantic, max_iterations;
+};
+
 struct DevProblem {
   // ---- structure (immutable after kb_create) ----
   int n_cams;
@@ -78,6 +104,7 @@ struct DevProblem {
   double* dxc;          // [n_c]
   double* dx;           // [jcols] in design-variable order (poses of other ranks stay 0)
   unsigned int* n_invalid;  // terms whose projection bailed out (Q6)
+  LmCtrl* ctrl;             // control block (device)
 };
 
 constexpr int LIN_OFF_STRIDE = 4 + MAX_CAMS;  // pose_q, pose_t, proj, dist, baseline j (q; t = +3)
@@ -99,6 +126,7 @@ cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta, const int4* slices, const int* slice_model_begin,
                                          const int* bfrag_pairs /*[NUM_MODELS]*/, unsigned int* counters /*[NUM_MODELS], device*/, double* jt_values,
                                          StreamCtx& s);
+// damping / lambda arguments: a negative value means "read it from the control block" (device-resident loop)
 cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_schur_finalize(const DevProblem& p, double damping, const double* partials, int n_partials, bool add_camera_block, StreamCtx& s);
 cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s);
@@ -108,6 +136,12 @@ cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int
 cudaError_t launch_pack_rank_scalars(double* pk /*[n_ranks][4], device*/, int rank, int n_ranks, const double* rho_max, const int* pos_def, StreamCtx& s);
 cudaError_t launch_apply_update(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, double* backup_cam,
                                 double* backup_base, double* backup_sets, StreamCtx& s);
+// device-resident LM loop: single-thread control kernels and the conditional revert
+cudaError_t launch_lm_pre_solve(const DevProblem& p, int* pos_def_flag, StreamCtx& s);
+cudaError_t launch_lm_post_solve(const DevProblem& p, const int* pos_def_flag, const double* rho_max, const double* rank_slots, int n_ranks, StreamCtx& s);
+cudaError_t launch_lm_post_eval(const DevProblem& p, double* trace, StreamCtx& s);
+cudaError_t launch_lm_revert(const DevProblem& p, const double* backup_cam, const double* backup_base, const double* backup_sets, StreamCtx& s);
+cudaError_t launch_lm_finish(const DevProblem& p, StreamCtx& s);
 int schur_num_partials(const DevProblem& p);
 size_t schur_partial_stride(const DevProblem& p);
 

@@ -120,6 +120,13 @@ struct kb_handle {
   int n_partials = 0;
   double* h_scalars = nullptr;  // pinned [8 + 4 * MAX_CAMS]: scalars, then the per-rank slots of the packed all-reduce
   DevBuf<double> rank_slots;    // [n_ranks][4]
+  DevBuf<LmCtrl> ctrl;          // control block of the device-resident LM loop (neutral flags outside kb_optimize)
+  DevBuf<double> trace_dev;
+  LmCtrl* h_ctrl = nullptr;     // pinned
+  cudaGraphExec_t lm_graph = nullptr;  // one LM iteration, captured once per handle (single rank, stage timing off)
+  bool lm_warm = false;                // a plain-launched iteration has run (first-launch attribute / allocation calls are done)
+  const double* lm_graph_trace = nullptr;
+  long long lm_graph_kernels = 0;      // kernels one replay of the graph launches
   int* h_posdef = nullptr;      // pinned
   // ---- solver state ----
   double lambda = 0.0;          // _diagonalConditioner (constant)
@@ -268,6 +275,8 @@ void kb_destroy(kb_handle* h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_posdef) cudaFreeHost(h->h_posdef);
+  if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  if (h->lm_graph) cudaGraphExecDestroy(h->lm_graph);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -323,6 +332,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   if (d->n_ranks > MAX_CAMS) return cfail(KB_ERR_INVALID_ARGUMENT, "more than 32 ranks");
   KB_CCUDA(cudaMallocHost((void**)&h->h_scalars, sizeof(double) * (8 + 4 * MAX_CAMS)));
   KB_CCUDA(cudaMallocHost((void**)&h->h_posdef, sizeof(int) * 2));
+  KB_CCUDA(cudaMallocHost((void**)&h->h_ctrl, sizeof(LmCtrl)));
   for (auto& e : h->ev) KB_CCUDA(cudaEventCreate(&e));
 
   // ---- local views / terms ----
@@ -588,6 +598,14 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->dx.alloc((size_t)h->jcols));
   KB_CCUDA(h->scalars.alloc(8));
   KB_CCUDA(h->rank_slots.alloc(4 * (size_t)d->n_ranks));
+  KB_CCUDA(h->ctrl.alloc(1));
+  {
+    LmCtrl neutral;
+    std::memset(&neutral, 0, sizeof(neutral));
+    neutral.need_build = 1;
+    KB_CCUDA(cudaMemcpyAsync(h->ctrl.p, &neutral, sizeof(neutral), cudaMemcpyHostToDevice, s));  // pageable source: staged at the call
+  }
+  D.ctrl = h->ctrl.p;
   KB_CCUDA(h->posdef.alloc(2));
   KB_CCUDA(h->n_invalid.alloc(1));
   KB_CCUDA(h->lm_counters.alloc(KB_NUM_MODELS));
@@ -918,10 +936,150 @@ void kb_default_optimizer_options(kb_optimizer_options* o) {
   o->max_iterations = 200;
   o->lm_lambda_init = 10.0;
   o->verbose = 0;
+  o->device_loop = 1;
+}
+
+// One LM iteration, enqueued without any host decision: every kernel looks at the control block and is a no-op when the
+// iteration does not need it (no rebuild after a rejected step, no update after a failed solve, nothing once the loop is done).
+static kb_status enqueue_lm_iteration(kb_handle* h) {
+  StreamCtx c = ctx(h);
+  const DevProblem& D = h->d;
+  KB_CUDA(h, launch_lm_pre_solve(D, h->posdef.p, c));
+  {
+    StageTimer t(h, 2);
+    KB_CUDA(h, launch_set_reduce(D, c));
+  }
+  {
+    StageTimer t(h, 3);
+    KB_CUDA(h, launch_schur(D, -1.0, h->partials.p, h->n_partials, h->posdef.p, c));
+    KB_CUDA(h, launch_schur_finalize(D, -1.0, h->partials.p, h->n_partials, true, c));
+    kb_status st = nccl_allreduce(h, D.Sred, (size_t)D.n_aug * D.n_aug, kNcclFloat64, kNcclSum);
+    if (st != KB_OK) return st;
+  }
+  {
+    StageTimer t(h, 4);
+    KB_CUDA(h, launch_reduced_solve(D, -1.0, h->posdef.p, c));
+  }
+  {
+    StageTimer t(h, 5);
+    KB_CUDA(h, launch_backsub(D, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->posdef.p, c));
+  }
+  KB_CUDA(h, launch_rho_denominator(D, -1.0, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2, c));
+  if (h->n_ranks > 1) {
+    KB_CUDA(h, launch_pack_rank_scalars(h->rank_slots.p, h->rank, h->n_ranks, h->scalars.p + 2, h->posdef.p, c));
+    kb_status st = nccl_allreduce(h, h->rank_slots.p, 4 * (size_t)h->n_ranks, kNcclFloat64, kNcclSum);
+    if (st != KB_OK) return st;
+  }
+  KB_CUDA(h, launch_lm_post_solve(D, h->posdef.p, h->scalars.p + 2, h->rank_slots.p, h->n_ranks, c));
+  {
+    StageTimer t(h, 6);
+    KB_CUDA(h, launch_apply_update(D, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->bk_cam.p, h->bk_base.p, h->bk_sets.p, c));
+  }
+  {
+    StageTimer t(h, 0);
+    KB_CUDA(h, launch_prep(D, c));
+    {
+      StageTimer t1(h, 1);
+      KB_CUDA(h, launch_linearise_assemble(D, h->vmeta.p, h->slices.p, h->slice_model_begin, true, true, c));
+    }
+    KB_CUDA(h, launch_finalize_gram(D, h->cam_slice_range.p, 1, &h->ctrl.p->cost_new, c));
+    kb_status st = nccl_allreduce(h, &h->ctrl.p->cost_new, 1, kNcclFloat64, kNcclSum);
+    if (st != KB_OK) return st;
+  }
+  KB_CUDA(h, launch_lm_post_eval(D, h->trace_dev.p, c));
+  KB_CUDA(h, launch_lm_revert(D, h->bk_cam.p, h->bk_base.p, h->bk_sets.p, c));
+  return KB_OK;
+}
+
+static kb_status optimize_on_device(kb_handle* h, const kb_optimizer_options* o, kb_solution* out) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  double J0 = 0.0;
+  kb_status st = kb_evaluate_error(h, 1, &J0);  // Optimizer2.cpp:198
+  if (st != KB_OK) return st;
+  const int max_it = std::max(o->max_iterations, 0);
+  if (h->trace_dev.n < (size_t)3 * (max_it + 1)) KB_CUDA(h, h->trace_dev.alloc((size_t)3 * (max_it + 1)));
+  LmCtrl c0;
+  std::memset(&c0, 0, sizeof(c0));
+  c0.need_build = 1;
+  c0.lambda = o->lm_lambda_init;
+  c0.J = c0.pJ = c0.JStart = J0;
+  c0.deltaX = o->convergence_delta_x + 1.0;
+  c0.deltaJ = o->convergence_delta_j + 1.0;
+  c0.mu = 2.0; c0.gamma = 3.0; c0.beta = 2.0; c0.p_exp = 3;  // LevenbergMarquardtTrustRegionPolicy.cpp:37-48
+  c0.polJ = c0.pol_pJ = c0.pol_lastJ = J0;
+  c0.first = 1;
+  c0.rho_den = 1.0;
+  c0.diag_residual = 0.0;
+  c0.conv_dx = o->convergence_delta_x;
+  c0.conv_dj = o->convergence_delta_j;
+  c0.semantic = h->semantic;
+  c0.max_iterations = max_it;
+  c0.done = max_it <= 0 ? 1 : 0;
+  KB_CUDA(h, cudaMemcpyAsync(h->ctrl.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));  // pageable source: staged at the call
+  *h->h_ctrl = c0;
+  // iterations are enqueued two at a time; the host only reads the control block back to see whether the loop has ended.
+  // The kernel arguments of an iteration never change (everything data-dependent lives in the control block), so after
+  // one plain-launched batch the iteration is captured into a CUDA graph and replayed: one launch per iteration instead of ~25.
+  const bool may_graph = h->n_ranks == 1 && !h->timing && !getenv("KB_NO_GRAPH");
+  while (!h->h_ctrl->done) {
+    if (may_graph && h->lm_warm && (!h->lm_graph || h->lm_graph_trace != h->trace_dev.p)) {
+      if (h->lm_graph) { cudaGraphExecDestroy(h->lm_graph); h->lm_graph = nullptr; }
+      cudaGraph_t graph = nullptr;
+      const long long l0 = h->launches;
+      KB_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      st = enqueue_lm_iteration(h);
+      cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+      h->lm_graph_kernels = h->launches - l0;  // captured, not launched
+      h->launches = l0;
+      if (st != KB_OK) return st;
+      KB_CUDA(h, ce);
+      KB_CUDA(h, cudaGraphInstantiate(&h->lm_graph, graph, 0));
+      cudaGraphDestroy(graph);
+      h->lm_graph_trace = h->trace_dev.p;
+    }
+    for (int k = 0; k < 2; ++k) {
+      if (may_graph && h->lm_graph) {
+        KB_CUDA(h, cudaGraphLaunch(h->lm_graph, h->stream));
+        h->launches += h->lm_graph_kernels;
+      } else if ((st = enqueue_lm_iteration(h)) != KB_OK) {
+        return st;
+      }
+    }
+    h->lm_warm = true;
+    KB_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->ctrl.p, sizeof(LmCtrl), cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    collect_stages(h);
+  }
+  const LmCtrl& c = *h->h_ctrl;
+  h->trace.assign((size_t)3 * c.iterations, 0.0);
+  if (c.iterations > 0) KB_CUDA(h, cudaMemcpyAsync(h->trace.data(), h->trace_dev.p, sizeof(double) * 3 * c.iterations, cudaMemcpyDeviceToHost, h->stream));
+  StreamCtx sc = ctx(h);
+  KB_CUDA(h, launch_lm_finish(h->d, sc));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  // host-side solver state after the loop
+  h->lambda = c.lambda;
+  h->rho_lambda = c.lambda;
+  h->diag_residual = c.diag_residual;
+  h->h_scalars[2] = c.rho_den;
+  h->h_scalars[3] = c.max_dx;
+  h->built = h->solved = h->has_backup = c.iterations + c.failed > 0;
+  ++h->state_version;
+  h->la_version = -1;  // the view blocks belong to the last TRIAL state: the next build linearises again
+  if (out) {
+    out->j_start = c.JStart;
+    out->j_final = c.pJ;
+    out->dx_final = c.deltaX;
+    out->dj_final = c.deltaJ;
+    out->iterations = c.iterations;
+    out->failed_iterations = c.failed;
+    out->linear_solver_failure = c.solver_failure;
+  }
+  return KB_OK;
 }
 
 kb_status kb_optimize(kb_handle* h, const kb_optimizer_options* o, kb_solution* out) {
   using namespace kalibr_b200::backend;
+  if (o->device_loop && !o->verbose && h->speculative) return optimize_on_device(h, o, out);
   try {
     Optimizer2Options opt;
     opt.convergenceDeltaX = o->convergence_delta_x;

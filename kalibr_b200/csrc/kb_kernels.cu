@@ -183,7 +183,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // =========================================================================================================
 __global__ void prep_kernel(DevProblem p) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n_cams) return;
+  if (k >= p.n_cams || p.ctrl->done || p.ctrl->skip_eval) return;
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
   for (int l = 0; l < k; ++l) {  // T_k = B_{k-1} ... B_0   (CalibrationTools.hpp:405-408)
     const double* b = p.baselines + l * POSE_STRIDE;
@@ -232,7 +232,7 @@ __global__ void prep_kernel(DevProblem p) {
 // per synced set: inverse pose (C^-1, -C^-1 t) and P_v, shared by the views of every camera of the set
 __global__ void __launch_bounds__(128) set_prep_kernel(DevProblem p) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= p.n_sets) return;
+  if (s >= p.n_sets || p.ctrl->done || p.ctrl->skip_eval) return;
   const double* pose = p.set_poses + (size_t)s * POSE_STRIDE;
   double C[9], Ci[9];
   quat2r(pose, C);
@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
   double* XT = smem + target_doubles + wib * LA_WARP_DOUBLES;  // [16 cols][68]
   double* sG = XT + XT_WARP_DOUBLES;                           // [3][64] slice sum of the three tiles
   double* sSP = sG + GRAM_TILES;                               // [2][16] per-set constants of the current / next view (cp.async)
+  if (p.ctrl->done || p.ctrl->skip_eval) return;
   for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
   __syncthreads();
 
@@ -726,6 +727,7 @@ __global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p)
   const int wib = threadIdx.x >> 5;
   const int arow = lane >> 2, acol = lane & 3;
   const int C = p.n_cams;
+  if (p.ctrl->done || !p.ctrl->need_build) return;
   // operand element of a 6x6 row-major matrix, zero padded to 8x8:  direct[ks] = X[arow][4ks + acol],  transposed[ks] = X[4ks + acol][arow]
   const bool in0 = arow < 6, in1 = arow < 6 && acol < 2;  // k-step 0: k = acol < 4 ; k-step 1: k = 4 + acol < 6
   const int d0 = arow * 6 + acol, d1 = arow * 6 + 4 + acol;
@@ -820,6 +822,7 @@ constexpr int FG_GROUPS = 5;
 __global__ void __launch_bounds__(GRAM_TILES * FG_GROUPS) finalize_gram_kernel(DevProblem p, const int* __restrict__ cam_slice_range, int n_ranges) {
   __shared__ double sh[FG_GROUPS][GRAM_TILES];
   const int k = blockIdx.x, t = threadIdx.x % GRAM_TILES, g = threadIdx.x / GRAM_TILES;
+  if (p.ctrl->done || p.ctrl->skip_eval) return;
   double s = 0.0;
   for (int r = 0; r < n_ranges; ++r) {
     const int lo = cam_slice_range[(k * n_ranges + r) * 2], hi = cam_slice_range[(k * n_ranges + r) * 2 + 1];
@@ -889,7 +892,7 @@ __device__ __forceinline__ bool red_column(const DevProblem& p, const RedIndex& 
 __global__ void __launch_bounds__(256) camera_block_kernel(DevProblem p) {
   const int n = p.n_aug;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * n) return;
+  if (idx >= n * n || p.ctrl->done || !p.ctrl->need_build) return;
   const int i = idx / n, j = idx % n;
   if (i > j) return;
   const RedIndex ri = red_index(p, i), rj = red_index(p, j);
@@ -914,7 +917,7 @@ __global__ void __launch_bounds__(256) camera_block_kernel(DevProblem p) {
 
 // cost at the linearisation point = sum_k G_k[e][e]
 __global__ void gram_cost_kernel(DevProblem p, double* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && !p.ctrl->done && !p.ctrl->skip_eval) {
     double s = 0.0;
     for (int k = 0; k < p.n_cams; ++k) s += p.sumG[(size_t)k * GRAM_SIZE + E_COL * GRAM_DIM + E_COL];
     out[0] = s;
@@ -926,9 +929,10 @@ __global__ void gram_cost_kernel(DevProblem p, double* __restrict__ out) {
 // (V_v + d I) = L_v L_v^T.  pose_factor_kernel inverts the 6x6 factors (thread per set); schur_kernel then turns the rows
 // of [W_v ; b_v^T] into Z rows with a 6x6 triangular product and accumulates Z Z^T with DMMA, SC_SETS sets per step.
 // =========================================================================================================
-__global__ void __launch_bounds__(128) pose_factor_kernel(DevProblem p, double damping, int* __restrict__ pos_def_flag) {
+__global__ void __launch_bounds__(128) pose_factor_kernel(DevProblem p, double damping_arg, int* __restrict__ pos_def_flag) {
   const int set = blockIdx.x * blockDim.x + threadIdx.x;
-  if (set >= p.n_sets) return;
+  if (set >= p.n_sets || p.ctrl->done) return;
+  const double damping = damping_arg >= 0.0 ? damping_arg : p.ctrl->damping;
   double L[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) L[i] = p.V[(size_t)set * 36 + i];
@@ -969,6 +973,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
   const int n_pad = nt * 8;
   double* Zbuf = smem;                         // [2][n_pad][SC_LD]
   double* sLi = smem + 2 * n_pad * SC_LD;      // [2][SC_SETS][36]
+  if (p.ctrl->done) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int arow = lane >> 2, acol = lane & 3;
   const int npairs = nt * (nt + 1) / 2;
@@ -1094,7 +1099,7 @@ __global__ void __launch_bounds__(256) schur_finalize_kernel(DevProblem p, const
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int idx = t >> 2, seg = t & 3;  // four lanes per element, each a quarter of the partials; combined in a fixed order
   const int i = idx / n, j = idx - i * n;
-  const bool live = idx < n * n && i <= j;
+  const bool live = idx < n * n && i <= j && !p.ctrl->done;
   // within a diagonal tile only the mma's own (i,j) entry is used for i<=j, so the result is exactly symmetric
   double s = 0.0;
   if (live) {
@@ -1193,12 +1198,14 @@ __device__ __forceinline__ void panel_rows(double* __restrict__ Lp, int j0, int 
 //   2. thread 0: Cholesky of the 8x8 diagonal block and its inverse,
 //   3. thread per row: L[row][panel] = A[row][panel] Ldd^-T.
 // Then L^T x = y with one barrier per unknown.
-__global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping, int* __restrict__ pos_def_flag) {
+__global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping_arg, int* __restrict__ pos_def_flag) {
   extern __shared__ __align__(16) double Lp[];  // packed lower triangle, n_rows rows (zero padded)
   __shared__ double s_Ldd[RS_NB * RS_NB], s_Linv[RS_NB * RS_NB];
   __shared__ double s_slot[2];
   __shared__ int s_ok;
   const int n = p.n_aug, nc = p.n_c;
+  if (p.ctrl->done) return;
+  const double damping = damping_arg >= 0.0 ? damping_arg : p.ctrl->damping;
   const int n_rows = ((n + RS_NB - 1) / RS_NB) * RS_NB + RS_NB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < n_rows * (n_rows + 1) / 2; idx += RS_THREADS) Lp[idx] = 0.0;
@@ -1288,6 +1295,7 @@ __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* _
                                                       const int* __restrict__ cam_cols) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (p.ctrl->done) return;
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < p.n_c; i += blockDim.x) p.dx[cam_cols[i]] = p.dxc[i];
   if (gw >= p.n_sets) return;
@@ -1348,9 +1356,11 @@ __device__ __forceinline__ void block_sum_max(double& s, double& m, double* sh_s
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   }
 }
-__global__ void __launch_bounds__(256) rho_stage1_kernel(DevProblem p, double lambda, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
+__global__ void __launch_bounds__(256) rho_stage1_kernel(DevProblem p, double lambda_arg, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
                                                            int include_shared, double* __restrict__ partial /*[RHO_BLOCKS][2]*/) {
   __shared__ double sh_s[32], sh_m[32];
+  if (p.ctrl->done) return;
+  const double lambda = lambda_arg >= 0.0 ? lambda_arg : p.ctrl->lambda;
   double s = 0.0, m = 0.0;
   for (int set = blockIdx.x * blockDim.x + threadIdx.x; set < p.n_sets; set += gridDim.x * blockDim.x) {
 #pragma unroll
@@ -1371,8 +1381,9 @@ __global__ void __launch_bounds__(256) rho_stage1_kernel(DevProblem p, double la
   block_sum_max(s, m, sh_s, sh_m);
   if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s; partial[2 * blockIdx.x + 1] = m; }
 }
-__global__ void __launch_bounds__(RHO_BLOCKS) rho_stage2_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+__global__ void __launch_bounds__(RHO_BLOCKS) rho_stage2_kernel(const LmCtrl* __restrict__ ctrl, const double* __restrict__ partial, int n, double* __restrict__ out) {
   __shared__ double sh_s[32], sh_m[32];
+  if (ctrl->done) return;
   double s = threadIdx.x < n ? partial[2 * threadIdx.x] : 0.0;
   double m = threadIdx.x < n ? partial[2 * threadIdx.x + 1] : 0.0;
   block_sum_max(s, m, sh_s, sh_m);
@@ -1408,6 +1419,7 @@ __device__ __forceinline__ void update_quat(double* q, const double* dq) {
 __global__ void __launch_bounds__(256) apply_update_kernel(DevProblem p, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
                                                            double* __restrict__ backup_cam, double* __restrict__ backup_base, double* __restrict__ backup_sets) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p.ctrl->done || p.ctrl->skip_eval) return;
   if (idx < p.n_sets) {
     double* pose = p.set_poses + (size_t)idx * POSE_STRIDE;
     double* bk = backup_sets + (size_t)idx * POSE_STRIDE;
@@ -1438,6 +1450,129 @@ __global__ void __launch_bounds__(256) apply_update_kernel(DevProblem p, const i
       for (int c = 0; c < 3; ++c) b[4 + c] += p.dxc[p.base_off[j] + 3 + c];
     }
   }
+}
+
+// =========================================================================================================
+// device-resident Levenberg-Marquardt loop: three single-thread control kernels per iteration carry the scalar logic of
+// Optimizer2::optimize (BE/src/Optimizer2.cpp:215-266) and LevenbergMarquardtTrustRegionPolicy::solveSystemImplementation
+// (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:50-113), so that no host round trip sits inside an iteration.
+// =========================================================================================================
+__device__ __forceinline__ void lm_check_loop(LmCtrl* c) {  // the while condition of Optimizer2.cpp:215-219
+  const bool go = c->iterations < c->max_iterations && c->failed < c->max_iterations &&
+                  ((c->deltaX > c->conv_dx && fabs(c->deltaJ) > c->conv_dj) || c->solver_failure);
+  if (!go) c->done = 1;
+}
+
+// before the solve: TrustRegionPolicy::solveSystem bookkeeping, rho, the lambda schedule, build / no build, damping
+__global__ void lm_pre_solve_kernel(LmCtrl* c, int* pos_def) {
+  if (c->done) return;
+  const double J = c->J;
+  if (c->prev_failed) {
+    c->polJ = J;
+  } else {
+    c->pol_pJ = c->pol_lastJ;
+    c->pol_lastJ = J;
+    c->polJ = J;
+  }
+  int build = 0;
+  double lambda = c->lambda;
+  if (c->first) {
+    build = 1;
+  } else {
+    const double rho = (c->pol_pJ - c->polJ) / c->rho_den;
+    if (c->prev_failed) {
+      c->mu *= 2.0;
+      lambda *= c->mu;
+    } else if (rho <= 0.0) {
+      c->mu *= 10.0;
+      lambda *= c->mu;
+    } else {
+      build = 1;
+      if (lambda > 1e-16) {
+        const double u1 = 1.0 / c->gamma;
+        const double u2 = 1.0 - (c->beta - 1.0) * pow(2.0 * rho - 1.0, (double)c->p_exp);
+        lambda *= (u1 > u2) ? u1 : u2;
+        c->mu = c->beta;
+      } else {
+        lambda = 1e-15;
+      }
+    }
+  }
+  c->first = 0;
+  c->lambda = lambda;
+  c->need_build = build;
+  if (build) c->diag_residual = 0.0;  // H.clear(false): BlockCholeskyLinearSystemSolver.cpp:64
+  c->damping = c->diag_residual + lambda * lambda;
+  c->revert = 0;
+  pos_def[0] = 1;
+}
+
+// after the solve: combine the ranks' (rho, max|dx|, pos-def) slots, the lambda^2 / lambda residual (Q2), failed solves
+__global__ void lm_post_solve_kernel(LmCtrl* c, const int* pos_def, const double* rho_max, const double* rank_slots, int n_ranks) {
+  if (c->done) return;
+  double rho = rho_max[0], mx = rho_max[1];
+  int pd = pos_def[0];
+  if (n_ranks > 1) {
+    rho = 0.0;
+    mx = 0.0;
+    pd = 1;
+    for (int r = 0; r < n_ranks; ++r) {
+      rho += rank_slots[4 * r];
+      mx = fmax(mx, rank_slots[4 * r + 1]);
+      if (rank_slots[4 * r + 2] < 0.5) pd = 0;
+    }
+  }
+  c->rho_den = rho;
+  c->max_dx = mx;
+  if (c->semantic == 0) c->diag_residual += c->lambda * c->lambda - c->lambda;
+  if (!pd) {  // Optimizer2.cpp:223-229
+    c->prev_failed = 1;
+    c->solver_failure = 1;
+    c->failed += 1;
+    c->skip_eval = 1;
+    lm_check_loop(c);
+  } else {
+    c->skip_eval = 0;
+  }
+}
+
+// after the evaluation of the trial state: accept / reject, trace, loop condition
+__global__ void lm_post_eval_kernel(LmCtrl* c, double* trace) {
+  if (c->done || c->skip_eval) return;
+  c->deltaX = c->max_dx;
+  c->J = c->cost_new;
+  c->deltaJ = c->pJ - c->J;
+  if (c->deltaJ < 0.0) {  // regression: revert (Optimizer2.cpp:241-249)
+    c->revert = 1;
+    c->failed += 1;
+    c->prev_failed = 1;
+  } else {
+    c->pJ = c->J;
+    c->prev_failed = 0;
+  }
+  trace[3 * c->iterations] = c->J;
+  trace[3 * c->iterations + 1] = c->deltaX;
+  trace[3 * c->iterations + 2] = c->lambda;
+  c->iterations += 1;
+  lm_check_loop(c);
+}
+
+// restore the backup when the step was rejected (idempotent: a finished loop may run it again with the same flag)
+__global__ void __launch_bounds__(256) lm_revert_kernel(DevProblem p, const double* __restrict__ bk_cam, const double* __restrict__ bk_base,
+                                                        const double* __restrict__ bk_sets) {
+  if (!p.ctrl->revert) return;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < p.n_sets * POSE_STRIDE) p.set_poses[idx] = bk_sets[idx];
+  if (idx < p.n_cams * CAM_PARAM_STRIDE) p.cam_params[idx] = bk_cam[idx];
+  if (idx < (p.n_cams - 1) * POSE_STRIDE) p.baselines[idx] = bk_base[idx];
+}
+
+// back to the neutral flags of the call-by-call API
+__global__ void lm_finish_kernel(LmCtrl* c) {
+  c->done = 0;
+  c->need_build = 1;
+  c->skip_eval = 0;
+  c->revert = 0;
 }
 
 // =========================================================================================================
@@ -1655,13 +1790,40 @@ cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int
   const int blocks = max(1, min(RHO_BLOCKS, (p.n_sets + 255) / 256));
   rho_stage1_kernel<<<blocks, 256, 0, s.stream>>>(p, lambda, set_col_q, set_col_t, include_shared, partial);
   KB_LAUNCHED(s);
-  rho_stage2_kernel<<<1, RHO_BLOCKS, 0, s.stream>>>(partial, blocks, out2);
+  rho_stage2_kernel<<<1, RHO_BLOCKS, 0, s.stream>>>(p.ctrl, partial, blocks, out2);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pack_rank_scalars(double* pk, int rank, int n_ranks, const double* rho_max, const int* pos_def, StreamCtx& s) {
   pack_rank_scalars_kernel<<<1, 128, 0, s.stream>>>(pk, rank, n_ranks, rho_max, pos_def);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lm_pre_solve(const DevProblem& p, int* pos_def_flag, StreamCtx& s) {
+  lm_pre_solve_kernel<<<1, 1, 0, s.stream>>>(p.ctrl, pos_def_flag);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+cudaError_t launch_lm_post_solve(const DevProblem& p, const int* pos_def_flag, const double* rho_max, const double* rank_slots, int n_ranks, StreamCtx& s) {
+  lm_post_solve_kernel<<<1, 1, 0, s.stream>>>(p.ctrl, pos_def_flag, rho_max, rank_slots, n_ranks);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+cudaError_t launch_lm_post_eval(const DevProblem& p, double* trace, StreamCtx& s) {
+  lm_post_eval_kernel<<<1, 1, 0, s.stream>>>(p.ctrl, trace);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+cudaError_t launch_lm_revert(const DevProblem& p, const double* backup_cam, const double* backup_base, const double* backup_sets, StreamCtx& s) {
+  const int n = max(max(p.n_sets * POSE_STRIDE, p.n_cams * CAM_PARAM_STRIDE), 1);
+  lm_revert_kernel<<<(n + 255) / 256, 256, 0, s.stream>>>(p, backup_cam, backup_base, backup_sets);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+cudaError_t launch_lm_finish(const DevProblem& p, StreamCtx& s) {
+  lm_finish_kernel<<<1, 1, 0, s.stream>>>(p.ctrl);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }

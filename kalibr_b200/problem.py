@@ -59,12 +59,13 @@ class KbOptimizerOptions(C.Structure):
         ("max_iterations", C.c_int32),
         ("lm_lambda_init", C.c_double),
         ("verbose", C.c_int32),
+        ("device_loop", C.c_int32),
     ]
 
     @classmethod
-    def kalibr2_default(cls, verbose: int = 0) -> "KbOptimizerOptions":
+    def kalibr2_default(cls, verbose: int = 0, device_loop: int = 1) -> "KbOptimizerOptions":
         """kalibr2::tools::CreateDefaultOptimizer (CalibrationTools.hpp:57-66)."""
-        return cls(1e-3, 1.0, 200, 10.0, verbose)
+        return cls(1e-3, 1.0, 200, 10.0, verbose, device_loop)
 
 
 class KbSolution(C.Structure):

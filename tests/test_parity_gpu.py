@@ -228,3 +228,38 @@ def test_streamed_evaluate_matches_separate_upload_and_oracle(capi, oracle_lib, 
     assert rel_err(dxa, dxb) < 1e-11
     assert rel_err(dxa, dxo) < 1e-7
     assert rel_err(a.rhs(), o.rhs()) < 1e-9
+
+
+@pytest.mark.parametrize("cfg,n_sets,lam0", [(1, 40, 10.0), (2, 30, 10.0), (3, 24, 10.0), (4, 12, 1e-4), (2, 30, 1e-6), (3, 24, 1e3)])
+def test_device_resident_loop_matches_host_loop_and_oracle(capi, oracle_lib, cfg, n_sets, lam0):
+    """kb_optimize with the LM loop on the device (control kernels, no host round trip inside an iteration) walks exactly the
+    same iterations as the host-side Optimizer2 mirror over the call-by-call entry points, and as the oracle."""
+    p = make(cfg, n_sets)
+    opt_dev = KbOptimizerOptions.kalibr2_default(device_loop=1)
+    opt_host = KbOptimizerOptions.kalibr2_default(device_loop=0)
+    opt_dev.lm_lambda_init = opt_host.lm_lambda_init = lam0
+    a = capi.B200SchurLinearSystemSolver(p)
+    b = capi.B200SchurLinearSystemSolver(p)
+    o = oracle_lib.OracleProblem(p)
+    sa, ta = a.optimize(opt_dev)
+    sb, tb = b.optimize(opt_host)
+    so, to = o.optimize(opt_host)
+    for s in (sb, so):
+        assert (sa.iterations, sa.failed_iterations, sa.linear_solver_failure) == (s.iterations, s.failed_iterations, s.linear_solver_failure)
+    assert ta.shape == tb.shape == to.shape
+    assert rel_err(ta[:, 2], tb[:, 2]) < 1e-9 and rel_err(ta[:, 2], to[:, 2]) < 1e-6   # lambda schedule
+    assert rel_err(ta[:, 0], tb[:, 0]) < 1e-12 and rel_err(ta[:, 0], to[:, 0]) < 1e-9  # cost per iteration
+    assert abs(sa.j_final - sb.j_final) <= 1e-12 * sb.j_final and abs(sa.j_final - so.j_final) <= 1e-9 * so.j_final
+    assert abs(sa.dx_final - sb.dx_final) <= 1e-6 * max(sb.dx_final, 1e-12)
+    assert rel_err(a.camera_params(), b.camera_params()) < 1e-10
+    assert rel_err(a.camera_params(), o.camera_params()) < REL_X
+    assert rel_err(a.set_poses(), b.set_poses()) < 1e-10
+    # the call-by-call API keeps working on the same handle afterwards (neutral control flags, fresh linearisation)
+    Ja, Jb = a.evaluate_error(), b.evaluate_error()
+    assert abs(Ja - Jb) <= 1e-12 * Jb
+    for s in (a, b):
+        s.build_system()
+        s.set_constant_conditioner(3.0)
+    dxa, oka = a.solve_system()
+    dxb, okb = b.solve_system()
+    assert oka == okb and rel_err(dxa, dxb) < 1e-8
