@@ -263,3 +263,66 @@ def test_device_resident_loop_matches_host_loop_and_oracle(capi, oracle_lib, cfg
     dxa, oka = a.solve_system()
     dxb, okb = b.solve_system()
     assert oka == okb and rel_err(dxa, dxb) < 1e-8
+
+
+def _edit_views(p, empty=(), remove=()):
+    """Copy of problem p with the views in `empty` emptied (zero terms, the view stays) and the views in `remove` dropped
+    entirely (the set then has no image of that camera)."""
+    from kalibr_b200.problem import Problem
+
+    keep_term = np.ones(p.n_terms, bool)
+    vs, vc, counts = [], [], []
+    for w in range(p.n_views):
+        b, e = int(p.view_begin[w]), int(p.view_begin[w + 1])
+        if w in remove:
+            keep_term[b:e] = False
+            continue
+        if w in empty:
+            keep_term[b:e] = False
+            counts.append(0)
+        else:
+            counts.append(e - b)
+        vs.append(p.view_set[w])
+        vc.append(p.view_cam[w])
+    vb = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return Problem(p.driver_order, p.cam_model, p.cam_params, p.baselines, p.set_poses, p.target_points, np.array(vs, np.int32),
+                   np.array(vc, np.int32), vb, p.y_u[keep_term], p.y_v[keep_term], p.corner_id[keep_term])
+
+
+@pytest.mark.parametrize("cfg,n_sets,dropout,empty,remove", [
+    (2, 12, 0.3, (), ()),            # ragged views: every view a different number of corners
+    (3, 10, 0.45, (5,), ()),         # mixed models, ragged, one empty view
+    (4, 6, 0.2, (3, 17), (9, 20, 21)),  # 8-camera chain with empty views and sets that miss cameras
+    (2, 9, 0.9, (), (4,)),           # almost everything dropped: views of one to a few corners
+])
+def test_ragged_empty_and_missing_views_match_oracle(capi, oracle_lib, cfg, n_sets, dropout, empty, remove):
+    """Edge cases of the observation structure: ragged views, empty views, sets without an image of some
+    camera — residuals, CCS Jacobian, block pattern (bit exact), normal equations, solution and the LM run against the oracle."""
+    p = _edit_views(make(cfg, n_sets, dropout=dropout), set(empty), set(remove))
+    assert np.unique(np.diff(p.view_begin)).size > 2
+    g = capi.B200SchurLinearSystemSolver(p)
+    o = oracle_lib.OracleProblem(p)
+    Jg, Jo = g.evaluate_error(), o.evaluate_error()
+    assert abs(Jg - Jo) <= 1e-11 * Jo
+    assert rel_err(g.error_vector(), o.error_vector()) < REL_J
+    g.linearise()
+    gp, gi, gv = g.jacobian_ccs()
+    op, oi, ov = o.jacobian_ccs()
+    assert np.array_equal(gp, op) and np.array_equal(gi, oi)
+    assert rel_err(gv, ov) < REL_J
+    g.build_system(); o.build_system()
+    assert rel_err(g.rhs(), o.rhs()) < REL_J
+    g.set_constant_conditioner(10.0); o.set_constant_conditioner(10.0)
+    gdx, gok = g.solve_system()
+    odx, ook = o.solve_system()
+    assert gok == ook
+    gcp, gbr, gvp, gval = g.hessian_blocks()
+    ocp, obr, ovp, oval = o.hessian_blocks()
+    assert np.array_equal(gcp, ocp) and np.array_equal(gbr, obr) and np.array_equal(gvp, ovp)
+    assert rel_err(gval, oval) < REL_J
+    assert rel_err(gdx, odx) < 1e-7
+    g.reset_state()
+    sg, tg = g.optimize(KbOptimizerOptions.kalibr2_default())
+    so, to = oracle_lib.OracleProblem(p).optimize(KbOptimizerOptions.kalibr2_default())
+    assert (sg.iterations, sg.failed_iterations, sg.linear_solver_failure) == (so.iterations, so.failed_iterations, so.linear_solver_failure)
+    assert abs(sg.j_final - so.j_final) <= 1e-9 * so.j_final
