@@ -1126,11 +1126,12 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_NB = 8;  // panel width = DMMA tile
 __device__ __forceinline__ int tri(int i, int k) { return i * (i + 1) / 2 + k; }
 
-// Cholesky of the W x W diagonal block at (j0, j0) of the packed matrix and the inverse of its factor; fully unrolled so that
-// the block lives in registers.  Returns false if a pivot is not positive.
+// Cholesky of the W x W diagonal block at (j0, j0) of the packed matrix, fully unrolled so that the block lives in
+// registers; leaves the factor in place and the reciprocals of its diagonal in rd[j0..j0+W).  Returns false if a pivot is
+// not positive.
 template <int W>
-__device__ __forceinline__ bool diag_block(double* __restrict__ Lp, int j0, double* __restrict__ s_Linv) {
-  double L[W][W], Li[W][W], rd[W];
+__device__ __forceinline__ bool diag_block(double* __restrict__ Lp, int j0, double* __restrict__ rd_all) {
+  double L[W][W], rd[W];
   bool ok = true;
 #pragma unroll
   for (int r = 0; r < W; ++r)
@@ -1154,38 +1155,35 @@ __device__ __forceinline__ bool diag_block(double* __restrict__ Lp, int j0, doub
     }
   }
 #pragma unroll
-  for (int c = 0; c < W; ++c) {
-    Li[c][c] = rd[c];
+  for (int r = 0; r < W; ++r) {
+    rd_all[j0 + r] = rd[r];
 #pragma unroll
-    for (int r = c + 1; r < W; ++r) {
-      double v = 0.0;
-#pragma unroll
-      for (int k = c; k < r; ++k) v -= L[r][k] * Li[k][c];
-      Li[r][c] = v * rd[r];
-    }
+    for (int c = 0; c <= r; ++c) Lp[(j0 + r) * (j0 + r + 1) / 2 + j0 + c] = L[r][c];
   }
-#pragma unroll
-  for (int r = 0; r < W; ++r)
-#pragma unroll
-    for (int c = 0; c <= r; ++c) {
-      Lp[(j0 + r) * (j0 + r + 1) / 2 + j0 + c] = L[r][c];
-      s_Linv[r * 8 + c] = Li[r][c];
-    }
   return ok;
 }
+// rows below the diagonal block: x Ldd^T = a, a forward substitution per row (thread per row) with the block in registers
 template <int W>
-__device__ __forceinline__ void panel_rows(double* __restrict__ Lp, int j0, int n, const double* __restrict__ s_Linv, int tid, int nthreads) {
+__device__ __forceinline__ void panel_rows(double* __restrict__ Lp, int j0, int n, const double* __restrict__ rd_all, int tid, int nthreads) {
+  if (j0 + W + tid >= n) return;
+  double L[W][W], rd[W];
+#pragma unroll
+  for (int r = 0; r < W; ++r) {
+    rd[r] = rd_all[j0 + r];
+#pragma unroll
+    for (int c = 0; c < r; ++c) L[r][c] = Lp[(j0 + r) * (j0 + r + 1) / 2 + j0 + c];
+  }
   for (int row = j0 + W + tid; row < n; row += nthreads) {
-    double a[W], x[W];
+    double x[W];
     double* base = Lp + row * (row + 1) / 2 + j0;
 #pragma unroll
-    for (int c = 0; c < W; ++c) a[c] = base[c];
+    for (int c = 0; c < W; ++c) x[c] = base[c];
 #pragma unroll
     for (int c = 0; c < W; ++c) {
-      double v = 0.0;
+      double v = x[c];
 #pragma unroll
-      for (int k = 0; k <= c; ++k) v += a[k] * s_Linv[c * 8 + k];
-      x[c] = v;
+      for (int k = 0; k < c; ++k) v -= x[k] * L[c][k];
+      x[c] = v * rd[c];
     }
 #pragma unroll
     for (int c = 0; c < W; ++c) base[c] = x[c];
@@ -1195,18 +1193,19 @@ __device__ __forceinline__ void panel_rows(double* __restrict__ Lp, int j0, int 
 // Blocked left-looking Cholesky of the augmented reduced system (n_aug = n_c + 1 rows; the last row carries the rhs and
 // comes out as y = L^-1 b), packed lower triangle in shared memory.  Per 8-column panel:
 //   1. all warps: A[rows >= j0][panel] -= L[rows][0:j0] L[panel][0:j0]^T with DMMA m8n8k4 (operands straight from the packed rows),
-//   2. thread 0: Cholesky of the 8x8 diagonal block and its inverse,
-//   3. thread per row: L[row][panel] = A[row][panel] Ldd^-T.
-// Then L^T x = y with one barrier per unknown.
+//   2. thread 0: Cholesky of the 8x8 diagonal block (registers),
+//   3. thread per row: L[row][panel] = A[row][panel] Ldd^-T by forward substitution.
+// Then L^T x = y panel by panel from the last: one thread solves the 8x8 triangle, all threads push the panel's x into the
+// rows above (two barriers per panel instead of one per unknown).
 __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping_arg, int* __restrict__ pos_def_flag) {
-  extern __shared__ __align__(16) double Lp[];  // packed lower triangle, n_rows rows (zero padded)
-  __shared__ double s_Ldd[RS_NB * RS_NB], s_Linv[RS_NB * RS_NB];
-  __shared__ double s_slot[2];
+  extern __shared__ __align__(16) double Lp[];  // packed lower triangle, n_rows rows (zero padded), then rd[n_rows], x[n_rows]
   __shared__ int s_ok;
   const int n = p.n_aug, nc = p.n_c;
   if (p.ctrl->done) return;
   const double damping = damping_arg >= 0.0 ? damping_arg : p.ctrl->damping;
   const int n_rows = ((n + RS_NB - 1) / RS_NB) * RS_NB + RS_NB;
+  double* s_rd = Lp + n_rows * (n_rows + 1) / 2;
+  double* s_x = s_rd + n_rows;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < n_rows * (n_rows + 1) / 2; idx += RS_THREADS) Lp[idx] = 0.0;
   __syncthreads();
@@ -1243,49 +1242,58 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
       }
       __syncthreads();
     }
-    // ---- 2. diagonal block: Cholesky and inverse (one thread, registers) ----
+    // ---- 2. diagonal block (one thread, registers) ----
     if (tid == 0) {
       bool ok = true;
       switch (w) {
-        case 8: ok = diag_block<8>(Lp, j0, s_Linv); break;
-        case 7: ok = diag_block<7>(Lp, j0, s_Linv); break;
-        case 6: ok = diag_block<6>(Lp, j0, s_Linv); break;
-        case 5: ok = diag_block<5>(Lp, j0, s_Linv); break;
-        case 4: ok = diag_block<4>(Lp, j0, s_Linv); break;
-        case 3: ok = diag_block<3>(Lp, j0, s_Linv); break;
-        case 2: ok = diag_block<2>(Lp, j0, s_Linv); break;
-        default: ok = diag_block<1>(Lp, j0, s_Linv); break;
+        case 8: ok = diag_block<8>(Lp, j0, s_rd); break;
+        case 7: ok = diag_block<7>(Lp, j0, s_rd); break;
+        case 6: ok = diag_block<6>(Lp, j0, s_rd); break;
+        case 5: ok = diag_block<5>(Lp, j0, s_rd); break;
+        case 4: ok = diag_block<4>(Lp, j0, s_rd); break;
+        case 3: ok = diag_block<3>(Lp, j0, s_rd); break;
+        case 2: ok = diag_block<2>(Lp, j0, s_rd); break;
+        default: ok = diag_block<1>(Lp, j0, s_rd); break;
       }
       if (!ok) s_ok = 0;
     }
     __syncthreads();
-    // ---- 3. rows below the block: x = a Ldd^-T ----
+    // ---- 3. rows below the block ----
     switch (w) {
-      case 8: panel_rows<8>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
-      case 7: panel_rows<7>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
-      case 6: panel_rows<6>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
-      case 5: panel_rows<5>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
-      case 4: panel_rows<4>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
-      case 3: panel_rows<3>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
-      case 2: panel_rows<2>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
-      default: panel_rows<1>(Lp, j0, n, s_Linv, tid, RS_THREADS); break;
+      case 8: panel_rows<8>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
+      case 7: panel_rows<7>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
+      case 6: panel_rows<6>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
+      case 5: panel_rows<5>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
+      case 4: panel_rows<4>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
+      case 3: panel_rows<3>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
+      case 2: panel_rows<2>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
+      default: panel_rows<1>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
     }
     __syncthreads();
   }
   if (tid == 0 && !s_ok) *pos_def_flag = 0;
-  // back substitution L^T x = y ; y is row nc of the factor.  Thread k owns x_k; one barrier per step.
-  double yk = (tid < nc) ? Lp[tri(nc, tid)] : 0.0;
-  for (int i = nc - 1; i >= 0; --i) {
-    if (tid == i) {
-      yk = yk / Lp[tri(i, i)];
-      s_slot[i & 1] = yk;
+  // ---- back substitution L^T x = y, y = row nc of the factor; panels from the last to the first ----
+  for (int i = tid; i < nc; i += RS_THREADS) s_x[i] = Lp[tri(nc, i)];
+  __syncthreads();
+  const int last = ((nc - 1) / RS_NB) * RS_NB;
+  for (int j0 = last; j0 >= 0; j0 -= RS_NB) {
+    const int w = min(RS_NB, nc - j0);
+    if (tid == 0) {  // the w x w triangle of the panel
+      for (int c = w - 1; c >= 0; --c) {
+        double v = s_x[j0 + c];
+        for (int k = c + 1; k < w; ++k) v -= Lp[tri(j0 + k, j0 + c)] * s_x[j0 + k];
+        s_x[j0 + c] = v * s_rd[j0 + c];
+      }
     }
     __syncthreads();
-    const double xi = s_slot[i & 1];
-    if (tid < i) yk -= Lp[tri(i, tid)] * xi;
+    for (int k = tid; k < j0; k += RS_THREADS) {  // y[k] -= sum_c L[j0 + c][k] x[j0 + c]
+      double v = s_x[k];
+      for (int c = 0; c < w; ++c) v -= Lp[tri(j0 + c, k)] * s_x[j0 + c];
+      s_x[k] = v;
+    }
+    __syncthreads();
   }
-  if (tid < nc) p.dxc[tid] = yk;
-  (void)s_Ldd;
+  for (int i = tid; i < nc; i += RS_THREADS) p.dxc[i] = s_x[i];
 }
 
 // =========================================================================================================
@@ -1761,7 +1769,7 @@ cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const
 
 cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s) {
   const size_t n_rows = ((p.n_aug + RS_NB - 1) / RS_NB) * RS_NB + RS_NB;
-  const size_t smem = sizeof(double) * (n_rows * (n_rows + 1) / 2);
+  const size_t smem = sizeof(double) * (n_rows * (n_rows + 1) / 2 + 2 * n_rows);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
