@@ -289,19 +289,42 @@ def main():
         yv_pin = torch.from_numpy(p.y_v).pin_memory()
         yu_np, yv_np = yu_pin.numpy(), yv_pin.numpy()
 
-        def e2e_step():
+        def e2e_step_streamed():
             # H2D of the observations from pinned host memory, pipelined in chunks against the fused kernel inside the
             # library; D2H: cost, pos-def flag, dx (jcols doubles), rho, max|dx|
             lm_step(g, fetch_dx=True, host_obs=(yu_np, yv_np))
 
-        for _ in range(2):
-            e2e_step()
+        def e2e_step_pipelined():
+            # double buffering across steps: this step's batch was uploaded while the previous step computed; the next
+            # step's batch starts travelling now (one 16 B/term upload per step inside the timed region either way)
+            g.commit_observations()
+            g.prefetch_observations(yu_np, yv_np)
+            lm_step(g, fetch_dx=True)
+
         k_e2e = max(3, args.steps // 2)
-        ms_e2e = timed(e2e_step, k_e2e)
+        for _ in range(2):
+            e2e_step_streamed()
+        ms_streamed = timed(e2e_step_streamed, k_e2e)
+        g.prefetch_observations(yu_np, yv_np)
+        for _ in range(2):
+            e2e_step_pipelined()
+
+        def pipelined_run():
+            for _ in range(k_e2e):
+                e2e_step_pipelined()
+            g.commit_observations()               # the last upload is waited for inside the timed region
+            g.prefetch_observations(yu_np, yv_np)
+
+        ms_e2e = timed(pipelined_run, 1)
+        g.commit_observations()
         e2e = {"value": terms_total * k_e2e / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(16 * terms_rank), "d2h_bytes_per_step": int(8 * g.jcols + 8 * 4 + 4),
                "ms_per_step": ms_e2e / k_e2e, "steps": k_e2e,
-               "note": "per rank; through B200SchurLinearSystemSolver (C ABI) with pinned HOST observation buffers re-uploaded and dx fetched every step"}
+               "single_step_latency_ms": ms_streamed / k_e2e,
+               "note": "per rank; through B200SchurLinearSystemSolver (C ABI) with pinned HOST observation buffers uploaded every step and dx fetched "
+                       "every step. value: double-buffered (kb_prefetch_observations / kb_commit_observations: the next step's upload overlaps this "
+                       "step's kernels); single_step_latency_ms: one isolated step with kb_evaluate_error_streamed (chunked upload overlapped with "
+                       "the fused kernel). Both are bounded by the 16 B/term PCIe transfer"}
 
     # ---- materialising linearise (HBM-bound variant), timed alone ----
     lin = None

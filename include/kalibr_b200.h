@@ -194,6 +194,12 @@ KB_API kb_status kb_set_observations(kb_handle* h, const double* y_u, const doub
  * for real overlap) pipelined against the evaluation: the terms travel in a few chunks and the kernel starts on each chunk
  * as it lands.  Same results as the two separate calls up to the summation order of the cost. */
 KB_API kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const double* y_v, int32_t use_m_estimator, double* out_cost);
+/* Double buffering for callers that feed a new batch of measurements per step (e.g. an incremental estimator): prefetch starts
+ * the host->device copy of the NEXT batch into a second set of device buffers on a copy stream and returns at once (the host
+ * arrays must stay valid and pinned until the matching commit); commit makes that batch the current one (stream-ordered, no
+ * host synchronisation).  The copy overlaps with whatever runs between the two calls. */
+KB_API kb_status kb_prefetch_observations(kb_handle* h, const double* y_u, const double* y_v);
+KB_API kb_status kb_commit_observations(kb_handle* h);
 /* terms whose projection bailed out before writing y_hat (zero-weighted here) since creation */
 KB_API int64_t kb_num_invalid_terms(kb_handle* h);
 /* reset state to the initial guess given at kb_create */

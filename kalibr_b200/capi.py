@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "kb_solve_system", "kb_lm_rho_denominator", "kb_apply_state_update", "kb_revert_last_state_update",
     "kb_default_optimizer_options", "kb_optimize", "kb_get_trace", "kb_set_solver_semantic", "kb_set_speculative_linearise", "kb_get_error_vector", "kb_get_rhs",
     "kb_linearise", "kb_jacobian_nnz", "kb_get_jacobian_ccs", "kb_get_hessian_blocks", "kb_get_camera_params", "kb_get_baselines",
-    "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
+    "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
 ]
 
@@ -85,6 +85,8 @@ def load_library() -> C.CDLL:
     L.kb_get_set_poses.argtypes = [vp, vp]
     L.kb_set_observations.argtypes = [vp, vp, vp]
     L.kb_evaluate_error_streamed.argtypes = [vp, vp, vp, C.c_int32, vp]
+    L.kb_prefetch_observations.argtypes = [vp, vp, vp]
+    L.kb_commit_observations.argtypes = [vp]
     L.kb_reset_state.argtypes = [vp]
     L.kb_get_stage_ms.argtypes = [vp, vp]
     L.kb_enable_stage_timing.argtypes = [vp, C.c_int32]
@@ -267,6 +269,13 @@ class B200SchurLinearSystemSolver:
         J = C.c_double(0.0)
         self._check(self._L.kb_evaluate_error_streamed(self._h, _p(y_u), _p(y_v), 0, C.byref(J)), "kb_evaluate_error_streamed")
         return J.value
+
+    def prefetch_observations(self, y_u: np.ndarray, y_v: np.ndarray):
+        """Start the upload of the NEXT batch of measurements into the back buffers (pinned host arrays, kept alive by the caller)."""
+        self._check(self._L.kb_prefetch_observations(self._h, _p(y_u), _p(y_v)), "kb_prefetch_observations")
+
+    def commit_observations(self):
+        self._check(self._L.kb_commit_observations(self._h), "kb_commit_observations")
 
     def reset_state(self):
         self._check(self._L.kb_reset_state(self._h), "kb_reset_state")

@@ -113,6 +113,12 @@ struct kb_handle {
   int64_t st_chunk_term[KB_STREAM_CHUNKS + 1] = {};
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_chunk[KB_STREAM_CHUNKS] = {}, ev_main = nullptr;
+  // double-buffered observations: kb_prefetch_observations fills the back buffers on the copy stream while the front ones
+  // are in use, kb_commit_observations swaps them
+  DevBuf<double> y_u_back, y_v_back;
+  double *front_u = nullptr, *front_v = nullptr, *back_u = nullptr, *back_v = nullptr;
+  cudaEvent_t ev_prefetch = nullptr, ev_front_free = nullptr;
+  bool prefetch_pending = false, front_free_recorded = false;
   DevBuf<unsigned int> n_invalid, lm_counters;
   DevBuf<int> col_desc;
   int lm_bfrag_pairs[KB_NUM_MODELS] = {};
@@ -272,6 +278,8 @@ void kb_destroy(kb_handle* h) {
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_chunk) if (e) cudaEventDestroy(e);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
+  if (h->ev_front_free) cudaEventDestroy(h->ev_front_free);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_posdef) cudaFreeHost(h->h_posdef);
@@ -563,6 +571,8 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (auto& e : h->ev_chunk) KB_CCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   KB_CCUDA(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
+  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_front_free, cudaEventDisableTiming));
   KB_CCUDA(h->set_col_q.upload(set_col_q, s));
   KB_CCUDA(h->set_col_t.upload(set_col_t, s));
   KB_CCUDA(h->cam_cols.upload(h->h_cam_cols, s));
@@ -615,6 +625,8 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(cudaMemsetAsync(h->e.p, 0, sizeof(double) * std::max<size_t>(1, 2 * (size_t)h->n_terms_local), s));
   KB_CCUDA(cudaMemsetAsync(h->camA.p, 0, sizeof(double) * C * C * 36, s));
   D.y_u = h->y_u.p; D.y_v = h->y_v.p; D.corner = h->corner.p; D.target = h->target.p;
+  h->front_u = h->y_u.p;
+  h->front_v = h->y_v.p;
   D.view_set = h->view_set.p; D.view_cam = h->view_cam.p; D.view_begin = h->view_begin.p; D.set_view = h->set_view.p;
   D.lin_off = h->lin_off.p; D.view_jbase = h->view_jbase.p; D.col_desc = h->col_desc.p;
   D.cam_params = h->cam_params.p; D.baselines = h->baselines.p; D.set_poses = h->set_poses.p;
@@ -730,8 +742,8 @@ kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const doub
   for (int k = 0; k < KB_STREAM_CHUNKS; ++k) {
     const int64_t lo = h->st_chunk_term[k], n = h->st_chunk_term[k + 1] - lo;
     if (n > 0) {
-      KB_CUDA(h, cudaMemcpyAsync(h->y_u.p + lo, y_u + lo, sizeof(double) * n, cudaMemcpyHostToDevice, h->copy_stream));
-      KB_CUDA(h, cudaMemcpyAsync(h->y_v.p + lo, y_v + lo, sizeof(double) * n, cudaMemcpyHostToDevice, h->copy_stream));
+      KB_CUDA(h, cudaMemcpyAsync(h->front_u + lo, y_u + lo, sizeof(double) * n, cudaMemcpyHostToDevice, h->copy_stream));
+      KB_CUDA(h, cudaMemcpyAsync(h->front_v + lo, y_v + lo, sizeof(double) * n, cudaMemcpyHostToDevice, h->copy_stream));
     }
     KB_CUDA(h, cudaEventRecord(h->ev_chunk[k], h->copy_stream));
   }
@@ -916,9 +928,47 @@ kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v
   if (h->n_ranks != 1 && !h->presharded)
     return fail(h, KB_ERR_STATE, "kb_set_observations needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
   KB_CUDA(h, cudaSetDevice(h->device));
-  KB_CUDA(h, cudaMemcpyAsync(h->y_u.p, y_u, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
-  KB_CUDA(h, cudaMemcpyAsync(h->y_v.p, y_v, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->front_u, y_u, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->front_v, y_v, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
   ++h->state_version;
+  return KB_OK;
+}
+
+// Double buffering of the measurements for callers that feed a new batch per step: the upload of the NEXT batch runs on the
+// copy stream into the back buffers while the current step computes on the front buffers.
+kb_status kb_prefetch_observations(kb_handle* h, const double* y_u, const double* y_v) {
+  if (h->n_ranks != 1 && !h->presharded)
+    return fail(h, KB_ERR_STATE, "kb_prefetch_observations needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
+  if (!y_u || !y_v) return fail(h, KB_ERR_INVALID_ARGUMENT, "null observation array");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  if (!h->back_u) {
+    KB_CUDA(h, h->y_u_back.alloc((size_t)h->n_terms_local));
+    KB_CUDA(h, h->y_v_back.alloc((size_t)h->n_terms_local));
+    h->back_u = h->y_u_back.p;
+    h->back_v = h->y_v_back.p;
+  }
+  // the back buffers were the front ones until the last commit: wait for everything that was enqueued on them
+  if (h->front_free_recorded) KB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_front_free, 0));
+  KB_CUDA(h, cudaMemcpyAsync(h->back_u, y_u, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->copy_stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->back_v, y_v, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->copy_stream));
+  KB_CUDA(h, cudaEventRecord(h->ev_prefetch, h->copy_stream));
+  h->prefetch_pending = true;
+  return KB_OK;
+}
+
+kb_status kb_commit_observations(kb_handle* h) {
+  if (!h->prefetch_pending) return fail(h, KB_ERR_STATE, "kb_commit_observations without a pending kb_prefetch_observations");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  KB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_prefetch, 0));
+  std::swap(h->front_u, h->back_u);
+  std::swap(h->front_v, h->back_v);
+  h->d.y_u = h->front_u;
+  h->d.y_v = h->front_v;
+  KB_CUDA(h, cudaEventRecord(h->ev_front_free, h->stream));  // everything enqueued so far read the old front buffers
+  h->front_free_recorded = true;
+  h->prefetch_pending = false;
+  ++h->state_version;
+  if (h->lm_graph) { cudaGraphExecDestroy(h->lm_graph); h->lm_graph = nullptr; }  // captured with the old buffer addresses
   return KB_OK;
 }
 

@@ -326,3 +326,31 @@ def test_ragged_empty_and_missing_views_match_oracle(capi, oracle_lib, cfg, n_se
     so, to = oracle_lib.OracleProblem(p).optimize(KbOptimizerOptions.kalibr2_default())
     assert (sg.iterations, sg.failed_iterations, sg.linear_solver_failure) == (so.iterations, so.failed_iterations, so.linear_solver_failure)
     assert abs(sg.j_final - so.j_final) <= 1e-9 * so.j_final
+
+
+def test_double_buffered_observations(capi):
+    """kb_prefetch_observations / kb_commit_observations: the committed batch is the one evaluated, batches alternate between the
+    two device buffers, and a commit without a prefetch is a state error."""
+    p = make(2, 20)
+    rng = np.random.default_rng(11)
+    batches = [(np.ascontiguousarray(p.y_u + rng.normal(0, 0.3, p.y_u.shape)), np.ascontiguousarray(p.y_v + rng.normal(0, 0.3, p.y_v.shape)))
+               for _ in range(3)]
+    a = capi.B200SchurLinearSystemSolver(p)
+    b = capi.B200SchurLinearSystemSolver(p)
+    with pytest.raises(capi.KalibrB200Error):
+        a.commit_observations()
+    J0 = a.evaluate_error()
+    a.prefetch_observations(*batches[0])
+    assert a.evaluate_error() == J0          # not committed yet: still the original observations
+    for i, (yu, yv) in enumerate(batches):
+        a.commit_observations()
+        if i + 1 < len(batches):
+            a.prefetch_observations(*batches[i + 1])
+        b.set_observations(yu, yv)
+        Ja, Jb = a.evaluate_error(), b.evaluate_error()
+        assert Ja == Jb
+        assert np.array_equal(a.error_vector(), b.error_vector())
+        sa, _ = a.optimize(KbOptimizerOptions.kalibr2_default())
+        sb, _ = b.optimize(KbOptimizerOptions.kalibr2_default())
+        assert (sa.iterations, sa.j_final) == (sb.iterations, sb.j_final)
+        a.reset_state(); b.reset_state()
