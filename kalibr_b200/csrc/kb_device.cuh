@@ -112,6 +112,10 @@ constexpr int LIN_OFF_STRIDE = 4 + MAX_CAMS;  // pose_q, pose_t, proj, dist, bas
 struct StreamCtx {
   cudaStream_t stream;
   long long* launches;  // incremented per kernel launch
+  // optional: side streams + events so that the per-model launches of a mixed rig run concurrently (fork / join on `stream`)
+  cudaStream_t* side = nullptr;    // [NUM_MODELS]
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t* ev_join = nullptr;  // [NUM_MODELS]
 };
 
 // launchers (kb_kernels.cu); every one returns the cudaGetLastError() of its launches

@@ -112,6 +112,8 @@ struct kb_handle {
   int st_chunk_model_begin[KB_STREAM_CHUNKS][KB_NUM_MODELS + 1] = {};
   int64_t st_chunk_term[KB_STREAM_CHUNKS + 1] = {};
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t model_stream[KB_NUM_MODELS] = {};  // per-model launches of a mixed rig run concurrently (fork / join)
+  cudaEvent_t ev_fork = nullptr, ev_join[KB_NUM_MODELS] = {};
   cudaEvent_t ev_chunk[KB_STREAM_CHUNKS] = {}, ev_main = nullptr;
   // double-buffered observations: kb_prefetch_observations fills the back buffers on the copy stream while the front ones
   // are in use, kb_commit_observations swaps them
@@ -177,7 +179,13 @@ void shard_range(int n_sets, int n_ranks, int rank, int& lo, int& hi) {
   hi = lo + base + (rank < rem ? 1 : 0);
 }
 
-StreamCtx ctx(kb_handle* h) { return StreamCtx{h->stream, &h->launches}; }
+StreamCtx ctx(kb_handle* h) {
+  StreamCtx c{h->stream, &h->launches};
+  c.side = h->model_stream;
+  c.ev_fork = h->ev_fork;
+  c.ev_join = h->ev_join;
+  return c;
+}
 
 struct StageTimer {
   kb_handle* h;
@@ -278,6 +286,9 @@ void kb_destroy(kb_handle* h) {
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_chunk) if (e) cudaEventDestroy(e);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (auto& e : h->ev_join) if (e) cudaEventDestroy(e);
+  for (auto& st : h->model_stream) if (st) cudaStreamDestroy(st);
   if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
   if (h->ev_front_free) cudaEventDestroy(h->ev_front_free);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -571,6 +582,9 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (auto& e : h->ev_chunk) KB_CCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   KB_CCUDA(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (auto& e : h->ev_join) KB_CCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& st : h->model_stream) KB_CCUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   KB_CCUDA(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
   KB_CCUDA(cudaEventCreateWithFlags(&h->ev_front_free, cudaEventDisableTiming));
   KB_CCUDA(h->set_col_q.upload(set_col_q, s));

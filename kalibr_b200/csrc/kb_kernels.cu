@@ -868,25 +868,26 @@ __device__ __forceinline__ RedIndex red_index(const DevProblem& p, int i) {
   r.kind = 0; r.id = k; r.sub = i - p.intr_off[k];
   return r;
 }
-// "local Jacobian column" of reduced index ri as seen from camera k: a 16-vector c such that J_red = J_local * c.
-// Returns false when camera k does not depend on ri.
-__device__ __forceinline__ bool red_column(const DevProblem& p, const RedIndex& ri, int k, double col[GRAM_DIM]) {
-#pragma unroll
-  for (int a = 0; a < GRAM_DIM; ++a) col[a] = 0.0;
+// "local Jacobian column" of reduced index ri as seen from camera k: a 16-vector c such that J_red = J_local * c, either a
+// signed unit vector (intrinsics: column 6 + sub; the augmented rhs row: -e) or a dense vector over the six pose columns
+// (baseline: column `sub` of A_{id,k}).  Returns 0 when camera k does not depend on ri, 1 for a unit vector, 2 for a dense one.
+__device__ __forceinline__ int red_column(const DevProblem& p, const RedIndex& ri, int k, int& unit, double& sign, double dense[6]) {
   if (ri.kind == 0) {
-    if (ri.id != k) return false;
-    col[6 + ri.sub] = 1.0;
-    return true;
+    if (ri.id != k) return 0;
+    unit = 6 + ri.sub;
+    sign = 1.0;
+    return 1;
   }
   if (ri.kind == 1) {
-    if (ri.id >= k) return false;
+    if (ri.id >= k) return 0;
     const double* A = p.camA + ((size_t)k * p.n_cams + ri.id) * 36;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) col[a] = A[a * 6 + ri.sub];
-    return true;
+    for (int a = 0; a < 6; ++a) dense[a] = A[a * 6 + ri.sub];
+    return 2;
   }
-  col[E_COL] = -1.0;  // rhs = -J^T e
-  return true;
+  unit = E_COL;  // rhs = -J^T e
+  sign = -1.0;
+  return 1;
 }
 
 __global__ void __launch_bounds__(256) camera_block_kernel(DevProblem p) {
@@ -898,16 +899,32 @@ __global__ void __launch_bounds__(256) camera_block_kernel(DevProblem p) {
   const RedIndex ri = red_index(p, i), rj = red_index(p, j);
   double acc = 0.0;
   for (int k = 0; k < p.n_cams; ++k) {
-    double ci[GRAM_DIM], cj[GRAM_DIM];
-    if (!red_column(p, ri, k, ci)) continue;
-    if (!red_column(p, rj, k, cj)) continue;
+    int ui = 0, uj = 0;
+    double si = 1.0, sj = 1.0, di[6], dj[6];
+    const int ti = red_column(p, ri, k, ui, si, di);
+    if (!ti) continue;
+    const int tj = red_column(p, rj, k, uj, sj, dj);
+    if (!tj) continue;
     const double* G = p.sumG + (size_t)k * 256;
     double s = 0.0;
-    for (int a = 0; a < GRAM_DIM; ++a) {
-      if (ci[a] == 0.0) continue;
-      double t = 0.0;
-      for (int b = 0; b < GRAM_DIM; ++b) t += sumg_sym(G, a, b) * cj[b];
-      s += ci[a] * t;
+    if (ti == 1 && tj == 1) {
+      s = si * sj * sumg_sym(G, ui, uj);
+    } else if (ti == 1) {
+#pragma unroll
+      for (int b = 0; b < 6; ++b) s += sumg_sym(G, ui, b) * dj[b];
+      s *= si;
+    } else if (tj == 1) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) s += di[a] * sumg_sym(G, a, uj);
+      s *= sj;
+    } else {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        double t = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) t += sumg_sym(G, a, b) * dj[b];
+        s += di[a] * t;
+      }
     }
     acc += s;
   }
@@ -1586,6 +1603,33 @@ __global__ void lm_finish_kernel(LmCtrl* c) {
 // =========================================================================================================
 // launchers
 // =========================================================================================================
+// Per-model launches of a mixed rig: the first model with work stays on the main stream, the others fork onto side streams and
+// join back, so that launches which each fill only part of the GPU overlap.  `launch(m, ctx)` launches model m on ctx.stream.
+template <typename F>
+static cudaError_t for_each_model_concurrently(const int* begin /*[NUM_MODELS+1]*/, StreamCtx& s, F launch) {
+  int n_models = 0;
+  for (int m = 0; m < NUM_MODELS; ++m) n_models += begin[m + 1] > begin[m];
+  const bool fork = n_models > 1 && s.side && s.ev_fork && s.ev_join;
+  cudaError_t e;
+  if (fork && (e = cudaEventRecord(s.ev_fork, s.stream)) != cudaSuccess) return e;
+  bool first = true;
+  for (int m = 0; m < NUM_MODELS; ++m) {
+    if (begin[m + 1] <= begin[m]) continue;
+    if (!fork || first) {
+      if ((e = launch(m, s)) != cudaSuccess) return e;
+    } else {
+      StreamCtx side = s;
+      side.stream = s.side[m];
+      if ((e = cudaStreamWaitEvent(side.stream, s.ev_fork, 0)) != cudaSuccess) return e;
+      if ((e = launch(m, side)) != cudaSuccess) return e;
+      if ((e = cudaEventRecord(s.ev_join[m], side.stream)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(s.stream, s.ev_join[m], 0)) != cudaSuccess) return e;
+    }
+    first = false;
+  }
+  return cudaSuccess;
+}
+
 static int g_sm_count = 0;
 static int sm_count() {
   if (!g_sm_count) {
@@ -1605,20 +1649,27 @@ cudaError_t launch_prep(const DevProblem& p, StreamCtx& s) {
 }
 
 template <int MODEL>
-static void launch_evaluate_model(const DevProblem& p, const int* list, int n, StreamCtx& s) {
-  if (n <= 0) return;
+static cudaError_t launch_evaluate_model(const DevProblem& p, const int* list, int n, StreamCtx& s) {
+  if (n <= 0) return cudaSuccess;
   const int warps_per_cta = EVAL_THREADS / 32;
   const int grid = min((n + warps_per_cta - 1) / warps_per_cta, sm_count() * 8);
   evaluate_kernel<MODEL><<<grid, EVAL_THREADS, sizeof(double) * p.n_target * 3, s.stream>>>(p, list, n);
   KB_LAUNCHED(s);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int* mb, double* cost_out, StreamCtx& s) {
-  launch_evaluate_model<0>(p, view_list + mb[0], mb[1] - mb[0], s);
-  launch_evaluate_model<1>(p, view_list + mb[1], mb[2] - mb[1], s);
-  launch_evaluate_model<2>(p, view_list + mb[2], mb[3] - mb[2], s);
-  launch_evaluate_model<3>(p, view_list + mb[3], mb[4] - mb[3], s);
-  launch_evaluate_model<4>(p, view_list + mb[4], mb[5] - mb[4], s);
+  cudaError_t e = for_each_model_concurrently(mb, s, [&](int m, StreamCtx& c) -> cudaError_t {
+    switch (m) {
+      case 0: return launch_evaluate_model<0>(p, view_list + mb[0], mb[1] - mb[0], c);
+      case 1: return launch_evaluate_model<1>(p, view_list + mb[1], mb[2] - mb[1], c);
+      case 2: return launch_evaluate_model<2>(p, view_list + mb[2], mb[3] - mb[2], c);
+      case 3: return launch_evaluate_model<3>(p, view_list + mb[3], mb[4] - mb[3], c);
+      case 4: return launch_evaluate_model<4>(p, view_list + mb[4], mb[5] - mb[4], c);
+    }
+    return cudaSuccess;
+  });
+  if (e != cudaSuccess) return e;
   sum_kernel<<<1, 1024, 0, s.stream>>>(p.view_cost, p.n_views, cost_out);
   KB_LAUNCHED(s);
   return cudaGetLastError();
@@ -1650,12 +1701,16 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, co
     set_prep_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p);
     KB_LAUNCHED(s);
   }
-#define KB_LA(M)                                                                                      \
-  if ((e = write_e ? launch_la_model<M, true>(p, vmeta, slices, smb[M], smb[M + 1], s)                \
-                   : launch_la_model<M, false>(p, vmeta, slices, smb[M], smb[M + 1], s)) != cudaSuccess) return e;
-  KB_LA(0) KB_LA(1) KB_LA(2) KB_LA(3) KB_LA(4)
+  e = for_each_model_concurrently(smb, s, [&](int m, StreamCtx& c) -> cudaError_t {
+    switch (m) {
+#define KB_LA(M) \
+  case M: return write_e ? launch_la_model<M, true>(p, vmeta, slices, smb[M], smb[M + 1], c) : launch_la_model<M, false>(p, vmeta, slices, smb[M], smb[M + 1], c);
+      KB_LA(0) KB_LA(1) KB_LA(2) KB_LA(3) KB_LA(4)
 #undef KB_LA
-  return cudaGetLastError();
+    }
+    return cudaSuccess;
+  });
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // per-camera Gram sums + cost of the linearisation point (-> cost_out[0])
@@ -1695,11 +1750,16 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
     set_prep_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p);
     KB_LAUNCHED(s);
   }
+  e = for_each_model_concurrently(smb, s, [&](int m, StreamCtx& c) -> cudaError_t {
+    switch (m) {
 #define KB_LM(M) \
-  if ((e = launch_lm_model<M>(p, vmeta, slices, smb[M], smb[M + 1], jt, bfrag_pairs[M], counters + M, s)) != cudaSuccess) return e;
-  KB_LM(0) KB_LM(1) KB_LM(2) KB_LM(3) KB_LM(4)
+  case M: return launch_lm_model<M>(p, vmeta, slices, smb[M], smb[M + 1], jt, bfrag_pairs[M], counters + M, c);
+      KB_LM(0) KB_LM(1) KB_LM(2) KB_LM(3) KB_LM(4)
 #undef KB_LM
-  return cudaGetLastError();
+    }
+    return cudaSuccess;
+  });
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // V_v, b_v, W_v from the view blocks; U, b_c from the per-camera Gram sums
