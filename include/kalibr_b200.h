@@ -45,7 +45,9 @@ typedef enum {
   KB_OMNI_RADTAN = 2,    /* OmniProjection<RadialTangentialDistortion>     P=5 (xi,fu,fv,cu,cv)         D=4               */
   KB_EUCM_NONE = 3,      /* ExtendedUnifiedProjection<NoDistortion>        P=6 (alpha,beta,fu,fv,cu,cv) D=0 (active, 0-dim) */
   KB_DS_NONE = 4,        /* DoubleSphereProjection<NoDistortion>           P=6 (xi,alpha,fu,fv,cu,cv)   D=0 (active, 0-dim) */
-  KB_NUM_MODELS = 5
+  KB_PINHOLE_FOV = 5,    /* PinholeProjection<FovDistortion>               P=4 (fu,fv,cu,cv)            D=1 (w) */
+  KB_OMNI_NONE = 6,      /* OmniProjection<NoDistortion>                   P=5 (xi,fu,fv,cu,cv)         D=0 (active, 0-dim) */
+  KB_NUM_MODELS = 7      /* = the model table of kalibr2::CreateCalibrator (K2/include/kalibr2/CameraCalibrator.hpp:421-441) */
 } kb_camera_model;
 
 /* Design-variable insertion order of the three batch drivers

@@ -8,9 +8,9 @@
 
 namespace kb {
 
-enum : int { PINHOLE_RADTAN = 0, PINHOLE_EQUI = 1, OMNI_RADTAN = 2, EUCM_NONE = 3, DS_NONE = 4, NUM_MODELS = 5 };  // = kb_camera_model
-__host__ __device__ constexpr int model_P(int m) { return m == OMNI_RADTAN ? 5 : (m == EUCM_NONE || m == DS_NONE) ? 6 : 4; }
-__host__ __device__ constexpr int model_D(int m) { return (m == EUCM_NONE || m == DS_NONE) ? 0 : 4; }
+enum : int { PINHOLE_RADTAN = 0, PINHOLE_EQUI = 1, OMNI_RADTAN = 2, EUCM_NONE = 3, DS_NONE = 4, PINHOLE_FOV = 5, OMNI_NONE = 6, NUM_MODELS = 7 };  // = kb_camera_model
+__host__ __device__ constexpr int model_P(int m) { return (m == OMNI_RADTAN || m == OMNI_NONE) ? 5 : (m == EUCM_NONE || m == DS_NONE) ? 6 : 4; }
+__host__ __device__ constexpr int model_D(int m) { return (m == EUCM_NONE || m == DS_NONE || m == OMNI_NONE) ? 0 : m == PINHOLE_FOV ? 1 : 4; }
 
 constexpr int MAX_CAMS = 32;
 constexpr int CAM_PARAM_STRIDE = 10;

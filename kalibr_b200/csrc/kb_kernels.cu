@@ -1630,6 +1630,7 @@ static cudaError_t for_each_model_concurrently(const int* begin /*[NUM_MODELS+1]
   return cudaSuccess;
 }
 
+static_assert(NUM_MODELS == 7, "the per-model switch statements below list models 0..6");
 static int g_sm_count = 0;
 static int sm_count() {
   if (!g_sm_count) {
@@ -1666,6 +1667,8 @@ cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int
       case 2: return launch_evaluate_model<2>(p, view_list + mb[2], mb[3] - mb[2], c);
       case 3: return launch_evaluate_model<3>(p, view_list + mb[3], mb[4] - mb[3], c);
       case 4: return launch_evaluate_model<4>(p, view_list + mb[4], mb[5] - mb[4], c);
+      case 5: return launch_evaluate_model<5>(p, view_list + mb[5], mb[6] - mb[5], c);
+      case 6: return launch_evaluate_model<6>(p, view_list + mb[6], mb[7] - mb[6], c);
     }
     return cudaSuccess;
   });
@@ -1705,7 +1708,7 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, co
     switch (m) {
 #define KB_LA(M) \
   case M: return write_e ? launch_la_model<M, true>(p, vmeta, slices, smb[M], smb[M + 1], c) : launch_la_model<M, false>(p, vmeta, slices, smb[M], smb[M + 1], c);
-      KB_LA(0) KB_LA(1) KB_LA(2) KB_LA(3) KB_LA(4)
+      KB_LA(0) KB_LA(1) KB_LA(2) KB_LA(3) KB_LA(4) KB_LA(5) KB_LA(6)
 #undef KB_LA
     }
     return cudaSuccess;
@@ -1754,7 +1757,7 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
     switch (m) {
 #define KB_LM(M) \
   case M: return launch_lm_model<M>(p, vmeta, slices, smb[M], smb[M + 1], jt, bfrag_pairs[M], counters + M, c);
-      KB_LM(0) KB_LM(1) KB_LM(2) KB_LM(3) KB_LM(4)
+      KB_LM(0) KB_LM(1) KB_LM(2) KB_LM(3) KB_LM(4) KB_LM(5) KB_LM(6)
 #undef KB_LM
     }
     return cudaSuccess;

@@ -6,7 +6,7 @@
 //   PinholeProjection.hpp:99-145, 326-378     OmniProjection.hpp:118-180, 383-445
 //   ExtendedUnifiedProjection.hpp:133-198, 399-455 (incl. the fu-for-fv quirk Q4)
 //   DoubleSphereProjection.hpp:142-221, 445-503
-//   RadialTangentialDistortion.hpp:28-65, 153-182   EquidistantDistortion.hpp:32-183, 244-273
+//   RadialTangentialDistortion.hpp:28-65, 153-182   EquidistantDistortion.hpp:32-183, 244-273   FovDistortion.hpp:23-92, 133-170
 // Parameter order per model = kb_camera_model in include/kalibr_b200.h.
 #pragma once
 #include <cuda_runtime.h>
@@ -82,16 +82,61 @@ __device__ __forceinline__ void equidistant(const double* __restrict__ k, double
   my = y * s;
 }
 
+// field-of-view distortion (Devernay-Faugeras), one parameter w.  Same three regimes as the reference: w^2 < 1e-5 (identity),
+// r^2 < 1e-5 (constant factor 2 tan(w/2) / w), general.  CAM/FovDistortion.hpp:23-92 (value + point Jacobian), :133-170 (d/dw)
+template <bool WITH_JAC>
+__device__ __forceinline__ void fov_distortion(const double* __restrict__ k, double& mx, double& my, double Jm[2][2], double Jk[2][4]) {
+  const double w = k[0];
+  const double u = mx, v = my;
+  const double r_u = sqrt(u * u + v * v);
+  const double r2 = r_u * r_u;
+  const double tanwhalf = tan(0.5 * w);
+  const double tanwhalfsq = tanwhalf * tanwhalf;
+  const double atan_wrd = atan(2.0 * tanwhalf * r_u);
+  const bool w_small = w * w < 1e-5, r_small = r2 < 1e-5;
+  double r_rd;
+  if (w_small) r_rd = 1.0;
+  else if (r_small) r_rd = 2.0 * tanwhalf / w;
+  else r_rd = atan_wrd / (r_u * w);
+  if (WITH_JAC) {
+    if (w_small) {
+      Jm[0][0] = 1.0; Jm[0][1] = 0.0; Jm[1][0] = 0.0; Jm[1][1] = 1.0;
+      Jk[0][0] = 0.0; Jk[1][0] = 0.0;
+    } else if (r_small) {
+      const double f = 2.0 * tanwhalf / w;
+      Jm[0][0] = f; Jm[0][1] = 0.0; Jm[1][0] = 0.0; Jm[1][1] = f;
+      const double ch = cos(0.5 * w);
+      const double g = (w - sin(w)) / (w * w * ch * ch);
+      Jk[0][0] = g; Jk[1][0] = g;
+    } else {
+      const double uv2 = u * u + v * v;
+      const double a = atan_wrd / (w * r_u);                                  // atan / (w r)
+      const double b = atan_wrd / (w * (r_u * r_u * r_u));                    // atan / (w r^3)
+      const double c = 2.0 * tanwhalf / (w * uv2 * (4.0 * tanwhalfsq * uv2 + 1.0));
+      Jm[0][0] = a - u * u * b + u * u * c;
+      Jm[0][1] = u * v * c - u * v * b;
+      Jm[1][0] = Jm[0][1];
+      Jm[1][1] = a - v * v * b + v * v * c;
+      const double d = 2.0 * (0.5 * tanwhalfsq + 0.5) / (w * (4.0 * tanwhalfsq * r2 + 1.0));
+      const double e = atan_wrd / (w * w * r_u);
+      Jk[0][0] = u * d - u * e;
+      Jk[1][0] = v * d - v * e;
+    }
+  }
+  mx = u * r_rd;
+  my = v * r_rd;
+}
+
 // ---- projections ----------------------------------------------------------------------------------------
 // NEG = true returns the NEGATED Jacobians (-Jp, -Ji, -Jd): what the error term e = y - y_hat needs, with the sign folded
 // into the focal-length factors instead of a separate pass over the rows.
 template <int MODEL, bool WITH_JAC, bool NEG = false>
 struct Camera;
 
-// pinhole + (radtan | equi): params fu,fv,cu,cv,d0..d3
+// pinhole + (radtan | equi | fov): params fu,fv,cu,cv,d0..
 template <int MODEL, bool WITH_JAC, bool NEG>
 struct PinholeCamera {
-  static constexpr int P = 4, D = 4;
+  static constexpr int P = 4, D = model_D(MODEL);
   __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
     const double fu = prm[0], fv = prm[1], cu = prm[2], cv = prm[3];
     const double rz = 1.0 / p[2];
@@ -99,8 +144,10 @@ struct PinholeCamera {
     double Jm[2][2], Jk[2][4];
     if (MODEL == PINHOLE_RADTAN)
       radtan<WITH_JAC>(prm + 4, mx, my, Jm, Jk);
-    else
+    else if (MODEL == PINHOLE_EQUI)
       equidistant<WITH_JAC>(prm + 4, mx, my, Jm, Jk);
+    else
+      fov_distortion<WITH_JAC>(prm + 4, mx, my, Jm, Jk);
     if (WITH_JAC) {
       const double ju = NEG ? -fu : fu, jv = NEG ? -fv : fv;
       const double one = NEG ? -1.0 : 1.0;
@@ -114,7 +161,7 @@ struct PinholeCamera {
       L.Ji[0][0] = NEG ? -mx : mx; L.Ji[0][1] = 0.0; L.Ji[0][2] = one; L.Ji[0][3] = 0.0;
       L.Ji[1][0] = 0.0; L.Ji[1][1] = NEG ? -my : my; L.Ji[1][2] = 0.0; L.Ji[1][3] = one;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < D; ++j) {
         L.Jd[0][j] = ju * Jk[0][j];
         L.Jd[1][j] = jv * Jk[1][j];
       }
@@ -128,11 +175,13 @@ template <bool WITH_JAC, bool NEG>
 struct Camera<PINHOLE_RADTAN, WITH_JAC, NEG> : PinholeCamera<PINHOLE_RADTAN, WITH_JAC, NEG> {};
 template <bool WITH_JAC, bool NEG>
 struct Camera<PINHOLE_EQUI, WITH_JAC, NEG> : PinholeCamera<PINHOLE_EQUI, WITH_JAC, NEG> {};
-
-// omni + radtan: params xi,fu,fv,cu,cv,k1,k2,p1,p2
 template <bool WITH_JAC, bool NEG>
-struct Camera<OMNI_RADTAN, WITH_JAC, NEG> {
-  static constexpr int P = 5, D = 4;
+struct Camera<PINHOLE_FOV, WITH_JAC, NEG> : PinholeCamera<PINHOLE_FOV, WITH_JAC, NEG> {};
+
+// omni + (radtan | none): params xi,fu,fv,cu,cv[,k1,k2,p1,p2]
+template <int MODEL, bool WITH_JAC, bool NEG>
+struct OmniCamera {
+  static constexpr int P = 5, D = model_D(MODEL);
   __device__ __forceinline__ static void eval(const double* __restrict__ prm, const double p[3], Linearisation<P, D>& L) {
     const double xi = prm[0], fu = prm[1], fv = prm[2], cu = prm[3], cv = prm[4];
     const double d = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
@@ -152,8 +201,8 @@ struct Camera<OMNI_RADTAN, WITH_JAC, NEG> {
       Jn[1][2] = p[1] * s2;
     }
     const double jxi0 = -mx * d * rz, jxi1 = -my * d * rz;  // d(m)/d(xi) at the undistorted point
-    double Jm[2][2], Jk[2][4];
-    radtan<WITH_JAC>(prm + 5, mx, my, Jm, Jk);
+    double Jm[2][2] = {{1.0, 0.0}, {0.0, 1.0}}, Jk[2][4];
+    if (MODEL == OMNI_RADTAN) radtan<WITH_JAC>(prm + 5, mx, my, Jm, Jk);
     if (WITH_JAC) {
       const double ju = NEG ? -fu : fu, jv = NEG ? -fv : fv;
       const double one = NEG ? -1.0 : 1.0;
@@ -167,7 +216,7 @@ struct Camera<OMNI_RADTAN, WITH_JAC, NEG> {
       L.Ji[0][1] = NEG ? -mx : mx; L.Ji[0][2] = 0.0; L.Ji[0][3] = one; L.Ji[0][4] = 0.0;
       L.Ji[1][1] = 0.0; L.Ji[1][2] = NEG ? -my : my; L.Ji[1][3] = 0.0; L.Ji[1][4] = one;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < D; ++j) {
         L.Jd[0][j] = ju * Jk[0][j];
         L.Jd[1][j] = jv * Jk[1][j];
       }
@@ -176,6 +225,10 @@ struct Camera<OMNI_RADTAN, WITH_JAC, NEG> {
     L.y[1] = fv * my + cv;
   }
 };
+template <bool WITH_JAC, bool NEG>
+struct Camera<OMNI_RADTAN, WITH_JAC, NEG> : OmniCamera<OMNI_RADTAN, WITH_JAC, NEG> {};
+template <bool WITH_JAC, bool NEG>
+struct Camera<OMNI_NONE, WITH_JAC, NEG> : OmniCamera<OMNI_NONE, WITH_JAC, NEG> {};
 
 // EUCM (no distortion): params alpha,beta,fu,fv,cu,cv
 template <bool WITH_JAC, bool NEG>

@@ -11,10 +11,10 @@ from dataclasses import dataclass, field
 import numpy as np
 
 # kb_camera_model (reference model strings: kalibr2/CameraCalibrator.hpp:421-441)
-PINHOLE_RADTAN, PINHOLE_EQUI, OMNI_RADTAN, EUCM_NONE, DS_NONE = range(5)
-MODEL_NAMES = ["pinhole-radtan", "pinhole-equi", "omni-radtan", "eucm-none", "ds-none"]
-MODEL_P = [4, 4, 5, 6, 6]  # projection parameters
-MODEL_D = [4, 4, 4, 0, 0]  # distortion parameters (0-dim distortion DV stays active: SURVEY.md Q7)
+PINHOLE_RADTAN, PINHOLE_EQUI, OMNI_RADTAN, EUCM_NONE, DS_NONE, PINHOLE_FOV, OMNI_NONE = range(7)
+MODEL_NAMES = ["pinhole-radtan", "pinhole-equi", "omni-radtan", "eucm-none", "ds-none", "pinhole-fov", "omni-none"]
+MODEL_P = [4, 4, 5, 6, 6, 4, 5]  # projection parameters
+MODEL_D = [4, 4, 4, 0, 0, 1, 0]  # distortion parameters (0-dim distortion DV stays active: SURVEY.md Q7)
 
 # kb_driver_order
 ORDER_SINGLE, ORDER_STEREO, ORDER_RIG = range(3)

@@ -14,11 +14,13 @@ from .problem import (
     EUCM_NONE,
     MODEL_D,
     MODEL_P,
+    OMNI_NONE,
     OMNI_RADTAN,
     ORDER_RIG,
     ORDER_SINGLE,
     ORDER_STEREO,
     PINHOLE_EQUI,
+    PINHOLE_FOV,
     PINHOLE_RADTAN,
     Problem,
 )
@@ -36,6 +38,8 @@ TRUTH_PARAMS = {
     OMNI_RADTAN: ([0.9, 400.0, 400.0, 320.0, 240.0, -0.2, 0.13, 0.0005, 0.0005], (640, 480)),
     EUCM_NONE: ([0.63, 1.04, 380.0, 380.0, 640.0, 512.0], (1280, 1024)),
     DS_NONE: ([-0.18, 0.59, 313.0, 313.0, 640.0, 512.0], (1280, 1024)),
+    PINHOLE_FOV: ([400.0, 400.0, 320.0, 240.0, 1.0], (640, 480)),  # FovDistortion::getTestDistortion: w = 1 (src/FovDistortion.cpp:52-54)
+    OMNI_NONE: ([0.9, 400.0, 400.0, 320.0, 240.0], (640, 480)),
 }
 
 
@@ -118,24 +122,38 @@ def _equi(mx, my, k):
     return mx * s, my * s
 
 
+def _fov(mx, my, k):
+    w = k[0]
+    r = np.sqrt(mx * mx + my * my)
+    t = np.tan(0.5 * w)
+    if w * w < 1e-5:
+        s = np.ones_like(r)
+    else:
+        small = r * r < 1e-5
+        s = np.where(small, 2 * t / w, np.arctan(2 * t * r) / (np.where(small, 1.0, r) * w))
+    return mx * s, my * s
+
+
 def project(model: int, params, p: np.ndarray):
     """p: [..., 3] points in the camera frame -> (u, v, valid)."""
     x, y, z = p[..., 0], p[..., 1], p[..., 2]
     params = list(params)
-    if model in (PINHOLE_RADTAN, PINHOLE_EQUI):
+    if model in (PINHOLE_RADTAN, PINHOLE_EQUI, PINHOLE_FOV):
         fu, fv, cu, cv = params[:4]
         zs = np.where(z > 1e-9, z, 1.0)
         mx, my = x / zs, y / zs
-        mx, my = (_radtan if model == PINHOLE_RADTAN else _equi)(mx, my, params[4:8])
+        mx, my = {PINHOLE_RADTAN: _radtan, PINHOLE_EQUI: _equi, PINHOLE_FOV: _fov}[model](mx, my, params[4:8])
         return fu * mx + cu, fv * my + cv, z > 1e-3
-    if model == OMNI_RADTAN:
+    if model in (OMNI_RADTAN, OMNI_NONE):
         xi, fu, fv, cu, cv = params[:5]
         d = np.sqrt(x * x + y * y + z * z)
         fov = xi if xi <= 1.0 else 1.0 / xi
         den = z + xi * d
         ok = z > -(fov * d) * 0.9
         den = np.where(ok, den, 1.0)
-        mx, my = _radtan(x / den, y / den, params[5:9])
+        mx, my = x / den, y / den
+        if model == OMNI_RADTAN:
+            mx, my = _radtan(mx, my, params[5:9])
         return fu * mx + cu, fv * my + cv, ok
     if model == EUCM_NONE:
         al, be, fu, fv, cu, cv = params[:6]
@@ -166,6 +184,9 @@ CONFIGS = {
     3: (ORDER_RIG, [OMNI_RADTAN, EUCM_NONE, DS_NONE, PINHOLE_EQUI], 5000),
     4: (ORDER_RIG, [PINHOLE_RADTAN] * 8, 20000),
     5: (ORDER_RIG, [PINHOLE_RADTAN] * 16, 6250),
+    # not a BASELINE config: the two remaining rows of kalibr2::CreateCalibrator's model table next to a pinhole-radtan camera
+    6: (ORDER_RIG, [PINHOLE_FOV, OMNI_NONE, PINHOLE_RADTAN], 1000),
+    7: (ORDER_STEREO, [OMNI_NONE, PINHOLE_FOV], 1000),
 }
 
 
@@ -288,7 +309,7 @@ def make_problem(
     if perturb:
         for k, m in enumerate(models):
             P, D = MODEL_P[m], MODEL_D[m]
-            n_shape = {OMNI_RADTAN: 1, EUCM_NONE: 2, DS_NONE: 2}.get(m, 0)  # xi / alpha,beta / xi,alpha lead the vector
+            n_shape = {OMNI_RADTAN: 1, OMNI_NONE: 1, EUCM_NONE: 2, DS_NONE: 2}.get(m, 0)  # xi / alpha,beta / xi,alpha lead the vector
             cam0[k, :n_shape] += rng_cam_guess.normal(0, 0.01, size=n_shape)
             cam0[k, n_shape:P] *= 1 + rng_cam_guess.uniform(-0.02, 0.02, size=P - n_shape)
             cam0[k, P : P + D] += rng_cam_guess.normal(0, 0.01, size=D)

@@ -123,6 +123,74 @@ struct NoDistortion : Distortion {
   void setParameters(const std::vector<double>&) override {}
 };
 
+// CAM/FovDistortion.hpp:23-92 (value + point Jacobian, three regimes), :133-170 (parameter Jacobian);
+// aslam_cv/aslam_cameras/src/FovDistortion.cpp:24-27 (update), :52-54 (test value w = 1)
+struct FovDistortion : Distortion {
+  double w = 1.0;
+  int dims() const override { return 1; }
+  void distort(double y[2]) const override {
+    Mat J;
+    distort(y, J);
+  }
+  void distort(double y[2], Mat& J) const override {
+    J = Mat(2, 2);
+    const double r_u = std::sqrt(y[0] * y[0] + y[1] * y[1]);
+    const double r_u_cubed = r_u * r_u * r_u;
+    const double tanwhalf = std::tan(w / 2.);
+    const double tanwhalfsq = tanwhalf * tanwhalf;
+    const double atan_wrd = std::atan(2. * tanwhalf * r_u);
+    double r_rd;
+    if (w * w < 1e-5) {
+      r_rd = 1.0;
+    } else {
+      if (r_u * r_u < 1e-5) r_rd = 2. * tanwhalf / w;
+      else r_rd = atan_wrd / (r_u * w);
+    }
+    const double u = y[0], v = y[1];
+    if (w * w < 1e-5) {
+      J = Mat::Identity(2);
+    } else if (r_u * r_u < 1e-5) {
+      J = Mat::Identity(2);
+      J(0, 0) *= (2. * tanwhalf / w);
+      J(1, 1) *= (2. * tanwhalf / w);
+    } else {
+      const double duf_du = (atan_wrd) / (w * r_u) - (u * u * atan_wrd) / (w * r_u_cubed) +
+                            (2 * u * u * tanwhalf) / (w * (u * u + v * v) * (4 * tanwhalfsq * (u * u + v * v) + 1));
+      const double duf_dv = (2 * u * v * tanwhalf) / (w * (u * u + v * v) * (4 * tanwhalfsq * (u * u + v * v) + 1)) -
+                            (u * v * atan_wrd) / (w * r_u_cubed);
+      const double dvf_du = duf_dv;
+      const double dvf_dv = (atan_wrd) / (w * r_u) - (v * v * atan_wrd) / (w * r_u_cubed) +
+                            (2 * v * v * tanwhalf) / (w * (u * u + v * v) * (4 * tanwhalfsq * (u * u + v * v) + 1));
+      J(0, 0) = duf_du; J(0, 1) = duf_dv;
+      J(1, 0) = dvf_du; J(1, 1) = dvf_dv;
+    }
+    y[0] *= r_rd;
+    y[1] *= r_rd;
+  }
+  void distortParameterJacobian(const double y[2], Mat& J) const override {
+    J = Mat(2, 1);
+    const double tanwhalf = std::tan(w / 2.);
+    const double tanwhalfsq = tanwhalf * tanwhalf;
+    const double r_u = std::sqrt(y[0] * y[0] + y[1] * y[1]);
+    const double atan_wrd = std::atan(2. * tanwhalf * r_u);
+    const double u = y[0], v = y[1];
+    if (w * w < 1e-5) {
+      J(0, 0) = 0.0;
+      J(1, 0) = 0.0;
+    } else if (r_u * r_u < 1e-5) {
+      const double g = (w - std::sin(w)) / (w * w * std::cos(w / 2) * std::cos(w / 2));
+      J(0, 0) = g;
+      J(1, 0) = g;
+    } else {
+      J(0, 0) = (2 * u * (tanwhalfsq / 2 + 0.5)) / (w * (4 * tanwhalfsq * r_u * r_u + 1)) - (u * atan_wrd) / (w * w * r_u);
+      J(1, 0) = (2 * v * (tanwhalfsq / 2 + 0.5)) / (w * (4 * tanwhalfsq * r_u * r_u + 1)) - (v * atan_wrd) / (w * w * r_u);
+    }
+  }
+  void update(const double* v) override { w += v[0]; }
+  void getParameters(std::vector<double>& p) const override { p = {w}; }
+  void setParameters(const std::vector<double>& p) override { w = p[0]; }
+};
+
 // ---------------------------------------------------------------------------------------------------
 // CameraGeometry<Projection<Distortion>, GlobalShutter, NoMask> — CAM/CameraGeometry.hpp:232-247 forwards to the projection.
 struct Projection {
@@ -467,6 +535,8 @@ inline std::unique_ptr<Projection> makeCamera(int model, const double* params /*
     case 2: proj.reset(new OmniProjection()); dist.reset(new RadialTangentialDistortion()); break;
     case 3: proj.reset(new ExtendedUnifiedProjection()); dist.reset(new NoDistortion()); break;
     case 4: proj.reset(new DoubleSphereProjection()); dist.reset(new NoDistortion()); break;
+    case 5: proj.reset(new PinholeProjection()); dist.reset(new FovDistortion()); break;
+    case 6: proj.reset(new OmniProjection()); dist.reset(new NoDistortion()); break;
     default: return nullptr;
   }
   const int P = proj->dims(), D = dist->dims();

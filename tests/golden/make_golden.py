@@ -18,12 +18,15 @@ from kalibr_b200 import synthetic  # noqa: E402
 from kalibr_b200.problem import KbOptimizerOptions  # noqa: E402
 from oracle import oracle_api as oa  # noqa: E402
 
-CASES = {"cfg1_S3": (1, 3), "cfg2_S2": (2, 2), "cfg3_S2": (3, 2), "cfg4_S1": (4, 1)}
+CASES = {"cfg1_S3": (1, 3), "cfg2_S2": (2, 2), "cfg3_S2": (3, 2), "cfg4_S1": (4, 1), "cfg6_S2": (6, 2), "cfg7_S2": (7, 2)}
 
 
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]
     for name, (cfg, S) in CASES.items():
+        if only and name not in only:
+            continue
         p = synthetic.make_config(cfg, n_sets=S)
         o = oa.OracleProblem(p, oa.BLOCK_CHOLESKY, n_threads=1)
         J0 = o.evaluate_error()

@@ -15,7 +15,7 @@ def rel(a, b):
     return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
 
 
-@pytest.mark.parametrize("name", ["cfg1_S3", "cfg2_S2", "cfg3_S2", "cfg4_S1"])
+@pytest.mark.parametrize("name", ["cfg1_S3", "cfg2_S2", "cfg3_S2", "cfg4_S1", "cfg6_S2", "cfg7_S2"])
 def test_cuda_path_reproduces_golden(name):
     from kalibr_b200 import capi
 

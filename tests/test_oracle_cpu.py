@@ -12,10 +12,11 @@ import numpy as np
 import pytest
 
 from kalibr_b200 import synthetic
-from kalibr_b200.problem import DS_NONE, EUCM_NONE, MODEL_D, MODEL_P, OMNI_RADTAN, PINHOLE_EQUI, PINHOLE_RADTAN, KbOptimizerOptions
+from kalibr_b200.problem import (DS_NONE, EUCM_NONE, MODEL_D, MODEL_P, OMNI_NONE, OMNI_RADTAN, PINHOLE_EQUI, PINHOLE_FOV, PINHOLE_RADTAN,
+                                 KbOptimizerOptions)
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = [PINHOLE_RADTAN, PINHOLE_EQUI, OMNI_RADTAN, EUCM_NONE, DS_NONE]
+MODELS = [PINHOLE_RADTAN, PINHOLE_EQUI, OMNI_RADTAN, EUCM_NONE, DS_NONE, PINHOLE_FOV, OMNI_NONE]
 
 
 def test_kinematics_helpers(oracle_lib):
@@ -118,7 +119,7 @@ def _dense_from_blocks(col_ptr, block_row, value_ptr, values, col, dims):
     return H
 
 
-@pytest.mark.parametrize("cfg,n_sets", [(1, 5), (2, 4), (3, 3), (4, 2)])
+@pytest.mark.parametrize("cfg,n_sets", [(1, 5), (2, 4), (3, 3), (4, 2), (6, 3), (7, 4)])
 def test_hessian_is_JtJ_and_rhs_is_minus_Jte(oracle_lib, cfg, n_sets):
     p = synthetic.make_config(cfg, n_sets=n_sets)
     o = oracle_lib.OracleProblem(p, n_threads=2)
@@ -224,7 +225,7 @@ def test_zero_dim_distortion_blocks_are_in_the_pattern(oracle_lib):
     assert vals.size == sum(dims[br[b]] * dims[c] for c in range(dims.size) for b in range(cp[c], cp[c + 1]))
 
 
-@pytest.mark.parametrize("cfg,n_sets", [(1, 30), (2, 20), (3, 12)])
+@pytest.mark.parametrize("cfg,n_sets", [(1, 30), (2, 20), (3, 12), (6, 14), (7, 20)])
 def test_lm_converges_to_ground_truth(oracle_lib, cfg, n_sets):
     p = synthetic.make_config(cfg, n_sets=n_sets)
     o = oracle_lib.OracleProblem(p, n_threads=4)
@@ -259,7 +260,7 @@ def test_empty_and_ragged_views(oracle_lib):
     assert sol.linear_solver_failure == 0
 
 
-@pytest.mark.parametrize("name", ["cfg1_S3", "cfg2_S2", "cfg3_S2", "cfg4_S1"])
+@pytest.mark.parametrize("name", ["cfg1_S3", "cfg2_S2", "cfg3_S2", "cfg4_S1", "cfg6_S2", "cfg7_S2"])
 def test_oracle_reproduces_golden_fixtures(oracle_lib, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     p = synthetic.make_config(int(g["cfg"]), n_sets=int(g["n_sets"]))
