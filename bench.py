@@ -174,7 +174,9 @@ def workload_config(args, sets_per_rank, terms_per_rank, n_ranks):
         "workload": f"BASELINE.json configs[{args.config - 1}]: {len(models)}-camera rig ({', '.join(sorted(set(MODEL_NAMES[m] for m in models)))}), "
                     f"6x5 aprilgrid (120 corners), {sets_per_rank} synced sets per rank",
         "cameras": len(models), "synced_sets_per_rank": sets_per_rank, "terms_per_rank": terms_per_rank, "ranks": n_ranks,
-        "parallelism": f"sets sharded over {n_ranks} rank(s), one all-reduce of the reduced camera system per solve" if n_ranks > 1 else "single GPU",
+        "parallelism": (f"sets sharded over {n_ranks} rank(s); per solve one exchange of the reduced camera system "
+                        + ("(NCCL all-reduce)" if args.no_peer_exchange or n_ranks > 8 else "(NVLink peer stores fused into the producing kernel, summed by the consumer)"))
+        if n_ranks > 1 else "single GPU",
         "l2": "inputs larger than L2 (observations alone exceed 126 MB)" if terms_per_rank * 18 > 126e6 else "L2 flushed between steps (128 MiB+ scratch write)",
     }
 
@@ -192,6 +194,7 @@ def main():
     ap.add_argument("--cpu-regime", default="block", choices=["block", "sparse"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-peer-exchange", action="store_true", help="N > 1: keep the exchange steps on NCCL instead of NVLink peer stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -243,6 +246,14 @@ def main():
         nccl_id = bytes(idt.cpu().tolist())
     g = capi.B200SchurLinearSystemSolver(p, n_ranks=world, rank=rank, nccl_id=nccl_id, device=local_rank,
                                          n_sets_total=S_total if world > 1 else 0, set_offset=set_offset, n_terms_total=terms_total)
+    peer_exchange = False
+    if world > 1 and world <= 8 and not args.no_peer_exchange:
+        # NVLink peer exchange: all-gather the CUDA IPC handles of the ranks' exchange buffers, then attach
+        mine = torch.tensor(list(g.peer_exchange_handle()), dtype=torch.uint8, device="cuda")
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        g.attach_peers(b"".join(bytes(t.cpu().tolist()) for t in allh))
+        peer_exchange = True
     stream = torch.cuda.ExternalStream(g.cuda_stream(), device=torch.device("cuda", local_rank))
 
     def barrier():

@@ -120,6 +120,14 @@ KB_API int32_t kb_num_design_variables(const kb_handle* h); /* active DVs incl. 
 /* ≙ DesignVariable::blockIndex/columnBase/minimalDimensions (BE/include/aslam/backend/DesignVariable.hpp:18-145) */
 KB_API kb_status kb_get_dv_layout(const kb_handle* h, int32_t* column_base /*[n_dv]*/, int32_t* dims /*[n_dv]*/);
 
+/* Peer exchange over NVLink (optional, 2..8 ranks on one node, one process per GPU).  After kb_create every rank publishes the
+ * CUDA IPC handle of its exchange buffer; the caller all-gathers the 64-byte handles (rank order) and hands them to
+ * kb_attach_peers.  From then on the three exchange steps of an LM iteration (the reduced camera system, the solve scalars,
+ * the cost) no longer go through NCCL: the producing kernels store straight into every rank's buffer and raise epoch flags,
+ * the consuming kernels wait for the flags and sum in rank order.  Collective: every rank must attach. */
+KB_API kb_status kb_peer_exchange_handle(kb_handle* h, char out[64]);
+KB_API kb_status kb_attach_peers(kb_handle* h, const char* handles /*[n_ranks][64]*/);
+
 /* ---- per-iteration hot path ---------------------------------------------- */
 /* ≙ LinearSystemSolver::evaluateError (BE/src/LinearSystemSolver.cpp:81-92): returns J = sum e^T invR e
  *   over ALL ranks and fills the device copy of e().  use_m_estimator must be 0 (NoMEstimator only). */

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "kb_solve_system", "kb_lm_rho_denominator", "kb_apply_state_update", "kb_revert_last_state_update",
     "kb_default_optimizer_options", "kb_optimize", "kb_get_trace", "kb_set_solver_semantic", "kb_set_speculative_linearise", "kb_get_error_vector", "kb_get_rhs",
     "kb_linearise", "kb_jacobian_nnz", "kb_get_jacobian_ccs", "kb_get_hessian_blocks", "kb_get_camera_params", "kb_get_baselines",
-    "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
+    "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
 ]
 
@@ -87,6 +87,8 @@ def load_library() -> C.CDLL:
     L.kb_evaluate_error_streamed.argtypes = [vp, vp, vp, C.c_int32, vp]
     L.kb_prefetch_observations.argtypes = [vp, vp, vp]
     L.kb_commit_observations.argtypes = [vp]
+    L.kb_peer_exchange_handle.argtypes = [vp, C.c_char_p]
+    L.kb_attach_peers.argtypes = [vp, C.c_char_p]
     L.kb_reset_state.argtypes = [vp]
     L.kb_get_stage_ms.argtypes = [vp, vp]
     L.kb_enable_stage_timing.argtypes = [vp, C.c_int32]
@@ -276,6 +278,16 @@ class B200SchurLinearSystemSolver:
 
     def commit_observations(self):
         self._check(self._L.kb_commit_observations(self._h), "kb_commit_observations")
+
+    def peer_exchange_handle(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's exchange buffer (all-gather them, then attach_peers on every rank)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._L.kb_peer_exchange_handle(self._h, buf), "kb_peer_exchange_handle")
+        return buf.raw
+
+    def attach_peers(self, handles: bytes):
+        """handles: n_ranks x 64 bytes in rank order.  Switches the three exchange steps of an iteration from NCCL to NVLink stores."""
+        self._check(self._L.kb_attach_peers(self._h, handles), "kb_attach_peers")
 
     def reset_state(self):
         self._check(self._L.kb_reset_state(self._h), "kb_reset_state")

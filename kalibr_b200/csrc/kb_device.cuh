@@ -50,6 +50,27 @@ struct LmCtrl {
   int semantic, max_iterations;
 };
 
+// Peer exchange over NVLink (multi-rank, one process per GPU, kb_attach_peers): every rank maps the exchange buffer of every
+// other rank (CUDA IPC) and the producing kernel of each exchange step stores its contribution straight into the slot it owns
+// in EVERY rank's buffer, then raises a per-source epoch flag there; the consuming kernel waits for the flags and sums the
+// slots in rank order.  No collective library call sits between producer and consumer, and the sum order is fixed.
+//   exchange A: this rank's reduced camera system (schur_finalize_kernel -> px_reduce_system_kernel)
+//   exchange B: (rho denominator, max|dx|, pos-def) of a solve (rho_stage2_kernel -> px_combine_solve_kernel)
+//   exchange C: cost of an evaluation (gram_cost_kernel -> px_combine_cost_kernel)
+// Slots are double-buffered by epoch parity: a rank can run at most one exchange ahead of the slowest one.
+constexpr int PX_MAX_RANKS = 8;
+struct PeerXchg {
+  int enabled, n_ranks, rank, na2;  // na2 = n_aug^2 rounded up to a multiple of 2
+  double* base[PX_MAX_RANKS];       // base[r]: exchange buffer of rank r as mapped into this process (base[rank] = own)
+};
+// layout of an exchange buffer, in doubles
+__host__ __device__ inline size_t px_off_a(const PeerXchg& x, int parity, int src) { return ((size_t)parity * x.n_ranks + src) * x.na2; }
+__host__ __device__ inline size_t px_off_b(const PeerXchg& x, int parity, int src) { return (size_t)2 * x.n_ranks * x.na2 + ((size_t)parity * x.n_ranks + src) * 4; }
+__host__ __device__ inline size_t px_off_c(const PeerXchg& x, int parity, int src) { return (size_t)2 * x.n_ranks * x.na2 + 8 * x.n_ranks + ((size_t)parity * x.n_ranks + src) * 2; }
+// 64-bit words after the slots: flags [3][n_ranks] (written by the peers), then local: epoch[3], block counter, error flag
+__host__ __device__ inline size_t px_off_flags(const PeerXchg& x) { return (size_t)2 * x.n_ranks * x.na2 + 12 * x.n_ranks; }
+__host__ __device__ inline size_t px_doubles(const PeerXchg& x) { return px_off_flags(x) + 3 * x.n_ranks + 8; }
+
 struct DevProblem {
   // ---- structure (immutable after kb_create) ----
   int n_cams;
@@ -105,6 +126,7 @@ struct DevProblem {
   double* dx;           // [jcols] in design-variable order (poses of other ranks stay 0)
   unsigned int* n_invalid;  // terms whose projection bailed out (Q6)
   LmCtrl* ctrl;             // control block (device)
+  PeerXchg px;              // peer exchange (enabled after kb_attach_peers)
 };
 
 constexpr int LIN_OFF_STRIDE = 4 + MAX_CAMS;  // pose_q, pose_t, proj, dist, baseline j (q; t = +3)
@@ -125,7 +147,8 @@ int la_grid_warps();
 cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta /*(view,set,begin,end) in view-list order*/, const int4* slices,
                                       const int* slice_model_begin, bool write_e, bool with_set_prep,
                                       StreamCtx& s);
-cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range /*[n_cams][n_ranges][2]*/, int n_ranges, double* cost_out, StreamCtx& s);
+cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range /*[n_cams][n_ranges][2]*/, int n_ranges, double* cost_out,
+                                 bool exchange_cost /* also the producer of peer exchange C */, StreamCtx& s);
 cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta, const int4* slices, const int* slice_model_begin,
                                          const int* bfrag_pairs /*[NUM_MODELS]*/, unsigned int* counters /*[NUM_MODELS], device*/, double* jt_values,
@@ -136,7 +159,8 @@ cudaError_t launch_schur_finalize(const DevProblem& p, double damping, const dou
 cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int* cam_cols,
-                                   int include_shared, double* out2 /* [0]=sum, [1]=max|dx| */, StreamCtx& s);
+                                   int include_shared, double* out2 /* [0]=sum, [1]=max|dx| */,
+                                   const int* pos_def_for_exchange /* non-null: also the producer of peer exchange B */, StreamCtx& s);
 cudaError_t launch_pack_rank_scalars(double* pk /*[n_ranks][4], device*/, int rank, int n_ranks, const double* rho_max, const int* pos_def, StreamCtx& s);
 cudaError_t launch_apply_update(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, double* backup_cam,
                                 double* backup_base, double* backup_sets, StreamCtx& s);
@@ -146,6 +170,10 @@ cudaError_t launch_lm_post_solve(const DevProblem& p, const int* pos_def_flag, c
 cudaError_t launch_lm_post_eval(const DevProblem& p, double* trace, StreamCtx& s);
 cudaError_t launch_lm_revert(const DevProblem& p, const double* backup_cam, const double* backup_base, const double* backup_sets, StreamCtx& s);
 cudaError_t launch_lm_finish(const DevProblem& p, StreamCtx& s);
+// peer exchange consumers
+cudaError_t launch_px_reduce_system(const DevProblem& p, StreamCtx& s);
+cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max /*[2]*/, int* pos_def_flag, StreamCtx& s);
+cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx& s);
 int schur_num_partials(const DevProblem& p);
 size_t schur_partial_stride(const DevProblem& p);
 

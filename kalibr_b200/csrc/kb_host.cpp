@@ -131,6 +131,10 @@ struct kb_handle {
   DevBuf<LmCtrl> ctrl;          // control block of the device-resident LM loop (neutral flags outside kb_optimize)
   DevBuf<double> trace_dev;
   LmCtrl* h_ctrl = nullptr;     // pinned
+  // peer exchange over NVLink (kb_attach_peers): own buffer + the peers' buffers opened through CUDA IPC
+  DevBuf<double> px_buf;
+  void* px_opened[PX_MAX_RANKS] = {};
+  bool px_on = false;
   cudaGraphExec_t lm_graph = nullptr;  // one LM iteration, captured once per handle (single rank, stage timing off)
   bool lm_warm = false;                // a plain-launched iteration has run (first-launch attribute / allocation calls are done)
   const double* lm_graph_trace = nullptr;
@@ -295,6 +299,7 @@ void kb_destroy(kb_handle* h) {
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_posdef) cudaFreeHost(h->h_posdef);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  for (auto& q : h->px_opened) if (q) cudaIpcCloseMemHandle(q);
   if (h->lm_graph) cudaGraphExecDestroy(h->lm_graph);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -623,6 +628,15 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->scalars.alloc(8));
   KB_CCUDA(h->rank_slots.alloc(4 * (size_t)d->n_ranks));
   KB_CCUDA(h->ctrl.alloc(1));
+  D.px.enabled = 0;
+  D.px.n_ranks = d->n_ranks;
+  D.px.rank = d->rank;
+  D.px.na2 = (int)((NA * NA + 1) & ~(size_t)1);
+  if (d->n_ranks > 1 && d->n_ranks <= PX_MAX_RANKS) {
+    KB_CCUDA(h->px_buf.alloc(px_doubles(D.px)));
+    KB_CCUDA(cudaMemsetAsync(h->px_buf.p, 0, sizeof(double) * px_doubles(D.px), s));
+    D.px.base[d->rank] = h->px_buf.p;
+  }
   {
     LmCtrl neutral;
     std::memset(&neutral, 0, sizeof(neutral));
@@ -704,7 +718,7 @@ static kb_status run_linearise_assemble(kb_handle* h, bool write_e, int cost_slo
     StageTimer t(h, 1);
     KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->slices.p, h->slice_model_begin, write_e, true, c));
   }
-  KB_CUDA(h, launch_finalize_gram(h->d, h->cam_slice_range.p, 1, h->scalars.p + cost_slot, c));
+  KB_CUDA(h, launch_finalize_gram(h->d, h->cam_slice_range.p, 1, h->scalars.p + cost_slot, write_e /* the evaluate-time call */, c));
   h->la_version = h->state_version;
   return KB_OK;
 }
@@ -731,8 +745,12 @@ kb_status kb_evaluate_error(kb_handle* h, int32_t /*use_m_estimator: kalibr2 ins
       KB_CUDA(h, launch_prep(h->d, c));
       KB_CUDA(h, launch_evaluate(h->d, h->view_list.p, h->model_begin, h->scalars.p, c));
     }
-    kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
-    if (st != KB_OK) return st;
+    if (h->px_on && h->speculative) {  // gram_cost_kernel has already put this rank's cost into every rank's slot
+      KB_CUDA(h, launch_px_combine_cost(h->d, h->scalars.p, c));
+    } else {
+      kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
+      if (st != KB_OK) return st;
+    }
   }
   return finish_evaluate(h, out_cost);
 }
@@ -768,10 +786,14 @@ kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const doub
       KB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[k], 0));
       KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->st_slices.p, h->st_chunk_model_begin[k], true, k == 0, c));
     }
-    KB_CUDA(h, launch_finalize_gram(h->d, h->st_cam_slice_range.p, KB_STREAM_CHUNKS, h->scalars.p, c));
+    KB_CUDA(h, launch_finalize_gram(h->d, h->st_cam_slice_range.p, KB_STREAM_CHUNKS, h->scalars.p, true, c));
     h->la_version = h->state_version;
-    kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
-    if (st != KB_OK) return st;
+    if (h->px_on) {
+      KB_CUDA(h, launch_px_combine_cost(h->d, h->scalars.p, c));
+    } else {
+      kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
+      if (st != KB_OK) return st;
+    }
   }
   return finish_evaluate(h, out_cost);
 }
@@ -791,6 +813,37 @@ kb_status kb_build_system(kb_handle* h, int32_t /*use_m_estimator*/) {
   h->built = true;
   h->solved = false;
   return KB_OK;  // stage times are collected at the next synchronising call
+}
+
+// ---- peer exchange over NVLink ------------------------------------------------------------------------------------
+kb_status kb_peer_exchange_handle(kb_handle* h, char out[64]) {
+  if (!h->px_buf.p) return fail(h, KB_ERR_STATE, "no peer-exchange buffer (n_ranks must be 2..8)");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t ipc;
+  KB_CUDA(h, cudaIpcGetMemHandle(&ipc, h->px_buf.p));
+  static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(out, &ipc, 64);
+  return KB_OK;
+}
+
+kb_status kb_attach_peers(kb_handle* h, const char* handles /*[n_ranks][64], in rank order*/) {
+  if (!h->px_buf.p) return fail(h, KB_ERR_STATE, "no peer-exchange buffer (n_ranks must be 2..8)");
+  if (h->px_on) return fail(h, KB_ERR_STATE, "peers are already attached");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < h->n_ranks; ++r) {
+    if (r == h->rank) continue;
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, handles + 64 * (size_t)r, 64);
+    void* ptr = nullptr;
+    KB_CUDA(h, cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->px_opened[r] = ptr;
+    h->d.px.base[r] = (double*)ptr;
+  }
+  h->d.px.enabled = 1;
+  h->px_on = true;
+  if (h->lm_graph) { cudaGraphExecDestroy(h->lm_graph); h->lm_graph = nullptr; }
+  return KB_OK;
 }
 
 kb_status kb_set_speculative_linearise(kb_handle* h, int32_t on) {
@@ -815,8 +868,12 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
     StageTimer t(h, 3);
     KB_CUDA(h, launch_schur(h->d, damping, h->partials.p, h->n_partials, h->posdef.p, c));
     KB_CUDA(h, launch_schur_finalize(h->d, damping, h->partials.p, h->n_partials, true, c));
-    kb_status st = nccl_allreduce(h, h->Sred.p, (size_t)h->d.n_aug * h->d.n_aug, kNcclFloat64, kNcclSum);
-    if (st != KB_OK) return st;
+    if (h->px_on) {  // the partials have gone straight into every rank's buffer: sum them in rank order
+      KB_CUDA(h, launch_px_reduce_system(h->d, c));
+    } else {
+      kb_status st = nccl_allreduce(h, h->Sred.p, (size_t)h->d.n_aug * h->d.n_aug, kNcclFloat64, kNcclSum);
+      if (st != KB_OK) return st;
+    }
   }
   {
     StageTimer t(h, 4);
@@ -828,8 +885,11 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
   }
   {
     // dx^T (lambda dx + rhs) and max|dx| of this solution, so that getLmRho / applyStateUpdate need no further launch
-    KB_CUDA(h, launch_rho_denominator(h->d, h->lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2, c));
-    if (h->n_ranks > 1) {  // one packed all-reduce instead of three (min / sum / max)
+    KB_CUDA(h, launch_rho_denominator(h->d, h->lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2,
+                                      h->posdef.p, c));
+    if (h->px_on) {
+      KB_CUDA(h, launch_px_combine_solve(h->d, h->scalars.p + 2, h->posdef.p, c));
+    } else if (h->n_ranks > 1) {  // one packed all-reduce instead of three (min / sum / max)
       KB_CUDA(h, launch_pack_rank_scalars(h->rank_slots.p, h->rank, h->n_ranks, h->scalars.p + 2, h->posdef.p, c));
       kb_status st = nccl_allreduce(h, h->rank_slots.p, 4 * (size_t)h->n_ranks, kNcclFloat64, kNcclSum);
       if (st != KB_OK) return st;
@@ -838,6 +898,8 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
   }
   KB_CUDA(h, cudaMemcpyAsync(h->h_posdef, h->posdef.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 2, h->scalars.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (h->px_on)  // the exchange's time-out flag travels with the scalars
+    KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 7, h->px_buf.p + px_off_flags(h->d.px) + 3 * (size_t)h->n_ranks + 4, 8, cudaMemcpyDeviceToHost, h->stream));
   if (dx) {
     if (gather_dx && h->n_ranks > 1) {
       // poses are disjoint across ranks, the shared block is identical: sum with the shared block kept on rank 0 only
@@ -864,7 +926,7 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
   }
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   collect_stages(h);
-  if (h->n_ranks > 1) {  // combine the ranks' slots in rank order: identical on every rank
+  if (h->n_ranks > 1 && !h->px_on) {  // combine the ranks' slots in rank order: identical on every rank
     double rho = 0.0, mx = 0.0;
     int pd = 1;
     for (int r = 0; r < h->n_ranks; ++r) {
@@ -875,6 +937,11 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
     h->h_scalars[2] = rho;
     h->h_scalars[3] = mx;
     h->h_posdef[0] = pd;
+  }
+  if (h->px_on) {
+    unsigned long long err = 0;
+    std::memcpy(&err, h->h_scalars + 7, 8);
+    if (err) return fail(h, KB_ERR_NCCL, "peer exchange timed out: a rank did not reach the exchange step");
   }
   // un-augment: BlockCholesky subtracts lambda, not lambda^2 (BlockCholeskyLinearSystemSolver.cpp:91-97)
   if (h->semantic == 0) h->diag_residual += h->lambda * h->lambda - h->lambda;
@@ -889,7 +956,7 @@ kb_status kb_lm_rho_denominator(kb_handle* h, double lambda, double* out) {
   if (lambda != h->rho_lambda) {  // the solve already computed it for its own lambda (the LM policy's case)
     KB_CUDA(h, cudaSetDevice(h->device));
     StreamCtx c = ctx(h);
-    KB_CUDA(h, launch_rho_denominator(h->d, lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 6, c));
+    KB_CUDA(h, launch_rho_denominator(h->d, lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 6, nullptr, c));
     kb_status st = nccl_allreduce(h, h->scalars.p + 6, 1, kNcclFloat64, kNcclSum);
     if (st != KB_OK) return st;
     KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 6, h->scalars.p + 6, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1017,8 +1084,12 @@ static kb_status enqueue_lm_iteration(kb_handle* h) {
     StageTimer t(h, 3);
     KB_CUDA(h, launch_schur(D, -1.0, h->partials.p, h->n_partials, h->posdef.p, c));
     KB_CUDA(h, launch_schur_finalize(D, -1.0, h->partials.p, h->n_partials, true, c));
-    kb_status st = nccl_allreduce(h, D.Sred, (size_t)D.n_aug * D.n_aug, kNcclFloat64, kNcclSum);
-    if (st != KB_OK) return st;
+    if (h->px_on) {
+      KB_CUDA(h, launch_px_reduce_system(D, c));
+    } else {
+      kb_status st = nccl_allreduce(h, D.Sred, (size_t)D.n_aug * D.n_aug, kNcclFloat64, kNcclSum);
+      if (st != KB_OK) return st;
+    }
   }
   {
     StageTimer t(h, 4);
@@ -1028,13 +1099,15 @@ static kb_status enqueue_lm_iteration(kb_handle* h) {
     StageTimer t(h, 5);
     KB_CUDA(h, launch_backsub(D, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->posdef.p, c));
   }
-  KB_CUDA(h, launch_rho_denominator(D, -1.0, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2, c));
-  if (h->n_ranks > 1) {
+  KB_CUDA(h, launch_rho_denominator(D, -1.0, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2, h->posdef.p, c));
+  if (h->px_on) {
+    KB_CUDA(h, launch_px_combine_solve(D, h->scalars.p + 2, h->posdef.p, c));
+  } else if (h->n_ranks > 1) {
     KB_CUDA(h, launch_pack_rank_scalars(h->rank_slots.p, h->rank, h->n_ranks, h->scalars.p + 2, h->posdef.p, c));
     kb_status st = nccl_allreduce(h, h->rank_slots.p, 4 * (size_t)h->n_ranks, kNcclFloat64, kNcclSum);
     if (st != KB_OK) return st;
   }
-  KB_CUDA(h, launch_lm_post_solve(D, h->posdef.p, h->scalars.p + 2, h->rank_slots.p, h->n_ranks, c));
+  KB_CUDA(h, launch_lm_post_solve(D, h->posdef.p, h->scalars.p + 2, h->rank_slots.p, h->px_on ? 1 : h->n_ranks, c));
   {
     StageTimer t(h, 6);
     KB_CUDA(h, launch_apply_update(D, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->bk_cam.p, h->bk_base.p, h->bk_sets.p, c));
@@ -1046,9 +1119,13 @@ static kb_status enqueue_lm_iteration(kb_handle* h) {
       StageTimer t1(h, 1);
       KB_CUDA(h, launch_linearise_assemble(D, h->vmeta.p, h->slices.p, h->slice_model_begin, true, true, c));
     }
-    KB_CUDA(h, launch_finalize_gram(D, h->cam_slice_range.p, 1, &h->ctrl.p->cost_new, c));
-    kb_status st = nccl_allreduce(h, &h->ctrl.p->cost_new, 1, kNcclFloat64, kNcclSum);
-    if (st != KB_OK) return st;
+    KB_CUDA(h, launch_finalize_gram(D, h->cam_slice_range.p, 1, &h->ctrl.p->cost_new, true, c));
+    if (h->px_on) {
+      KB_CUDA(h, launch_px_combine_cost(D, &h->ctrl.p->cost_new, c));
+    } else {
+      kb_status st = nccl_allreduce(h, &h->ctrl.p->cost_new, 1, kNcclFloat64, kNcclSum);
+      if (st != KB_OK) return st;
+    }
   }
   KB_CUDA(h, launch_lm_post_eval(D, h->trace_dev.p, c));
   KB_CUDA(h, launch_lm_revert(D, h->bk_cam.p, h->bk_base.p, h->bk_sets.p, c));
@@ -1084,7 +1161,7 @@ static kb_status optimize_on_device(kb_handle* h, const kb_optimizer_options* o,
   // iterations are enqueued two at a time; the host only reads the control block back to see whether the loop has ended.
   // The kernel arguments of an iteration never change (everything data-dependent lives in the control block), so after
   // one plain-launched batch the iteration is captured into a CUDA graph and replayed: one launch per iteration instead of ~25.
-  const bool may_graph = h->n_ranks == 1 && !h->timing && !getenv("KB_NO_GRAPH");
+  const bool may_graph = (h->n_ranks == 1 || h->px_on) && !h->timing && !getenv("KB_NO_GRAPH");  // no NCCL call inside an iteration
   while (!h->h_ctrl->done) {
     if (may_graph && h->lm_warm && (!h->lm_graph || h->lm_graph_trace != h->trace_dev.p)) {
       if (h->lm_graph) { cudaGraphExecDestroy(h->lm_graph); h->lm_graph = nullptr; }

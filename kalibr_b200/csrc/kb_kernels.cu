@@ -178,6 +178,40 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ---- peer exchange primitives (kb_device.cuh: PeerXchg) -------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long* px_words(const PeerXchg& x, int r) {
+  return reinterpret_cast<unsigned long long*>(x.base[r] + px_off_flags(x));
+}
+// words: [which * n_ranks + src] flags | 3 n_ranks + which: local epoch | 3 n_ranks + 3: block counter | 3 n_ranks + 4: error
+__device__ __forceinline__ unsigned long long px_next_epoch(const PeerXchg& x, int which) { return px_words(x, x.rank)[3 * x.n_ranks + which] + 1ull; }
+__device__ __forceinline__ unsigned long long px_cur_epoch(const PeerXchg& x, int which) { return px_words(x, x.rank)[3 * x.n_ranks + which]; }
+// after this rank's stores of exchange `which`, epoch e, are fenced: publish
+__device__ __forceinline__ void px_signal(const PeerXchg& x, int which, unsigned long long e) {
+  px_words(x, x.rank)[3 * x.n_ranks + which] = e;
+  __threadfence_system();
+  for (int r = 0; r < x.n_ranks; ++r) st_release_sys(px_words(x, r) + which * x.n_ranks + x.rank, e);
+}
+// wait until rank src has published epoch e of exchange `which`; gives up after ~5 s (a peer that died must not hang the GPU)
+__device__ __forceinline__ void px_wait(const PeerXchg& x, int which, int src, unsigned long long e) {
+  const unsigned long long* f = px_words(x, x.rank) + which * x.n_ranks + src;
+  const long long t0 = clock64();
+  while (ld_acquire_sys(f) < e) {
+    if (clock64() - t0 > 10000000000ll) {
+      px_words(x, x.rank)[3 * x.n_ranks + 4] = 1ull;
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
 // =========================================================================================================
 // prep: per camera k, the constants shared by all of its views.
 // =========================================================================================================
@@ -933,12 +967,59 @@ __global__ void __launch_bounds__(256) camera_block_kernel(DevProblem p) {
 }
 
 // cost at the linearisation point = sum_k G_k[e][e]
-__global__ void gram_cost_kernel(DevProblem p, double* __restrict__ out) {
+__global__ void gram_cost_kernel(DevProblem p, double* __restrict__ out, int exchange) {
   if (threadIdx.x == 0 && blockIdx.x == 0 && !p.ctrl->done && !p.ctrl->skip_eval) {
     double s = 0.0;
     for (int k = 0; k < p.n_cams; ++k) s += p.sumG[(size_t)k * GRAM_SIZE + E_COL * GRAM_DIM + E_COL];
     out[0] = s;
+    if (p.px.enabled && exchange) {  // exchange C: this rank's cost into every rank's slot
+      const unsigned long long e = px_next_epoch(p.px, 2);
+      for (int r = 0; r < p.px.n_ranks; ++r) p.px.base[r][px_off_c(p.px, (int)(e & 1), p.px.rank)] = s;
+      __threadfence_system();
+      px_signal(p.px, 2, e);
+    }
   }
+}
+// exchange C consumer: total cost, summed in rank order
+__global__ void px_combine_cost_kernel(DevProblem p, double* __restrict__ out) {
+  if (p.ctrl->done || p.ctrl->skip_eval) return;
+  const unsigned long long e = px_cur_epoch(p.px, 2);
+  double s = 0.0;
+  for (int r = 0; r < p.px.n_ranks; ++r) {
+    px_wait(p.px, 2, r, e);
+    s += __ldcg(p.px.base[p.px.rank] + px_off_c(p.px, (int)(e & 1), r));
+  }
+  out[0] = s;
+}
+// exchange A consumer: the reduced camera system = the ranks' partials summed in rank order, spread over many CTAs
+__global__ void __launch_bounds__(256) px_reduce_system_kernel(DevProblem p) {
+  if (p.ctrl->done) return;
+  const unsigned long long e = px_cur_epoch(p.px, 0);
+  if (threadIdx.x < p.px.n_ranks) px_wait(p.px, 0, threadIdx.x, e);
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.n_aug * p.n_aug) return;
+  const double* slots = p.px.base[p.px.rank] + px_off_a(p.px, (int)(e & 1), 0) + idx;
+  double v = 0.0;
+  for (int r = 0; r < p.px.n_ranks; ++r) v += __ldcg(slots + (size_t)r * p.px.na2);
+  p.Sred[idx] = v;
+}
+// exchange B consumer: rho denominator (sum), max|dx| (max), pos-def (min) over the ranks, in rank order
+__global__ void px_combine_solve_kernel(DevProblem p, double* __restrict__ rho_max, int* __restrict__ pos_def) {
+  if (p.ctrl->done) return;
+  const unsigned long long e = px_cur_epoch(p.px, 1);
+  double rho = 0.0, mx = 0.0;
+  int pd = 1;
+  for (int r = 0; r < p.px.n_ranks; ++r) {
+    px_wait(p.px, 1, r, e);
+    const double* slot = p.px.base[p.px.rank] + px_off_b(p.px, (int)(e & 1), r);
+    rho += __ldcg(slot);
+    mx = fmax(mx, __ldcg(slot + 1));
+    if (__ldcg(slot + 2) < 0.5) pd = 0;
+  }
+  rho_max[0] = rho;
+  rho_max[1] = mx;
+  pos_def[0] = pd;
 }
 
 // =========================================================================================================
@@ -1128,10 +1209,36 @@ __global__ void __launch_bounds__(256) schur_finalize_kernel(DevProblem p, const
   }
   s += __shfl_down_sync(0xffffffffu, s, 2);
   s += __shfl_down_sync(0xffffffffu, s, 1);
+  if (!p.px.enabled) {
+    if (live && seg == 0) {
+      const double v = p.U[(size_t)i * n + j] - s;
+      p.Sred[(size_t)i * n + j] = v;
+      p.Sred[(size_t)j * n + i] = v;
+    }
+    return;
+  }
+  // exchange A: the partial goes straight into this rank's slot of EVERY rank's exchange buffer (NVLink stores); the last
+  // block to finish publishes the epoch.  reduced_solve_kernel sums the slots.
+  if (p.ctrl->done) return;
+  const unsigned long long e = px_next_epoch(p.px, 0);
   if (live && seg == 0) {
     const double v = p.U[(size_t)i * n + j] - s;
-    p.Sred[(size_t)i * n + j] = v;
-    p.Sred[(size_t)j * n + i] = v;
+    const size_t off = px_off_a(p.px, (int)(e & 1), p.px.rank);
+    for (int r = 0; r < p.px.n_ranks; ++r) {
+      double* dst = p.px.base[r] + off;
+      dst[(size_t)i * n + j] = v;
+      dst[(size_t)j * n + i] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* words = px_words(p.px, p.px.rank);
+    __threadfence_system();  // cumulative: orders the block's stores (observed through the barrier) before the counter update
+    const unsigned long long prev = atomicAdd(words + 3 * p.px.n_ranks + 3, 1ull);
+    if (prev == gridDim.x - 1) {
+      words[3 * p.px.n_ranks + 3] = 0ull;
+      px_signal(p.px, 0, e);
+    }
   }
 }
 
@@ -1406,13 +1513,29 @@ __global__ void __launch_bounds__(256) rho_stage1_kernel(DevProblem p, double la
   block_sum_max(s, m, sh_s, sh_m);
   if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s; partial[2 * blockIdx.x + 1] = m; }
 }
-__global__ void __launch_bounds__(RHO_BLOCKS) rho_stage2_kernel(const LmCtrl* __restrict__ ctrl, const double* __restrict__ partial, int n, double* __restrict__ out) {
+__global__ void __launch_bounds__(RHO_BLOCKS) rho_stage2_kernel(const LmCtrl* __restrict__ ctrl, PeerXchg px, const int* __restrict__ pos_def,
+                                                                const double* __restrict__ partial, int n, double* __restrict__ out) {
   __shared__ double sh_s[32], sh_m[32];
   if (ctrl->done) return;
   double s = threadIdx.x < n ? partial[2 * threadIdx.x] : 0.0;
   double m = threadIdx.x < n ? partial[2 * threadIdx.x + 1] : 0.0;
   block_sum_max(s, m, sh_s, sh_m);
-  if (threadIdx.x == 0) { out[0] = s; out[1] = m; }
+  if (threadIdx.x == 0) {
+    out[0] = s;
+    out[1] = m;
+    if (px.enabled) {  // exchange B: (rho partial, max|dx|, pos-def) into every rank's slot
+      const unsigned long long e = px_next_epoch(px, 1);
+      const double pd = (double)pos_def[0];
+      for (int r = 0; r < px.n_ranks; ++r) {
+        double* slot = px.base[r] + px_off_b(px, (int)(e & 1), px.rank);
+        slot[0] = s;
+        slot[1] = m;
+        slot[2] = pd;
+      }
+      __threadfence_system();
+      px_signal(px, 1, e);
+    }
+  }
 }
 
 // Multi-rank: every rank drops (rho partial, max|dx|, pos-def flag) into its own slot of a zeroed [n_ranks][4] array; ONE
@@ -1717,10 +1840,10 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, co
 }
 
 // per-camera Gram sums + cost of the linearisation point (-> cost_out[0])
-cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, int n_ranges, double* cost_out, StreamCtx& s) {
+cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, int n_ranges, double* cost_out, bool exchange_cost, StreamCtx& s) {
   finalize_gram_kernel<<<p.n_cams, GRAM_TILES * FG_GROUPS, 0, s.stream>>>(p, cam_slice_range, n_ranges);
   KB_LAUNCHED(s);
-  gram_cost_kernel<<<1, 32, 0, s.stream>>>(p, cost_out);
+  gram_cost_kernel<<<1, 32, 0, s.stream>>>(p, cost_out, exchange_cost ? 1 : 0);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -1852,7 +1975,7 @@ cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int*
 }
 
 cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int*, int include_shared,
-                                   double* out2, StreamCtx& s) {
+                                   double* out2, const int* pos_def_for_exchange, StreamCtx& s) {
   static double* partial = nullptr;
   if (!partial) {
     cudaError_t e = cudaMalloc(&partial, sizeof(double) * 2 * RHO_BLOCKS);
@@ -1861,7 +1984,9 @@ cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int
   const int blocks = max(1, min(RHO_BLOCKS, (p.n_sets + 255) / 256));
   rho_stage1_kernel<<<blocks, 256, 0, s.stream>>>(p, lambda, set_col_q, set_col_t, include_shared, partial);
   KB_LAUNCHED(s);
-  rho_stage2_kernel<<<1, RHO_BLOCKS, 0, s.stream>>>(p.ctrl, partial, blocks, out2);
+  PeerXchg px = p.px;
+  if (!pos_def_for_exchange) px.enabled = 0;  // a rho query outside a solve is not an exchange step
+  rho_stage2_kernel<<<1, RHO_BLOCKS, 0, s.stream>>>(p.ctrl, px, pos_def_for_exchange, partial, blocks, out2);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -1872,6 +1997,21 @@ cudaError_t launch_pack_rank_scalars(double* pk, int rank, int n_ranks, const do
   return cudaGetLastError();
 }
 
+cudaError_t launch_px_reduce_system(const DevProblem& p, StreamCtx& s) {
+  px_reduce_system_kernel<<<(p.n_aug * p.n_aug + 255) / 256, 256, 0, s.stream>>>(p);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max, int* pos_def_flag, StreamCtx& s) {
+  px_combine_solve_kernel<<<1, 1, 0, s.stream>>>(p, rho_max, pos_def_flag);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx& s) {
+  px_combine_cost_kernel<<<1, 1, 0, s.stream>>>(p, cost);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
 cudaError_t launch_lm_pre_solve(const DevProblem& p, int* pos_def_flag, StreamCtx& s) {
   lm_pre_solve_kernel<<<1, 1, 0, s.stream>>>(p.ctrl, pos_def_flag);
   KB_LAUNCHED(s);

@@ -23,10 +23,20 @@ def fresh_nccl_id():
 def rel(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
 
+def attach_peers(g):
+    """all-gather the CUDA IPC handles of the exchange buffers and attach (NVLink peer exchange instead of NCCL)"""
+    mine = torch.tensor(list(g.peer_exchange_handle()), dtype=torch.uint8, device="cuda")
+    allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(allh, mine)
+    g.attach_peers(b"".join(bytes(t.cpu().tolist()) for t in allh))
+
 ok_all = True
-for cfg, S in [(2, 9), (3, 7), (4, 10), (5, 5)]:
+use_px = os.environ.get("KB_PEER_EXCHANGE", "1") != "0" and world <= 8
+for cfg, S in [(2, 9), (3, 7), (4, 10), (5, 5), (6, 8)]:
     p = synthetic.make_config(cfg, n_sets=S)
     g = capi.B200SchurLinearSystemSolver(p, n_ranks=world, rank=rank, nccl_id=fresh_nccl_id(), device=lr)
+    if use_px:
+        attach_peers(g)
     J = g.evaluate_error()
     g.build_system()
     g.set_constant_conditioner(10.0)
@@ -48,7 +58,7 @@ for cfg, S in [(2, 9), (3, 7), (4, 10), (5, 5)]:
                  jfinal=abs(sol.j_final - osol.j_final) / osol.j_final, cam=rel(cam, o2.camera_params()))
         good = r["J"] < 1e-11 and r["dx"] < 1e-7 and r["rhs"] < 1e-9 and r["rho"] < 1e-7 and sol.iterations == osol.iterations and r["jfinal"] < 1e-9 and r["cam"] < 1e-6 and ok == ook
         ok_all &= good
-        print(f"cfg{cfg} S={S} world={world}: {'OK' if good else 'MISMATCH'} {r}", flush=True)
+        print(f"cfg{cfg} S={S} world={world} peer_exchange={use_px}: {'OK' if good else 'MISMATCH'} {r}", flush=True)
     g.close()
 dist.barrier()
 if rank == 0:
