@@ -1,18 +1,23 @@
 // Hand-written sm_100a kernels of the batch-calibration hot path.
 //
-//   prep            per-linearisation camera-chain constants (T_cam_k_cam_0, boxTimes products, baseline adjoints)
-//   evaluate        K5: residual-only pass, cost                     ≙ BE/src/LinearSystemSolver.cpp:12-23, 81-92
+//   prep / set_prep   per-linearisation constants: camera chain (T_cam_k_cam_0, boxTimes products, baseline adjoints), per-set
+//                     inverse pose and P_v
+//   evaluate          K5: residual-only pass, cost (non-speculative mode)   ≙ BE/src/LinearSystemSolver.cpp:12-23, 81-92
 //   linearise_assemble  K1+K2 fused: per term chain + projection + 3 Jacobians, per view Gram block
-//                   G = [J_xi|J_proj|J_dist|e]^T [..] on the FP64 tensor pipe (DMMA m8n8k4)
-//                                                                     ≙ ReprojectionError.hpp:63-77 + JacobianContainer.cpp:103-167
-//   linearise_materialise  K1 with J written out in the reference's CCS J^T layout
-//                                                                     ≙ CompressedColumnJacobianTransposeBuilder.hpp:59-100
-//   set_reduce      per set: V_v, b_v, W_v from the view blocks       ≙ sparse_block_matrix.hpp:121-143 (block += J1^T J2)
-//   finalize_gram/camera_block  U, b_c, cost
-//   schur           K3a: S = U - sum_v W_v (V_v + d I)^-1 W_v^T on DMMA ≙ BE/src/sparse_matrix_functions.cpp:8-60
-//   reduced_solve   K3b: dense Cholesky of the reduced system          ≙ linear_solver_cholmod.h:70-112
-//   backsub         K3c: dx_v = (V_v + d I)^-1 (b_v - W_v^T dx_c)       ≙ sparse_matrix_functions.cpp:64-83
-//   apply_update / rho                                                 ≙ Optimizer2.cpp:290-318, LevenbergMarquardtTrustRegionPolicy.cpp:107-113
+//                     G = [J_xi|J_proj|J_dist|e]^T [..] on the FP64 tensor pipe (DMMA m8n8k4)
+//                                                                       ≙ ReprojectionError.hpp:63-77 + JacobianContainer.cpp:103-167
+//   linearise_materialise  K1 with J written out in the reference's CCS J^T layout (J = A B on the tensor pipe)
+//                                                                       ≙ CompressedColumnJacobianTransposeBuilder.hpp:59-100
+//   set_reduce        per set: V_v, b_v, W_v from the views' Gram tiles (register-resident DMMA chain)
+//                                                                       ≙ sparse_block_matrix.hpp:121-143 (block += J1^T J2)
+//   finalize_gram / camera_block / gram_cost  U, b_c, cost
+//   pose_factor / schur / schur_finalize  K3a: S = U - sum_v W_v (V_v + d I)^-1 W_v^T on DMMA  ≙ BE/src/sparse_matrix_functions.cpp:8-60
+//   reduced_solve     K3b: dense Cholesky of the reduced system            ≙ linear_solver_cholmod.h:70-112
+//   backsub           K3c: dx_v = (V_v + d I)^-1 (b_v - W_v^T dx_c)         ≙ sparse_matrix_functions.cpp:64-83
+//   rho / apply_update                                                   ≙ LevenbergMarquardtTrustRegionPolicy.cpp:107-113, Optimizer2.cpp:290-318
+//   lm_pre_solve / lm_post_solve / lm_post_eval / lm_revert / lm_finish  device-resident LM loop
+//                                                                       ≙ Optimizer2.cpp:215-266, LevenbergMarquardtTrustRegionPolicy.cpp:50-113
+//   px_*              NVLink peer exchange between ranks (producers are fused into schur_finalize / rho_stage2 / gram_cost)
 #include <cstdio>
 #include <cstdlib>
 
@@ -1754,15 +1759,21 @@ static cudaError_t for_each_model_concurrently(const int* begin /*[NUM_MODELS+1]
 }
 
 static_assert(NUM_MODELS == 7, "the per-model switch statements below list models 0..6");
-static int g_sm_count = 0;
+// launch-time caches are kept per device, so that several handles on different GPUs can live in one process
+constexpr int MAX_DEVICES = 64;
+static int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & (MAX_DEVICES - 1);
+}
 static int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+  static int count[MAX_DEVICES] = {};
+  const int dev = cur_device();
+  if (!count[dev]) {
+    cudaDeviceGetAttribute(&count[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (count[dev] <= 0) count[dev] = 148;
   }
-  return g_sm_count;
+  return count[dev];
 }
 #define KB_LAUNCHED(s) (++*(s).launches)
 
@@ -1807,7 +1818,8 @@ template <int MODEL, bool WRITE_E>
 static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const int4* slices, int lo, int hi, StreamCtx& s) {
   if (hi <= lo) return cudaSuccess;
   const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[MAX_DEVICES] = {};
+  size_t& attr_smem = attr_smem_dev[cur_device()];
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(linearise_assemble_kernel<MODEL, WRITE_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1853,7 +1865,8 @@ static cudaError_t launch_lm_model(const DevProblem& p, const int4* vmeta, const
                                    unsigned int* counter, StreamCtx& s) {
   if (hi <= lo) return cudaSuccess;
   const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + (size_t)LM_WARPS * (XT_WARP_DOUBLES + bfrag_pairs * 32 + 36 + SETPREP_STRIDE));
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[MAX_DEVICES] = {};
+  size_t& attr_smem = attr_smem_dev[cur_device()];
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(linearise_materialise_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1921,7 +1934,8 @@ template <int WARPS, int MAX_PAIRS>
 static cudaError_t launch_schur_t(const DevProblem& p, double* partials, int n_partials, StreamCtx& s) {
   const int n_pad = ((p.n_aug + 7) >> 3) * 8;
   const size_t smem = sizeof(double) * (2 * (size_t)n_pad * SC_LD + 2 * SC_SETS * 36);
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[MAX_DEVICES] = {};
+  size_t& attr_smem = attr_smem_dev[cur_device()];
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(schur_kernel<WARPS, MAX_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1956,7 +1970,8 @@ cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const
 cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s) {
   const size_t n_rows = ((p.n_aug + RS_NB - 1) / RS_NB) * RS_NB + RS_NB;
   const size_t smem = sizeof(double) * (n_rows * (n_rows + 1) / 2 + 2 * n_rows);
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[MAX_DEVICES] = {};
+  size_t& attr_smem = attr_smem_dev[cur_device()];
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1976,7 +1991,8 @@ cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int*
 
 cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int*, int include_shared,
                                    double* out2, const int* pos_def_for_exchange, StreamCtx& s) {
-  static double* partial = nullptr;
+  static double* partial_dev[MAX_DEVICES] = {};
+  double*& partial = partial_dev[cur_device()];
   if (!partial) {
     cudaError_t e = cudaMalloc(&partial, sizeof(double) * 2 * RHO_BLOCKS);
     if (e != cudaSuccess) return e;
