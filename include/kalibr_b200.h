@@ -178,6 +178,33 @@ KB_API kb_status kb_set_solver_semantic(kb_handle* h, int32_t semantic);
  * only has to reduce the view blocks.  Off: kb_evaluate_error runs the residual-only kernel. Results are identical. */
 KB_API kb_status kb_set_speculative_linearise(kb_handle* h, int32_t on);
 
+/* ---- marginal analysis of the calibration block --------------------------------
+ * ≙ aslam::calibration::LinearSolver::analyzeMarginal (aslam_incremental_calibration/incremental_calibration/src/core/
+ *   LinearSolver.cpp:466-528) — what IncrementalEstimator::addBatch asks of its solver after every re-optimisation
+ *   (src/core/IncrementalEstimator.cpp:404-433): the information matrix of the camera-side variables with the set poses
+ *   marginalised out, Omega = A_r^T A_r - (A_r^T Q)(A_r^T Q)^T, is exactly the undamped Schur-reduced camera system of this
+ *   path; its singular values, numerical rank (tolerance sv[0] * eps_svd * n unless svd_tol is given: linalg.cpp:244-261),
+ *   gap and log2-sum over the first `rank` values (LinearSolver.cpp:196-200; information gain = half the difference of two
+ *   such sums) come from a one-sided Jacobi iteration on the device.  Linearises at the current state and rebuilds the system
+ *   (like kb_build_system); a following kb_solve_system needs no further build. */
+typedef struct {
+  double eps_svd; /* std::numeric_limits<double>::epsilon() (LinearSolverOptions.cpp:33) */
+  double svd_tol; /* -1: derive from eps_svd (LinearSolverOptions.cpp:35) */
+} kb_marginal_options;
+typedef struct {
+  int32_t n;               /* dimension of the calibration block (= camera-side columns) */
+  int32_t rank;            /* ≙ getSVDRank */
+  int32_t rank_deficiency; /* ≙ getSVDRankDeficiency */
+  double tolerance;        /* ≙ getSVDTolerance */
+  double sv_log2_sum;      /* ≙ getSingularValuesLog2Sum */
+  double sv_gap;           /* ≙ getSvGap (inf when full rank) */
+} kb_marginal_result;
+KB_API void kb_default_marginal_options(kb_marginal_options* o);
+/* singular_values: [n] descending; V (may be NULL): [n][n] row-major, column k = k-th right singular vector (≙ getRowSpace /
+ * getNullSpace = its first rank / remaining columns); columns (may be NULL): [n] design-variable column of each row of V */
+KB_API kb_status kb_analyze_marginal(kb_handle* h, const kb_marginal_options* o, kb_marginal_result* out, double* singular_values,
+                                     double* V, int32_t* columns);
+
 /* ---- read-back (parity / results) ----------------------------------------- */
 KB_API kb_status kb_get_error_vector(kb_handle* h, double* e /*[2*local terms]*/);      /* ≙ LinearSystemSolver::e() : -sqrtInvR^T e */
 KB_API kb_status kb_get_rhs(kb_handle* h, double* rhs /*[jcols]*/);                     /* ≙ LinearSystemSolver::rhs() */

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "kb_solve_system", "kb_lm_rho_denominator", "kb_apply_state_update", "kb_revert_last_state_update",
     "kb_default_optimizer_options", "kb_optimize", "kb_get_trace", "kb_set_solver_semantic", "kb_set_speculative_linearise", "kb_get_error_vector", "kb_get_rhs",
     "kb_linearise", "kb_jacobian_nnz", "kb_get_jacobian_ccs", "kb_get_hessian_blocks", "kb_get_camera_params", "kb_get_baselines",
-    "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
+    "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
 ]
 
@@ -87,6 +87,9 @@ def load_library() -> C.CDLL:
     L.kb_evaluate_error_streamed.argtypes = [vp, vp, vp, C.c_int32, vp]
     L.kb_prefetch_observations.argtypes = [vp, vp, vp]
     L.kb_commit_observations.argtypes = [vp]
+    L.kb_default_marginal_options.argtypes = [vp]
+    L.kb_default_marginal_options.restype = None
+    L.kb_analyze_marginal.argtypes = [vp, vp, vp, vp, vp, vp]
     L.kb_peer_exchange_handle.argtypes = [vp, C.c_char_p]
     L.kb_attach_peers.argtypes = [vp, C.c_char_p]
     L.kb_reset_state.argtypes = [vp]
@@ -278,6 +281,17 @@ class B200SchurLinearSystemSolver:
 
     def commit_observations(self):
         self._check(self._L.kb_commit_observations(self._h), "kb_commit_observations")
+
+    def analyze_marginal(self, options=None):
+        """≙ LinearSolver::analyzeMarginal: (KbMarginalResult, singular values, V, DV column of each row of V)."""
+        from .problem import KbMarginalOptions, KbMarginalResult
+
+        o = options or KbMarginalOptions.default()
+        n = self.problem.n_c
+        res = KbMarginalResult()
+        sv, V, cols = np.zeros(n), np.zeros((n, n)), np.zeros(n, np.int32)
+        self._check(self._L.kb_analyze_marginal(self._h, C.byref(o), C.byref(res), _p(sv), _p(V), _p(cols)), "kb_analyze_marginal")
+        return res, sv, V, cols
 
     def peer_exchange_handle(self) -> bytes:
         """64-byte CUDA IPC handle of this rank's exchange buffer (all-gather them, then attach_peers on every rank)."""

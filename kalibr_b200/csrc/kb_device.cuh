@@ -170,6 +170,9 @@ cudaError_t launch_lm_post_solve(const DevProblem& p, const int* pos_def_flag, c
 cudaError_t launch_lm_post_eval(const DevProblem& p, double* trace, StreamCtx& s);
 cudaError_t launch_lm_revert(const DevProblem& p, const double* backup_cam, const double* backup_base, const double* backup_sets, StreamCtx& s);
 cudaError_t launch_lm_finish(const DevProblem& p, StreamCtx& s);
+// marginal analysis: one-sided Jacobi on the reduced system in p.Sred (G, V: scratch of (n_c + 1) * n_c doubles each)
+cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, double* sv_out /*[n_c]*/, double* V_out /*[n_c][n_c]*/, int* sweeps_out,
+                                StreamCtx& s);
 // peer exchange consumers
 cudaError_t launch_px_reduce_system(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max /*[2]*/, int* pos_def_flag, StreamCtx& s);

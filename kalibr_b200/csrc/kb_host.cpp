@@ -129,6 +129,8 @@ struct kb_handle {
   double* h_scalars = nullptr;  // pinned [8 + 4 * MAX_CAMS]: scalars, then the per-rank slots of the packed all-reduce
   DevBuf<double> rank_slots;    // [n_ranks][4]
   DevBuf<LmCtrl> ctrl;          // control block of the device-resident LM loop (neutral flags outside kb_optimize)
+  DevBuf<double> eig_G, eig_V, eig_sv, eig_Vout;  // marginal analysis scratch / results
+  DevBuf<int> eig_sweeps;
   DevBuf<double> trace_dev;
   LmCtrl* h_ctrl = nullptr;     // pinned
   // peer exchange over NVLink (kb_attach_peers): own buffer + the peers' buffers opened through CUDA IPC
@@ -813,6 +815,68 @@ kb_status kb_build_system(kb_handle* h, int32_t /*use_m_estimator*/) {
   h->built = true;
   h->solved = false;
   return KB_OK;  // stage times are collected at the next synchronising call
+}
+
+// ---- marginal analysis of the calibration block ----------------------------------------------------------------------
+void kb_default_marginal_options(kb_marginal_options* o) {
+  o->eps_svd = 2.220446049250313e-16;  // std::numeric_limits<double>::epsilon(): LinearSolverOptions.cpp:33
+  o->svd_tol = -1.0;
+}
+
+kb_status kb_analyze_marginal(kb_handle* h, const kb_marginal_options* o, kb_marginal_result* out, double* singular_values, double* V, int32_t* columns) {
+  if (!o || !out || !singular_values) return fail(h, KB_ERR_INVALID_ARGUMENT, "null argument");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  const int n = h->d.n_c;
+  if (n > 255) return fail(h, KB_ERR_INVALID_ARGUMENT, "calibration block too large");
+  if (h->eig_G.n != (size_t)(n + 1) * n) {
+    KB_CUDA(h, h->eig_G.alloc((size_t)(n + 1) * n));
+    KB_CUDA(h, h->eig_V.alloc((size_t)(n + 1) * n));
+    KB_CUDA(h, h->eig_sv.alloc(n));
+    KB_CUDA(h, h->eig_Vout.alloc((size_t)n * n));
+    KB_CUDA(h, h->eig_sweeps.alloc(1));
+  }
+  // the undamped normal equations at the current state, set poses eliminated: exactly the analyzeMarginal matrix
+  kb_status st = kb_build_system(h, 1);
+  if (st != KB_OK) return st;
+  h->h_posdef[0] = 1;
+  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  KB_CUDA(h, launch_schur(h->d, 0.0, h->partials.p, h->n_partials, h->posdef.p, c));
+  KB_CUDA(h, launch_schur_finalize(h->d, 0.0, h->partials.p, h->n_partials, true, c));
+  if (h->px_on) {
+    KB_CUDA(h, launch_px_reduce_system(h->d, c));
+  } else if ((st = nccl_allreduce(h, h->Sred.p, (size_t)h->d.n_aug * h->d.n_aug, kNcclFloat64, kNcclSum)) != KB_OK) {
+    return st;
+  }
+  if (h->n_ranks > 1 && (st = nccl_allreduce(h, h->posdef.p, 1, kNcclInt32, kNcclMin)) != KB_OK) return st;
+  KB_CUDA(h, launch_marginal_eig(h->d, h->eig_G.p, h->eig_V.p, h->eig_sv.p, h->eig_Vout.p, h->eig_sweeps.p, c));
+  KB_CUDA(h, cudaMemcpyAsync(h->h_posdef, h->posdef.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(singular_values, h->eig_sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (V) KB_CUDA(h, cudaMemcpyAsync(V, h->eig_Vout.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
+  int sweeps = 0;
+  KB_CUDA(h, cudaMemcpyAsync(&sweeps, h->eig_sweeps.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->solved = false;  // the pose factors now belong to the undamped system
+  if (!h->h_posdef[0])
+    return fail(h, KB_ERR_STATE, "a set pose is not constrained by its observations (pose block not positive definite): the marginal is undefined");
+  if (sweeps >= 40) return fail(h, KB_ERR_STATE, "the Jacobi iteration of the marginal analysis did not converge");
+  if (columns)
+    for (int i = 0; i < n; ++i) columns[i] = h->h_cam_cols[i];
+  // IC/src/algorithms/linalg.cpp:244-282, IC/src/core/LinearSolver.cpp:196-200
+  out->n = n;
+  out->tolerance = o->svd_tol != -1.0 ? o->svd_tol : singular_values[0] * o->eps_svd * n;
+  int rank = n;
+  for (int i = n - 1; i > 0; --i) {
+    if (singular_values[i] > out->tolerance) break;
+    --rank;
+  }
+  out->rank = rank;
+  out->rank_deficiency = n - rank;
+  out->sv_gap = rank < n ? singular_values[rank - 1] / singular_values[rank] : INFINITY;
+  double lg = 0.0;
+  for (int i = 0; i < rank; ++i) lg += std::log(singular_values[i]);
+  out->sv_log2_sum = lg / std::log(2.0);
+  return KB_OK;
 }
 
 // ---- peer exchange over NVLink ------------------------------------------------------------------------------------

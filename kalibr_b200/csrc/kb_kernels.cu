@@ -1426,6 +1426,98 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
 }
 
 // =========================================================================================================
+// marginal analysis: singular values and right singular vectors of the (symmetric, positive semi-definite) reduced camera
+// system — the calibration block's information matrix with the set poses marginalised out — by a one-sided (Hestenes)
+// Jacobi iteration.               ≙ analyzeSVD (Eigen::JacobiSVD of Omega), aslam_incremental_calibration/.../linalg.cpp:409-425
+// One CTA; the columns of G = S and of V = I live in global memory (column-major, L1/L2-resident: n <= 223).  A sweep is
+// n - 1 round-robin steps of n / 2 disjoint column pairs; a warp takes a pair: three dot products, then the plane rotation
+// that makes the two columns orthogonal, applied to G and V.  Converged when a whole sweep rotates nothing; the column norms
+// are the singular values, the columns of V the singular vectors; both are written sorted by descending singular value.
+// =========================================================================================================
+constexpr int EIG_THREADS = 1024;
+__global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem p, double* __restrict__ G, double* __restrict__ V,
+                                                                      double* __restrict__ sv_out, double* __restrict__ V_out, int* __restrict__ sweeps_out) {
+  __shared__ double s_sigma[256];
+  __shared__ int s_perm[256];
+  const int n = p.n_c, na = p.n_aug;
+  const int np = (n + 1) & ~1;  // padded to an even number of columns (the extra one is zero and never rotates)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = EIG_THREADS / 32;
+  for (int idx = tid; idx < np * n; idx += EIG_THREADS) {
+    const int c = idx / n, r = idx - c * n;
+    G[idx] = c < n ? p.Sred[(size_t)r * na + c] : 0.0;
+    V[idx] = (c == r) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  int sweep = 0;
+  for (; sweep < 40; ++sweep) {
+    int rotated = 0;
+    for (int step = 0; step < np - 1; ++step) {
+      for (int k = warp; k < np / 2; k += n_warps) {
+        // round-robin pairing: player np - 1 stays, the others rotate
+        int a, b;
+        if (k == 0) {
+          a = np - 1;
+          b = step;
+        } else {
+          a = (step + k) % (np - 1);
+          b = (step - k + (np - 1)) % (np - 1);
+        }
+        double* ga = G + (size_t)a * n;
+        double* gb = G + (size_t)b * n;
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        for (int r = lane; r < n; r += 32) {
+          const double x = ga[r], y = gb[r];
+          alpha += x * x;
+          beta += y * y;
+          gamma += x * y;
+        }
+        alpha = warp_sum(alpha);
+        beta = warp_sum(beta);
+        gamma = warp_sum(gamma);
+        if (fabs(gamma) > 1e-15 * sqrt(alpha * beta) && gamma != 0.0) {
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+          double* va = V + (size_t)a * n;
+          double* vb = V + (size_t)b * n;
+          for (int r = lane; r < n; r += 32) {
+            const double x = ga[r], y = gb[r];
+            ga[r] = c * x - sn * y;
+            gb[r] = sn * x + c * y;
+            const double u = va[r], w = vb[r];
+            va[r] = c * u - sn * w;
+            vb[r] = sn * u + c * w;
+          }
+          rotated = 1;
+        }
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) break;
+  }
+  if (tid == 0) sweeps_out[0] = sweep;
+  for (int c = warp; c < n; c += n_warps) {
+    double s = 0.0;
+    for (int r = lane; r < n; r += 32) s += G[(size_t)c * n + r] * G[(size_t)c * n + r];
+    s = warp_sum(s);
+    if (lane == 0) s_sigma[c] = sqrt(s);
+  }
+  __syncthreads();
+  if (tid < n) {  // rank sort, descending, ties by index
+    const double me = s_sigma[tid];
+    int pos = 0;
+    for (int j = 0; j < n; ++j) pos += (s_sigma[j] > me) || (s_sigma[j] == me && j < tid);
+    s_perm[pos] = tid;
+    sv_out[pos] = me;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += EIG_THREADS) {
+    const int r = idx / n, k = idx - r * n;
+    V_out[idx] = V[(size_t)s_perm[k] * n + r];
+  }
+}
+
+// =========================================================================================================
 // back substitution for the poses + scatter of dx into design-variable order
 // =========================================================================================================
 __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
@@ -2025,6 +2117,11 @@ cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max, int* p
 }
 cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx& s) {
   px_combine_cost_kernel<<<1, 1, 0, s.stream>>>(p, cost);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, double* sv_out, double* V_out, int* sweeps_out, StreamCtx& s) {
+  marginal_eig_kernel<<<1, EIG_THREADS, 0, s.stream>>>(p, G, V, sv_out, V_out, sweeps_out);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }

@@ -68,6 +68,26 @@ class KbOptimizerOptions(C.Structure):
         return cls(1e-3, 1.0, 200, 10.0, verbose, device_loop)
 
 
+class KbMarginalOptions(C.Structure):
+    _fields_ = [("eps_svd", C.c_double), ("svd_tol", C.c_double)]
+
+    @classmethod
+    def default(cls) -> "KbMarginalOptions":
+        """aslam::calibration::LinearSolverOptions (src/core/LinearSolverOptions.cpp:31-36)."""
+        return cls(float(np.finfo(np.float64).eps), -1.0)
+
+
+class KbMarginalResult(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("rank", C.c_int32),
+        ("rank_deficiency", C.c_int32),
+        ("tolerance", C.c_double),
+        ("sv_log2_sum", C.c_double),
+        ("sv_gap", C.c_double),
+    ]
+
+
 class KbSolution(C.Structure):
     _fields_ = [
         ("j_start", C.c_double),

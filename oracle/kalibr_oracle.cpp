@@ -13,6 +13,7 @@
 
 #include "../include/kalibr_b200.h"
 #include "ko_backend.hpp"
+#include "ko_marginal.hpp"
 
 namespace ko {
 
@@ -750,6 +751,62 @@ __attribute__((visibility("default"))) int64_t ko_get_jacobian_ccs(ko_problem* h
       },
       std::max(1, nThreads), n);
   return cp.back();
+}
+
+// Marginal analysis of the camera-side block at the current state (ko_marginal.hpp).  The set-pose columns are A_l, the
+// remaining columns, in the order [camera 0 projection | distortion, camera 1 ..., baseline 0 q | t, ...], are A_r.
+// V, columns, omega may be NULL.
+__attribute__((visibility("default"))) int32_t ko_analyze_marginal(ko_problem* h, int nThreads, const kb_marginal_options* o, kb_marginal_result* out,
+                                                                   double* sv, double* V, int32_t* columns, double* omega) {
+  Problem& P = *h->P;
+  P.evaluateError(std::max(1, nThreads));  // Jacobians are taken at the state of the last evaluation (quirk Q8)
+  const size_t m = 2 * P.errorTerms.size(), nAll = P.solver->JCols;
+  std::vector<char> isPose(nAll, 0);
+  for (size_t v = 0; v < P.setQ.size(); ++v) {
+    for (int c = 0; c < 3; ++c) {
+      isPose[P.setQ[v]->columnBase + c] = 1;
+      isPose[P.setT[v]->columnBase + c] = 1;
+    }
+  }
+  std::vector<int> colR, colL;
+  for (int k = 0; k < P.nCams; ++k) {
+    for (int c = 0; c < P.cams[k]->projectionDv->minimalDimensions(); ++c) colR.push_back(P.cams[k]->projectionDv->columnBase + c);
+    for (int c = 0; c < P.cams[k]->distortionDv->minimalDimensions(); ++c) colR.push_back(P.cams[k]->distortionDv->columnBase + c);
+  }
+  for (size_t j = 0; j < P.baseQ.size(); ++j) {
+    for (int c = 0; c < 3; ++c) colR.push_back(P.baseQ[j]->columnBase + c);
+    for (int c = 0; c < 3; ++c) colR.push_back(P.baseT[j]->columnBase + c);
+  }
+  std::vector<int> slot(nAll, -1);
+  for (size_t i = 0; i < colR.size(); ++i) slot[colR[i]] = (int)i;
+  for (size_t c = 0; c < nAll; ++c)
+    if (isPose[c]) { slot[c] = (int)colL.size(); colL.push_back((int)c); }
+  const int nl = (int)colL.size(), nr = (int)colR.size();
+  std::vector<double> Al(m * (size_t)nl, 0.0), Ar(m * (size_t)nr, 0.0);
+  for (size_t i = 0; i < P.errorTerms.size(); ++i) {
+    JacobianContainer jc(2);
+    P.errorTerms[i]->getWeightedJacobians(jc);
+    for (int r = 0; r < 2; ++r)
+      for (auto& kv : jc.jacobianMap)
+        for (int c = 0; c < kv.second.c; ++c) {
+          const int col = kv.first->columnBase + c;
+          if (isPose[col]) Al[(2 * i + r) * (size_t)nl + slot[col]] = kv.second(r, c);
+          else Ar[(2 * i + r) * (size_t)nr + slot[col]] = kv.second(r, c);
+        }
+  }
+  MarginalResult R = analyzeMarginalDense(Al, (int)m, nl, Ar, nr, o->eps_svd, o->svd_tol);
+  out->n = R.n;
+  out->rank = R.rank;
+  out->rank_deficiency = R.rankDeficiency;
+  out->tolerance = R.tolerance;
+  out->sv_log2_sum = R.svLog2Sum;
+  out->sv_gap = R.svGap;
+  std::memcpy(sv, R.singularValues.data(), sizeof(double) * nr);
+  if (V) std::memcpy(V, R.V.data(), sizeof(double) * nr * nr);
+  if (omega) std::memcpy(omega, R.Omega.data(), sizeof(double) * nr * nr);
+  if (columns)
+    for (int i = 0; i < nr; ++i) columns[i] = colR[i];
+  return nr;
 }
 
 // Upper-triangular block pattern + values of H as SparseBlockMatrix holds them (BlockCholesky semantic only).

@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
         L.ko_quat2r.argtypes = [C.c_void_p, C.c_void_p]
         L.ko_update_quat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ko_inverse4.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_analyze_marginal.restype = C.c_int32
+        L.ko_analyze_marginal.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.ko_time_iteration.restype = C.c_int32
         L.ko_time_iteration.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         _lib = L
@@ -164,6 +166,18 @@ class OracleProblem:
         vals = np.zeros(nnz)
         lib().ko_get_jacobian_ccs(self._h, self.n_threads, _p(col_ptr), _p(row_idx), _p(vals))
         return col_ptr, row_idx, vals
+
+    def analyze_marginal(self, options=None):
+        """LinearSolver::analyzeMarginal restated (oracle/ko_marginal.hpp): (result, singular values, V, DV columns, Omega)."""
+        from kalibr_b200.problem import KbMarginalOptions, KbMarginalResult
+
+        o = options or KbMarginalOptions.default()
+        n = self._problem.n_c
+        res = KbMarginalResult()
+        sv, V, cols, om = np.zeros(n), np.zeros((n, n)), np.zeros(n, np.int32), np.zeros((n, n))
+        got = lib().ko_analyze_marginal(self._h, self.n_threads, C.byref(o), C.byref(res), _p(sv), _p(V), _p(cols), _p(om))
+        assert got == n
+        return res, sv, V, cols, om
 
     def hessian_blocks(self):
         nb = C.c_int64()

@@ -281,3 +281,54 @@ def test_oracle_reproduces_golden_fixtures(oracle_lib, name):
     sol, _ = o2.optimize(KbOptimizerOptions.kalibr2_default())
     assert sol.iterations == int(g["iterations"]) and sol.failed_iterations == int(g["failed_iterations"])
     assert np.abs(o2.camera_params() - g["cam_params"]).max() <= 1e-8 * np.abs(g["cam_params"]).max()
+
+
+def _schur_marginal_numpy(o, cols):
+    cp, ri, jv = o.jacobian_ccs()
+    J = _dense_from_ccs(cp, ri, jv, o.jcols)
+    H = J.T @ J
+    pose = np.setdiff1d(np.arange(o.jcols), cols)
+    return H[np.ix_(cols, cols)] - H[np.ix_(cols, pose)] @ np.linalg.pinv(H[np.ix_(pose, pose)]) @ H[np.ix_(pose, cols)]
+
+
+@pytest.mark.parametrize("cfg,n_sets", [(1, 12), (2, 9), (3, 6), (6, 7)])
+def test_marginal_analysis_matches_dense_schur_complement(oracle_lib, cfg, n_sets):
+    """analyzeMarginal restated (QR of the pose columns, Omega, SVD) == the Schur complement of the dense normal equations;
+    rank, tolerance and log2-sum follow aslam_incremental_calibration's linalg.cpp:244-282 / LinearSolver.cpp:196-200."""
+    p = synthetic.make_config(cfg, n_sets=n_sets)
+    o = oracle_lib.OracleProblem(p)
+    res, sv, V, cols, om = o.analyze_marginal()
+    S = _schur_marginal_numpy(o, cols)
+    assert np.abs(S - om).max() <= 1e-11 * np.abs(S).max()
+    svn = np.linalg.svd(S, compute_uv=False)
+    assert np.abs(svn - sv).max() <= 1e-12 * svn[0]
+    tol = svn[0] * np.finfo(float).eps * p.n_c
+    rank = p.n_c
+    for i in range(p.n_c - 1, 0, -1):  # estimateNumericalRank
+        if svn[i] > tol:
+            break
+        rank -= 1
+    assert res.n == p.n_c and res.rank == rank and res.rank_deficiency == p.n_c - rank
+    assert np.isinf(res.sv_gap) if rank == p.n_c else abs(res.sv_gap - svn[rank - 1] / svn[rank]) <= 0.3 * res.sv_gap  # the tiny trailing value is only known absolutely
+    svn = svn[:rank]
+    assert abs(res.tolerance - sv[0] * np.finfo(float).eps * res.n) <= 1e-15 * res.tolerance
+    assert abs(res.sv_log2_sum - np.log2(svn).sum()) <= 1e-9 * abs(res.sv_log2_sum)
+    assert np.abs(V.T @ V - np.eye(res.n)).max() < 1e-12
+    assert np.abs(V @ np.diag(sv) @ V.T - om).max() <= 1e-12 * sv[0]
+
+
+def test_marginal_analysis_finds_the_rank_deficiency(oracle_lib):
+    """A camera nobody observes leaves its intrinsics and its baseline unobservable: 8 + 6 zero singular values."""
+    from kalibr_b200.problem import Problem
+
+    p = synthetic.make_config(2, n_sets=8)
+    keep_view = p.view_cam == 0
+    keep_term = np.repeat(keep_view, np.diff(p.view_begin))
+    vb = np.concatenate([[0], np.cumsum(np.diff(p.view_begin)[keep_view])]).astype(np.int64)
+    q = Problem(p.driver_order, p.cam_model, p.cam_params, p.baselines, p.set_poses, p.target_points, p.view_set[keep_view],
+                p.view_cam[keep_view], vb, p.y_u[keep_term], p.y_v[keep_term], p.corner_id[keep_term])
+    res, sv, V, cols, om = oracle_lib.OracleProblem(q).analyze_marginal()
+    assert res.rank == 8 and res.rank_deficiency == 14
+    assert sv[8:].max() <= res.tolerance and sv[7] > 1e3 * res.tolerance
+    assert res.sv_gap > 1e6
+    assert abs(res.sv_log2_sum - np.log2(sv[:8]).sum()) < 1e-9

@@ -354,3 +354,48 @@ def test_double_buffered_observations(capi):
         sb, _ = b.optimize(KbOptimizerOptions.kalibr2_default())
         assert (sa.iterations, sa.j_final) == (sb.iterations, sb.j_final)
         a.reset_state(); b.reset_state()
+
+
+@pytest.mark.parametrize("cfg,n_sets", [(1, 40), (2, 30), (3, 24), (4, 12), (5, 6), (6, 20)])
+def test_marginal_analysis_matches_oracle(capi, oracle_lib, cfg, n_sets):
+    """kb_analyze_marginal (undamped Schur-reduced camera system + one-sided Jacobi on the device) against the oracle's
+    restatement of LinearSolver::analyzeMarginal: singular values, rank, tolerance, log2-sum, singular subspaces."""
+    p = make(cfg, n_sets)
+    g = capi.B200SchurLinearSystemSolver(p)
+    o = oracle_lib.OracleProblem(p)
+    g.optimize(KbOptimizerOptions.kalibr2_default())
+    o.optimize(KbOptimizerOptions.kalibr2_default())
+    rg, svg, Vg, cg = g.analyze_marginal()
+    ro, svo, Vo, co, om = o.analyze_marginal()
+    assert np.array_equal(cg, co)
+    assert (rg.n, rg.rank, rg.rank_deficiency) == (ro.n, ro.rank, ro.rank_deficiency)
+    assert np.abs(svg - svo).max() <= 1e-9 * svo[0]
+    assert abs(rg.tolerance - ro.tolerance) <= 1e-9 * ro.tolerance
+    assert abs(rg.sv_log2_sum - ro.sv_log2_sum) <= 1e-6 * abs(ro.sv_log2_sum)
+    assert np.abs(Vg.T @ Vg - np.eye(rg.n)).max() < 1e-10
+    assert np.abs(Vg @ np.diag(svg) @ Vg.T - om).max() <= 1e-9 * svo[0]
+    # a solve right after the analysis works on the system it has built
+    g.set_constant_conditioner(10.0)
+    o.build_system()
+    o.set_constant_conditioner(10.0)
+    dxg, okg = g.solve_system()
+    dxo, oko = o.solve_system()
+    assert okg and oko and rel_err(dxg, dxo) < 1e-6
+
+
+def test_marginal_analysis_rank_deficient_camera(capi, oracle_lib):
+    """Stereo rig in which camera 1 has no image at all: its intrinsics (8) and the baseline (6) are unobservable."""
+    p0 = make(2, 16)
+    p = _edit_views(p0, remove={w for w in range(p0.n_views) if p0.view_cam[w] == 1})
+    g = capi.B200SchurLinearSystemSolver(p)
+    o = oracle_lib.OracleProblem(p)
+    rg, svg, Vg, cg = g.analyze_marginal()
+    ro, svo, Vo, co, om = o.analyze_marginal()
+    assert (rg.rank, rg.rank_deficiency) == (ro.rank, ro.rank_deficiency) == (8, 14)
+    assert np.abs(svg[:8] - svo[:8]).max() <= 1e-9 * svo[0]
+    assert svg[8:].max() <= rg.tolerance
+    assert abs(rg.sv_log2_sum - ro.sv_log2_sum) <= 1e-6 * abs(ro.sv_log2_sum)
+    # the null space is spanned by the unit vectors of camera 1's intrinsics and the baseline
+    null_cols = np.abs(Vg[:, 8:]).sum(axis=1) > 1e-6
+    expected = np.isin(cg, np.setdiff1d(cg, cg[:8])) if False else ~np.isin(np.arange(rg.n), np.arange(8))
+    assert np.array_equal(null_cols, expected)
