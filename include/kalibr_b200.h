@@ -129,8 +129,10 @@ KB_API kb_status kb_peer_exchange_handle(kb_handle* h, char out[64]);
 KB_API kb_status kb_attach_peers(kb_handle* h, const char* handles /*[n_ranks][64]*/);
 
 /* ---- per-iteration hot path ---------------------------------------------- */
-/* ≙ LinearSystemSolver::evaluateError (BE/src/LinearSystemSolver.cpp:81-92): returns J = sum e^T invR e
- *   over ALL ranks and fills the device copy of e().  use_m_estimator must be 0 (NoMEstimator only). */
+/* ≙ LinearSystemSolver::evaluateError (BE/src/LinearSystemSolver.cpp:81-92): returns J = sum w e^T invR e
+ *   over ALL ranks (w = weight of the installed M-estimator policy, 1 without one: BE/src/ErrorTerm.cpp:19-24) and fills the
+ *   device copy of e() = -sqrt(w) sqrtInvR^T e; use_m_estimator = 0 leaves sqrt(w) out of e() exactly as
+ *   ErrorTermFs::getWeightedError does (BE/include/aslam/backend/implementation/ErrorTerm.hpp:183-192). */
 KB_API kb_status kb_evaluate_error(kb_handle* h, int32_t use_m_estimator, double* out_cost);
 /* ≙ BlockCholeskyLinearSystemSolver::buildSystem (BE/src/BlockCholeskyLinearSystemSolver.cpp:58-72):
  *   linearise every term at the current state and assemble H, rhs. */
@@ -177,6 +179,38 @@ KB_API kb_status kb_set_solver_semantic(kb_handle* h, int32_t semantic);
  * the cost, e() is written too), so that a kb_build_system at the same state — the accepted-step case of the LM loop —
  * only has to reduce the view blocks.  Off: kb_evaluate_error runs the residual-only kernel. Results are identical. */
 KB_API kb_status kb_set_speculative_linearise(kb_handle* h, int32_t on);
+
+/* ---- weighting of the terms ---------------------------------------------------------
+ * ≙ ErrorTermFs<2>::setInvR on every ReprojectionError (BE/include/aslam/backend/implementation/ErrorTerm.hpp:118-127;
+ *   K2 passes invR = I in the batch drivers, CalibrationTools.hpp:105-108, and I / sigma^2 in CreateBatchProblem, :495-496).
+ *   inv_r: symmetric positive definite 2x2, row-major.  Its square root follows sm::eigen::computeMatrixSqrt
+ *   (Schweizer-Messer/sm_eigen/include/sm/eigen/matrix_sqrt.hpp:21-40: S = P^T L sqrt(D) of Eigen's pivoted LDL^T), so that
+ *   e() = -S^T e and the exported Jacobian rows S^T J match the reference value for value.  Default: identity. */
+KB_API kb_status kb_set_inv_r(kb_handle* h, const double inv_r[4]);
+KB_API kb_status kb_get_sqrt_inv_r(const kb_handle* h, double sqrt_inv_r[4] /* row-major S */);
+/* ≙ ErrorTerm::setMEstimatorPolicy on every term (BE/src/ErrorTerm.cpp:46-56) with the policies of
+ *   BE/src/MEstimatorPolicies.cpp.  Parameters: HUBER p0 = k; CAUCHY, GEMAN_MCCLURE p0 = sigma^2;
+ *   BLAKE_ZISSERMAN p0 = df, p1 = pCut (0.999), p2 = wCut (0.1) -> epsilon = (1 - wCut) / wCut exp(-chi2inv(pCut, df)).
+ *   The weight w = policy(e^T invR e) always enters the cost; it scales e() and the Jacobian rows when the
+ *   use_m_estimator argument of kb_evaluate_error / kb_build_system is non-zero (Optimizer2 always passes true:
+ *   BE/src/Optimizer2.cpp:198, 237; BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:56, 72). */
+typedef enum {
+  KB_MEST_NONE = 0,            /* NoMEstimator            w = 1 */
+  KB_MEST_HUBER = 1,           /* HuberMEstimator         w = s < k^2 ? 1 : k / sqrt(s) */
+  KB_MEST_CAUCHY = 2,          /* CauchyMEstimator        w = 1 / (1 + s / sigma^2) */
+  KB_MEST_GEMAN_MCCLURE = 3,   /* GemanMcClureMEstimator  w = sigma^2 / (sigma^2 + s)^2 */
+  KB_MEST_BLAKE_ZISSERMAN = 4  /* BlakeZissermanMEstimator w = exp(-s) / (exp(-s) + epsilon) */
+} kb_m_estimator;
+KB_API kb_status kb_set_m_estimator(kb_handle* h, int32_t kind, double p0, double p1, double p2);
+KB_API double kb_m_estimator_parameter(const kb_handle* h); /* k, sigma^2 or the derived epsilon */
+
+/* ---- reprojection statistics ---------------------------------------------------------
+ * ≙ CameraCalibrator::PrintReprojectionErrorStatistics (K2/include/kalibr2/CameraCalibrator.hpp:368-405) for every camera, at
+ *   the current state, over ALL ranks: per camera [n, mean_u, mean_v, std_u, std_v, rmse] with the raw errors y - y_hat
+ *   (:267-286), the two-pass sample standard deviation (N - 1; 0 below two samples) and "RMSE" exactly as printed there:
+ *   |sum of the error vectors| / sqrt(n).  Collective when n_ranks > 1.  e() is left untouched. */
+#define KB_REPROJ_STAT_STRIDE 6
+KB_API kb_status kb_reprojection_statistics(kb_handle* h, double* out /*[n_cams][KB_REPROJ_STAT_STRIDE]*/);
 
 /* ---- marginal analysis of the calibration block --------------------------------
  * ≙ aslam::calibration::LinearSolver::analyzeMarginal (aslam_incremental_calibration/incremental_calibration/src/core/

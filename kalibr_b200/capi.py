@@ -25,7 +25,11 @@ EXPORTED_SYMBOLS = [
     "kb_linearise", "kb_jacobian_nnz", "kb_get_jacobian_ccs", "kb_get_hessian_blocks", "kb_get_camera_params", "kb_get_baselines",
     "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
+    "kb_set_inv_r", "kb_get_sqrt_inv_r", "kb_set_m_estimator", "kb_m_estimator_parameter", "kb_reprojection_statistics",
 ]
+
+MEST_NONE, MEST_HUBER, MEST_CAUCHY, MEST_GEMAN_MCCLURE, MEST_BLAKE_ZISSERMAN = range(5)  # = kb_m_estimator
+REPROJ_STAT_STRIDE = 6
 
 _lib = None
 
@@ -98,6 +102,12 @@ def load_library() -> C.CDLL:
     L.kb_get_stage_totals.argtypes = [vp, vp, vp]
     L.kb_cuda_stream.argtypes = [vp]
     L.kb_cuda_stream.restype = vp
+    L.kb_set_inv_r.argtypes = [vp, vp]
+    L.kb_get_sqrt_inv_r.argtypes = [vp, vp]
+    L.kb_set_m_estimator.argtypes = [vp, C.c_int32, C.c_double, C.c_double, C.c_double]
+    L.kb_m_estimator_parameter.argtypes = [vp]
+    L.kb_m_estimator_parameter.restype = C.c_double
+    L.kb_reprojection_statistics.argtypes = [vp, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:  # default: status-returning entry points
@@ -169,11 +179,11 @@ class B200SchurLinearSystemSolver:
 
     def evaluate_error(self, use_m_estimator: bool = True) -> float:
         out = C.c_double()
-        self._check(self._L.kb_evaluate_error(self._h, 0, C.byref(out)), "kb_evaluate_error")
+        self._check(self._L.kb_evaluate_error(self._h, 1 if use_m_estimator else 0, C.byref(out)), "kb_evaluate_error")
         return out.value
 
     def build_system(self, use_m_estimator: bool = True):
-        self._check(self._L.kb_build_system(self._h, 0), "kb_build_system")
+        self._check(self._L.kb_build_system(self._h, 1 if use_m_estimator else 0), "kb_build_system")
 
     def set_constant_conditioner(self, lam: float):
         self._check(self._L.kb_set_constant_conditioner(self._h, lam), "kb_set_constant_conditioner")
@@ -196,6 +206,27 @@ class B200SchurLinearSystemSolver:
 
     def revert_last_state_update(self):
         self._check(self._L.kb_revert_last_state_update(self._h), "kb_revert_last_state_update")
+
+    # -- weighting of the terms (≙ ErrorTermFs::setInvR, ErrorTerm::setMEstimatorPolicy on every term)
+    def set_inv_r(self, inv_r):
+        a = np.ascontiguousarray(inv_r, np.float64).reshape(2, 2)
+        self._check(self._L.kb_set_inv_r(self._h, _p(a)), "kb_set_inv_r")
+
+    def sqrt_inv_r(self) -> np.ndarray:
+        out = np.zeros((2, 2))
+        self._check(self._L.kb_get_sqrt_inv_r(self._h, _p(out)), "kb_get_sqrt_inv_r")
+        return out
+
+    def set_m_estimator(self, kind: int, p0: float = 0.0, p1: float = 0.999, p2: float = 0.1) -> float:
+        """Installs the policy; returns its parameter (k, sigma^2, or the derived epsilon of Blake-Zisserman)."""
+        self._check(self._L.kb_set_m_estimator(self._h, kind, p0, p1, p2), "kb_set_m_estimator")
+        return float(self._L.kb_m_estimator_parameter(self._h))
+
+    def reprojection_statistics(self) -> np.ndarray:
+        """≙ CameraCalibrator::PrintReprojectionErrorStatistics per camera: rows [n, mean_u, mean_v, std_u, std_v, rmse]."""
+        out = np.zeros((self.problem.n_cams, REPROJ_STAT_STRIDE))
+        self._check(self._L.kb_reprojection_statistics(self._h, _p(out)), "kb_reprojection_statistics")
+        return out
 
     def set_solver_semantic(self, semantic: int):
         self._check(self._L.kb_set_solver_semantic(self._h, semantic), "kb_set_solver_semantic")
@@ -269,10 +300,10 @@ class B200SchurLinearSystemSolver:
     def set_observations(self, y_u: np.ndarray, y_v: np.ndarray):
         self._check(self._L.kb_set_observations(self._h, _p(y_u), _p(y_v)), "kb_set_observations")
 
-    def evaluate_error_streamed(self, y_u: np.ndarray, y_v: np.ndarray) -> float:
+    def evaluate_error_streamed(self, y_u: np.ndarray, y_v: np.ndarray, use_m_estimator: bool = True) -> float:
         """set_observations + evaluate_error with the upload pipelined against the evaluation (pass pinned host arrays)."""
         J = C.c_double(0.0)
-        self._check(self._L.kb_evaluate_error_streamed(self._h, _p(y_u), _p(y_v), 0, C.byref(J)), "kb_evaluate_error_streamed")
+        self._check(self._L.kb_evaluate_error_streamed(self._h, _p(y_u), _p(y_v), 1 if use_m_estimator else 0, C.byref(J)), "kb_evaluate_error_streamed")
         return J.value
 
     def prefetch_observations(self, y_u: np.ndarray, y_v: np.ndarray):

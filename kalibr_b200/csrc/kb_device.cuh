@@ -127,6 +127,15 @@ struct DevProblem {
   unsigned int* n_invalid;  // terms whose projection bailed out (Q6)
   LmCtrl* ctrl;             // control block (device)
   PeerXchg px;              // peer exchange (enabled after kb_attach_peers)
+  // ---- weighting of the terms (kb_set_inv_r / kb_set_m_estimator) ----
+  // weighted == 0 (default): invR = I and NoMEstimator, the kernels run their unweighted instantiations.  Otherwise every term's
+  // rows and residual are multiplied by sqrt(w) sqrtInvR^T (BE/include/aslam/backend/implementation/ErrorTerm.hpp:97-109, 170-192)
+  // with w = policy(e^T invR e) (BE/src/MEstimatorPolicies.cpp), and the cost is sum w e^T invR e (BE/src/ErrorTerm.cpp:19-24).
+  int weighted;
+  int mest_kind;       // kb_m_estimator
+  int mest_rows;       // 1: w also scales e() and the Jacobian rows (useMEstimator = true); 0: only the cost
+  double mest_param;   // Huber: k; Cauchy, Geman-McClure: sigma^2; Blake-Zisserman: epsilon
+  double sT[4];        // sqrtInvR^T, row-major
 };
 
 constexpr int LIN_OFF_STRIDE = 4 + MAX_CAMS;  // pose_q, pose_t, proj, dist, baseline j (q; t = +3)
@@ -143,6 +152,10 @@ struct StreamCtx {
 // launchers (kb_kernels.cu); every one returns the cudaGetLastError() of its launches
 cudaError_t launch_prep(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int* model_begin, double* cost_out, StreamCtx& s);
+// reprojection statistics per camera from raw residuals in e_raw (= -(y - y_hat) per term, as evaluate writes them): pass 0 sums
+// (n, sum e_u, sum e_v) into acc[cam][4], pass 1 (after the sums are global) the squared deviations from the mean into acc[cam][4 + {0,1}]
+cudaError_t launch_reproj_stats(const DevProblem& p, const double* e_raw, const int* cam_view_list, const int* cam_view_begin, int pass,
+                                double* acc /*[n_cams][8]*/, StreamCtx& s);
 int la_grid_warps();
 cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta /*(view,set,begin,end) in view-list order*/, const int4* slices,
                                       const int* slice_model_begin, bool write_e, bool with_set_prep,

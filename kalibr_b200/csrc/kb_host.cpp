@@ -151,6 +151,9 @@ struct kb_handle {
   bool speculative = true;       // kb_evaluate_error linearises too, so that a build at the same state is free
   long long state_version = 0;   // bumped whenever design variables or observations change
   long long la_version = -1;     // state the view blocks / Gram sums were computed at
+  int la_rows = 0;               // DevProblem::mest_rows they were computed with
+  double inv_r[4] = {1.0, 0.0, 0.0, 1.0}, sqrt_inv_r[4] = {1.0, 0.0, 0.0, 1.0};  // row-major
+  DevBuf<double> stats_e, stats_acc;  // reprojection statistics scratch
   std::vector<double> trace;
   // ---- multi-GPU ----
   NcclComm comm = nullptr;
@@ -397,6 +400,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   // ---- reduced-system layout: [cam0 proj|dist, cam1 ..., | baseline 0 q,t, ...] ----
   DevProblem& D = h->d;
   D.n_cams = d->n_cams;
+  D.sT[0] = D.sT[3] = 1.0;  // invR = I, NoMEstimator (CalibrationTools.hpp:105-108; BE/src/ErrorTerm.cpp:8-12)
   D.n_sets = n_local_sets;
   D.n_views = n_views;
   D.n_target = d->n_target_points;
@@ -722,6 +726,7 @@ static kb_status run_linearise_assemble(kb_handle* h, bool write_e, int cost_slo
   }
   KB_CUDA(h, launch_finalize_gram(h->d, h->cam_slice_range.p, 1, h->scalars.p + cost_slot, write_e /* the evaluate-time call */, c));
   h->la_version = h->state_version;
+  h->la_rows = h->d.mest_rows;
   return KB_OK;
 }
 
@@ -733,12 +738,20 @@ static kb_status finish_evaluate(kb_handle* h, double* out_cost) {
   return KB_OK;
 }
 
-kb_status kb_evaluate_error(kb_handle* h, int32_t /*use_m_estimator: kalibr2 installs none on these terms (weight 1)*/, double* out_cost) {
+// useMEstimator of the reference only gates whether the policy weight scales e() and the Jacobian rows; the cost is weighted by
+// the policy regardless (BE/src/ErrorTerm.cpp:19-24, BE/include/aslam/backend/implementation/ErrorTerm.hpp:97-109, 170-192)
+static void set_rows_mode(kb_handle* h, int32_t use_m_estimator) { h->d.mest_rows = (h->d.mest_kind != 0 && use_m_estimator) ? 1 : 0; }
+
+kb_status kb_evaluate_error(kb_handle* h, int32_t use_m_estimator, double* out_cost) {
   KB_CUDA(h, cudaSetDevice(h->device));
+  set_rows_mode(h, use_m_estimator);
+  // with a policy installed but useMEstimator off, the Gram block's e-column holds sum e^T invR e, not the weighted cost:
+  // that combination runs the residual-only kernel, which accumulates w e^T invR e directly
+  const bool speculative = h->speculative && !(h->d.mest_kind != 0 && !use_m_estimator);
   StreamCtx c = ctx(h);
   {
     StageTimer t(h, 0);
-    if (h->speculative) {
+    if (speculative) {
       // The LM loop evaluates the cost of a trial state and, when the step is accepted, linearises at that same state
       // (Optimizer2.cpp:237 then LevenbergMarquardtTrustRegionPolicy.cpp:72): do both now, the Gram column of e gives the cost.
       kb_status st = run_linearise_assemble(h, true, 0);
@@ -747,7 +760,7 @@ kb_status kb_evaluate_error(kb_handle* h, int32_t /*use_m_estimator: kalibr2 ins
       KB_CUDA(h, launch_prep(h->d, c));
       KB_CUDA(h, launch_evaluate(h->d, h->view_list.p, h->model_begin, h->scalars.p, c));
     }
-    if (h->px_on && h->speculative) {  // gram_cost_kernel has already put this rank's cost into every rank's slot
+    if (h->px_on && speculative) {  // gram_cost_kernel has already put this rank's cost into every rank's slot
       KB_CUDA(h, launch_px_combine_cost(h->d, h->scalars.p, c));
     } else {
       kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
@@ -763,11 +776,12 @@ kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const doub
   if (h->n_ranks != 1 && !h->presharded)
     return fail(h, KB_ERR_STATE, "kb_evaluate_error_streamed needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
   if (!y_u || !y_v) return fail(h, KB_ERR_INVALID_ARGUMENT, "null observation array");
-  if (!h->speculative) {
+  if (!h->speculative || (h->d.mest_kind != 0 && !use_m_estimator)) {
     kb_status st = kb_set_observations(h, y_u, y_v);
     return st != KB_OK ? st : kb_evaluate_error(h, use_m_estimator, out_cost);
   }
   KB_CUDA(h, cudaSetDevice(h->device));
+  set_rows_mode(h, use_m_estimator);
   StreamCtx c = ctx(h);
   ++h->state_version;
   // the copies may only overwrite the observations once everything queued so far has read them
@@ -790,6 +804,7 @@ kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const doub
     }
     KB_CUDA(h, launch_finalize_gram(h->d, h->st_cam_slice_range.p, KB_STREAM_CHUNKS, h->scalars.p, true, c));
     h->la_version = h->state_version;
+    h->la_rows = h->d.mest_rows;
     if (h->px_on) {
       KB_CUDA(h, launch_px_combine_cost(h->d, h->scalars.p, c));
     } else {
@@ -800,10 +815,11 @@ kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const doub
   return finish_evaluate(h, out_cost);
 }
 
-kb_status kb_build_system(kb_handle* h, int32_t /*use_m_estimator*/) {
+kb_status kb_build_system(kb_handle* h, int32_t use_m_estimator) {
   KB_CUDA(h, cudaSetDevice(h->device));
+  set_rows_mode(h, use_m_estimator);
   StreamCtx c = ctx(h);
-  if (h->la_version != h->state_version) {
+  if (h->la_version != h->state_version || h->la_rows != h->d.mest_rows) {
     kb_status st = run_linearise_assemble(h, false, 6);
     if (st != KB_OK) return st;
   }
@@ -815,6 +831,170 @@ kb_status kb_build_system(kb_handle* h, int32_t /*use_m_estimator*/) {
   h->built = true;
   h->solved = false;
   return KB_OK;  // stage times are collected at the next synchronising call
+}
+
+// ---- weighting of the terms: inverse measurement covariance and M-estimator policy --------------------------------------
+namespace {
+// regularised lower incomplete gamma function P(a, x): power series below a + 1, continued fraction (modified Lentz) above
+double gamma_p(double a, double x) {
+  if (!(x > 0.0)) return 0.0;
+  const double pre = std::exp(a * std::log(x) - x - std::lgamma(a));
+  if (x < a + 1.0) {
+    double term = 1.0 / a, sum = term;
+    for (int n = 1; n < 100000 && std::fabs(term) > 1e-18 * std::fabs(sum); ++n) {
+      term *= x / (a + n);
+      sum += term;
+    }
+    return pre * sum;
+  }
+  const double fpmin = 1e-290;
+  double b = x + 1.0 - a, c = 1.0 / fpmin, d = 1.0 / b, f = d;
+  for (int i = 1; i < 100000; ++i) {
+    const double an = -(double)i * ((double)i - a);
+    b += 2.0;
+    d = an * d + b;
+    if (std::fabs(d) < fpmin) d = fpmin;
+    c = b + an / c;
+    if (std::fabs(c) < fpmin) c = fpmin;
+    d = 1.0 / d;
+    const double delta = d * c;
+    f *= delta;
+    if (std::fabs(delta - 1.0) < 1e-16) break;
+  }
+  return 1.0 - pre * f;
+}
+// chi-squared quantile: the x with P(df / 2, x / 2) = p.  The reference takes it from boost::math::quantile
+// (BE/src/MEstimatorPolicies.cpp:116-119); here a bracketed Newton iteration from the Wilson-Hilferty guess.
+double chi2_quantile(double p, double df) {
+  const double a = 0.5 * df;
+  // Wilson-Hilferty: x ~ df (1 - 2/(9 df) + z sqrt(2/(9 df)))^3, z the normal quantile (Acklam-free: bisection on erfc)
+  double zlo = -40.0, zhi = 40.0;
+  for (int i = 0; i < 200; ++i) {
+    const double zm = 0.5 * (zlo + zhi);
+    if (0.5 * std::erfc(-zm / std::sqrt(2.0)) < p) zlo = zm; else zhi = zm;
+  }
+  const double z = 0.5 * (zlo + zhi), k = 2.0 / (9.0 * df);
+  double x = df * std::pow(std::max(1.0 - k + z * std::sqrt(k), 1e-3), 3.0);
+  double lo = 0.0, hi = std::max(2.0 * x, 4.0 * df + 16.0);
+  while (gamma_p(a, 0.5 * hi) < p) hi *= 2.0;
+  for (int it = 0; it < 200; ++it) {
+    const double F = gamma_p(a, 0.5 * x) - p;
+    if (F < 0.0) lo = x; else hi = x;
+    const double pdf = 0.5 * std::exp((a - 1.0) * std::log(0.5 * x) - 0.5 * x - std::lgamma(a));
+    double nx = (pdf > 0.0) ? x - F / pdf : 0.5 * (lo + hi);
+    if (!(nx > lo && nx < hi)) nx = 0.5 * (lo + hi);
+    if (std::fabs(nx - x) <= 1e-16 * std::fabs(x)) { x = nx; break; }
+    x = nx;
+  }
+  return x;
+}
+void weighting_changed(kb_handle* h) {
+  const double* S = h->sqrt_inv_r;
+  h->d.sT[0] = S[0]; h->d.sT[1] = S[2]; h->d.sT[2] = S[1]; h->d.sT[3] = S[3];
+  const bool identity = S[0] == 1.0 && S[1] == 0.0 && S[2] == 0.0 && S[3] == 1.0;
+  h->d.weighted = (!identity || h->d.mest_kind != 0) ? 1 : 0;
+  ++h->state_version;  // every cached linearisation is stale
+  h->built = h->solved = false;
+  if (h->lm_graph) { cudaGraphExecDestroy(h->lm_graph); h->lm_graph = nullptr; }  // captured with the old kernel arguments
+}
+}  // namespace
+
+kb_status kb_set_inv_r(kb_handle* h, const double inv_r[4]) {
+  if (!inv_r) return fail(h, KB_ERR_INVALID_ARGUMENT, "null invR");
+  const double a00 = inv_r[0], a01 = inv_r[1], a10 = inv_r[2], a11 = inv_r[3];
+  if (!(std::fabs(a01 - a10) <= 1e-12 * (std::fabs(a00) + std::fabs(a11))) || !(a00 > 0.0) || !(a11 > 0.0) || !(a00 * a11 - a01 * a10 > 0.0))
+    return fail(h, KB_ERR_INVALID_ARGUMENT, "invR must be symmetric positive definite");
+  // sm::eigen::computeMatrixSqrt (Schweizer-Messer/sm_eigen/include/sm/eigen/matrix_sqrt.hpp:21-40): S = P^T L sqrt(D) of the
+  // pivoted LDL^T (the larger diagonal entry is eliminated first, the first one on ties; the lower triangle is read)
+  const bool swap = std::fabs(a11) > std::fabs(a00);
+  const double d0 = swap ? a11 : a00, dd = swap ? a00 : a11;
+  const double l10 = a10 / d0;
+  const double d1 = dd - l10 * (d0 * l10);
+  const double s0 = std::sqrt(d0), s1 = std::sqrt(d1);
+  double* S = h->sqrt_inv_r;
+  if (!swap) { S[0] = s0; S[1] = 0.0; S[2] = l10 * s0; S[3] = s1; }
+  else { S[0] = l10 * s0; S[1] = s1; S[2] = s0; S[3] = 0.0; }
+  for (int i = 0; i < 4; ++i) h->inv_r[i] = inv_r[i];
+  weighting_changed(h);
+  return KB_OK;
+}
+kb_status kb_get_sqrt_inv_r(const kb_handle* h, double out[4]) {
+  for (int i = 0; i < 4; ++i) out[i] = h->sqrt_inv_r[i];
+  return KB_OK;
+}
+
+kb_status kb_set_m_estimator(kb_handle* h, int32_t kind, double p0, double p1, double p2) {
+  double prm = 0.0;
+  switch (kind) {
+    case KB_MEST_NONE: break;
+    case KB_MEST_HUBER:
+    case KB_MEST_CAUCHY:
+    case KB_MEST_GEMAN_MCCLURE:
+      if (!(p0 > 0.0)) return fail(h, KB_ERR_INVALID_ARGUMENT, "the M-estimator parameter must be positive");
+      prm = p0;
+      break;
+    case KB_MEST_BLAKE_ZISSERMAN: {  // BlakeZissermanMEstimator(df, pCut, wCut): MEstimatorPolicies.cpp:80-86, 116-124
+      const double df = p0, p_cut = p1, w_cut = p2;
+      if (!(df >= 1.0) || !(p_cut > 0.0 && p_cut < 1.0) || !(w_cut > 0.0 && w_cut < 1.0))
+        return fail(h, KB_ERR_INVALID_ARGUMENT, "Blake-Zisserman needs df >= 1, 0 < pCut < 1, 0 < wCut < 1");
+      prm = (1.0 - w_cut) / w_cut * std::exp(-chi2_quantile(p_cut, std::floor(df)));
+      break;
+    }
+    default: return fail(h, KB_ERR_INVALID_ARGUMENT, "unknown M-estimator kind");
+  }
+  h->d.mest_kind = kind;
+  h->d.mest_param = prm;
+  h->d.mest_rows = kind != KB_MEST_NONE ? 1 : 0;
+  weighting_changed(h);
+  return KB_OK;
+}
+double kb_m_estimator_parameter(const kb_handle* h) { return h->d.mest_param; }
+
+// ---- reprojection statistics ≙ CameraCalibrator::PrintReprojectionErrorStatistics (K2/include/kalibr2/CameraCalibrator.hpp:368-405)
+kb_status kb_reprojection_statistics(kb_handle* h, double* out) {
+  if (!out) return fail(h, KB_ERR_INVALID_ARGUMENT, "null output");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  if (h->stats_e.n < (size_t)2 * std::max<int64_t>(h->n_terms_local, 1)) KB_CUDA(h, h->stats_e.alloc((size_t)2 * std::max<int64_t>(h->n_terms_local, 1)));
+  if (h->stats_acc.n < (size_t)8 * h->n_cams) KB_CUDA(h, h->stats_acc.alloc((size_t)8 * h->n_cams));
+  // raw residuals y - y_hat at the current state (getMeasurement() - getPredictedMeasurement(), CameraCalibrator.hpp:267-286):
+  // the residual-only kernel, unweighted, into a scratch vector so that e() keeps what the last evaluation wrote
+  DevProblem q = h->d;
+  q.weighted = 0;
+  q.e = h->stats_e.p;
+  KB_CUDA(h, launch_prep(q, c));
+  KB_CUDA(h, launch_evaluate(q, h->view_list.p, h->model_begin, h->scalars.p + 7, c));
+  KB_CUDA(h, launch_reproj_stats(q, h->stats_e.p, h->cam_view_list.p, h->cam_view_begin.p, 0, h->stats_acc.p, c));
+  if (h->n_ranks > 1) {  // make (n, sum e_u, sum e_v) global before the second pass
+    kb_status st = nccl_allreduce(h, h->stats_acc.p, (size_t)8 * h->n_cams, kNcclFloat64, kNcclSum);
+    if (st != KB_OK) return st;
+  }
+  KB_CUDA(h, launch_reproj_stats(q, h->stats_e.p, h->cam_view_list.p, h->cam_view_begin.p, 1, h->stats_acc.p, c));
+  std::vector<double> acc((size_t)8 * h->n_cams, 0.0), acc1;
+  KB_CUDA(h, cudaMemcpyAsync(acc.data(), h->stats_acc.p, sizeof(double) * acc.size(), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->n_ranks > 1) {  // the squared deviations: sum over ranks (slots 0..3 were already global: keep one copy)
+    acc1 = acc;
+    for (int k = 0; k < h->n_cams; ++k) for (int i = 0; i < 4; ++i) acc1[8 * k + i] = 0.0;
+    KB_CUDA(h, cudaMemcpyAsync(h->stats_acc.p, acc1.data(), sizeof(double) * acc1.size(), cudaMemcpyHostToDevice, h->stream));
+    kb_status st = nccl_allreduce(h, h->stats_acc.p, (size_t)8 * h->n_cams, kNcclFloat64, kNcclSum);
+    if (st != KB_OK) return st;
+    KB_CUDA(h, cudaMemcpyAsync(acc1.data(), h->stats_acc.p, sizeof(double) * acc1.size(), cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < h->n_cams; ++k) for (int i = 4; i < 8; ++i) acc[8 * k + i] = acc1[8 * k + i];
+  }
+  for (int k = 0; k < h->n_cams; ++k) {
+    const double* a = &acc[8 * k];
+    double* o = out + (size_t)k * KB_REPROJ_STAT_STRIDE;
+    const double n = a[0];
+    o[0] = n;
+    o[1] = n > 0 ? a[1] / n : 0.0;
+    o[2] = n > 0 ? a[2] / n : 0.0;
+    o[3] = n > 1 ? std::sqrt(a[4] / (n - 1.0)) : 0.0;  // sample standard deviation; zero below two samples (:384-397)
+    o[4] = n > 1 ? std::sqrt(a[5] / (n - 1.0)) : 0.0;
+    o[5] = n > 0 ? std::sqrt(a[1] * a[1] + a[2] * a[2]) / std::sqrt(n) : 0.0;  // "RMSE" as printed: |sum of errors| / sqrt(n) (:404)
+  }
+  return KB_OK;
 }
 
 // ---- marginal analysis of the calibration block ----------------------------------------------------------------------

@@ -303,7 +303,32 @@ __device__ __forceinline__ void view_transform_prepped(const double* __restrict_
 // =========================================================================================================
 constexpr int EVAL_THREADS = 256;
 
-template <int MODEL>
+// M-estimator weight of a term from its raw squared error e^T invR e (BE/src/MEstimatorPolicies.cpp:16-21 none, :61-75 Huber,
+// :41-57 Cauchy, :23-39 Geman-McClure, :101-103 Blake-Zisserman with epsilon precomputed on the host as in :121-124)
+__device__ __forceinline__ double mest_weight(int kind, double prm, double s) {
+  switch (kind) {
+    case 1: return s < prm * prm ? 1.0 : prm / sqrt(s);
+    case 2: return 1.0 / (1.0 + s / prm);
+    case 3: { const double se = prm + s; return prm / (se * se); }
+    case 4: { const double ex = exp(-s); return ex / (ex + prm); }
+  }
+  return 1.0;
+}
+// The weighting of one term: t = sqrtInvR^T e, raw = t^T t = e^T invR e, w = policy(raw).  Returns the 2x2 matrix
+// A = sw sqrtInvR^T (row-major a, b, c, d) that turns the raw rows into the weighted ones (sw = sqrt(w) when the M-estimator
+// also scales rows, else 1), replaces (e0, e1) by A e and gives the term's cost contribution w * raw.
+__device__ __forceinline__ double term_weighting(const DevProblem& p, double& e0, double& e1, double& a, double& b, double& c, double& d) {
+  const double t0 = p.sT[0] * e0 + p.sT[1] * e1, t1 = p.sT[2] * e0 + p.sT[3] * e1;
+  const double raw = t0 * t0 + t1 * t1;
+  const double w = mest_weight(p.mest_kind, p.mest_param, raw);
+  const double sw = p.mest_rows ? sqrt(w) : 1.0;
+  a = sw * p.sT[0]; b = sw * p.sT[1]; c = sw * p.sT[2]; d = sw * p.sT[3];
+  e0 = sw * t0;
+  e1 = sw * t1;
+  return w * raw;
+}
+
+template <int MODEL, bool WEIGHTED>
 __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(DevProblem p, const int* __restrict__ view_list, int n_list) {
   extern __shared__ double smem_target[];
   for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) smem_target[i] = p.target[i];
@@ -334,11 +359,58 @@ __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(DevProblem p, co
         e1 = 0.0;
         atomicAdd(p.n_invalid, 1u);
       }
+      if (WEIGHTED) {
+        double wa, wb, wc, wd;
+        cost += term_weighting(p, e0, e1, wa, wb, wc, wd);
+      } else {
+        cost += e0 * e0 + e1 * e1;
+      }
       reinterpret_cast<double2*>(p.e)[i] = make_double2(-e0, -e1);
-      cost += e0 * e0 + e1 * e1;
     }
     cost = warp_sum(cost);
     if (lane == 0) p.view_cost[view] = cost;
+  }
+}
+
+// per camera: sums of the raw residuals (pass 0) and of their squared deviations from the mean (pass 1) over the camera's views, in
+// a fixed order (thread-strided, then the block tree).  acc[cam] = {n, sum e_u, sum e_v, -, ssd_u, ssd_v, -, -}; between the passes
+// the host makes the first three global (multi-rank).  ≙ K2/include/kalibr2/CameraCalibrator.hpp:368-405 (two-pass mean / variance)
+__global__ void __launch_bounds__(1024) reproj_stats_kernel(DevProblem p, const double* __restrict__ e_raw, const int* __restrict__ cam_view_list,
+                                                            const int* __restrict__ cam_view_begin, int pass, double* __restrict__ acc) {
+  __shared__ double sh[3][32];
+  const int cam = blockIdx.x;
+  double* a = acc + cam * 8;
+  double mu = 0.0, mv = 0.0;
+  if (pass == 1 && a[0] > 0.0) {
+    mu = a[1] / a[0];
+    mv = a[2] / a[0];
+  }
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int vi = cam_view_begin[cam]; vi < cam_view_begin[cam + 1]; ++vi) {
+    const int view = cam_view_list[vi];
+    const int b = p.view_begin[view], e = p.view_begin[view + 1];
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const double2 r = reinterpret_cast<const double2*>(e_raw)[i];
+      const double eu = -r.x, ev = -r.y;  // y - y_hat
+      if (pass == 0) {
+        s0 += 1.0;
+        s1 += eu;
+        s2 += ev;
+      } else {
+        s1 += (eu - mu) * (eu - mu);
+        s2 += (ev - mv) * (ev - mv);
+      }
+    }
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s0; sh[1][threadIdx.x >> 5] = s1; sh[2][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s0 = warp_sum(sh[0][threadIdx.x]); s1 = warp_sum(sh[1][threadIdx.x]); s2 = warp_sum(sh[2][threadIdx.x]);
+    if (threadIdx.x == 0) {
+      if (pass == 0) { a[0] = s0; a[1] = s1; a[2] = s2; a[3] = 0.0; }
+      else { a[4] = s1; a[5] = s2; a[6] = 0.0; a[7] = 0.0; }
+    }
   }
 }
 
@@ -368,9 +440,9 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ v,
 constexpr int XT_LD = 68;  // 64 rows (32 terms x 2) + 4: conflict-free for the row stores and the DMMA operand loads
 constexpr int XT_WARP_DOUBLES = GRAM_DIM * XT_LD;
 
-template <int MODEL>
-__device__ __forceinline__ bool term_rows(const double* __restrict__ prm, const double Rcw[9], const double tcw[3], const double* __restrict__ pt,
-                                          double yu, double yv, double* __restrict__ xt_lane, double& e0, double& e1) {
+template <int MODEL, bool WEIGHTED>
+__device__ __forceinline__ bool term_rows(const DevProblem& p, const double* __restrict__ prm, const double Rcw[9], const double tcw[3],
+                                          const double* __restrict__ pt, double yu, double yv, double* __restrict__ xt_lane, double& e0, double& e1) {
   using Cam = Camera<MODEL, true, true>;  // negated Jacobians: e = y - y_hat
   constexpr int P = Cam::P, D = Cam::D;
   const double pc[3] = {Rcw[0] * pt[0] + Rcw[1] * pt[1] + Rcw[2] * pt[2] + tcw[0], Rcw[3] * pt[0] + Rcw[4] * pt[1] + Rcw[5] * pt[2] + tcw[1],
@@ -379,23 +451,52 @@ __device__ __forceinline__ bool term_rows(const double* __restrict__ prm, const 
   Cam::eval(prm, pc, L);
   e0 = yu - L.y[0];
   e1 = yv - L.y[1];
+  if constexpr (!WEIGHTED) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    double* __restrict__ x = xt_lane + 32 * r;
-    const double j0 = L.Jp[r][0], j1 = L.Jp[r][1], j2 = L.Jp[r][2];  // = -Jp
-    x[0 * XT_LD] = j0;
-    x[1 * XT_LD] = j1;
-    x[2 * XT_LD] = j2;
-    x[3 * XT_LD] = j1 * pc[2] - j2 * pc[1];
-    x[4 * XT_LD] = j2 * pc[0] - j0 * pc[2];
-    x[5 * XT_LD] = j0 * pc[1] - j1 * pc[0];
+    for (int r = 0; r < 2; ++r) {
+      double* __restrict__ x = xt_lane + 32 * r;
+      const double j0 = L.Jp[r][0], j1 = L.Jp[r][1], j2 = L.Jp[r][2];  // = -Jp
+      x[0 * XT_LD] = j0;
+      x[1 * XT_LD] = j1;
+      x[2 * XT_LD] = j2;
+      x[3 * XT_LD] = j1 * pc[2] - j2 * pc[1];
+      x[4 * XT_LD] = j2 * pc[0] - j0 * pc[2];
+      x[5 * XT_LD] = j0 * pc[1] - j1 * pc[0];
 #pragma unroll
-    for (int c = 0; c < P; ++c) x[(6 + c) * XT_LD] = L.Ji[r][c];
+      for (int c = 0; c < P; ++c) x[(6 + c) * XT_LD] = L.Ji[r][c];
 #pragma unroll
-    for (int c = 0; c < D; ++c) x[(6 + P + c) * XT_LD] = L.Jd[r][c];
+      for (int c = 0; c < D; ++c) x[(6 + P + c) * XT_LD] = L.Jd[r][c];
 #pragma unroll
-    for (int c = 6 + P + D; c < E_COL; ++c) x[c * XT_LD] = 0.0;
-    x[E_COL * XT_LD] = r == 0 ? e0 : e1;
+      for (int c = 6 + P + D; c < E_COL; ++c) x[c * XT_LD] = 0.0;
+      x[E_COL * XT_LD] = r == 0 ? e0 : e1;
+    }
+  } else {
+    // weighted rows: [u-row; v-row] <- sqrt(w) sqrtInvR^T [u-row; v-row], column by column
+    double wa, wb, wc, wd;
+    if (L.valid) term_weighting(p, e0, e1, wa, wb, wc, wd);
+    else { wa = wb = wc = wd = 0.0; }
+    auto put = [&](int col, double u, double v) {
+      xt_lane[col * XT_LD] = wa * u + wb * v;
+      xt_lane[col * XT_LD + 32] = wc * u + wd * v;
+    };
+    const double u0 = L.Jp[0][0], u1 = L.Jp[0][1], u2 = L.Jp[0][2], v0 = L.Jp[1][0], v1 = L.Jp[1][1], v2 = L.Jp[1][2];
+    put(0, u0, v0);
+    put(1, u1, v1);
+    put(2, u2, v2);
+    put(3, u1 * pc[2] - u2 * pc[1], v1 * pc[2] - v2 * pc[1]);
+    put(4, u2 * pc[0] - u0 * pc[2], v2 * pc[0] - v0 * pc[2]);
+    put(5, u0 * pc[1] - u1 * pc[0], v0 * pc[1] - v1 * pc[0]);
+#pragma unroll
+    for (int c = 0; c < P; ++c) put(6 + c, L.Ji[0][c], L.Ji[1][c]);
+#pragma unroll
+    for (int c = 0; c < D; ++c) put(6 + P + c, L.Jd[0][c], L.Jd[1][c]);
+#pragma unroll
+    for (int c = 6 + P + D; c < E_COL; ++c) {
+      xt_lane[c * XT_LD] = 0.0;
+      xt_lane[c * XT_LD + 32] = 0.0;
+    }
+    xt_lane[E_COL * XT_LD] = e0;       // already A e
+    xt_lane[E_COL * XT_LD + 32] = e1;
   }
   return L.valid;
 }
@@ -432,7 +533,7 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-template <int MODEL, bool WRITE_E>
+template <int MODEL, bool WRITE_E, bool WEIGHTED>
 __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevProblem p, const int4* __restrict__ vmeta,
                                                                             const int4* __restrict__ slices, int slice_lo, int slice_hi) {
   extern __shared__ __align__(16) double smem[];
@@ -511,7 +612,7 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
         const int n = min(32, e - base);
         const int kq = (n + 3) >> 2;  // DMMA k-steps per row half: a partial last chunk only spends DMMAs on rows that exist
         double e0, e1;
-        const bool valid = term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, XT + lane, e0, e1);
+        const bool valid = term_rows<MODEL, WEIGHTED>(p, prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, XT + lane, e0, e1);
         if (cactive && !valid) atomicAdd(p.n_invalid, 1u);
         const bool keep = cactive && valid;
         if (__any_sync(0xffffffffu, !keep && lane < 4 * kq)) {
@@ -578,7 +679,7 @@ constexpr int LM_SUB = 4;  // sub-slices per slice of the fused kernel's slice t
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream2(double* p, double v0, double v1) { __stcs(reinterpret_cast<double2*>(p), make_double2(v0, v1)); }
 
-template <int MODEL>
+template <int MODEL, bool WEIGHTED>
 __global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(DevProblem p, const int4* __restrict__ vmeta, const int4* __restrict__ slices,
                                                                                int slice_lo, int slice_hi, double* __restrict__ jt, int bfrag_pairs,
                                                                                unsigned int* __restrict__ work_counter) {
@@ -685,7 +786,7 @@ __global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(De
         if (base + 32 < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
         {
           double e0, e1;
-          const bool valid = term_rows<MODEL>(prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, XT + lane, e0, e1);
+          const bool valid = term_rows<MODEL, WEIGHTED>(p, prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, XT + lane, e0, e1);
           if (cactive && !valid) atomicAdd(p.n_invalid, 1u);
           if (__any_sync(0xffffffffu, cactive && !valid)) {
             if (cactive && !valid) {
@@ -1880,7 +1981,8 @@ static cudaError_t launch_evaluate_model(const DevProblem& p, const int* list, i
   if (n <= 0) return cudaSuccess;
   const int warps_per_cta = EVAL_THREADS / 32;
   const int grid = min((n + warps_per_cta - 1) / warps_per_cta, sm_count() * 8);
-  evaluate_kernel<MODEL><<<grid, EVAL_THREADS, sizeof(double) * p.n_target * 3, s.stream>>>(p, list, n);
+  if (p.weighted) evaluate_kernel<MODEL, true><<<grid, EVAL_THREADS, sizeof(double) * p.n_target * 3, s.stream>>>(p, list, n);
+  else evaluate_kernel<MODEL, false><<<grid, EVAL_THREADS, sizeof(double) * p.n_target * 3, s.stream>>>(p, list, n);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -1904,21 +2006,28 @@ cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int
   return cudaGetLastError();
 }
 
+cudaError_t launch_reproj_stats(const DevProblem& p, const double* e_raw, const int* cam_view_list, const int* cam_view_begin, int pass, double* acc,
+                                StreamCtx& s) {
+  reproj_stats_kernel<<<p.n_cams, 1024, 0, s.stream>>>(p, e_raw, cam_view_list, cam_view_begin, pass, acc);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+
 int la_grid_warps() { return sm_count() * 2 * LA_WARPS; }
 
-template <int MODEL, bool WRITE_E>
+template <int MODEL, bool WRITE_E, bool WEIGHTED>
 static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const int4* slices, int lo, int hi, StreamCtx& s) {
   if (hi <= lo) return cudaSuccess;
   const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
   size_t& attr_smem = attr_smem_dev[cur_device()];
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(linearise_assemble_kernel<MODEL, WRITE_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
   const int grid = min((hi - lo + LA_WARPS - 1) / LA_WARPS, sm_count() * 2);
-  linearise_assemble_kernel<MODEL, WRITE_E><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
+  linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -1933,8 +2042,13 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, co
   }
   e = for_each_model_concurrently(smb, s, [&](int m, StreamCtx& c) -> cudaError_t {
     switch (m) {
-#define KB_LA(M) \
-  case M: return write_e ? launch_la_model<M, true>(p, vmeta, slices, smb[M], smb[M + 1], c) : launch_la_model<M, false>(p, vmeta, slices, smb[M], smb[M + 1], c);
+#define KB_LA(M)                                                                                                                      \
+  case M:                                                                                                                             \
+    if (p.weighted)                                                                                                                   \
+      return write_e ? launch_la_model<M, true, true>(p, vmeta, slices, smb[M], smb[M + 1], c)                                       \
+                     : launch_la_model<M, false, true>(p, vmeta, slices, smb[M], smb[M + 1], c);                                     \
+    return write_e ? launch_la_model<M, true, false>(p, vmeta, slices, smb[M], smb[M + 1], c)                                        \
+                   : launch_la_model<M, false, false>(p, vmeta, slices, smb[M], smb[M + 1], c);
       KB_LA(0) KB_LA(1) KB_LA(2) KB_LA(3) KB_LA(4) KB_LA(5) KB_LA(6)
 #undef KB_LA
     }
@@ -1952,7 +2066,7 @@ cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range
   return cudaGetLastError();
 }
 
-template <int MODEL>
+template <int MODEL, bool WEIGHTED>
 static cudaError_t launch_lm_model(const DevProblem& p, const int4* vmeta, const int4* slices, int lo, int hi, double* jt, int bfrag_pairs,
                                    unsigned int* counter, StreamCtx& s) {
   if (hi <= lo) return cudaSuccess;
@@ -1960,13 +2074,13 @@ static cudaError_t launch_lm_model(const DevProblem& p, const int4* vmeta, const
   static size_t attr_smem_dev[MAX_DEVICES] = {};
   size_t& attr_smem = attr_smem_dev[cur_device()];
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(linearise_materialise_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(linearise_materialise_kernel<MODEL, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
   const int ctas_per_sm = (int)max((size_t)1, min((size_t)4, (size_t)(220 * 1024) / (smem + 1024)));
   const int grid = min(((hi - lo) * LM_SUB + LM_WARPS - 1) / LM_WARPS, sm_count() * ctas_per_sm);
-  linearise_materialise_kernel<MODEL><<<grid, LM_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi, jt, bfrag_pairs, counter);
+  linearise_materialise_kernel<MODEL, WEIGHTED><<<grid, LM_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi, jt, bfrag_pairs, counter);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -1983,8 +2097,10 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
   }
   e = for_each_model_concurrently(smb, s, [&](int m, StreamCtx& c) -> cudaError_t {
     switch (m) {
-#define KB_LM(M) \
-  case M: return launch_lm_model<M>(p, vmeta, slices, smb[M], smb[M + 1], jt, bfrag_pairs[M], counters + M, c);
+#define KB_LM(M)                                                                                                          \
+  case M:                                                                                                                 \
+    return p.weighted ? launch_lm_model<M, true>(p, vmeta, slices, smb[M], smb[M + 1], jt, bfrag_pairs[M], counters + M, c) \
+                      : launch_lm_model<M, false>(p, vmeta, slices, smb[M], smb[M + 1], jt, bfrag_pairs[M], counters + M, c);
       KB_LM(0) KB_LM(1) KB_LM(2) KB_LM(3) KB_LM(4) KB_LM(5) KB_LM(6)
 #undef KB_LM
     }

@@ -8,6 +8,7 @@
 // Cholesky of the whole matrix is kept as a cross-check.
 //
 // K2 = aslam_offline_calibration/kalibr2/include/kalibr2, BE = aslam_optimizer/aslam_backend.
+#include <array>
 #include <chrono>
 #include <cstdio>
 
@@ -64,6 +65,7 @@ struct LinearSystemSolver {
   std::vector<double> e, rhs, diagonalConditioner;
   size_t JRows = 0, JCols = 0;
   bool useDiagonalConditioner = true;
+  bool useMEstimator = true;  // Optimizer2 always passes true (Optimizer2.cpp:198, 237; LevenbergMarquardtTrustRegionPolicy.cpp:56, 72)
   virtual ~LinearSystemSolver() {}
   // LinearSystemSolver.cpp:12-23, 81-92
   double evaluateError(size_t nThreads) {
@@ -74,7 +76,7 @@ struct LinearSystemSolver {
           for (size_t i = a; i < b; ++i) {
             threadLocalErrors[tid] += errorTerms[i]->evaluateError();
             double we[2];
-            errorTerms[i]->getWeightedError(we);
+            errorTerms[i]->getWeightedError(we, useMEstimator);
             e[errorTerms[i]->rowBase] = -we[0];
             e[errorTerms[i]->rowBase + 1] = -we[1];
           }
@@ -434,7 +436,7 @@ struct BlockCholeskyLinearSystemSolver : LinearSystemSolver {
   void buildSystem(size_t /*nThreads: ignored, serial by design*/) override {
     H.clear(false);
     std::fill(rhs.begin(), rhs.end(), 0.0);
-    for (auto* t : errorTerms) t->buildHessian(H, rhs);
+    for (auto* t : errorTerms) t->buildHessian(H, rhs, useMEstimator);
   }
   bool solveSystem(std::vector<double>& dx) override {
     if (useDiagonalConditioner) {
@@ -491,7 +493,7 @@ struct SparseCholeskyLinearSystemSolver : LinearSystemSolver {
         [&](size_t, size_t a, size_t b) {
           for (size_t i = a; i < b; ++i) {
             JacobianContainer jc(2);
-            errorTerms[i]->getWeightedJacobians(jc);
+            errorTerms[i]->getWeightedJacobians(jc, useMEstimator);
             for (int r = 0; r < 2; ++r) {
               double* out = &Jt.values[Jt.col_ptr[2 * i + r]];
               for (auto& kv : jc.jacobianMap)
@@ -738,7 +740,7 @@ __attribute__((visibility("default"))) int64_t ko_get_jacobian_ccs(ko_problem* h
       [&](size_t, size_t a, size_t b) {
         for (size_t i = a; i < b; ++i) {
           JacobianContainer jc(2);
-          P.errorTerms[i]->getWeightedJacobians(jc);
+          P.errorTerms[i]->getWeightedJacobians(jc, P.solver->useMEstimator);
           for (int r = 0; r < 2; ++r) {
             int64_t o = cp[2 * i + r];
             for (auto& kv : jc.jacobianMap)
@@ -785,7 +787,7 @@ __attribute__((visibility("default"))) int32_t ko_analyze_marginal(ko_problem* h
   std::vector<double> Al(m * (size_t)nl, 0.0), Ar(m * (size_t)nr, 0.0);
   for (size_t i = 0; i < P.errorTerms.size(); ++i) {
     JacobianContainer jc(2);
-    P.errorTerms[i]->getWeightedJacobians(jc);
+    P.errorTerms[i]->getWeightedJacobians(jc, P.solver->useMEstimator);
     for (int r = 0; r < 2; ++r)
       for (auto& kv : jc.jacobianMap)
         for (int c = 0; c < kv.second.c; ++c) {
@@ -898,6 +900,89 @@ __attribute__((visibility("default"))) void ko_inverse4(const double* M16_rowmaj
   Mat I = inverse4(M);
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) out16_rowmajor[i * 4 + j] = I(i, j);
+}
+
+// ---- weighting: ErrorTermFs<2>::setInvR / ErrorTerm::setMEstimatorPolicy on every term -------------------------------------
+__attribute__((visibility("default"))) void ko_set_inv_r(ko_problem* h, const double* invR_rowmajor) {
+  Mat A(2, 2);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) A(i, j) = invR_rowmajor[i * 2 + j];
+  for (auto* t : h->P->errorTerms) t->setInvR(A);
+}
+// kind = kb_m_estimator; parameters as kb_set_m_estimator.  Returns the policy's derived parameter (epsilon for Blake-Zisserman).
+__attribute__((visibility("default"))) double ko_set_m_estimator(ko_problem* h, int kind, double p0, double p1, double p2) {
+  std::shared_ptr<MEstimator> m;
+  double prm = p0;
+  switch (kind) {
+    case 1: m = std::make_shared<HuberMEstimator>(p0); break;
+    case 2: m = std::make_shared<CauchyMEstimator>(p0); break;
+    case 3: m = std::make_shared<GemanMcClureMEstimator>(p0); break;
+    case 4: {
+      auto bz = std::make_shared<BlakeZissermanMEstimator>((size_t)p0, p1, p2);
+      prm = bz->epsilon;
+      m = bz;
+      break;
+    }
+    default: m = std::make_shared<NoMEstimator>(); prm = 0.0;
+  }
+  for (auto* t : h->P->errorTerms) t->setMEstimatorPolicy(m);  // one shared policy object, as kalibr's Python tooling did
+  return prm;
+}
+__attribute__((visibility("default"))) void ko_set_use_m_estimator(ko_problem* h, int on) { h->P->solver->useMEstimator = on != 0; }
+__attribute__((visibility("default"))) double ko_chi2_inv_cdf(double p, int df) { return chi2InvCDF(p, (size_t)df); }
+__attribute__((visibility("default"))) double ko_m_estimator_weight(int kind, double p0, double p1, double p2, double squaredError) {
+  switch (kind) {
+    case 1: return HuberMEstimator(p0).getWeight(squaredError);
+    case 2: return CauchyMEstimator(p0).getWeight(squaredError);
+    case 3: return GemanMcClureMEstimator(p0).getWeight(squaredError);
+    case 4: return BlakeZissermanMEstimator((size_t)p0, p1, p2).getWeight(squaredError);
+  }
+  return NoMEstimator().getWeight(squaredError);
+}
+__attribute__((visibility("default"))) void ko_matrix_sqrt2(const double* A_rowmajor, double* S_rowmajor) {
+  Mat A(2, 2);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) A(i, j) = A_rowmajor[i * 2 + j];
+  Mat S = computeMatrixSqrt2(A);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) S_rowmajor[i * 2 + j] = S(i, j);
+}
+
+// ---- K2/include/kalibr2/CameraCalibrator.hpp:267-286, 368-405: PrintReprojectionErrorStatistics per camera ------------------
+// out[cam] = {n, mean_u, mean_v, std_u, std_v, rmse}; error values = getMeasurement() - getPredictedMeasurement() at the current state
+__attribute__((visibility("default"))) void ko_reprojection_statistics(ko_problem* h, double* out) {
+  Problem& P = *h->P;
+  for (int k = 0; k < P.nCams; ++k) {
+    std::vector<std::array<double, 2>> error_values;
+    for (size_t i = 0; i < P.errorTerms.size(); ++i) {
+      if (P.termCam[i] != k) continue;
+      ReprojectionError* t = P.errorTerms[i];
+      double p4[4], hat_y[2] = {0.0, 0.0};
+      t->point.toHomogeneous(p4);
+      t->camera->camera->homogeneousToKeypoint(p4, hat_y);
+      error_values.push_back({t->y[0] - hat_y[0], t->y[1] - hat_y[1]});
+    }
+    double* o = out + 6 * k;
+    for (int i = 0; i < 6; ++i) o[i] = 0.0;
+    const double n = (double)error_values.size();
+    o[0] = n;
+    if (error_values.empty()) continue;
+    double sum[2] = {0.0, 0.0};
+    for (auto& e : error_values) { sum[0] += e[0]; sum[1] += e[1]; }
+    const double mean[2] = {sum[0] / n, sum[1] / n};
+    double ssd[2] = {0.0, 0.0};
+    if (error_values.size() > 1) {
+      for (auto& e : error_values) {
+        ssd[0] += (e[0] - mean[0]) * (e[0] - mean[0]);
+        ssd[1] += (e[1] - mean[1]) * (e[1] - mean[1]);
+      }
+      o[3] = std::sqrt(ssd[0] / (n - 1.0));
+      o[4] = std::sqrt(ssd[1] / (n - 1.0));
+    }
+    o[1] = mean[0];
+    o[2] = mean[1];
+    o[5] = std::sqrt(sum[0] * sum[0] + sum[1] * sum[1]) / std::sqrt(n);  // sum_of_errors.norm() / sqrt(size), as printed
+  }
 }
 
 // CPU baseline timing: one LM-iteration's worth of hot path (evaluate + build + solve) at the current state,

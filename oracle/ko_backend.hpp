@@ -326,21 +326,138 @@ inline void evaluateHessian(const JacobianContainer& jc, const double e[2], cons
   }
 }
 
+// ---- BE/src/MEstimatorPolicies.cpp:13-125, BE/include/aslam/backend/MEstimatorPolicies.hpp ---------
+struct MEstimator {
+  virtual ~MEstimator() {}
+  virtual double getWeight(double squaredError) const = 0;
+};
+struct NoMEstimator : MEstimator {  // MEstimatorPolicies.cpp:16-21
+  double getWeight(double) const override { return 1.0; }
+};
+struct GemanMcClureMEstimator : MEstimator {  // :23-39
+  double sigma2;
+  explicit GemanMcClureMEstimator(double s2) : sigma2(s2) {}
+  double getWeight(double error) const override {
+    const double se = sigma2 + error;
+    return sigma2 / (se * se);
+  }
+};
+struct CauchyMEstimator : MEstimator {  // :41-57
+  double sigma2;
+  explicit CauchyMEstimator(double s2) : sigma2(s2) {}
+  double getWeight(double error) const override {
+    const double se = error / sigma2;
+    return 1.0 / (1.0 + se);
+  }
+};
+struct HuberMEstimator : MEstimator {  // :61-75
+  double k, k2;
+  explicit HuberMEstimator(double k_) : k(k_), k2(k_ * k_) {}
+  double getWeight(double error) const override { return error < k2 ? 1.0 : k / std::sqrt(error); }
+};
+// Quantile of the chi-squared distribution.  The reference calls boost::math::quantile(chi_squared_distribution<>(df), p)
+// (MEstimatorPolicies.cpp:116-119; Boost.Math is a third-party dependency that is absent here, apt libboost-all-dev, unpinned:
+// packages-ubuntu-24.04.txt).  Restated from the definition: the x with P(df/2, x/2) = p, P the regularised lower incomplete
+// gamma function (series for x < a + 1, Lentz continued fraction otherwise), solved by bisection then Newton; checked against
+// scipy.stats.chi2.ppf in tests/test_oracle_cpu.py.
+inline double regularizedGammaP(double a, double x) {
+  if (x <= 0.0) return 0.0;
+  const double lg = std::lgamma(a);
+  if (x < a + 1.0) {
+    double sum = 1.0 / a, term = sum;
+    for (int n = 1; n < 10000; ++n) {
+      term *= x / (a + n);
+      sum += term;
+      if (std::fabs(term) < std::fabs(sum) * 1e-17) break;
+    }
+    return sum * std::exp(-x + a * std::log(x) - lg);
+  }
+  const double tiny = 1e-300;
+  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+  for (int i = 1; i < 10000; ++i) {
+    const double an = -i * (i - a);
+    b += 2.0;
+    d = an * d + b;
+    if (std::fabs(d) < tiny) d = tiny;
+    c = b + an / c;
+    if (std::fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (std::fabs(del - 1.0) < 1e-17) break;
+  }
+  return 1.0 - std::exp(-x + a * std::log(x) - lg) * h;
+}
+inline double chi2InvCDF(double p, size_t df) {
+  const double a = 0.5 * (double)df;
+  double lo = 0.0, hi = std::max(1.0, 2.0 * a);
+  while (regularizedGammaP(a, 0.5 * hi) < p) hi *= 2.0;
+  for (int i = 0; i < 200; ++i) {
+    const double mid = 0.5 * (lo + hi);
+    if (regularizedGammaP(a, 0.5 * mid) < p) lo = mid; else hi = mid;
+  }
+  double x = 0.5 * (lo + hi);
+  for (int i = 0; i < 3; ++i) {  // Newton polish: pdf of chi2(df)
+    const double pdf = std::exp((a - 1.0) * std::log(0.5 * x) - 0.5 * x - std::lgamma(a)) * 0.5;
+    if (!(pdf > 0.0)) break;
+    const double nx = x - (regularizedGammaP(a, 0.5 * x) - p) / pdf;
+    if (nx > lo && nx < hi) x = nx;
+  }
+  return x;
+}
+struct BlakeZissermanMEstimator : MEstimator {  // :77-123
+  size_t df;
+  double pCut, wCut, epsilon;
+  explicit BlakeZissermanMEstimator(size_t df_, double pCut_ = 0.999, double wCut_ = 0.1)
+      : df(df_), pCut(pCut_), wCut(wCut_), epsilon(computeEpsilon(df_, pCut_, wCut_)) {}
+  double getWeight(double mahalanobis2) const override { return std::exp(-mahalanobis2) / (std::exp(-mahalanobis2) + epsilon); }
+  static double computeEpsilon(size_t df, double pCut, double wCut) { return (1 - wCut) / wCut * std::exp(-chi2InvCDF(pCut, df)); }
+};
+
+// Schweizer-Messer/sm_eigen/include/sm/eigen/matrix_sqrt.hpp:21-40 for a 2x2 matrix: S = P^T L sqrt(D) of Eigen::LDLT, which
+// pivots on the larger diagonal entry (first one on ties); A = S S^T.  Eigen (libeigen3-dev, unpinned; noble ships 3.4.0) is absent:
+// restated from Eigen/src/Cholesky/LDLT.h (ldlt_inplace<Lower>::unblocked).
+inline Mat computeMatrixSqrt2(const Mat& A) {
+  const bool swap = std::fabs(A(1, 1)) > std::fabs(A(0, 0));
+  const double a = swap ? A(1, 1) : A(0, 0), d = swap ? A(0, 0) : A(1, 1), b = A(1, 0);
+  const double l10 = (std::fabs(a) > 0.0) ? b / a : b;
+  const double d0 = a, d1 = d - l10 * (d0 * l10);
+  Mat L(2, 2);
+  L(0, 0) = 1.0;
+  L(1, 0) = l10;
+  L(1, 1) = 1.0;
+  Mat R(2, 2);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) R(i, j) = L(swap ? 1 - i : i, j);
+  const double s0 = std::sqrt(d0), s1 = std::sqrt(d1);
+  for (int i = 0; i < 2; ++i) {
+    R(i, 0) *= s0;
+    R(i, 1) *= s1;
+  }
+  return R;
+}
+
 // ---- CVE/include/aslam/backend/implementation/ReprojectionError.hpp:27-75 over BE ErrorTermFs<2> -----
 struct ReprojectionError {
   double y[2];
   HomogeneousExpressionNodeMultiply point;
   CameraDesignVariable* camera;
   double error[2] = {0, 0};
+  double squaredError = 0.0;  // ErrorTerm::_squaredError: the raw e^T invR e of the last evaluateError()
   Mat sqrtInvR;  // computeMatrixSqrt(I) = I  (Schweizer-Messer/sm_eigen/include/sm/eigen/matrix_sqrt.hpp:21-40)
+  std::shared_ptr<MEstimator> mEstimatorPolicy;  // BE/src/ErrorTerm.cpp:8-12: NoMEstimator by default
   int rowBase = 0;
   ReprojectionError(const double y_[2], const HomogeneousExpressionNodeMultiply& pt, CameraDesignVariable* cam)
-      : point(pt), camera(cam), sqrtInvR(Mat::Identity(2)) {
+      : point(pt), camera(cam), sqrtInvR(Mat::Identity(2)), mEstimatorPolicy(std::make_shared<NoMEstimator>()) {
     y[0] = y_[0];
     y[1] = y_[1];
   }
+  // BE/include/aslam/backend/implementation/ErrorTerm.hpp:118-127
+  void setInvR(const Mat& invR) { sqrtInvR = computeMatrixSqrt2(invR); }
+  // BE/src/ErrorTerm.cpp:46-56
+  void setMEstimatorPolicy(const std::shared_ptr<MEstimator>& m) { mEstimatorPolicy = m; }
   // ReprojectionError.hpp:50-60 ; the projection's validity bool is ignored (Q6)
-  double evaluateError() {
+  double evaluateErrorImplementation() {
     double p[4];
     point.toHomogeneous(p);
     double hat_y[2] = {0.0, 0.0};  // the reference leaves this uninitialised when the projection bails out
@@ -350,6 +467,11 @@ struct ReprojectionError {
     // e^T invR e with invR = sqrtInvR sqrtInvR^T
     Mat invR = sqrtInvR * transpose(sqrtInvR);
     return error[0] * (invR(0, 0) * error[0] + invR(0, 1) * error[1]) + error[1] * (invR(1, 0) * error[0] + invR(1, 1) * error[1]);
+  }
+  // BE/src/ErrorTerm.cpp:19-24: the returned cost is ALWAYS weighted by the policy (useMEstimator only gates e and J)
+  double evaluateError() {
+    squaredError = evaluateErrorImplementation();
+    return mEstimatorPolicy->getWeight(squaredError) * squaredError;
   }
   // ReprojectionError.hpp:63-77
   void evaluateJacobians(JacobianContainer& out) const {
@@ -361,23 +483,26 @@ struct ReprojectionError {
     point.evaluateJacobians(out, -J);
     camera->evaluateJacobians(out, p);
   }
-  // BE/include/aslam/backend/implementation/ErrorTerm.hpp:97-109 (no M-estimator: weight 1)
-  void buildHessian(SparseBlockMatrix& H, std::vector<double>& rhs) {
+  double sqrtWeight(bool useMEstimator) const { return useMEstimator ? std::sqrt(mEstimatorPolicy->getWeight(squaredError)) : 1.0; }
+  // BE/include/aslam/backend/implementation/ErrorTerm.hpp:97-109
+  void buildHessian(SparseBlockMatrix& H, std::vector<double>& rhs, bool useMEstimator = true) {
     JacobianContainer J(2);
     evaluateJacobians(J);
-    evaluateHessian(J, error, sqrtInvR, H, rhs);
+    evaluateHessian(J, error, sqrtWeight(useMEstimator) * sqrtInvR, H, rhs);
   }
   // ErrorTerm.hpp:183-192
-  void getWeightedError(double e[2]) const {
+  void getWeightedError(double e[2], bool useMEstimator = true) const {
     Mat sT = transpose(sqrtInvR);
-    e[0] = sT(0, 0) * error[0] + sT(0, 1) * error[1];
-    e[1] = sT(1, 0) * error[0] + sT(1, 1) * error[1];
+    const double sw = sqrtWeight(useMEstimator);
+    e[0] = (sT(0, 0) * error[0] + sT(0, 1) * error[1]) * sw;
+    e[1] = (sT(1, 0) * error[0] + sT(1, 1) * error[1]) * sw;
   }
   // ErrorTerm.hpp:170-181
-  void getWeightedJacobians(JacobianContainer& out) const {
+  void getWeightedJacobians(JacobianContainer& out, bool useMEstimator = true) const {
     evaluateJacobians(out);
     Mat sT = transpose(sqrtInvR);
-    for (auto& kv : out.jacobianMap) kv.second = kv.first->scaling * (sT * kv.second);
+    const double sw = sqrtWeight(useMEstimator);
+    for (auto& kv : out.jacobianMap) kv.second = (sw * kv.first->scaling) * (sT * kv.second);
   }
 };
 

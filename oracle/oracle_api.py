@@ -73,6 +73,16 @@ def lib() -> C.CDLL:
         L.ko_inverse4.argtypes = [C.c_void_p, C.c_void_p]
         L.ko_analyze_marginal.restype = C.c_int32
         L.ko_analyze_marginal.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        L.ko_set_inv_r.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_set_m_estimator.restype = C.c_double
+        L.ko_set_m_estimator.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.ko_set_use_m_estimator.argtypes = [C.c_void_p, C.c_int]
+        L.ko_chi2_inv_cdf.restype = C.c_double
+        L.ko_chi2_inv_cdf.argtypes = [C.c_double, C.c_int]
+        L.ko_m_estimator_weight.restype = C.c_double
+        L.ko_m_estimator_weight.argtypes = [C.c_int] + [C.c_double] * 4
+        L.ko_matrix_sqrt2.argtypes = [C.c_void_p, C.c_void_p]
+        L.ko_reprojection_statistics.argtypes = [C.c_void_p, C.c_void_p]
         L.ko_time_iteration.restype = C.c_int32
         L.ko_time_iteration.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         _lib = L
@@ -206,6 +216,23 @@ class OracleProblem:
         lib().ko_get_set_poses(self._h, _p(out))
         return out
 
+    def set_inv_r(self, inv_r):
+        """ErrorTermFs<2>::setInvR on every term."""
+        a = np.ascontiguousarray(inv_r, np.float64).reshape(2, 2)
+        lib().ko_set_inv_r(self._h, _p(a))
+
+    def set_m_estimator(self, kind: int, p0: float = 0.0, p1: float = 0.999, p2: float = 0.1) -> float:
+        """ErrorTerm::setMEstimatorPolicy on every term; returns the policy's parameter (epsilon for Blake-Zisserman)."""
+        return lib().ko_set_m_estimator(self._h, kind, p0, p1, p2)
+
+    def set_use_m_estimator(self, on: bool):
+        lib().ko_set_use_m_estimator(self._h, 1 if on else 0)
+
+    def reprojection_statistics(self) -> np.ndarray:
+        out = np.zeros((self._problem.n_cams, 6))
+        lib().ko_reprojection_statistics(self._h, _p(out))
+        return out
+
     def time_iteration(self, lam: float = 10.0):
         t = np.zeros(3)
         ok = lib().ko_time_iteration(self._h, self.n_threads, lam, _p(t))
@@ -243,3 +270,18 @@ def inverse4(M):
     out = np.zeros((4, 4))
     lib().ko_inverse4(_p(M), _p(out))
     return out
+
+
+def chi2_inv_cdf(p: float, df: int) -> float:
+    return lib().ko_chi2_inv_cdf(p, df)
+
+
+def m_estimator_weight(kind: int, squared_error: float, p0: float = 0.0, p1: float = 0.999, p2: float = 0.1) -> float:
+    return lib().ko_m_estimator_weight(kind, p0, p1, p2, squared_error)
+
+
+def matrix_sqrt2(A):
+    A = np.ascontiguousarray(A, np.float64).reshape(2, 2)
+    S = np.zeros((2, 2))
+    lib().ko_matrix_sqrt2(_p(A), _p(S))
+    return S
