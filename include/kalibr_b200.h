@@ -212,6 +212,28 @@ KB_API double kb_m_estimator_parameter(const kb_handle* h); /* k, sigma^2 or the
 #define KB_REPROJ_STAT_STRIDE 6
 KB_API kb_status kb_reprojection_statistics(kb_handle* h, double* out /*[n_cams][KB_REPROJ_STAT_STRIDE]*/);
 
+/* ---- initial-guess stage (what the drivers run before Optimizer2) -----------------------
+ * ≙ CameraGeometry::estimateTransformation for EVERY local view with the handle's current intrinsics
+ *   (CAM/include/aslam/cameras/implementation/PinholeProjection.hpp:831-891, OmniProjection.hpp:882-955,
+ *    ExtendedUnifiedProjection.hpp:791-860, DoubleSphereProjection.hpp:842-910): corners through cv::Point2f / Point3f
+ *   (float), keypointToEuclidean, the 80 degree cone, then cv::solvePnP (planar target: homography start + Levenberg-
+ *   Marquardt on the reprojection error), one warp per view.  T_t_c: pose (q xyzw, t) of T_target_camera as
+ *   sm::kinematics::Transformation::set stores it; ok[w] = 0 ≙ estimateTransformation returning false (fewer than 4 usable
+ *   corners).  resolution: [n_cams][2] (ru, rv) for the pinhole models' isValid(keypoint) test, or NULL to skip it. */
+KB_API kb_status kb_estimate_transformations(kb_handle* h, const int32_t* resolution, double* T_t_c /*[n_views][KB_POSE_STRIDE]*/,
+                                             int32_t* ok /*[n_views]*/);
+/* ≙ getTargetPoseGuess for every synced set (K2/include/kalibr2/CalibrationTools.hpp:316-356): PnP in the camera that saw most
+ *   corners (first one on ties), chained through the handle's current baselines exactly as the reference's std::accumulate does
+ *   (((T_t_cN B_0) B_1) ... B_{N-1}).  The guesses replace the set-pose state and what kb_reset_state returns to.
+ *   n_failed (may be NULL): local sets whose PnP failed (they get the identity chained through the baselines, as the reference,
+ *   which ignores estimateTransformation's return value there) or that no camera saw (pose left as it was). */
+KB_API kb_status kb_initialize_set_poses(kb_handle* h, const int32_t* resolution, int32_t* n_failed);
+/* ≙ the baseline guess of CalibrateStereoPair (CalibrationTools.hpp:195-234): per-component upper median (K2/src/
+ *   BasicMathUtils.cpp:10-33) of the translation and the rotation vector (sm::kinematics::RotationVector) of T_H^-1 T_L over
+ *   the synced sets both cameras saw.  baseline: pose (q, t) of T_camH_camL; n_used (may be NULL): sets that contributed. */
+KB_API kb_status kb_estimate_stereo_baseline(kb_handle* h, const int32_t* resolution, int32_t cam_l, int32_t cam_h, double* baseline /*[7]*/,
+                                             int32_t* n_used);
+
 /* ---- marginal analysis of the calibration block --------------------------------
  * ≙ aslam::calibration::LinearSolver::analyzeMarginal (aslam_incremental_calibration/incremental_calibration/src/core/
  *   LinearSolver.cpp:466-528) — what IncrementalEstimator::addBatch asks of its solver after every re-optimisation

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
     "kb_set_inv_r", "kb_get_sqrt_inv_r", "kb_set_m_estimator", "kb_m_estimator_parameter", "kb_reprojection_statistics",
+    "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline",
 ]
 
 MEST_NONE, MEST_HUBER, MEST_CAUCHY, MEST_GEMAN_MCCLURE, MEST_BLAKE_ZISSERMAN = range(5)  # = kb_m_estimator
@@ -108,6 +109,9 @@ def load_library() -> C.CDLL:
     L.kb_m_estimator_parameter.argtypes = [vp]
     L.kb_m_estimator_parameter.restype = C.c_double
     L.kb_reprojection_statistics.argtypes = [vp, vp]
+    L.kb_estimate_transformations.argtypes = [vp, vp, vp, vp]
+    L.kb_initialize_set_poses.argtypes = [vp, vp, C.POINTER(C.c_int32)]
+    L.kb_estimate_stereo_baseline.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, C.POINTER(C.c_int32)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:  # default: status-returning entry points
@@ -227,6 +231,36 @@ class B200SchurLinearSystemSolver:
         out = np.zeros((self.problem.n_cams, REPROJ_STAT_STRIDE))
         self._check(self._L.kb_reprojection_statistics(self._h, _p(out)), "kb_reprojection_statistics")
         return out
+
+    # -- initial-guess stage (≙ CameraGeometry::estimateTransformation, getTargetPoseGuess, CalibrateStereoPair's baseline guess)
+    @staticmethod
+    def _res(resolution):
+        return None if resolution is None else np.ascontiguousarray(resolution, np.int32)
+
+    def estimate_transformations(self, resolution=None):
+        """PnP per local view: (T_target_camera poses [n_views, 7], ok [n_views])."""
+        nv = len(self.problem.view_set) if self.local_jrows == self.jrows else None
+        if nv is None:
+            raise KalibrB200Error("estimate_transformations: use one rank or a pre-sharded problem from Python")
+        T = np.zeros((nv, 7))
+        ok = np.zeros(nv, np.int32)
+        r = self._res(resolution)
+        self._check(self._L.kb_estimate_transformations(self._h, _p(r), _p(T), _p(ok)), "kb_estimate_transformations")
+        return T, ok.astype(bool)
+
+    def initialize_set_poses(self, resolution=None) -> int:
+        """getTargetPoseGuess for every set; returns the number of sets without a usable PnP."""
+        nf = C.c_int32()
+        r = self._res(resolution)
+        self._check(self._L.kb_initialize_set_poses(self._h, _p(r), C.byref(nf)), "kb_initialize_set_poses")
+        return int(nf.value)
+
+    def estimate_stereo_baseline(self, cam_l: int = 0, cam_h: int = 1, resolution=None):
+        out = np.zeros(7)
+        n = C.c_int32()
+        r = self._res(resolution)
+        self._check(self._L.kb_estimate_stereo_baseline(self._h, _p(r), cam_l, cam_h, _p(out), C.byref(n)), "kb_estimate_stereo_baseline")
+        return out, int(n.value)
 
     def set_solver_semantic(self, semantic: int):
         self._check(self._L.kb_set_solver_semantic(self._h, semantic), "kb_set_solver_semantic")

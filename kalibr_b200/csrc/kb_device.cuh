@@ -190,6 +190,12 @@ cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, doubl
 cudaError_t launch_px_reduce_system(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max /*[2]*/, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx& s);
+// initial-guess stage (kb_init.cu): PnP per view (view_mask: null = every view of the list), best view per set, target pose guesses
+cudaError_t launch_estimate_transformations(const DevProblem& p, const int* view_list, const int* model_begin, const unsigned char* view_mask,
+                                            const int* resolution /*[n_cams][2] device, or null*/, double* T_out /*[n_views][7]*/, int* ok_out /*[n_views]*/,
+                                            StreamCtx& s);
+cudaError_t launch_best_view_mask(const DevProblem& p, unsigned char* mask /*[n_views]*/, StreamCtx& s);
+cudaError_t launch_set_pose_guess(const DevProblem& p, const double* T_views, const int* ok_views, double* set_poses_out, int* set_ok, StreamCtx& s);
 int schur_num_partials(const DevProblem& p);
 size_t schur_partial_stride(const DevProblem& p);
 

@@ -154,6 +154,9 @@ struct kb_handle {
   int la_rows = 0;               // DevProblem::mest_rows they were computed with
   double inv_r[4] = {1.0, 0.0, 0.0, 1.0}, sqrt_inv_r[4] = {1.0, 0.0, 0.0, 1.0};  // row-major
   DevBuf<double> stats_e, stats_acc;  // reprojection statistics scratch
+  DevBuf<double> pnp_T;               // initial-guess stage: T_target_camera per view
+  DevBuf<int> pnp_ok, pnp_res, pnp_set_ok;
+  DevBuf<unsigned char> pnp_mask;
   std::vector<double> trace;
   // ---- multi-GPU ----
   NcclComm comm = nullptr;
@@ -994,6 +997,143 @@ kb_status kb_reprojection_statistics(kb_handle* h, double* out) {
     o[4] = n > 1 ? std::sqrt(a[5] / (n - 1.0)) : 0.0;
     o[5] = n > 0 ? std::sqrt(a[1] * a[1] + a[2] * a[2]) / std::sqrt(n) : 0.0;  // "RMSE" as printed: |sum of errors| / sqrt(n) (:404)
   }
+  return KB_OK;
+}
+
+// ---- initial-guess stage -----------------------------------------------------------------------------
+namespace {
+kb_status pnp_prepare(kb_handle* h, const int32_t* resolution, const int** res_dev) {
+  const size_t V = (size_t)std::max(h->d.n_views, 1);
+  if (h->pnp_T.n < V * POSE_STRIDE) KB_CUDA(h, h->pnp_T.alloc(V * POSE_STRIDE));
+  if (h->pnp_ok.n < V) KB_CUDA(h, h->pnp_ok.alloc(V));
+  *res_dev = nullptr;
+  if (resolution) {
+    std::vector<int> r(resolution, resolution + 2 * h->n_cams);
+    KB_CUDA(h, h->pnp_res.upload(r, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));  // r is a stack-lifetime staging buffer
+    *res_dev = h->pnp_res.p;
+  }
+  return KB_OK;
+}
+void host_quat2r(const double* q, double R[9]) {  // sm quat2r, row-major
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = x * x - y * y - z * z + w * w; R[1] = 2 * x * y + 2 * z * w; R[2] = 2 * x * z - 2 * y * w;
+  R[3] = 2 * x * y - 2 * z * w; R[4] = -x * x + y * y - z * z + w * w; R[5] = 2 * x * w + 2 * y * z;
+  R[6] = 2 * x * z + 2 * y * w; R[7] = -2 * x * w + 2 * y * z; R[8] = -x * x - y * y + z * z + w * w;
+}
+void host_r2quat(const double R[9], double q[4]) {  // sm r2quat (quaternion_algebra.cpp:16-75)
+  const double c1 = R[0], c2 = R[3], c3 = R[6], c4 = R[1], c5 = R[4], c6 = R[7], c7 = R[2], c8 = R[5], c9 = R[8];
+  const double dc[4] = {std::fabs(1.0 + c1 - c5 - c9), std::fabs(1.0 - c1 + c5 - c9), std::fabs(1.0 - c1 - c5 + c9), std::fabs(1.0 + c1 + c5 + c9)};
+  int m = 0;
+  for (int i = 1; i < 4; ++i) if (dc[i] > dc[m]) m = i;
+  double c;
+  if (m == 0) { q[0] = 0.5 * std::sqrt(dc[0]); c = 0.25 / q[0]; q[1] = c * (c4 + c2); q[2] = c * (c7 + c3); q[3] = c * (c8 - c6); }
+  else if (m == 1) { q[1] = 0.5 * std::sqrt(dc[1]); c = 0.25 / q[1]; q[0] = c * (c4 + c2); q[2] = c * (c6 + c8); q[3] = c * (c3 - c7); }
+  else if (m == 2) { q[2] = 0.5 * std::sqrt(dc[2]); c = 0.25 / q[2]; q[0] = c * (c3 + c7); q[1] = c * (c6 + c8); q[3] = c * (c4 - c2); }
+  else { q[3] = 0.5 * std::sqrt(dc[3]); c = 0.25 / q[3]; q[0] = c * (c8 - c6); q[1] = c * (c3 - c7); q[2] = c * (c4 - c2); }
+  if (q[3] < 0) for (int i = 0; i < 4; ++i) q[i] = -q[i];
+}
+double upper_median(std::vector<double> v) {  // kalibr2::math::median (K2/src/BasicMathUtils.cpp:10-17)
+  std::nth_element(v.begin(), v.begin() + v.size() / 2, v.end());
+  return v[v.size() / 2];
+}
+}  // namespace
+
+kb_status kb_estimate_transformations(kb_handle* h, const int32_t* resolution, double* T_t_c, int32_t* ok) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const int* res_dev = nullptr;
+  kb_status st = pnp_prepare(h, resolution, &res_dev);
+  if (st != KB_OK) return st;
+  StreamCtx c = ctx(h);
+  KB_CUDA(h, launch_estimate_transformations(h->d, h->view_list.p, h->model_begin, nullptr, res_dev, h->pnp_T.p, h->pnp_ok.p, c));
+  const size_t V = (size_t)h->d.n_views;
+  if (T_t_c && V) KB_CUDA(h, cudaMemcpyAsync(T_t_c, h->pnp_T.p, sizeof(double) * V * POSE_STRIDE, cudaMemcpyDeviceToHost, h->stream));
+  if (ok && V) KB_CUDA(h, cudaMemcpyAsync(ok, h->pnp_ok.p, sizeof(int32_t) * V, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+kb_status kb_initialize_set_poses(kb_handle* h, const int32_t* resolution, int32_t* n_failed) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const int* res_dev = nullptr;
+  kb_status st = pnp_prepare(h, resolution, &res_dev);
+  if (st != KB_OK) return st;
+  const size_t V = (size_t)std::max(h->d.n_views, 1), S = (size_t)std::max(h->d.n_sets, 1);
+  if (h->pnp_mask.n < V) KB_CUDA(h, h->pnp_mask.alloc(V));
+  if (h->pnp_set_ok.n < S) KB_CUDA(h, h->pnp_set_ok.alloc(S));
+  StreamCtx c = ctx(h);
+  KB_CUDA(h, cudaMemsetAsync(h->pnp_mask.p, 0, V, h->stream));
+  KB_CUDA(h, launch_best_view_mask(h->d, h->pnp_mask.p, c));
+  KB_CUDA(h, launch_estimate_transformations(h->d, h->view_list.p, h->model_begin, h->pnp_mask.p, res_dev, h->pnp_T.p, h->pnp_ok.p, c));
+  KB_CUDA(h, launch_set_pose_guess(h->d, h->pnp_T.p, h->pnp_ok.p, h->set_poses.p, h->pnp_set_ok.p, c));
+  // the guesses are the state AND what kb_reset_state returns to
+  if (h->set_poses.n) KB_CUDA(h, cudaMemcpyAsync(h->init_sets.p, h->set_poses.p, sizeof(double) * h->set_poses.n, cudaMemcpyDeviceToDevice, h->stream));
+  std::vector<int> sok((size_t)h->d.n_sets, 0);
+  if (!sok.empty()) KB_CUDA(h, cudaMemcpyAsync(sok.data(), h->pnp_set_ok.p, sizeof(int) * sok.size(), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int failed = 0;
+  for (int v : sok) failed += v ? 0 : 1;
+  if (n_failed) *n_failed = failed;
+  ++h->state_version;
+  h->built = h->solved = h->has_backup = false;
+  return KB_OK;
+}
+
+kb_status kb_estimate_stereo_baseline(kb_handle* h, const int32_t* resolution, int32_t cam_l, int32_t cam_h, double* baseline, int32_t* n_used) {
+  if (h->n_ranks != 1) return fail(h, KB_ERR_STATE, "kb_estimate_stereo_baseline needs a single rank (the median runs over all sets)");
+  if (cam_l < 0 || cam_h < 0 || cam_l >= h->n_cams || cam_h >= h->n_cams || cam_l == cam_h || !baseline)
+    return fail(h, KB_ERR_INVALID_ARGUMENT, "bad camera pair");
+  const size_t V = (size_t)h->d.n_views;
+  std::vector<double> T(V * POSE_STRIDE);
+  std::vector<int32_t> ok(V);
+  kb_status st = kb_estimate_transformations(h, resolution, T.data(), ok.data());
+  if (st != KB_OK) return st;
+  std::vector<int> vl((size_t)h->n_sets_global, -1), vh((size_t)h->n_sets_global, -1);
+  for (size_t w = 0; w < V; ++w) {
+    if (h->h_view_cam[w] == cam_l) vl[h->h_view_set[w]] = (int)w;
+    if (h->h_view_cam[w] == cam_h) vh[h->h_view_set[w]] = (int)w;
+  }
+  std::vector<double> tr[3], rv[3];
+  for (int s = 0; s < h->n_sets_global; ++s) {
+    if (vl[s] < 0 || vh[s] < 0 || !ok[vl[s]] || !ok[vh[s]]) continue;  // CalibrationTools.hpp:198-214
+    const double* L = &T[(size_t)vl[s] * POSE_STRIDE];
+    const double* H = &T[(size_t)vh[s] * POSE_STRIDE];
+    double Rl[9], Rh[9], C[9], t[3];
+    host_quat2r(L, Rl);
+    host_quat2r(H, Rh);
+    // T_H^-1 T_L: C = Rh^T Rl, t = Rh^T (t_L - t_H)
+    const double d[3] = {L[4] - H[4], L[5] - H[5], L[6] - H[6]};
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) C[i * 3 + j] = Rh[0 * 3 + i] * Rl[0 * 3 + j] + Rh[1 * 3 + i] * Rl[1 * 3 + j] + Rh[2 * 3 + i] * Rl[2 * 3 + j];
+      t[i] = Rh[0 * 3 + i] * d[0] + Rh[1 * 3 + i] * d[1] + Rh[2 * 3 + i] * d[2];
+    }
+    // RotationVector::rotationMatrixToParameters (Schweizer-Messer/sm_kinematics/src/RotationVector.cpp:58-80)
+    const double trc = std::max(-1.0, std::min((C[0] + C[4] + C[8] - 1.0) * 0.5, 1.0));
+    const double a = std::acos(trc);
+    double pr[3] = {0.0, 0.0, 0.0};
+    if (std::fabs(a) >= 1e-14) {
+      const double px = C[7] - C[5], py = C[2] - C[6], pz = C[3] - C[1];
+      const double n2 = std::sqrt(px * px + py * py + pz * pz);
+      if (std::fabs(n2) >= 1e-14) { const double sc = -a / n2; pr[0] = sc * px; pr[1] = sc * py; pr[2] = sc * pz; }
+    }
+    for (int i = 0; i < 3; ++i) { tr[i].push_back(t[i]); rv[i].push_back(pr[i]); }
+  }
+  if (n_used) *n_used = (int32_t)tr[0].size();
+  if (tr[0].empty()) return fail(h, KB_ERR_STATE, "no synced set was seen by both cameras");  // the reference's median throws
+  double mt[3], mr[3];
+  for (int i = 0; i < 3; ++i) { mt[i] = upper_median(tr[i]); mr[i] = upper_median(rv[i]); }
+  // RotationVector::parametersToRotationMatrix (RotationVector.cpp:10-55)
+  double C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const double angle = std::sqrt(mr[0] * mr[0] + mr[1] * mr[1] + mr[2] * mr[2]);
+  if (angle >= 1e-14) {
+    const double ax = mr[0] / angle, ay = mr[1] / angle, az = mr[2] / angle, sa = std::sin(angle), ca = std::cos(angle);
+    const double m[9] = {ax * ax + ca * (1 - ax * ax), ax * ay - ca * ax * ay + sa * az, ax * az - ca * ax * az - sa * ay,
+                         ax * ay - ca * ax * ay - sa * az, ay * ay + ca * (1 - ay * ay), ay * az - ca * ay * az + sa * ax,
+                         ax * az - ca * ax * az + sa * ay, ay * az - ca * ay * az - sa * ax, az * az + ca * (1 - az * az)};
+    for (int i = 0; i < 9; ++i) C[i] = m[i];
+  }
+  host_r2quat(C, baseline);
+  for (int i = 0; i < 3; ++i) baseline[4 + i] = mt[i];
   return KB_OK;
 }
 

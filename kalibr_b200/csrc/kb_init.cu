@@ -1,0 +1,622 @@
+// Initial-guess stage on the device: what Kalibr2's drivers run BEFORE the batch solve.
+//
+//   pnp_kernel<MODEL>      CameraGeometry::estimateTransformation for a batch of views, one warp per view:
+//                          corners rounded to float (cv::Point2f / Point3f) -> keypointToEuclidean -> 80 degree cone filter ->
+//                          normalised coordinates rounded to float -> planar PnP (cv::solvePnP, SOLVEPNP_ITERATIVE: homography
+//                          initialisation, then Levenberg-Marquardt on the reprojection error) -> T_target_camera
+//                            ≙ CAM/.../implementation/PinholeProjection.hpp:831-891, OmniProjection.hpp:882-955,
+//                              ExtendedUnifiedProjection.hpp:791-860, DoubleSphereProjection.hpp:842-910
+//   set_pose_guess_kernel  getTargetPoseGuess for every synced set: the view of the camera that saw most corners, chained through the
+//                          baseline guesses                           ≙ K2/include/kalibr2/CalibrationTools.hpp:316-356
+//
+// The PnP minimises the same cost as OpenCV from the same kind of start (plane-to-image homography), on the manifold
+// (R <- exp(d) R) instead of the Rodrigues vector; both end in the same minimum (tests pin it against cv2.solvePnP outputs).
+// Everything a warp needs lives in shared memory (6 doubles per corner) and registers; sums are warp butterflies in a fixed order.
+#include "kb_device.cuh"
+#include "kb_models.cuh"
+
+namespace kb {
+namespace {
+
+constexpr int PNP_WARPS = 4;
+constexpr double COS80 = 0.17364817766693041;       // std::cos(80.0 * M_PI / 180.0)
+constexpr double FOV_MAX_VALID_ANGLE = 1.5533430342749532;  // 89 degrees: CAM/include/aslam/cameras/FovDistortion.hpp:146
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- undistort: CAM/.../implementation/RadialTangentialDistortion.hpp:68-100, EquidistantDistortion.hpp:186-211, FovDistortion.hpp:89-116
+__device__ __forceinline__ void undistort_radtan(const double* __restrict__ k, double& x, double& y) {
+  double bx = x, by = y;
+  for (int i = 0; i < 5; ++i) {
+    double tx = bx, ty = by, F[2][2], Jk[2][4];
+    radtan<true>(k, tx, ty, F, Jk);
+    const double ex = x - tx, ey = y - ty;
+    // du = (F^T F)^-1 F^T e
+    const double a00 = F[0][0] * F[0][0] + F[1][0] * F[1][0], a01 = F[0][0] * F[0][1] + F[1][0] * F[1][1], a11 = F[0][1] * F[0][1] + F[1][1] * F[1][1];
+    const double g0 = F[0][0] * ex + F[1][0] * ey, g1 = F[0][1] * ex + F[1][1] * ey;
+    const double id = 1.0 / (a00 * a11 - a01 * a01);
+    bx += (a11 * g0 - a01 * g1) * id;
+    by += (a00 * g1 - a01 * g0) * id;
+    if (ex * ex + ey * ey < 1e-15) break;
+  }
+  x = bx;
+  y = by;
+}
+__device__ __forceinline__ void undistort_equi(const double* __restrict__ k, double& x, double& y) {
+  const double thetad = sqrt(x * x + y * y);
+  double theta = thetad;
+  for (int i = 0; i < 20; ++i) {
+    const double t2 = theta * theta, t4 = t2 * t2;
+    theta = thetad / (1.0 + k[0] * t2 + k[1] * t4 + k[2] * t4 * t2 + k[3] * t4 * t4);
+  }
+  const double scaling = tan(theta) / thetad;  // 0 / 0 at the image centre, as in the reference: the corner drops out below
+  x *= scaling;
+  y *= scaling;
+}
+__device__ __forceinline__ void undistort_fov(const double* __restrict__ k, double& x, double& y) {
+  const double w = k[0];
+  const double mul2tanwby2 = tan(w / 2.0) * 2.0;
+  const double r_d = sqrt(x * x + y * y);
+  if (mul2tanwby2 == 0.0 || r_d == 0.0) return;
+  if (fabs(r_d * w) <= FOV_MAX_VALID_ANGLE) {
+    const double r_u = tan(r_d * w) / (r_d * mul2tanwby2);
+    x *= r_u;
+    y *= r_u;
+  }
+}
+
+// keypointToEuclidean: PinholeProjection.hpp:200-229, OmniProjection.hpp:232-263, ExtendedUnifiedProjection.hpp:248-283,
+// DoubleSphereProjection.hpp:271-307.  res = (ru, rv) or null: the pinhole's isValid(keypoint) image-bounds test.
+template <int MODEL>
+__device__ __forceinline__ bool keypoint_to_euclidean(const double* __restrict__ prm, const int* __restrict__ res, double u, double v, double out[3]) {
+  constexpr int P = model_P(MODEL);
+  const double* k = prm + P;
+  if (MODEL == PINHOLE_RADTAN || MODEL == PINHOLE_EQUI || MODEL == PINHOLE_FOV) {
+    double x = (u - prm[2]) / prm[0], y = (v - prm[3]) / prm[1];
+    if (MODEL == PINHOLE_RADTAN) undistort_radtan(k, x, y);
+    else if (MODEL == PINHOLE_EQUI) undistort_equi(k, x, y);
+    else undistort_fov(k, x, y);
+    out[0] = x; out[1] = y; out[2] = 1.0;
+    return res == nullptr || (u >= 0.0 && u < (double)res[0] && v >= 0.0 && v < (double)res[1]);
+  } else if (MODEL == OMNI_RADTAN || MODEL == OMNI_NONE) {
+    const double xi = prm[0];
+    double x = (1.0 / prm[1]) * (u - prm[3]), y = (1.0 / prm[2]) * (v - prm[4]);
+    if (MODEL == OMNI_RADTAN) undistort_radtan(k, x, y);
+    const double rho2 = x * x + y * y;
+    if (!(xi <= 1.0 || rho2 <= 1.0 / (xi * xi - 1.0))) return false;
+    out[0] = x; out[1] = y;
+    out[2] = 1.0 - xi * (rho2 + 1.0) / (xi + sqrt(1.0 + (1.0 - xi * xi) * rho2));
+    return true;
+  } else if (MODEL == EUCM_NONE) {
+    const double alpha = prm[0], beta = prm[1];
+    const double mx = (1.0 / prm[2]) * (u - prm[4]), my = (1.0 / prm[3]) * (v - prm[5]);
+    const double r2 = mx * mx + my * my;
+    if (!(alpha <= 0.5 || r2 <= 1.0 / (beta * (2.0 * alpha - 1.0)))) return false;
+    const double gamma = 1.0 - alpha;
+    const double kk = (1.0 - alpha * alpha * beta * r2) / (alpha * sqrt(1.0 - (alpha - gamma) * beta * r2) + gamma);
+    const double ni = 1.0 / sqrt(r2 + kk * kk);
+    out[0] = mx * ni; out[1] = my * ni; out[2] = kk * ni;
+    return true;
+  } else {  // DS_NONE
+    const double xi = prm[0], alpha = prm[1];
+    const double mx = (1.0 / prm[2]) * (u - prm[4]), my = (1.0 / prm[3]) * (v - prm[5]);
+    const double r2 = mx * mx + my * my;
+    if (!(alpha <= 0.5 || r2 <= 1.0 / (2.0 * alpha - 1.0))) return false;
+    const double mz = (1.0 - alpha * alpha * r2) / (alpha * sqrt(1.0 - (2.0 * alpha - 1.0) * r2) + 1.0 - alpha);
+    const double mz2 = mz * mz;
+    const double kk = (mz * xi + sqrt(mz2 + (1.0 - xi * xi) * r2)) / (mz2 + r2);
+    out[0] = kk * mx; out[1] = kk * my; out[2] = kk * mz - xi;
+    return true;
+  }
+}
+
+// ---- small dense helpers (uniform across the warp: every lane computes the same values) ----------------------------------
+__device__ __forceinline__ void mat3_mul(const double A[9], const double B[9], double C[9]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+__device__ __forceinline__ void mat3_inv_t(const double A[9], double B[9]) {  // B = A^-T
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double id = 1.0 / (A[0] * c00 + A[1] * c01 + A[2] * c02);
+  B[0] = c00 * id; B[1] = c01 * id; B[2] = c02 * id;
+  B[3] = (A[2] * A[7] - A[1] * A[8]) * id; B[4] = (A[0] * A[8] - A[2] * A[6]) * id; B[5] = (A[1] * A[6] - A[0] * A[7]) * id;
+  B[6] = (A[1] * A[5] - A[2] * A[4]) * id; B[7] = (A[2] * A[3] - A[0] * A[5]) * id; B[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+// nearest rotation (polar factor = U V^T of the SVD, what cv::Rodrigues(matrix) projects onto): Newton iteration X <- (X + X^-T) / 2
+__device__ __forceinline__ void nearest_rotation(double R[9]) {
+  for (int it = 0; it < 12; ++it) {
+    double Y[9];
+    mat3_inv_t(R, Y);
+    double d = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double n = 0.5 * (R[i] + Y[i]);
+      d = fmax(d, fabs(n - R[i]));
+      R[i] = n;
+    }
+    if (d < 1e-15) break;
+  }
+}
+// R <- exp([w]x) R (Rodrigues formula)
+__device__ __forceinline__ void rotate_left(const double w[3], const double R[9], double out[9]) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th = sqrt(th2);
+  double a, b;  // exp = I + a K + b K^2
+  if (th < 1e-8) { a = 1.0 - th2 / 6.0; b = 0.5 - th2 / 24.0; }
+  else { a = sin(th) / th; b = (1.0 - cos(th)) / th2; }
+  const double K[9] = {0.0, -w[2], w[1], w[2], 0.0, -w[0], -w[1], w[0], 0.0};
+  double K2[9], E[9];
+  mat3_mul(K, K, K2);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) E[i] = a * K[i] + b * K2[i] + ((i % 4 == 0) ? 1.0 : 0.0);
+  mat3_mul(E, R, out);
+}
+// symmetric 3x3 eigen-decomposition by cyclic Jacobi; eigenvalues in w, eigenvectors in the columns of V
+__device__ __forceinline__ void eig3(double A[9], double w[3], double V[9]) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
+    if (off < 1e-300) break;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      const double apq = A[p * 3 + q];
+      if (fabs(apq) < 1e-300) continue;
+      const double theta = (A[q * 3 + q] - A[p * 3 + p]) / (2.0 * apq);
+      const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {  // A <- A J
+        const double akp = A[k * 3 + p], akq = A[k * 3 + q];
+        A[k * 3 + p] = c * akp - s * akq;
+        A[k * 3 + q] = s * akp + c * akq;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {  // A <- J^T A
+        const double apk = A[p * 3 + k], aqk = A[q * 3 + k];
+        A[p * 3 + k] = c * apk - s * aqk;
+        A[q * 3 + k] = s * apk + c * aqk;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
+        V[k * 3 + p] = c * vkp - s * vkq;
+        V[k * 3 + q] = s * vkp + c * vkq;
+      }
+    }
+  }
+  w[0] = A[0]; w[1] = A[4]; w[2] = A[8];
+}
+// Cholesky solve of an N x N SPD system held as a full row-major array (in place); returns false when not positive definite
+template <int N>
+__device__ __forceinline__ bool chol_solve(double A[N * N], double x[N]) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double d = A[j * N + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= A[j * N + k] * A[j * N + k];
+    if (!(d > 0.0)) ok = false;
+    d = sqrt(d);
+    A[j * N + j] = d;
+    const double id = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      double s = A[i * N + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= A[i * N + k] * A[j * N + k];
+      A[i * N + j] = s * id;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = x[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= A[i * N + k] * x[k];
+    x[i] = s / A[i * N + i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double s = x[i];
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) s -= A[k * N + i] * x[k];
+    x[i] = s / A[i * N + i];
+  }
+  return ok;
+}
+// sm::kinematics::r2quat (Schweizer-Messer/sm_kinematics/src/quaternion_algebra.cpp:16-75), R row-major
+__device__ __forceinline__ void r2quat(const double R[9], double q[4]) {
+  const double c1 = R[0], c2 = R[3], c3 = R[6], c4 = R[1], c5 = R[4], c6 = R[7], c7 = R[2], c8 = R[5], c9 = R[8];
+  const double dc[4] = {fabs(1.0 + c1 - c5 - c9), fabs(1.0 - c1 + c5 - c9), fabs(1.0 - c1 - c5 + c9), fabs(1.0 + c1 + c5 + c9)};
+  int m = 0;
+  double mv = dc[0];
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (dc[i] > mv) { m = i; mv = dc[i]; }
+  double c;
+  if (m == 0) { q[0] = 0.5 * sqrt(dc[0]); c = 0.25 / q[0]; q[1] = c * (c4 + c2); q[2] = c * (c7 + c3); q[3] = c * (c8 - c6); }
+  else if (m == 1) { q[1] = 0.5 * sqrt(dc[1]); c = 0.25 / q[1]; q[0] = c * (c4 + c2); q[2] = c * (c6 + c8); q[3] = c * (c3 - c7); }
+  else if (m == 2) { q[2] = 0.5 * sqrt(dc[2]); c = 0.25 / q[2]; q[0] = c * (c3 + c7); q[1] = c * (c6 + c8); q[3] = c * (c4 - c2); }
+  else { q[3] = 0.5 * sqrt(dc[3]); c = 0.25 / q[3]; q[0] = c * (c8 - c6); q[1] = c * (c3 - c7); q[2] = c * (c4 - c2); }
+  if (q[3] < 0.0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+}
+// sm quat2r (quaternion_algebra.cpp:77-101), row-major
+__device__ __forceinline__ void quat2r_rm(const double* __restrict__ q, double R[9]) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = x * x - y * y - z * z + w * w; R[1] = 2.0 * x * y + 2.0 * z * w;        R[2] = 2.0 * x * z - 2.0 * y * w;
+  R[3] = 2.0 * x * y - 2.0 * z * w;     R[4] = -x * x + y * y - z * z + w * w;   R[5] = 2.0 * x * w + 2.0 * y * z;
+  R[6] = 2.0 * x * z + 2.0 * y * w;     R[7] = -2.0 * x * w + 2.0 * y * z;       R[8] = -x * x - y * y + z * z + w * w;
+}
+
+// reprojection cost of the pose (R, t) over the warp's points (weights 0 / 1), summed over the warp
+__device__ __forceinline__ double pnp_cost(const double R[9], const double t[3], const double* sX, const double* sY, const double* sZ,
+                                           const double* sx, const double* sy, const double* sw, int n, int lane) {
+  double c = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const double X = sX[i], Y = sY[i], Z = sZ[i];
+    const double px = R[0] * X + R[1] * Y + R[2] * Z + t[0], py = R[3] * X + R[4] * Y + R[5] * Z + t[1], pz = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+    const double iz = 1.0 / pz;
+    const double ru = px * iz - sx[i], rv = py * iz - sy[i];
+    c += sw[i] * (ru * ru + rv * rv);
+  }
+  return wsum(c);
+}
+
+// ---- estimateTransformation, one warp per view ---------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const int* __restrict__ view_list, int n_list,
+                                                              const unsigned char* __restrict__ view_mask, const int* __restrict__ resolution,
+                                                              int n_max, double* __restrict__ T_out, int* __restrict__ ok_out) {
+  extern __shared__ double smem_pnp[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* sX = smem_pnp + (size_t)wib * 6 * n_max;
+  double* sY = sX + n_max;
+  double* sZ = sY + n_max;
+  double* sx = sZ + n_max;
+  double* sy = sx + n_max;
+  double* sw = sy + n_max;
+  const int warp = blockIdx.x * PNP_WARPS + wib, n_warps = gridDim.x * PNP_WARPS;
+  for (int vi = warp; vi < n_list; vi += n_warps) {
+    const int view = view_list[vi];
+    if (view_mask && !view_mask[view]) continue;
+    const int cam = p.view_cam[view];
+    const int b = p.view_begin[view];
+    const int n = min(p.view_begin[view + 1] - b, n_max);
+    double prm[CAM_PARAM_STRIDE];
+#pragma unroll
+    for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
+    const int* res = resolution ? resolution + 2 * cam : nullptr;
+    __syncwarp();
+    // -- back-projection and the 80 degree cone; everything passes through float as cv::Point2f / cv::Point3f do
+    double cnt = 0.0, cX = 0.0, cY = 0.0, cZ = 0.0, cx = 0.0, cy = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const double u = (double)(float)p.y_u[b + i], v = (double)(float)p.y_v[b + i];
+      const double* tp = p.target + 3 * p.corner[b + i];
+      double bp[3] = {0.0, 0.0, 0.0};
+      bool ok = keypoint_to_euclidean<MODEL>(prm, res, u, v, bp);
+      ok = ok && (bp[2] / sqrt(bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]) > COS80);  // false for NaN as well
+      const double X = (double)(float)tp[0], Y = (double)(float)tp[1], Z = (double)(float)tp[2];
+      const double mx = ok ? (double)(float)(bp[0] / bp[2]) : 0.0, my = ok ? (double)(float)(bp[1] / bp[2]) : 0.0;
+      const double w = ok ? 1.0 : 0.0;
+      sX[i] = X; sY[i] = Y; sZ[i] = Z; sx[i] = mx; sy[i] = my; sw[i] = w;
+      cnt += w; cX += w * X; cY += w * Y; cZ += w * Z; cx += w * mx; cy += w * my;
+    }
+    __syncwarp();
+    cnt = wsum(cnt);
+    double* To = T_out + (size_t)view * POSE_STRIDE;
+    if (cnt < 4.0) {  // "if (Ps.size() < 4) return false"
+      if (lane == 0) { To[0] = To[1] = To[2] = 0.0; To[3] = 1.0; To[4] = To[5] = To[6] = 0.0; ok_out[view] = 0; }
+      continue;
+    }
+    const double icnt = 1.0 / cnt;
+    cX = wsum(cX) * icnt; cY = wsum(cY) * icnt; cZ = wsum(cZ) * icnt; cx = wsum(cx) * icnt; cy = wsum(cy) * icnt;
+    // -- the object plane: principal axes of the corners (cvFindExtrinsicCameraParams2's planar branch)
+    double Rt[9], Tt[3];
+    {
+      double m[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = lane; i < n; i += 32) {
+        const double w = sw[i], dx = sX[i] - cX, dy = sY[i] - cY, dz = sZ[i] - cZ;
+        m[0] += w * dx * dx; m[1] += w * dx * dy; m[2] += w * dx * dz; m[3] += w * dy * dy; m[4] += w * dy * dz; m[5] += w * dz * dz;
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) m[i] = wsum(m[i]);
+      double A[9] = {m[0], m[1], m[2], m[1], m[3], m[4], m[2], m[4], m[5]}, ev[3], V[9];
+      eig3(A, ev, V);
+      // sort descending: the plane normal is the eigenvector of the smallest eigenvalue
+      int i0 = 0, i2 = 0;
+#pragma unroll
+      for (int i = 1; i < 3; ++i) { if (ev[i] > ev[i0]) i0 = i; if (ev[i] < ev[i2]) i2 = i; }
+      if (i0 == i2) { i0 = 0; i2 = 2; }
+      const int i1 = 3 - i0 - i2;
+      const bool planar = ev[i2] < 1e-3 * ev[i1];
+      if (!planar) {  // kalibr's grid targets are planar; a general 3-D object would need the 12-parameter DLT start
+        if (lane == 0) { To[0] = To[1] = To[2] = 0.0; To[3] = 1.0; To[4] = To[5] = To[6] = 0.0; ok_out[view] = 0; }
+        continue;
+      }
+      if (V[0 * 3 + i2] * V[0 * 3 + i2] + V[1 * 3 + i2] * V[1 * 3 + i2] < 1e-10) {  // normal along z already
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rt[i] = (i % 4 == 0) ? 1.0 : 0.0;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { Rt[0 * 3 + c] = V[c * 3 + i0]; Rt[1 * 3 + c] = V[c * 3 + i1]; Rt[2 * 3 + c] = V[c * 3 + i2]; }
+        const double det = Rt[0] * (Rt[4] * Rt[8] - Rt[5] * Rt[7]) - Rt[1] * (Rt[3] * Rt[8] - Rt[5] * Rt[6]) + Rt[2] * (Rt[3] * Rt[7] - Rt[4] * Rt[6]);
+        if (det < 0.0)
+#pragma unroll
+          for (int i = 0; i < 9; ++i) Rt[i] = -Rt[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Tt[i] = -(Rt[i * 3] * cX + Rt[i * 3 + 1] * cY + Rt[i * 3 + 2] * cZ);
+    }
+    // -- plane-to-image homography: normalised DLT with h33 = 1 (8 x 8 normal equations)
+    double R[9], t[3];
+    {
+      // per-axis scales: count / sum |deviation| (the normalisation of OpenCV's homography kernel)
+      double aX = 0.0, aY = 0.0, ax = 0.0, ay = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        const double w = sw[i];
+        const double X = Rt[0] * sX[i] + Rt[1] * sY[i] + Rt[2] * sZ[i] + Tt[0], Y = Rt[3] * sX[i] + Rt[4] * sY[i] + Rt[5] * sZ[i] + Tt[1];
+        aX += w * fabs(X); aY += w * fabs(Y); ax += w * fabs(sx[i] - cx); ay += w * fabs(sy[i] - cy);
+      }
+      const double sMx = cnt / wsum(aX), sMy = cnt / wsum(aY), smx = cnt / wsum(ax), smy = cnt / wsum(ay);
+      // L^T L of the rows [X Y 1 0 0 0 -xX -xY -x], [0 0 0 X Y 1 -yX -yY -y] in blocks: A = sum q q^T, B = sum x q q^T,
+      // C = sum y q q^T, D = sum (x^2 + y^2) q q^T with q = (X, Y, 1)
+      double Aq[6] = {0, 0, 0, 0, 0, 0}, Bq[6] = {0, 0, 0, 0, 0, 0}, Cq[6] = {0, 0, 0, 0, 0, 0}, Dq[6] = {0, 0, 0, 0, 0, 0};
+      for (int i = lane; i < n; i += 32) {
+        const double w = sw[i];
+        const double X = (Rt[0] * sX[i] + Rt[1] * sY[i] + Rt[2] * sZ[i] + Tt[0]) * sMx, Y = (Rt[3] * sX[i] + Rt[4] * sY[i] + Rt[5] * sZ[i] + Tt[1]) * sMy;
+        const double x = (sx[i] - cx) * smx, y = (sy[i] - cy) * smy;
+        const double qq[6] = {w * X * X, w * X * Y, w * X, w * Y * Y, w * Y, w};
+        const double r2 = x * x + y * y;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { Aq[k] += qq[k]; Bq[k] += x * qq[k]; Cq[k] += y * qq[k]; Dq[k] += r2 * qq[k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { Aq[k] = wsum(Aq[k]); Bq[k] = wsum(Bq[k]); Cq[k] = wsum(Cq[k]); Dq[k] = wsum(Dq[k]); }
+      // symmetric 3x3 blocks from the 6 unique sums: index (r, c) -> {0: XX, 1: XY, 2: X, 3: YY, 4: Y, 5: 1}
+      const int sidx[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+      double N[64], rhs[8];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) N[i] = 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int s = sidx[r * 3 + c];
+          N[r * 8 + c] = Aq[s];
+          N[(3 + r) * 8 + 3 + c] = Aq[s];
+          if (c < 2) {
+            N[r * 8 + 6 + c] = -Bq[s];
+            N[(6 + c) * 8 + r] = -Bq[s];
+            N[(3 + r) * 8 + 6 + c] = -Cq[s];
+            N[(6 + c) * 8 + 3 + r] = -Cq[s];
+          }
+          if (r < 2 && c < 2) N[(6 + r) * 8 + 6 + c] = Dq[s];
+        }
+      // right-hand side: -L^T L[0:8][8] = -(column of -x q, -y q, (x^2+y^2) q) at q-index 2 (the "1" entry)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { rhs[r] = Bq[sidx[r * 3 + 2]]; rhs[3 + r] = Cq[sidx[r * 3 + 2]]; }
+      rhs[6] = -Dq[sidx[0 * 3 + 2]];
+      rhs[7] = -Dq[sidx[1 * 3 + 2]];
+      const bool spd = chol_solve<8>(N, rhs);
+      if (!spd) {
+        if (lane == 0) { To[0] = To[1] = To[2] = 0.0; To[3] = 1.0; To[4] = To[5] = To[6] = 0.0; ok_out[view] = 0; }
+        continue;
+      }
+      // de-normalise: H = Tm^-1 Hn TM, Tm^-1 = [1/smx 0 cx; 0 1/smy cy; 0 0 1], TM = diag(sMx, sMy, 1) (the plane points are centred)
+      const double Hn[9] = {rhs[0], rhs[1], rhs[2], rhs[3], rhs[4], rhs[5], rhs[6], rhs[7], 1.0};
+      double H[9];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double sc = c == 0 ? sMx : c == 1 ? sMy : 1.0;
+        H[0 * 3 + c] = (Hn[0 * 3 + c] / smx + cx * Hn[2 * 3 + c]) * sc;
+        H[1 * 3 + c] = (Hn[1 * 3 + c] / smy + cy * Hn[2 * 3 + c]) * sc;
+        H[2 * 3 + c] = Hn[2 * 3 + c] * sc;
+      }
+      if (H[8] < 0.0)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] = -H[i];
+      const double n1 = sqrt(H[0] * H[0] + H[3] * H[3] + H[6] * H[6]), n2 = sqrt(H[1] * H[1] + H[4] * H[4] + H[7] * H[7]);
+      const double i1 = 1.0 / fmax(n1, 2.220446049250313e-16), i2 = 1.0 / fmax(n2, 2.220446049250313e-16), i3 = 2.0 / fmax(n1 + n2, 2.220446049250313e-16);
+      const double r1[3] = {H[0] * i1, H[3] * i1, H[6] * i1}, r2[3] = {H[1] * i2, H[4] * i2, H[7] * i2};
+      double R0[9] = {r1[0], r2[0], r1[1] * r2[2] - r1[2] * r2[1], r1[1], r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[2], r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+      nearest_rotation(R0);
+      mat3_mul(R0, Rt, R);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) t[i] = R0[i * 3] * Tt[0] + R0[i * 3 + 1] * Tt[1] + R0[i * 3 + 2] * Tt[2] + H[i * 3 + 2] * i3;
+    }
+    // -- Levenberg-Marquardt on the reprojection error in normalised coordinates, update R <- exp(d_theta) R, t <- t + d_t
+    double cost = pnp_cost(R, t, sX, sY, sZ, sx, sy, sw, n, lane);
+    double lambda = 1e-3;
+    bool good = isfinite(cost);
+    for (int it = 0; it < 60 && good; ++it) {
+      double Hs[21], g[6];
+#pragma unroll
+      for (int i = 0; i < 21; ++i) Hs[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) g[i] = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        const double w = sw[i], X = sX[i], Y = sY[i], Z = sZ[i];
+        const double qx = R[0] * X + R[1] * Y + R[2] * Z, qy = R[3] * X + R[4] * Y + R[5] * Z, qz = R[6] * X + R[7] * Y + R[8] * Z;
+        const double px = qx + t[0], py = qy + t[1], pz = qz + t[2];
+        const double iz = 1.0 / pz, u = px * iz, v = py * iz;
+        const double ru = u - sx[i], rv = v - sy[i];
+        // d(u, v)/dp = [iz 0 -u iz; 0 iz -v iz];  dp/d(theta) = -[q]x, dp/dt = I
+        const double a = iz, bu = -u * iz, bv = -v * iz;
+        const double Ju[6] = {bu * qy, a * qz - bu * qx, -a * qy, a, 0.0, bu};
+        const double Jv[6] = {-a * qz + bv * qy, -bv * qx, a * qx, 0.0, a, bv};
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int c = r; c < 6; ++c) Hs[k++] += w * (Ju[r] * Ju[c] + Jv[r] * Jv[c]);
+          g[r] += w * (Ju[r] * ru + Jv[r] * rv);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 21; ++i) Hs[i] = wsum(Hs[i]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) g[i] = wsum(g[i]);
+      bool accepted = false;
+      double step_max = 0.0;
+      for (int tries = 0; tries < 12 && !accepted; ++tries) {
+        double A[36], d[6];
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = r; c < 6; ++c) {
+            const double v = Hs[k++];
+            A[r * 6 + c] = v;
+            A[c * 6 + r] = v;
+          }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { A[r * 6 + r] *= 1.0 + lambda; d[r] = -g[r]; }
+        if (!chol_solve<6>(A, d)) { lambda *= 10.0; continue; }
+        double Rn[9];
+        rotate_left(d, R, Rn);
+        const double tn[3] = {t[0] + d[3], t[1] + d[4], t[2] + d[5]};
+        const double cn = pnp_cost(Rn, tn, sX, sY, sZ, sx, sy, sw, n, lane);
+        if (cn <= cost) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+          t[0] = tn[0]; t[1] = tn[1]; t[2] = tn[2];
+          cost = cn;
+          lambda = fmax(lambda * 0.1, 1e-15);
+          accepted = true;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) step_max = fmax(step_max, fabs(d[i]));
+        } else {
+          lambda *= 10.0;
+        }
+      }
+      if (!accepted) break;  // no descent direction left at this precision: converged
+      if (step_max < 1e-13 * fmax(1.0, fmax(fabs(t[0]), fmax(fabs(t[1]), fabs(t[2]))))) break;
+    }
+    // -- T_target_camera = inverse([R t]) -> (q, t) as sm::kinematics::Transformation::set stores it
+    if (lane == 0) {
+      nearest_rotation(R);  // rounding drift of the multiplicative updates
+      const double Ri[9] = {R[0], R[3], R[6], R[1], R[4], R[7], R[2], R[5], R[8]};
+      double q[4];
+      r2quat(Ri, q);
+      To[0] = q[0]; To[1] = q[1]; To[2] = q[2]; To[3] = q[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) To[4 + i] = -(Ri[i * 3] * t[0] + Ri[i * 3 + 1] * t[1] + Ri[i * 3 + 2] * t[2]);
+      ok_out[view] = (good && isfinite(cost)) ? 1 : 0;
+    }
+  }
+}
+
+// ---- getTargetPoseGuess: one thread per synced set -------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) set_pose_guess_kernel(DevProblem p, const double* __restrict__ T_views, const int* __restrict__ ok_views,
+                                                             double* __restrict__ set_poses_out, int* __restrict__ set_ok) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.n_sets) return;
+  // camera with most corners, the first one on ties (std::max_element)
+  int best = -1, best_n = 0, best_view = -1;
+  for (int k = 0; k < p.n_cams; ++k) {
+    const int w = p.set_view[(size_t)s * p.n_cams + k];
+    const int n = w >= 0 ? p.view_begin[w + 1] - p.view_begin[w] : 0;
+    if (best < 0 || n > best_n) { best = k; best_n = n; best_view = w; }
+  }
+  double* o = set_poses_out + (size_t)s * POSE_STRIDE;
+  if (best_view < 0) {  // nobody saw this set: keep the pose that is there
+    set_ok[s] = 0;
+    return;
+  }
+  const double* Tv = T_views + (size_t)best_view * POSE_STRIDE;
+  double R[9], t[3] = {Tv[4], Tv[5], Tv[6]};
+  quat2r_rm(Tv, R);
+  // T_t_c0 = ((T_t_cN B_0) B_1) ... B_{N-1}: std::accumulate over baseline_guesses[0 .. N) in that order (CalibrationTools.hpp:352-353)
+  for (int j = 0; j < best; ++j) {
+    const double* b = p.baselines + (size_t)j * POSE_STRIDE;
+    double Rb[9], Rn[9];
+    quat2r_rm(b, Rb);
+    mat3_mul(R, Rb, Rn);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] += R[i * 3] * b[4] + R[i * 3 + 1] * b[5] + R[i * 3 + 2] * b[6];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  }
+  double q[4];
+  r2quat(R, q);
+  o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3]; o[4] = t[0]; o[5] = t[1]; o[6] = t[2];
+  set_ok[s] = ok_views[best_view];
+}
+
+// per view: 1 when the view is the one getTargetPoseGuess picks for its set
+__global__ void __launch_bounds__(128) best_view_mask_kernel(DevProblem p, unsigned char* __restrict__ mask) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.n_sets) return;
+  int best_n = 0, best_view = -1;
+  bool first = true;
+  for (int k = 0; k < p.n_cams; ++k) {
+    const int w = p.set_view[(size_t)s * p.n_cams + k];
+    const int n = w >= 0 ? p.view_begin[w + 1] - p.view_begin[w] : 0;
+    if (w >= 0) mask[w] = 0;
+    if (first || n > best_n) { best_n = n; best_view = w; first = false; }
+  }
+  if (best_view >= 0) mask[best_view] = 1;
+}
+
+template <int MODEL>
+cudaError_t launch_pnp_model(const DevProblem& p, const int* list, int n, const unsigned char* mask, const int* resolution, int n_max, double* T_out,
+                             int* ok_out, StreamCtx& s) {
+  if (n <= 0) return cudaSuccess;
+  const size_t smem = sizeof(double) * 6 * (size_t)n_max * PNP_WARPS;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(pnp_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = min((n + PNP_WARPS - 1) / PNP_WARPS, sms * 8);
+  pnp_kernel<MODEL><<<grid, PNP_WARPS * 32, smem, s.stream>>>(p, list, n, mask, resolution, n_max, T_out, ok_out);
+  ++*s.launches;
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_estimate_transformations(const DevProblem& p, const int* view_list, const int* mb, const unsigned char* view_mask,
+                                            const int* resolution, double* T_out, int* ok_out, StreamCtx& s) {
+  const int n_max = p.n_target;
+  for (int m = 0; m < NUM_MODELS; ++m) {
+    cudaError_t e = cudaSuccess;
+    const int n = mb[m + 1] - mb[m];
+    switch (m) {
+      case 0: e = launch_pnp_model<0>(p, view_list + mb[0], n, view_mask, resolution, n_max, T_out, ok_out, s); break;
+      case 1: e = launch_pnp_model<1>(p, view_list + mb[1], n, view_mask, resolution, n_max, T_out, ok_out, s); break;
+      case 2: e = launch_pnp_model<2>(p, view_list + mb[2], n, view_mask, resolution, n_max, T_out, ok_out, s); break;
+      case 3: e = launch_pnp_model<3>(p, view_list + mb[3], n, view_mask, resolution, n_max, T_out, ok_out, s); break;
+      case 4: e = launch_pnp_model<4>(p, view_list + mb[4], n, view_mask, resolution, n_max, T_out, ok_out, s); break;
+      case 5: e = launch_pnp_model<5>(p, view_list + mb[5], n, view_mask, resolution, n_max, T_out, ok_out, s); break;
+      case 6: e = launch_pnp_model<6>(p, view_list + mb[6], n, view_mask, resolution, n_max, T_out, ok_out, s); break;
+    }
+    if (e != cudaSuccess) return e;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_best_view_mask(const DevProblem& p, unsigned char* mask, StreamCtx& s) {
+  if (p.n_sets <= 0) return cudaSuccess;
+  best_view_mask_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p, mask);
+  ++*s.launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_pose_guess(const DevProblem& p, const double* T_views, const int* ok_views, double* set_poses_out, int* set_ok, StreamCtx& s) {
+  if (p.n_sets <= 0) return cudaSuccess;
+  set_pose_guess_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p, T_views, ok_views, set_poses_out, set_ok);
+  ++*s.launches;
+  return cudaGetLastError();
+}
+
+}  // namespace kb
