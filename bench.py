@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--cpu-regime", default="block", choices=["block", "sparse"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-init-stage", action="store_true")
     ap.add_argument("--no-peer-exchange", action="store_true", help="N > 1: keep the exchange steps on NCCL instead of NVLink peer stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -357,6 +358,49 @@ def main():
         except Exception as ex:  # e.g. out of memory for the J buffer on huge problems
             lin = {"error": str(ex)}
 
+    # ---- initial-guess stage (the step before the path): PnP for every view, timed alone ----
+    init = None
+    if rank == 0 and not args.no_init_stage:
+        try:
+            g.estimate_transformations()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            e0.record(stream)
+            for _ in range(reps):
+                T_views, ok_views = g.estimate_transformations()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            pnp_ms = e0.elapsed_time(e1) / reps
+            init = {"kernel": "pnp_kernel (estimateTransformation, one warp per view)", "views": int(p.n_views), "ms": pnp_ms,
+                    "views_per_s": p.n_views / (pnp_ms * 1e-3), "ok_fraction": float(ok_views.mean()),
+                    "note": "kb_estimate_transformations through the C ABI incl. the device-to-host copy of the poses"}
+            try:
+                import cv2
+                from oracle import ko_init as ki
+
+                n_s = min(p.n_views, 400)
+                inputs = []
+                for w in range(n_s):
+                    b, e = p.view_begin[w], p.view_begin[w + 1]
+                    k = p.view_cam[w]
+                    Ps, Ms = ki.pnp_inputs(p.cam_model[k], p.cam_params[k], p.y_u[b:e], p.y_v[b:e], p.target_points[p.corner_id[b:e]])
+                    inputs.append((np.float32(Ps), np.float32(Ms)))
+                K, dz = np.eye(3), np.zeros(4)
+                t0 = time.time()
+                n_done = 0
+                while time.time() - t0 < 3.0:
+                    for Ps, Ms in inputs:
+                        cv2.solvePnP(Ps, Ms, K, dz)
+                    n_done += len(inputs)
+                el = time.time() - t0
+                init["cpu_baseline"] = {"value": n_done / el, "unit": "views/s", "cores": 1, "kind": "reference",
+                                        "sample": f"cv2.solvePnP {cv2.__version__} (the library call inside estimateTransformation) on the "
+                                                  f"prepared corners of {n_s} views, repeated for 3 s, one thread as in the reference's drivers"}
+            except Exception as ex:
+                init["cpu_baseline"] = {"error": str(ex)}
+        except Exception as ex:
+            init = {"error": str(ex)}
+
     if rank == 0:
         hbm_peak, hbm_src, fp64_peak, fp64_src = peaks()
         la_ms, la_calls = totals["linearise_assemble"]
@@ -398,7 +442,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, S_rank, terms_rank, world),
             "per_gpu_value": value / world, "lm_iteration_ms": ms_total / args.steps, "terms_total": terms_total,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "linearise_materialised": lin, "stage_ms": stages, "cpu_baseline": cpu,
+            "linearise_materialised": lin, "initial_guess": init, "stage_ms": stages, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
