@@ -22,9 +22,17 @@ constexpr int PNP_WARPS = 4;
 constexpr double COS80 = 0.17364817766693041;       // std::cos(80.0 * M_PI / 180.0)
 constexpr double FOV_MAX_VALID_ANGLE = 1.5533430342749532;  // 89 degrees: CAM/include/aslam/cameras/FovDistortion.hpp:146
 
-__device__ __forceinline__ double wsum(double v) {
+// A view is worked on by a group of PNP_G adjacent lanes (4 views per warp): the serial parts of the algorithm (small
+// factorisations, the LM control flow) are latency-bound and identical in every lane of a group, so narrower groups keep more
+// views in flight per warp.  Sums are butterflies inside the group, in a fixed order.
+#ifndef KB_PNP_G
+#define KB_PNP_G 8
+#endif
+constexpr int PNP_G = KB_PNP_G;
+constexpr int PNP_GROUPS = PNP_WARPS * 32 / PNP_G;  // views in flight per CTA
+__device__ __forceinline__ double wsum(double v, unsigned mask) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = PNP_G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
 
@@ -49,9 +57,11 @@ __device__ __forceinline__ void undistort_radtan(const double* __restrict__ k, d
 __device__ __forceinline__ void undistort_equi(const double* __restrict__ k, double& x, double& y) {
   const double thetad = sqrt(x * x + y * y);
   double theta = thetad;
-  for (int i = 0; i < 20; ++i) {
+  for (int i = 0; i < 20; ++i) {  // the reference always runs 20 rounds; once the value repeats, the remaining ones reproduce it
     const double t2 = theta * theta, t4 = t2 * t2;
-    theta = thetad / (1.0 + k[0] * t2 + k[1] * t4 + k[2] * t4 * t2 + k[3] * t4 * t4);
+    const double tn = thetad / (1.0 + k[0] * t2 + k[1] * t4 + k[2] * t4 * t2 + k[3] * t4 * t4);
+    if (tn == theta) break;
+    theta = tn;
   }
   const double scaling = tan(theta) / thetad;  // 0 / 0 at the image centre, as in the reference: the corner drops out below
   x *= scaling;
@@ -256,33 +266,35 @@ __device__ __forceinline__ void quat2r_rm(const double* __restrict__ q, double R
 }
 
 // reprojection cost of the pose (R, t) over the warp's points (weights 0 / 1), summed over the warp
-__device__ __forceinline__ double pnp_cost(const double R[9], const double t[3], const double* sX, const double* sY, const double* sZ,
-                                           const double* sx, const double* sy, const double* sw, int n, int lane) {
+__device__ __forceinline__ double pnp_cost(const double R[9], const double t[3], const float* sX, const float* sY, const float* sZ,
+                                           const float* sx, const float* sy, const float* sw, int n, int lane, unsigned mask) {
   double c = 0.0;
-  for (int i = lane; i < n; i += 32) {
+  for (int i = lane; i < n; i += PNP_G) {
     const double X = sX[i], Y = sY[i], Z = sZ[i];
     const double px = R[0] * X + R[1] * Y + R[2] * Z + t[0], py = R[3] * X + R[4] * Y + R[5] * Z + t[1], pz = R[6] * X + R[7] * Y + R[8] * Z + t[2];
     const double iz = 1.0 / pz;
     const double ru = px * iz - sx[i], rv = py * iz - sy[i];
     c += sw[i] * (ru * ru + rv * rv);
   }
-  return wsum(c);
+  return wsum(c, mask);
 }
 
 // ---- estimateTransformation, one warp per view ---------------------------------------------------------------------------
 template <int MODEL>
-__global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const int* __restrict__ view_list, int n_list,
+__global__ void __launch_bounds__(PNP_WARPS * 32, 3) pnp_kernel(DevProblem p, const int* __restrict__ view_list, int n_list,
                                                               const unsigned char* __restrict__ view_mask, const int* __restrict__ resolution,
                                                               int n_max, double* __restrict__ T_out, int* __restrict__ ok_out) {
-  extern __shared__ double smem_pnp[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  double* sX = smem_pnp + (size_t)wib * 6 * n_max;
-  double* sY = sX + n_max;
-  double* sZ = sY + n_max;
-  double* sx = sZ + n_max;
-  double* sy = sx + n_max;
-  double* sw = sy + n_max;
-  const int warp = blockIdx.x * PNP_WARPS + wib, n_warps = gridDim.x * PNP_WARPS;
+  // the staged values have all passed through float (cv::Point2f / Point3f), so float storage is exact: 24 bytes per corner
+  extern __shared__ float smem_pnp[];
+  const int lane = threadIdx.x & (PNP_G - 1), gib = threadIdx.x / PNP_G;
+  const unsigned mask = ((1u << PNP_G) - 1u) << ((threadIdx.x & 31) & ~(PNP_G - 1));
+  float* sX = smem_pnp + (size_t)gib * 6 * n_max;
+  float* sY = sX + n_max;
+  float* sZ = sY + n_max;
+  float* sx = sZ + n_max;
+  float* sy = sx + n_max;
+  float* sw = sy + n_max;
+  const int warp = blockIdx.x * PNP_GROUPS + gib, n_warps = gridDim.x * PNP_GROUPS;
   for (int vi = warp; vi < n_list; vi += n_warps) {
     const int view = view_list[vi];
     if (view_mask && !view_mask[view]) continue;
@@ -293,10 +305,10 @@ __global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const
 #pragma unroll
     for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
     const int* res = resolution ? resolution + 2 * cam : nullptr;
-    __syncwarp();
+    __syncwarp(mask);
     // -- back-projection and the 80 degree cone; everything passes through float as cv::Point2f / cv::Point3f do
     double cnt = 0.0, cX = 0.0, cY = 0.0, cZ = 0.0, cx = 0.0, cy = 0.0;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n; i += PNP_G) {
       const double u = (double)(float)p.y_u[b + i], v = (double)(float)p.y_v[b + i];
       const double* tp = p.target + 3 * p.corner[b + i];
       double bp[3] = {0.0, 0.0, 0.0};
@@ -305,28 +317,28 @@ __global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const
       const double X = (double)(float)tp[0], Y = (double)(float)tp[1], Z = (double)(float)tp[2];
       const double mx = ok ? (double)(float)(bp[0] / bp[2]) : 0.0, my = ok ? (double)(float)(bp[1] / bp[2]) : 0.0;
       const double w = ok ? 1.0 : 0.0;
-      sX[i] = X; sY[i] = Y; sZ[i] = Z; sx[i] = mx; sy[i] = my; sw[i] = w;
+      sX[i] = (float)X; sY[i] = (float)Y; sZ[i] = (float)Z; sx[i] = (float)mx; sy[i] = (float)my; sw[i] = (float)w;
       cnt += w; cX += w * X; cY += w * Y; cZ += w * Z; cx += w * mx; cy += w * my;
     }
-    __syncwarp();
-    cnt = wsum(cnt);
+    __syncwarp(mask);
+    cnt = wsum(cnt, mask);
     double* To = T_out + (size_t)view * POSE_STRIDE;
     if (cnt < 4.0) {  // "if (Ps.size() < 4) return false"
       if (lane == 0) { To[0] = To[1] = To[2] = 0.0; To[3] = 1.0; To[4] = To[5] = To[6] = 0.0; ok_out[view] = 0; }
       continue;
     }
     const double icnt = 1.0 / cnt;
-    cX = wsum(cX) * icnt; cY = wsum(cY) * icnt; cZ = wsum(cZ) * icnt; cx = wsum(cx) * icnt; cy = wsum(cy) * icnt;
+    cX = wsum(cX, mask) * icnt; cY = wsum(cY, mask) * icnt; cZ = wsum(cZ, mask) * icnt; cx = wsum(cx, mask) * icnt; cy = wsum(cy, mask) * icnt;
     // -- the object plane: principal axes of the corners (cvFindExtrinsicCameraParams2's planar branch)
     double Rt[9], Tt[3];
     {
       double m[6] = {0, 0, 0, 0, 0, 0};
-      for (int i = lane; i < n; i += 32) {
+      for (int i = lane; i < n; i += PNP_G) {
         const double w = sw[i], dx = sX[i] - cX, dy = sY[i] - cY, dz = sZ[i] - cZ;
         m[0] += w * dx * dx; m[1] += w * dx * dy; m[2] += w * dx * dz; m[3] += w * dy * dy; m[4] += w * dy * dz; m[5] += w * dz * dz;
       }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) m[i] = wsum(m[i]);
+      for (int i = 0; i < 6; ++i) m[i] = wsum(m[i], mask);
       double A[9] = {m[0], m[1], m[2], m[1], m[3], m[4], m[2], m[4], m[5]}, ev[3], V[9];
       eig3(A, ev, V);
       // sort descending: the plane normal is the eigenvector of the smallest eigenvalue
@@ -359,16 +371,16 @@ __global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const
     {
       // per-axis scales: count / sum |deviation| (the normalisation of OpenCV's homography kernel)
       double aX = 0.0, aY = 0.0, ax = 0.0, ay = 0.0;
-      for (int i = lane; i < n; i += 32) {
+      for (int i = lane; i < n; i += PNP_G) {
         const double w = sw[i];
         const double X = Rt[0] * sX[i] + Rt[1] * sY[i] + Rt[2] * sZ[i] + Tt[0], Y = Rt[3] * sX[i] + Rt[4] * sY[i] + Rt[5] * sZ[i] + Tt[1];
         aX += w * fabs(X); aY += w * fabs(Y); ax += w * fabs(sx[i] - cx); ay += w * fabs(sy[i] - cy);
       }
-      const double sMx = cnt / wsum(aX), sMy = cnt / wsum(aY), smx = cnt / wsum(ax), smy = cnt / wsum(ay);
+      const double sMx = cnt / wsum(aX, mask), sMy = cnt / wsum(aY, mask), smx = cnt / wsum(ax, mask), smy = cnt / wsum(ay, mask);
       // L^T L of the rows [X Y 1 0 0 0 -xX -xY -x], [0 0 0 X Y 1 -yX -yY -y] in blocks: A = sum q q^T, B = sum x q q^T,
       // C = sum y q q^T, D = sum (x^2 + y^2) q q^T with q = (X, Y, 1)
       double Aq[6] = {0, 0, 0, 0, 0, 0}, Bq[6] = {0, 0, 0, 0, 0, 0}, Cq[6] = {0, 0, 0, 0, 0, 0}, Dq[6] = {0, 0, 0, 0, 0, 0};
-      for (int i = lane; i < n; i += 32) {
+      for (int i = lane; i < n; i += PNP_G) {
         const double w = sw[i];
         const double X = (Rt[0] * sX[i] + Rt[1] * sY[i] + Rt[2] * sZ[i] + Tt[0]) * sMx, Y = (Rt[3] * sX[i] + Rt[4] * sY[i] + Rt[5] * sZ[i] + Tt[1]) * sMy;
         const double x = (sx[i] - cx) * smx, y = (sy[i] - cy) * smy;
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const
         for (int k = 0; k < 6; ++k) { Aq[k] += qq[k]; Bq[k] += x * qq[k]; Cq[k] += y * qq[k]; Dq[k] += r2 * qq[k]; }
       }
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { Aq[k] = wsum(Aq[k]); Bq[k] = wsum(Bq[k]); Cq[k] = wsum(Cq[k]); Dq[k] = wsum(Dq[k]); }
+      for (int k = 0; k < 6; ++k) { Aq[k] = wsum(Aq[k], mask); Bq[k] = wsum(Bq[k], mask); Cq[k] = wsum(Cq[k], mask); Dq[k] = wsum(Dq[k], mask); }
       // symmetric 3x3 blocks from the 6 unique sums: index (r, c) -> {0: XX, 1: XY, 2: X, 3: YY, 4: Y, 5: 1}
       const int sidx[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
       double N[64], rhs[8];
@@ -432,7 +444,7 @@ __global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const
       for (int i = 0; i < 3; ++i) t[i] = R0[i * 3] * Tt[0] + R0[i * 3 + 1] * Tt[1] + R0[i * 3 + 2] * Tt[2] + H[i * 3 + 2] * i3;
     }
     // -- Levenberg-Marquardt on the reprojection error in normalised coordinates, update R <- exp(d_theta) R, t <- t + d_t
-    double cost = pnp_cost(R, t, sX, sY, sZ, sx, sy, sw, n, lane);
+    double cost = pnp_cost(R, t, sX, sY, sZ, sx, sy, sw, n, lane, mask);
     double lambda = 1e-3;
     bool good = isfinite(cost);
     for (int it = 0; it < 60 && good; ++it) {
@@ -441,7 +453,7 @@ __global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const
       for (int i = 0; i < 21; ++i) Hs[i] = 0.0;
 #pragma unroll
       for (int i = 0; i < 6; ++i) g[i] = 0.0;
-      for (int i = lane; i < n; i += 32) {
+      for (int i = lane; i < n; i += PNP_G) {
         const double w = sw[i], X = sX[i], Y = sY[i], Z = sZ[i];
         const double qx = R[0] * X + R[1] * Y + R[2] * Z, qy = R[3] * X + R[4] * Y + R[5] * Z, qz = R[6] * X + R[7] * Y + R[8] * Z;
         const double px = qx + t[0], py = qy + t[1], pz = qz + t[2];
@@ -460,10 +472,10 @@ __global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const
         }
       }
 #pragma unroll
-      for (int i = 0; i < 21; ++i) Hs[i] = wsum(Hs[i]);
+      for (int i = 0; i < 21; ++i) Hs[i] = wsum(Hs[i], mask);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) g[i] = wsum(g[i]);
-      bool accepted = false;
+      for (int i = 0; i < 6; ++i) g[i] = wsum(g[i], mask);
+      bool accepted = false, flat = false;
       double step_max = 0.0;
       for (int tries = 0; tries < 12 && !accepted; ++tries) {
         double A[36], d[6];
@@ -482,11 +494,12 @@ __global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const
         double Rn[9];
         rotate_left(d, R, Rn);
         const double tn[3] = {t[0] + d[3], t[1] + d[4], t[2] + d[5]};
-        const double cn = pnp_cost(Rn, tn, sX, sY, sZ, sx, sy, sw, n, lane);
+        const double cn = pnp_cost(Rn, tn, sX, sY, sZ, sx, sy, sw, n, lane, mask);
         if (cn <= cost) {
 #pragma unroll
           for (int i = 0; i < 9; ++i) R[i] = Rn[i];
           t[0] = tn[0]; t[1] = tn[1]; t[2] = tn[2];
+          flat = (cost - cn) <= 1e-15 * cost;  // the cost has stopped moving at double precision
           cost = cn;
           lambda = fmax(lambda * 0.1, 1e-15);
           accepted = true;
@@ -496,8 +509,10 @@ __global__ void __launch_bounds__(PNP_WARPS * 32) pnp_kernel(DevProblem p, const
           lambda *= 10.0;
         }
       }
-      if (!accepted) break;  // no descent direction left at this precision: converged
-      if (step_max < 1e-13 * fmax(1.0, fmax(fabs(t[0]), fmax(fabs(t[1]), fabs(t[2]))))) break;
+      if (!accepted || flat) break;  // no descent left at this precision: converged
+      // the iteration contracts at least as fast as lambda (<= 1e-4 by now) near the minimum: after a step this small the next one
+      // is below rounding
+      if (step_max < 1e-10 * fmax(1.0, fmax(fabs(t[0]), fmax(fabs(t[1]), fabs(t[2]))))) break;
     }
     // -- T_target_camera = inverse([R t]) -> (q, t) as sm::kinematics::Transformation::set stores it
     if (lane == 0) {
@@ -569,7 +584,7 @@ template <int MODEL>
 cudaError_t launch_pnp_model(const DevProblem& p, const int* list, int n, const unsigned char* mask, const int* resolution, int n_max, double* T_out,
                              int* ok_out, StreamCtx& s) {
   if (n <= 0) return cudaSuccess;
-  const size_t smem = sizeof(double) * 6 * (size_t)n_max * PNP_WARPS;
+  const size_t smem = sizeof(float) * 6 * (size_t)n_max * PNP_GROUPS;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(pnp_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -577,7 +592,7 @@ cudaError_t launch_pnp_model(const DevProblem& p, const int* list, int n, const 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = min((n + PNP_WARPS - 1) / PNP_WARPS, sms * 8);
+  const int grid = min((n + PNP_GROUPS - 1) / PNP_GROUPS, sms * 8);
   pnp_kernel<MODEL><<<grid, PNP_WARPS * 32, smem, s.stream>>>(p, list, n, mask, resolution, n_max, T_out, ok_out);
   ++*s.launches;
   return cudaGetLastError();

@@ -60,6 +60,52 @@ for cfg, S in [(2, 9), (3, 7), (4, 10), (5, 5), (6, 8)]:
         ok_all &= good
         print(f"cfg{cfg} S={S} world={world} peer_exchange={use_px}: {'OK' if good else 'MISMATCH'} {r}", flush=True)
     g.close()
+# ---- weighting, reprojection statistics and the initial-guess stage on sharded problems ----
+INV_R = np.array([[3.0, 0.4], [0.4, 5.0]])
+for cfg, S, policy in [(2, 9, (1, 1.5, 0.0, 0.0)), (3, 7, (2, 4.0, 0.0, 0.0)), (4, 10, None)]:
+    p = synthetic.make_config(cfg, n_sets=S)
+    g = capi.B200SchurLinearSystemSolver(p, n_ranks=world, rank=rank, nccl_id=fresh_nccl_id(), device=lr)
+    if use_px:
+        attach_peers(g)
+    g.set_inv_r(INV_R)
+    if policy:
+        g.set_m_estimator(*policy)
+    J = g.evaluate_error()
+    g.build_system()
+    g.set_constant_conditioner(10.0)
+    dx, ok = g.solve_system(fetch_dx=True, gather=True)
+    stats = g.reprojection_statistics()
+    sol, tr = g.optimize(KbOptimizerOptions.kalibr2_default())
+    stats_final = g.reprojection_statistics()
+    # initial-guess stage: every rank initialises its own sets
+    g.reset_state()
+    n_failed = g.initialize_set_poses()
+    lo, hi = synthetic.shard_sets(S, world, rank)
+    mine = g.set_poses()[lo:hi]
+    from oracle import ko_init as ki
+    so, _ = ki.target_pose_guesses(p)
+    init_err = max((np.abs(ki.pose_to_T(a) - ki.pose_to_T(b)).max() for a, b in zip(mine, so[lo:hi])), default=0.0)
+    t = torch.tensor([init_err, float(n_failed)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        from oracle import oracle_api as oa
+        o = oa.OracleProblem(p)
+        o.set_inv_r(INV_R)
+        if policy:
+            o.set_m_estimator(*policy)
+        Jo = o.evaluate_error(); o.build_system(); o.set_constant_conditioner(10.0)
+        odx, ook = o.solve_system()
+        ostats = o.reprojection_statistics()
+        osol, otr = o.optimize(KbOptimizerOptions.kalibr2_default())
+        ostats_final = o.reprojection_statistics()
+        r = dict(J=abs(J - Jo) / Jo, dx=rel(dx, odx), stats=float(np.abs(stats - ostats).max()), iters=(sol.iterations, osol.iterations),
+                 jfinal=abs(sol.j_final - osol.j_final) / osol.j_final, stats_final=float(np.abs(stats_final - ostats_final).max()),
+                 init_pose_err=float(t[0].item()), init_failed=int(t[1].item()))
+        good = (r["J"] < 1e-11 and r["dx"] < 1e-7 and r["stats"] < 1e-10 and sol.iterations == osol.iterations and r["jfinal"] < 1e-9
+                and r["stats_final"] < 1e-6 and r["init_pose_err"] < 1e-8 and r["init_failed"] == 0)
+        ok_all &= good
+        print(f"weighted cfg{cfg} S={S} policy={policy} world={world} peer_exchange={use_px}: {'OK' if good else 'MISMATCH'} {r}", flush=True)
+    g.close()
 dist.barrier()
 if rank == 0:
     print("MULTI_GPU_PARITY", "PASS" if ok_all else "FAIL", flush=True)
