@@ -234,6 +234,20 @@ KB_API kb_status kb_initialize_set_poses(kb_handle* h, const int32_t* resolution
 KB_API kb_status kb_estimate_stereo_baseline(kb_handle* h, const int32_t* resolution, int32_t cam_l, int32_t cam_h, double* baseline /*[7]*/,
                                              int32_t* n_used);
 
+/* ≙ CameraGeometry::initializeIntrinsics for camera `cam` from all of its views, on a target_rows x target_cols grid target
+ *   (corner id = row * cols + col, CAM/src/GridCalibrationTargetBase.cpp:28-30):
+ *   pinhole-*: focal length = median of |v1 - v2| / pi over the vanishing-point pairs of the grid rows seen as circles, complete views
+ *              only (CAM/.../implementation/PinholeProjection.hpp:599-803); fallback_focal_length > 0 is used when no guess exists;
+ *   omni-*, eucm-none, ds-none: per (view, row) a focal guess from the row's line image, kept if it gives the lowest mean reprojection
+ *              error after a PnP of that view (OmniProjection.hpp:721-866; ExtendedUnifiedProjection.hpp:734-760 and
+ *              DoubleSphereProjection.hpp:785-811 halve it and set alpha = 0.5, beta = 1 / xi = 0, alpha = 0.5).
+ *   Principal point = image centre, distortion cleared.  The guess replaces the camera's parameters (state and the reset point) and is
+ *   returned in params; *success ≙ the reference's return value.  Single rank.  The reference's pinhole pair loop reads past its
+ *   circle arrays when cols > rows (undefined behaviour); here the pairs are taken among the rows that exist. */
+KB_API kb_status kb_initialize_intrinsics(kb_handle* h, int32_t cam, int32_t target_rows, int32_t target_cols,
+                                          const int32_t* resolution /*[n_cams][2]*/, double fallback_focal_length /* <= 0: none */,
+                                          double* params /*[KB_CAM_PARAM_STRIDE], may be NULL*/, int32_t* success);
+
 /* ---- marginal analysis of the calibration block --------------------------------
  * ≙ aslam::calibration::LinearSolver::analyzeMarginal (aslam_incremental_calibration/incremental_calibration/src/core/
  *   LinearSolver.cpp:466-528) — what IncrementalEstimator::addBatch asks of its solver after every re-optimisation

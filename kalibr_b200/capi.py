@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
     "kb_set_inv_r", "kb_get_sqrt_inv_r", "kb_set_m_estimator", "kb_m_estimator_parameter", "kb_reprojection_statistics",
-    "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline",
+    "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics",
 ]
 
 MEST_NONE, MEST_HUBER, MEST_CAUCHY, MEST_GEMAN_MCCLURE, MEST_BLAKE_ZISSERMAN = range(5)  # = kb_m_estimator
@@ -112,6 +112,7 @@ def load_library() -> C.CDLL:
     L.kb_estimate_transformations.argtypes = [vp, vp, vp, vp]
     L.kb_initialize_set_poses.argtypes = [vp, vp, C.POINTER(C.c_int32)]
     L.kb_estimate_stereo_baseline.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, C.POINTER(C.c_int32)]
+    L.kb_initialize_intrinsics.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_double, vp, C.POINTER(C.c_int32)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:  # default: status-returning entry points
@@ -254,6 +255,15 @@ class B200SchurLinearSystemSolver:
         r = self._res(resolution)
         self._check(self._L.kb_initialize_set_poses(self._h, _p(r), C.byref(nf)), "kb_initialize_set_poses")
         return int(nf.value)
+
+    def initialize_intrinsics(self, cam: int, rows: int, cols: int, resolution, fallback_focal_length: float = 0.0):
+        """≙ CameraGeometry::initializeIntrinsics for one camera: (params[10], success); the guess becomes the camera's state."""
+        out = np.zeros(10)
+        ok = C.c_int32()
+        r = self._res(resolution)
+        self._check(self._L.kb_initialize_intrinsics(self._h, cam, rows, cols, _p(r), fallback_focal_length, _p(out), C.byref(ok)),
+                    "kb_initialize_intrinsics")
+        return out, bool(ok.value)
 
     def estimate_stereo_baseline(self, cam_l: int = 0, cam_h: int = 1, resolution=None):
         out = np.zeros(7)

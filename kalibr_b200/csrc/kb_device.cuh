@@ -194,6 +194,11 @@ cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx&
 cudaError_t launch_estimate_transformations(const DevProblem& p, const int* view_list, const int* model_begin, const unsigned char* view_mask,
                                             const int* resolution /*[n_cams][2] device, or null*/, double* T_out /*[n_views][7]*/, int* ok_out /*[n_views]*/,
                                             StreamCtx& s);
+// initializeIntrinsics: pinhole family -> out2 = (median focal guess, number of guesses); omni family -> out3 = (gamma, success, error)
+cudaError_t launch_focal_guesses(const DevProblem& p, const int* cam_views, int n_views, int rows, int cols, double* fg /*[n_views][pairs]*/, double* out2,
+                                 StreamCtx& s);
+cudaError_t launch_omni_candidates(const DevProblem& p, const int* cam_views, int n_views, int rows, int cols, int ru, int rv,
+                                   double* cand /*[n_views * rows][2]*/, double* out3, StreamCtx& s);
 cudaError_t launch_best_view_mask(const DevProblem& p, unsigned char* mask /*[n_views]*/, StreamCtx& s);
 cudaError_t launch_set_pose_guess(const DevProblem& p, const double* T_views, const int* ok_views, double* set_poses_out, int* set_ok, StreamCtx& s);
 int schur_num_partials(const DevProblem& p);

@@ -157,6 +157,7 @@ struct kb_handle {
   DevBuf<double> pnp_T;               // initial-guess stage: T_target_camera per view
   DevBuf<int> pnp_ok, pnp_res, pnp_set_ok;
   DevBuf<unsigned char> pnp_mask;
+  DevBuf<double> init_scratch, init_out;  // initializeIntrinsics: candidates / guesses, results
   std::vector<double> trace;
   // ---- multi-GPU ----
   NcclComm comm = nullptr;
@@ -1134,6 +1135,75 @@ kb_status kb_estimate_stereo_baseline(kb_handle* h, const int32_t* resolution, i
   }
   host_r2quat(C, baseline);
   for (int i = 0; i < 3; ++i) baseline[4 + i] = mt[i];
+  return KB_OK;
+}
+
+kb_status kb_initialize_intrinsics(kb_handle* h, int32_t cam, int32_t target_rows, int32_t target_cols, const int32_t* resolution,
+                                   double fallback_focal_length, double* params, int32_t* success) {
+  if (h->n_ranks != 1) return fail(h, KB_ERR_STATE, "kb_initialize_intrinsics needs a single rank (it looks at every view of the camera)");
+  if (cam < 0 || cam >= h->n_cams || !resolution) return fail(h, KB_ERR_INVALID_ARGUMENT, "bad camera index or null resolution");
+  if (target_rows < 1 || target_cols < 1 || target_rows * target_cols != h->d.n_target || target_cols > 32 || target_rows > 1024)
+    return fail(h, KB_ERR_INVALID_ARGUMENT, "target_rows x target_cols must equal the number of target points (cols <= 32)");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  const int model = h->cam_model[cam];
+  const int ru = resolution[2 * cam], rv = resolution[2 * cam + 1];
+  const double cu = (ru - 1.0) / 2.0, cv = (rv - 1.0) / 2.0;  // "initialize the image center at the center of the image"
+  int n_views = 0, first = 0;
+  for (size_t w = 0; w < h->h_view_cam.size(); ++w) n_views += h->h_view_cam[w] == cam;
+  for (int k = 0; k < cam; ++k)
+    for (size_t w = 0; w < h->h_view_cam.size(); ++w) first += h->h_view_cam[w] == k;  // offset into the camera-major view list
+  const int* cam_views = h->cam_view_list.p + first;
+  if (h->init_out.n < 4) KB_CUDA(h, h->init_out.alloc(4));
+  double res4[4] = {0, 0, 0, 0};
+  double prm[KB_CAM_PARAM_STRIDE] = {0};
+  bool ok = false, write = false;
+  const bool pinhole = model == KB_PINHOLE_RADTAN || model == KB_PINHOLE_EQUI || model == KB_PINHOLE_FOV;
+  if (pinhole) {
+    const int rr = std::min(target_rows, target_cols), n_pairs = rr * (rr - 1) / 2;
+    const size_t need = (size_t)std::max(n_views, 1) * std::max(n_pairs, 1);
+    if (h->init_scratch.n < need) KB_CUDA(h, h->init_scratch.alloc(need));
+    KB_CUDA(h, launch_focal_guesses(h->d, cam_views, n_views, target_rows, target_cols, h->init_scratch.p, h->init_out.p, c));
+    KB_CUDA(h, cudaMemcpyAsync(res4, h->init_out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    double f0 = res4[0];
+    ok = res4[1] > 0.0;
+    if (!ok && fallback_focal_length > 0.0) { f0 = fallback_focal_length; ok = true; }  // PinholeProjection.hpp:781-791: returns true
+    if (ok) { prm[0] = prm[1] = f0; prm[2] = cu; prm[3] = cv; write = true; }
+  } else {
+    const size_t need = (size_t)2 * std::max(n_views, 1) * target_rows;
+    if (h->init_scratch.n < need) KB_CUDA(h, h->init_scratch.alloc(need));
+    KB_CUDA(h, launch_omni_candidates(h->d, cam_views, n_views, target_rows, target_cols, ru, rv, h->init_scratch.p, h->init_out.p, c));
+    KB_CUDA(h, cudaMemcpyAsync(res4, h->init_out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    double gamma0 = res4[0];
+    ok = res4[1] > 0.0;
+    const bool have_gamma = ok || fallback_focal_length > 0.0;
+    if (!ok && fallback_focal_length > 0.0) gamma0 = fallback_focal_length;  // OmniProjection.hpp:826-841: parameters set, still returns false
+    if (model == KB_OMNI_RADTAN || model == KB_OMNI_NONE) {
+      if (have_gamma) { prm[0] = 1.0; prm[1] = prm[2] = gamma0; prm[3] = cu; prm[4] = cv; write = true; }
+    } else if (ok) {  // EUCM / double sphere adopt the omni result only on success (ExtendedUnifiedProjection.hpp:741-757, DoubleSphereProjection.hpp:792-808)
+      if (model == KB_EUCM_NONE) { prm[0] = 0.5; prm[1] = 1.0; }
+      else { prm[0] = 0.0; prm[1] = 0.5; }
+      prm[2] = prm[3] = 0.5 * gamma0; prm[4] = cu; prm[5] = cv;
+      write = true;
+    }
+  }
+  if (write) {  // the reference mutates the geometry in place; the guess also becomes what kb_reset_state returns to
+    const size_t off = (size_t)cam * CAM_PARAM_STRIDE;
+    KB_CUDA(h, cudaMemcpyAsync(h->cam_params.p + off, prm, sizeof(prm), cudaMemcpyHostToDevice, h->stream));
+    KB_CUDA(h, cudaMemcpyAsync(h->init_cam.p + off, prm, sizeof(prm), cudaMemcpyHostToDevice, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    ++h->state_version;
+    h->built = h->solved = h->has_backup = false;
+    if (params) std::memcpy(params, prm, sizeof(prm));
+  } else if (params) {
+    std::vector<double> cur((size_t)h->n_cams * CAM_PARAM_STRIDE);
+    KB_CUDA(h, cudaMemcpyAsync(cur.data(), h->cam_params.p, sizeof(double) * cur.size(), cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(params, &cur[(size_t)cam * CAM_PARAM_STRIDE], sizeof(prm));
+  }
+  if (success) *success = ok ? 1 : 0;
   return KB_OK;
 }
 

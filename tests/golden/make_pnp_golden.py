@@ -44,6 +44,12 @@ def main():
         out[name + "/set_ok"] = good
         if p.n_cams >= 2:
             out[name + "/baseline01"] = ki.stereo_baseline_guess(p, 0, 1, pnp=ki.cv2_pnp)
+        # initializeIntrinsics per camera with cv2's PnP inside the omni family's candidate test
+        res = [synthetic.TRUTH_PARAMS[m][1] for m in p.cam_model]
+        for k in range(p.n_cams):
+            prm, ok_k = ki.initialize_intrinsics(p, k, 10, 12, res[k], pnp=ki.cv2_pnp)
+            out[name + f"/init_params{k}"] = prm
+            out[name + f"/init_ok{k}"] = np.array(ok_k)
         # the raw PnP problem of the first view, for a test of solve_pnp alone
         b, e = p.view_begin[0], p.view_begin[1]
         k = p.view_cam[0]

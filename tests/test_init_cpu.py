@@ -14,6 +14,8 @@ from kalibr_b200 import synthetic
 from kalibr_b200.problem import MODEL_D, MODEL_P
 from oracle import ko_init as ki
 
+EUCM, DS = 3, 4
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pnp_cv2.npz")
 CASES = {"cfg1_S6": (1, 6, {}), "cfg2_S9": (2, 9, {}), "cfg3_S5": (3, 5, {}), "cfg4_S2": (4, 2, {}), "cfg6_S4": (6, 4, {}),
          "cfg7_S7": (7, 7, {}), "cfg3_S4_ragged": (3, 4, {"dropout": 0.3})}
@@ -124,3 +126,59 @@ def test_fewer_than_four_corners_fails():
     p = synthetic.make_config(1, n_sets=1)
     pose, ok = ki.estimate_transformation(p.cam_model[0], p.cam_params[0], p.y_u[:3], p.y_v[:3], p.target_points[p.corner_id[:3]])
     assert not ok and np.array_equal(pose, [0, 0, 0, 1, 0, 0, 0])
+
+
+# ---- initializeIntrinsics --------------------------------------------------------------------------------------------------
+def test_circle_helpers():
+    """PinholeHelpers::fitCircle / intersectCircles / medianOfVectorElements (PinholeProjection.hpp:612-707)."""
+    a = np.linspace(0.3, 1.4, 12)
+    cx, cy, r = ki.fit_circle(np.stack([5.0 + 3.0 * np.cos(a), -2.0 + 3.0 * np.sin(a)], 1))
+    assert abs(cx - 5.0) < 1e-9 and abs(cy + 2.0) < 1e-9 and abs(r - 3.0) < 1e-9
+    ip = ki.intersect_circles(0, 0, 5, 6, 0, 5)
+    assert len(ip) == 2 and np.allclose(sorted(ip), [(3, -4), (3, 4)])
+    assert ki.intersect_circles(0, 0, 1, 5, 0, 1) == [] and ki.intersect_circles(0, 0, 5, 1, 0, 1) == []
+    assert len(ki.intersect_circles(0, 0, 1, 2, 0, 1)) == 1
+    assert ki.median_of_vector_elements([3, 1, 2]) == 2 and ki.median_of_vector_elements([4, 1, 3, 2]) == 2.5
+    assert ki.median([4, 1, 3, 2]) == 3  # kalibr2::math::median is the upper median: the two helpers differ
+
+
+def test_omni_line_image_recovers_the_focal_length():
+    """A straight line seen by a unified camera with xi = 1 gives gamma exactly (the camodocal construction)."""
+    rng = np.random.default_rng(2)
+    gamma, cu, cv = 420.0, 319.5, 239.5
+    for _ in range(5):
+        p0 = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), rng.uniform(0.5, 1.0)])
+        d = rng.normal(size=3)
+        pts = p0 + np.linspace(-0.4, 0.4, 12)[:, None] * d / np.linalg.norm(d)
+        rz = 1.0 / (pts[:, 2] + np.linalg.norm(pts, axis=1))
+        u, v = gamma * pts[:, 0] * rz, gamma * pts[:, 1] * rz
+        g = ki.omni_row_candidate(u, v)
+        assert g is None or abs(g - gamma) < 1e-6 * gamma
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_initialize_intrinsics_matches_golden(golden, name):
+    cfg, S, kw = CASES[name]
+    p = synthetic.make_config(cfg, n_sets=S, **kw)
+    for k in range(p.n_cams):
+        m = p.cam_model[k]
+        res = synthetic.TRUTH_PARAMS[m][1]
+        prm, ok = ki.initialize_intrinsics(p, k, 10, 12, res)
+        assert ok == bool(golden[name + f"/init_ok{k}"])
+        assert np.abs(prm - golden[name + f"/init_params{k}"]).max() <= 1e-9 * max(np.abs(prm).max(), 1.0)
+        if ok:
+            P = MODEL_P[m]
+            assert np.all(prm[P:] == 0.0)                                   # distortion cleared
+            assert prm[P - 2] == (res[0] - 1) / 2 and prm[P - 1] == (res[1] - 1) / 2   # image centre
+            truth_f = synthetic.TRUTH_PARAMS[m][0][P - 4]
+            f_equiv = prm[P - 4] * (2.0 if m in (EUCM, DS) else 1.0)  # EUCM / DS store half the unified-model focal length
+            assert 0.5 * truth_f < f_equiv < 4.0 * truth_f                # a usable start, not an estimate
+
+
+def test_initialize_intrinsics_fallbacks():
+    p = synthetic.make_config(3, n_sets=2, dropout=0.7)  # no complete view, hardly a row with more than 4 corners
+    res = synthetic.TRUTH_PARAMS
+    prm, ok = ki.initialize_intrinsics(p, 3, 10, 12, res[1][1])            # pinhole-equi: no complete view
+    assert not ok and np.all(prm == 0)
+    prm, ok = ki.initialize_intrinsics(p, 3, 10, 12, res[1][1], fallback=450.0)
+    assert ok and prm[0] == prm[1] == 450.0                                # PinholeProjection.hpp:781-791 returns true with the fallback

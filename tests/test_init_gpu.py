@@ -128,3 +128,69 @@ def test_edge_cases(capi):
     assert pose_err(sp[0], so[0]) < 1e-12                        # failed PnP: identity (chained), as the reference
     b, n = g.estimate_stereo_baseline(0, 1)
     assert n == 1 and pose_err(b, ki.stereo_baseline_guess(q, 0, 1)) < 1e-7
+
+
+# ---- initializeIntrinsics --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CASES))
+def test_initialize_intrinsics_matches_golden_and_oracle(capi, golden, name):
+    cfg, S, kw = CASES[name]
+    p = synthetic.make_config(cfg, n_sets=S, **kw)
+    g = capi.B200SchurLinearSystemSolver(p)
+    res = [synthetic.TRUTH_PARAMS[m][1] for m in p.cam_model]
+    before = g.camera_params()
+    for k in range(p.n_cams):
+        prm, ok = g.initialize_intrinsics(k, 10, 12, res)
+        assert ok == bool(golden[name + f"/init_ok{k}"])
+        gold = golden[name + f"/init_params{k}"]
+        if ok:
+            assert np.abs(prm - gold).max() <= 1e-8 * max(np.abs(gold).max(), 1.0), (k, prm, gold)
+            assert np.array_equal(g.camera_params()[k], prm)              # the guess is the camera's state now
+        else:
+            assert np.array_equal(g.camera_params()[k], before[k])
+    g.reset_state()
+    for k in range(p.n_cams):
+        if bool(golden[name + f"/init_ok{k}"]):
+            assert np.abs(g.camera_params()[k] - golden[name + f"/init_params{k}"]).max() <= 1e-8 * 1e3   # ... and the reset point
+
+
+def test_initialize_intrinsics_fallbacks_and_errors(capi):
+    p = synthetic.make_config(3, n_sets=2, dropout=0.7)
+    g = capi.B200SchurLinearSystemSolver(p)
+    res = [synthetic.TRUTH_PARAMS[m][1] for m in p.cam_model]
+    for k in range(p.n_cams):
+        prm_o, ok_o = ki.initialize_intrinsics(p, k, 10, 12, res[k])
+        prm, ok = g.initialize_intrinsics(k, 10, 12, res)
+        assert ok == ok_o
+        if ok:
+            assert np.abs(prm - prm_o).max() <= 1e-8 * max(np.abs(prm_o).max(), 1.0)
+        prm_o, ok_o = ki.initialize_intrinsics(p, k, 10, 12, res[k], fallback=450.0)
+        prm, ok = g.initialize_intrinsics(k, 10, 12, res, fallback_focal_length=450.0)
+        assert ok == ok_o
+        if ok or p.cam_model[k] in (2, 6):  # omni sets the fallback but still reports failure
+            assert np.abs(prm - prm_o).max() <= 1e-8 * max(np.abs(prm_o).max(), 1.0)
+    with pytest.raises(capi.KalibrB200Error):
+        g.initialize_intrinsics(0, 9, 12, res)      # rows x cols must match the target
+    with pytest.raises(capi.KalibrB200Error):
+        g.initialize_intrinsics(7, 10, 12, res)
+
+
+def test_full_initialisation_then_calibration(capi, oracle_lib):
+    """CalibrateSingleCamera end to end on the device (CalibrationTools.hpp:93-144): initializeIntrinsics -> estimateTransformation per
+    view -> Optimizer2; the oracle optimises from the device's initial guesses."""
+    for model, S in ((1, 30), (6, 30)):  # pinhole-equi, omni-none
+        p = synthetic.make_problem([model], S, 0, seed=77 + model)
+        res = [synthetic.TRUTH_PARAMS[model][1]]
+        q = Problem(p.driver_order, p.cam_model, np.zeros((1, 10)) + 1.0, p.baselines, np.tile([0, 0, 0, 1.0, 0, 0, 0], (p.n_sets, 1)), p.target_points,
+                    p.view_set, p.view_cam, p.view_begin, p.y_u, p.y_v, p.corner_id)
+        g = capi.B200SchurLinearSystemSolver(q)
+        prm, ok = g.initialize_intrinsics(0, 10, 12, res)
+        assert ok
+        assert g.initialize_set_poses(res) == 0
+        sp = g.set_poses()
+        gs, _ = g.optimize(KbOptimizerOptions.kalibr2_default())
+        q2 = Problem(q.driver_order, q.cam_model, prm[None], q.baselines, sp, q.target_points, q.view_set, q.view_cam, q.view_begin, q.y_u, q.y_v, q.corner_id)
+        os_, _ = oracle_lib.OracleProblem(q2).optimize(KbOptimizerOptions.kalibr2_default())
+        assert gs.iterations == os_.iterations and abs(gs.j_final - os_.j_final) <= 1e-9 * os_.j_final
+        truth = np.asarray(synthetic.TRUTH_PARAMS[model][0], float)
+        P = 4 if model == 1 else 5
+        assert np.abs(g.camera_params()[0, P - 4:P] / truth[P - 4:P] - 1).max() < 2e-2, (model, g.camera_params()[0], truth)
