@@ -1,0 +1,48 @@
+"""Helpers shared by the C++ driver tests: build tests/cpp/driver_main.cpp against the in-tree library, write a problem file."""
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "driver_main")
+
+
+def build_driver():
+    src = os.path.join(ROOT, "tests", "cpp", "driver_main.cpp")
+    lib_dir = os.path.join(ROOT, "kalibr_b200")
+    hdr = os.path.join(ROOT, "include", "kalibr_b200", "calibration_tools.hpp")
+    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-L", lib_dir,
+                        "-lkalibr_b200", f"-Wl,-rpath,{lib_dir}", "-o", BIN], check=True)
+    return BIN
+
+
+def write_problem(path, p, resolution, rows=10, cols=12):
+    def arr(f, a, dt):
+        a = np.ascontiguousarray(a, dt).ravel()
+        f.write(np.int64(a.size).tobytes())
+        f.write(a.tobytes())
+
+    with open(path, "wb") as f:
+        arr(f, [p.n_cams, p.n_sets, rows, cols], np.int32)
+        arr(f, p.cam_model, np.int32)
+        arr(f, resolution, np.int32)
+        arr(f, p.cam_params, np.float64)
+        arr(f, p.baselines, np.float64)
+        arr(f, p.target_points, np.float64)
+        arr(f, p.view_set, np.int32)
+        arr(f, p.view_cam, np.int32)
+        arr(f, p.view_begin, np.int64)
+        arr(f, p.corner_id, np.int32)
+        arr(f, p.y_u, np.float64)
+        arr(f, p.y_v, np.float64)
+
+
+def run_driver(mode, path):
+    r = subprocess.run([build_driver(), mode, path], capture_output=True, text=True)
+    out = {}
+    for line in r.stdout.splitlines():
+        k, *v = line.split(" ")
+        out[k] = " ".join(v) if k == "error" else np.array([float(x) for x in v])
+    return r.returncode, out
