@@ -248,6 +248,34 @@ KB_API kb_status kb_initialize_intrinsics(kb_handle* h, int32_t cam, int32_t tar
                                           const int32_t* resolution /*[n_cams][2]*/, double fallback_focal_length /* <= 0: none */,
                                           double* params /*[KB_CAM_PARAM_STRIDE], may be NULL*/, int32_t* success);
 
+/* ---- the incremental estimator's linear solver ------------------------------------------
+ * ≙ aslam::calibration::LinearSolver::solveSystem -> solve (aslam_incremental_calibration/incremental_calibration/src/core/
+ *   LinearSolver.cpp:245-285, 299-463), the solver IncrementalEstimator gives Optimizer2 together with the Gauss-Newton policy
+ *   (src/core/IncrementalEstimator.cpp:66-71): an UNDAMPED least-squares step in which the set-pose columns are eliminated (QR
+ *   there, the Schur complement here) and the calibration block (intrinsics + baselines) is solved through the SVD of
+ *   Omega = A_r^T A_r - (A_r^T Q)(A_r^T Q)^T cut at the numerical rank (tolerance sv[0] * eps_svd * n unless svd_tol is given:
+ *   src/algorithms/linalg.cpp:244-261), so that unobservable directions get a zero update; column_scaling scales the calibration
+ *   columns to unit norm first (linalg.cpp:128-152, kalibr2_ros turns it on with eps_svd = 1e-6: CalibrateCameras.cpp:264-267).
+ *   Call after kb_build_system; kb_apply_state_update then applies the step. */
+typedef struct {
+  int32_t column_scaling; /* 0 */
+  double eps_norm;        /* std::numeric_limits<double>::epsilon() */
+  double eps_svd;         /* std::numeric_limits<double>::epsilon() */
+  double svd_tol;         /* -1: derive from eps_svd */
+} kb_svd_solver_options;
+typedef struct {
+  int32_t n, rank, rank_deficiency; /* ≙ getSVDRank / getSVDRankDeficiency of the (scaled) system */
+  double tolerance, sv_gap;         /* ≙ getSVDTolerance, getSvGap */
+} kb_svd_solve_result;
+KB_API void kb_default_svd_solver_options(kb_svd_solver_options* o);
+KB_API kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, double* dx /*[jcols] or NULL*/, int32_t gather_dx,
+                                     kb_svd_solve_result* out /*may be NULL*/, double* singular_values /*[n] or NULL: of the scaled system*/);
+
+/* One Optimizer2::optimize() with GaussNewtonTrustRegionPolicy (BE/src/GaussNewtonTrustRegionPolicy.cpp:18-40: rebuild and solve
+ * every iteration, no conditioner, never revert) over kb_solve_system_svd — the optimisation IncrementalEstimator::addBatch runs
+ * (IC/src/core/IncrementalEstimator.cpp:66-71, 377; kalibr2_ros: max_iterations = 20, both convergence deltas 1e-3). */
+KB_API kb_status kb_optimize_gauss_newton(kb_handle* h, const kb_optimizer_options* o, const kb_svd_solver_options* so, kb_solution* out);
+
 /* ---- marginal analysis of the calibration block --------------------------------
  * ≙ aslam::calibration::LinearSolver::analyzeMarginal (aslam_incremental_calibration/incremental_calibration/src/core/
  *   LinearSolver.cpp:466-528) — what IncrementalEstimator::addBatch asks of its solver after every re-optimisation

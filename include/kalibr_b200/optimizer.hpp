@@ -110,15 +110,64 @@ class B200SchurLinearSystemSolver : public LinearSystemSolver {
   std::vector<double> _rhs, _e;
 };
 
-// TrustRegionPolicy.cpp:28-57 + LevenbergMarquardtTrustRegionPolicy.cpp:37-113
-class LevenbergMarquardtTrustRegionPolicy {
+// B200 replacement of aslam::calibration::LinearSolver (aslam_incremental_calibration/incremental_calibration/src/core/
+// LinearSolver.cpp:241-463), the solver of the incremental estimator: same build, but an undamped solve whose calibration block goes
+// through a truncated SVD (kb_solve_system_svd).
+class B200SvdLinearSystemSolver : public B200SchurLinearSystemSolver {
+ public:
+  B200SvdLinearSystemSolver(kb_handle* h, const kb_svd_solver_options& options) : B200SchurLinearSystemSolver(h, true), _hs(h), _svdOptions(options) {}
+  std::string name() const override { return "b200_marginal_svd"; }
+  void setConstantConditioner(double /*diag*/) override {}  // the Gauss-Newton policy never asks for one
+  bool solveSystem(std::vector<double>& /*outDx: stays on the device*/) override {
+    if (kb_solve_system_svd(_hs, &_svdOptions, nullptr, 0, &_last, nullptr) != KB_OK) return false;  // ≙ the exceptions solveSystem turns into false
+    return true;
+  }
+  const kb_svd_solve_result& lastSolve() const { return _last; }
+
+ private:
+  kb_handle* _hs;
+  kb_svd_solver_options _svdOptions;
+  kb_svd_solve_result _last{};
+};
+
+// aslam::backend::TrustRegionPolicy (BE/include/aslam/backend/TrustRegionPolicy.hpp, BE/src/TrustRegionPolicy.cpp:28-57)
+class TrustRegionPolicy {
+ public:
+  virtual ~TrustRegionPolicy() {}
+  virtual std::string name() const = 0;
+  virtual bool requiresAugmentedDiagonal() const = 0;
+  virtual bool revertOnFailure() const = 0;
+  virtual void optimizationStarting(double J) = 0;
+  virtual bool solveSystem(double J, bool previousIterationFailed, int nThreads, std::vector<double>& outDx) = 0;
+  virtual double lambda() const { return 0.0; }
+  virtual double mu() const { return 0.0; }
+  void setSolver(std::shared_ptr<LinearSystemSolver> s) { _solver = s; }
+
+ protected:
+  std::shared_ptr<LinearSystemSolver> _solver;
+};
+
+// BE/src/GaussNewtonTrustRegionPolicy.cpp:18-40: rebuild and solve every iteration, no conditioner, never revert
+class GaussNewtonTrustRegionPolicy : public TrustRegionPolicy {
+ public:
+  std::string name() const override { return "gauss_newton"; }
+  bool requiresAugmentedDiagonal() const override { return false; }
+  bool revertOnFailure() const override { return false; }
+  void optimizationStarting(double /*J*/) override {}
+  bool solveSystem(double /*J*/, bool /*previousIterationFailed*/, int nThreads, std::vector<double>& outDx) override {
+    _solver->buildSystem(nThreads, true);
+    return _solver->solveSystem(outDx);
+  }
+};
+
+// LevenbergMarquardtTrustRegionPolicy.cpp:37-113
+class LevenbergMarquardtTrustRegionPolicy : public TrustRegionPolicy {
  public:
   explicit LevenbergMarquardtTrustRegionPolicy(double lambdaInit = 1e-3) : _lambdaInit(lambdaInit) {}
-  std::string name() const { return "levenberg_marquardt"; }
-  bool requiresAugmentedDiagonal() const { return true; }
-  bool revertOnFailure() const { return true; }
-  void setSolver(std::shared_ptr<LinearSystemSolver> s) { _solver = s; }
-  void optimizationStarting(double J) {
+  std::string name() const override { return "levenberg_marquardt"; }
+  bool requiresAugmentedDiagonal() const override { return true; }
+  bool revertOnFailure() const override { return true; }
+  void optimizationStarting(double J) override {
     _J = _p_J = _last_successful_J = J;
     _isFirstIteration = true;
     _lambda = _lambdaInit;
@@ -127,7 +176,7 @@ class LevenbergMarquardtTrustRegionPolicy {
     _p = _pInit;
     _mu = _muInit;
   }
-  bool solveSystem(double J, bool previousIterationFailed, int nThreads, std::vector<double>& outDx) {
+  bool solveSystem(double J, bool previousIterationFailed, int nThreads, std::vector<double>& outDx) override {
     if (previousIterationFailed) {
       _J = J;
     } else {
@@ -165,8 +214,8 @@ class LevenbergMarquardtTrustRegionPolicy {
   }
   double get_dJ() const { return _p_J - _J; }
   double getLmRho() { return get_dJ() / _solver->lmRhoDenominator(_lambda, _dx); }
-  double lambda() const { return _lambda; }
-  double mu() const { return _mu; }
+  double lambda() const override { return _lambda; }
+  double mu() const override { return _mu; }
 
  private:
   double _lambdaInit, _gammaInit = 3, _betaInit = 2, _muInit = 2;
@@ -175,7 +224,6 @@ class LevenbergMarquardtTrustRegionPolicy {
   int _p = 0;
   double _J = 0, _p_J = 0, _last_successful_J = 0;
   bool _isFirstIteration = true;
-  std::shared_ptr<LinearSystemSolver> _solver;
   std::vector<double> _dx;
 };
 
@@ -186,7 +234,7 @@ struct Optimizer2Options {  // Optimizer2Options.hpp:9-41 with kalibr2's values 
   int nThreads = 4;
   bool verbose = false;
   std::shared_ptr<LinearSystemSolver> linearSystemSolver;
-  std::shared_ptr<LevenbergMarquardtTrustRegionPolicy> trustRegionPolicy;
+  std::shared_ptr<TrustRegionPolicy> trustRegionPolicy;
 };
 
 class Optimizer2 {
@@ -201,7 +249,7 @@ class Optimizer2 {
   SolutionReturnValue optimize() {
     if (!_options.linearSystemSolver) throw std::runtime_error("kalibr_b200::Optimizer2: a B200 linear system solver must be set (no CPU fallback)");
     _solver = _options.linearSystemSolver;
-    _trustRegionPolicy = _options.trustRegionPolicy ? _options.trustRegionPolicy : std::make_shared<LevenbergMarquardtTrustRegionPolicy>();
+    _trustRegionPolicy = _options.trustRegionPolicy ? _options.trustRegionPolicy : std::shared_ptr<TrustRegionPolicy>(std::make_shared<LevenbergMarquardtTrustRegionPolicy>());
     SolutionReturnValue srv;
     _trace.clear();
     _p_J = 0.0;
@@ -264,7 +312,7 @@ class Optimizer2 {
  private:
   Optimizer2Options _options;
   std::shared_ptr<LinearSystemSolver> _solver;
-  std::shared_ptr<LevenbergMarquardtTrustRegionPolicy> _trustRegionPolicy;
+  std::shared_ptr<TrustRegionPolicy> _trustRegionPolicy;
   std::vector<double> _dx, _trace;
   double _J = 0, _p_J = 0;
 };

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
     "kb_set_inv_r", "kb_get_sqrt_inv_r", "kb_set_m_estimator", "kb_m_estimator_parameter", "kb_reprojection_statistics",
-    "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics",
+    "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics", "kb_default_svd_solver_options", "kb_solve_system_svd", "kb_optimize_gauss_newton",
 ]
 
 MEST_NONE, MEST_HUBER, MEST_CAUCHY, MEST_GEMAN_MCCLURE, MEST_BLAKE_ZISSERMAN = range(5)  # = kb_m_estimator
@@ -112,6 +112,10 @@ def load_library() -> C.CDLL:
     L.kb_estimate_transformations.argtypes = [vp, vp, vp, vp]
     L.kb_initialize_set_poses.argtypes = [vp, vp, C.POINTER(C.c_int32)]
     L.kb_estimate_stereo_baseline.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, C.POINTER(C.c_int32)]
+    L.kb_default_svd_solver_options.argtypes = [vp]
+    L.kb_default_svd_solver_options.restype = None
+    L.kb_solve_system_svd.argtypes = [vp, vp, vp, C.c_int32, vp, vp]
+    L.kb_optimize_gauss_newton.argtypes = [vp, vp, vp, vp]
     L.kb_initialize_intrinsics.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_double, vp, C.POINTER(C.c_int32)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
@@ -199,6 +203,18 @@ class B200SchurLinearSystemSolver:
         self._check(self._L.kb_solve_system(self._h, _p(dx), 1 if gather else 0, C.byref(pd)), "kb_solve_system")
         return dx, bool(pd.value)
 
+    def solve_system_svd(self, options=None, fetch_dx: bool = True, gather: bool = True):
+        """≙ aslam::calibration::LinearSolver::solveSystem: undamped step, calibration block by truncated SVD.
+        Returns (dx, KbSvdSolveResult, singular values of the (scaled) reduced system)."""
+        from .problem import KbSvdSolveResult, KbSvdSolverOptions
+
+        o = options or KbSvdSolverOptions.default()
+        res = KbSvdSolveResult()
+        dx = np.zeros(self.jcols) if fetch_dx else None
+        sv = np.zeros(self.problem.n_c)
+        self._check(self._L.kb_solve_system_svd(self._h, C.byref(o), _p(dx), 1 if gather else 0, C.byref(res), _p(sv)), "kb_solve_system_svd")
+        return dx, res, sv
+
     def lm_rho_denominator(self, lam: float) -> float:
         out = C.c_double()
         self._check(self._L.kb_lm_rho_denominator(self._h, lam, C.byref(out)), "kb_lm_rho_denominator")
@@ -283,6 +299,20 @@ class B200SchurLinearSystemSolver:
         options = options or KbOptimizerOptions.kalibr2_default()
         sol = KbSolution()
         self._check(self._L.kb_optimize(self._h, C.byref(options), C.byref(sol)), "kb_optimize")
+        n = self._L.kb_get_trace(self._h, None, 0)
+        tr = np.zeros((n, 3))
+        if n:
+            self._L.kb_get_trace(self._h, _p(tr), n)
+        return sol, tr
+
+    def optimize_gauss_newton(self, options: KbOptimizerOptions | None = None, solver_options=None):
+        """Optimizer2 with the Gauss-Newton policy over the truncated-SVD solver (the incremental estimator's optimisation)."""
+        from .problem import KbSvdSolverOptions
+
+        options = options or KbOptimizerOptions.estimator_default()
+        so = solver_options or KbSvdSolverOptions.kalibr2()
+        sol = KbSolution()
+        self._check(self._L.kb_optimize_gauss_newton(self._h, C.byref(options), C.byref(so), C.byref(sol)), "kb_optimize_gauss_newton")
         n = self._L.kb_get_trace(self._h, None, 0)
         tr = np.zeros((n, 3))
         if n:

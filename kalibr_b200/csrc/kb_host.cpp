@@ -157,6 +157,7 @@ struct kb_handle {
   DevBuf<double> pnp_T;               // initial-guess stage: T_target_camera per view
   DevBuf<int> pnp_ok, pnp_res, pnp_set_ok;
   DevBuf<unsigned char> pnp_mask;
+  DevBuf<double> svd_diag, svd_g, svd_result;  // truncated-SVD solve: diag of the camera block, column scales, {rank, tol, gap}
   DevBuf<double> init_scratch, init_out;  // initializeIntrinsics: candidates / guesses, results
   std::vector<double> trace;
   // ---- multi-GPU ----
@@ -1310,29 +1311,10 @@ kb_status kb_set_constant_conditioner(kb_handle* h, double lambda) {
   return KB_OK;
 }
 
-kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* pos_def) {
-  if (!h->built) return fail(h, KB_ERR_STATE, "kb_solve_system called before kb_build_system");
-  KB_CUDA(h, cudaSetDevice(h->device));
+// Everything after the camera-side solution sits in dxc: back-substitution of the set poses, dx^T (lambda dx + rhs) and max|dx|
+// (combined over the ranks), the optional copy of dx to the host.  The pose factors Lv must belong to the same damping.
+static kb_status solve_finish(kb_handle* h, double* dx, int32_t gather_dx) {
   StreamCtx c = ctx(h);
-  // diag(H) += lambda^2 on top of whatever earlier solves left there (BlockCholeskyLinearSystemSolver.cpp:77-86)
-  const double damping = h->diag_residual + h->lambda * h->lambda;
-  h->h_posdef[0] = 1;
-  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  {
-    StageTimer t(h, 3);
-    KB_CUDA(h, launch_schur(h->d, damping, h->partials.p, h->n_partials, h->posdef.p, c));
-    KB_CUDA(h, launch_schur_finalize(h->d, damping, h->partials.p, h->n_partials, true, c));
-    if (h->px_on) {  // the partials have gone straight into every rank's buffer: sum them in rank order
-      KB_CUDA(h, launch_px_reduce_system(h->d, c));
-    } else {
-      kb_status st = nccl_allreduce(h, h->Sred.p, (size_t)h->d.n_aug * h->d.n_aug, kNcclFloat64, kNcclSum);
-      if (st != KB_OK) return st;
-    }
-  }
-  {
-    StageTimer t(h, 4);
-    KB_CUDA(h, launch_reduced_solve(h->d, damping, h->posdef.p, c));
-  }
   {
     StageTimer t(h, 5);
     KB_CUDA(h, launch_backsub(h->d, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->posdef.p, c));
@@ -1397,11 +1379,112 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
     std::memcpy(&err, h->h_scalars + 7, 8);
     if (err) return fail(h, KB_ERR_NCCL, "peer exchange timed out: a rank did not reach the exchange step");
   }
+  return KB_OK;
+}
+
+kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* pos_def) {
+  if (!h->built) return fail(h, KB_ERR_STATE, "kb_solve_system called before kb_build_system");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  // diag(H) += lambda^2 on top of whatever earlier solves left there (BlockCholeskyLinearSystemSolver.cpp:77-86)
+  const double damping = h->diag_residual + h->lambda * h->lambda;
+  h->h_posdef[0] = 1;
+  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  {
+    StageTimer t(h, 3);
+    KB_CUDA(h, launch_schur(h->d, damping, h->partials.p, h->n_partials, h->posdef.p, c));
+    KB_CUDA(h, launch_schur_finalize(h->d, damping, h->partials.p, h->n_partials, true, c));
+    if (h->px_on) {  // the partials have gone straight into every rank's buffer: sum them in rank order
+      KB_CUDA(h, launch_px_reduce_system(h->d, c));
+    } else {
+      kb_status st = nccl_allreduce(h, h->Sred.p, (size_t)h->d.n_aug * h->d.n_aug, kNcclFloat64, kNcclSum);
+      if (st != KB_OK) return st;
+    }
+  }
+  {
+    StageTimer t(h, 4);
+    KB_CUDA(h, launch_reduced_solve(h->d, damping, h->posdef.p, c));
+  }
+  {
+    kb_status st = solve_finish(h, dx, gather_dx);
+    if (st != KB_OK) return st;
+  }
   // un-augment: BlockCholesky subtracts lambda, not lambda^2 (BlockCholeskyLinearSystemSolver.cpp:91-97)
   if (h->semantic == 0) h->diag_residual += h->lambda * h->lambda - h->lambda;
   h->solved = true;
   h->rho_lambda = h->lambda;
   if (pos_def) *pos_def = h->h_posdef[0];
+  return KB_OK;
+}
+
+// ---- the incremental estimator's linear solver: undamped, calibration block through a truncated SVD ---------------------------
+void kb_default_svd_solver_options(kb_svd_solver_options* o) {  // IC/src/core/LinearSolverOptions.cpp:30-38
+  o->column_scaling = 0;
+  o->eps_norm = 2.220446049250313e-16;
+  o->eps_svd = 2.220446049250313e-16;
+  o->svd_tol = -1.0;
+}
+
+kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, double* dx, int32_t gather_dx, kb_svd_solve_result* out,
+                              double* singular_values) {
+  if (!o) return fail(h, KB_ERR_INVALID_ARGUMENT, "null options");
+  if (!h->built) return fail(h, KB_ERR_STATE, "kb_solve_system_svd called before kb_build_system");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  StreamCtx c = ctx(h);
+  const int n = h->d.n_c;
+  if (n > 255) return fail(h, KB_ERR_INVALID_ARGUMENT, "calibration block too large");
+  if (h->eig_G.n != (size_t)(n + 1) * n) {
+    KB_CUDA(h, h->eig_G.alloc((size_t)(n + 1) * n));
+    KB_CUDA(h, h->eig_V.alloc((size_t)(n + 1) * n));
+    KB_CUDA(h, h->eig_sv.alloc(n));
+    KB_CUDA(h, h->eig_Vout.alloc((size_t)n * n));
+    KB_CUDA(h, h->eig_sweeps.alloc(1));
+  }
+  if (h->svd_diag.n != (size_t)n) {
+    KB_CUDA(h, h->svd_diag.alloc(n));
+    KB_CUDA(h, h->svd_g.alloc(n));
+    KB_CUDA(h, h->svd_result.alloc(4));
+  }
+  h->lambda = 0.0;  // GaussNewtonTrustRegionPolicy: no conditioner (requiresAugmentedDiagonal() == false)
+  h->h_posdef[0] = 1;
+  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  kb_status st;
+  {
+    StageTimer t(h, 3);
+    KB_CUDA(h, launch_schur(h->d, 0.0, h->partials.p, h->n_partials, h->posdef.p, c));
+    KB_CUDA(h, launch_schur_finalize(h->d, 0.0, h->partials.p, h->n_partials, true, c));
+    if (h->px_on) {
+      KB_CUDA(h, launch_px_reduce_system(h->d, c));
+    } else if ((st = nccl_allreduce(h, h->Sred.p, (size_t)h->d.n_aug * h->d.n_aug, kNcclFloat64, kNcclSum)) != KB_OK) {
+      return st;
+    }
+    KB_CUDA(h, launch_camera_diag(h->d, h->svd_diag.p, c));
+    if ((st = nccl_allreduce(h, h->svd_diag.p, (size_t)n, kNcclFloat64, kNcclSum)) != KB_OK) return st;
+  }
+  {
+    StageTimer t(h, 4);
+    const double norm_tol = std::sqrt((double)kb_jrows(h) * o->eps_norm);  // columnScalingMatrix: sqrt(A->nrow * eps)
+    KB_CUDA(h, launch_svd_solve(h->d, h->svd_diag.p, norm_tol, o->column_scaling ? 1 : 0, o->eps_svd, o->svd_tol, h->svd_g.p, h->eig_G.p, h->eig_V.p,
+                                h->eig_sv.p, h->eig_Vout.p, h->eig_sweeps.p, h->svd_result.p, c));
+  }
+  double res[4] = {0, 0, 0, 0};
+  int sweeps = 0;
+  KB_CUDA(h, cudaMemcpyAsync(res, h->svd_result.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(&sweeps, h->eig_sweeps.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (singular_values) KB_CUDA(h, cudaMemcpyAsync(singular_values, h->eig_sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  st = solve_finish(h, dx, gather_dx);  // synchronises
+  if (st != KB_OK) return st;
+  h->solved = true;
+  h->rho_lambda = 0.0;
+  if (!h->h_posdef[0]) return fail(h, KB_ERR_STATE, "a set pose is not constrained by its observations (pose block not positive definite)");
+  if (sweeps >= 40) return fail(h, KB_ERR_STATE, "the Jacobi iteration of the truncated-SVD solve did not converge");
+  if (out) {
+    out->n = n;
+    out->rank = (int32_t)res[0];
+    out->rank_deficiency = n - out->rank;
+    out->tolerance = res[1];
+    out->sv_gap = res[2];
+  }
   return KB_OK;
 }
 
@@ -1683,6 +1766,38 @@ kb_status kb_optimize(kb_handle* h, const kb_optimizer_options* o, kb_solution* 
     opt.verbose = o->verbose != 0;
     opt.linearSystemSolver = std::make_shared<B200SchurLinearSystemSolver>(h, true);
     opt.trustRegionPolicy = std::make_shared<LevenbergMarquardtTrustRegionPolicy>(o->lm_lambda_init);
+    Optimizer2 optimizer(opt);
+    SolutionReturnValue srv = optimizer.optimize();
+    h->trace = optimizer.trace();
+    if (out) {
+      out->j_start = srv.JStart;
+      out->j_final = srv.JFinal;
+      out->dx_final = srv.dXFinal;
+      out->dj_final = srv.dJFinal;
+      out->iterations = srv.iterations;
+      out->failed_iterations = srv.failedIterations;
+      out->linear_solver_failure = srv.linearSolverFailure ? 1 : 0;
+    }
+    return KB_OK;
+  } catch (const std::exception& e) {
+    if (h->error.empty()) h->error = e.what();
+    return KB_ERR_CUDA;
+  }
+}
+
+// Optimizer2::optimize with the Gauss-Newton policy and the estimator's linear solver: what IncrementalEstimator runs per batch
+// (IC/src/core/IncrementalEstimator.cpp:66-71, 377).  Host-driven (two synchronisations per iteration).
+kb_status kb_optimize_gauss_newton(kb_handle* h, const kb_optimizer_options* o, const kb_svd_solver_options* so, kb_solution* out) {
+  using namespace kalibr_b200::backend;
+  if (!o || !so) return fail(h, KB_ERR_INVALID_ARGUMENT, "null options");
+  try {
+    Optimizer2Options opt;
+    opt.convergenceDeltaX = o->convergence_delta_x;
+    opt.convergenceDeltaJ = o->convergence_delta_j;
+    opt.maxIterations = o->max_iterations;
+    opt.verbose = o->verbose != 0;
+    opt.linearSystemSolver = std::make_shared<B200SvdLinearSystemSolver>(h, *so);
+    opt.trustRegionPolicy = std::make_shared<GaussNewtonTrustRegionPolicy>();
     Optimizer2 optimizer(opt);
     SolutionReturnValue srv = optimizer.optimize();
     h->trace = optimizer.trace();

@@ -1618,6 +1618,67 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem
   }
 }
 
+// ---- truncated-SVD solve of the reduced system (the incremental estimator's linear solver) ----------------------------------------
+// ≙ aslam::calibration::LinearSolver::solve (IC/src/core/LinearSolver.cpp:299-463, IC = aslam_incremental_calibration/
+// incremental_calibration): the pose columns are eliminated by QR, the calibration columns are solved through the SVD of
+// Omega = A_r^T A_r - (A_r^T Q)(A_r^T Q)^T — this path's undamped Schur-reduced camera system — cut at the numerical rank.
+// diag of the camera block of H = squared column norms of the calibration columns of J
+__global__ void __launch_bounds__(256) camera_diag_kernel(DevProblem p, double* __restrict__ out) {
+  for (int i = threadIdx.x; i < p.n_c; i += blockDim.x) out[i] = p.U[(size_t)i * p.n_aug + i];
+}
+// columnScalingMatrix (IC/src/algorithms/linalg.cpp:128-152): g_i = 1 / |column i| (0 below sqrt(rows * eps)); S <- G S G, b <- G b
+__global__ void __launch_bounds__(256) svd_scale_kernel(DevProblem p, const double* __restrict__ diag_h, double norm_tol, int enable, double* __restrict__ g) {
+  const int n = p.n_c, na = p.n_aug;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double norm = sqrt(diag_h[i]);
+    g[i] = enable ? (norm < norm_tol ? 0.0 : 1.0 / norm) : 1.0;
+  }
+  __syncthreads();
+  if (!enable) return;
+  for (int idx = threadIdx.x; idx < na * na; idx += blockDim.x) {
+    const int r = idx / na, c = idx - r * na;
+    p.Sred[idx] *= (r < n ? g[r] : 1.0) * (c < n ? g[c] : 1.0);
+  }
+}
+// rankTol / estimateNumericalRank / svGap / solveSVD (linalg.cpp:244-282, 426-443) on the singular values (descending) and vectors
+// of the scaled reduced system, then the un-scaling x_r = G x_r' (LinearSolver.cpp:443-453).  result = {rank, tolerance, gap}
+__global__ void __launch_bounds__(256) svd_truncated_solve_kernel(DevProblem p, const double* __restrict__ sv, const double* __restrict__ V,
+                                                                  const double* __restrict__ g, double eps_svd, double svd_tol,
+                                                                  double* __restrict__ result) {
+  __shared__ double s_coef[256];
+  __shared__ int s_rank;
+  const int n = p.n_c, na = p.n_aug;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double tol = svd_tol != -1.0 ? svd_tol : sv[0] * eps_svd * (double)n;
+  if (tid == 0) {
+    int rank = n;
+    for (int i = n - 1; i > 0; --i) {
+      if (sv[i] > tol) break;
+      --rank;
+    }
+    s_rank = rank;
+    result[0] = (double)rank;
+    result[1] = tol;
+    result[2] = rank < n ? sv[rank - 1] / sv[rank] : __longlong_as_double(0x7ff0000000000000ll);
+  }
+  __syncthreads();
+  const int rank = s_rank;
+  const double* b = p.Sred + (size_t)n * na;  // right-hand side: last row of the augmented system
+  for (int k = warp; k < n; k += 8) {
+    double d = 0.0;
+    if (k < rank)
+      for (int r = lane; r < n; r += 32) d += V[(size_t)r * n + k] * b[r];
+    d = warp_sum(d);
+    if (lane == 0) s_coef[k] = k < rank ? d / sv[k] : 0.0;
+  }
+  __syncthreads();
+  for (int r = tid; r < n; r += blockDim.x) {
+    double x = 0.0;
+    for (int k = 0; k < rank; ++k) x += V[(size_t)r * n + k] * s_coef[k];
+    p.dxc[r] = g[r] * x;
+  }
+}
+
 // =========================================================================================================
 // back substitution for the poses + scatter of dx into design-variable order
 // =========================================================================================================
@@ -2238,6 +2299,21 @@ cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx&
 }
 cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, double* sv_out, double* V_out, int* sweeps_out, StreamCtx& s) {
   marginal_eig_kernel<<<1, EIG_THREADS, 0, s.stream>>>(p, G, V, sv_out, V_out, sweeps_out);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+cudaError_t launch_camera_diag(const DevProblem& p, double* out, StreamCtx& s) {
+  camera_diag_kernel<<<1, 256, 0, s.stream>>>(p, out);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+cudaError_t launch_svd_solve(const DevProblem& p, const double* diag_h, double norm_tol, int column_scaling, double eps_svd, double svd_tol, double* g,
+                             double* G, double* V, double* sv, double* V_out, int* sweeps, double* result, StreamCtx& s) {
+  svd_scale_kernel<<<1, 256, 0, s.stream>>>(p, diag_h, norm_tol, column_scaling, g);
+  KB_LAUNCHED(s);
+  marginal_eig_kernel<<<1, EIG_THREADS, 0, s.stream>>>(p, G, V, sv, V_out, sweeps);
+  KB_LAUNCHED(s);
+  svd_truncated_solve_kernel<<<1, 256, 0, s.stream>>>(p, sv, V_out, g, eps_svd, svd_tol, result);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }

@@ -67,6 +67,12 @@ class KbOptimizerOptions(C.Structure):
         """kalibr2::tools::CreateDefaultOptimizer (CalibrationTools.hpp:57-66)."""
         return cls(1e-3, 1.0, 200, 10.0, verbose, device_loop)
 
+    @classmethod
+    def estimator_default(cls, verbose: int = 0) -> "KbOptimizerOptions":
+        """Optimizer2Options defaults (BE/include/aslam/backend/Optimizer2Options.hpp: deltas 1e-3) with kalibr2_ros' maxIterations = 20
+        (CalibrateCameras.cpp:269-272): what IncrementalEstimator's optimiser runs with."""
+        return cls(1e-3, 1e-3, 20, 0.0, verbose, 0)
+
 
 class KbMarginalOptions(C.Structure):
     _fields_ = [("eps_svd", C.c_double), ("svd_tol", C.c_double)]
@@ -226,3 +232,21 @@ class Problem:
         dims = np.asarray(dims, np.int32)
         col = np.concatenate([[0], np.cumsum(dims)[:-1]]).astype(np.int32)
         return col, dims, labels
+
+
+class KbSvdSolverOptions(C.Structure):  # kb_svd_solver_options
+    _fields_ = [("column_scaling", C.c_int32), ("eps_norm", C.c_double), ("eps_svd", C.c_double), ("svd_tol", C.c_double)]
+
+    @classmethod
+    def default(cls):
+        eps = float(np.finfo(float).eps)
+        return cls(0, eps, eps, -1.0)
+
+    @classmethod
+    def kalibr2(cls):
+        """kalibr2_ros CalibrateCameras.cpp:264-267: column scaling on, epsSVD = 1e-6."""
+        return cls(1, float(np.finfo(float).eps), 1e-6, -1.0)
+
+
+class KbSvdSolveResult(C.Structure):  # kb_svd_solve_result
+    _fields_ = [("n", C.c_int32), ("rank", C.c_int32), ("rank_deficiency", C.c_int32), ("tolerance", C.c_double), ("sv_gap", C.c_double)]

@@ -709,6 +709,11 @@ __attribute__((visibility("default"))) void ko_get_rhs(ko_problem* h, double* rh
 }
 __attribute__((visibility("default"))) double ko_apply_state_update(ko_problem* h) { return h->P->applyStateUpdate(); }
 __attribute__((visibility("default"))) void ko_revert_last_state_update(ko_problem* h) { h->P->revertLastStateUpdate(); }
+// Optimizer2::applyStateUpdate with a step computed outside (the estimator's linear solver restated in oracle/ko_estimator.py)
+__attribute__((visibility("default"))) double ko_apply_dx(ko_problem* h, const double* dx) {
+  h->P->dx.assign(dx, dx + h->P->solver->JCols);
+  return h->P->applyStateUpdate();
+}
 __attribute__((visibility("default"))) void ko_optimize(ko_problem* h, const kb_optimizer_options* o, int nThreads, kb_solution* out) {
   h->trace.clear();
   optimize(*h->P, *o, nThreads, out, &h->trace);

@@ -1,0 +1,118 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY (never imported by kalibr_b200/).
+
+CPU restatement (numpy, dense) of the incremental estimator's numerical core (IC = aslam_incremental_calibration/
+incremental_calibration):
+
+  aslam::calibration::LinearSolver::solve            IC/src/core/LinearSolver.cpp:299-463
+  columnScalingMatrix, rankTol, estimateNumericalRank, svGap, solveSVD   IC/src/algorithms/linalg.cpp:128-152, 244-282, 426-443
+  Optimizer2::optimize with GaussNewtonTrustRegionPolicy   BE/src/Optimizer2.cpp:183-273, BE/src/GaussNewtonTrustRegionPolicy.cpp:18-40
+  IncrementalEstimator::addBatch (accept / reject)   IC/src/core/IncrementalEstimator.cpp:338-540
+
+Third-party arithmetic: the reference factorises the pose columns with SuiteSparseQR (libsuitesparse-dev, unpinned) and takes the
+SVD of the reduced matrix with Eigen; both are replaced by numpy's dense QR / SVD, which compute the same mathematical objects
+(the orthogonal complement of the pose columns, the singular triplets of Omega).  PARITY UNPINNED for this part: the reference
+stores no expected values for it; it is pinned through properties (tests/test_estimator_cpu.py): the truncated solve equals the
+plain least-squares solution when the system has full rank, and the minimum-norm solution on the observable subspace when not.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+EPS = float(np.finfo(float).eps)
+
+
+def dense_from_ccs(col_ptr, row_idx, vals, n_cols):
+    J = np.zeros((col_ptr.size - 1, n_cols))
+    for r in range(col_ptr.size - 1):
+        J[r, row_idx[col_ptr[r]:col_ptr[r + 1]]] = vals[col_ptr[r]:col_ptr[r + 1]]
+    return J
+
+
+def calibration_columns(problem):
+    """Columns of the calibration group (intrinsics + baselines: what IncrementalEstimator marginalises onto) and of the rest."""
+    col, dims, labels = problem.dv_layout()
+    cal = [c + i for c, d, l in zip(col, dims, labels) if l[0] in ("proj", "dist", "baseline_q", "baseline_t") for i in range(d)]
+    rest = [c + i for c, d, l in zip(col, dims, labels) if l[0] in ("set_q", "set_t") for i in range(d)]
+    return np.array(cal, int), np.array(rest, int)
+
+
+def column_scaling(A, eps):
+    """columnScalingMatrix: 1 / column norm, 0 for columns below sqrt(rows * eps)."""
+    norm = np.sqrt((A * A).sum(0))
+    tol = np.sqrt(A.shape[0] * eps)
+    with np.errstate(divide="ignore"):
+        return np.where(norm < tol, 0.0, 1.0 / norm)
+
+
+def linear_solver_solve(J, b, cal, rest, column_scaling_on=False, eps_norm=EPS, eps_svd=EPS, svd_tol=-1.0):
+    """LinearSolver::solve: x minimising |J x - b| with the calibration block cut at the numerical rank of Omega.
+    Returns (x, info) with info = dict(rank, tolerance, sv_gap, singular_values)."""
+    A_l, A_r = J[:, rest].copy(), J[:, cal].copy()
+    G_l = column_scaling(A_l, eps_norm) if column_scaling_on else np.ones(A_l.shape[1])
+    G_r = column_scaling(A_r, eps_norm) if column_scaling_on else np.ones(A_r.shape[1])
+    A_l *= G_l
+    A_r *= G_r
+    Q, R = np.linalg.qr(A_l)  # thin QR of the pose columns (full column rank: every pose is observed)
+    ArtQ = A_r.T @ Q
+    Omega = A_r.T @ A_r - ArtQ @ ArtQ.T
+    U, sv, Vt = np.linalg.svd(Omega)
+    tol = svd_tol if svd_tol != -1.0 else sv[0] * eps_svd * len(sv)
+    rank = len(sv)
+    for i in range(len(sv) - 1, 0, -1):
+        if sv[i] > tol:
+            break
+        rank -= 1
+    b_r = A_r.T @ b - ArtQ @ (Q.T @ b)
+    x_r = Vt[:rank].T @ ((U[:, :rank].T @ b_r) / sv[:rank])
+    x_l = np.linalg.solve(R, Q.T @ (b - A_r @ x_r))
+    x = np.zeros(J.shape[1])
+    x[rest] = G_l * x_l
+    x[cal] = G_r * x_r
+    with np.errstate(divide="ignore"):
+        gap = sv[rank - 1] / sv[rank] if rank < len(sv) else np.inf
+    return x, dict(rank=rank, tolerance=tol, sv_gap=gap, singular_values=sv)
+
+
+def system_of(o, problem):
+    """(J, b) of the oracle problem at its current state: J dx ~ b with b = -(weighted error), as LinearSolver::solveSystem hands them over."""
+    o.evaluate_error()
+    J = dense_from_ccs(*o.jacobian_ccs(), o.jcols)
+    return J, o.error_vector().copy()
+
+
+def gauss_newton_optimize(o, problem, solver_kw, max_iterations=20, conv_dx=1e-3, conv_dj=1e-3):
+    """Optimizer2::optimize with the Gauss-Newton policy (build + solve every iteration, never revert) and the estimator's solver.
+    Returns dict(j_start, j_final, iterations, dx_final, dj_final, trace)."""
+    cal, rest = calibration_columns(problem)
+    J_cost = o.evaluate_error()
+    p_J = J_cost
+    out = dict(j_start=J_cost, iterations=0, trace=[])
+    delta_x, delta_j = conv_dx + 1.0, conv_dj + 1.0
+    while out["iterations"] < max_iterations and delta_x > conv_dx and abs(delta_j) > conv_dj:
+        J, b = system_of(o, problem)
+        dx, _ = linear_solver_solve(J, b, cal, rest, **solver_kw)
+        delta_x = o.apply_dx(dx)
+        J_cost = o.evaluate_error()
+        delta_j = p_J - J_cost
+        p_J = J_cost
+        out["iterations"] += 1
+        out["trace"].append((J_cost, delta_x))
+    out.update(j_final=p_J, dx_final=delta_x, dj_final=delta_j)
+    return out
+
+
+def analyze_marginal(o, problem, eps_svd=EPS, svd_tol=-1.0):
+    """LinearSolver::analyzeMarginal on the UNSCALED system (LinearSolver.cpp:466-528): singular values of Omega, rank, log2 sum."""
+    cal, rest = calibration_columns(problem)
+    J, _ = system_of(o, problem)
+    Q, _ = np.linalg.qr(J[:, rest])
+    A_r = J[:, cal]
+    ArtQ = A_r.T @ Q
+    sv = np.linalg.svd(A_r.T @ A_r - ArtQ @ ArtQ.T, compute_uv=False)
+    tol = svd_tol if svd_tol != -1.0 else sv[0] * eps_svd * len(sv)
+    rank = len(sv)
+    for i in range(len(sv) - 1, 0, -1):
+        if sv[i] > tol:
+            break
+        rank -= 1
+    return dict(rank=rank, tolerance=tol, singular_values=sv, sv_log2_sum=float(np.log2(sv[:rank]).sum()))

@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
         L.ko_apply_state_update.restype = C.c_double
         L.ko_apply_state_update.argtypes = [C.c_void_p]
         L.ko_revert_last_state_update.argtypes = [C.c_void_p]
+        L.ko_apply_dx.restype = C.c_double
+        L.ko_apply_dx.argtypes = [C.c_void_p, C.c_void_p]
         L.ko_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ko_get_trace.restype = C.c_int32
         L.ko_get_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
@@ -153,6 +155,12 @@ class OracleProblem:
 
     def apply_state_update(self) -> float:
         return lib().ko_apply_state_update(self._h)
+
+    def apply_dx(self, dx) -> float:
+        """applyStateUpdate with a step computed by the caller; returns max|dx|."""
+        dx = np.ascontiguousarray(dx, np.float64)
+        assert dx.size == self.jcols
+        return lib().ko_apply_dx(self._h, _p(dx))
 
     def revert_last_state_update(self):
         lib().ko_revert_last_state_update(self._h)
