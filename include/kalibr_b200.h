@@ -274,6 +274,10 @@ KB_API kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* 
 /* One Optimizer2::optimize() with GaussNewtonTrustRegionPolicy (BE/src/GaussNewtonTrustRegionPolicy.cpp:18-40: rebuild and solve
  * every iteration, no conditioner, never revert) over kb_solve_system_svd — the optimisation IncrementalEstimator::addBatch runs
  * (IC/src/core/IncrementalEstimator.cpp:66-71, 377; kalibr2_ros: max_iterations = 20, both convergence deltas 1e-3). */
+/* rank / tolerance / gap of the most recent kb_solve_system_svd on this handle (rank = -1 before the first one): what
+ * LinearSolver::getSVDRank() keeps returning after analyzeMarginal(), which only recomputes them when no solve has run
+ * (LinearSolver.cpp:517-523) */
+KB_API kb_status kb_get_last_svd_solve(const kb_handle* h, kb_svd_solve_result* out);
 KB_API kb_status kb_optimize_gauss_newton(kb_handle* h, const kb_optimizer_options* o, const kb_svd_solver_options* so, kb_solution* out);
 
 /* ---- marginal analysis of the calibration block --------------------------------
@@ -302,6 +306,11 @@ KB_API void kb_default_marginal_options(kb_marginal_options* o);
  * getNullSpace = its first rank / remaining columns); columns (may be NULL): [n] design-variable column of each row of V */
 KB_API kb_status kb_analyze_marginal(kb_handle* h, const kb_marginal_options* o, kb_marginal_result* out, double* singular_values,
                                      double* V, int32_t* columns);
+/* The same analysis on the system of the LAST kb_build_system instead of a fresh linearisation: IncrementalEstimator::addBatch calls
+ * analyzeMarginal() after optimize(), i.e. on the Jacobian of the last Gauss-Newton iteration, one update behind the final state
+ * (IC/src/core/IncrementalEstimator.cpp:377, 404; LinearSolver.cpp:530-537). */
+KB_API kb_status kb_analyze_marginal_last_build(kb_handle* h, const kb_marginal_options* o, kb_marginal_result* out, double* singular_values,
+                                                double* V, int32_t* columns);
 
 /* ---- read-back (parity / results) ----------------------------------------- */
 KB_API kb_status kb_get_error_vector(kb_handle* h, double* e /*[2*local terms]*/);      /* ≙ LinearSystemSolver::e() : -sqrtInvR^T e */

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
     "kb_set_inv_r", "kb_get_sqrt_inv_r", "kb_set_m_estimator", "kb_m_estimator_parameter", "kb_reprojection_statistics",
-    "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics", "kb_default_svd_solver_options", "kb_solve_system_svd", "kb_optimize_gauss_newton",
+    "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics", "kb_default_svd_solver_options", "kb_solve_system_svd", "kb_optimize_gauss_newton", "kb_analyze_marginal_last_build", "kb_get_last_svd_solve",
 ]
 
 MEST_NONE, MEST_HUBER, MEST_CAUCHY, MEST_GEMAN_MCCLURE, MEST_BLAKE_ZISSERMAN = range(5)  # = kb_m_estimator
@@ -116,6 +116,8 @@ def load_library() -> C.CDLL:
     L.kb_default_svd_solver_options.restype = None
     L.kb_solve_system_svd.argtypes = [vp, vp, vp, C.c_int32, vp, vp]
     L.kb_optimize_gauss_newton.argtypes = [vp, vp, vp, vp]
+    L.kb_analyze_marginal_last_build.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.kb_get_last_svd_solve.argtypes = [vp, vp]
     L.kb_initialize_intrinsics.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_double, vp, C.POINTER(C.c_int32)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
@@ -387,16 +389,25 @@ class B200SchurLinearSystemSolver:
     def commit_observations(self):
         self._check(self._L.kb_commit_observations(self._h), "kb_commit_observations")
 
-    def analyze_marginal(self, options=None):
-        """≙ LinearSolver::analyzeMarginal: (KbMarginalResult, singular values, V, DV column of each row of V)."""
+    def analyze_marginal(self, options=None, last_build: bool = False):
+        """≙ LinearSolver::analyzeMarginal: (KbMarginalResult, singular values, V, DV column of each row of V).
+        last_build: analyse the system of the last build_system (what addBatch sees after optimize()) instead of re-linearising."""
         from .problem import KbMarginalOptions, KbMarginalResult
 
         o = options or KbMarginalOptions.default()
         n = self.problem.n_c
         res = KbMarginalResult()
         sv, V, cols = np.zeros(n), np.zeros((n, n)), np.zeros(n, np.int32)
-        self._check(self._L.kb_analyze_marginal(self._h, C.byref(o), C.byref(res), _p(sv), _p(V), _p(cols)), "kb_analyze_marginal")
+        fn = self._L.kb_analyze_marginal_last_build if last_build else self._L.kb_analyze_marginal
+        self._check(fn(self._h, C.byref(o), C.byref(res), _p(sv), _p(V), _p(cols)), "kb_analyze_marginal")
         return res, sv, V, cols
+
+    def last_svd_solve(self):
+        from .problem import KbSvdSolveResult
+
+        res = KbSvdSolveResult()
+        self._check(self._L.kb_get_last_svd_solve(self._h, C.byref(res)), "kb_get_last_svd_solve")
+        return res
 
     def peer_exchange_handle(self) -> bytes:
         """64-byte CUDA IPC handle of this rank's exchange buffer (all-gather them, then attach_peers on every rank)."""

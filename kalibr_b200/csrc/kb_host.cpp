@@ -157,6 +157,7 @@ struct kb_handle {
   DevBuf<double> pnp_T;               // initial-guess stage: T_target_camera per view
   DevBuf<int> pnp_ok, pnp_res, pnp_set_ok;
   DevBuf<unsigned char> pnp_mask;
+  kb_svd_solve_result last_svd = {0, -1, -1, 0.0, 0.0};  // of the last kb_solve_system_svd (rank -1: none yet)
   DevBuf<double> svd_diag, svd_g, svd_result;  // truncated-SVD solve: diag of the camera block, column scales, {rank, tol, gap}
   DevBuf<double> init_scratch, init_out;  // initializeIntrinsics: candidates / guesses, results
   std::vector<double> trace;
@@ -1214,8 +1215,10 @@ void kb_default_marginal_options(kb_marginal_options* o) {
   o->svd_tol = -1.0;
 }
 
-kb_status kb_analyze_marginal(kb_handle* h, const kb_marginal_options* o, kb_marginal_result* out, double* singular_values, double* V, int32_t* columns) {
+static kb_status analyze_marginal_impl(kb_handle* h, const kb_marginal_options* o, kb_marginal_result* out, double* singular_values, double* V,
+                                       int32_t* columns, bool rebuild) {
   if (!o || !out || !singular_values) return fail(h, KB_ERR_INVALID_ARGUMENT, "null argument");
+  if (!rebuild && !h->built) return fail(h, KB_ERR_STATE, "kb_analyze_marginal_last_build called before any kb_build_system");
   KB_CUDA(h, cudaSetDevice(h->device));
   StreamCtx c = ctx(h);
   const int n = h->d.n_c;
@@ -1227,8 +1230,8 @@ kb_status kb_analyze_marginal(kb_handle* h, const kb_marginal_options* o, kb_mar
     KB_CUDA(h, h->eig_Vout.alloc((size_t)n * n));
     KB_CUDA(h, h->eig_sweeps.alloc(1));
   }
-  // the undamped normal equations at the current state, set poses eliminated: exactly the analyzeMarginal matrix
-  kb_status st = kb_build_system(h, 1);
+  // the undamped normal equations at the current state (or of the last build), set poses eliminated: exactly the analyzeMarginal matrix
+  kb_status st = rebuild ? kb_build_system(h, 1) : KB_OK;
   if (st != KB_OK) return st;
   h->h_posdef[0] = 1;
   KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1417,6 +1420,19 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
   return KB_OK;
 }
 
+kb_status kb_analyze_marginal(kb_handle* h, const kb_marginal_options* o, kb_marginal_result* out, double* singular_values, double* V, int32_t* columns) {
+  return analyze_marginal_impl(h, o, out, singular_values, V, columns, true);
+}
+kb_status kb_analyze_marginal_last_build(kb_handle* h, const kb_marginal_options* o, kb_marginal_result* out, double* singular_values, double* V,
+                                         int32_t* columns) {
+  return analyze_marginal_impl(h, o, out, singular_values, V, columns, false);
+}
+kb_status kb_get_last_svd_solve(const kb_handle* h, kb_svd_solve_result* out) {
+  if (!out) return KB_ERR_INVALID_ARGUMENT;
+  *out = h->last_svd;
+  return KB_OK;
+}
+
 // ---- the incremental estimator's linear solver: undamped, calibration block through a truncated SVD ---------------------------
 void kb_default_svd_solver_options(kb_svd_solver_options* o) {  // IC/src/core/LinearSolverOptions.cpp:30-38
   o->column_scaling = 0;
@@ -1478,13 +1494,12 @@ kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, doub
   h->rho_lambda = 0.0;
   if (!h->h_posdef[0]) return fail(h, KB_ERR_STATE, "a set pose is not constrained by its observations (pose block not positive definite)");
   if (sweeps >= 40) return fail(h, KB_ERR_STATE, "the Jacobi iteration of the truncated-SVD solve did not converge");
-  if (out) {
-    out->n = n;
-    out->rank = (int32_t)res[0];
-    out->rank_deficiency = n - out->rank;
-    out->tolerance = res[1];
-    out->sv_gap = res[2];
-  }
+  h->last_svd.n = n;
+  h->last_svd.rank = (int32_t)res[0];
+  h->last_svd.rank_deficiency = n - h->last_svd.rank;
+  h->last_svd.tolerance = res[1];
+  h->last_svd.sv_gap = res[2];
+  if (out) *out = h->last_svd;
   return KB_OK;
 }
 

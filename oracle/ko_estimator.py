@@ -90,7 +90,10 @@ def gauss_newton_optimize(o, problem, solver_kw, max_iterations=20, conv_dx=1e-3
     delta_x, delta_j = conv_dx + 1.0, conv_dj + 1.0
     while out["iterations"] < max_iterations and delta_x > conv_dx and abs(delta_j) > conv_dj:
         J, b = system_of(o, problem)
-        dx, _ = linear_solver_solve(J, b, cal, rest, **solver_kw)
+        dx, info = linear_solver_solve(J, b, cal, rest, **solver_kw)
+        out["last_jacobian"], out["last_solve"] = J, info  # what analyzeMarginal() and getSVDRank() see after optimize()
+        ratio = info["singular_values"] / info["tolerance"]
+        out["rank_margin"] = min(out.get("rank_margin", np.inf), float(np.abs(np.log(ratio[ratio > 0])).min()))  # distance of the closest singular value to the cut
         delta_x = o.apply_dx(dx)
         J_cost = o.evaluate_error()
         delta_j = p_J - J_cost
@@ -116,3 +119,65 @@ def analyze_marginal(o, problem, eps_svd=EPS, svd_tol=-1.0):
             break
         rank -= 1
     return dict(rank=rank, tolerance=tol, singular_values=sv, sv_log2_sum=float(np.log2(sv[:rank]).sum()))
+
+
+def marginal_singular_values(J, cal, rest):
+    """Singular values of Omega for the UNSCALED Jacobian J (LinearSolver::analyzeMarginal, LinearSolver.cpp:466-516)."""
+    Q, _ = np.linalg.qr(J[:, rest])
+    A_r = J[:, cal]
+    ArtQ = A_r.T @ Q
+    return np.linalg.svd(A_r.T @ A_r - ArtQ @ ArtQ.T, compute_uv=False)
+
+
+class OracleIncrementalEstimator:
+    """IncrementalEstimator::addBatch (IC/src/core/IncrementalEstimator.cpp:338-540) on flattened batches: a batch is one synced set
+    {camera: (corner_id, y_u, y_v)} with a target-pose guess.  Quirks kept: analyzeMarginal() runs on the Jacobian of the LAST
+    Gauss-Newton iteration (one update behind the final state) and, because a solve has run, keeps that solve's rank — the rank of the
+    SCALED system — for the log2 sum over the UNSCALED singular values (LinearSolver.cpp:517-523, 196-200)."""
+
+    def __init__(self, oracle_api, cam_model, cam_params, baselines, target_points, info_gain_delta=0.2, check_validity=False,
+                 solver_kw=None, max_iterations=20):
+        self.oa = oracle_api
+        self.cam_model = np.asarray(cam_model, np.int32)
+        self.cam_params = np.array(cam_params, float)
+        self.baselines = np.array(baselines, float).reshape(-1, 7)
+        self.target_points = np.asarray(target_points, float)
+        self.info_gain_delta, self.check_validity, self.max_iterations = info_gain_delta, check_validity, max_iterations
+        self.solver_kw = solver_kw or dict(column_scaling_on=True, eps_svd=1e-6)
+        self.batches, self.poses = [], []
+        self.sv_log2_sum, self.rank_theta, self.information_gain = 0.0, -1, 0.0
+
+    def _problem(self, batches, poses):
+        from kalibr_b200.problem import ORDER_RIG, Problem
+
+        vs, vc, vb, cid, yu, yv = [], [], [0], [], [], []
+        for s, b in enumerate(batches):
+            for k in sorted(b):
+                c, u, v = b[k]
+                vs.append(s); vc.append(k)
+                cid.extend(c); yu.extend(u); yv.extend(v)
+                vb.append(len(cid))
+        return Problem(ORDER_RIG, self.cam_model, self.cam_params, self.baselines, np.array(poses, float).reshape(-1, 7), self.target_points,
+                       np.array(vs, np.int32), np.array(vc, np.int32), np.array(vb, np.int64), np.array(yu, float), np.array(yv, float),
+                       np.array(cid, np.int32))
+
+    def add_batch(self, batch, pose_guess, force=False):
+        p = self._problem(self.batches + [batch], self.poses + [np.asarray(pose_guess, float)])
+        o = self.oa.OracleProblem(p)
+        r = gauss_newton_optimize(o, p, self.solver_kw, max_iterations=self.max_iterations)
+        cal, rest = calibration_columns(p)
+        sv = marginal_singular_values(r["last_jacobian"], cal, rest)
+        rank = r["last_solve"]["rank"]
+        sv_log2_sum = float(np.log2(sv[:rank]).sum())
+        gain = 0.5 * (sv_log2_sum - self.sv_log2_sum)
+        valid = not (self.check_validity and (r["iterations"] == self.max_iterations or r["j_final"] >= r["j_start"]))
+        keep = ((gain > self.info_gain_delta or rank > self.rank_theta) and valid) or force
+        ret = dict(batch_accepted=bool(keep), information_gain=gain, rank_theta=rank, rank_theta_deficiency=len(sv) - rank,
+                   svd_tolerance=r["last_solve"]["tolerance"], singular_values=sv, rank_margin=r["rank_margin"], num_iterations=r["iterations"], j_start=r["j_start"],
+                   j_final=r["j_final"])
+        if keep:
+            self.information_gain, self.sv_log2_sum, self.rank_theta = gain, sv_log2_sum, rank
+            self.cam_params, self.baselines = o.camera_params(), o.baselines()
+            self.batches.append(batch)
+            self.poses = list(o.set_poses())
+        return ret

@@ -1,11 +1,12 @@
 // Test driver for include/kalibr_b200/calibration_tools.hpp: reads a flattened set of observations written by
 // tests/test_drivers_gpu.py, runs one of the three kalibr2 drivers on the device and prints the results as "key value..." lines.
 //   driver_main <single|stereo|rig> <problem.bin>
+//   driver_main estimator <problem.bin> <infoGainDelta>     every synced set offered to the incremental estimator, in order
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 
-#include "kalibr_b200/calibration_tools.hpp"
+#include "kalibr_b200/incremental_estimator.hpp"
 
 using namespace kalibr_b200::tools;
 
@@ -44,6 +45,7 @@ int main(int argc, char** argv) {
   auto corner = readArray<int32_t>(f);
   auto yu = readArray<double>(f);
   auto yv = readArray<double>(f);
+  auto set_poses = readArray<double>(f);
   const int n_cams = dims[0], n_sets = dims[1];
   Target target;
   target.rows = dims[2];
@@ -87,6 +89,27 @@ int main(int argc, char** argv) {
       }
       auto out = CalibrateMultiCameraRig(cams, synced, target, guesses, &sol);
       for (size_t j = 0; j < out.size(); ++j) printPose(("baseline" + std::to_string(j)).c_str(), out[j]);
+    } else if (mode == "estimator") {
+      std::vector<Transformation> guesses((size_t)n_cams - 1);
+      for (int j = 0; j + 1 < n_cams; ++j) {
+        std::memcpy(guesses[j].q, &baselines[(size_t)j * 7], sizeof(guesses[j].q));
+        std::memcpy(guesses[j].t, &baselines[(size_t)j * 7 + 4], sizeof(guesses[j].t));
+      }
+      kalibr_b200::calibration::IncrementalEstimator::Options eo;
+      eo.infoGainDelta = argc > 3 ? std::atof(argv[3]) : 0.2;
+      eo.checkValidity = true;  // CalibrateCameras.cpp:261
+      kalibr_b200::calibration::IncrementalEstimator estimator(cams, guesses, target, eo);
+      for (int s = 0; s < n_sets; ++s) {
+        Transformation T;
+        std::memcpy(T.q, &set_poses[(size_t)s * 7], sizeof(T.q));
+        std::memcpy(T.t, &set_poses[(size_t)s * 7 + 4], sizeof(T.t));
+        auto r = estimator.addBatch(synced[(size_t)s], T);
+        std::printf("batch%d %d %.17g %td %zu %.17g %.17g\n", s, r.batchAccepted ? 1 : 0, r.informationGain, r.rankTheta, r.numIterations, r.JStart, r.JFinal);
+      }
+      std::printf("accepted %zu\n", estimator.getNumBatches());
+      for (size_t j = 0; j < estimator.baselines().size(); ++j) printPose(("baseline" + std::to_string(j)).c_str(), estimator.baselines()[j]);
+      for (int k = 0; k < n_cams; ++k) printCamera(("camera" + std::to_string(k)).c_str(), estimator.cameras()[(size_t)k]);
+      return 0;
     } else {
       return 2;
     }

@@ -11,8 +11,8 @@ BIN = os.path.join(ROOT, "tests", "cpp", "driver_main")
 def build_driver():
     src = os.path.join(ROOT, "tests", "cpp", "driver_main.cpp")
     lib_dir = os.path.join(ROOT, "kalibr_b200")
-    hdr = os.path.join(ROOT, "include", "kalibr_b200", "calibration_tools.hpp")
-    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "include", "kalibr_b200", h) for h in ("calibration_tools.hpp", "incremental_estimator.hpp")] + [os.path.join(ROOT, "include", "kalibr_b200.h")]
+    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-L", lib_dir,
                         "-lkalibr_b200", f"-Wl,-rpath,{lib_dir}", "-o", BIN], check=True)
     return BIN
@@ -37,10 +37,11 @@ def write_problem(path, p, resolution, rows=10, cols=12):
         arr(f, p.corner_id, np.int32)
         arr(f, p.y_u, np.float64)
         arr(f, p.y_v, np.float64)
+        arr(f, p.set_poses, np.float64)
 
 
-def run_driver(mode, path):
-    r = subprocess.run([build_driver(), mode, path], capture_output=True, text=True)
+def run_driver(mode, path, *extra):
+    r = subprocess.run([build_driver(), mode, path, *[str(e) for e in extra]], capture_output=True, text=True)
     out = {}
     for line in r.stdout.splitlines():
         k, *v = line.split(" ")

@@ -124,3 +124,42 @@ def test_calibrate_multi_camera_rig(capi, oracle_lib, tmp_path):
     cams = np.stack([out[f"camera{k}"] for k in range(p.n_cams)])
     base = np.stack([out[f"baseline{j}"] for j in range(p.n_cams - 1)])
     check_against_oracle(oracle_lib, start, out["solution"], cams, base)
+
+
+@pytest.mark.parametrize("cfg,n_sets,delta", [(2, 10, 0.2), (2, 12, 2.5), (3, 8, 1.0)])
+def test_incremental_estimator_matches_oracle(oracle_lib, tmp_path, cfg, n_sets, delta):
+    """IncrementalEstimator::addBatch over a sequence of synced sets (kalibr2_ros CalibrateCameras.cpp:279-304): the same accept /
+    reject decisions, information gains, ranks, iteration counts and costs as the dense numpy restatement, and the same calibration."""
+    from oracle import ko_estimator as ke
+
+    p = synthetic.make_config(cfg, n_sets=n_sets)
+    res = [synthetic.TRUTH_PARAMS[m][1] for m in p.cam_model]
+    path = str(tmp_path / "estimator.bin")
+    write_problem(path, p, res)
+    code, out = run_driver("estimator", path, delta)
+    assert code == 0, out
+    est = ke.OracleIncrementalEstimator(oracle_lib, p.cam_model, p.cam_params, p.baselines, p.target_points, info_gain_delta=delta, check_validity=True)
+    decisions = []
+    for s in range(p.n_sets):
+        batch = {}
+        for w in np.flatnonzero(p.view_set == s):
+            b, e = p.view_begin[w], p.view_begin[w + 1]
+            batch[int(p.view_cam[w])] = (p.corner_id[b:e], p.y_u[b:e], p.y_v[b:e])
+        r = est.add_batch(batch, p.set_poses[s])
+        acc, gain, rank, iters, j0, j1 = out[f"batch{s}"]
+        if r["rank_margin"] < 1e-3:
+            pytest.skip("a singular value sits at the rank tolerance: the truncation may legitimately differ by rounding")
+        if abs(r["information_gain"] - delta) < 1e-3:
+            pytest.skip("an information gain sits at the acceptance threshold")
+        assert bool(acc) == r["batch_accepted"], (s, out[f"batch{s}"], r)
+        assert int(rank) == r["rank_theta"] and int(iters) == r["num_iterations"]
+        assert abs(gain - r["information_gain"]) <= 1e-6 * max(1.0, abs(r["information_gain"]))
+        assert abs(j1 - r["j_final"]) <= 1e-9 * r["j_final"] and abs(j0 - r["j_start"]) <= 1e-9 * r["j_start"]
+        decisions.append(bool(acc))
+    assert int(out["accepted"][0]) == len(est.batches) == sum(decisions)
+    if delta > 1.0:
+        assert not all(decisions)  # the threshold really rejects something in this sequence
+    cams = np.stack([out[f"camera{k}"] for k in range(p.n_cams)])
+    assert (np.abs(cams - est.cam_params) / np.maximum(np.abs(est.cam_params), 1e-3)).max() < 1e-6
+    base = np.stack([out[f"baseline{j}"] for j in range(p.n_cams - 1)])
+    assert np.abs(base - est.baselines).max() < 1e-6
