@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -278,6 +279,19 @@ std::vector<int> camside_dvs(const kb_handle* h, int k) {
 
 }  // namespace
 
+namespace {
+struct CreateTrace {  // KB_CREATE_TRACE=1: wall-clock checkpoints of kb_create / kb_destroy on stderr
+  bool on = getenv("KB_CREATE_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on) return;
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[kb trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t0).count());
+    t0 = t;
+  }
+};
+}  // namespace
+
 // =========================================================================================================
 extern "C" {
 
@@ -295,6 +309,7 @@ kb_status kb_nccl_unique_id(char out[128]) {
 
 void kb_destroy(kb_handle* h) {
   if (!h) return;
+  CreateTrace trace;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) g_nccl.CommDestroy(h->comm);
@@ -313,10 +328,13 @@ void kb_destroy(kb_handle* h) {
   for (auto& q : h->px_opened) if (q) cudaIpcCloseMemHandle(q);
   if (h->lm_graph) cudaGraphExecDestroy(h->lm_graph);
   if (h->stream) cudaStreamDestroy(h->stream);
+  trace.mark("destroy: streams, events");
   delete h;
+  trace.mark("destroy: device buffers");
 }
 
 kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
+  CreateTrace trace;
   if (!d || !out) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "null argument");
   *out = nullptr;
   if (d->n_cams < 1 || d->n_cams > MAX_CAMS) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "n_cams out of range (1..32)");
@@ -370,6 +388,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(cudaMallocHost((void**)&h->h_ctrl, sizeof(LmCtrl)));
   for (auto& e : h->ev) KB_CCUDA(cudaEventCreate(&e));
 
+  trace.mark("device, streams, events");
   // ---- local views / terms ----
   const int n_local_sets = h->set_hi - h->set_lo;
   std::vector<double> yu, yv;
@@ -560,6 +579,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     }
   }
 
+  trace.mark("host tables");
   // ---- upload ----
   cudaStream_t s = h->stream;
   std::vector<double> target(d->target_points, d->target_points + (size_t)3 * d->n_target_points);
@@ -617,6 +637,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->bk_base.upload(base, s));
   KB_CCUDA(h->bk_sets.upload(sets, s));
   const size_t C = d->n_cams, S = n_local_sets, NA = D.n_aug;
+  trace.mark("uploads");
   KB_CCUDA(h->camT.alloc(C * 12));
   KB_CCUDA(h->camPi.alloc(C * 36));
   KB_CCUDA(h->camA.alloc(C * C * 36));
@@ -676,6 +697,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   D.U = h->U.p; D.Sred = h->Sred.p; D.dxc = h->dxc.p; D.dx = h->dx.p; D.n_invalid = h->n_invalid.p;
   h->n_partials = schur_num_partials(D);
   KB_CCUDA(h->partials.alloc(schur_partial_stride(D) * h->n_partials));
+  trace.mark("allocations, memsets");
 
   if (d->n_ranks > 1) {
     std::string err;
@@ -687,6 +709,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     if (r != 0) return cfail(KB_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
   }
   KB_CCUDA(cudaStreamSynchronize(s));
+  trace.mark("nccl, synchronise");
 #undef KB_CCUDA
   *out = hp.release();
   return KB_OK;

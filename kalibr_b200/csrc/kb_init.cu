@@ -29,6 +29,12 @@ constexpr double FOV_MAX_VALID_ANGLE = 1.5533430342749532;  // 89 degrees: CAM/i
 #define KB_PNP_G 8
 #endif
 constexpr int PNP_G = KB_PNP_G;
+#ifndef KB_PNP_MINB
+#define KB_PNP_MINB 4
+#endif
+#ifndef KB_PNP_STEP_TOL
+#define KB_PNP_STEP_TOL 1e-10
+#endif
 constexpr int PNP_GROUPS = PNP_WARPS * 32 / PNP_G;  // views in flight per CTA
 __device__ __forceinline__ double wsum(double v, unsigned mask) {
 #pragma unroll
@@ -495,7 +501,7 @@ __device__ __forceinline__ bool pnp_group(const DevProblem& p, const double* __r
 
 // ---- estimateTransformation for a list of views ---------------------------------------------------------------------------
 template <int MODEL>
-__global__ void __launch_bounds__(PNP_WARPS * 32, 3) pnp_kernel(DevProblem p, const int* __restrict__ view_list, int n_list,
+__global__ void __launch_bounds__(PNP_WARPS * 32, KB_PNP_MINB) pnp_kernel(DevProblem p, const int* __restrict__ view_list, int n_list,
                                                               const unsigned char* __restrict__ view_mask, const int* __restrict__ resolution,
                                                               int n_max, double* __restrict__ T_out, int* __restrict__ ok_out) {
   // the staged values have all passed through float (cv::Point2f / Point3f), so float storage is exact: 24 bytes per corner

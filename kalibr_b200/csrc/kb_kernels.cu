@@ -1536,12 +1536,18 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
 // are the singular values, the columns of V the singular vectors; both are written sorted by descending singular value.
 // =========================================================================================================
 constexpr int EIG_THREADS = 1024;
-__global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem p, double* __restrict__ G, double* __restrict__ V,
-                                                                      double* __restrict__ sv_out, double* __restrict__ V_out, int* __restrict__ sweeps_out) {
+__global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem p, double* __restrict__ G_glob, double* __restrict__ V_glob,
+                                                                      double* __restrict__ sv_out, double* __restrict__ V_out, int* __restrict__ sweeps_out,
+                                                                      int use_smem) {
+  extern __shared__ __align__(16) double eig_smem[];
   __shared__ double s_sigma[256];
   __shared__ int s_perm[256];
   const int n = p.n_c, na = p.n_aug;
   const int np = (n + 1) & ~1;  // padded to an even number of columns (the extra one is zero and never rotates)
+  // the rotated columns and the accumulated rotations live in shared memory when they fit (n <= 119: every pair step then costs
+  // shared-memory latency instead of an L1 / L2 round trip), else in the global scratch buffers
+  double* __restrict__ G = use_smem ? eig_smem : G_glob;
+  double* __restrict__ V = use_smem ? eig_smem + (size_t)np * n : V_glob;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = EIG_THREADS / 32;
   for (int idx = tid; idx < np * n; idx += EIG_THREADS) {
     const int c = idx / n, r = idx - c * n;
@@ -2297,8 +2303,19 @@ cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx&
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
+// dynamic shared memory of marginal_eig_kernel: both n x np column arrays, or 0 when they do not fit beside the static arrays
+static size_t eig_smem_bytes(const DevProblem& p) {
+  const size_t np = ((size_t)p.n_c + 1) & ~(size_t)1;
+  const size_t bytes = sizeof(double) * 2 * np * (size_t)p.n_c;
+  return bytes <= 220 * 1024 ? bytes : 0;
+}
 cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, double* sv_out, double* V_out, int* sweeps_out, StreamCtx& s) {
-  marginal_eig_kernel<<<1, EIG_THREADS, 0, s.stream>>>(p, G, V, sv_out, V_out, sweeps_out);
+  const size_t smem = eig_smem_bytes(p);
+  if (smem) {
+    cudaError_t e = cudaFuncSetAttribute(marginal_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  marginal_eig_kernel<<<1, EIG_THREADS, smem, s.stream>>>(p, G, V, sv_out, V_out, sweeps_out, smem ? 1 : 0);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2311,7 +2328,12 @@ cudaError_t launch_svd_solve(const DevProblem& p, const double* diag_h, double n
                              double* G, double* V, double* sv, double* V_out, int* sweeps, double* result, StreamCtx& s) {
   svd_scale_kernel<<<1, 256, 0, s.stream>>>(p, diag_h, norm_tol, column_scaling, g);
   KB_LAUNCHED(s);
-  marginal_eig_kernel<<<1, EIG_THREADS, 0, s.stream>>>(p, G, V, sv, V_out, sweeps);
+  const size_t smem = eig_smem_bytes(p);
+  if (smem) {
+    cudaError_t e = cudaFuncSetAttribute(marginal_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  marginal_eig_kernel<<<1, EIG_THREADS, smem, s.stream>>>(p, G, V, sv, V_out, sweeps, smem ? 1 : 0);
   KB_LAUNCHED(s);
   svd_truncated_solve_kernel<<<1, 256, 0, s.stream>>>(p, sv, V_out, g, eps_svd, svd_tol, result);
   KB_LAUNCHED(s);

@@ -3,6 +3,7 @@
 //   driver_main <single|stereo|rig> <problem.bin>
 //   driver_main estimator <problem.bin> <infoGainDelta>     every synced set offered to the incremental estimator, in order
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <fstream>
 
@@ -99,6 +100,7 @@ int main(int argc, char** argv) {
       eo.infoGainDelta = argc > 3 ? std::atof(argv[3]) : 0.2;
       eo.checkValidity = true;  // CalibrateCameras.cpp:261
       kalibr_b200::calibration::IncrementalEstimator estimator(cams, guesses, target, eo);
+      const auto t0 = std::chrono::steady_clock::now();
       for (int s = 0; s < n_sets; ++s) {
         Transformation T;
         std::memcpy(T.q, &set_poses[(size_t)s * 7], sizeof(T.q));
@@ -106,6 +108,7 @@ int main(int argc, char** argv) {
         auto r = estimator.addBatch(synced[(size_t)s], T);
         std::printf("batch%d %d %.17g %td %zu %.17g %.17g\n", s, r.batchAccepted ? 1 : 0, r.informationGain, r.rankTheta, r.numIterations, r.JStart, r.JFinal);
       }
+      std::printf("loop_ms %.3f\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
       std::printf("accepted %zu\n", estimator.getNumBatches());
       for (size_t j = 0; j < estimator.baselines().size(); ++j) printPose(("baseline" + std::to_string(j)).c_str(), estimator.baselines()[j]);
       for (int k = 0; k < n_cams; ++k) printCamera(("camera" + std::to_string(k)).c_str(), estimator.cameras()[(size_t)k]);
