@@ -1548,6 +1548,9 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem
   // shared-memory latency instead of an L1 / L2 round trip), else in the global scratch buffers
   double* __restrict__ G = use_smem ? eig_smem : G_glob;
   double* __restrict__ V = use_smem ? eig_smem + (size_t)np * n : V_glob;
+  // two columns count as orthogonal below n * eps relative to their norms (the usual one-sided Jacobi criterion); anything tighter
+  // only adds sweeps that chase rounding noise
+  const double ortho_tol = 2.220446049250313e-16 * (double)(n > 8 ? n : 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = EIG_THREADS / 32;
   for (int idx = tid; idx < np * n; idx += EIG_THREADS) {
     const int c = idx / n, r = idx - c * n;
@@ -1581,7 +1584,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem
         alpha = warp_sum(alpha);
         beta = warp_sum(beta);
         gamma = warp_sum(gamma);
-        if (fabs(gamma) > 1e-15 * sqrt(alpha * beta) && gamma != 0.0) {
+        if (fabs(gamma) > ortho_tol * sqrt(alpha * beta) && gamma != 0.0) {
           const double zeta = (beta - alpha) / (2.0 * gamma);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
