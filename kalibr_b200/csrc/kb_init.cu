@@ -967,8 +967,7 @@ cudaError_t launch_omni_candidates(const DevProblem& p, const int* cam_views, in
   if (n_views <= 0) return cudaMemsetAsync(out3, 0, 3 * sizeof(double), s.stream);
   const int n_max = p.n_target;
   const size_t smem = sizeof(float) * (size_t)(6 * n_max + 6 * cols) * PNP_GROUPS;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+  if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(omni_candidate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
