@@ -1516,6 +1516,7 @@ kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, doub
   h->solved = true;
   h->rho_lambda = 0.0;
   if (!h->h_posdef[0]) return fail(h, KB_ERR_STATE, "a set pose is not constrained by its observations (pose block not positive definite)");
+  if (getenv("KB_SVD_TRACE")) std::fprintf(stderr, "[kb trace] truncated-SVD solve: n = %d, Jacobi sweeps = %d, rank = %d\n", n, sweeps, (int)res[0]);
   if (sweeps >= 40) return fail(h, KB_ERR_STATE, "the Jacobi iteration of the truncated-SVD solve did not converge");
   h->last_svd.n = n;
   h->last_svd.rank = (int32_t)res[0];
