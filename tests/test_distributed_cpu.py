@@ -120,3 +120,91 @@ def test_sharded_reduced_system_matches_single_process(oracle_lib, cfg, n_sets):
         assert np.abs(dx_c - dx[cam_idx]).max() <= 1e-8 * np.abs(dx[cam_idx]).max()
     # both ranks hold the identical replicated solution
     assert np.array_equal(results[0][2], results[1][2])
+
+
+# ---- the widened rows: what their multi-rank paths rely on -------------------------------------------------------------------
+def _worker_widened(rank, world, port, cfg, n_sets, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import ko_estimator as ke
+    from oracle import ko_init as ki
+    from oracle import oracle_api as oa
+
+    p = synthetic.make_config(cfg, n_sets=n_sets)
+    lo, hi = synthetic.shard_sets(n_sets, world, rank)
+    mine = sub_problem(p, lo, hi)
+    o = oa.OracleProblem(mine, n_threads=1)
+    o.evaluate_error()
+    # (1) kb_reprojection_statistics: pass 0 sums (n, sum e_u, sum e_v) per camera, all-reduce, pass 1 squared deviations from the
+    #     GLOBAL mean, all-reduce
+    e = -o.error_vector().reshape(-1, 2)
+    cam = np.repeat(mine.view_cam, np.diff(mine.view_begin))
+    acc = torch.zeros((p.n_cams, 3), dtype=torch.float64)
+    for k in range(p.n_cams):
+        acc[k] = torch.tensor([np.sum(cam == k), e[cam == k, 0].sum(), e[cam == k, 1].sum()])
+    dist.all_reduce(acc)
+    mean = (acc[:, 1:] / acc[:, :1]).numpy()
+    ssd = torch.zeros((p.n_cams, 2), dtype=torch.float64)
+    for k in range(p.n_cams):
+        ssd[k] = torch.from_numpy(((e[cam == k] - mean[k]) ** 2).sum(0))
+    dist.all_reduce(ssd)
+    stats = np.concatenate([acc[:, :1].numpy(), mean, np.sqrt(ssd.numpy() / (acc[:, :1].numpy() - 1)),
+                            (np.linalg.norm(acc[:, 1:].numpy(), axis=1) / np.sqrt(acc[:, 0].numpy()))[:, None]], 1)
+    # (2) kb_solve_system_svd: the undamped reduced system and the diagonal of the camera block are sums over the ranks; every rank
+    #     then scales, decomposes and truncates the identical matrix
+    o.build_system()
+    S_part, cam_idx = reduced_system(o, mine, 0.0)
+    col, dims = o.dv_layout()
+    J = ke.dense_from_ccs(*o.jacobian_ccs(), o.jcols)
+    diag = torch.from_numpy((J[:, cam_idx] ** 2).sum(0))
+    t = torch.from_numpy(S_part)
+    dist.all_reduce(t)
+    dist.all_reduce(diag)
+    S = t.numpy()
+    rows = 2 * p.n_terms
+    g = np.where(np.sqrt(diag.numpy()) < np.sqrt(rows * ke.EPS), 0.0, 1.0 / np.sqrt(diag.numpy()))
+    Ss, bs = S[:-1, :-1] * np.outer(g, g), S[:-1, -1] * g
+    U, sv, Vt = np.linalg.svd(Ss)
+    tol = sv[0] * 1e-6 * len(sv)
+    rank_svd = len(sv)
+    for i in range(len(sv) - 1, 0, -1):
+        if sv[i] > tol:
+            break
+        rank_svd -= 1
+    x_c = g * (Vt[:rank_svd].T @ ((U[:, :rank_svd].T @ bs) / sv[:rank_svd]))
+    # (3) kb_initialize_set_poses: every rank initialises its own sets
+    guesses, ok = ki.target_pose_guesses(mine)
+    q.put((rank, stats, x_c, rank_svd, guesses, lo, hi))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_statistics_svd_solve_and_pose_guesses_match_single_process(oracle_lib):
+    from oracle import ko_estimator as ke
+    from oracle import ko_init as ki
+
+    cfg, n_sets, world = 2, 7, 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_widened, args=(r, world, port, cfg, n_sets, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = sorted((q.get(timeout=180) for _ in range(world)), key=lambda r: r[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    p = synthetic.make_config(cfg, n_sets=n_sets)
+    o = oracle_lib.OracleProblem(p, n_threads=1)
+    st = o.reprojection_statistics()
+    J, b = ke.system_of(o, p)
+    cal, rest = ke.calibration_columns(p)
+    x, info = ke.linear_solver_solve(J, b, cal, rest, column_scaling_on=True, eps_svd=1e-6)
+    guesses, _ = ki.target_pose_guesses(p)
+    for rank, stats, x_c, rank_svd, g_loc, lo, hi in results:
+        assert np.abs(stats - st).max() < 1e-10
+        assert rank_svd == info["rank"]
+        assert np.abs(x_c - x[cal]).max() <= 1e-7 * np.abs(x[cal]).max()
+        assert np.abs(g_loc - guesses[lo:hi]).max() < 1e-12
+    assert np.array_equal(results[0][2], results[1][2])  # the replicated solution is identical on both ranks
