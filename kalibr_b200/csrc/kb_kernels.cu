@@ -1552,6 +1552,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem
   // only adds sweeps that chase rounding noise
   const double ortho_tol = 2.220446049250313e-16 * (double)(n > 8 ? n : 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = EIG_THREADS / 32;
+  const int half = lane >> 4, hl = lane & 15;
   for (int idx = tid; idx < np * n; idx += EIG_THREADS) {
     const int c = idx / n, r = idx - c * n;
     G[idx] = c < n ? p.Sred[(size_t)r * na + c] : 0.0;
@@ -1562,35 +1563,47 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem
   for (; sweep < 40; ++sweep) {
     int rotated = 0;
     for (int step = 0; step < np - 1; ++step) {
-      for (int k = warp; k < np / 2; k += n_warps) {
+      // A half-warp per column pair: the two halves of a warp run the division / square-root chain of their rotation parameters in
+      // the same instructions, so a step issues half as many of them, and the 53 pairs of n = 106 fit one round of the 32 warps.
+      for (int k0 = 2 * warp; k0 < np / 2; k0 += 2 * n_warps) {
+        const int k = k0 + half;
+        const bool valid = k < np / 2;
         // round-robin pairing: player np - 1 stays, the others rotate
-        int a, b;
-        if (k == 0) {
-          a = np - 1;
-          b = step;
-        } else {
-          a = (step + k) % (np - 1);
-          b = (step - k + (np - 1)) % (np - 1);
+        int a = 0, b = 0;
+        if (valid) {
+          if (k == 0) {
+            a = np - 1;
+            b = step;
+          } else {
+            a = (step + k) % (np - 1);
+            b = (step - k + (np - 1)) % (np - 1);
+          }
         }
         double* ga = G + (size_t)a * n;
         double* gb = G + (size_t)b * n;
         double alpha = 0.0, beta = 0.0, gamma = 0.0;
-        for (int r = lane; r < n; r += 32) {
-          const double x = ga[r], y = gb[r];
-          alpha += x * x;
-          beta += y * y;
-          gamma += x * y;
+        if (valid)
+          for (int r = hl; r < n; r += 16) {
+            const double x = ga[r], y = gb[r];
+            alpha += x * x;
+            beta += y * y;
+            gamma += x * y;
+          }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {  // sums inside the half-warp (xor offsets below 16 stay in the half)
+          alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+          beta += __shfl_xor_sync(0xffffffffu, beta, o);
+          gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
         }
-        alpha = warp_sum(alpha);
-        beta = warp_sum(beta);
-        gamma = warp_sum(gamma);
-        if (fabs(gamma) > ortho_tol * sqrt(alpha * beta) && gamma != 0.0) {
-          const double zeta = (beta - alpha) / (2.0 * gamma);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        if (valid && gamma * gamma > ortho_tol * ortho_tol * (alpha * beta) && gamma != 0.0) {
+          // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = (beta - alpha) / (2 gamma), written with one square root and one
+          // division: t = sign(d) g2 / (|d| + sqrt(d^2 + g2^2)), d = beta - alpha, g2 = 2 gamma
+          const double d = beta - alpha, g2 = 2.0 * gamma;
+          const double t = copysign(1.0, d) * g2 / (fabs(d) + sqrt(d * d + g2 * g2));
+          const double c = rsqrt(1.0 + t * t), sn = c * t;
           double* va = V + (size_t)a * n;
           double* vb = V + (size_t)b * n;
-          for (int r = lane; r < n; r += 32) {
+          for (int r = hl; r < n; r += 16) {
             const double x = ga[r], y = gb[r];
             ga[r] = c * x - sn * y;
             gb[r] = sn * x + c * y;
