@@ -9,10 +9,13 @@ BIN = os.path.join(ROOT, "tests", "cpp", "driver_main")
 
 
 def build_driver():
+    from kalibr_b200 import build as kb_build
+
+    kb_build.build_extension()  # no-op when the in-tree library is up to date
     src = os.path.join(ROOT, "tests", "cpp", "driver_main.cpp")
     lib_dir = os.path.join(ROOT, "kalibr_b200")
     hdrs = [os.path.join(ROOT, "include", "kalibr_b200", h) for h in ("calibration_tools.hpp", "incremental_estimator.hpp")] + [os.path.join(ROOT, "include", "kalibr_b200.h")]
-    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(f) for f in [src] + hdrs):
+    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(f) for f in [src, kb_build.LIB_PATH] + hdrs):
         subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-L", lib_dir,
                         "-lkalibr_b200", f"-Wl,-rpath,{lib_dir}", "-o", BIN], check=True)
     return BIN
