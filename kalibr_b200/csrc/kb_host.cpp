@@ -1029,6 +1029,10 @@ kb_status kb_reprojection_statistics(kb_handle* h, double* out) {
 // ---- initial-guess stage -----------------------------------------------------------------------------
 namespace {
 kb_status pnp_prepare(kb_handle* h, const int32_t* resolution, const int** res_dev) {
+  // a view is one image of the target: it cannot hold more corners than the target has (the kernels stage n_target corners per view)
+  for (size_t w = 0; w + 1 < h->h_view_begin.size(); ++w)
+    if (h->h_view_begin[w + 1] - h->h_view_begin[w] > h->d.n_target)
+      return fail(h, KB_ERR_INVALID_ARGUMENT, "a view lists more corners than the target has points");
   const size_t V = (size_t)std::max(h->d.n_views, 1);
   if (h->pnp_T.n < V * POSE_STRIDE) KB_CUDA(h, h->pnp_T.alloc(V * POSE_STRIDE));
   if (h->pnp_ok.n < V) KB_CUDA(h, h->pnp_ok.alloc(V));
@@ -1169,6 +1173,9 @@ kb_status kb_initialize_intrinsics(kb_handle* h, int32_t cam, int32_t target_row
   if (cam < 0 || cam >= h->n_cams || !resolution) return fail(h, KB_ERR_INVALID_ARGUMENT, "bad camera index or null resolution");
   if (target_rows < 1 || target_cols < 1 || target_rows * target_cols != h->d.n_target || target_cols > 32 || target_rows > 1024)
     return fail(h, KB_ERR_INVALID_ARGUMENT, "target_rows x target_cols must equal the number of target points (cols <= 32)");
+  for (size_t w = 0; w + 1 < h->h_view_begin.size(); ++w)
+    if (h->h_view_begin[w + 1] - h->h_view_begin[w] > h->d.n_target)
+      return fail(h, KB_ERR_INVALID_ARGUMENT, "a view lists more corners than the target has points");
   KB_CUDA(h, cudaSetDevice(h->device));
   StreamCtx c = ctx(h);
   const int model = h->cam_model[cam];
