@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(_HERE, "libkalibr_oracle.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("kalibr_oracle.cpp", "ko_backend.hpp", "ko_cameras.hpp", "ko_math.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("kalibr_oracle.cpp", "ko_backend.hpp", "ko_cameras.hpp", "ko_marginal.hpp", "ko_math.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "kalibr_b200.h"))
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
