@@ -157,6 +157,7 @@ class B200SchurLinearSystemSolver:
         if st != KB_OK:
             raise KalibrB200Error(f"kb_create failed ({st}): " + self._L.kb_last_error(None).decode())
         self._h = h
+        self._local_views_known = n_ranks == 1 or n_sets_total > 0  # the description's views are exactly this rank's views
         self.jrows = self._L.kb_jrows(h)
         self.local_jrows = self._L.kb_local_jrows(h)
         self.jcols = self._L.kb_jcols(h)
@@ -258,9 +259,9 @@ class B200SchurLinearSystemSolver:
 
     def estimate_transformations(self, resolution=None):
         """PnP per local view: (T_target_camera poses [n_views, 7], ok [n_views])."""
-        nv = len(self.problem.view_set) if self.local_jrows == self.jrows else None
-        if nv is None:
+        if not self._local_views_known:
             raise KalibrB200Error("estimate_transformations: use one rank or a pre-sharded problem from Python")
+        nv = len(self.problem.view_set)
         T = np.zeros((nv, 7))
         ok = np.zeros(nv, np.int32)
         r = self._res(resolution)
