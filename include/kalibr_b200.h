@@ -10,8 +10,13 @@
  *   K2  = aslam_offline_calibration/kalibr2
  *
  * Conventions: opaque handle, int status (0 = OK, negative = error, message
- * via kb_last_error), no exceptions cross the boundary, one caller thread per
- * handle (BE/src/Optimizer2.cpp:183-273 drives a solver from one thread).
+ * via kb_last_error), no exceptions cross the boundary.
+ * Thread safety: a handle is driven by ONE caller thread at a time
+ * (BE/src/Optimizer2.cpp:183-273 drives a solver from one thread); different
+ * handles - on the same GPU or on different GPUs - may be driven from different
+ * threads concurrently: every handle owns its stream, its scratch buffers and
+ * its CUDA graph, and the library's only process-wide state (per-device launch
+ * attribute caches, the dlopen'ed NCCL entry points) is guarded.
  * All pointers in the signatures are caller-owned HOST pointers (FP64 /
  * int32 / int64, SoA); the library owns every device buffer.  There is no CPU
  * fallback: kb_create fails with KB_ERR_NO_DEVICE when no sm_100 device is
@@ -37,6 +42,7 @@ typedef int32_t kb_status;
 #define KB_ERR_NCCL (-4)
 #define KB_ERR_STATE (-5)      /* call sequence violated (e.g. solve before build) */
 #define KB_ERR_ALLOC (-6)
+#define KB_ERR_NUMERICAL (-7)  /* a numerical outcome, not a fault: pose block not positive definite, SVD iteration not converged */
 
 /* ---- camera models: K2/include/kalibr2/CameraCalibrator.hpp:421-441 ------ */
 typedef enum {

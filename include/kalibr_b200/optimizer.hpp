@@ -21,6 +21,12 @@
 namespace kalibr_b200 {
 namespace backend {
 
+// A failed C-ABI call: carries the kb_status so that kb_optimize* can hand the original code back to the caller
+struct KbError : std::runtime_error {
+  KbError(kb_status c, const std::string& what) : std::runtime_error(what), code(c) {}
+  kb_status code;
+};
+
 struct SolutionReturnValue {  // backend.hpp:14-27
   double JStart = 0, JFinal = 0;
   int iterations = 0, failedIterations = 0;
@@ -103,7 +109,7 @@ class B200SchurLinearSystemSolver : public LinearSystemSolver {
 
  private:
   void check(kb_status s) {
-    if (s != KB_OK) throw std::runtime_error(std::string("kalibr_b200: ") + kb_last_error(_h));
+    if (s != KB_OK) throw KbError(s, std::string("kalibr_b200: ") + kb_last_error(_h));
   }
   kb_handle* _h;
   bool _deviceDx;
@@ -119,8 +125,13 @@ class B200SvdLinearSystemSolver : public B200SchurLinearSystemSolver {
   std::string name() const override { return "b200_marginal_svd"; }
   void setConstantConditioner(double /*diag*/) override {}  // the Gauss-Newton policy never asks for one
   bool solveSystem(std::vector<double>& /*outDx: stays on the device*/) override {
-    if (kb_solve_system_svd(_hs, &_svdOptions, nullptr, 0, &_last, nullptr) != KB_OK) return false;  // ≙ the exceptions solveSystem turns into false
-    return true;
+    const kb_status st = kb_solve_system_svd(_hs, &_svdOptions, nullptr, 0, &_last, nullptr);
+    if (st == KB_OK) return true;
+    // only the NUMERICAL outcomes (pose block not positive definite, SVD iteration not converged) are "the solve failed" (≙ the
+    // exceptions LinearSolver::solveSystem turns into false, IC/src/core/LinearSolver.cpp:245-285); a device / NCCL / state error
+    // must not be retried as a linear-solver failure
+    if (st == KB_ERR_NUMERICAL) return false;
+    throw KbError(st, std::string("kalibr_b200: ") + kb_last_error(_hs));
   }
   const kb_svd_solve_result& lastSolve() const { return _last; }
 

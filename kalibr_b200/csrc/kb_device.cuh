@@ -125,6 +125,7 @@ struct DevProblem {
   double* dxc;          // [n_c]
   double* dx;           // [jcols] in design-variable order (poses of other ranks stay 0)
   unsigned int* n_invalid;  // terms whose projection bailed out (Q6)
+  double* rho_partial;      // [2 * 64] stage-1 partials of the rho denominator / max|dx| reduction (per handle)
   LmCtrl* ctrl;             // control block (device)
   PeerXchg px;              // peer exchange (enabled after kb_attach_peers)
   // ---- weighting of the terms (kb_set_inv_r / kb_set_m_estimator) ----

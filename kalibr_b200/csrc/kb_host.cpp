@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -21,6 +22,7 @@
 #include "kb_device.cuh"
 
 using namespace kb;
+using kalibr_b200::backend::KbError;
 
 // ---------------------------------------------------------------------------------------------------------
 // NCCL through dlopen (no link-time dependency; single-GPU use never touches it)
@@ -35,7 +37,9 @@ struct NcclApi {
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  std::mutex mu;
   bool load(std::string& err) {
+    std::lock_guard<std::mutex> lock(mu);
     if (lib) return true;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
@@ -54,7 +58,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 constexpr int kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3;
-std::string g_create_error;
+thread_local std::string g_create_error;  // kb_last_error(NULL) reports the calling thread's last kb_create failure
 
 template <typename T>
 struct DevBuf {
@@ -99,7 +103,7 @@ struct kb_handle {
   // ---- device ----
   DevProblem d;
   DevBuf<double> y_u, y_v, target, cam_params, baselines, set_poses, camT, camPi, camA, baseBt, baseM, e, view_cost, set_prep, VB, gram_partial, sumG, V, bv, W, Lv, yv, U, Sred, dxc, dx;
-  DevBuf<double> init_cam, init_base, init_sets, bk_cam, bk_base, bk_sets, partials, scalars, jt, gather;
+  DevBuf<double> init_cam, init_base, init_sets, bk_cam, bk_base, bk_sets, partials, scalars, jt, gather, rho_partial;
   DevBuf<uint16_t> corner;
   DevBuf<int> view_set, view_cam, view_begin, set_view, lin_off, view_list, cam_view_list, cam_view_begin, set_col_q, set_col_t, cam_cols, posdef;
   DevBuf<long long> view_jbase;
@@ -659,6 +663,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->dxc.alloc(D.n_c));
   KB_CCUDA(h->dx.alloc((size_t)h->jcols));
   KB_CCUDA(h->scalars.alloc(8));
+  KB_CCUDA(h->rho_partial.alloc(2 * 64));
   KB_CCUDA(h->rank_slots.alloc(4 * (size_t)d->n_ranks));
   KB_CCUDA(h->ctrl.alloc(1));
   D.px.enabled = 0;
@@ -694,7 +699,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   D.camT = h->camT.p; D.camPi = h->camPi.p; D.camA = h->camA.p; D.baseBt = h->baseBt.p; D.baseM = h->baseM.p;
   D.e = h->e.p; D.view_cost = h->view_cost.p; D.set_prep = h->set_prep.p; D.VB = h->VB.p; D.gram_partial = h->gram_partial.p; D.sumG = h->sumG.p;
   D.V = h->V.p; D.bv = h->bv.p; D.W = h->W.p; D.Lv = h->Lv.p; D.yv = h->yv.p;
-  D.U = h->U.p; D.Sred = h->Sred.p; D.dxc = h->dxc.p; D.dx = h->dx.p; D.n_invalid = h->n_invalid.p;
+  D.U = h->U.p; D.Sred = h->Sred.p; D.dxc = h->dxc.p; D.dx = h->dx.p; D.n_invalid = h->n_invalid.p; D.rho_partial = h->rho_partial.p;
   h->n_partials = schur_num_partials(D);
   KB_CCUDA(h->partials.alloc(schur_partial_stride(D) * h->n_partials));
   trace.mark("allocations, memsets");
@@ -1282,8 +1287,8 @@ static kb_status analyze_marginal_impl(kb_handle* h, const kb_marginal_options* 
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   h->solved = false;  // the pose factors now belong to the undamped system
   if (!h->h_posdef[0])
-    return fail(h, KB_ERR_STATE, "a set pose is not constrained by its observations (pose block not positive definite): the marginal is undefined");
-  if (sweeps >= 40) return fail(h, KB_ERR_STATE, "the Jacobi iteration of the marginal analysis did not converge");
+    return fail(h, KB_ERR_NUMERICAL, "a set pose is not constrained by its observations (pose block not positive definite): the marginal is undefined");
+  if (sweeps >= 40) return fail(h, KB_ERR_NUMERICAL, "the Jacobi iteration of the marginal analysis did not converge");
   if (columns)
     for (int i = 0; i < n; ++i) columns[i] = h->h_cam_cols[i];
   // IC/src/algorithms/linalg.cpp:244-282, IC/src/core/LinearSolver.cpp:196-200
@@ -1522,9 +1527,9 @@ kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, doub
   if (st != KB_OK) return st;
   h->solved = true;
   h->rho_lambda = 0.0;
-  if (!h->h_posdef[0]) return fail(h, KB_ERR_STATE, "a set pose is not constrained by its observations (pose block not positive definite)");
+  if (!h->h_posdef[0]) return fail(h, KB_ERR_NUMERICAL, "a set pose is not constrained by its observations (pose block not positive definite)");
   if (getenv("KB_SVD_TRACE")) std::fprintf(stderr, "[kb trace] truncated-SVD solve: n = %d, Jacobi sweeps = %d, rank = %d\n", n, sweeps, (int)res[0]);
-  if (sweeps >= 40) return fail(h, KB_ERR_STATE, "the Jacobi iteration of the truncated-SVD solve did not converge");
+  if (sweeps >= 40) return fail(h, KB_ERR_NUMERICAL, "the Jacobi iteration of the truncated-SVD solve did not converge");
   h->last_svd.n = n;
   h->last_svd.rank = (int32_t)res[0];
   h->last_svd.rank_deficiency = n - h->last_svd.rank;
@@ -1591,6 +1596,7 @@ kb_status kb_reset_state(kb_handle* h) {
 kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v) {
   if (h->n_ranks != 1 && !h->presharded)
     return fail(h, KB_ERR_STATE, "kb_set_observations needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
+  if (!y_u || !y_v) return fail(h, KB_ERR_INVALID_ARGUMENT, "null observation array");
   KB_CUDA(h, cudaSetDevice(h->device));
   KB_CUDA(h, cudaMemcpyAsync(h->front_u, y_u, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(h->front_v, y_v, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
@@ -1636,11 +1642,15 @@ kb_status kb_commit_observations(kb_handle* h) {
   return KB_OK;
 }
 
-int64_t kb_num_invalid_terms(kb_handle* h) {
+int64_t kb_num_invalid_terms(kb_handle* h) {  // -1 on a CUDA error (message in kb_last_error)
   unsigned int v = 0;
-  cudaSetDevice(h->device);
-  cudaMemcpyAsync(&v, h->n_invalid.p, sizeof(v), cudaMemcpyDeviceToHost, h->stream);
-  cudaStreamSynchronize(h->stream);
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&v, h->n_invalid.p, sizeof(v), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    h->error = std::string("kb_num_invalid_terms: ") + cudaGetErrorString(e);
+    return -1;
+  }
   return (int64_t)v;
 }
 
@@ -1755,10 +1765,14 @@ static kb_status optimize_on_device(kb_handle* h, const kb_optimizer_options* o,
       cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
       h->lm_graph_kernels = h->launches - l0;  // captured, not launched
       h->launches = l0;
-      if (st != KB_OK) return st;
-      KB_CUDA(h, ce);
-      KB_CUDA(h, cudaGraphInstantiate(&h->lm_graph, graph, 0));
+      if (st != KB_OK || ce != cudaSuccess) {  // never leak the captured graph
+        if (graph) cudaGraphDestroy(graph);
+        if (st != KB_OK) return st;
+        KB_CUDA(h, ce);
+      }
+      ce = cudaGraphInstantiate(&h->lm_graph, graph, 0);
       cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { h->lm_graph = nullptr; KB_CUDA(h, ce); }
       h->lm_graph_trace = h->trace_dev.p;
     }
     for (int k = 0; k < 2; ++k) {
@@ -1771,8 +1785,20 @@ static kb_status optimize_on_device(kb_handle* h, const kb_optimizer_options* o,
     }
     h->lm_warm = true;
     KB_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->ctrl.p, sizeof(LmCtrl), cudaMemcpyDeviceToHost, h->stream));
+    if (h->px_on)  // the exchange's time-out flag travels with the control block (a timed-out wait also sets ctrl->done)
+      KB_CUDA(h, cudaMemcpyAsync(h->h_scalars + 7, h->px_buf.p + px_off_flags(h->d.px) + 3 * (size_t)h->n_ranks + 4, 8, cudaMemcpyDeviceToHost, h->stream));
     KB_CUDA(h, cudaStreamSynchronize(h->stream));
     collect_stages(h);
+    if (h->px_on) {
+      unsigned long long err = 0;
+      std::memcpy(&err, h->h_scalars + 7, 8);
+      if (err) {
+        StreamCtx sc = ctx(h);
+        launch_lm_finish(h->d, sc);  // back to the neutral flags: the handle reports the error instead of silently idling
+        cudaStreamSynchronize(h->stream);
+        return fail(h, KB_ERR_NCCL, "peer exchange timed out inside the device-resident loop: a rank did not reach the exchange step");
+      }
+    }
   }
   const LmCtrl& c = *h->h_ctrl;
   h->trace.assign((size_t)3 * c.iterations, 0.0);
@@ -1825,9 +1851,12 @@ kb_status kb_optimize(kb_handle* h, const kb_optimizer_options* o, kb_solution* 
       out->linear_solver_failure = srv.linearSolverFailure ? 1 : 0;
     }
     return KB_OK;
-  } catch (const std::exception& e) {
+  } catch (const KbError& e) {  // the status of the entry point that failed, not a blanket KB_ERR_CUDA
     if (h->error.empty()) h->error = e.what();
-    return KB_ERR_CUDA;
+    return e.code;
+  } catch (const std::exception& e) {
+    h->error = e.what();
+    return KB_ERR_INVALID_ARGUMENT;
   }
 }
 
@@ -1857,9 +1886,12 @@ kb_status kb_optimize_gauss_newton(kb_handle* h, const kb_optimizer_options* o, 
       out->linear_solver_failure = srv.linearSolverFailure ? 1 : 0;
     }
     return KB_OK;
-  } catch (const std::exception& e) {
+  } catch (const KbError& e) {
     if (h->error.empty()) h->error = e.what();
-    return KB_ERR_CUDA;
+    return e.code;
+  } catch (const std::exception& e) {
+    h->error = e.what();
+    return KB_ERR_INVALID_ARGUMENT;
   }
 }
 

@@ -20,6 +20,8 @@
 //   px_*              NVLink peer exchange between ranks (producers are fused into schur_finalize / rho_stage2 / gram_cost)
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
+#include <mutex>
 
 #include "kb_device.cuh"
 #include "kb_models.cuh"
@@ -204,13 +206,22 @@ __device__ __forceinline__ void px_signal(const PeerXchg& x, int which, unsigned
   __threadfence_system();
   for (int r = 0; r < x.n_ranks; ++r) st_release_sys(px_words(x, r) + which * x.n_ranks + x.rank, e);
 }
-// wait until rank src has published epoch e of exchange `which`; gives up after ~5 s (a peer that died must not hang the GPU)
-__device__ __forceinline__ void px_wait(const PeerXchg& x, int which, int src, unsigned long long e) {
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long PX_TIMEOUT_NS = 5000000000ull;  // wall clock (globaltimer), independent of the SM clock
+// wait until rank src has published epoch e of exchange `which`; gives up after 5 s (a peer that died must not hang the GPU):
+// the error word of the exchange buffer is raised and the device-resident loop is told to stop (ctrl->done), so that nothing
+// downstream iterates on the stale slots; the host turns the error word into KB_ERR_NCCL.
+__device__ __forceinline__ void px_wait(const PeerXchg& x, int which, int src, unsigned long long e, LmCtrl* ctrl) {
   const unsigned long long* f = px_words(x, x.rank) + which * x.n_ranks + src;
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_timer_ns();
   while (ld_acquire_sys(f) < e) {
-    if (clock64() - t0 > 10000000000ll) {
+    if (global_timer_ns() - t0 > PX_TIMEOUT_NS) {
       px_words(x, x.rank)[3 * x.n_ranks + 4] = 1ull;
+      ctrl->done = 1;
       break;
     }
     __nanosleep(64);
@@ -1092,7 +1103,7 @@ __global__ void px_combine_cost_kernel(DevProblem p, double* __restrict__ out) {
   const unsigned long long e = px_cur_epoch(p.px, 2);
   double s = 0.0;
   for (int r = 0; r < p.px.n_ranks; ++r) {
-    px_wait(p.px, 2, r, e);
+    px_wait(p.px, 2, r, e, p.ctrl);
     s += __ldcg(p.px.base[p.px.rank] + px_off_c(p.px, (int)(e & 1), r));
   }
   out[0] = s;
@@ -1101,7 +1112,7 @@ __global__ void px_combine_cost_kernel(DevProblem p, double* __restrict__ out) {
 __global__ void __launch_bounds__(256) px_reduce_system_kernel(DevProblem p) {
   if (p.ctrl->done) return;
   const unsigned long long e = px_cur_epoch(p.px, 0);
-  if (threadIdx.x < p.px.n_ranks) px_wait(p.px, 0, threadIdx.x, e);
+  if (threadIdx.x < p.px.n_ranks) px_wait(p.px, 0, threadIdx.x, e, p.ctrl);
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.n_aug * p.n_aug) return;
@@ -1117,7 +1128,7 @@ __global__ void px_combine_solve_kernel(DevProblem p, double* __restrict__ rho_m
   double rho = 0.0, mx = 0.0;
   int pd = 1;
   for (int r = 0; r < p.px.n_ranks; ++r) {
-    px_wait(p.px, 1, r, e);
+    px_wait(p.px, 1, r, e, p.ctrl);
     const double* slot = p.px.base[p.px.rank] + px_off_b(p.px, (int)(e & 1), r);
     rho += __ldcg(slot);
     mx = fmax(mx, __ldcg(slot + 1));
@@ -2043,15 +2054,32 @@ static int cur_device() {
   return dev & (MAX_DEVICES - 1);
 }
 static int sm_count() {
-  static int count[MAX_DEVICES] = {};
+  static std::atomic<int> count[MAX_DEVICES] = {};
   const int dev = cur_device();
-  if (!count[dev]) {
-    cudaDeviceGetAttribute(&count[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (count[dev] <= 0) count[dev] = 148;
+  int c = count[dev].load(std::memory_order_relaxed);
+  if (!c) {
+    cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+    if (c <= 0) c = 148;
+    count[dev].store(c, std::memory_order_relaxed);
   }
-  return count[dev];
+  return c;
 }
 #define KB_LAUNCHED(s) (++*(s).launches)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is raised once per (kernel, device); the cache is guarded so that handles driven
+// from different threads can launch concurrently (the attribute itself is only ever raised)
+static std::mutex g_attr_mutex;
+template <typename K>
+static cudaError_t ensure_dynamic_smem(K kernel, size_t smem, size_t (&cache)[MAX_DEVICES]) {
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  size_t& have = cache[cur_device()];
+  if (smem > have) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    have = smem;
+  }
+  return cudaSuccess;
+}
 
 cudaError_t launch_prep(const DevProblem& p, StreamCtx& s) {
   prep_kernel<<<1, 32, 0, s.stream>>>(p);
@@ -2103,12 +2131,7 @@ static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const
   if (hi <= lo) return cudaSuccess;
   const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
-  size_t& attr_smem = attr_smem_dev[cur_device()];
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_smem = smem;
-  }
+  if (cudaError_t e = ensure_dynamic_smem(linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED>, smem, attr_smem_dev); e != cudaSuccess) return e;
   const int grid = min((hi - lo + LA_WARPS - 1) / LA_WARPS, sm_count() * 2);
   linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
   KB_LAUNCHED(s);
@@ -2155,12 +2178,7 @@ static cudaError_t launch_lm_model(const DevProblem& p, const int4* vmeta, const
   if (hi <= lo) return cudaSuccess;
   const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + (size_t)LM_WARPS * (XT_WARP_DOUBLES + bfrag_pairs * 32 + 36 + SETPREP_STRIDE));
   static size_t attr_smem_dev[MAX_DEVICES] = {};
-  size_t& attr_smem = attr_smem_dev[cur_device()];
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(linearise_materialise_kernel<MODEL, WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_smem = smem;
-  }
+  if (cudaError_t e = ensure_dynamic_smem(linearise_materialise_kernel<MODEL, WEIGHTED>, smem, attr_smem_dev); e != cudaSuccess) return e;
   const int ctas_per_sm = (int)max((size_t)1, min((size_t)4, (size_t)(220 * 1024) / (smem + 1024)));
   const int grid = min(((hi - lo) * LM_SUB + LM_WARPS - 1) / LM_WARPS, sm_count() * ctas_per_sm);
   linearise_materialise_kernel<MODEL, WEIGHTED><<<grid, LM_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi, jt, bfrag_pairs, counter);
@@ -2226,12 +2244,7 @@ static cudaError_t launch_schur_t(const DevProblem& p, double* partials, int n_p
   const int n_pad = ((p.n_aug + 7) >> 3) * 8;
   const size_t smem = sizeof(double) * (2 * (size_t)n_pad * SC_LD + 2 * SC_SETS * 36);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
-  size_t& attr_smem = attr_smem_dev[cur_device()];
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(schur_kernel<WARPS, MAX_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_smem = smem;
-  }
+  if (cudaError_t e = ensure_dynamic_smem(schur_kernel<WARPS, MAX_PAIRS>, smem, attr_smem_dev); e != cudaSuccess) return e;
   const int nt = (p.n_aug + 7) >> 3;
   const int npairs = nt * (nt + 1) / 2;
   const int gy = (npairs + WARPS * MAX_PAIRS - 1) / (WARPS * MAX_PAIRS);
@@ -2262,12 +2275,7 @@ cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_d
   const size_t n_rows = ((p.n_aug + RS_NB - 1) / RS_NB) * RS_NB + RS_NB;
   const size_t smem = sizeof(double) * (n_rows * (n_rows + 1) / 2 + 2 * n_rows);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
-  size_t& attr_smem = attr_smem_dev[cur_device()];
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(reduced_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_smem = smem;
-  }
+  if (cudaError_t e = ensure_dynamic_smem(reduced_solve_kernel, smem, attr_smem_dev); e != cudaSuccess) return e;
   reduced_solve_kernel<<<1, RS_THREADS, smem, s.stream>>>(p, damping, pos_def_flag);
   KB_LAUNCHED(s);
   return cudaGetLastError();
@@ -2282,12 +2290,7 @@ cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int*
 
 cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int*, int include_shared,
                                    double* out2, const int* pos_def_for_exchange, StreamCtx& s) {
-  static double* partial_dev[MAX_DEVICES] = {};
-  double*& partial = partial_dev[cur_device()];
-  if (!partial) {
-    cudaError_t e = cudaMalloc(&partial, sizeof(double) * 2 * RHO_BLOCKS);
-    if (e != cudaSuccess) return e;
-  }
+  double* partial = p.rho_partial;  // per handle (kb_create): two handles on one GPU never share scratch
   const int blocks = max(1, min(RHO_BLOCKS, (p.n_sets + 255) / 256));
   rho_stage1_kernel<<<blocks, 256, 0, s.stream>>>(p, lambda, set_col_q, set_col_t, include_shared, partial);
   KB_LAUNCHED(s);
