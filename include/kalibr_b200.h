@@ -62,7 +62,13 @@ typedef enum {
 typedef enum {
   KB_ORDER_SINGLE = 0, /* proj, dist ; per set q_v, t_v                                  */
   KB_ORDER_STEREO = 1, /* baseline q,t ; per set q_v,t_v ; proj0,dist0, proj1,dist1      */
-  KB_ORDER_RIG = 2     /* per cam proj,dist ; per baseline q,t ; per set q_v,t_v         */
+  KB_ORDER_RIG = 2,    /* per cam proj,dist ; per baseline q,t ; per set q_v,t_v         */
+  KB_ORDER_BATCH = 3   /* per set q_v,t_v ; per baseline q,t ; per cam proj,dist: the incremental estimator's merged problem -
+                        * CreateBatchProblem puts the target pose in group 1, baselines then intrinsics in group 0 and the (inactive)
+                        * landmarks in group 2 (K2/include/kalibr2/CalibrationTools.hpp:460-491); groups are ordered by first
+                        * appearance, [1, 0, 2] (IC/src/core/IncrementalOptimizationProblem.cpp:186-223), and
+                        * IncrementalEstimator::orderMarginalizedDesignVariables moves the marginalised group 0 last
+                        * (IC/src/core/IncrementalEstimator.cpp:550-565): the calibration block is the LAST n_c columns */
 } kb_driver_order;
 
 #define KB_CAM_PARAM_STRIDE 10 /* per camera: P projection params then D distortion params, zero padded */
@@ -334,6 +340,23 @@ KB_API kb_status kb_get_jacobian_ccs(kb_handle* h, int64_t* col_ptr /*[2*local t
  * ascending.  values are the blocks column-major one after another (value_ptr[k] offsets).  Call with NULL arrays to query counts. */
 KB_API kb_status kb_get_hessian_blocks(kb_handle* h, int64_t* n_blocks, int64_t* n_values, int64_t* col_ptr /*[n_dv+1]*/,
                                        int32_t* block_row, int64_t* value_ptr, double* values);
+/* Replace the current state ≙ DesignVariable::setParameters / what Optimizer2::applyStateUpdate and revertLastStateUpdate leave in
+ * the HOST design variables (BE/src/Optimizer2.cpp:290-318; BE/include/aslam/backend/DesignVariable.hpp:18-145): a
+ * LinearSystemSolver plugged into an unmodified Optimizer2 does not own the design variables, so its adapter pushes their values
+ * before every evaluateError / buildSystem.  Any of the three pointers may be NULL (left as is).  The normal
+ * equations of the last kb_build_system stay valid for further solves (the LM policy re-solves a built system after a revert);
+ * the cached speculative linearisation is invalidated.  set_poses: [n_sets][7] in the layout of kb_problem_desc (global sets,
+ * or this rank's sets when pre-sharded); quaternions are taken as given (the reference's updates keep them normalised). */
+KB_API kb_status kb_set_state(kb_handle* h, const double* cam_params /*[n_cams][KB_CAM_PARAM_STRIDE]*/, const double* baselines /*[n_cams-1][7]*/,
+                              const double* set_poses /*[n_sets][7]*/);
+KB_API kb_status kb_set_camera_params(kb_handle* h, const double* cam_params);
+KB_API kb_status kb_set_baselines(kb_handle* h, const double* baselines);
+KB_API kb_status kb_set_set_poses(kb_handle* h, const double* set_poses);
+/* ≙ LinearSystemSolver::setConditioner(const Eigen::VectorXd&) (BE/include/aslam/backend/LinearSystemSolver.hpp:35-36): the per-column
+ * conditioner.  The trust-region policies of the reference only ever install a constant one (setConstantConditioner,
+ * LevenbergMarquardtTrustRegionPolicy.cpp:87), which is what the Schur path implements: a vector whose jcols entries are all equal
+ * is accepted (= kb_set_constant_conditioner), anything else returns KB_ERR_INVALID_ARGUMENT. */
+KB_API kb_status kb_set_conditioner(kb_handle* h, const double* diag /*[jcols]*/);
 /* current state ≙ DesignVariable::getParameters */
 KB_API kb_status kb_get_camera_params(kb_handle* h, double* cam_params /*[n_cams][KB_CAM_PARAM_STRIDE]*/);
 KB_API kb_status kb_get_baselines(kb_handle* h, double* baselines /*[n_cams-1][7]*/);

@@ -1,8 +1,7 @@
 // Host-side C++ mirror of the reference's optimiser plugin surface for the batch-calibration hot path,
 // written over the C ABI (kalibr_b200.h).  Same class / method names, argument meaning and error behaviour as
 //   aslam::backend::LinearSystemSolver              BE/include/aslam/backend/LinearSystemSolver.hpp:16-109
-//   aslam::backend::LevenbergMarquardtTrustRegionPolicy  BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:37-113
-//   aslam::backend::TrustRegionPolicy               BE/src/TrustRegionPolicy.cpp:28-57
+//   aslam::backend::TrustRegionPolicy subclasses (policy selection only; the schedule lives in lm_state_machine.h)
 //   aslam::backend::Optimizer2 / Optimizer2Options / SolutionReturnValue
 //                                                   BE/src/Optimizer2.cpp:183-318, Optimizer2Options.hpp:9-41, backend.hpp:14-27
 // (BE = aslam_optimizer/aslam_backend).  Eigen::VectorXd is replaced by std::vector<double>; design variables and
@@ -17,6 +16,7 @@
 #include <vector>
 
 #include "../kalibr_b200.h"
+#include "lm_state_machine.h"
 
 namespace kalibr_b200 {
 namespace backend {
@@ -141,101 +141,36 @@ class B200SvdLinearSystemSolver : public B200SchurLinearSystemSolver {
   kb_svd_solve_result _last{};
 };
 
-// aslam::backend::TrustRegionPolicy (BE/include/aslam/backend/TrustRegionPolicy.hpp, BE/src/TrustRegionPolicy.cpp:28-57)
+// Trust-region policies.  In the reference these classes carry the lambda schedule themselves
+// (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:50-113, BE/src/GaussNewtonTrustRegionPolicy.cpp:18-40, BE/src/TrustRegionPolicy.cpp:28-57);
+// here they only SELECT a policy and hold its options: the transitions live once, in lm_state_machine.h, for host and device.
 class TrustRegionPolicy {
  public:
   virtual ~TrustRegionPolicy() {}
   virtual std::string name() const = 0;
+  virtual int kind() const = 0;  // KB_POLICY_*
   virtual bool requiresAugmentedDiagonal() const = 0;
   virtual bool revertOnFailure() const = 0;
-  virtual void optimizationStarting(double J) = 0;
-  virtual bool solveSystem(double J, bool previousIterationFailed, int nThreads, std::vector<double>& outDx) = 0;
-  virtual double lambda() const { return 0.0; }
-  virtual double mu() const { return 0.0; }
-  void setSolver(std::shared_ptr<LinearSystemSolver> s) { _solver = s; }
-
- protected:
-  std::shared_ptr<LinearSystemSolver> _solver;
+  virtual double lambdaInit() const { return 0.0; }
 };
-
-// BE/src/GaussNewtonTrustRegionPolicy.cpp:18-40: rebuild and solve every iteration, no conditioner, never revert
 class GaussNewtonTrustRegionPolicy : public TrustRegionPolicy {
  public:
   std::string name() const override { return "gauss_newton"; }
+  int kind() const override { return KB_POLICY_GAUSS_NEWTON; }
   bool requiresAugmentedDiagonal() const override { return false; }
   bool revertOnFailure() const override { return false; }
-  void optimizationStarting(double /*J*/) override {}
-  bool solveSystem(double /*J*/, bool /*previousIterationFailed*/, int nThreads, std::vector<double>& outDx) override {
-    _solver->buildSystem(nThreads, true);
-    return _solver->solveSystem(outDx);
-  }
 };
-
-// LevenbergMarquardtTrustRegionPolicy.cpp:37-113
 class LevenbergMarquardtTrustRegionPolicy : public TrustRegionPolicy {
  public:
   explicit LevenbergMarquardtTrustRegionPolicy(double lambdaInit = 1e-3) : _lambdaInit(lambdaInit) {}
   std::string name() const override { return "levenberg_marquardt"; }
+  int kind() const override { return KB_POLICY_LEVENBERG_MARQUARDT; }
   bool requiresAugmentedDiagonal() const override { return true; }
   bool revertOnFailure() const override { return true; }
-  void optimizationStarting(double J) override {
-    _J = _p_J = _last_successful_J = J;
-    _isFirstIteration = true;
-    _lambda = _lambdaInit;
-    _gamma = _gammaInit;
-    _beta = _betaInit;
-    _p = _pInit;
-    _mu = _muInit;
-  }
-  bool solveSystem(double J, bool previousIterationFailed, int nThreads, std::vector<double>& outDx) override {
-    if (previousIterationFailed) {
-      _J = J;
-    } else {
-      _p_J = _last_successful_J;
-      _last_successful_J = J;
-      _J = J;
-    }
-    if (_isFirstIteration) {
-      _solver->buildSystem(nThreads, true);
-    } else {
-      const double rho = getLmRho();
-      if (previousIterationFailed) {
-        _mu *= 2;
-        _lambda *= _mu;
-      } else if (rho <= 0) {
-        _mu *= 10;
-        _lambda *= _mu;
-      } else {
-        _solver->buildSystem(nThreads, true);
-        if (_lambda > 1e-16) {
-          const double u1 = 1 / _gamma;
-          const double u2 = 1 - (_beta - 1) * std::pow((2 * rho - 1), _p);
-          _lambda *= (u1 > u2) ? u1 : u2;
-          _mu = _beta;
-        } else {
-          _lambda = 1e-15;
-        }
-      }
-    }
-    _solver->setConstantConditioner(_lambda);
-    const bool success = _solver->solveSystem(_dx);
-    outDx = _dx;
-    _isFirstIteration = false;
-    return success;
-  }
-  double get_dJ() const { return _p_J - _J; }
-  double getLmRho() { return get_dJ() / _solver->lmRhoDenominator(_lambda, _dx); }
-  double lambda() const override { return _lambda; }
-  double mu() const override { return _mu; }
+  double lambdaInit() const override { return _lambdaInit; }
 
  private:
-  double _lambdaInit, _gammaInit = 3, _betaInit = 2, _muInit = 2;
-  int _pInit = 3;
-  double _lambda = 0, _gamma = 0, _beta = 0, _mu = 0;
-  int _p = 0;
-  double _J = 0, _p_J = 0, _last_successful_J = 0;
-  bool _isFirstIteration = true;
-  std::vector<double> _dx;
+  double _lambdaInit;
 };
 
 struct Optimizer2Options {  // Optimizer2Options.hpp:9-41 with kalibr2's values (CalibrationTools.hpp:57-66) as defaults
@@ -248,84 +183,69 @@ struct Optimizer2Options {  // Optimizer2Options.hpp:9-41 with kalibr2's values 
   std::shared_ptr<TrustRegionPolicy> trustRegionPolicy;
 };
 
+// Host driver of the state machine over a LinearSystemSolver: the same three events per iteration the device-resident loop runs
+// in its control kernels (kb_kernels.cu), with the solver's virtual calls in between.  ≙ Optimizer2::optimize (BE/src/Optimizer2.cpp:183-273)
 class Optimizer2 {
  public:
   explicit Optimizer2(const Optimizer2Options& options) : _options(options) {}
   Optimizer2Options& options() { return _options; }
-  double J() const { return _J; }
+  double J() const { return _state.J; }
   const std::vector<double>& dx() const { return _dx; }
   const std::vector<double>& trace() const { return _trace; }  // (J, deltaX, lambda) per iteration
+  const LmState& state() const { return _state; }
 
-  // Optimizer2.cpp:183-273
   SolutionReturnValue optimize() {
     if (!_options.linearSystemSolver) throw std::runtime_error("kalibr_b200::Optimizer2: a B200 linear system solver must be set (no CPU fallback)");
-    _solver = _options.linearSystemSolver;
-    _trustRegionPolicy = _options.trustRegionPolicy ? _options.trustRegionPolicy : std::shared_ptr<TrustRegionPolicy>(std::make_shared<LevenbergMarquardtTrustRegionPolicy>());
-    SolutionReturnValue srv;
+    LinearSystemSolver& solver = *_options.linearSystemSolver;
+    std::shared_ptr<TrustRegionPolicy> policy =
+        _options.trustRegionPolicy ? _options.trustRegionPolicy : std::shared_ptr<TrustRegionPolicy>(std::make_shared<LevenbergMarquardtTrustRegionPolicy>());
     _trace.clear();
-    _p_J = 0.0;
-    evaluateError(true);
-    _p_J = _J;
-    srv.JStart = _p_J;
-    if (_options.verbose) std::printf("[0.0]: J: %.10g\n", _J);
-    double deltaX = _options.convergenceDeltaX + 1.0;
-    double deltaJ = _options.convergenceDeltaJ + 1.0;
-    bool previousIterationFailed = false;
-    bool linearSolverFailure = false;
-    _trustRegionPolicy->setSolver(_solver);
-    _trustRegionPolicy->optimizationStarting(_J);
-    while (srv.iterations < _options.maxIterations && srv.failedIterations < _options.maxIterations &&
-           ((deltaX > _options.convergenceDeltaX && std::fabs(deltaJ) > _options.convergenceDeltaJ) || linearSolverFailure)) {
-      const bool solutionSuccess = _trustRegionPolicy->solveSystem(_J, previousIterationFailed, _options.nThreads, _dx);
-      if (!solutionSuccess) {
+    const double J0 = solver.evaluateError(_options.nThreads, true);
+    LmState& c = _state;
+    // semantic 1: the host-driven solver keeps its own lambda^2 / lambda residual (kb_solve_system), the machine's copy is unused
+    lm_start(&c, policy->kind(), J0, policy->lambdaInit(), _options.convergenceDeltaX, _options.convergenceDeltaJ, _options.maxIterations, 1);
+    if (_options.verbose) std::printf("[0.0]: J: %.10g\n", J0);
+    while (!c.done) {
+      lm_before_solve(&c);
+      if (c.need_build) solver.buildSystem(_options.nThreads, true);
+      if (policy->requiresAugmentedDiagonal()) solver.setConstantConditioner(c.lambda);
+      const bool ok = solver.solveSystem(_dx);
+      // dx^T (lambda dx + rhs) of THIS solve: what getLmRho reads at the next iteration, before any rebuild
+      const double rho_den = ok && policy->kind() == KB_POLICY_LEVENBERG_MARQUARDT ? solver.lmRhoDenominator(c.lambda, _dx) : 1.0;
+      if (!ok) {
         if (_options.verbose) std::printf("[WARNING] System solution failed\n");
-        previousIterationFailed = true;
-        linearSolverFailure = true;
-        srv.failedIterations++;
-      } else {
-        deltaX = _solver->applyStateUpdate(_dx);
-        evaluateError(true);
-        deltaJ = _p_J - _J;
-        if (_trustRegionPolicy->revertOnFailure()) {
-          if (deltaJ < 0.0) {
-            if (_options.verbose) std::printf("Last step was a regression. Reverting\n");
-            _solver->revertLastStateUpdate();
-            srv.failedIterations++;
-            previousIterationFailed = true;
-          } else {
-            _p_J = _J;
-            previousIterationFailed = false;
-          }
-        } else {
-          _p_J = _J;
-        }
-        srv.iterations++;
-        _trace.push_back(_J);
-        _trace.push_back(deltaX);
-        _trace.push_back(_trustRegionPolicy->lambda());
-        if (_options.verbose)
-          std::printf("[%d]: J: %.10g, dJ: %.6g, deltaX: %.6g, LM - lambda:%.6g mu:%.6g\n", srv.iterations, _J, deltaJ, deltaX,
-                      _trustRegionPolicy->lambda(), _trustRegionPolicy->mu());
+        lm_after_solve(&c, rho_den, 0.0, 0);
+        continue;
       }
+      const double max_dx = solver.applyStateUpdate(_dx);
+      lm_after_solve(&c, rho_den, max_dx, 1);
+      const double J = solver.evaluateError(_options.nThreads, true);
+      lm_after_eval(&c, J);
+      if (c.revert) {
+        if (_options.verbose) std::printf("Last step was a regression. Reverting\n");
+        solver.revertLastStateUpdate();
+      }
+      _trace.push_back(c.J);
+      _trace.push_back(c.deltaX);
+      _trace.push_back(c.lambda);
+      if (_options.verbose)
+        std::printf("[%d]: J: %.10g, dJ: %.6g, deltaX: %.6g, %s - lambda:%.6g mu:%.6g\n", c.iterations, c.J, c.deltaJ, c.deltaX, policy->name().c_str(), c.lambda, c.mu);
     }
-    srv.JFinal = _p_J;
-    srv.dXFinal = deltaX;
-    srv.dJFinal = deltaJ;
-    srv.linearSolverFailure = linearSolverFailure;
+    SolutionReturnValue srv;
+    srv.JStart = c.JStart;
+    srv.JFinal = c.pJ;
+    srv.iterations = c.iterations;
+    srv.failedIterations = c.failed;
+    srv.dXFinal = c.deltaX;
+    srv.dJFinal = c.deltaJ;
+    srv.linearSolverFailure = c.solver_failure != 0;
     return srv;
-  }
-
-  double evaluateError(bool useMEstimator) {  // Optimizer2.cpp:327-332
-    _J = _solver->evaluateError(_options.nThreads, useMEstimator);
-    return _J;
   }
 
  private:
   Optimizer2Options _options;
-  std::shared_ptr<LinearSystemSolver> _solver;
-  std::shared_ptr<TrustRegionPolicy> _trustRegionPolicy;
+  LmState _state{};
   std::vector<double> _dx, _trace;
-  double _J = 0, _p_J = 0;
 };
 
 }  // namespace backend

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
     "kb_set_inv_r", "kb_get_sqrt_inv_r", "kb_set_m_estimator", "kb_m_estimator_parameter", "kb_reprojection_statistics",
+    "kb_set_state", "kb_set_camera_params", "kb_set_baselines", "kb_set_set_poses", "kb_set_conditioner",
     "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics", "kb_default_svd_solver_options", "kb_solve_system_svd", "kb_optimize_gauss_newton", "kb_analyze_marginal_last_build", "kb_get_last_svd_solve",
 ]
 
@@ -88,6 +89,11 @@ def load_library() -> C.CDLL:
     L.kb_get_camera_params.argtypes = [vp, vp]
     L.kb_get_baselines.argtypes = [vp, vp]
     L.kb_get_set_poses.argtypes = [vp, vp]
+    L.kb_set_state.argtypes = [vp, vp, vp, vp]
+    L.kb_set_camera_params.argtypes = [vp, vp]
+    L.kb_set_baselines.argtypes = [vp, vp]
+    L.kb_set_set_poses.argtypes = [vp, vp]
+    L.kb_set_conditioner.argtypes = [vp, vp]
     L.kb_set_observations.argtypes = [vp, vp, vp]
     L.kb_evaluate_error_streamed.argtypes = [vp, vp, vp, C.c_int32, vp]
     L.kb_prefetch_observations.argtypes = [vp, vp, vp]
@@ -373,6 +379,15 @@ class B200SchurLinearSystemSolver:
         out = np.zeros((self.problem.n_sets, 7))
         self._check(self._L.kb_get_set_poses(self._h, _p(out)), "kb_get_set_poses")
         return out
+
+    def set_state(self, cam_params=None, baselines=None, set_poses=None):
+        """≙ DesignVariable::setParameters for every design variable: the host's values replace the device state."""
+        a = [None if x is None else np.ascontiguousarray(x, np.float64) for x in (cam_params, baselines, set_poses)]
+        self._check(self._L.kb_set_state(self._h, _p(a[0]), _p(a[1]), _p(a[2])), "kb_set_state")
+
+    def set_conditioner(self, diag):
+        d = np.ascontiguousarray(diag, np.float64)
+        self._check(self._L.kb_set_conditioner(self._h, _p(d)), "kb_set_conditioner")
 
     def set_observations(self, y_u: np.ndarray, y_v: np.ndarray):
         self._check(self._L.kb_set_observations(self._h, _p(y_u), _p(y_v)), "kb_set_observations")

@@ -6,6 +6,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../../include/kalibr_b200/lm_state_machine.h"
+
 namespace kb {
 
 enum : int { PINHOLE_RADTAN = 0, PINHOLE_EQUI = 1, OMNI_RADTAN = 2, EUCM_NONE = 3, DS_NONE = 4, PINHOLE_FOV = 5, OMNI_NONE = 6, NUM_MODELS = 7 };  // = kb_camera_model
@@ -24,31 +26,11 @@ constexpr int SETPREP_STRIDE = 48;                 // per set: C^-1 (9), -C^-1 t
 //   tile (0,0): G[0:8][0:8]  (pose x pose, pose x first two intrinsics)      tile (0,1): G[0:8][8:16]  (pose x remaining intrinsics, pose x e)
 constexpr int VB_STRIDE = 128;
 
-// Control block of the device-resident Levenberg-Marquardt loop (kb_optimize): the optimiser / trust-region state of
-// Optimizer2 + LevenbergMarquardtTrustRegionPolicy and the flags that make an enqueued kernel a no-op when the iteration it
-// belongs to does not need it.  In the call-by-call API (kb_evaluate_error, kb_build_system, ...) the flags stay neutral
-// (done = 0, need_build = 1, skip_eval = 0, revert = 0) and the scalar parameters travel as kernel arguments.
-struct LmCtrl {
-  // flags read by the kernels
-  int done;        // the loop has ended: everything still enqueued exits at once
-  int need_build;  // this iteration rebuilds the normal equations (first iteration, or the last step was accepted with rho > 0)
-  int skip_eval;   // the solve failed (not positive definite): no update, no evaluation this iteration
-  int revert;      // the step was a regression: restore the backup of the design variables
-  // parameters read by the kernels when their argument is negative
-  double damping;  // added to every diagonal entry of H for this solve (residual + lambda^2)
-  double lambda;
-  // results written by kernels
-  double cost_new;  // cost of the trial state
-  // Optimizer2 state (BE/src/Optimizer2.cpp:183-273)
-  double J, pJ, deltaX, deltaJ, JStart;
-  int iterations, failed, prev_failed, solver_failure;
-  // LevenbergMarquardtTrustRegionPolicy state (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:37-113)
-  double mu, gamma, beta, polJ, pol_pJ, pol_lastJ, rho_den, max_dx;
-  int p_exp, first;
-  // solver state / options
-  double diag_residual, conv_dx, conv_dj;
-  int semantic, max_iterations;
-};
+// Control block of the device-resident Levenberg-Marquardt loop (kb_optimize): the optimiser / trust-region state machine of
+// include/kalibr_b200/lm_state_machine.h (shared with the host mirror) and the flags that make an enqueued kernel a no-op when
+// the iteration it belongs to does not need it.  In the call-by-call API (kb_evaluate_error, kb_build_system, ...) the flags stay
+// neutral (done = 0, need_build = 1, skip_eval = 0, revert = 0) and the scalar parameters travel as kernel arguments.
+using LmCtrl = kalibr_b200::LmState;
 
 // Peer exchange over NVLink (multi-rank, one process per GPU, kb_attach_peers): every rank maps the exchange buffer of every
 // other rank (CUDA IPC) and the producing kernel of each exchange step stores its contribution straight into the slot it owns

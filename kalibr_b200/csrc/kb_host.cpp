@@ -267,6 +267,7 @@ void build_dv_layout(kb_handle* h) {
   };
   if (h->driver_order == KB_ORDER_SINGLE) { intr(0); sets(); }
   else if (h->driver_order == KB_ORDER_STEREO) { base(); sets(); intr(0); intr(1); }
+  else if (h->driver_order == KB_ORDER_BATCH) { sets(); base(); for (int k = 0; k < h->n_cams; ++k) intr(k); }
   else { for (int k = 0; k < h->n_cams; ++k) intr(k); base(); sets(); }
   h->dv_col.resize(h->dv_dim.size());
   int c = 0;
@@ -342,7 +343,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   if (!d || !out) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "null argument");
   *out = nullptr;
   if (d->n_cams < 1 || d->n_cams > MAX_CAMS) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "n_cams out of range (1..32)");
-  if (d->driver_order < 0 || d->driver_order > 2) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "unknown driver order");
+  if (d->driver_order < 0 || d->driver_order > KB_ORDER_BATCH) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "unknown driver order");
   if (d->driver_order == KB_ORDER_SINGLE && d->n_cams != 1) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "single-camera order needs one camera");
   if (d->driver_order == KB_ORDER_STEREO && d->n_cams != 2) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "stereo order needs two cameras");
   if (d->n_target_points < 1 || d->n_target_points > 65535) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "n_target_points out of range");
@@ -1734,21 +1735,8 @@ static kb_status optimize_on_device(kb_handle* h, const kb_optimizer_options* o,
   if (h->trace_dev.n < (size_t)3 * (max_it + 1)) KB_CUDA(h, h->trace_dev.alloc((size_t)3 * (max_it + 1)));
   LmCtrl c0;
   std::memset(&c0, 0, sizeof(c0));
-  c0.need_build = 1;
-  c0.lambda = o->lm_lambda_init;
-  c0.J = c0.pJ = c0.JStart = J0;
-  c0.deltaX = o->convergence_delta_x + 1.0;
-  c0.deltaJ = o->convergence_delta_j + 1.0;
-  c0.mu = 2.0; c0.gamma = 3.0; c0.beta = 2.0; c0.p_exp = 3;  // LevenbergMarquardtTrustRegionPolicy.cpp:37-48
-  c0.polJ = c0.pol_pJ = c0.pol_lastJ = J0;
-  c0.first = 1;
-  c0.rho_den = 1.0;
-  c0.diag_residual = 0.0;
-  c0.conv_dx = o->convergence_delta_x;
-  c0.conv_dj = o->convergence_delta_j;
-  c0.semantic = h->semantic;
-  c0.max_iterations = max_it;
-  c0.done = max_it <= 0 ? 1 : 0;
+  kalibr_b200::lm_start(&c0, kalibr_b200::KB_POLICY_LEVENBERG_MARQUARDT, J0, o->lm_lambda_init, o->convergence_delta_x, o->convergence_delta_j, max_it,
+                        h->semantic);
   KB_CUDA(h, cudaMemcpyAsync(h->ctrl.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));  // pageable source: staged at the call
   *h->h_ctrl = c0;
   // iterations are enqueued two at a time; the host only reads the control block back to see whether the loop has ended.
@@ -2072,6 +2060,40 @@ kb_status kb_get_hessian_blocks(kb_handle* h, int64_t* n_blocks, int64_t* n_valu
   }
   col_ptr[n_dv] = bi;
   return KB_OK;
+}
+
+// ---- state setters: the design variables live on the host when an unmodified Optimizer2 drives the solver ------------------
+kb_status kb_set_state(kb_handle* h, const double* cam_params, const double* baselines, const double* set_poses) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  if (cam_params)
+    KB_CUDA(h, cudaMemcpyAsync(h->cam_params.p, cam_params, sizeof(double) * h->cam_params.n, cudaMemcpyHostToDevice, h->stream));
+  if (baselines && h->baselines.n)
+    KB_CUDA(h, cudaMemcpyAsync(h->baselines.p, baselines, sizeof(double) * h->baselines.n, cudaMemcpyHostToDevice, h->stream));
+  if (set_poses && h->set_poses.n)
+    KB_CUDA(h, cudaMemcpyAsync(h->set_poses.p, set_poses + (h->presharded ? 0 : (size_t)KB_POSE_STRIDE * h->set_lo), sizeof(double) * h->set_poses.n,
+                               cudaMemcpyHostToDevice, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));  // the caller's arrays may be pageable and may change right after the call
+  ++h->state_version;     // any cached (speculative) linearisation belongs to the old state
+  h->has_backup = false;  // the device-side backup belongs to the old state: reverting is the host's business now
+  return KB_OK;
+}
+kb_status kb_set_camera_params(kb_handle* h, const double* cam_params) {
+  if (!cam_params) return fail(h, KB_ERR_INVALID_ARGUMENT, "null camera parameters");
+  return kb_set_state(h, cam_params, nullptr, nullptr);
+}
+kb_status kb_set_baselines(kb_handle* h, const double* baselines) {
+  if (!baselines && h->n_cams > 1) return fail(h, KB_ERR_INVALID_ARGUMENT, "null baselines");
+  return kb_set_state(h, nullptr, baselines, nullptr);
+}
+kb_status kb_set_set_poses(kb_handle* h, const double* set_poses) {
+  if (!set_poses && h->set_poses.n) return fail(h, KB_ERR_INVALID_ARGUMENT, "null set poses");
+  return kb_set_state(h, nullptr, nullptr, set_poses);
+}
+kb_status kb_set_conditioner(kb_handle* h, const double* diag) {
+  if (!diag) return fail(h, KB_ERR_INVALID_ARGUMENT, "null conditioner");
+  for (int64_t i = 1; i < h->jcols; ++i)
+    if (diag[i] != diag[0]) return fail(h, KB_ERR_INVALID_ARGUMENT, "only a constant diagonal conditioner is supported (every trust-region policy of the reference installs a constant one)");
+  return kb_set_constant_conditioner(h, h->jcols > 0 ? diag[0] : 0.0);
 }
 
 kb_status kb_get_camera_params(kb_handle* h, double* out) {

@@ -1897,53 +1897,10 @@ __global__ void __launch_bounds__(256) apply_update_kernel(DevProblem p, const i
 // Optimizer2::optimize (BE/src/Optimizer2.cpp:215-266) and LevenbergMarquardtTrustRegionPolicy::solveSystemImplementation
 // (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:50-113), so that no host round trip sits inside an iteration.
 // =========================================================================================================
-__device__ __forceinline__ void lm_check_loop(LmCtrl* c) {  // the while condition of Optimizer2.cpp:215-219
-  const bool go = c->iterations < c->max_iterations && c->failed < c->max_iterations &&
-                  ((c->deltaX > c->conv_dx && fabs(c->deltaJ) > c->conv_dj) || c->solver_failure);
-  if (!go) c->done = 1;
-}
-
 // before the solve: TrustRegionPolicy::solveSystem bookkeeping, rho, the lambda schedule, build / no build, damping
 __global__ void lm_pre_solve_kernel(LmCtrl* c, int* pos_def) {
   if (c->done) return;
-  const double J = c->J;
-  if (c->prev_failed) {
-    c->polJ = J;
-  } else {
-    c->pol_pJ = c->pol_lastJ;
-    c->pol_lastJ = J;
-    c->polJ = J;
-  }
-  int build = 0;
-  double lambda = c->lambda;
-  if (c->first) {
-    build = 1;
-  } else {
-    const double rho = (c->pol_pJ - c->polJ) / c->rho_den;
-    if (c->prev_failed) {
-      c->mu *= 2.0;
-      lambda *= c->mu;
-    } else if (rho <= 0.0) {
-      c->mu *= 10.0;
-      lambda *= c->mu;
-    } else {
-      build = 1;
-      if (lambda > 1e-16) {
-        const double u1 = 1.0 / c->gamma;
-        const double u2 = 1.0 - (c->beta - 1.0) * pow(2.0 * rho - 1.0, (double)c->p_exp);
-        lambda *= (u1 > u2) ? u1 : u2;
-        c->mu = c->beta;
-      } else {
-        lambda = 1e-15;
-      }
-    }
-  }
-  c->first = 0;
-  c->lambda = lambda;
-  c->need_build = build;
-  if (build) c->diag_residual = 0.0;  // H.clear(false): BlockCholeskyLinearSystemSolver.cpp:64
-  c->damping = c->diag_residual + lambda * lambda;
-  c->revert = 0;
+  kalibr_b200::lm_before_solve(c);
   pos_def[0] = 1;
 }
 
@@ -1962,39 +1919,17 @@ __global__ void lm_post_solve_kernel(LmCtrl* c, const int* pos_def, const double
       if (rank_slots[4 * r + 2] < 0.5) pd = 0;
     }
   }
-  c->rho_den = rho;
-  c->max_dx = mx;
-  if (c->semantic == 0) c->diag_residual += c->lambda * c->lambda - c->lambda;
-  if (!pd) {  // Optimizer2.cpp:223-229
-    c->prev_failed = 1;
-    c->solver_failure = 1;
-    c->failed += 1;
-    c->skip_eval = 1;
-    lm_check_loop(c);
-  } else {
-    c->skip_eval = 0;
-  }
+  kalibr_b200::lm_after_solve(c, rho, mx, pd);
 }
 
 // after the evaluation of the trial state: accept / reject, trace, loop condition
 __global__ void lm_post_eval_kernel(LmCtrl* c, double* trace) {
   if (c->done || c->skip_eval) return;
-  c->deltaX = c->max_dx;
-  c->J = c->cost_new;
-  c->deltaJ = c->pJ - c->J;
-  if (c->deltaJ < 0.0) {  // regression: revert (Optimizer2.cpp:241-249)
-    c->revert = 1;
-    c->failed += 1;
-    c->prev_failed = 1;
-  } else {
-    c->pJ = c->J;
-    c->prev_failed = 0;
-  }
-  trace[3 * c->iterations] = c->J;
-  trace[3 * c->iterations + 1] = c->deltaX;
-  trace[3 * c->iterations + 2] = c->lambda;
-  c->iterations += 1;
-  lm_check_loop(c);
+  const int it = c->iterations;
+  kalibr_b200::lm_after_eval(c, c->cost_new);
+  trace[3 * it] = c->J;
+  trace[3 * it + 1] = c->deltaX;
+  trace[3 * it + 2] = c->lambda;
 }
 
 // restore the backup when the step was rejected (idempotent: a finished loop may run it again with the same flag)

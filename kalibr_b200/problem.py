@@ -17,7 +17,7 @@ MODEL_P = [4, 4, 5, 6, 6, 4, 5]  # projection parameters
 MODEL_D = [4, 4, 4, 0, 0, 1, 0]  # distortion parameters (0-dim distortion DV stays active: SURVEY.md Q7)
 
 # kb_driver_order
-ORDER_SINGLE, ORDER_STEREO, ORDER_RIG = range(3)
+ORDER_SINGLE, ORDER_STEREO, ORDER_RIG, ORDER_BATCH = range(4)
 
 CAM_PARAM_STRIDE = 10
 POSE_STRIDE = 7
@@ -224,6 +224,11 @@ class Problem:
             sets()
             intr(0)
             intr(1)
+        elif self.driver_order == ORDER_BATCH:
+            sets()
+            base()
+            for k in range(self.n_cams):
+                intr(k)
         else:
             for k in range(self.n_cams):
                 intr(k)

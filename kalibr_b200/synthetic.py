@@ -16,6 +16,7 @@ from .problem import (
     MODEL_P,
     OMNI_NONE,
     OMNI_RADTAN,
+    ORDER_BATCH,
     ORDER_RIG,
     ORDER_SINGLE,
     ORDER_STEREO,
@@ -187,6 +188,8 @@ CONFIGS = {
     # not a BASELINE config: the two remaining rows of kalibr2::CreateCalibrator's model table next to a pinhole-radtan camera
     6: (ORDER_RIG, [PINHOLE_FOV, OMNI_NONE, PINHOLE_RADTAN], 1000),
     7: (ORDER_STEREO, [OMNI_NONE, PINHOLE_FOV], 1000),
+    # the design-variable order of the incremental estimator's merged problem (CreateBatchProblem: set poses, baselines, intrinsics)
+    8: (ORDER_BATCH, [PINHOLE_RADTAN, OMNI_RADTAN, PINHOLE_EQUI], 1000),
 }
 
 

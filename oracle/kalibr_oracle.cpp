@@ -171,6 +171,13 @@ struct Problem {
         addBaselines();
         addSets();
         break;
+      case KB_ORDER_BATCH:  // the incremental estimator's merged problem: CalibrationTools.hpp:460-491 (groups 1, 0, 2 by first appearance,
+                            // IncrementalOptimizationProblem.cpp:186-223), marginalised group 0 moved last (IncrementalEstimator.cpp:550-565);
+                            // inside group 0 the baselines come before the intrinsics (CalibrationTools.hpp:470-486)
+        addSets();
+        addBaselines();
+        for (int k = 0; k < nCams; ++k) addIntrinsics(k);
+        break;
       default: throw std::runtime_error("unknown driver order");
     }
     // error terms in the caller's (reference insertion) order

@@ -81,3 +81,34 @@ def test_missing_library_fails_loudly(capi, monkeypatch, tmp_path):
     monkeypatch.setattr(capi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(capi.KalibrB200Error, match="no CPU fallback"):
         capi.load_library()
+
+
+@pytest.mark.parametrize("virtual_evaluate", [False, True])
+def test_reference_adapter_compiles_against_the_reference_interface(capi, virtual_evaluate, tmp_path):
+    """include/kalibr_b200/reference_adapter.hpp (the LinearSystemSolver subclass a Kalibr2 maintainer adds) builds warning-free against
+    the stand-in of the reference's plugin headers, in both variants of INTEGRATION.md §2, and refuses to run without a device."""
+    import subprocess
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from driver_util import build_adapter, write_problem
+
+    exe = build_adapter(virtual_evaluate)
+    assert os.path.exists(exe)
+    if os.path.exists("/dev/nvidia0"):
+        return
+    p = synthetic.make_config(1, n_sets=2)
+    path = str(tmp_path / "p.bin")
+    write_problem(path, p, [synthetic.TRUTH_PARAMS[0][1]])
+    r = subprocess.run([exe, path, "0"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stdout  # kb_create inside initMatrixStructureImplementation: no CPU fallback
+
+
+def test_state_machine_is_the_single_policy_implementation():
+    """One LM / Gauss-Newton state machine (include/kalibr_b200/lm_state_machine.h) is used by the device control kernels and the host
+    mirror alike: neither kb_kernels.cu nor optimizer.hpp carries its own copy of the lambda schedule."""
+    kern = open(os.path.join(ROOT, "kalibr_b200", "csrc", "kb_kernels.cu")).read()
+    host = open(os.path.join(ROOT, "include", "kalibr_b200", "optimizer.hpp")).read()
+    for text in (kern, host):
+        assert "lm_before_solve" in text and "lm_after_solve" in text and "lm_after_eval" in text
+        assert "mu *= 10" not in text.replace("_mu", "mu") and "pow(" not in text

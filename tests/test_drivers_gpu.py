@@ -10,7 +10,7 @@ from kalibr_b200 import synthetic
 from kalibr_b200.problem import KbOptimizerOptions, Problem
 from oracle import ko_init as ki
 
-from driver_util import run_driver, write_problem
+from driver_util import run_adapter, run_driver, write_problem
 
 pytestmark = pytest.mark.gpu
 IDENT = np.array([0, 0, 0, 1.0, 0, 0, 0])
@@ -163,3 +163,48 @@ def test_incremental_estimator_matches_oracle(oracle_lib, tmp_path, cfg, n_sets,
     assert (np.abs(cams - est.cam_params) / np.maximum(np.abs(est.cam_params), 1e-3)).max() < 1e-6
     base = np.stack([out[f"baseline{j}"] for j in range(p.n_cams - 1)])
     assert np.abs(base - est.baselines).max() < 1e-6
+
+
+# ---- the reference-side adapter under a host optimiser that owns the design variables ------------------------------------------
+# include/kalibr_b200/reference_adapter.hpp compiled against the stand-in of aslam::backend::{LinearSystemSolver, DesignVariable,
+# ErrorTerm} (exact virtual signatures: BE/include/aslam/backend/LinearSystemSolver.hpp:16-109), driven by a host loop in the role
+# of Optimizer2 (state updates / reverts on the HOST, Optimizer2.cpp:290-318).  It must reproduce kb_optimize - same iterations,
+# failed iterations, cost and parameters - in both integration variants of INTEGRATION.md §2.
+@pytest.mark.parametrize("virtual_evaluate", [False, True])
+@pytest.mark.parametrize("cfg,n_sets", [(1, 60), (2, 40), (3, 30), (8, 24)])
+def test_reference_adapter_reproduces_kb_optimize(capi, oracle_lib, tmp_path, cfg, n_sets, virtual_evaluate):
+    p = synthetic.make_config(cfg, n_sets=n_sets)
+    res = [synthetic.TRUTH_PARAMS[int(m)][1] for m in p.cam_model]
+    path = str(tmp_path / "adapter.bin")
+    write_problem(path, p, res)
+    code, out = run_adapter(path, p.driver_order, virtual_evaluate)
+    assert code == 0, out.get("error")
+    g = capi.B200SchurLinearSystemSolver(p)
+    sol, _ = g.optimize(KbOptimizerOptions.kalibr2_default())
+    assert int(out["solution"][0]) == sol.iterations and int(out["solution"][1]) == sol.failed_iterations
+    assert int(out["solution"][2]) == sol.linear_solver_failure
+    assert abs(out["solution"][3] - sol.j_start) <= 1e-12 * sol.j_start
+    assert abs(out["solution"][4] - sol.j_final) <= 1e-9 * sol.j_final
+    gc = g.camera_params()
+    for k in range(p.n_cams):
+        n = len(out[f"camera{k}"])
+        assert (np.abs(out[f"camera{k}"] - gc[k, :n]) / np.maximum(np.abs(gc[k, :n]), 1e-3)).max() < 1e-6
+    gb = g.baselines()
+    for j in range(p.n_cams - 1):
+        assert np.abs(out[f"baseline{j}"] - gb[j]).max() < 1e-6
+    # and the oracle agrees on the iteration count (the chain reference -> oracle -> device -> adapter)
+    os_, _ = oracle_lib.OracleProblem(p).optimize(KbOptimizerOptions.kalibr2_default())
+    assert int(out["solution"][0]) == os_.iterations and int(out["solution"][1]) == os_.failed_iterations
+    assert out["launches"][0] > 0
+
+
+def test_reference_adapter_rejects_a_wrong_design_variable_order(tmp_path):
+    p = synthetic.make_config(3, n_sets=6)
+    res = [synthetic.TRUTH_PARAMS[int(m)][1] for m in p.cam_model]
+    path = str(tmp_path / "adapter.bin")
+    write_problem(path, p, res)
+    code, out = run_adapter(path, 3, False)  # the host optimiser orders the variables as CreateBatchProblem does, the recorder says so too: fine
+    assert code == 0
+    # stereo order announced for a four-camera problem: kb_create refuses
+    code, out = run_adapter(path, 1, False)
+    assert code == 1 and "stereo" in out["error"]

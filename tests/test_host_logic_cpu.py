@@ -3,10 +3,10 @@ import numpy as np
 import pytest
 
 from kalibr_b200 import synthetic
-from kalibr_b200.problem import ORDER_RIG, ORDER_SINGLE, ORDER_STEREO
+from kalibr_b200.problem import ORDER_BATCH, ORDER_RIG, ORDER_SINGLE, ORDER_STEREO
 
 
-@pytest.mark.parametrize("cfg,n_sets", [(1, 5), (2, 4), (3, 3), (4, 2), (5, 2)])
+@pytest.mark.parametrize("cfg,n_sets", [(1, 5), (2, 4), (3, 3), (4, 2), (5, 2), (8, 3)])
 def test_dv_layout_matches_the_oracle_problem_construction(oracle_lib, cfg, n_sets):
     p = synthetic.make_config(cfg, n_sets=n_sets)
     col, dims, labels = p.dv_layout()
@@ -23,6 +23,12 @@ def test_driver_orders():
     p3 = synthetic.make_config(3, n_sets=1)
     assert [l[0] for l in p3.dv_layout()[2]][:8] == ["proj", "dist"] * 4
     assert p1.driver_order == ORDER_SINGLE and p2.driver_order == ORDER_STEREO and p3.driver_order == ORDER_RIG
+    # the incremental estimator's merged problem (CalibrationTools.hpp:460-491 + IncrementalEstimator.cpp:550-565): poses, baselines, intrinsics
+    p8 = synthetic.make_config(8, n_sets=2)
+    assert p8.driver_order == ORDER_BATCH
+    assert [l[0] for l in p8.dv_layout()[2]] == ["set_q", "set_t"] * 2 + ["baseline_q", "baseline_t"] * 2 + ["proj", "dist"] * 3
+    col8, dims8, _ = p8.dv_layout()
+    assert int(col8[4]) == 12 and int(col8[-1] + dims8[-1]) - 12 == p8.n_c  # the calibration block is the last n_c columns
     # term order: stereo lists all camera-0 views first, the rig driver interleaves cameras per set
     assert list(p2.view_cam) == [0, 1]
     assert list(synthetic.make_config(2, n_sets=3).view_cam) == [0, 0, 0, 1, 1, 1]

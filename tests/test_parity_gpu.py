@@ -15,7 +15,7 @@ REL_J = 1e-9   # residuals / Jacobians
 REL_X = 1e-6   # converged parameters
 
 # (config, n_sets): scaled-down versions of the five BASELINE configs that the oracle finishes in seconds
-CASES = [(1, 40), (2, 30), (3, 24), (4, 12), (5, 6), (6, 20), (7, 25)]  # 6, 7: pinhole-fov and omni-none (rig / stereo order)
+CASES = [(1, 40), (2, 30), (3, 24), (4, 12), (5, 6), (6, 20), (7, 25), (8, 18)]  # 6, 7: pinhole-fov and omni-none (rig / stereo order); 8: batch order
 
 
 def rel_err(a, b):
