@@ -451,9 +451,12 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ v,
 constexpr int XT_LD = 68;  // 64 rows (32 terms x 2) + 4: conflict-free for the row stores and the DMMA operand loads
 constexpr int XT_WARP_DOUBLES = GRAM_DIM * XT_LD;
 
-template <int MODEL, bool WEIGHTED>
+// CHECK: *nonfinite is set when any staged Jacobian value of the term is NaN or Inf (value * 0 is then NaN) - the materialising
+// kernel needs to know, because its J = A B product on the tensor pipe would spread such a value over the structural zeros of B.
+template <int MODEL, bool WEIGHTED, bool CHECK = false>
 __device__ __forceinline__ bool term_rows(const DevProblem& p, const double* __restrict__ prm, const double Rcw[9], const double tcw[3],
-                                          const double* __restrict__ pt, double yu, double yv, double* __restrict__ xt_lane, double& e0, double& e1) {
+                                          const double* __restrict__ pt, double yu, double yv, double* __restrict__ xt_lane, double& e0, double& e1,
+                                          bool* nonfinite = nullptr) {
   using Cam = Camera<MODEL, true, true>;  // negated Jacobians: e = y - y_hat
   constexpr int P = Cam::P, D = Cam::D;
   const double pc[3] = {Rcw[0] * pt[0] + Rcw[1] * pt[1] + Rcw[2] * pt[2] + tcw[0], Rcw[3] * pt[0] + Rcw[4] * pt[1] + Rcw[5] * pt[2] + tcw[1],
@@ -480,6 +483,20 @@ __device__ __forceinline__ bool term_rows(const DevProblem& p, const double* __r
 #pragma unroll
       for (int c = 6 + P + D; c < E_COL; ++c) x[c * XT_LD] = 0.0;
       x[E_COL * XT_LD] = r == 0 ? e0 : e1;
+    }
+    if constexpr (CHECK) {
+      double chk = 0.0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) chk = fma(L.Jp[r][c], 0.0, chk);
+#pragma unroll
+        for (int c = 0; c < P; ++c) chk = fma(L.Ji[r][c], 0.0, chk);
+#pragma unroll
+        for (int c = 0; c < D; ++c) chk = fma(L.Jd[r][c], 0.0, chk);
+      }
+      chk = fma(pc[0] + pc[1] + pc[2], 0.0, chk);
+      *nonfinite = chk != chk;
     }
   } else {
     // weighted rows: [u-row; v-row] <- sqrt(w) sqrtInvR^T [u-row; v-row], column by column
@@ -508,6 +525,12 @@ __device__ __forceinline__ bool term_rows(const DevProblem& p, const double* __r
     }
     xt_lane[E_COL * XT_LD] = e0;       // already A e
     xt_lane[E_COL * XT_LD + 32] = e1;
+    if constexpr (CHECK) {
+      double chk = 0.0;
+#pragma unroll
+      for (int c = 0; c < E_COL; ++c) chk = fma(xt_lane[c * XT_LD], 0.0, fma(xt_lane[c * XT_LD + 32], 0.0, chk));
+      *nonfinite = chk != chk;
+    }
   }
   return L.valid;
 }
@@ -690,6 +713,30 @@ constexpr int LM_SUB = 4;  // sub-slices per slice of the fused kernel's slice t
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream2(double* p, double v0, double v1) { __stcs(reinterpret_cast<double2*>(p), make_double2(v0, v1)); }
 
+// A non-finite Jacobian entry must stay in the columns the reference's chain rule puts it in (J_pose = J_xi A, the intrinsics
+// columns are copies): the tensor-pipe product J = A B would multiply it with the structural zeros of B.  Rare (an equidistant
+// corner exactly on the optical axis): the whole 32-term chunk is then written by this scalar routine instead -
+// out of line and with by-value arguments only, so that the hot path's register allocation does not see it.
+__device__ __noinline__ void exact_chunk(const double* __restrict__ XT, const int* __restrict__ desc, const double* __restrict__ sM,
+                                         const double* __restrict__ camA_k, double* __restrict__ dst_chunk, int W, int rows_valid, int lane) {
+  for (int idx = lane; idx < rows_valid * W; idx += 32) {
+    const int row = idx / W, col = idx - row * W;
+    const int pos = 32 * (row & 1) + (row >> 1);  // staged position of (term row / 2, residual row % 2)
+    const int dsc = desc[col];
+    const int kind = dsc >> 16, j = (dsc >> 8) & 0xff, sub = dsc & 0xff;
+    double v = 0.0;
+    if (kind == 2) {
+      v = XT[(6 + sub) * XT_LD + pos];
+    } else if (kind == 0 || kind == 1) {
+      for (int k = 0; k < 6; ++k) {
+        const double bk = kind == 0 ? sM[k * 6 + sub] : __ldg(camA_k + (size_t)j * 36 + k * 6 + sub);
+        v = fma(XT[k * XT_LD + pos], bk, v);
+      }
+    }
+    dst_chunk[(long long)row * W + col] = v;
+  }
+}
+
 template <int MODEL, bool WEIGHTED>
 __global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(DevProblem p, const int4* __restrict__ vmeta, const int4* __restrict__ slices,
                                                                                int slice_lo, int slice_hi, double* __restrict__ jt, int bfrag_pairs,
@@ -795,23 +842,32 @@ __global__ void __launch_bounds__(LM_THREADS, 4) linearise_materialise_kernel(De
         active = i < e;
         ii = active ? i : b;
         if (base + 32 < e) { yu = p.y_u[ii]; yv = p.y_v[ii]; cid = p.corner[ii]; }
+        bool exact_rows = false;  // warp-uniform: some term of the chunk carries a NaN / Inf in its Jacobian
         {
           double e0, e1;
-          const bool valid = term_rows<MODEL, WEIGHTED>(p, prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, XT + lane, e0, e1);
+          bool nonfinite = false;
+          const bool valid = term_rows<MODEL, WEIGHTED, true>(p, prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, XT + lane, e0, e1, &nonfinite);
           if (cactive && !valid) atomicAdd(p.n_invalid, 1u);
           if (__any_sync(0xffffffffu, cactive && !valid)) {
             if (cactive && !valid) {
               zero_rows(XT + lane);
               e0 = 0.0;
               e1 = 0.0;
+              nonfinite = false;
             }
           }
+          exact_rows = __any_sync(0xffffffffu, cactive && nonfinite);
           if (cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-e0, -e1);
         }
         __syncwarp();
         const int rows_valid = 2 * min(32, e - base);
         const int mtiles = (rows_valid + 7) >> 3;
         double* __restrict__ dst_chunk = dst_view + (long long)(base - b) * 2 * W;
+        if (exact_rows) {
+          exact_chunk(XT, desc, sM, p.camA + (size_t)cam * p.n_cams * 36, dst_chunk, W, rows_valid, lane);
+          __syncwarp();
+          continue;
+        }
         for (int mt = 0; mt < mtiles; ++mt) {
           double a[4];
 #pragma unroll
@@ -1538,25 +1594,234 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
 }
 
 // =========================================================================================================
-// marginal analysis: singular values and right singular vectors of the (symmetric, positive semi-definite) reduced camera
-// system — the calibration block's information matrix with the set poses marginalised out — by a one-sided (Hestenes)
-// Jacobi iteration.               ≙ analyzeSVD (Eigen::JacobiSVD of Omega), aslam_incremental_calibration/.../linalg.cpp:409-425
-// One CTA; the columns of G = S and of V = I live in global memory (column-major, L1/L2-resident: n <= 223).  A sweep is
-// n - 1 round-robin steps of n / 2 disjoint column pairs; a warp takes a pair: three dot products, then the plane rotation
-// that makes the two columns orthogonal, applied to G and V.  Converged when a whole sweep rotates nothing; the column norms
-// are the singular values, the columns of V the singular vectors; both are written sorted by descending singular value.
+// Symmetric eigen-decomposition of the reduced camera system (the calibration block's information matrix with the set poses
+// marginalised out).                 ≙ analyzeSVD (Eigen::JacobiSVD of Omega), aslam_incremental_calibration/.../linalg.cpp:409-425
+// Two kernels, one CTA each:
+//   sym_eig_kernel       Householder tridiagonalisation + implicit-shift QL.  Absolutely accurate (errors ~ eps |S|): all the
+//                        column-SCALED solve of every Gauss-Newton iteration needs (its tolerance is 1e-6 n sv_0).
+//   jacobi_polish_kernel one-sided (Hestenes) Jacobi sweeps on G = S V started from the QL vectors: restores the RELATIVE accuracy
+//                        of the small singular values of the unscaled, graded system (they span 12 decades; the marginal analysis
+//                        sums their logarithms).  From the QL start it needs 1-2 rotating sweeps instead of 17-21 from the identity.
 // =========================================================================================================
 constexpr int EIG_THREADS = 1024;
-__global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem p, double* __restrict__ G_glob, double* __restrict__ V_glob,
-                                                                      double* __restrict__ sv_out, double* __restrict__ V_out, int* __restrict__ sweeps_out,
-                                                                      int use_smem) {
+constexpr int EIG_MAX_N = 256;
+__device__ __forceinline__ double eig_block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < EIG_THREADS / 32; ++i) s += red[i];  // fixed order, identical in every thread
+  return s;
+}
+
+// status_out[0]: 0 = converged, 1 = a QL iteration did not converge.  sv_out: |eigenvalues| sorted descending; V_out: [n][n] row-major,
+// column k = eigenvector of sv_out[k].  A_glob / Z_glob: scratch of n * (n | 1) doubles each, used when the matrices do not fit in
+// shared memory (n > 114).
+__global__ void __launch_bounds__(EIG_THREADS, 1) sym_eig_kernel(DevProblem p, double* __restrict__ A_glob, double* __restrict__ Z_glob,
+                                                                  double* __restrict__ sv_out, double* __restrict__ V_out, int* __restrict__ status_out,
+                                                                  int use_smem) {
   extern __shared__ __align__(16) double eig_smem[];
-  __shared__ double s_sigma[256];
-  __shared__ int s_perm[256];
+  __shared__ double red[EIG_THREADS / 32];
+  __shared__ double v[EIG_MAX_N], w[EIG_MAX_N], d[EIG_MAX_N], e[EIG_MAX_N];
+  __shared__ double cs[2][EIG_MAX_N], sn[2][EIG_MAX_N];
+  __shared__ int s_m[2], s_lo[2], s_has[2], s_done[2], s_fail[2];  // per buffer: a round only reads what the previous round wrote
+  __shared__ int s_perm[EIG_MAX_N];
+  const int n = p.n_c, na = p.n_aug;
+  const int ld = n | 1;  // odd leading dimension: conflict-free rows and columns
+  double* __restrict__ A = use_smem ? eig_smem : A_glob;
+  double* __restrict__ Z = use_smem ? eig_smem + (size_t)n * ld : Z_glob;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = EIG_THREADS / 32;
+  for (int idx = tid; idx < n * n; idx += EIG_THREADS) {
+    const int r = idx / n, c = idx - r * n;
+    A[r * ld + c] = p.Sred[(size_t)r * na + c];
+    Z[r * ld + c] = (r == c) ? 1.0 : 0.0;
+  }
+  if (tid < EIG_MAX_N) e[tid] = 0.0;
+  __syncthreads();
+  // ---- Householder tridiagonalisation: H_k zeroes A[k+2.., k]; Z <- Z H_k ----
+  for (int k = 0; k + 2 < n; ++k) {
+    double part = 0.0;
+    for (int i = k + 1 + tid; i < n; i += EIG_THREADS) part += A[i * ld + k] * A[i * ld + k];
+    const double norm2 = eig_block_sum(part, red);
+    const double x0 = A[(k + 1) * ld + k];
+    if (norm2 == 0.0) continue;  // uniform: the column is already reduced (e[k] stays 0 = A[k+1][k])
+    const double norm = sqrt(norm2);
+    const double alpha = x0 >= 0.0 ? -norm : norm;
+    const double vn2 = 2.0 * norm * (norm + fabs(x0));  // |x - alpha e_1|^2 without a second reduction
+    const double ivn = rsqrt(vn2);
+    for (int i = k + 1 + tid; i < n; i += EIG_THREADS) v[i] = (A[i * ld + k] - (i == k + 1 ? alpha : 0.0)) * ivn;
+    __syncthreads();
+    // p = A_sub v (a warp per row) and, in the same phase, Z <- Z (I - 2 v v^T) (a warp per row of Z)
+    part = 0.0;
+    for (int j = k + 1 + warp; j < n; j += NW) {
+      double t = 0.0;
+      for (int i = k + 1 + lane; i < n; i += 32) t += A[j * ld + i] * v[i];
+      t = warp_sum(t);
+      if (lane == 0) {
+        w[j] = t;
+        part += v[j] * t;
+      }
+    }
+    for (int r = warp; r < n; r += NW) {
+      double t = 0.0;
+      for (int i = k + 1 + lane; i < n; i += 32) t += Z[r * ld + i] * v[i];
+      t = 2.0 * warp_sum(t);
+      for (int i = k + 1 + lane; i < n; i += 32) Z[r * ld + i] -= t * v[i];
+    }
+    const double K = eig_block_sum(part, red);
+    for (int j = k + 1 + tid; j < n; j += EIG_THREADS) w[j] = 2.0 * (w[j] - K * v[j]);
+    if (tid == 0) e[k] = alpha;
+    __syncthreads();
+    const int m = n - k - 1;
+    for (int idx = tid; idx < m * m; idx += EIG_THREADS) {
+      const int j = k + 1 + idx / m, i = k + 1 + idx - (idx / m) * m;
+      A[j * ld + i] -= v[j] * w[i] + w[j] * v[i];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += EIG_THREADS) d[i] = A[i * ld + i];
+  if (tid == 0) {
+    if (n >= 2) e[n - 2] = A[(n - 1) * ld + n - 2];
+    s_fail[0] = s_fail[1] = 0;
+    s_done[0] = s_done[1] = 0;
+    s_has[0] = s_has[1] = 0;
+  }
+  // transpose Z in place: from now on Z[i * ld + k] = component k of basis vector i, so that the rotation of the vector pair (i, i + 1)
+  // is a coalesced, conflict-free sweep over k
+  for (int idx = tid; idx < n * n; idx += EIG_THREADS) {
+    const int r = idx / n, c = idx - r * n;
+    if (r < c) {
+      const double t = Z[r * ld + c];
+      Z[r * ld + c] = Z[c * ld + r];
+      Z[c * ld + r] = t;
+    }
+  }
+  __syncthreads();
+  // ---- implicit-shift QL on (d, e).  Thread 0 walks the rotation chain of one QL step (a dependent chain of one square root and one
+  // reciprocal square root per rotation); meanwhile the other warps apply the PREVIOUS step's rotations to the vectors, so the
+  // application is off the critical path. ----
+  int l = 0, iter = 0;  // thread 0 only
+  int buf = 0, have_prev = 0, failed = 0;
+  for (;;) {
+    if (tid == 0) {
+      s_has[buf] = 0;
+      s_done[buf] = 0;
+      s_fail[buf] = 0;
+      while (l < n) {
+        int m;
+        for (m = l; m + 1 < n; ++m)
+          if (fabs(e[m]) <= 2.220446049250313e-16 * (fabs(d[m]) + fabs(d[m + 1]))) break;
+        if (m == l) {
+          ++l;
+          iter = 0;
+          continue;
+        }
+        if (iter++ == 60) {
+          s_fail[buf] = 1;
+          break;
+        }
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = sqrt(g * g + 1.0);
+        g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
+        double sr = 1.0, c = 1.0, pp = 0.0;
+        double ei = e[m - 1], di = d[m - 1];
+        int i;
+        bool split = false;
+        for (i = m - 1; i >= l; --i) {
+          const double en = i > l ? e[i - 1] : 0.0, dn = i > l ? d[i - 1] : 0.0;  // operands of the next rotation, off the chain
+          const double f = sr * ei, b = c * ei;
+          const double rr = f * f + g * g;
+          if (rr == 0.0) {
+            e[i + 1] = 0.0;
+            d[i + 1] -= pp;
+            e[m] = 0.0;
+            split = true;
+            break;
+          }
+          const double ir = rsqrt(rr);
+          r = sqrt(rr);
+          e[i + 1] = r;
+          sr = f * ir;
+          c = g * ir;
+          g = d[i + 1] - pp;
+          r = (di - g) * sr + 2.0 * c * b;
+          pp = sr * r;
+          d[i + 1] = g + pp;
+          g = c * r - b;
+          cs[buf][i] = c;
+          sn[buf][i] = sr;
+          ei = en;
+          di = dn;
+        }
+        s_m[buf] = m;
+        s_lo[buf] = i + 1;  // rotations exist for the indices m - 1 .. i + 1
+        s_has[buf] = (i + 1 <= m - 1) ? 1 : 0;
+        if (!split) {
+          d[l] -= pp;
+          e[l] = g;
+          e[m] = 0.0;
+        }
+        break;
+      }
+      if (l >= n) s_done[buf] = 1;
+    } else if (have_prev && tid >= 32 && tid - 32 < n) {
+      const int k = tid - 32, pb = buf ^ 1;
+      const int m = s_m[pb], lo = s_lo[pb];
+      double zi1 = Z[m * ld + k];
+      for (int i = m - 1; i >= lo; --i) {
+        const double zi = Z[i * ld + k];
+        const double c = cs[pb][i], sr = sn[pb][i];
+        Z[(i + 1) * ld + k] = sr * zi + c * zi1;
+        zi1 = c * zi - sr * zi1;
+      }
+      Z[lo * ld + k] = zi1;
+    }
+    __syncthreads();
+    if (s_fail[buf]) {
+      failed = 1;
+      break;
+    }
+    have_prev = s_has[buf];
+    const int done = s_done[buf];
+    buf ^= 1;
+    if (done && !have_prev) break;
+  }
+  if (tid == 0) status_out[0] = failed;
+  // ---- sorted output: |lambda| descending (ties by index) ----
+  if (tid < n) {
+    const double me = fabs(d[tid]);
+    int pos = 0;
+    for (int j = 0; j < n; ++j) {
+      const double o = fabs(d[j]);
+      pos += (o > me) || (o == me && j < tid);
+    }
+    s_perm[pos] = tid;
+    sv_out[pos] = me;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += EIG_THREADS) {
+    const int r = idx / n, k = idx - r * n;
+    V_out[idx] = Z[s_perm[k] * ld + r];
+  }
+}
+
+// One-sided (Hestenes) Jacobi on G = S V0, started from the eigenvectors V0 of sym_eig_kernel (row-major [n][n], column k = k-th vector;
+// V0 == nullptr starts from the identity).  One CTA; the columns of G and V live in shared memory when they fit (n <= 119), else in
+// the global scratch buffers (column-major, L1/L2-resident).  A sweep is n - 1 round-robin steps of n / 2 disjoint column pairs; a
+// half-warp takes a pair: three dot products, then the plane rotation that makes the two columns orthogonal, applied to G and V.
+// Converged when a whole sweep rotates nothing; the column norms are the singular values, the columns of V the singular vectors;
+// both are written sorted by descending singular value.
+__global__ void __launch_bounds__(EIG_THREADS, 1) jacobi_polish_kernel(DevProblem p, const double* __restrict__ V0, double* __restrict__ G_glob,
+                                                                        double* __restrict__ V_glob, double* __restrict__ sv_out, double* __restrict__ V_out,
+                                                                        int* __restrict__ sweeps_out, int use_smem) {
+  extern __shared__ __align__(16) double eig_smem[];
+  __shared__ double s_sigma[EIG_MAX_N];
+  __shared__ int s_perm[EIG_MAX_N];
   const int n = p.n_c, na = p.n_aug;
   const int np = (n + 1) & ~1;  // padded to an even number of columns (the extra one is zero and never rotates)
-  // the rotated columns and the accumulated rotations live in shared memory when they fit (n <= 119: every pair step then costs
-  // shared-memory latency instead of an L1 / L2 round trip), else in the global scratch buffers
   double* __restrict__ G = use_smem ? eig_smem : G_glob;
   double* __restrict__ V = use_smem ? eig_smem + (size_t)np * n : V_glob;
   // two columns count as orthogonal below n * eps relative to their norms (the usual one-sided Jacobi criterion); anything tighter
@@ -1566,16 +1831,25 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem
   const int half = lane >> 4, hl = lane & 15;
   for (int idx = tid; idx < np * n; idx += EIG_THREADS) {
     const int c = idx / n, r = idx - c * n;
-    G[idx] = c < n ? p.Sred[(size_t)r * na + c] : 0.0;
-    V[idx] = (c == r) ? 1.0 : 0.0;
+    double g = 0.0, vv = (c == r) ? 1.0 : 0.0;
+    if (c < n) {
+      if (V0) {
+        vv = V0[(size_t)r * n + c];
+        for (int j = 0; j < n; ++j) g = fma(p.Sred[(size_t)r * na + j], V0[(size_t)j * n + c], g);
+      } else {
+        g = p.Sred[(size_t)r * na + c];
+      }
+    } else {
+      vv = 0.0;
+    }
+    G[idx] = g;
+    V[idx] = vv;
   }
   __syncthreads();
   int sweep = 0;
   for (; sweep < 40; ++sweep) {
     int rotated = 0;
     for (int step = 0; step < np - 1; ++step) {
-      // A half-warp per column pair: the two halves of a warp run the division / square-root chain of their rotation parameters in
-      // the same instructions, so a step issues half as many of them, and the 53 pairs of n = 106 fit one round of the 32 warps.
       for (int k0 = 2 * warp; k0 < np / 2; k0 += 2 * n_warps) {
         const int k = k0 + half;
         const bool valid = k < np / 2;
@@ -1609,8 +1883,8 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem
         if (valid && gamma * gamma > ortho_tol * ortho_tol * (alpha * beta) && gamma != 0.0) {
           // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = (beta - alpha) / (2 gamma), written with one square root and one
           // division: t = sign(d) g2 / (|d| + sqrt(d^2 + g2^2)), d = beta - alpha, g2 = 2 gamma
-          const double d = beta - alpha, g2 = 2.0 * gamma;
-          const double t = copysign(1.0, d) * g2 / (fabs(d) + sqrt(d * d + g2 * g2));
+          const double dd = beta - alpha, g2 = 2.0 * gamma;
+          const double t = copysign(1.0, dd) * g2 / (fabs(dd) + sqrt(dd * dd + g2 * g2));
           const double c = rsqrt(1.0 + t * t), sn = c * t;
           double* va = V + (size_t)a * n;
           double* vb = V + (size_t)b * n;
@@ -1618,9 +1892,9 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) marginal_eig_kernel(DevProblem
             const double x = ga[r], y = gb[r];
             ga[r] = c * x - sn * y;
             gb[r] = sn * x + c * y;
-            const double u = va[r], w = vb[r];
-            va[r] = c * u - sn * w;
-            vb[r] = sn * u + c * w;
+            const double u = va[r], ww = vb[r];
+            va[r] = c * u - sn * ww;
+            vb[r] = sn * u + c * ww;
           }
           rotated = 1;
         }
@@ -2257,21 +2531,35 @@ cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx&
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
-// dynamic shared memory of marginal_eig_kernel: both n x np column arrays, or 0 when they do not fit beside the static arrays
-static size_t eig_smem_bytes(const DevProblem& p) {
-  const size_t np = ((size_t)p.n_c + 1) & ~(size_t)1;
-  const size_t bytes = sizeof(double) * 2 * np * (size_t)p.n_c;
-  return bytes <= 220 * 1024 ? bytes : 0;
-}
-cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, double* sv_out, double* V_out, int* sweeps_out, StreamCtx& s) {
-  const size_t smem = eig_smem_bytes(p);
-  if (smem) {
-    cudaError_t e = cudaFuncSetAttribute(marginal_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// Eigen-decomposition of the reduced system in p.Sred: QL (always), then the Jacobi polish when `polish` (unscaled, graded systems).
+// status[0] = Jacobi sweeps of the polish (0 without it), status[1] = 1 when the QL iteration did not converge.
+static cudaError_t launch_sym_eig(const DevProblem& p, double* G, double* V, double* sv_out, double* V_out, double* V_tmp, int* status, bool polish,
+                                  StreamCtx& s) {
+  const size_t n = (size_t)p.n_c, ld = n | 1;
+  {
+    const size_t bytes = sizeof(double) * 2 * n * ld;
+    const size_t smem = bytes <= 200 * 1024 ? bytes : 0;
+    static size_t attr_smem_dev[MAX_DEVICES] = {};
+    if (cudaError_t e = ensure_dynamic_smem(sym_eig_kernel, smem, attr_smem_dev); e != cudaSuccess) return e;
+    sym_eig_kernel<<<1, EIG_THREADS, smem, s.stream>>>(p, G, V, sv_out, polish ? V_tmp : V_out, status + 1, smem ? 1 : 0);
+    KB_LAUNCHED(s);
+  }
+  if (polish) {
+    const size_t np = (n + 1) & ~(size_t)1;
+    const size_t bytes = sizeof(double) * 2 * np * n;
+    const size_t smem = bytes <= 220 * 1024 ? bytes : 0;
+    static size_t attr_smem_dev[MAX_DEVICES] = {};
+    if (cudaError_t e = ensure_dynamic_smem(jacobi_polish_kernel, smem, attr_smem_dev); e != cudaSuccess) return e;
+    jacobi_polish_kernel<<<1, EIG_THREADS, smem, s.stream>>>(p, V_tmp, G, V, sv_out, V_out, status, smem ? 1 : 0);
+    KB_LAUNCHED(s);
+  } else {
+    cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), s.stream);
     if (e != cudaSuccess) return e;
   }
-  marginal_eig_kernel<<<1, EIG_THREADS, smem, s.stream>>>(p, G, V, sv_out, V_out, sweeps_out, smem ? 1 : 0);
-  KB_LAUNCHED(s);
   return cudaGetLastError();
+}
+cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, double* sv_out, double* V_out, double* V_tmp, int* status, StreamCtx& s) {
+  return launch_sym_eig(p, G, V, sv_out, V_out, V_tmp, status, true, s);
 }
 cudaError_t launch_camera_diag(const DevProblem& p, double* out, StreamCtx& s) {
   camera_diag_kernel<<<1, 256, 0, s.stream>>>(p, out);
@@ -2279,16 +2567,11 @@ cudaError_t launch_camera_diag(const DevProblem& p, double* out, StreamCtx& s) {
   return cudaGetLastError();
 }
 cudaError_t launch_svd_solve(const DevProblem& p, const double* diag_h, double norm_tol, int column_scaling, double eps_svd, double svd_tol, double* g,
-                             double* G, double* V, double* sv, double* V_out, int* sweeps, double* result, StreamCtx& s) {
+                             double* G, double* V, double* sv, double* V_out, double* V_tmp, int* sweeps, double* result, StreamCtx& s) {
   svd_scale_kernel<<<1, 256, 0, s.stream>>>(p, diag_h, norm_tol, column_scaling, g);
   KB_LAUNCHED(s);
-  const size_t smem = eig_smem_bytes(p);
-  if (smem) {
-    cudaError_t e = cudaFuncSetAttribute(marginal_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  marginal_eig_kernel<<<1, EIG_THREADS, smem, s.stream>>>(p, G, V, sv, V_out, sweeps, smem ? 1 : 0);
-  KB_LAUNCHED(s);
+  // the column-scaled system is well graded: absolute accuracy suffices (tolerance 1e-6 n sv_0); the unscaled one gets the polish
+  if (cudaError_t e = launch_sym_eig(p, G, V, sv, V_out, V_tmp, sweeps, column_scaling == 0, s); e != cudaSuccess) return e;
   svd_truncated_solve_kernel<<<1, 256, 0, s.stream>>>(p, sv, V_out, g, eps_svd, svd_tol, result);
   KB_LAUNCHED(s);
   return cudaGetLastError();

@@ -147,10 +147,8 @@ def test_incremental_estimator_matches_oracle(oracle_lib, tmp_path, cfg, n_sets,
             batch[int(p.view_cam[w])] = (p.corner_id[b:e], p.y_u[b:e], p.y_v[b:e])
         r = est.add_batch(batch, p.set_poses[s])
         acc, gain, rank, iters, j0, j1 = out[f"batch{s}"]
-        if r["rank_margin"] < 1e-3:
-            pytest.skip("a singular value sits at the rank tolerance: the truncation may legitimately differ by rounding")
-        if abs(r["information_gain"] - delta) < 1e-3:
-            pytest.skip("an information gain sits at the acceptance threshold")
+        # the sequences are chosen (on the CPU, with the oracle) away from the rank tolerance and the acceptance threshold: no skip
+        assert r["rank_margin"] >= 1e-3 and abs(r["information_gain"] - delta) >= 1e-3, "pick another sequence instead of skipping"
         assert bool(acc) == r["batch_accepted"], (s, out[f"batch{s}"], r)
         assert int(rank) == r["rank_theta"] and int(iters) == r["num_iterations"]
         assert abs(gain - r["information_gain"]) <= 1e-6 * max(1.0, abs(r["information_gain"]))

@@ -35,7 +35,7 @@ def clear_rank(info):
 
 
 @pytest.mark.parametrize("cfg,n_sets,scaling", [(1, 12, False), (2, 9, False), (7, 7, False), (1, 12, True), (2, 9, True), (3, 6, True), (3, 30, True),
-                                                (4, 3, True), (6, 5, True), (7, 7, True)])
+                                                (4, 5, True), (6, 5, True), (7, 7, True)])
 def test_svd_solve_matches_oracle(capi, oracle_lib, cfg, n_sets, scaling):
     p = synthetic.make_config(cfg, n_sets=n_sets)
     g = capi.B200SchurLinearSystemSolver(p)
@@ -49,8 +49,8 @@ def test_svd_solve_matches_oracle(capi, oracle_lib, cfg, n_sets, scaling):
     x, info = ke.linear_solver_solve(J, b, cal, rest, column_scaling_on=scaling, eps_svd=opt.eps_svd)
     assert rel(sv, info["singular_values"]) < 1e-8  # relative to the largest one
     assert abs(res.tolerance - info["tolerance"]) <= 1e-8 * info["tolerance"]
-    if not clear_rank(info):
-        pytest.skip("a singular value sits at the rank tolerance")
+    # the cases are chosen (on the CPU, with the oracle) so that no singular value sits within 1 % of the rank tolerance: no skip
+    assert clear_rank(info), "this case sits on the rank tolerance: pick another size / seed instead of skipping"
     assert res.n == p.n_c and res.rank == info["rank"] and res.rank_deficiency == p.n_c - info["rank"]
     if info["rank"] < p.n_c:
         assert abs(res.sv_gap - info["sv_gap"]) <= 1e-4 * info["sv_gap"]
