@@ -4,10 +4,11 @@
 One "step" = one Levenberg-Marquardt iteration's worth of hot path on one batch of synthetic observations:
   evaluate error -> linearise + assemble -> set conditioner -> Schur-reduced solve -> rho denominator ->
   apply state update -> revert (so every step does identical work from the same state).
-Workload (N=1): BASELINE.json configs[3] "8-camera rig, 20k views": 8 x pinhole-radtan, 20 000 synced sets,
-19.2 M reprojection terms.  N>1: every rank holds 20 000 sets of the same rig (weak scaling, sets sharded by
-rank, one NCCL all-reduce of the reduced camera system per solve); `--scaling strong` shards the single
-20k-set problem instead.
+Workload: BASELINE.json configs[3] "8-camera rig, 20k views": 8 x pinhole-radtan, 20 000 synced sets, 19.2 M
+reprojection terms.  N>1 (torchrun): the headline is STRONG scaling - the one 20k-set problem sharded by synced set
+over the ranks, as BASELINE configs[3] / configs[4] describe it; the same line also carries `weak_scaling` (20 000
+sets per rank) and `cfg5_strong` (configs[4]: 16 cameras, 6 250 sets, 12 M terms, sharded the same way).
+`--scaling weak` makes the weak run the headline instead.
 
   python bench.py --gpus N --steps K --warmup W                 (torchrun launches it for N>1)
   python bench.py --impl reference ...                            CPU oracle (reference semantics) on host cores
@@ -123,62 +124,232 @@ def lm_step(g, lam=10.0, fetch_dx=False, host_obs=None):
     return J, ok, rho, m, dx
 
 
-def run_reference(args):
-    """CPU arm: the oracle (restatement of the reference's aslam_backend path; the reference itself cannot be compiled
-    here) on the host cores.  Each step = evaluate + build + solve on a bounded sample of the same workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+CPU_REGIMES = [("sparse", "all"), ("sparse", 4), ("block", "all"), ("block", 4)]  # (solver semantic, threads); first = headline
+
+
+def cpu_regimes(config, cpu_sets, headline_steps, other_steps, warmup=1):
+    """The oracle (restatement of the reference's aslam_backend path; the reference itself cannot be compiled here: no Eigen / Boost /
+    SuiteSparse in the image) on the host cores, in the reference's two solver regimes - SparseCholesky (Kalibr2's DEFAULT:
+    Optimizer2.cpp:83-86; Jacobian materialisation threaded) and BlockCholesky (serial assembly) - at T = 4 threads (the reference's
+    default nThreads, Optimizer2Options.hpp:16) and T = all host cores.  One step = evaluate + build + solve at lambda = 10 on a bounded
+    sample of the workload.  Returns (per-regime results, problem of the sample)."""
     from kalibr_b200 import synthetic
     from oracle import oracle_api as oa
 
     cores = os.cpu_count() or 1
-    S = args.cpu_sets
-    p = synthetic.make_config(args.config, n_sets=S)
-    t0 = time.time()
-    o = oa.OracleProblem(p, oa.BLOCK_CHOLESKY if args.cpu_regime == "block" else oa.SPARSE_CHOLESKY, n_threads=cores)
-    build_s = time.time() - t0
-    o.evaluate_error()
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        o.time_iteration(10.0)
-    stage = np.zeros(3)
-    t0 = time.time()
-    for _ in range(args.steps):
-        t, _ok = o.time_iteration(10.0)
-        stage += t
-    el = time.time() - t0
-    val = p.n_terms * args.steps / el
-    sample = (f"cfg{args.config} restricted to {S} synced sets ({p.n_terms} terms), {args.steps} LM iterations "
-              f"(evaluate+build+solve), {'BlockCholesky (serial assemble)' if args.cpu_regime == 'block' else 'SparseCholesky (threaded J)'} semantic, "
-              f"{cores} threads for evaluate")
+    ps = synthetic.make_config(config, n_sets=cpu_sets)
+    out = []
+    for i, (regime, T) in enumerate(CPU_REGIMES):
+        threads = cores if T == "all" else min(int(T), cores)
+        t0 = time.time()
+        o = oa.OracleProblem(ps, oa.BLOCK_CHOLESKY if regime == "block" else oa.SPARSE_CHOLESKY, n_threads=threads)
+        build_s = time.time() - t0
+        o.evaluate_error()
+        for _ in range(warmup):
+            o.time_iteration(10.0)
+        steps = headline_steps if i == 0 else other_steps
+        st = np.zeros(3)
+        t0 = time.time()
+        for _ in range(steps):
+            t, _ok = o.time_iteration(10.0)
+            st += t
+        el = time.time() - t0
+        out.append({"regime": "SparseCholesky (reference default: threaded Jacobian materialisation)" if regime == "sparse" else "BlockCholesky (threaded evaluate, serial assembly)",
+                    "solver": regime, "threads": threads, "value": ps.n_terms * steps / el, "unit": UNIT, "ms_per_step": 1e3 * el / steps, "steps": steps,
+                    "stage_s_per_iteration": {"evaluate": st[0] / steps, "build": st[1] / steps, "solve": st[2] / steps},
+                    "problem_construction_s": build_s})
+        o.close()
+    return out, ps
+
+
+def cpu_sample_text(config, ps, cores):
+    return (f"bounded sample of the workload: cfg{config} restricted to {ps.n_sets} of its synced sets ({ps.n_terms} terms); one step = evaluate + "
+            f"build + solve(lambda = 10); regimes: SparseCholesky / BlockCholesky semantic x 4 threads / {cores} threads (all host cores); "
+            f"headline = SparseCholesky at {cores} threads (Kalibr2's default solver with every host thread); throughput metric, so the "
+            f"sample size does not enter the unit")
+
+
+def run_reference(args):
+    """CPU arm of the driver's ratio: same metric, unit and `config` (the workload) as the b200 arm; every step is a bounded sample of
+    that workload (cpu_baseline.sample says which)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    from kalibr_b200 import synthetic
+
+    _, _, S_cfg = synthetic.CONFIGS[args.config]
+    regimes, ps = cpu_regimes(args.config, args.cpu_sets, max(args.steps, 1), max(2, args.steps // 5), warmup=1 if args.warmup else 0)
+    head = regimes[0]
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "impl": "reference", "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling or ("strong" if args.gpus > 1 else "weak"),
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, S, p.n_terms, 1),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "stage_s_per_iteration": {"evaluate": stage[0] / args.steps, "build": stage[1] / args.steps, "solve": stage[2] / args.steps},
-                         "problem_construction_s": build_s},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(args, args.gpus, args.scaling or ("strong" if args.gpus > 1 else "weak")),
+        "cpu_baseline": {"value": head["value"], "unit": UNIT, "cores": head["threads"], "kind": "port", "cpu_sets": int(ps.n_sets),
+                         "sample": cpu_sample_text(args.config, ps, cores), "regimes": regimes,
+                         "fastest_regime": max(regimes, key=lambda r: r["value"])["solver"] + f"/{max(regimes, key=lambda r: r['value'])['threads']} threads"},
+        "e2e": {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, sets_per_rank, terms_per_rank, n_ranks):
+L2_BYTES = 126e6
+
+
+def workload_config(args, n_ranks, scaling):
+    """`config` of the JSON line: a function of the command line alone, so that the b200 arm and the reference arm (which runs a bounded
+    sample of the same workload on the host) print the identical object."""
     from kalibr_b200 import synthetic
     from kalibr_b200.problem import MODEL_NAMES
 
-    order, models, _ = synthetic.CONFIGS[args.config]
-    return {
+    order, models, S_cfg = synthetic.CONFIGS[args.config]
+    S_total = args.sets if args.sets is not None else S_cfg
+    per_set = 120 * len(models)
+    if n_ranks > 1 and scaling == "strong":
+        lo, hi = synthetic.shard_sets(S_total, n_ranks, 0)
+        sets_rank0 = hi - lo
+    else:
+        sets_rank0 = S_total
+    flush = sets_rank0 * per_set * 18 <= L2_BYTES * 1.5
+    cfg = {
         "workload": f"BASELINE.json configs[{args.config - 1}]: {len(models)}-camera rig ({', '.join(sorted(set(MODEL_NAMES[m] for m in models)))}), "
-                    f"6x5 aprilgrid (120 corners), {sets_per_rank} synced sets per rank",
-        "cameras": len(models), "synced_sets_per_rank": sets_per_rank, "terms_per_rank": terms_per_rank, "ranks": n_ranks,
-        "parallelism": (f"sets sharded over {n_ranks} rank(s); per solve one exchange of the reduced camera system "
-                        + ("(NCCL all-reduce)" if args.no_peer_exchange or n_ranks > 8 else "(NVLink peer stores fused into the producing kernel, summed by the consumer)"))
+                    f"6x5 aprilgrid (120 corners), {S_total} synced sets" + (" per rank" if n_ranks > 1 and scaling == "weak" else "")
+                    + f", {S_total * per_set} reprojection terms" + (" per rank" if n_ranks > 1 and scaling == "weak" else ""),
+        "cameras": len(models), "synced_sets": S_total,
+        "parallelism": (f"{scaling} scaling: synced sets sharded over {n_ranks} ranks ({sets_rank0} sets on rank 0); per solve one exchange of the "
+                        "reduced camera system " + ("(NCCL all-reduce)" if args.no_peer_exchange or n_ranks > 8 else "(NVLink peer stores fused into the producing kernel, summed by the consumer)"))
         if n_ranks > 1 else "single GPU",
-        "l2": "inputs larger than L2 (observations alone exceed 126 MB)" if terms_per_rank * 18 > 126e6 else "L2 flushed between steps (128 MiB+ scratch write)",
+        "l2": "L2 flushed between steps (a 256 MiB scratch buffer is overwritten before every step; steps timed one by one)" if flush
+              else "inputs larger than L2 (the observations of a rank alone exceed 126 MB)",
     }
+    return cfg
+
+
+def flush_needed(terms_rank):
+    return terms_rank * 18 <= L2_BYTES * 1.5
+
+
+
+
+
+class Harness:
+    """torch.distributed plumbing of one bench process (one rank per GPU): barrier, device-side timing, NCCL id, peer handles."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.flush_buf = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.int64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return int(t.item())
+
+    def timed(self, stream, fn, steps, flush_l2=False):
+        """K steps timed on the device (CUDA events on the library's stream) between barrier + synchronize on both sides, MAX over
+        ranks.  flush_l2: the per-rank working set fits the 126 MB L2, so a 256 MiB buffer is overwritten before every step and
+        every step is timed on its own (the flush stays outside the timed intervals)."""
+        torch = self.torch
+        self.barrier()
+        if not flush_l2:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+            self.barrier()
+            return self.max_over_ranks(e0.elapsed_time(e1))
+        if self.flush_buf is None:
+            self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        evs = []
+        for _ in range(steps):
+            with torch.cuda.stream(stream):
+                self.flush_buf.add_(1)  # read + write of 256 MiB: evicts the L2
+            if self.world > 1:
+                self.dist.barrier()      # every rank starts the step together (the exchange steps wait for the slowest rank anyway)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            evs.append((e0, e1))
+        self.barrier()
+        # a step ends when its slowest rank ends: max over ranks per step, then the sum
+        per_step = torch.tensor([a.elapsed_time(b) for a, b in evs], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(per_step, op=self.dist.ReduceOp.MAX)
+        return float(per_step.sum().item())
+
+    def make_solver(self, config, scaling, sets_total):
+        """Problem + handle of this rank for `config` under weak (sets_total per rank) or strong (sets_total sharded) scaling."""
+        from kalibr_b200 import capi, synthetic
+
+        torch, dist, world, rank = self.torch, self.dist, self.world, self.rank
+        if scaling == "weak":
+            S_rank, set_offset, S_total = sets_total, rank * sets_total, sets_total * world
+        else:
+            lo, hi = synthetic.shard_sets(sets_total, world, rank)
+            S_rank, set_offset, S_total = hi - lo, lo, sets_total
+        p = synthetic.make_config(config, n_sets=S_rank, set_seed=20260000 + 100 * config + 7919 + set_offset)
+        terms_total = self.sum_over_ranks(p.n_terms)
+        nccl_id = None
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt = torch.tensor(list(capi.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(idt, 0)
+            nccl_id = bytes(idt.cpu().tolist())
+        g = capi.B200SchurLinearSystemSolver(p, n_ranks=world, rank=rank, nccl_id=nccl_id, device=self.local_rank,
+                                             n_sets_total=S_total if world > 1 else 0, set_offset=set_offset, n_terms_total=terms_total)
+        if world > 1 and world <= 8 and not self.args.no_peer_exchange:
+            # NVLink peer exchange: all-gather the CUDA IPC handles of the ranks' exchange buffers, then attach
+            mine = torch.tensor(list(g.peer_exchange_handle()), dtype=torch.uint8, device="cuda")
+            allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            g.attach_peers(b"".join(bytes(t.cpu().tolist()) for t in allh))
+        stream = torch.cuda.ExternalStream(g.cuda_stream(), device=torch.device("cuda", self.local_rank))
+        return p, g, stream, terms_total
+
+    def run_steps(self, config, scaling, sets_total, steps, warmup, sample_clocks=False):
+        """The device-resident arm for one (config, scaling): W warm-up steps, K timed steps.  Returns a dict and keeps (p, g, stream)."""
+        p, g, stream, terms_total = self.make_solver(config, scaling, sets_total)
+        for _ in range(warmup):
+            lm_step(g)
+        sampler = ClockSampler(self.local_rank) if sample_clocks and self.rank == 0 else None
+        if sampler:
+            sampler.start()
+        flush = bool(self.max_over_ranks(1.0 if flush_needed(p.n_terms) else 0.0))  # the same decision on every rank
+        g.enable_stage_timing(True)
+        l0 = g.kernel_launches()
+        ms_total = self.timed(stream, lambda: lm_step(g), steps, flush_l2=flush)
+        launches = self.sum_over_ranks(g.kernel_launches() - l0)
+        totals = g.stage_totals()
+        g.enable_stage_timing(False)
+        clocks = sampler.stop() if sampler else None
+        return {"p": p, "g": g, "stream": stream, "terms_total": terms_total, "ms_total": ms_total, "launches": launches, "totals": totals,
+                "clocks": clocks, "l2_flushed": flush, "value": terms_total * steps / (ms_total * 1e-3), "ms_per_step": ms_total / steps}
 
 
 def main():
@@ -188,13 +359,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=4, help="BASELINE config 1..5 (default 4: 8-camera rig, 20k views)")
-    ap.add_argument("--sets", type=int, default=None, help="override the number of synced sets per rank")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--sets", type=int, default=None, help="override the number of synced sets of the workload")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="N > 1: which scaling the headline value is (default strong)")
     ap.add_argument("--cpu-sets", type=int, default=None, help="synced sets of the bounded CPU-baseline sample")
-    ap.add_argument("--cpu-regime", default="block", choices=["block", "sparse"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-init-stage", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the weak-scaling and cfg-5 extra measurements")
     ap.add_argument("--no-peer-exchange", action="store_true", help="N > 1: keep the exchange steps on NCCL instead of NVLink peer stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -203,96 +374,27 @@ def main():
 
     order, models, S_cfg = synthetic.CONFIGS[args.config]
     if args.cpu_sets is None:
-        # about 10-30 s of CPU work: the oracle runs ~0.1-0.2 M terms/s per LM iteration
-        args.cpu_sets = max(8, min(S_cfg, int(400_000 / (120 * len(models)))))
+        # about 10-30 s of CPU work for the four regimes: the oracle runs ~0.1-0.2 M terms/s per LM iteration
+        per_set = 120 * len(models)
+        args.cpu_sets = max(8, min(S_cfg, int((400_000 if args.impl == "reference" else 200_000) / per_set)))
     if args.impl == "reference":
         return run_reference(args)
-
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from kalibr_b200 import capi
 
     capi.load_library()
-    S_total_cfg = args.sets if args.sets is not None else S_cfg
-    if args.scaling == "weak":
-        S_rank = S_total_cfg
-        set_offset = rank * S_rank
-        S_total = S_rank * world
-    else:
-        lo, hi = synthetic.shard_sets(S_total_cfg, world, rank)
-        S_rank, set_offset, S_total = hi - lo, lo, S_total_cfg
-    p = synthetic.make_config(args.config, n_sets=S_rank, set_seed=20260000 + 100 * args.config + 7919 + set_offset)
-    terms_rank = p.n_terms
-    terms_total = terms_rank
-    nccl_id = None
-    if world > 1:
-        t = torch.tensor([terms_rank], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t)
-        terms_total = int(t.item())
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(capi.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
-    g = capi.B200SchurLinearSystemSolver(p, n_ranks=world, rank=rank, nccl_id=nccl_id, device=local_rank,
-                                         n_sets_total=S_total if world > 1 else 0, set_offset=set_offset, n_terms_total=terms_total)
-    peer_exchange = False
-    if world > 1 and world <= 8 and not args.no_peer_exchange:
-        # NVLink peer exchange: all-gather the CUDA IPC handles of the ranks' exchange buffers, then attach
-        mine = torch.tensor(list(g.peer_exchange_handle()), dtype=torch.uint8, device="cuda")
-        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        dist.all_gather(allh, mine)
-        g.attach_peers(b"".join(bytes(t.cpu().tolist()) for t in allh))
-        peer_exchange = True
-    stream = torch.cuda.ExternalStream(g.cuda_stream(), device=torch.device("cuda", local_rank))
+    H = Harness(args)
+    torch, world, rank = H.torch, H.world, H.rank
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    scaling = args.scaling or ("strong" if world > 1 else "weak")
+    S_workload = args.sets if args.sets is not None else S_cfg
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    # ---- device-resident arm ----
-    for _ in range(args.warmup):
-        lm_step(g)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    g.enable_stage_timing(True)
-    l0 = g.kernel_launches()
-    ms_total = timed(lambda: lm_step(g), args.steps)
-    launches = g.kernel_launches() - l0
-    totals = g.stage_totals()
-    g.enable_stage_timing(False)
-    clocks = sampler.stop() if rank == 0 else None
-    value = terms_total * args.steps / (ms_total * 1e-3)
-    if world > 1:
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt)
-        launches = int(lt.item())
+    # ---- headline: device-resident arm ----
+    R = H.run_steps(args.config, scaling, S_workload, args.steps, args.warmup, sample_clocks=True)
+    p, g, stream = R["p"], R["g"], R["stream"]
+    terms_rank, terms_total = p.n_terms, R["terms_total"]
+    ms_total, launches, totals, clocks, value = R["ms_total"], R["launches"], R["totals"], R["clocks"], R["value"]
 
     # ---- end-to-end arm: host buffers in, host results out, every step ----
     e2e = None
@@ -316,7 +418,7 @@ def main():
         k_e2e = max(3, args.steps // 2)
         for _ in range(2):
             e2e_step_streamed()
-        ms_streamed = timed(e2e_step_streamed, k_e2e)
+        ms_streamed = H.timed(stream, e2e_step_streamed, k_e2e)
         g.prefetch_observations(yu_np, yv_np)
         for _ in range(2):
             e2e_step_pipelined()
@@ -327,13 +429,13 @@ def main():
             g.commit_observations()               # the last upload is waited for inside the timed region
             g.prefetch_observations(yu_np, yv_np)
 
-        ms_e2e = timed(pipelined_run, 1)
+        ms_e2e = H.timed(stream, pipelined_run, 1)
         g.commit_observations()
         e2e = {"value": terms_total * k_e2e / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(16 * terms_rank), "d2h_bytes_per_step": int(8 * g.jcols + 8 * 4 + 4),
                "ms_per_step": ms_e2e / k_e2e, "steps": k_e2e,
                "single_step_latency_ms": ms_streamed / k_e2e,
-               "note": "per rank; through B200SchurLinearSystemSolver (C ABI) with pinned HOST observation buffers uploaded every step and dx fetched "
+               "note": "bytes per rank; through B200SchurLinearSystemSolver (C ABI) with pinned HOST observation buffers uploaded every step and dx fetched "
                        "every step. value: double-buffered (kb_prefetch_observations / kb_commit_observations: the next step's upload overlaps this "
                        "step's kernels); single_step_latency_ms: one isolated step with kb_evaluate_error_streamed (chunked upload overlapped with "
                        "the fused kernel). Both are bounded by the 16 B/term PCIe transfer"}
@@ -401,6 +503,35 @@ def main():
         except Exception as ex:
             init = {"error": str(ex)}
 
+    g.close()
+    del g
+
+    # ---- N > 1: the other scaling mode and the cfg-5 sweep point, same harness ----
+    extras = {}
+    if world > 1 and not args.no_extras:
+        other = "weak" if scaling == "strong" else "strong"
+        k_x, w_x = max(5, args.steps // 2), 3
+        X = H.run_steps(args.config, other, S_workload, k_x, w_x)
+        extras[f"{other}_scaling"] = {"value": X["value"], "unit": UNIT, "ms_per_step": X["ms_per_step"], "steps": k_x, "terms_total": X["terms_total"],
+                                      "synced_sets_rank0": int(X["p"].n_sets), "l2_flushed_between_steps": X["l2_flushed"],
+                                      "note": "weak: every rank holds the full workload's number of synced sets; strong: the one workload sharded by synced set"}
+        X["g"].close()
+        del X
+    if not args.no_extras and args.config == 4:
+        k_x, w_x = max(5, args.steps // 2), 3
+        X = H.run_steps(5, "strong", synthetic.CONFIGS[5][2], k_x, w_x)
+        extras["cfg5_strong"] = {"workload": "BASELINE.json configs[4]: 16-camera rig (pinhole-radtan), 6250 synced sets, 12000000 terms (n_c = 218)",
+                                 "value": X["value"], "unit": UNIT, "ms_per_step": X["ms_per_step"], "steps": k_x, "terms_total": X["terms_total"],
+                                 "l2_flushed_between_steps": X["l2_flushed"],
+                                 "stage_ms": {k: (v[0] / max(v[1], 1)) for k, v in X["totals"].items() if v[1] > 0}}
+        X["g"].close()
+        del X
+
+    # ---- N = 1: calibration-level end to end (create -> optimize to convergence -> fetch), next to the oracle's optimize ----
+    calib = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        calib = calibration_e2e(args, capi, synthetic, S_workload)
+
     if rank == 0:
         hbm_peak, hbm_src, fp64_peak, fp64_src = peaks()
         la_ms, la_calls = totals["linearise_assemble"]
@@ -408,47 +539,83 @@ def main():
         n_views_rank = p.n_views
         flops = FLOP_PER_TERM * terms_rank
         byts = (BYTES_IN_PER_TERM + BYTES_E_PER_TERM) * terms_rank + BYTES_OUT_PER_VIEW * n_views_rank
-        traffic = (read_json(os.path.join(ROOT, "profiles", "r01_traffic.json")) or {}).get("linearise_assemble_dram_bytes_per_launch")
+        traffic = (read_json(os.path.join(ROOT, "profiles", "r01_traffic.json")) or {}).get("linearise_assemble_dram_bytes_per_launch") if world == 1 and args.config == 4 and args.sets is None else None
         roofline = {"kernel": "linearise_assemble_kernel<pinhole-radtan>", "bound": "tensor",
                     "achieved": flops / (la_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": flops / (la_ms * 1e-3) / 1e12 / fp64_peak, "traffic": traffic,
                     "peak_source": fp64_src, "avg_launch_ms": la_ms, "launches_timed": la_calls,
-                    "note": "FP64 pipe bound (about 24 flop/B): DMMA m8n8k4 Gram accumulation + FP64 projection/Jacobian math"}
+                    "note": "rank 0's launch; FP64 pipe bound (about 24 flop/B): DMMA m8n8k4 Gram accumulation + FP64 projection/Jacobian math"}
         roofline_hbm = {"kernel": "linearise_assemble_kernel<pinhole-radtan>", "bound": "hbm", "achieved": byts / (la_ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "frac": byts / (la_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                         "algorithmic_bytes_per_launch": byts}
         stages = {k: (v[0] / max(v[1], 1)) for k, v in totals.items() if v[1] > 0}
         cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            regimes, ps = cpu_regimes(args.config, args.cpu_sets, 3, 2, warmup=0)
+            head = regimes[0]
+            cpu = {"value": head["value"], "unit": UNIT, "cores": head["threads"], "kind": "port", "cpu_sets": int(ps.n_sets),
+                   "sample": cpu_sample_text(args.config, ps, cores), "regimes": regimes,
+                   "fastest_regime": max(regimes, key=lambda r: r["value"])["solver"] + f"/{max(regimes, key=lambda r: r['value'])['threads']} threads"}
+        cfg = workload_config(args, world, scaling)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "per_gpu_value": value / world, "lm_iteration_ms": ms_total / args.steps, "terms_total": terms_total,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": roofline_hbm,
+            "linearise_materialised": lin, "initial_guess": init, "stage_ms": stages, "cpu_baseline": cpu, "calibration_e2e": calib,
+        }
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        H.dist.barrier()
+        H.dist.destroy_process_group()
+
+
+def calibration_e2e(args, capi, synthetic, S_workload):
+    """A whole calibration through the public entry points, host arrays in, host parameters out: kb_create (uploads the problem once)
+    -> kb_optimize (device-resident LM loop to convergence) -> kb_get_camera_params / kb_get_baselines.  At the workload's full size,
+    and on the bounded CPU sample next to the oracle's Optimizer2::optimize restatement (same problem, same options)."""
+    from kalibr_b200.problem import KbOptimizerOptions
+
+    def gpu_run(p):
+        t0 = time.time()
+        g = capi.B200SchurLinearSystemSolver(p)
+        t1 = time.time()
+        sol, _ = g.optimize(KbOptimizerOptions.kalibr2_default())
+        cam, base = g.camera_params(), g.baselines()
+        t2 = time.time()
+        g.close()
+        return {"create_ms": 1e3 * (t1 - t0), "optimize_and_fetch_ms": 1e3 * (t2 - t1), "total_ms": 1e3 * (t2 - t0), "iterations": sol.iterations,
+                "failed_iterations": sol.failed_iterations, "j_final": sol.j_final, "terms": int(p.n_terms),
+                "terms_iterations_per_s": p.n_terms * (sol.iterations + sol.failed_iterations) / max(t2 - t0, 1e-9)}, cam, base
+
+    out = {"note": "wall clock of the calling process (time.time), not device events: this is what a caller of the C ABI sees"}
+    try:
+        p_full = synthetic.make_config(args.config, n_sets=S_workload)
+        gpu_run(p_full)  # first call pays module load / graph capture
+        out["gpu_full_size"], _, _ = gpu_run(p_full)
         if not args.no_cpu_baseline:
             from oracle import oracle_api as oa
 
+            ps = synthetic.make_config(args.config, n_sets=max(8, args.cpu_sets // 2))
+            out["gpu_cpu_sample"], cam, base = gpu_run(ps)
             cores = os.cpu_count() or 1
-            ps = synthetic.make_config(args.config, n_sets=args.cpu_sets)
-            o = oa.OracleProblem(ps, oa.BLOCK_CHOLESKY, n_threads=cores)
-            o.evaluate_error()
-            n_it, t0, st = 0, time.time(), np.zeros(3)
-            while n_it < 2 or (time.time() - t0 < 10.0 and n_it < 50):
-                t, _ = o.time_iteration(10.0)
-                st += t
-                n_it += 1
-            el = time.time() - t0
-            cpu = {"value": ps.n_terms * n_it / el, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"cfg{args.config} restricted to {args.cpu_sets} synced sets ({ps.n_terms} terms), {n_it} LM iterations (evaluate+build+solve), "
-                             f"BlockCholesky semantic (threaded evaluate on {cores} threads, serial assemble as in the reference)",
-                   "stage_s_per_iteration": {"evaluate": st[0] / n_it, "build": st[1] / n_it, "solve": st[2] / n_it}}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, S_rank, terms_rank, world),
-            "per_gpu_value": value / world, "lm_iteration_ms": ms_total / args.steps, "terms_total": terms_total,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "linearise_materialised": lin, "initial_guess": init, "stage_ms": stages, "cpu_baseline": cpu,
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        g.close()
-        dist.destroy_process_group()
+            t0 = time.time()
+            o = oa.OracleProblem(ps, oa.SPARSE_CHOLESKY if args.config == 3 else oa.BLOCK_CHOLESKY, n_threads=cores)
+            t1 = time.time()
+            osol, _ = o.optimize(KbOptimizerOptions.kalibr2_default())
+            t2 = time.time()
+            oc = o.camera_params()
+            out["cpu_sample"] = {"kind": "port", "cores": cores, "sets": int(ps.n_sets), "terms": int(ps.n_terms), "construct_ms": 1e3 * (t1 - t0),
+                                 "optimize_ms": 1e3 * (t2 - t1), "total_ms": 1e3 * (t2 - t0), "iterations": osol.iterations,
+                                 "failed_iterations": osol.failed_iterations, "j_final": osol.j_final,
+                                 "max_rel_parameter_difference_vs_gpu": float((np.abs(cam - oc) / np.maximum(np.abs(oc), 1e-3)).max())}
+            o.close()
+    except Exception as ex:
+        out["error"] = str(ex)
+    return out
 
 
 if __name__ == "__main__":

@@ -34,7 +34,8 @@ struct LmState {
   int done;        // the loop has ended
   int need_build;  // lm_before_solve: linearise + assemble before this solve (first iteration, or the last step was accepted with rho > 0)
   int skip_eval;   // lm_after_solve: the solve failed (not positive definite) - no update, no evaluation this iteration
-  int revert;      // lm_after_eval: the step was a regression - restore the design variables
+  int revert;      // lm_after_eval: the step was a regression - restore the design variables (stays set until the next lm_after_eval:
+                   // the device loop restores lazily, right before the next update or when the loop ends)
   double damping;  // lm_before_solve: what this solve adds to every diagonal entry of H (residual + lambda^2)
   double lambda;   // the conditioner (squared when applied: LinearSystemSolver.hpp:34-38)
   double cost_new; // device loop: where the evaluation of the trial state puts its cost
@@ -121,7 +122,6 @@ KB_HD void lm_before_solve(LmState* c) {
   c->need_build = build;
   if (build) c->diag_residual = 0.0;  // buildSystem clears H
   c->damping = c->diag_residual + lambda * lambda;
-  c->revert = 0;
 }
 
 // After the solve: its scalars, the lambda^2 / lambda residual of the BlockCholesky semantic, and the failed-solve branch.
@@ -145,6 +145,7 @@ KB_HD void lm_after_eval(LmState* c, double cost_new) {
   c->deltaX = c->max_dx;
   c->J = cost_new;
   c->deltaJ = c->pJ - c->J;
+  c->revert = 0;
   if (c->policy == KB_POLICY_LEVENBERG_MARQUARDT) {  // revertOnFailure()
     if (c->deltaJ < 0.0) {
       c->revert = 1;

@@ -107,7 +107,8 @@ struct DevProblem {
   double* dxc;          // [n_c]
   double* dx;           // [jcols] in design-variable order (poses of other ranks stay 0)
   unsigned int* n_invalid;  // terms whose projection bailed out (Q6)
-  double* rho_partial;      // [2 * 64] stage-1 partials of the rho denominator / max|dx| reduction (per handle)
+  double* rho_partial;      // [2 * max(64, back-substitution blocks)] stage-1 partials of the rho denominator / max|dx| reduction (per handle)
+  unsigned int* tickets;    // [4] zero-initialised "last block" ticket counters (finalize_gram)
   LmCtrl* ctrl;             // control block (device)
   PeerXchg px;              // peer exchange (enabled after kb_attach_peers)
   // ---- weighting of the terms (kb_set_inv_r / kb_set_m_estimator) ----
@@ -140,11 +141,12 @@ cudaError_t launch_evaluate(const DevProblem& p, const int* view_list, const int
 cudaError_t launch_reproj_stats(const DevProblem& p, const double* e_raw, const int* cam_view_list, const int* cam_view_begin, int pass,
                                 double* acc /*[n_cams][8]*/, StreamCtx& s);
 int la_grid_warps();
+// with_set_prep / with_cam_prep: the per-set and per-camera constants are (re)computed by one launch in front of the fused kernel
 cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta /*(view,set,begin,end) in view-list order*/, const int4* slices,
-                                      const int* slice_model_begin, bool write_e, bool with_set_prep,
-                                      StreamCtx& s);
+                                      const int* slice_model_begin, bool write_e, bool with_set_prep, bool with_cam_prep, StreamCtx& s);
+// lm_mode 1 (single-rank device-resident loop): the kernel also runs the loop boundary (accept / reject, next iteration's decisions)
 cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range /*[n_cams][n_ranges][2]*/, int n_ranges, double* cost_out,
-                                 bool exchange_cost /* also the producer of peer exchange C */, StreamCtx& s);
+                                 bool exchange_cost /* also the producer of peer exchange C */, int lm_mode, double* trace, int* pos_def, StreamCtx& s);
 cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta, const int4* slices, const int* slice_model_begin,
                                          const int* bfrag_pairs /*[NUM_MODELS]*/, unsigned int* counters /*[NUM_MODELS], device*/, double* jt_values,
@@ -152,8 +154,12 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
 // damping / lambda arguments: a negative value means "read it from the control block" (device-resident loop)
 cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_schur_finalize(const DevProblem& p, double damping, const double* partials, int n_partials, bool add_camera_block, StreamCtx& s);
-cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s);
-cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, int* pos_def_flag, StreamCtx& s);
+// from_peers: the kernel waits for exchange A and sums the ranks' slots itself (no launch_px_reduce_system in front)
+cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, bool from_peers, StreamCtx& s);
+int backsub_blocks(const DevProblem& p);
+cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, double lambda, int include_shared,
+                           bool with_rho, StreamCtx& s);
+cudaError_t launch_solve_scalars(const DevProblem& p, double* out2, const int* pos_def_for_exchange, const int* pos_def, int lm_mode, StreamCtx& s);
 cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int* cam_cols,
                                    int include_shared, double* out2 /* [0]=sum, [1]=max|dx| */,
                                    const int* pos_def_for_exchange /* non-null: also the producer of peer exchange B */, StreamCtx& s);
@@ -161,9 +167,8 @@ cudaError_t launch_pack_rank_scalars(double* pk /*[n_ranks][4], device*/, int ra
 cudaError_t launch_apply_update(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, double* backup_cam,
                                 double* backup_base, double* backup_sets, StreamCtx& s);
 // device-resident LM loop: single-thread control kernels and the conditional revert
-cudaError_t launch_lm_pre_solve(const DevProblem& p, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_lm_post_solve(const DevProblem& p, const int* pos_def_flag, const double* rho_max, const double* rank_slots, int n_ranks, StreamCtx& s);
-cudaError_t launch_lm_post_eval(const DevProblem& p, double* trace, StreamCtx& s);
+cudaError_t launch_lm_boundary(const DevProblem& p, double* trace, int* pos_def, StreamCtx& s);
 cudaError_t launch_lm_revert(const DevProblem& p, const double* backup_cam, const double* backup_base, const double* backup_sets, StreamCtx& s);
 cudaError_t launch_lm_finish(const DevProblem& p, StreamCtx& s);
 // eigen-decomposition of the reduced system in p.Sred (G, V: scratch of (n_c + 1) * n_c doubles each, V_tmp: n_c * n_c):
@@ -179,8 +184,8 @@ cudaError_t launch_svd_solve(const DevProblem& p, const double* diag_h, double n
                              StreamCtx& s);
 // peer exchange consumers
 cudaError_t launch_px_reduce_system(const DevProblem& p, StreamCtx& s);
-cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max /*[2]*/, int* pos_def_flag, StreamCtx& s);
-cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx& s);
+cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max /*[2]*/, int* pos_def_flag, int lm_mode, StreamCtx& s);
+cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, int lm_mode, double* trace, int* pos_def, StreamCtx& s);
 // initial-guess stage (kb_init.cu): PnP per view (view_mask: null = every view of the list), best view per set, target pose guesses
 cudaError_t launch_estimate_transformations(const DevProblem& p, const int* view_list, const int* model_begin, const unsigned char* view_mask,
                                             const int* resolution /*[n_cams][2] device, or null*/, double* T_out /*[n_views][7]*/, int* ok_out /*[n_views]*/,

@@ -126,7 +126,7 @@ struct kb_handle {
   double *front_u = nullptr, *front_v = nullptr, *back_u = nullptr, *back_v = nullptr;
   cudaEvent_t ev_prefetch = nullptr, ev_front_free = nullptr;
   bool prefetch_pending = false, front_free_recorded = false;
-  DevBuf<unsigned int> n_invalid, lm_counters;
+  DevBuf<unsigned int> n_invalid, lm_counters, tickets;
   DevBuf<int> col_desc;
   int lm_bfrag_pairs[KB_NUM_MODELS] = {};
   int model_begin[KB_NUM_MODELS + 1] = {};
@@ -664,7 +664,9 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->dxc.alloc(D.n_c));
   KB_CCUDA(h->dx.alloc((size_t)h->jcols));
   KB_CCUDA(h->scalars.alloc(8));
-  KB_CCUDA(h->rho_partial.alloc(2 * 64));
+  KB_CCUDA(h->rho_partial.alloc(2 * std::max<size_t>(64, (size_t)n_local_sets / 8 + 2)));
+  KB_CCUDA(h->tickets.alloc(4));
+  KB_CCUDA(cudaMemsetAsync(h->tickets.p, 0, 4 * sizeof(unsigned int), s));
   KB_CCUDA(h->rank_slots.alloc(4 * (size_t)d->n_ranks));
   KB_CCUDA(h->ctrl.alloc(1));
   D.px.enabled = 0;
@@ -700,7 +702,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   D.camT = h->camT.p; D.camPi = h->camPi.p; D.camA = h->camA.p; D.baseBt = h->baseBt.p; D.baseM = h->baseM.p;
   D.e = h->e.p; D.view_cost = h->view_cost.p; D.set_prep = h->set_prep.p; D.VB = h->VB.p; D.gram_partial = h->gram_partial.p; D.sumG = h->sumG.p;
   D.V = h->V.p; D.bv = h->bv.p; D.W = h->W.p; D.Lv = h->Lv.p; D.yv = h->yv.p;
-  D.U = h->U.p; D.Sred = h->Sred.p; D.dxc = h->dxc.p; D.dx = h->dx.p; D.n_invalid = h->n_invalid.p; D.rho_partial = h->rho_partial.p;
+  D.U = h->U.p; D.Sred = h->Sred.p; D.dxc = h->dxc.p; D.dx = h->dx.p; D.n_invalid = h->n_invalid.p; D.rho_partial = h->rho_partial.p; D.tickets = h->tickets.p;
   h->n_partials = schur_num_partials(D);
   KB_CCUDA(h->partials.alloc(schur_partial_stride(D) * h->n_partials));
   trace.mark("allocations, memsets");
@@ -754,12 +756,11 @@ kb_status kb_set_solver_semantic(kb_handle* h, int32_t semantic) {
 // fused linearise+assemble at the current state: view blocks, per-camera Gram sums, cost (-> scalars[slot]) and, if asked, e()
 static kb_status run_linearise_assemble(kb_handle* h, bool write_e, int cost_slot) {
   StreamCtx c = ctx(h);
-  KB_CUDA(h, launch_prep(h->d, c));
   {
     StageTimer t(h, 1);
-    KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->slices.p, h->slice_model_begin, write_e, true, c));
+    KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->slices.p, h->slice_model_begin, write_e, true, true, c));
   }
-  KB_CUDA(h, launch_finalize_gram(h->d, h->cam_slice_range.p, 1, h->scalars.p + cost_slot, write_e /* the evaluate-time call */, c));
+  KB_CUDA(h, launch_finalize_gram(h->d, h->cam_slice_range.p, 1, h->scalars.p + cost_slot, write_e /* the evaluate-time call */, 0, nullptr, nullptr, c));
   h->la_version = h->state_version;
   h->la_rows = h->d.mest_rows;
   return KB_OK;
@@ -796,7 +797,7 @@ kb_status kb_evaluate_error(kb_handle* h, int32_t use_m_estimator, double* out_c
       KB_CUDA(h, launch_evaluate(h->d, h->view_list.p, h->model_begin, h->scalars.p, c));
     }
     if (h->px_on && speculative) {  // gram_cost_kernel has already put this rank's cost into every rank's slot
-      KB_CUDA(h, launch_px_combine_cost(h->d, h->scalars.p, c));
+      KB_CUDA(h, launch_px_combine_cost(h->d, h->scalars.p, 0, nullptr, nullptr, c));
     } else {
       kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
       if (st != KB_OK) return st;
@@ -832,16 +833,15 @@ kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const doub
   }
   {
     StageTimer t(h, 0);
-    KB_CUDA(h, launch_prep(h->d, c));
     for (int k = 0; k < KB_STREAM_CHUNKS; ++k) {
       KB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[k], 0));
-      KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->st_slices.p, h->st_chunk_model_begin[k], true, k == 0, c));
+      KB_CUDA(h, launch_linearise_assemble(h->d, h->vmeta.p, h->st_slices.p, h->st_chunk_model_begin[k], true, k == 0, k == 0, c));
     }
-    KB_CUDA(h, launch_finalize_gram(h->d, h->st_cam_slice_range.p, KB_STREAM_CHUNKS, h->scalars.p, true, c));
+    KB_CUDA(h, launch_finalize_gram(h->d, h->st_cam_slice_range.p, KB_STREAM_CHUNKS, h->scalars.p, true, 0, nullptr, nullptr, c));
     h->la_version = h->state_version;
     h->la_rows = h->d.mest_rows;
     if (h->px_on) {
-      KB_CUDA(h, launch_px_combine_cost(h->d, h->scalars.p, c));
+      KB_CUDA(h, launch_px_combine_cost(h->d, h->scalars.p, 0, nullptr, nullptr, c));
     } else {
       kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
       if (st != KB_OK) return st;
@@ -1265,7 +1265,7 @@ static kb_status analyze_marginal_impl(kb_handle* h, const kb_marginal_options* 
     KB_CUDA(h, h->eig_sv.alloc(n));
     KB_CUDA(h, h->eig_Vout.alloc((size_t)n * n));
     KB_CUDA(h, h->eig_Vtmp.alloc((size_t)n * n));
-    KB_CUDA(h, h->eig_sweeps.alloc(2));
+    KB_CUDA(h, h->eig_sweeps.alloc(8));
   }
   // the undamped normal equations at the current state (or of the last build), set poses eliminated: exactly the analyzeMarginal matrix
   kb_status st = rebuild ? kb_build_system(h, 1) : KB_OK;
@@ -1287,12 +1287,12 @@ static kb_status analyze_marginal_impl(kb_handle* h, const kb_marginal_options* 
   KB_CUDA(h, cudaMemcpyAsync(h->h_posdef, h->posdef.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(singular_values, h->eig_sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
   if (V) KB_CUDA(h, cudaMemcpyAsync(V, h->eig_Vout.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
-  int sweeps2[2] = {0, 0};
-  KB_CUDA(h, cudaMemcpyAsync(sweeps2, h->eig_sweeps.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  int sweeps2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  KB_CUDA(h, cudaMemcpyAsync(sweeps2, h->eig_sweeps.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   collect_stages(h);
   const int sweeps = sweeps2[1] ? 99 : sweeps2[0];
-  if (getenv("KB_SVD_TRACE")) std::fprintf(stderr, "[kb trace] marginal analysis: n = %d, Jacobi polish sweeps = %d, QL failed = %d\n", n, sweeps2[0], sweeps2[1]);
+  if (getenv("KB_SVD_TRACE")) std::fprintf(stderr, "[kb trace] marginal analysis: n = %d, Jacobi polish sweeps = %d, QL failed = %d, tridiag %d kcycles, QL %d kcycles, %d QL steps, %d rotations\n", n, sweeps2[0], sweeps2[1], sweeps2[2], sweeps2[3], sweeps2[4], sweeps2[5]);
   h->solved = false;  // the pose factors now belong to the undamped system
   if (!h->h_posdef[0])
     return fail(h, KB_ERR_NUMERICAL, "a set pose is not constrained by its observations (pose block not positive definite): the marginal is undefined");
@@ -1363,14 +1363,14 @@ static kb_status solve_finish(kb_handle* h, double* dx, int32_t gather_dx) {
   StreamCtx c = ctx(h);
   {
     StageTimer t(h, 5);
-    KB_CUDA(h, launch_backsub(h->d, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->posdef.p, c));
+    // the back substitution leaves the per-block partials of dx^T (lambda dx + rhs) and max|dx| behind
+    KB_CUDA(h, launch_backsub(h->d, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->lambda, h->rank == 0 ? 1 : 0, true, c));
   }
   {
-    // dx^T (lambda dx + rhs) and max|dx| of this solution, so that getLmRho / applyStateUpdate need no further launch
-    KB_CUDA(h, launch_rho_denominator(h->d, h->lambda, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2,
-                                      h->posdef.p, c));
+    // ... so that getLmRho / applyStateUpdate need no further pass over dx
+    KB_CUDA(h, launch_solve_scalars(h->d, h->scalars.p + 2, h->posdef.p, h->posdef.p, 0, c));
     if (h->px_on) {
-      KB_CUDA(h, launch_px_combine_solve(h->d, h->scalars.p + 2, h->posdef.p, c));
+      KB_CUDA(h, launch_px_combine_solve(h->d, h->scalars.p + 2, h->posdef.p, 0, c));
     } else if (h->n_ranks > 1) {  // one packed all-reduce instead of three (min / sum / max)
       KB_CUDA(h, launch_pack_rank_scalars(h->rank_slots.p, h->rank, h->n_ranks, h->scalars.p + 2, h->posdef.p, c));
       kb_status st = nccl_allreduce(h, h->rank_slots.p, 4 * (size_t)h->n_ranks, kNcclFloat64, kNcclSum);
@@ -1440,16 +1440,14 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
     StageTimer t(h, 3);
     KB_CUDA(h, launch_schur(h->d, damping, h->partials.p, h->n_partials, h->posdef.p, c));
     KB_CUDA(h, launch_schur_finalize(h->d, damping, h->partials.p, h->n_partials, true, c));
-    if (h->px_on) {  // the partials have gone straight into every rank's buffer: sum them in rank order
-      KB_CUDA(h, launch_px_reduce_system(h->d, c));
-    } else {
+    if (!h->px_on) {  // (peer exchange: the partials have gone straight into every rank's buffer; the solve kernel sums them in rank order)
       kb_status st = nccl_allreduce(h, h->Sred.p, (size_t)h->d.n_aug * h->d.n_aug, kNcclFloat64, kNcclSum);
       if (st != KB_OK) return st;
     }
   }
   {
     StageTimer t(h, 4);
-    KB_CUDA(h, launch_reduced_solve(h->d, damping, h->posdef.p, c));
+    KB_CUDA(h, launch_reduced_solve(h->d, damping, h->posdef.p, h->px_on, c));
   }
   {
     kb_status st = solve_finish(h, dx, gather_dx);
@@ -1498,7 +1496,7 @@ kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, doub
     KB_CUDA(h, h->eig_sv.alloc(n));
     KB_CUDA(h, h->eig_Vout.alloc((size_t)n * n));
     KB_CUDA(h, h->eig_Vtmp.alloc((size_t)n * n));
-    KB_CUDA(h, h->eig_sweeps.alloc(2));
+    KB_CUDA(h, h->eig_sweeps.alloc(8));
   }
   if (h->svd_diag.n != (size_t)n) {
     KB_CUDA(h, h->svd_diag.alloc(n));
@@ -1528,9 +1526,9 @@ kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, doub
                                 h->eig_sv.p, h->eig_Vout.p, h->eig_Vtmp.p, h->eig_sweeps.p, h->svd_result.p, c));
   }
   double res[4] = {0, 0, 0, 0};
-  int sweeps2[2] = {0, 0};
+  int sweeps2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   KB_CUDA(h, cudaMemcpyAsync(res, h->svd_result.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  KB_CUDA(h, cudaMemcpyAsync(sweeps2, h->eig_sweeps.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(sweeps2, h->eig_sweeps.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (singular_values) KB_CUDA(h, cudaMemcpyAsync(singular_values, h->eig_sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
   st = solve_finish(h, dx, gather_dx);  // synchronises
   if (st != KB_OK) return st;
@@ -1538,7 +1536,7 @@ kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, doub
   h->rho_lambda = 0.0;
   if (!h->h_posdef[0]) return fail(h, KB_ERR_NUMERICAL, "a set pose is not constrained by its observations (pose block not positive definite)");
   const int sweeps = sweeps2[1] ? 99 : sweeps2[0];
-  if (getenv("KB_SVD_TRACE")) std::fprintf(stderr, "[kb trace] truncated-SVD solve: n = %d, Jacobi polish sweeps = %d, QL failed = %d, rank = %d\n", n, sweeps2[0], sweeps2[1], (int)res[0]);
+  if (getenv("KB_SVD_TRACE")) std::fprintf(stderr, "[kb trace] truncated-SVD solve: n = %d, Jacobi polish sweeps = %d, QL failed = %d, rank = %d, tridiag %d kcycles, QL %d kcycles, %d QL steps, %d rotations\n", n, sweeps2[0], sweeps2[1], (int)res[0], sweeps2[2], sweeps2[3], sweeps2[4], sweeps2[5]);
   if (sweeps >= 40) return fail(h, KB_ERR_NUMERICAL, "the eigen-decomposition of the truncated-SVD solve did not converge");
   h->last_svd.n = n;
   h->last_svd.rank = (int32_t)res[0];
@@ -1678,7 +1676,9 @@ void kb_default_optimizer_options(kb_optimizer_options* o) {
 static kb_status enqueue_lm_iteration(kb_handle* h) {
   StreamCtx c = ctx(h);
   const DevProblem& D = h->d;
-  KB_CUDA(h, launch_lm_pre_solve(D, h->posdef.p, c));
+  // where the state-machine transitions run: inside the last kernel of the solve / of the evaluation (single rank: 10 launches per
+  // iteration; peer exchange: inside the exchange consumers), or in their own one-thread kernels behind an NCCL all-reduce
+  const int lm_local = h->n_ranks == 1 ? 1 : 0, lm_px = h->px_on ? 1 : 0;
   {
     StageTimer t(h, 2);
     KB_CUDA(h, launch_set_reduce(D, c));
@@ -1687,51 +1687,47 @@ static kb_status enqueue_lm_iteration(kb_handle* h) {
     StageTimer t(h, 3);
     KB_CUDA(h, launch_schur(D, -1.0, h->partials.p, h->n_partials, h->posdef.p, c));
     KB_CUDA(h, launch_schur_finalize(D, -1.0, h->partials.p, h->n_partials, true, c));
-    if (h->px_on) {
-      KB_CUDA(h, launch_px_reduce_system(D, c));
-    } else {
+    if (!h->px_on) {
       kb_status st = nccl_allreduce(h, D.Sred, (size_t)D.n_aug * D.n_aug, kNcclFloat64, kNcclSum);
       if (st != KB_OK) return st;
     }
   }
   {
     StageTimer t(h, 4);
-    KB_CUDA(h, launch_reduced_solve(D, -1.0, h->posdef.p, c));
+    KB_CUDA(h, launch_reduced_solve(D, -1.0, h->posdef.p, h->px_on, c));
   }
   {
     StageTimer t(h, 5);
-    KB_CUDA(h, launch_backsub(D, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->posdef.p, c));
+    KB_CUDA(h, launch_backsub(D, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, -1.0, h->rank == 0 ? 1 : 0, true, c));
   }
-  KB_CUDA(h, launch_rho_denominator(D, -1.0, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->rank == 0 ? 1 : 0, h->scalars.p + 2, h->posdef.p, c));
+  KB_CUDA(h, launch_solve_scalars(D, h->scalars.p + 2, h->posdef.p, h->posdef.p, lm_local, c));
   if (h->px_on) {
-    KB_CUDA(h, launch_px_combine_solve(D, h->scalars.p + 2, h->posdef.p, c));
+    KB_CUDA(h, launch_px_combine_solve(D, h->scalars.p + 2, h->posdef.p, lm_px, c));
   } else if (h->n_ranks > 1) {
     KB_CUDA(h, launch_pack_rank_scalars(h->rank_slots.p, h->rank, h->n_ranks, h->scalars.p + 2, h->posdef.p, c));
     kb_status st = nccl_allreduce(h, h->rank_slots.p, 4 * (size_t)h->n_ranks, kNcclFloat64, kNcclSum);
     if (st != KB_OK) return st;
+    KB_CUDA(h, launch_lm_post_solve(D, h->posdef.p, h->scalars.p + 2, h->rank_slots.p, h->n_ranks, c));
   }
-  KB_CUDA(h, launch_lm_post_solve(D, h->posdef.p, h->scalars.p + 2, h->rank_slots.p, h->px_on ? 1 : h->n_ranks, c));
   {
     StageTimer t(h, 6);
     KB_CUDA(h, launch_apply_update(D, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->bk_cam.p, h->bk_base.p, h->bk_sets.p, c));
   }
   {
     StageTimer t(h, 0);
-    KB_CUDA(h, launch_prep(D, c));
     {
       StageTimer t1(h, 1);
-      KB_CUDA(h, launch_linearise_assemble(D, h->vmeta.p, h->slices.p, h->slice_model_begin, true, true, c));
+      KB_CUDA(h, launch_linearise_assemble(D, h->vmeta.p, h->slices.p, h->slice_model_begin, true, true, true, c));
     }
-    KB_CUDA(h, launch_finalize_gram(D, h->cam_slice_range.p, 1, &h->ctrl.p->cost_new, true, c));
+    KB_CUDA(h, launch_finalize_gram(D, h->cam_slice_range.p, 1, &h->ctrl.p->cost_new, true, lm_local, h->trace_dev.p, h->posdef.p, c));
     if (h->px_on) {
-      KB_CUDA(h, launch_px_combine_cost(D, &h->ctrl.p->cost_new, c));
-    } else {
+      KB_CUDA(h, launch_px_combine_cost(D, &h->ctrl.p->cost_new, lm_px, h->trace_dev.p, h->posdef.p, c));
+    } else if (h->n_ranks > 1) {
       kb_status st = nccl_allreduce(h, &h->ctrl.p->cost_new, 1, kNcclFloat64, kNcclSum);
       if (st != KB_OK) return st;
+      KB_CUDA(h, launch_lm_boundary(D, h->trace_dev.p, h->posdef.p, c));
     }
   }
-  KB_CUDA(h, launch_lm_post_eval(D, h->trace_dev.p, c));
-  KB_CUDA(h, launch_lm_revert(D, h->bk_cam.p, h->bk_base.p, h->bk_sets.p, c));
   return KB_OK;
 }
 
@@ -1746,6 +1742,10 @@ static kb_status optimize_on_device(kb_handle* h, const kb_optimizer_options* o,
   std::memset(&c0, 0, sizeof(c0));
   kalibr_b200::lm_start(&c0, kalibr_b200::KB_POLICY_LEVENBERG_MARQUARDT, J0, o->lm_lambda_init, o->convergence_delta_x, o->convergence_delta_j, max_it,
                         h->semantic);
+  // the decisions of the FIRST iteration are taken here; those of every later one by the device at the end of the iteration before
+  if (!c0.done) kalibr_b200::lm_before_solve(&c0);
+  h->h_posdef[0] = 1;
+  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(h->ctrl.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));  // pageable source: staged at the call
   *h->h_ctrl = c0;
   // iterations are enqueued two at a time; the host only reads the control block back to see whether the loop has ended.
@@ -1801,6 +1801,7 @@ static kb_status optimize_on_device(kb_handle* h, const kb_optimizer_options* o,
   h->trace.assign((size_t)3 * c.iterations, 0.0);
   if (c.iterations > 0) KB_CUDA(h, cudaMemcpyAsync(h->trace.data(), h->trace_dev.p, sizeof(double) * 3 * c.iterations, cudaMemcpyDeviceToHost, h->stream));
   StreamCtx sc = ctx(h);
+  KB_CUDA(h, launch_lm_revert(h->d, h->bk_cam.p, h->bk_base.p, h->bk_sets.p, sc));  // a rejected last step is undone now (restores are lazy)
   KB_CUDA(h, launch_lm_finish(h->d, sc));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   // host-side solver state after the loop
@@ -1950,7 +1951,6 @@ kb_status kb_linearise(kb_handle* h) {
   StreamCtx c = ctx(h);
   {
     StageTimer t(h, 7);
-    KB_CUDA(h, launch_prep(h->d, c));
     KB_CUDA(h, launch_linearise_materialise(h->d, h->vmeta.p, h->slices.p, h->slice_model_begin, h->lm_bfrag_pairs, h->lm_counters.p, h->jt.p, c));
   }
   if (h->timing) {

@@ -15,7 +15,8 @@
 //   reduced_solve     K3b: dense Cholesky of the reduced system            ≙ linear_solver_cholmod.h:70-112
 //   backsub           K3c: dx_v = (V_v + d I)^-1 (b_v - W_v^T dx_c)         ≙ sparse_matrix_functions.cpp:64-83
 //   rho / apply_update                                                   ≙ LevenbergMarquardtTrustRegionPolicy.cpp:107-113, Optimizer2.cpp:290-318
-//   lm_pre_solve / lm_post_solve / lm_post_eval / lm_revert / lm_finish  device-resident LM loop
+//   lm_boundary (inside finalize_gram / px_combine_cost) / lm_after_solve (inside rho_stage2 / px_combine_solve) / lm_revert / lm_finish
+//                     device-resident LM loop: the transitions of include/kalibr_b200/lm_state_machine.h
 //                                                                       ≙ Optimizer2.cpp:215-266, LevenbergMarquardtTrustRegionPolicy.cpp:50-113
 //   px_*              NVLink peer exchange between ranks (producers are fused into schur_finalize / rho_stage2 / gram_cost)
 #include <cstdio>
@@ -231,9 +232,7 @@ __device__ __forceinline__ void px_wait(const PeerXchg& x, int which, int src, u
 // =========================================================================================================
 // prep: per camera k, the constants shared by all of its views.
 // =========================================================================================================
-__global__ void prep_kernel(DevProblem p) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n_cams || p.ctrl->done || p.ctrl->skip_eval) return;
+__device__ __forceinline__ void camera_prep(const DevProblem& p, int k) {
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
   for (int l = 0; l < k; ++l) {  // T_k = B_{k-1} ... B_0   (CalibrationTools.hpp:405-408)
     const double* b = p.baselines + l * POSE_STRIDE;
@@ -278,11 +277,22 @@ __global__ void prep_kernel(DevProblem p) {
     }
   }
 }
+__global__ void prep_kernel(DevProblem p) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p.n_cams || p.ctrl->done || p.ctrl->skip_eval) return;
+  camera_prep(p, k);
+}
 
 // per synced set: inverse pose (C^-1, -C^-1 t) and P_v, shared by the views of every camera of the set
-__global__ void __launch_bounds__(128) set_prep_kernel(DevProblem p) {
+// with_cam_prep: one extra block at the end of the grid computes the per-camera constants (prep_kernel's work) in the same launch
+__global__ void __launch_bounds__(128) set_prep_kernel(DevProblem p, int with_cam_prep) {
+  if (p.ctrl->done || p.ctrl->skip_eval) return;
+  if (with_cam_prep && blockIdx.x == gridDim.x - 1) {
+    if (threadIdx.x < p.n_cams) camera_prep(p, threadIdx.x);
+    return;
+  }
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= p.n_sets || p.ctrl->done || p.ctrl->skip_eval) return;
+  if (s >= p.n_sets) return;
   const double* pose = p.set_poses + (size_t)s * POSE_STRIDE;
   double C[9], Ci[9];
   quat2r(pose, C);
@@ -929,17 +939,23 @@ __device__ __forceinline__ double c_to_b(double c0, double c1, int ks, int arow,
 //   R0 = G00 M       rows 0..5 = Y_k, rows 6,7 = W rows of the first two intrinsics          (2 DMMA)
 //   R1 = G01^T M     rows 0..PD-3 = W rows of the remaining intrinsics, row 7 = -b_k^T       (2 DMMA)
 //   V += M^T Y_k                                                                              (2 DMMA)
-__global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p) {
+__device__ void camera_block_element(const DevProblem& p, int idx);
+// Blocks [0, n_set_blocks) reduce the sets; the remaining blocks of the grid compute the camera block U (one element per thread).
+__global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p, int n_set_blocks) {
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int arow = lane >> 2, acol = lane & 3;
   const int C = p.n_cams;
   if (p.ctrl->done || !p.ctrl->need_build) return;
+  if ((int)blockIdx.x >= n_set_blocks) {
+    camera_block_element(p, ((int)blockIdx.x - n_set_blocks) * SR_WARPS * 32 + threadIdx.x);
+    return;
+  }
   // operand element of a 6x6 row-major matrix, zero padded to 8x8:  direct[ks] = X[arow][4ks + acol],  transposed[ks] = X[4ks + acol][arow]
   const bool in0 = arow < 6, in1 = arow < 6 && acol < 2;  // k-step 0: k = acol < 4 ; k-step 1: k = 4 + acol < 6
   const int d0 = arow * 6 + acol, d1 = arow * 6 + 4 + acol;
   const int t0 = acol * 6 + arow, t1 = (4 + acol) * 6 + arow;
-  for (int set = blockIdx.x * SR_WARPS + wib; set < p.n_sets; set += gridDim.x * SR_WARPS) {
+  for (int set = blockIdx.x * SR_WARPS + wib; set < p.n_sets; set += n_set_blocks * SR_WARPS) {
     double* __restrict__ Wout = p.W + (size_t)set * p.n_c * 6;
     // lane k fetches the view of camera k (n_cams <= 32), so that the tile loads below have no dependent address chain
     int my_view = -1;
@@ -1026,10 +1042,36 @@ __global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p)
 // ---- per-camera Gram sums from the slice partials (fixed order) -------------------------------------------------
 constexpr int FG_GROUPS = 5;
 // cam_slice_range: [n_cams][n_ranges][2] slice ranges of camera k (one per chunk of the streamed slice table)
-__global__ void __launch_bounds__(GRAM_TILES * FG_GROUPS) finalize_gram_kernel(DevProblem p, const int* __restrict__ cam_slice_range, int n_ranges) {
+// end of an iteration of the device-resident loop: accept / reject of the evaluated step (skipped after a failed solve), trace, loop
+// condition, and - unless the loop has ended - the trust-region decisions of the NEXT iteration (build or not, lambda, damping)
+__device__ __forceinline__ void lm_boundary(LmCtrl* c, double* __restrict__ trace, int* __restrict__ pos_def, bool evaluated) {
+  if (evaluated) {
+    const int it = c->iterations;
+    kalibr_b200::lm_after_eval(c, c->cost_new);
+    trace[3 * it] = c->J;
+    trace[3 * it + 1] = c->deltaX;
+    trace[3 * it + 2] = c->lambda;
+  }
+  if (!c->done) {
+    kalibr_b200::lm_before_solve(c);
+    pos_def[0] = 1;
+  }
+}
+
+// The last block to finish (ticket counter) adds the cameras' e^T e entries in camera order: the cost at the linearisation point
+// (-> cost_out, and into every rank's slot as the producer of peer exchange C).  lm_mode 1 (single-rank device loop): it then also
+// runs the loop boundary, so that an iteration ends with this launch.
+__global__ void __launch_bounds__(GRAM_TILES * FG_GROUPS) finalize_gram_kernel(DevProblem p, const int* __restrict__ cam_slice_range, int n_ranges,
+                                                                               double* __restrict__ cost_out, int exchange, int lm_mode,
+                                                                               double* __restrict__ trace, int* __restrict__ pos_def) {
   __shared__ double sh[FG_GROUPS][GRAM_TILES];
+  __shared__ int s_last;
   const int k = blockIdx.x, t = threadIdx.x % GRAM_TILES, g = threadIdx.x / GRAM_TILES;
-  if (p.ctrl->done || p.ctrl->skip_eval) return;
+  if (p.ctrl->done) return;
+  if (p.ctrl->skip_eval) {  // failed solve: nothing was evaluated, but the next iteration still needs its decisions
+    if (lm_mode == 1 && blockIdx.x == 0 && threadIdx.x == 0) lm_boundary(p.ctrl, trace, pos_def, false);
+    return;
+  }
   double s = 0.0;
   for (int r = 0; r < n_ranges; ++r) {
     const int lo = cam_slice_range[(k * n_ranges + r) * 2], hi = cam_slice_range[(k * n_ranges + r) * 2 + 1];
@@ -1040,15 +1082,39 @@ __global__ void __launch_bounds__(GRAM_TILES * FG_GROUPS) finalize_gram_kernel(D
   }
   sh[g][t] = s;
   __syncthreads();
-  if (g != 0) return;
+  if (g == 0) {
 #pragma unroll
-  for (int q = 1; q < FG_GROUPS; ++q) s += sh[q][t];
-  // tile t/64: 0 -> (0,0), 1 -> (0,1), 2 -> (1,1); within a tile the mma C layout: lane = (t%64)/2, element = t%2
-  const int tile = t >> 6, lane = (t & 63) >> 1, el = t & 1;
-  const int r = (tile == 2 ? 8 : 0) + (lane >> 2), c = (tile >= 1 ? 8 : 0) + 2 * (lane & 3) + el;
-  double* G = p.sumG + (size_t)k * GRAM_SIZE;
-  G[r * GRAM_DIM + c] = s;
-  if (tile == 1) G[c * GRAM_DIM + r] = s;
+    for (int q = 1; q < FG_GROUPS; ++q) s += sh[q][t];
+    // tile t/64: 0 -> (0,0), 1 -> (0,1), 2 -> (1,1); within a tile the mma C layout: lane = (t%64)/2, element = t%2
+    const int tile = t >> 6, lane = (t & 63) >> 1, el = t & 1;
+    const int r = (tile == 2 ? 8 : 0) + (lane >> 2), c = (tile >= 1 ? 8 : 0) + 2 * (lane & 3) + el;
+    double* G = p.sumG + (size_t)k * GRAM_SIZE;
+    G[r * GRAM_DIM + c] = s;
+    if (tile == 1) G[c * GRAM_DIM + r] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // this block's Gram sum is visible before its ticket
+    const unsigned int ticket = atomicAdd(p.tickets, 1u);
+    s_last = ticket == gridDim.x - 1;
+    if (s_last) {
+      p.tickets[0] = 0u;
+      __threadfence();
+      double cost = 0.0;
+      for (int q = 0; q < p.n_cams; ++q) cost += __ldcg(p.sumG + (size_t)q * GRAM_SIZE + E_COL * GRAM_DIM + E_COL);
+      cost_out[0] = cost;
+      if (p.px.enabled && exchange) {  // exchange C: this rank's cost into every rank's slot
+        const unsigned long long e = px_next_epoch(p.px, 2);
+        for (int r = 0; r < p.px.n_ranks; ++r) p.px.base[r][px_off_c(p.px, (int)(e & 1), p.px.rank)] = cost;
+        __threadfence_system();
+        px_signal(p.px, 2, e);
+      }
+      if (lm_mode == 1) {
+        p.ctrl->cost_new = cost;
+        lm_boundary(p.ctrl, trace, pos_def, true);
+      }
+    }
+  }
 }
 
 // ---- camera block U (augmented with b_c as last row/col and the linearisation-point cost in the corner) ----------
@@ -1097,10 +1163,9 @@ __device__ __forceinline__ int red_column(const DevProblem& p, const RedIndex& r
   return 1;
 }
 
-__global__ void __launch_bounds__(256) camera_block_kernel(DevProblem p) {
+__device__ void camera_block_element(const DevProblem& p, int idx) {
   const int n = p.n_aug;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * n || p.ctrl->done || !p.ctrl->need_build) return;
+  if (idx >= n * n) return;
   const int i = idx / n, j = idx % n;
   if (i > j) return;
   const RedIndex ri = red_index(p, i), rj = red_index(p, j);
@@ -1139,23 +1204,14 @@ __global__ void __launch_bounds__(256) camera_block_kernel(DevProblem p) {
   p.U[(size_t)j * n + i] = acc;
 }
 
-// cost at the linearisation point = sum_k G_k[e][e]
-__global__ void gram_cost_kernel(DevProblem p, double* __restrict__ out, int exchange) {
-  if (threadIdx.x == 0 && blockIdx.x == 0 && !p.ctrl->done && !p.ctrl->skip_eval) {
-    double s = 0.0;
-    for (int k = 0; k < p.n_cams; ++k) s += p.sumG[(size_t)k * GRAM_SIZE + E_COL * GRAM_DIM + E_COL];
-    out[0] = s;
-    if (p.px.enabled && exchange) {  // exchange C: this rank's cost into every rank's slot
-      const unsigned long long e = px_next_epoch(p.px, 2);
-      for (int r = 0; r < p.px.n_ranks; ++r) p.px.base[r][px_off_c(p.px, (int)(e & 1), p.px.rank)] = s;
-      __threadfence_system();
-      px_signal(p.px, 2, e);
-    }
-  }
-}
 // exchange C consumer: total cost, summed in rank order
-__global__ void px_combine_cost_kernel(DevProblem p, double* __restrict__ out) {
-  if (p.ctrl->done || p.ctrl->skip_eval) return;
+// lm_mode 1 (device loop over the peer exchange): the loop boundary runs here, on the combined cost
+__global__ void px_combine_cost_kernel(DevProblem p, double* __restrict__ out, int lm_mode, double* __restrict__ trace, int* __restrict__ pos_def) {
+  if (p.ctrl->done) return;
+  if (p.ctrl->skip_eval) {
+    if (lm_mode == 1) lm_boundary(p.ctrl, trace, pos_def, false);
+    return;
+  }
   const unsigned long long e = px_cur_epoch(p.px, 2);
   double s = 0.0;
   for (int r = 0; r < p.px.n_ranks; ++r) {
@@ -1163,6 +1219,10 @@ __global__ void px_combine_cost_kernel(DevProblem p, double* __restrict__ out) {
     s += __ldcg(p.px.base[p.px.rank] + px_off_c(p.px, (int)(e & 1), r));
   }
   out[0] = s;
+  if (lm_mode == 1 && !p.ctrl->done) {
+    p.ctrl->cost_new = s;
+    lm_boundary(p.ctrl, trace, pos_def, true);
+  }
 }
 // exchange A consumer: the reduced camera system = the ranks' partials summed in rank order, spread over many CTAs
 __global__ void __launch_bounds__(256) px_reduce_system_kernel(DevProblem p) {
@@ -1178,7 +1238,7 @@ __global__ void __launch_bounds__(256) px_reduce_system_kernel(DevProblem p) {
   p.Sred[idx] = v;
 }
 // exchange B consumer: rho denominator (sum), max|dx| (max), pos-def (min) over the ranks, in rank order
-__global__ void px_combine_solve_kernel(DevProblem p, double* __restrict__ rho_max, int* __restrict__ pos_def) {
+__global__ void px_combine_solve_kernel(DevProblem p, double* __restrict__ rho_max, int* __restrict__ pos_def, int lm_mode) {
   if (p.ctrl->done) return;
   const unsigned long long e = px_cur_epoch(p.px, 1);
   double rho = 0.0, mx = 0.0;
@@ -1193,17 +1253,17 @@ __global__ void px_combine_solve_kernel(DevProblem p, double* __restrict__ rho_m
   rho_max[0] = rho;
   rho_max[1] = mx;
   pos_def[0] = pd;
+  if (lm_mode == 1 && !p.ctrl->done) kalibr_b200::lm_after_solve(p.ctrl, rho, mx, pd);
 }
 
 // =========================================================================================================
 // Schur complement on the FP64 tensor pipe:  partial = sum_{v in CTA slice} Z_v Z_v^T,  Z_v = [W_v ; b_v^T] L_v^-T,
-// (V_v + d I) = L_v L_v^T.  pose_factor_kernel inverts the 6x6 factors (thread per set); schur_kernel then turns the rows
-// of [W_v ; b_v^T] into Z rows with a 6x6 triangular product and accumulates Z Z^T with DMMA, SC_SETS sets per step.
+// (V_v + d I) = L_v L_v^T.  Every CTA first inverts the 6x6 factors of its own slice of sets (thread per set, -> p.Lv, which the
+// back substitution reads too), then turns the rows of [W_v ; b_v^T] into Z rows with a 6x6 triangular product and accumulates
+// Z Z^T with DMMA, SC_SETS sets per step.
 // =========================================================================================================
-__global__ void __launch_bounds__(128) pose_factor_kernel(DevProblem p, double damping_arg, int* __restrict__ pos_def_flag) {
-  const int set = blockIdx.x * blockDim.x + threadIdx.x;
-  if (set >= p.n_sets || p.ctrl->done) return;
-  const double damping = damping_arg >= 0.0 ? damping_arg : p.ctrl->damping;
+// inverse Cholesky factor of V_v + d I of one set -> p.Lv (row-major lower); clears the flag when the block is not positive definite
+__device__ __forceinline__ void pose_factor(const DevProblem& p, int set, double damping, int* __restrict__ pos_def_flag) {
   double L[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) L[i] = p.V[(size_t)set * 36 + i];
@@ -1237,7 +1297,8 @@ constexpr int SC_LD = 36;               // ld % 16 == 4 keeps the operand loads 
 // straight into the other Z buffer while the DMMA phase runs on the current one; afterwards every thread turns the rows it
 // copied into Z rows in place (z = L^-1 w, a 6x6 triangular product).
 template <int WARPS, int MAX_PAIRS>
-__global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, double* __restrict__ partials, int sets_per_cta) {
+__global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, double* __restrict__ partials, int sets_per_cta, double damping_arg,
+                                                              int* __restrict__ pos_def_flag) {
   extern __shared__ __align__(16) double smem[];
   const int n = p.n_aug;
   const int nt = (n + 7) >> 3;
@@ -1269,6 +1330,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
   }
   for (int i = tid; i < 2 * n_pad * SC_LD; i += blockDim.x) Zbuf[i] = 0.0;
   const int s_lo = blockIdx.x * sets_per_cta, s_hi = min(p.n_sets, s_lo + sets_per_cta);
+  {
+    // the factors of this slice (the CTAs of a gridDim.y split compute the same values: identical, benign double stores)
+    const double damping = damping_arg >= 0.0 ? damping_arg : p.ctrl->damping;
+    for (int set = s_lo + tid; set < s_hi; set += blockDim.x) pose_factor(p, set, damping, pos_def_flag);
+  }
   __syncthreads();
   // raw rows of the sets [s0, s0 + SC_SETS) -> Zs, their inverse factors -> Ls  (asynchronous; rows of sets past the end are zeroed)
   auto fetch = [&](double* Zs, double* Ls, int s0) {
@@ -1494,7 +1560,7 @@ __device__ __forceinline__ void panel_rows(double* __restrict__ Lp, int j0, int 
 //   3. thread per row: L[row][panel] = A[row][panel] Ldd^-T by forward substitution.
 // Then L^T x = y panel by panel from the last: one thread solves the 8x8 triangle, all threads push the panel's x into the
 // rows above (two barriers per panel instead of one per unknown).
-__global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping_arg, int* __restrict__ pos_def_flag) {
+__global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping_arg, int* __restrict__ pos_def_flag, int from_peers) {
   extern __shared__ __align__(16) double Lp[];  // packed lower triangle, n_rows rows (zero padded), then rd[n_rows], x[n_rows]
   __shared__ int s_ok;
   const int n = p.n_aug, nc = p.n_c;
@@ -1506,10 +1572,24 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < n_rows * (n_rows + 1) / 2; idx += RS_THREADS) Lp[idx] = 0.0;
   __syncthreads();
+  // from_peers: the reduced system is the sum of the ranks' partials in the peer-exchange slots (exchange A): wait for the epoch
+  // flags, then sum the slots in rank order while loading - no separate reduction launch
+  const double* slots = nullptr;
+  if (from_peers) {
+    const unsigned long long e = px_cur_epoch(p.px, 0);
+    if (tid < p.px.n_ranks) px_wait(p.px, 0, tid, e, p.ctrl);
+    __syncthreads();
+    slots = p.px.base[p.px.rank] + px_off_a(p.px, (int)(e & 1), 0);
+  }
   for (int idx = tid; idx < n * n; idx += RS_THREADS) {
     const int i = idx / n, k = idx % n;
     if (k > i) continue;
-    double v = p.Sred[idx];
+    double v = 0.0;
+    if (from_peers) {
+      for (int r = 0; r < p.px.n_ranks; ++r) v += __ldcg(slots + (size_t)r * p.px.na2 + idx);
+    } else {
+      v = p.Sred[idx];
+    }
     if (i == k && i < nc) v += damping;
     Lp[tri(i, k)] = v;
   }
@@ -1641,6 +1721,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) sym_eig_kernel(DevProblem p, d
   }
   if (tid < EIG_MAX_N) e[tid] = 0.0;
   __syncthreads();
+  const long long t_start = clock64();
   // ---- Householder tridiagonalisation: H_k zeroes A[k+2.., k]; Z <- Z H_k ----
   for (int k = 0; k + 2 < n; ++k) {
     double part = 0.0;
@@ -1705,6 +1786,8 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) sym_eig_kernel(DevProblem p, d
   // application is off the critical path. ----
   int l = 0, iter = 0;  // thread 0 only
   int buf = 0, have_prev = 0, failed = 0;
+  int n_steps = 0, n_rot = 0;  // thread 0: diagnostics
+  const long long t_tridiag = clock64();
   for (;;) {
     if (tid == 0) {
       s_has[buf] = 0;
@@ -1724,7 +1807,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) sym_eig_kernel(DevProblem p, d
           break;
         }
         double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
-        double r = sqrt(g * g + 1.0);
+        const double r = sqrt(g * g + 1.0);
         g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
         double sr = 1.0, c = 1.0, pp = 0.0;
         double ei = e[m - 1], di = d[m - 1];
@@ -1732,8 +1815,10 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) sym_eig_kernel(DevProblem p, d
         bool split = false;
         for (i = m - 1; i >= l; --i) {
           const double en = i > l ? e[i - 1] : 0.0, dn = i > l ? d[i - 1] : 0.0;  // operands of the next rotation, off the chain
+          // critical path per rotation: rr -> rsqrt -> c -> r2 -> g -> rr (one reciprocal square root and a handful of dependent
+          // FP64 operations); the square root itself, r = rr / sqrt(rr), is off the chain
           const double f = sr * ei, b = c * ei;
-          const double rr = f * f + g * g;
+          const double rr = fma(g, g, f * f);
           if (rr == 0.0) {
             e[i + 1] = 0.0;
             d[i + 1] -= pp;
@@ -1742,20 +1827,21 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) sym_eig_kernel(DevProblem p, d
             break;
           }
           const double ir = rsqrt(rr);
-          r = sqrt(rr);
-          e[i + 1] = r;
+          const double gd = d[i + 1] - pp;
+          e[i + 1] = rr * ir;
           sr = f * ir;
           c = g * ir;
-          g = d[i + 1] - pp;
-          r = (di - g) * sr + 2.0 * c * b;
-          pp = sr * r;
-          d[i + 1] = g + pp;
-          g = c * r - b;
+          const double r2 = fma(di - gd, sr, 2.0 * c * b);
+          pp = sr * r2;
+          d[i + 1] = gd + pp;
+          g = fma(c, r2, -b);
           cs[buf][i] = c;
           sn[buf][i] = sr;
           ei = en;
           di = dn;
         }
+        ++n_steps;
+        n_rot += m - 1 - i;
         s_m[buf] = m;
         s_lo[buf] = i + 1;  // rotations exist for the indices m - 1 .. i + 1
         s_has[buf] = (i + 1 <= m - 1) ? 1 : 0;
@@ -1789,7 +1875,13 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) sym_eig_kernel(DevProblem p, d
     buf ^= 1;
     if (done && !have_prev) break;
   }
-  if (tid == 0) status_out[0] = failed;
+  if (tid == 0) {
+    status_out[0] = failed;
+    status_out[1] = (int)((t_tridiag - t_start) >> 10);  // diagnostics (KB_SVD_TRACE): kilo-cycles of the two phases, QL steps, rotations
+    status_out[2] = (int)((clock64() - t_tridiag) >> 10);
+    status_out[3] = n_steps;
+    status_out[4] = n_rot;
+  }
   // ---- sorted output: |lambda| descending (ties by index) ----
   if (tid < n) {
     const double me = fabs(d[tid]);
@@ -1989,15 +2081,31 @@ __global__ void __launch_bounds__(256) svd_truncated_solve_kernel(DevProblem p, 
 // =========================================================================================================
 // back substitution for the poses + scatter of dx into design-variable order
 // =========================================================================================================
+// partial (may be null): [gridDim.x][2] = per block (sum over its sets of dx_v^T (lambda dx_v + b_v), max |dx_v|); block 0 adds the
+// camera-side part (dx_c^T b_c of this rank, + lambda |dx_c|^2 when include_shared) - stage 1 of the rho denominator for free
 __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
-                                                      const int* __restrict__ cam_cols) {
-  const int lane = threadIdx.x & 31;
+                                                      const int* __restrict__ cam_cols, double lambda_arg, int include_shared,
+                                                      double* __restrict__ partial) {
+  __shared__ double sh_s[8], sh_m[8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (p.ctrl->done) return;
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < p.n_c; i += blockDim.x) p.dx[cam_cols[i]] = p.dxc[i];
-  if (gw >= p.n_sets) return;
+  const double lambda = lambda_arg >= 0.0 ? lambda_arg : p.ctrl->lambda;
+  double ps = 0.0, pm = 0.0;  // this warp's contribution (lane 0)
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < p.n_c; i += blockDim.x) {
+      const double d = p.dxc[i];
+      p.dx[cam_cols[i]] = d;
+      ps += d * p.U[(size_t)i * p.n_aug + p.n_c];  // this rank's partial b_c
+      if (include_shared) ps += lambda * d * d;
+      pm = fmax(pm, fabs(d));
+    }
+    ps = warp_sum(ps);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+  }
   const int set = gw;
+  if (set < p.n_sets) {
   double acc[6] = {0, 0, 0, 0, 0, 0};
   const double* W = p.W + (size_t)set * p.n_c * 6;
   for (int i = lane; i < p.n_c; i += 32) {
@@ -2033,6 +2141,21 @@ __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* _
       p.dx[set_col_q[set] + c] = r[c];
       p.dx[set_col_t[set] + c] = r[3 + c];
     }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      ps += r[c] * (lambda * r[c] + p.bv[(size_t)set * 6 + c]);
+      pm = fmax(pm, fabs(r[c]));
+    }
+  }
+  }
+  if (!partial) return;
+  if (lane == 0) { sh_s[wib] = ps; sh_m[wib] = pm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0, m = 0.0;
+    for (int w = 0; w < 8; ++w) { s += sh_s[w]; m = fmax(m, sh_m[w]); }  // fixed order
+    partial[2 * blockIdx.x] = s;
+    partial[2 * blockIdx.x + 1] = m;
   }
 }
 
@@ -2079,16 +2202,22 @@ __global__ void __launch_bounds__(256) rho_stage1_kernel(DevProblem p, double la
   block_sum_max(s, m, sh_s, sh_m);
   if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s; partial[2 * blockIdx.x + 1] = m; }
 }
-__global__ void __launch_bounds__(RHO_BLOCKS) rho_stage2_kernel(const LmCtrl* __restrict__ ctrl, PeerXchg px, const int* __restrict__ pos_def,
-                                                                const double* __restrict__ partial, int n, double* __restrict__ out) {
+constexpr int RHO2_THREADS = 256;
+// lm_mode 1 (single-rank device loop): thread 0 also runs the after-solve transition of the state machine on the result
+__global__ void __launch_bounds__(RHO2_THREADS) rho_stage2_kernel(LmCtrl* __restrict__ ctrl, PeerXchg px, const int* __restrict__ pos_def,
+                                                                  const double* __restrict__ partial, int n, double* __restrict__ out, int lm_mode) {
   __shared__ double sh_s[32], sh_m[32];
   if (ctrl->done) return;
-  double s = threadIdx.x < n ? partial[2 * threadIdx.x] : 0.0;
-  double m = threadIdx.x < n ? partial[2 * threadIdx.x + 1] : 0.0;
+  double s = 0.0, m = 0.0;
+  for (int i = threadIdx.x; i < n; i += RHO2_THREADS) {  // fixed assignment of partials to threads, fixed order inside a thread
+    s += partial[2 * i];
+    m = fmax(m, partial[2 * i + 1]);
+  }
   block_sum_max(s, m, sh_s, sh_m);
   if (threadIdx.x == 0) {
     out[0] = s;
     out[1] = m;
+    if (lm_mode == 1) kalibr_b200::lm_after_solve(ctrl, s, m, pos_def[0]);
     if (px.enabled) {  // exchange B: (rho partial, max|dx|, pos-def) into every rank's slot
       const unsigned long long e = px_next_epoch(px, 1);
       const double pd = (double)pos_def[0];
@@ -2134,11 +2263,16 @@ __global__ void __launch_bounds__(256) apply_update_kernel(DevProblem p, const i
                                                            double* __restrict__ backup_cam, double* __restrict__ backup_base, double* __restrict__ backup_sets) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (p.ctrl->done || p.ctrl->skip_eval) return;
+  // device-resident loop: a rejected step is undone lazily, here (the backup IS the state to start from) - outside the loop the flag is 0
+  const bool restore = p.ctrl->revert != 0;
   if (idx < p.n_sets) {
     double* pose = p.set_poses + (size_t)idx * POSE_STRIDE;
     double* bk = backup_sets + (size_t)idx * POSE_STRIDE;
 #pragma unroll
-    for (int i = 0; i < POSE_STRIDE; ++i) bk[i] = pose[i];
+    for (int i = 0; i < POSE_STRIDE; ++i) {
+      if (restore) pose[i] = bk[i];
+      else bk[i] = pose[i];
+    }
     double dq[3], dt[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { dq[c] = p.dx[set_col_q[idx] + c]; dt[c] = p.dx[set_col_t[idx] + c]; }
@@ -2150,14 +2284,18 @@ __global__ void __launch_bounds__(256) apply_update_kernel(DevProblem p, const i
     for (int k = threadIdx.x; k < p.n_cams; k += blockDim.x) {
       const int PD = p.cam_P[k] + p.cam_D[k];
       for (int c = 0; c < CAM_PARAM_STRIDE; ++c) {
-        const double v = p.cam_params[k * CAM_PARAM_STRIDE + c];
+        const double v = restore ? backup_cam[k * CAM_PARAM_STRIDE + c] : p.cam_params[k * CAM_PARAM_STRIDE + c];
         backup_cam[k * CAM_PARAM_STRIDE + c] = v;
+        p.cam_params[k * CAM_PARAM_STRIDE + c] = v;
         if (c < PD) p.cam_params[k * CAM_PARAM_STRIDE + c] = v + p.dxc[p.intr_off[k] + c];
       }
     }
     for (int j = threadIdx.x; j < p.n_cams - 1; j += blockDim.x) {
       double* b = p.baselines + j * POSE_STRIDE;
-      for (int i = 0; i < POSE_STRIDE; ++i) backup_base[j * POSE_STRIDE + i] = b[i];
+      for (int i = 0; i < POSE_STRIDE; ++i) {
+        if (restore) b[i] = backup_base[j * POSE_STRIDE + i];
+        else backup_base[j * POSE_STRIDE + i] = b[i];
+      }
       double dq[3];
       for (int c = 0; c < 3; ++c) dq[c] = p.dxc[p.base_off[j] + c];
       update_quat(b, dq);
@@ -2171,13 +2309,6 @@ __global__ void __launch_bounds__(256) apply_update_kernel(DevProblem p, const i
 // Optimizer2::optimize (BE/src/Optimizer2.cpp:215-266) and LevenbergMarquardtTrustRegionPolicy::solveSystemImplementation
 // (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:50-113), so that no host round trip sits inside an iteration.
 // =========================================================================================================
-// before the solve: TrustRegionPolicy::solveSystem bookkeeping, rho, the lambda schedule, build / no build, damping
-__global__ void lm_pre_solve_kernel(LmCtrl* c, int* pos_def) {
-  if (c->done) return;
-  kalibr_b200::lm_before_solve(c);
-  pos_def[0] = 1;
-}
-
 // after the solve: combine the ranks' (rho, max|dx|, pos-def) slots, the lambda^2 / lambda residual (Q2), failed solves
 __global__ void lm_post_solve_kernel(LmCtrl* c, const int* pos_def, const double* rho_max, const double* rank_slots, int n_ranks) {
   if (c->done) return;
@@ -2196,14 +2327,11 @@ __global__ void lm_post_solve_kernel(LmCtrl* c, const int* pos_def, const double
   kalibr_b200::lm_after_solve(c, rho, mx, pd);
 }
 
-// after the evaluation of the trial state: accept / reject, trace, loop condition
-__global__ void lm_post_eval_kernel(LmCtrl* c, double* trace) {
-  if (c->done || c->skip_eval) return;
-  const int it = c->iterations;
-  kalibr_b200::lm_after_eval(c, c->cost_new);
-  trace[3 * it] = c->J;
-  trace[3 * it + 1] = c->deltaX;
-  trace[3 * it + 2] = c->lambda;
+// NCCL path only (the single-rank and peer-exchange paths run the boundary inside finalize_gram / px_combine_cost): after the
+// all-reduce of the cost
+__global__ void lm_boundary_kernel(LmCtrl* c, double* trace, int* pos_def) {
+  if (c->done) return;
+  lm_boundary(c, trace, pos_def, !c->skip_eval);
 }
 
 // restore the backup when the step was rejected (idempotent: a finished loop may run it again with the same flag)
@@ -2349,10 +2477,10 @@ static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const
 
 // slice_model_begin[m] .. [m+1]: slices of camera model m
 cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, const int4* slices, const int* smb, bool write_e, bool with_set_prep,
-                                      StreamCtx& s) {
+                                      bool with_cam_prep, StreamCtx& s) {
   cudaError_t e;
-  if (with_set_prep && p.n_sets > 0) {
-    set_prep_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p);
+  if ((with_set_prep && p.n_sets > 0) || with_cam_prep) {  // per-set constants and (extra block) per-camera constants in one launch
+    set_prep_kernel<<<(with_set_prep ? (p.n_sets + 127) / 128 : 0) + (with_cam_prep ? 1 : 0), 128, 0, s.stream>>>(p, with_cam_prep ? 1 : 0);
     KB_LAUNCHED(s);
   }
   e = for_each_model_concurrently(smb, s, [&](int m, StreamCtx& c) -> cudaError_t {
@@ -2372,11 +2500,11 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, co
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-// per-camera Gram sums + cost of the linearisation point (-> cost_out[0])
-cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, int n_ranges, double* cost_out, bool exchange_cost, StreamCtx& s) {
-  finalize_gram_kernel<<<p.n_cams, GRAM_TILES * FG_GROUPS, 0, s.stream>>>(p, cam_slice_range, n_ranges);
-  KB_LAUNCHED(s);
-  gram_cost_kernel<<<1, 32, 0, s.stream>>>(p, cost_out, exchange_cost ? 1 : 0);
+// per-camera Gram sums + cost of the linearisation point (-> cost_out[0]); lm_mode 1: + the loop boundary of the device-resident loop
+cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, int n_ranges, double* cost_out, bool exchange_cost, int lm_mode,
+                                 double* trace, int* pos_def, StreamCtx& s) {
+  finalize_gram_kernel<<<p.n_cams, GRAM_TILES * FG_GROUPS, 0, s.stream>>>(p, cam_slice_range, n_ranges, cost_out, exchange_cost ? 1 : 0, lm_mode, trace,
+                                                                          pos_def);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2401,10 +2529,8 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
                                          unsigned int* counters, double* jt, StreamCtx& s) {
   cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * NUM_MODELS, s.stream);
   if (e != cudaSuccess) return e;
-  if (p.n_sets > 0) {
-    set_prep_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p);
-    KB_LAUNCHED(s);
-  }
+  set_prep_kernel<<<(p.n_sets + 127) / 128 + 1, 128, 0, s.stream>>>(p, 1);  // per-set and (last block) per-camera constants
+  KB_LAUNCHED(s);
   e = for_each_model_concurrently(smb, s, [&](int m, StreamCtx& c) -> cudaError_t {
     switch (m) {
 #define KB_LM(M)                                                                                                          \
@@ -2419,15 +2545,11 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-// V_v, b_v, W_v from the view blocks; U, b_c from the per-camera Gram sums
+// V_v, b_v, W_v from the view blocks (first blocks of the grid); U, b_c from the per-camera Gram sums (remaining blocks): one launch
 cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s) {
-  if (p.n_sets > 0) {
-    const int grid = min((p.n_sets + SR_WARPS - 1) / SR_WARPS, sm_count() * 8);
-    set_reduce_kernel<<<grid, SR_WARPS * 32, 0, s.stream>>>(p);
-    KB_LAUNCHED(s);
-  }
+  const int set_blocks = p.n_sets > 0 ? min((p.n_sets + SR_WARPS - 1) / SR_WARPS, sm_count() * 8) : 0;
   const int n2 = p.n_aug * p.n_aug;
-  camera_block_kernel<<<(n2 + 255) / 256, 256, 0, s.stream>>>(p);
+  set_reduce_kernel<<<set_blocks + (n2 + SR_WARPS * 32 - 1) / (SR_WARPS * 32), SR_WARPS * 32, 0, s.stream>>>(p, set_blocks);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2449,7 +2571,7 @@ size_t schur_partial_stride(const DevProblem& p) {
 }
 
 template <int WARPS, int MAX_PAIRS>
-static cudaError_t launch_schur_t(const DevProblem& p, double* partials, int n_partials, StreamCtx& s) {
+static cudaError_t launch_schur_t(const DevProblem& p, double damping, double* partials, int n_partials, int* flag, StreamCtx& s) {
   const int n_pad = ((p.n_aug + 7) >> 3) * 8;
   const size_t smem = sizeof(double) * (2 * (size_t)n_pad * SC_LD + 2 * SC_SETS * 36);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
@@ -2457,20 +2579,17 @@ static cudaError_t launch_schur_t(const DevProblem& p, double* partials, int n_p
   const int nt = (p.n_aug + 7) >> 3;
   const int npairs = nt * (nt + 1) / 2;
   const int gy = (npairs + WARPS * MAX_PAIRS - 1) / (WARPS * MAX_PAIRS);
-  schur_kernel<WARPS, MAX_PAIRS><<<dim3(n_partials, gy), WARPS * 32, smem, s.stream>>>(p, partials, schur_sets_per_cta(p));
+  schur_kernel<WARPS, MAX_PAIRS><<<dim3(n_partials, gy), WARPS * 32, smem, s.stream>>>(p, partials, schur_sets_per_cta(p), damping, flag);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
 
 cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* flag, StreamCtx& s) {
-  // every CTA writes all of its tile pairs (zeros when it has no sets), so the partials need no clearing
-  if (p.n_sets > 0) {
-    pose_factor_kernel<<<(p.n_sets + 127) / 128, 128, 0, s.stream>>>(p, damping, flag);
-    KB_LAUNCHED(s);
-  }
+  // every CTA writes all of its tile pairs (zeros when it has no sets), so the partials need no clearing; the 6x6 pose factors are
+  // computed by the CTAs themselves
   const int nt = (p.n_aug + 7) >> 3;
-  if (nt <= 6) return launch_schur_t<8, 3>(p, partials, n_partials, s);
-  return launch_schur_t<8, 14>(p, partials, n_partials, s);  // nt <= 14: one CTA per slice; larger systems: tile pairs split over gridDim.y
+  if (nt <= 6) return launch_schur_t<8, 3>(p, damping, partials, n_partials, flag, s);
+  return launch_schur_t<8, 14>(p, damping, partials, n_partials, flag, s);  // nt <= 14: one CTA per slice; larger systems: tile pairs split over gridDim.y
 }
 
 cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const double* partials, int n_partials, bool, StreamCtx& s) {
@@ -2480,19 +2599,32 @@ cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const
   return cudaGetLastError();
 }
 
-cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, StreamCtx& s) {
+cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, bool from_peers, StreamCtx& s) {
   const size_t n_rows = ((p.n_aug + RS_NB - 1) / RS_NB) * RS_NB + RS_NB;
   const size_t smem = sizeof(double) * (n_rows * (n_rows + 1) / 2 + 2 * n_rows);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
   if (cudaError_t e = ensure_dynamic_smem(reduced_solve_kernel, smem, attr_smem_dev); e != cudaSuccess) return e;
-  reduced_solve_kernel<<<1, RS_THREADS, smem, s.stream>>>(p, damping, pos_def_flag);
+  reduced_solve_kernel<<<1, RS_THREADS, smem, s.stream>>>(p, damping, pos_def_flag, from_peers && p.px.enabled ? 1 : 0);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
 
-cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, int*, StreamCtx& s) {
-  const int warps = p.n_sets > 0 ? p.n_sets : 1;
-  backsub_kernel<<<(warps * 32 + 255) / 256, 256, 0, s.stream>>>(p, set_col_q, set_col_t, cam_cols);
+int backsub_blocks(const DevProblem& p) { return ((p.n_sets > 0 ? p.n_sets : 1) * 32 + 255) / 256; }
+// back substitution; with_rho: its blocks also leave the stage-1 partials of the rho denominator / max|dx| in p.rho_partial, and
+// launch_solve_scalars finishes them
+cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, double lambda, int include_shared,
+                           bool with_rho, StreamCtx& s) {
+  backsub_kernel<<<backsub_blocks(p), 256, 0, s.stream>>>(p, set_col_q, set_col_t, cam_cols, lambda, include_shared, with_rho ? p.rho_partial : nullptr);
+  KB_LAUNCHED(s);
+  return cudaGetLastError();
+}
+// out2 = (dx^T (lambda dx + rhs), max|dx|) of this rank from the partials launch_backsub left; producer of peer exchange B when
+// pos_def_for_exchange is given; lm_mode 1: + the after-solve transition of the device-resident loop (single rank)
+cudaError_t launch_solve_scalars(const DevProblem& p, double* out2, const int* pos_def_for_exchange, const int* pos_def, int lm_mode, StreamCtx& s) {
+  PeerXchg px = p.px;
+  if (!pos_def_for_exchange) px.enabled = 0;
+  rho_stage2_kernel<<<1, RHO2_THREADS, 0, s.stream>>>(p.ctrl, px, pos_def_for_exchange ? pos_def_for_exchange : pos_def, p.rho_partial, backsub_blocks(p), out2,
+                                                      lm_mode);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2505,7 +2637,7 @@ cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int
   KB_LAUNCHED(s);
   PeerXchg px = p.px;
   if (!pos_def_for_exchange) px.enabled = 0;  // a rho query outside a solve is not an exchange step
-  rho_stage2_kernel<<<1, RHO_BLOCKS, 0, s.stream>>>(p.ctrl, px, pos_def_for_exchange, partial, blocks, out2);
+  rho_stage2_kernel<<<1, RHO2_THREADS, 0, s.stream>>>(p.ctrl, px, pos_def_for_exchange, partial, blocks, out2, 0);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2521,13 +2653,13 @@ cudaError_t launch_px_reduce_system(const DevProblem& p, StreamCtx& s) {
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
-cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max, int* pos_def_flag, StreamCtx& s) {
-  px_combine_solve_kernel<<<1, 1, 0, s.stream>>>(p, rho_max, pos_def_flag);
+cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max, int* pos_def_flag, int lm_mode, StreamCtx& s) {
+  px_combine_solve_kernel<<<1, 1, 0, s.stream>>>(p, rho_max, pos_def_flag, lm_mode);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
-cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, StreamCtx& s) {
-  px_combine_cost_kernel<<<1, 1, 0, s.stream>>>(p, cost);
+cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, int lm_mode, double* trace, int* pos_def, StreamCtx& s) {
+  px_combine_cost_kernel<<<1, 1, 0, s.stream>>>(p, cost, lm_mode, trace, pos_def);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2576,18 +2708,13 @@ cudaError_t launch_svd_solve(const DevProblem& p, const double* diag_h, double n
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
-cudaError_t launch_lm_pre_solve(const DevProblem& p, int* pos_def_flag, StreamCtx& s) {
-  lm_pre_solve_kernel<<<1, 1, 0, s.stream>>>(p.ctrl, pos_def_flag);
-  KB_LAUNCHED(s);
-  return cudaGetLastError();
-}
 cudaError_t launch_lm_post_solve(const DevProblem& p, const int* pos_def_flag, const double* rho_max, const double* rank_slots, int n_ranks, StreamCtx& s) {
   lm_post_solve_kernel<<<1, 1, 0, s.stream>>>(p.ctrl, pos_def_flag, rho_max, rank_slots, n_ranks);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
-cudaError_t launch_lm_post_eval(const DevProblem& p, double* trace, StreamCtx& s) {
-  lm_post_eval_kernel<<<1, 1, 0, s.stream>>>(p.ctrl, trace);
+cudaError_t launch_lm_boundary(const DevProblem& p, double* trace, int* pos_def, StreamCtx& s) {
+  lm_boundary_kernel<<<1, 1, 0, s.stream>>>(p.ctrl, trace, pos_def);
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }

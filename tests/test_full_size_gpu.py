@@ -225,7 +225,7 @@ def test_failed_solves_are_sticky_like_optimizer2(capi, oracle_lib, device_loop)
     os_, ot = o.optimize(opt)
     assert os_.linear_solver_failure == 1 and os_.iterations == 0 and os_.failed_iterations == 9
     assert (gs.iterations, gs.failed_iterations, gs.linear_solver_failure) == (os_.iterations, os_.failed_iterations, os_.linear_solver_failure)
-    assert gs.j_final == os_.j_final == gs.j_start  # nothing was applied
+    assert gs.j_final == gs.j_start and abs(gs.j_final - os_.j_final) <= 1e-11 * os_.j_final  # nothing was applied
     assert np.array_equal(g.camera_params(), p.cam_params) and np.array_equal(g.set_poses(), p.set_poses)
 
 
