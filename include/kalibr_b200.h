@@ -290,6 +290,11 @@ KB_API kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* 
  * LinearSolver::getSVDRank() keeps returning after analyzeMarginal(), which only recomputes them when no solve has run
  * (LinearSolver.cpp:517-523) */
 KB_API kb_status kb_get_last_svd_solve(const kb_handle* h, kb_svd_solve_result* out);
+/* |eigenvalues| (descending) and eigenvectors of the (column-scaled) reduced system of the most recent kb_solve_system_svd, as they
+ * sit on the device right after it: ≙ LinearSolver::getSingularValues / getNullSpace / getRowSpace after optimize() and before
+ * analyzeMarginal() (IC/src/core/IncrementalEstimator.cpp:387-401).  V: [n][n] row-major, column k = k-th vector; columns: [n]
+ * design-variable column of each row of V.  Any pointer may be NULL.  A later kb_analyze_marginal* overwrites the buffers. */
+KB_API kb_status kb_get_last_svd_decomposition(kb_handle* h, double* singular_values, double* V, int32_t* columns);
 KB_API kb_status kb_optimize_gauss_newton(kb_handle* h, const kb_optimizer_options* o, const kb_svd_solver_options* so, kb_solution* out);
 
 /* ---- marginal analysis of the calibration block --------------------------------
@@ -340,6 +345,24 @@ KB_API kb_status kb_get_jacobian_ccs(kb_handle* h, int64_t* col_ptr /*[2*local t
  * ascending.  values are the blocks column-major one after another (value_ptr[k] offsets).  Call with NULL arrays to query counts. */
 KB_API kb_status kb_get_hessian_blocks(kb_handle* h, int64_t* n_blocks, int64_t* n_values, int64_t* col_ptr /*[n_dv+1]*/,
                                        int32_t* block_row, int64_t* value_ptr, double* values);
+/* ---- a live handle grows by synced sets ------------------------------------------------------------------------
+ * ≙ IncrementalOptimizationProblem::add / remove of one batch (IC/src/core/IncrementalOptimizationProblem.cpp:186-260; a kalibr2 batch
+ *   is one synced set: CalibrationTools.hpp:460-521) on the problem a handle holds, instead of re-creating the handle per batch:
+ *   kb_append_set adds synced set number kb "n_sets" with its views (terms appended behind the existing ones: only the new
+ *   observations are uploaded; device arrays grow by capacity doubling; streams, events, pinned buffers and every buffer that is
+ *   already large enough are kept) and its pose guess; kb_remove_last_set drops the last synced set again (a rejected batch:
+ *   IncrementalEstimator.cpp:520-530).  The design-variable layout follows the handle's driver order with the new number of sets
+ *   (kb_jcols / kb_get_dv_layout change).  Single rank.  view_cam: [n_views] distinct cameras; view_begin: [n_views + 1] term
+ *   range of each view inside y_u / y_v / corner_id (as in kb_problem_desc); set_pose: [7]. */
+KB_API kb_status kb_append_set(kb_handle* h, int32_t n_views, const int32_t* view_cam, const int64_t* view_begin, const double* y_u, const double* y_v,
+                               const int32_t* corner_id, const double* set_pose);
+KB_API kb_status kb_remove_last_set(kb_handle* h);
+/* ≙ OptimizationProblem::saveDesignVariables / restoreDesignVariables (IC/src/core/OptimizationProblem.cpp:260-272), the bracket
+ *   IncrementalEstimator::addBatch puts around a batch (IncrementalEstimator.cpp:348-350, 520-524): a snapshot of every design variable
+ *   on the device, and back.  A set appended after the snapshot keeps its own pose on restore. */
+KB_API kb_status kb_save_design_variables(kb_handle* h);
+KB_API kb_status kb_restore_design_variables(kb_handle* h);
+
 /* Replace the current state ≙ DesignVariable::setParameters / what Optimizer2::applyStateUpdate and revertLastStateUpdate leave in
  * the HOST design variables (BE/src/Optimizer2.cpp:290-318; BE/include/aslam/backend/DesignVariable.hpp:18-145): a
  * LinearSystemSolver plugged into an unmodified Optimizer2 does not own the design variables, so its adapter pushes their values

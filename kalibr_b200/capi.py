@@ -26,8 +26,9 @@ EXPORTED_SYMBOLS = [
     "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
     "kb_set_inv_r", "kb_get_sqrt_inv_r", "kb_set_m_estimator", "kb_m_estimator_parameter", "kb_reprojection_statistics",
+    "kb_append_set", "kb_remove_last_set", "kb_save_design_variables", "kb_restore_design_variables",
     "kb_set_state", "kb_set_camera_params", "kb_set_baselines", "kb_set_set_poses", "kb_set_conditioner",
-    "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics", "kb_default_svd_solver_options", "kb_solve_system_svd", "kb_optimize_gauss_newton", "kb_analyze_marginal_last_build", "kb_get_last_svd_solve",
+    "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics", "kb_default_svd_solver_options", "kb_solve_system_svd", "kb_optimize_gauss_newton", "kb_analyze_marginal_last_build", "kb_get_last_svd_solve", "kb_get_last_svd_decomposition",
 ]
 
 MEST_NONE, MEST_HUBER, MEST_CAUCHY, MEST_GEMAN_MCCLURE, MEST_BLAKE_ZISSERMAN = range(5)  # = kb_m_estimator
@@ -89,6 +90,10 @@ def load_library() -> C.CDLL:
     L.kb_get_camera_params.argtypes = [vp, vp]
     L.kb_get_baselines.argtypes = [vp, vp]
     L.kb_get_set_poses.argtypes = [vp, vp]
+    L.kb_append_set.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.kb_remove_last_set.argtypes = [vp]
+    L.kb_save_design_variables.argtypes = [vp]
+    L.kb_restore_design_variables.argtypes = [vp]
     L.kb_set_state.argtypes = [vp, vp, vp, vp]
     L.kb_set_camera_params.argtypes = [vp, vp]
     L.kb_set_baselines.argtypes = [vp, vp]
@@ -124,6 +129,7 @@ def load_library() -> C.CDLL:
     L.kb_optimize_gauss_newton.argtypes = [vp, vp, vp, vp]
     L.kb_analyze_marginal_last_build.argtypes = [vp, vp, vp, vp, vp, vp]
     L.kb_get_last_svd_solve.argtypes = [vp, vp]
+    L.kb_get_last_svd_decomposition.argtypes = [vp, vp, vp, vp]
     L.kb_initialize_intrinsics.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_double, vp, C.POINTER(C.c_int32)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
@@ -376,9 +382,37 @@ class B200SchurLinearSystemSolver:
         return out
 
     def set_poses(self) -> np.ndarray:
-        out = np.zeros((self.problem.n_sets, 7))
+        out = np.zeros((getattr(self, "_n_sets_live", self.problem.n_sets), 7))
         self._check(self._L.kb_get_set_poses(self._h, _p(out)), "kb_get_set_poses")
         return out
+
+    def _refresh_sizes(self):
+        self.jrows = self._L.kb_jrows(self._h)
+        self.local_jrows = self._L.kb_local_jrows(self._h)
+        self.jcols = self._L.kb_jcols(self._h)
+        self.n_dv = self._L.kb_num_design_variables(self._h)
+
+    def append_set(self, view_cam, view_begin, y_u, y_v, corner_id, set_pose):
+        """≙ IncrementalOptimizationProblem::add of one batch (one synced set): the live handle grows by this set and its views."""
+        vc = np.ascontiguousarray(view_cam, np.int32)
+        vb = np.ascontiguousarray(view_begin, np.int64)
+        yu, yv = np.ascontiguousarray(y_u, np.float64), np.ascontiguousarray(y_v, np.float64)
+        cid = np.ascontiguousarray(corner_id, np.int32)
+        pose = np.ascontiguousarray(set_pose, np.float64)
+        self._check(self._L.kb_append_set(self._h, len(vc), _p(vc), _p(vb), _p(yu), _p(yv), _p(cid), _p(pose)), "kb_append_set")
+        self._refresh_sizes()
+        self._n_sets_live = getattr(self, "_n_sets_live", self.problem.n_sets) + 1
+
+    def remove_last_set(self):
+        self._check(self._L.kb_remove_last_set(self._h), "kb_remove_last_set")
+        self._refresh_sizes()
+        self._n_sets_live = getattr(self, "_n_sets_live", self.problem.n_sets) - 1
+
+    def save_design_variables(self):
+        self._check(self._L.kb_save_design_variables(self._h), "kb_save_design_variables")
+
+    def restore_design_variables(self):
+        self._check(self._L.kb_restore_design_variables(self._h), "kb_restore_design_variables")
 
     def set_state(self, cam_params=None, baselines=None, set_poses=None):
         """≙ DesignVariable::setParameters for every design variable: the host's values replace the device state."""
@@ -417,6 +451,13 @@ class B200SchurLinearSystemSolver:
         fn = self._L.kb_analyze_marginal_last_build if last_build else self._L.kb_analyze_marginal
         self._check(fn(self._h, C.byref(o), C.byref(res), _p(sv), _p(V), _p(cols)), "kb_analyze_marginal")
         return res, sv, V, cols
+
+    def last_svd_decomposition(self):
+        """(|eigenvalues| descending, V, DV columns of V's rows) of the last solve_system_svd (the column-scaled system when scaling is on)."""
+        n = self.problem.n_c
+        sv, V, cols = np.zeros(n), np.zeros((n, n)), np.zeros(n, np.int32)
+        self._check(self._L.kb_get_last_svd_decomposition(self._h, _p(sv), _p(V), _p(cols)), "kb_get_last_svd_decomposition")
+        return sv, V, cols
 
     def last_svd_solve(self):
         from .problem import KbSvdSolveResult

@@ -63,14 +63,34 @@ thread_local std::string g_create_error;  // kb_last_error(NULL) reports the cal
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
-  size_t n = 0;
+  size_t n = 0, cap = 0;  // logical size, allocated elements
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; cap = 0; }
+  // `count` elements with undefined contents; an allocation that is already large enough is kept (handles are re-sized in place)
   cudaError_t alloc(size_t count) {
+    if (p && count <= cap) { n = count; return cudaSuccess; }
     release();
+    const size_t c = count ? count : 1;
+    cudaError_t e = cudaMalloc((void**)&p, sizeof(T) * c);
+    if (e == cudaSuccess) { n = count; cap = c; }
+    return e;
+  }
+  // grow to `count` elements KEEPING the first n (capacity doubling): the append-only arrays of a live handle
+  cudaError_t grow(size_t count, cudaStream_t s) {
+    if (p && count <= cap) { n = count; return cudaSuccess; }
+    const size_t c = std::max<size_t>(std::max(count, 2 * cap), 1);
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc((void**)&q, sizeof(T) * c);
+    if (e != cudaSuccess) return e;
+    if (p && n) {
+      e = cudaMemcpyAsync(q, p, sizeof(T) * n, cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = c;
     n = count;
-    if (count == 0) count = 1;
-    return cudaMalloc((void**)&p, sizeof(T) * count);
+    return e;
   }
   cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
     cudaError_t e = alloc(v.size());
@@ -103,7 +123,9 @@ struct kb_handle {
   // ---- device ----
   DevProblem d;
   DevBuf<double> y_u, y_v, target, cam_params, baselines, set_poses, camT, camPi, camA, baseBt, baseM, e, view_cost, set_prep, VB, gram_partial, sumG, V, bv, W, Lv, yv, U, Sred, dxc, dx;
-  DevBuf<double> init_cam, init_base, init_sets, bk_cam, bk_base, bk_sets, partials, scalars, jt, gather, rho_partial;
+  DevBuf<double> init_cam, init_base, init_sets, bk_cam, bk_base, bk_sets, partials, scalars, jt, gather, rho_partial, sv_cam, sv_base, sv_sets;
+  size_t saved_sets = 0;
+  bool has_saved = false;
   DevBuf<uint16_t> corner;
   DevBuf<int> view_set, view_cam, view_begin, set_view, lin_off, view_list, cam_view_list, cam_view_begin, set_col_q, set_col_t, cam_cols, posdef;
   DevBuf<long long> view_jbase;
@@ -338,6 +360,247 @@ void kb_destroy(kb_handle* h) {
   trace.mark("destroy: device buffers");
 }
 
+// Everything DERIVED from the host-side master copy of the structure (cameras, local synced sets, views as term ranges): the
+// design-variable layout, the reduced-system layout, the CCS J^T descriptors, the view lists / slice tables, the work buffers (kept
+// when their capacity suffices) and the device-side problem view.  Called by kb_create and again after kb_append_set /
+// kb_remove_last_set.  Observations, target points and the state arrays are NOT touched here.
+static kb_status build_tables(kb_handle* h) {
+  cudaStream_t s = h->stream;
+  const int n_local_sets = h->set_hi - h->set_lo;
+  build_dv_layout(h);
+  std::vector<int>& vs = h->h_view_set;
+  std::vector<int>& vc = h->h_view_cam;
+  std::vector<int>& vb = h->h_view_begin;
+  const int n_views = (int)vs.size();
+  std::vector<int> set_view((size_t)n_local_sets * h->n_cams, -1);
+  for (int w = 0; w < n_views; ++w) set_view[(size_t)vs[w] * h->n_cams + vc[w]] = w;
+  std::fill(std::begin(h->lm_bfrag_pairs), std::end(h->lm_bfrag_pairs), 0);
+  // ---- reduced-system layout: [cam0 proj|dist, cam1 ..., | baseline 0 q,t, ...] ----
+  DevProblem& D = h->d;
+  D.n_cams = h->n_cams;
+  D.n_sets = n_local_sets;
+  D.n_views = n_views;
+  D.n_terms = h->n_terms_local;
+  int off = 0;
+  for (int k = 0; k < h->n_cams; ++k) {
+    D.cam_model[k] = h->cam_model[k];
+    D.cam_P[k] = model_P(h->cam_model[k]);
+    D.cam_D[k] = model_D(h->cam_model[k]);
+    D.intr_off[k] = off;
+    off += D.cam_P[k] + D.cam_D[k];
+  }
+  for (int j = 0; j + 1 < h->n_cams; ++j) { D.base_off[j] = off; off += 6; }
+  D.n_c = off;
+  D.n_aug = off + 1;
+  if (D.n_aug > 224) return fail(h, KB_ERR_INVALID_ARGUMENT, "reduced camera system larger than 223 unknowns is not supported");
+  h->h_cam_cols.assign(D.n_c, 0);
+  for (int k = 0; k < h->n_cams; ++k) {
+    for (int c = 0; c < D.cam_P[k]; ++c) h->h_cam_cols[D.intr_off[k] + c] = h->dv_col[h->dv_proj[k]] + c;
+    for (int c = 0; c < D.cam_D[k]; ++c) h->h_cam_cols[D.intr_off[k] + D.cam_P[k] + c] = h->dv_col[h->dv_dist[k]] + c;
+  }
+  for (int j = 0; j + 1 < h->n_cams; ++j)
+    for (int c = 0; c < 3; ++c) {
+      h->h_cam_cols[D.base_off[j] + c] = h->dv_col[h->dv_base_q[j]] + c;
+      h->h_cam_cols[D.base_off[j] + 3 + c] = h->dv_col[h->dv_base_t[j]] + c;
+    }
+  std::vector<int> set_col_q(n_local_sets), set_col_t(n_local_sets);
+  for (int lv = 0; lv < n_local_sets; ++lv) {
+    set_col_q[lv] = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv)];
+    set_col_t[lv] = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv) + 1];
+  }
+  // ---- CCS J^T slot offsets per camera: design variables of a term sorted by block index ----
+  std::vector<int> lin_off((size_t)h->n_cams * LIN_OFF_STRIDE, 0);
+  h->h_view_jbase.assign(n_views, 0);
+  {
+    const int pose_q_block = h->dv_first_set;  // relative order against the camera-side blocks is the same for every set
+    for (int k = 0; k < h->n_cams; ++k) {
+      struct Seg { int block, dim, slot; };
+      std::vector<Seg> segs;
+      segs.push_back({pose_q_block, 3, 0});
+      segs.push_back({pose_q_block + 1, 3, 1});
+      segs.push_back({h->dv_proj[k], D.cam_P[k], 2});
+      segs.push_back({h->dv_dist[k], D.cam_D[k], 3});
+      for (int j = 0; j < k; ++j) segs.push_back({h->dv_base_q[j], 6, 4 + j});  // q,t adjacent in every order
+      std::sort(segs.begin(), segs.end(), [](const Seg& a, const Seg& b) { return a.block < b.block; });
+      int o = 0;
+      for (auto& s : segs) { lin_off[(size_t)k * LIN_OFF_STRIDE + s.slot] = o; o += s.dim; }
+    }
+    // per-column descriptors of the CCS J^T layout and the DMMA B-fragment slots the materialising kernel needs per model
+    const int desc_stride = 6 * h->n_cams + KB_CAM_PARAM_STRIDE;
+    std::vector<int> col_desc((size_t)h->n_cams * desc_stride, 3 << 16);
+    for (int k = 0; k < h->n_cams; ++k) {
+      const int* off = &lin_off[(size_t)k * LIN_OFF_STRIDE];
+      int* cd = &col_desc[(size_t)k * desc_stride];
+      for (int c = 0; c < 3; ++c) { cd[off[0] + c] = (0 << 16) | c; cd[off[1] + c] = (0 << 16) | (3 + c); }
+      for (int c = 0; c < D.cam_P[k]; ++c) cd[off[2] + c] = (2 << 16) | c;
+      for (int c = 0; c < D.cam_D[k]; ++c) cd[off[3] + c] = (2 << 16) | (D.cam_P[k] + c);
+      for (int j = 0; j < k; ++j)
+        for (int c = 0; c < 6; ++c) cd[off[4 + j] + c] = (1 << 16) | (j << 8) | c;
+      const int Wk = 6 + 6 * k + D.cam_P[k] + D.cam_D[k];
+      int pairs = 0;
+      for (int n0 = 0; n0 < Wk; n0 += 8) {
+        unsigned need = 0;
+        for (int c = n0; c < std::min(Wk, n0 + 8); ++c) {
+          const int kind = cd[c] >> 16, sub = cd[c] & 0xff;
+          need |= kind == 2 ? 1u << ((6 + sub) >> 2) : 3u;
+        }
+        for (int ks = 0; ks < 4; ++ks) pairs += (need >> ks) & 1;
+      }
+      h->lm_bfrag_pairs[h->cam_model[k]] = std::max(h->lm_bfrag_pairs[h->cam_model[k]], pairs);
+    }
+    KB_CUDA(h, h->col_desc.upload(col_desc, h->stream));
+    D.col_desc_stride = desc_stride;
+    long long jb = 0;
+    for (int w = 0; w < n_views; ++w) {
+      h->h_view_jbase[w] = jb;
+      const int k = vc[w];
+      jb += (long long)(vb[w + 1] - vb[w]) * 2 * (6 + 6 * k + D.cam_P[k] + D.cam_D[k]);
+    }
+    h->jac_nnz = jb;
+  }
+  // ---- view lists: by model (kernel specialisation) and by camera (Gram sums) ----
+  std::vector<int> view_list;
+  for (int m = 0; m < KB_NUM_MODELS; ++m) {
+    h->model_begin[m] = (int)view_list.size();
+    for (int k = 0; k < h->n_cams; ++k)
+      if (h->cam_model[k] == m)
+        for (int w = 0; w < n_views; ++w)
+          if (vc[w] == k) view_list.push_back(w);
+  }
+  h->model_begin[KB_NUM_MODELS] = (int)view_list.size();
+  std::vector<int> cam_view_list, cam_view_begin(h->n_cams + 1, 0);
+  for (int k = 0; k < h->n_cams; ++k) {
+    cam_view_begin[k] = (int)cam_view_list.size();
+    for (int w = 0; w < n_views; ++w)
+      if (vc[w] == k) cam_view_list.push_back(w);
+  }
+  cam_view_begin[h->n_cams] = (int)cam_view_list.size();
+  // ---- slices of the model/camera-sorted view list: one warp of the fused kernel per slice, never crossing a camera ----
+  std::vector<int4> slices;
+  std::vector<int> cam_slice_range(2 * (size_t)h->n_cams, 0);
+  {
+    const int per = std::max(1, (n_views + la_grid_warps() - 1) / la_grid_warps());
+    int pos = 0;  // position in view_list
+    for (int m = 0; m < KB_NUM_MODELS; ++m) {
+      h->slice_model_begin[m] = (int)slices.size();
+      for (int k = 0; k < h->n_cams; ++k) {
+        if (h->cam_model[k] != m) continue;
+        const int nk = cam_view_begin[k + 1] - cam_view_begin[k];
+        cam_slice_range[2 * k] = (int)slices.size();
+        for (int a = 0; a < nk; a += per) slices.push_back(make_int4(pos + a, pos + std::min(nk, a + per), k, 0));
+        cam_slice_range[2 * k + 1] = (int)slices.size();
+        pos += nk;
+      }
+    }
+    h->slice_model_begin[KB_NUM_MODELS] = (int)slices.size();
+  }
+  // streamed table: chunk c = local views [cv[c], cv[c+1]) = terms [st_chunk_term[c], st_chunk_term[c+1])
+  std::vector<int4> st_slices;
+  std::vector<int> st_cam_slice_range((size_t)h->n_cams * KB_STREAM_CHUNKS * 2, 0);
+  {
+    int cv[KB_STREAM_CHUNKS + 1];
+    for (int c = 0; c <= KB_STREAM_CHUNKS; ++c) {
+      cv[c] = (int)((long long)n_views * c / KB_STREAM_CHUNKS);
+      h->st_chunk_term[c] = vb[cv[c]];
+    }
+    // position of every camera's first view in the model/camera-sorted list
+    std::vector<int> cam_pos(h->n_cams, 0);
+    {
+      int pos = 0;
+      for (int m = 0; m < KB_NUM_MODELS; ++m)
+        for (int k = 0; k < h->n_cams; ++k)
+          if (h->cam_model[k] == m) { cam_pos[k] = pos; pos += cam_view_begin[k + 1] - cam_view_begin[k]; }
+    }
+    for (int c = 0; c < KB_STREAM_CHUNKS; ++c) {
+      const int per = std::max(1, (cv[c + 1] - cv[c] + la_grid_warps() - 1) / la_grid_warps());
+      for (int m = 0; m < KB_NUM_MODELS; ++m) {
+        h->st_chunk_model_begin[c][m] = (int)st_slices.size();
+        for (int k = 0; k < h->n_cams; ++k) {
+          if (h->cam_model[k] != m) continue;
+          // views of camera k inside the chunk: a contiguous run of its (ascending) view list
+          const int* lst = cam_view_list.data() + cam_view_begin[k];
+          const int nk = cam_view_begin[k + 1] - cam_view_begin[k];
+          const int lo = (int)(std::lower_bound(lst, lst + nk, cv[c]) - lst), hi = (int)(std::lower_bound(lst, lst + nk, cv[c + 1]) - lst);
+          st_cam_slice_range[((size_t)k * KB_STREAM_CHUNKS + c) * 2] = (int)st_slices.size();
+          for (int a = lo; a < hi; a += per) st_slices.push_back(make_int4(cam_pos[k] + a, cam_pos[k] + std::min(hi, a + per), k, 0));
+          st_cam_slice_range[((size_t)k * KB_STREAM_CHUNKS + c) * 2 + 1] = (int)st_slices.size();
+        }
+      }
+      h->st_chunk_model_begin[c][KB_NUM_MODELS] = (int)st_slices.size();
+    }
+  }
+
+  KB_CUDA(h, h->view_set.upload(vs, s));
+  KB_CUDA(h, h->view_cam.upload(vc, s));
+  KB_CUDA(h, h->view_begin.upload(vb, s));
+  KB_CUDA(h, h->set_view.upload(set_view, s));
+  KB_CUDA(h, h->lin_off.upload(lin_off, s));
+  KB_CUDA(h, h->view_jbase.upload(h->h_view_jbase, s));
+  KB_CUDA(h, h->view_list.upload(view_list, s));
+  KB_CUDA(h, h->cam_view_list.upload(cam_view_list, s));
+  KB_CUDA(h, h->cam_view_begin.upload(cam_view_begin, s));
+  KB_CUDA(h, h->slices.upload(slices, s));
+  {
+    std::vector<int4> vmeta(view_list.size());
+    for (size_t i = 0; i < view_list.size(); ++i) {
+      const int w = view_list[i];
+      vmeta[i] = make_int4(w, vs[w], vb[w], vb[w + 1]);
+    }
+    KB_CUDA(h, h->vmeta.upload(vmeta, s));
+  }
+  KB_CUDA(h, h->cam_slice_range.upload(cam_slice_range, s));
+  KB_CUDA(h, h->st_slices.upload(st_slices, s));
+  KB_CUDA(h, h->st_cam_slice_range.upload(st_cam_slice_range, s));
+  KB_CUDA(h, h->set_col_q.upload(set_col_q, s));
+  KB_CUDA(h, h->set_col_t.upload(set_col_t, s));
+  KB_CUDA(h, h->cam_cols.upload(h->h_cam_cols, s));
+  const size_t C = h->n_cams, S = n_local_sets, NA = D.n_aug;
+
+  KB_CUDA(h, h->camT.alloc(C * 12));
+  KB_CUDA(h, h->camPi.alloc(C * 36));
+  KB_CUDA(h, h->camA.alloc(C * C * 36));
+  KB_CUDA(h, h->baseBt.alloc(C * 36));
+  KB_CUDA(h, h->baseM.alloc(C * 36));
+  KB_CUDA(h, h->e.alloc(2 * (size_t)h->n_terms_local));
+  KB_CUDA(h, h->view_cost.alloc(n_views));
+  KB_CUDA(h, h->set_prep.alloc(S * SETPREP_STRIDE));
+  KB_CUDA(h, h->VB.alloc((size_t)n_views * VB_STRIDE));
+  KB_CUDA(h, h->gram_partial.alloc(std::max(slices.size(), st_slices.size()) * GRAM_TILES));
+  KB_CUDA(h, h->sumG.alloc(C * GRAM_SIZE));
+  KB_CUDA(h, h->V.alloc(S * 36));
+  KB_CUDA(h, h->bv.alloc(S * 6));
+  KB_CUDA(h, h->W.alloc(S * D.n_c * 6));
+  KB_CUDA(h, h->Lv.alloc(S * 36));
+  KB_CUDA(h, h->yv.alloc(S * 6));
+  KB_CUDA(h, h->U.alloc(NA * NA));
+  KB_CUDA(h, h->Sred.alloc(NA * NA));
+  KB_CUDA(h, h->dxc.alloc(D.n_c));
+  KB_CUDA(h, h->dx.alloc((size_t)h->jcols));
+  KB_CUDA(h, h->scalars.alloc(8));
+  KB_CUDA(h, h->rho_partial.alloc(2 * std::max<size_t>(64, (size_t)n_local_sets / 8 + 2)));
+  D.ctrl = h->ctrl.p;
+  KB_CUDA(h, h->posdef.alloc(2));
+  KB_CUDA(h, h->lm_counters.alloc(KB_NUM_MODELS));
+  KB_CUDA(h, cudaMemsetAsync(h->dx.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)h->jcols), s));
+  KB_CUDA(h, cudaMemsetAsync(h->VB.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)n_views * VB_STRIDE), s));
+  KB_CUDA(h, cudaMemsetAsync(h->e.p, 0, sizeof(double) * std::max<size_t>(1, 2 * (size_t)h->n_terms_local), s));
+  KB_CUDA(h, cudaMemsetAsync(h->camA.p, 0, sizeof(double) * C * C * 36, s));
+  D.y_u = h->y_u.p; D.y_v = h->y_v.p; D.corner = h->corner.p; D.target = h->target.p;
+  h->front_u = h->y_u.p;
+  h->front_v = h->y_v.p;
+  h->back_u = h->back_v = nullptr;  // the double buffer (kb_prefetch_observations) is re-created at the new size on demand
+  D.view_set = h->view_set.p; D.view_cam = h->view_cam.p; D.view_begin = h->view_begin.p; D.set_view = h->set_view.p;
+  D.lin_off = h->lin_off.p; D.view_jbase = h->view_jbase.p; D.col_desc = h->col_desc.p;
+  D.cam_params = h->cam_params.p; D.baselines = h->baselines.p; D.set_poses = h->set_poses.p;
+  D.camT = h->camT.p; D.camPi = h->camPi.p; D.camA = h->camA.p; D.baseBt = h->baseBt.p; D.baseM = h->baseM.p;
+  D.e = h->e.p; D.view_cost = h->view_cost.p; D.set_prep = h->set_prep.p; D.VB = h->VB.p; D.gram_partial = h->gram_partial.p; D.sumG = h->sumG.p;
+  D.V = h->V.p; D.bv = h->bv.p; D.W = h->W.p; D.Lv = h->Lv.p; D.yv = h->yv.p;
+  D.U = h->U.p; D.Sred = h->Sred.p; D.dxc = h->dxc.p; D.dx = h->dx.p; D.n_invalid = h->n_invalid.p; D.rho_partial = h->rho_partial.p; D.tickets = h->tickets.p;
+  h->n_partials = schur_num_partials(D);
+  KB_CUDA(h, h->partials.alloc(schur_partial_stride(D) * h->n_partials));
+  return KB_OK;
+}
+
 kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   CreateTrace trace;
   if (!d || !out) return fail(nullptr, KB_ERR_INVALID_ARGUMENT, "null argument");
@@ -379,7 +642,6 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   if (presharded) { h->set_lo = d->set_offset; h->set_hi = d->set_offset + d->n_sets; }
   else shard_range(d->n_sets, d->n_ranks, d->rank, h->set_lo, h->set_hi);
   const int in_set_shift = presharded ? d->set_offset : 0;  // input view_set is local when pre-sharded
-  build_dv_layout(h);
   auto cfail = [&](kb_status c, const std::string& m) { g_create_error = m; return c; };
 #define KB_CCUDA(call)                                                                                        \
   do {                                                                                                        \
@@ -393,6 +655,15 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(cudaMallocHost((void**)&h->h_ctrl, sizeof(LmCtrl)));
   for (auto& e : h->ev) KB_CCUDA(cudaEventCreate(&e));
 
+  // every stream / event of the handle up front (re-used for the whole life of the handle, also across kb_append_set)
+  KB_CCUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev_chunk) KB_CCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (auto& e : h->ev_join) KB_CCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& st : h->model_stream) KB_CCUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
+  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_front_free, cudaEventDisableTiming));
   trace.mark("device, streams, events");
   // ---- local views / terms ----
   const int n_local_sets = h->set_hi - h->set_lo;
@@ -402,7 +673,7 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   std::vector<int>& vc = h->h_view_cam;
   std::vector<int>& vb = h->h_view_begin;
   vb.push_back(0);
-  std::vector<int> set_view((size_t)n_local_sets * d->n_cams, -1);
+  std::vector<char> seen((size_t)n_local_sets * d->n_cams, 0);
   for (int w = 0; w < d->n_views; ++w) {
     const int k = d->view_cam[w];
     if (d->view_set[w] < 0 || d->view_set[w] >= d->n_sets || k < 0 || k >= d->n_cams) return cfail(KB_ERR_INVALID_ARGUMENT, "view index out of range");
@@ -411,8 +682,8 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     if (b < 0 || e < b || e > d->n_terms) return cfail(KB_ERR_INVALID_ARGUMENT, "view_begin is not a monotone partition of the terms");
     if (v < h->set_lo || v >= h->set_hi) continue;
     const int lv = v - h->set_lo;
-    if (set_view[(size_t)lv * d->n_cams + k] >= 0) return cfail(KB_ERR_INVALID_ARGUMENT, "two views for the same (set, camera)");
-    set_view[(size_t)lv * d->n_cams + k] = (int)vs.size();
+    if (seen[(size_t)lv * d->n_cams + k]) return cfail(KB_ERR_INVALID_ARGUMENT, "two views for the same (set, camera)");
+    seen[(size_t)lv * d->n_cams + k] = 1;
     vs.push_back(lv);
     vc.push_back(k);
     for (int64_t i = b; i < e; ++i) {
@@ -424,169 +695,13 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     if (yu.size() > (size_t)0x7fffffff) return cfail(KB_ERR_INVALID_ARGUMENT, "more than 2^31 terms on one rank");
     vb.push_back((int)yu.size());
   }
-  const int n_views = (int)vs.size();
   h->n_terms_local = (int64_t)yu.size();
 
-  // ---- reduced-system layout: [cam0 proj|dist, cam1 ..., | baseline 0 q,t, ...] ----
-  DevProblem& D = h->d;
-  D.n_cams = d->n_cams;
-  D.sT[0] = D.sT[3] = 1.0;  // invR = I, NoMEstimator (CalibrationTools.hpp:105-108; BE/src/ErrorTerm.cpp:8-12)
-  D.n_sets = n_local_sets;
-  D.n_views = n_views;
-  D.n_target = d->n_target_points;
-  D.n_terms = h->n_terms_local;
-  int off = 0;
-  for (int k = 0; k < d->n_cams; ++k) {
-    D.cam_model[k] = d->cam_model[k];
-    D.cam_P[k] = model_P(d->cam_model[k]);
-    D.cam_D[k] = model_D(d->cam_model[k]);
-    D.intr_off[k] = off;
-    off += D.cam_P[k] + D.cam_D[k];
-  }
-  for (int j = 0; j + 1 < d->n_cams; ++j) { D.base_off[j] = off; off += 6; }
-  D.n_c = off;
-  D.n_aug = off + 1;
-  if (D.n_aug > 224) return cfail(KB_ERR_INVALID_ARGUMENT, "reduced camera system larger than 223 unknowns is not supported");
-  h->h_cam_cols.assign(D.n_c, 0);
-  for (int k = 0; k < d->n_cams; ++k) {
-    for (int c = 0; c < D.cam_P[k]; ++c) h->h_cam_cols[D.intr_off[k] + c] = h->dv_col[h->dv_proj[k]] + c;
-    for (int c = 0; c < D.cam_D[k]; ++c) h->h_cam_cols[D.intr_off[k] + D.cam_P[k] + c] = h->dv_col[h->dv_dist[k]] + c;
-  }
-  for (int j = 0; j + 1 < d->n_cams; ++j)
-    for (int c = 0; c < 3; ++c) {
-      h->h_cam_cols[D.base_off[j] + c] = h->dv_col[h->dv_base_q[j]] + c;
-      h->h_cam_cols[D.base_off[j] + 3 + c] = h->dv_col[h->dv_base_t[j]] + c;
-    }
-  std::vector<int> set_col_q(n_local_sets), set_col_t(n_local_sets);
-  for (int lv = 0; lv < n_local_sets; ++lv) {
-    set_col_q[lv] = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv)];
-    set_col_t[lv] = h->dv_col[h->dv_first_set + 2 * (h->set_lo + lv) + 1];
-  }
-  // ---- CCS J^T slot offsets per camera: design variables of a term sorted by block index ----
-  std::vector<int> lin_off((size_t)d->n_cams * LIN_OFF_STRIDE, 0);
-  h->h_view_jbase.assign(n_views, 0);
-  {
-    const int pose_q_block = h->dv_first_set;  // relative order against the camera-side blocks is the same for every set
-    for (int k = 0; k < d->n_cams; ++k) {
-      struct Seg { int block, dim, slot; };
-      std::vector<Seg> segs;
-      segs.push_back({pose_q_block, 3, 0});
-      segs.push_back({pose_q_block + 1, 3, 1});
-      segs.push_back({h->dv_proj[k], D.cam_P[k], 2});
-      segs.push_back({h->dv_dist[k], D.cam_D[k], 3});
-      for (int j = 0; j < k; ++j) segs.push_back({h->dv_base_q[j], 6, 4 + j});  // q,t adjacent in every order
-      std::sort(segs.begin(), segs.end(), [](const Seg& a, const Seg& b) { return a.block < b.block; });
-      int o = 0;
-      for (auto& s : segs) { lin_off[(size_t)k * LIN_OFF_STRIDE + s.slot] = o; o += s.dim; }
-    }
-    // per-column descriptors of the CCS J^T layout and the DMMA B-fragment slots the materialising kernel needs per model
-    const int desc_stride = 6 * d->n_cams + KB_CAM_PARAM_STRIDE;
-    std::vector<int> col_desc((size_t)d->n_cams * desc_stride, 3 << 16);
-    for (int k = 0; k < d->n_cams; ++k) {
-      const int* off = &lin_off[(size_t)k * LIN_OFF_STRIDE];
-      int* cd = &col_desc[(size_t)k * desc_stride];
-      for (int c = 0; c < 3; ++c) { cd[off[0] + c] = (0 << 16) | c; cd[off[1] + c] = (0 << 16) | (3 + c); }
-      for (int c = 0; c < D.cam_P[k]; ++c) cd[off[2] + c] = (2 << 16) | c;
-      for (int c = 0; c < D.cam_D[k]; ++c) cd[off[3] + c] = (2 << 16) | (D.cam_P[k] + c);
-      for (int j = 0; j < k; ++j)
-        for (int c = 0; c < 6; ++c) cd[off[4 + j] + c] = (1 << 16) | (j << 8) | c;
-      const int Wk = 6 + 6 * k + D.cam_P[k] + D.cam_D[k];
-      int pairs = 0;
-      for (int n0 = 0; n0 < Wk; n0 += 8) {
-        unsigned need = 0;
-        for (int c = n0; c < std::min(Wk, n0 + 8); ++c) {
-          const int kind = cd[c] >> 16, sub = cd[c] & 0xff;
-          need |= kind == 2 ? 1u << ((6 + sub) >> 2) : 3u;
-        }
-        for (int ks = 0; ks < 4; ++ks) pairs += (need >> ks) & 1;
-      }
-      h->lm_bfrag_pairs[d->cam_model[k]] = std::max(h->lm_bfrag_pairs[d->cam_model[k]], pairs);
-    }
-    KB_CCUDA(h->col_desc.upload(col_desc, h->stream));
-    D.col_desc_stride = desc_stride;
-    long long jb = 0;
-    for (int w = 0; w < n_views; ++w) {
-      h->h_view_jbase[w] = jb;
-      const int k = vc[w];
-      jb += (long long)(vb[w + 1] - vb[w]) * 2 * (6 + 6 * k + D.cam_P[k] + D.cam_D[k]);
-    }
-    h->jac_nnz = jb;
-  }
-  // ---- view lists: by model (kernel specialisation) and by camera (Gram sums) ----
-  std::vector<int> view_list;
-  for (int m = 0; m < KB_NUM_MODELS; ++m) {
-    h->model_begin[m] = (int)view_list.size();
-    for (int k = 0; k < d->n_cams; ++k)
-      if (d->cam_model[k] == m)
-        for (int w = 0; w < n_views; ++w)
-          if (vc[w] == k) view_list.push_back(w);
-  }
-  h->model_begin[KB_NUM_MODELS] = (int)view_list.size();
-  std::vector<int> cam_view_list, cam_view_begin(d->n_cams + 1, 0);
-  for (int k = 0; k < d->n_cams; ++k) {
-    cam_view_begin[k] = (int)cam_view_list.size();
-    for (int w = 0; w < n_views; ++w)
-      if (vc[w] == k) cam_view_list.push_back(w);
-  }
-  cam_view_begin[d->n_cams] = (int)cam_view_list.size();
-  // ---- slices of the model/camera-sorted view list: one warp of the fused kernel per slice, never crossing a camera ----
-  std::vector<int4> slices;
-  std::vector<int> cam_slice_range(2 * (size_t)d->n_cams, 0);
-  {
-    const int per = std::max(1, (n_views + la_grid_warps() - 1) / la_grid_warps());
-    int pos = 0;  // position in view_list
-    for (int m = 0; m < KB_NUM_MODELS; ++m) {
-      h->slice_model_begin[m] = (int)slices.size();
-      for (int k = 0; k < d->n_cams; ++k) {
-        if (d->cam_model[k] != m) continue;
-        const int nk = cam_view_begin[k + 1] - cam_view_begin[k];
-        cam_slice_range[2 * k] = (int)slices.size();
-        for (int a = 0; a < nk; a += per) slices.push_back(make_int4(pos + a, pos + std::min(nk, a + per), k, 0));
-        cam_slice_range[2 * k + 1] = (int)slices.size();
-        pos += nk;
-      }
-    }
-    h->slice_model_begin[KB_NUM_MODELS] = (int)slices.size();
-  }
-  // streamed table: chunk c = local views [cv[c], cv[c+1]) = terms [st_chunk_term[c], st_chunk_term[c+1])
-  std::vector<int4> st_slices;
-  std::vector<int> st_cam_slice_range((size_t)d->n_cams * KB_STREAM_CHUNKS * 2, 0);
-  {
-    int cv[KB_STREAM_CHUNKS + 1];
-    for (int c = 0; c <= KB_STREAM_CHUNKS; ++c) {
-      cv[c] = (int)((long long)n_views * c / KB_STREAM_CHUNKS);
-      h->st_chunk_term[c] = vb[cv[c]];
-    }
-    // position of every camera's first view in the model/camera-sorted list
-    std::vector<int> cam_pos(d->n_cams, 0);
-    {
-      int pos = 0;
-      for (int m = 0; m < KB_NUM_MODELS; ++m)
-        for (int k = 0; k < d->n_cams; ++k)
-          if (d->cam_model[k] == m) { cam_pos[k] = pos; pos += cam_view_begin[k + 1] - cam_view_begin[k]; }
-    }
-    for (int c = 0; c < KB_STREAM_CHUNKS; ++c) {
-      const int per = std::max(1, (cv[c + 1] - cv[c] + la_grid_warps() - 1) / la_grid_warps());
-      for (int m = 0; m < KB_NUM_MODELS; ++m) {
-        h->st_chunk_model_begin[c][m] = (int)st_slices.size();
-        for (int k = 0; k < d->n_cams; ++k) {
-          if (d->cam_model[k] != m) continue;
-          // views of camera k inside the chunk: a contiguous run of its (ascending) view list
-          const int* lst = cam_view_list.data() + cam_view_begin[k];
-          const int nk = cam_view_begin[k + 1] - cam_view_begin[k];
-          const int lo = (int)(std::lower_bound(lst, lst + nk, cv[c]) - lst), hi = (int)(std::lower_bound(lst, lst + nk, cv[c + 1]) - lst);
-          st_cam_slice_range[((size_t)k * KB_STREAM_CHUNKS + c) * 2] = (int)st_slices.size();
-          for (int a = lo; a < hi; a += per) st_slices.push_back(make_int4(cam_pos[k] + a, cam_pos[k] + std::min(hi, a + per), k, 0));
-          st_cam_slice_range[((size_t)k * KB_STREAM_CHUNKS + c) * 2 + 1] = (int)st_slices.size();
-        }
-      }
-      h->st_chunk_model_begin[c][KB_NUM_MODELS] = (int)st_slices.size();
-    }
-  }
-
-  trace.mark("host tables");
-  // ---- upload ----
+  h->n_terms_local = (int64_t)yu.size();
+  trace.mark("host copy of the structure");
+  // ---- upload: observations, target, state ----
   cudaStream_t s = h->stream;
+  h->d.n_target = d->n_target_points;
   std::vector<double> target(d->target_points, d->target_points + (size_t)3 * d->n_target_points);
   std::vector<double> cam(d->cam_params, d->cam_params + (size_t)KB_CAM_PARAM_STRIDE * d->n_cams);
   std::vector<double> base;
@@ -600,38 +715,6 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->y_v.upload(yv, s));
   KB_CCUDA(h->corner.upload(corner, s));
   KB_CCUDA(h->target.upload(target, s));
-  KB_CCUDA(h->view_set.upload(vs, s));
-  KB_CCUDA(h->view_cam.upload(vc, s));
-  KB_CCUDA(h->view_begin.upload(vb, s));
-  KB_CCUDA(h->set_view.upload(set_view, s));
-  KB_CCUDA(h->lin_off.upload(lin_off, s));
-  KB_CCUDA(h->view_jbase.upload(h->h_view_jbase, s));
-  KB_CCUDA(h->view_list.upload(view_list, s));
-  KB_CCUDA(h->cam_view_list.upload(cam_view_list, s));
-  KB_CCUDA(h->cam_view_begin.upload(cam_view_begin, s));
-  KB_CCUDA(h->slices.upload(slices, s));
-  {
-    std::vector<int4> vmeta(view_list.size());
-    for (size_t i = 0; i < view_list.size(); ++i) {
-      const int w = view_list[i];
-      vmeta[i] = make_int4(w, vs[w], vb[w], vb[w + 1]);
-    }
-    KB_CCUDA(h->vmeta.upload(vmeta, s));
-  }
-  KB_CCUDA(h->cam_slice_range.upload(cam_slice_range, s));
-  KB_CCUDA(h->st_slices.upload(st_slices, s));
-  KB_CCUDA(h->st_cam_slice_range.upload(st_cam_slice_range, s));
-  KB_CCUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-  for (auto& e : h->ev_chunk) KB_CCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
-  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  for (auto& e : h->ev_join) KB_CCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto& st : h->model_stream) KB_CCUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
-  KB_CCUDA(cudaEventCreateWithFlags(&h->ev_front_free, cudaEventDisableTiming));
-  KB_CCUDA(h->set_col_q.upload(set_col_q, s));
-  KB_CCUDA(h->set_col_t.upload(set_col_t, s));
-  KB_CCUDA(h->cam_cols.upload(h->h_cam_cols, s));
   KB_CCUDA(h->cam_params.upload(cam, s));
   KB_CCUDA(h->baselines.upload(base, s));
   KB_CCUDA(h->set_poses.upload(sets, s));
@@ -641,70 +724,39 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(h->bk_cam.upload(cam, s));
   KB_CCUDA(h->bk_base.upload(base, s));
   KB_CCUDA(h->bk_sets.upload(sets, s));
-  const size_t C = d->n_cams, S = n_local_sets, NA = D.n_aug;
   trace.mark("uploads");
-  KB_CCUDA(h->camT.alloc(C * 12));
-  KB_CCUDA(h->camPi.alloc(C * 36));
-  KB_CCUDA(h->camA.alloc(C * C * 36));
-  KB_CCUDA(h->baseBt.alloc(C * 36));
-  KB_CCUDA(h->baseM.alloc(C * 36));
-  KB_CCUDA(h->e.alloc(2 * (size_t)h->n_terms_local));
-  KB_CCUDA(h->view_cost.alloc(n_views));
-  KB_CCUDA(h->set_prep.alloc(S * SETPREP_STRIDE));
-  KB_CCUDA(h->VB.alloc((size_t)n_views * VB_STRIDE));
-  KB_CCUDA(h->gram_partial.alloc(std::max(slices.size(), st_slices.size()) * GRAM_TILES));
-  KB_CCUDA(h->sumG.alloc(C * GRAM_SIZE));
-  KB_CCUDA(h->V.alloc(S * 36));
-  KB_CCUDA(h->bv.alloc(S * 6));
-  KB_CCUDA(h->W.alloc(S * D.n_c * 6));
-  KB_CCUDA(h->Lv.alloc(S * 36));
-  KB_CCUDA(h->yv.alloc(S * 6));
-  KB_CCUDA(h->U.alloc(NA * NA));
-  KB_CCUDA(h->Sred.alloc(NA * NA));
-  KB_CCUDA(h->dxc.alloc(D.n_c));
-  KB_CCUDA(h->dx.alloc((size_t)h->jcols));
-  KB_CCUDA(h->scalars.alloc(8));
-  KB_CCUDA(h->rho_partial.alloc(2 * std::max<size_t>(64, (size_t)n_local_sets / 8 + 2)));
+  // ---- one-time device objects ----
+  KB_CCUDA(h->ctrl.alloc(1));
+  KB_CCUDA(h->n_invalid.alloc(1));
+  KB_CCUDA(cudaMemsetAsync(h->n_invalid.p, 0, sizeof(unsigned int), s));
   KB_CCUDA(h->tickets.alloc(4));
   KB_CCUDA(cudaMemsetAsync(h->tickets.p, 0, 4 * sizeof(unsigned int), s));
   KB_CCUDA(h->rank_slots.alloc(4 * (size_t)d->n_ranks));
-  KB_CCUDA(h->ctrl.alloc(1));
-  D.px.enabled = 0;
-  D.px.n_ranks = d->n_ranks;
-  D.px.rank = d->rank;
-  D.px.na2 = (int)((NA * NA + 1) & ~(size_t)1);
-  if (d->n_ranks > 1 && d->n_ranks <= PX_MAX_RANKS) {
-    KB_CCUDA(h->px_buf.alloc(px_doubles(D.px)));
-    KB_CCUDA(cudaMemsetAsync(h->px_buf.p, 0, sizeof(double) * px_doubles(D.px), s));
-    D.px.base[d->rank] = h->px_buf.p;
-  }
   {
     LmCtrl neutral;
     std::memset(&neutral, 0, sizeof(neutral));
     neutral.need_build = 1;
     KB_CCUDA(cudaMemcpyAsync(h->ctrl.p, &neutral, sizeof(neutral), cudaMemcpyHostToDevice, s));  // pageable source: staged at the call
   }
-  D.ctrl = h->ctrl.p;
-  KB_CCUDA(h->posdef.alloc(2));
-  KB_CCUDA(h->n_invalid.alloc(1));
-  KB_CCUDA(h->lm_counters.alloc(KB_NUM_MODELS));
-  KB_CCUDA(cudaMemsetAsync(h->n_invalid.p, 0, sizeof(unsigned int), s));
-  KB_CCUDA(cudaMemsetAsync(h->dx.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)h->jcols), s));
-  KB_CCUDA(cudaMemsetAsync(h->VB.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)n_views * VB_STRIDE), s));
-  KB_CCUDA(cudaMemsetAsync(h->e.p, 0, sizeof(double) * std::max<size_t>(1, 2 * (size_t)h->n_terms_local), s));
-  KB_CCUDA(cudaMemsetAsync(h->camA.p, 0, sizeof(double) * C * C * 36, s));
-  D.y_u = h->y_u.p; D.y_v = h->y_v.p; D.corner = h->corner.p; D.target = h->target.p;
-  h->front_u = h->y_u.p;
-  h->front_v = h->y_v.p;
-  D.view_set = h->view_set.p; D.view_cam = h->view_cam.p; D.view_begin = h->view_begin.p; D.set_view = h->set_view.p;
-  D.lin_off = h->lin_off.p; D.view_jbase = h->view_jbase.p; D.col_desc = h->col_desc.p;
-  D.cam_params = h->cam_params.p; D.baselines = h->baselines.p; D.set_poses = h->set_poses.p;
-  D.camT = h->camT.p; D.camPi = h->camPi.p; D.camA = h->camA.p; D.baseBt = h->baseBt.p; D.baseM = h->baseM.p;
-  D.e = h->e.p; D.view_cost = h->view_cost.p; D.set_prep = h->set_prep.p; D.VB = h->VB.p; D.gram_partial = h->gram_partial.p; D.sumG = h->sumG.p;
-  D.V = h->V.p; D.bv = h->bv.p; D.W = h->W.p; D.Lv = h->Lv.p; D.yv = h->yv.p;
-  D.U = h->U.p; D.Sred = h->Sred.p; D.dxc = h->dxc.p; D.dx = h->dx.p; D.n_invalid = h->n_invalid.p; D.rho_partial = h->rho_partial.p; D.tickets = h->tickets.p;
-  h->n_partials = schur_num_partials(D);
-  KB_CCUDA(h->partials.alloc(schur_partial_stride(D) * h->n_partials));
+  // ---- derived tables, work buffers, device problem view ----
+  h->d.sT[0] = h->d.sT[3] = 1.0;  // invR = I, NoMEstimator (CalibrationTools.hpp:105-108; BE/src/ErrorTerm.cpp:8-12)
+  {
+    const kb_status st = build_tables(h);
+    if (st != KB_OK) return cfail(st, h->error);
+  }
+  {
+    DevProblem& D = h->d;
+    const size_t NA = D.n_aug;
+    D.px.enabled = 0;
+    D.px.n_ranks = d->n_ranks;
+    D.px.rank = d->rank;
+    D.px.na2 = (int)((NA * NA + 1) & ~(size_t)1);
+    if (d->n_ranks > 1 && d->n_ranks <= PX_MAX_RANKS) {
+      KB_CCUDA(h->px_buf.alloc(px_doubles(D.px)));
+      KB_CCUDA(cudaMemsetAsync(h->px_buf.p, 0, sizeof(double) * px_doubles(D.px), s));
+      D.px.base[d->rank] = h->px_buf.p;
+    }
+  }
   trace.mark("allocations, memsets");
 
   if (d->n_ranks > 1) {
@@ -1468,6 +1520,17 @@ kb_status kb_analyze_marginal_last_build(kb_handle* h, const kb_marginal_options
                                          int32_t* columns) {
   return analyze_marginal_impl(h, o, out, singular_values, V, columns, false);
 }
+kb_status kb_get_last_svd_decomposition(kb_handle* h, double* singular_values, double* V, int32_t* columns) {
+  if (h->last_svd.rank < 0) return fail(h, KB_ERR_STATE, "kb_get_last_svd_decomposition before any kb_solve_system_svd");
+  const int n = h->d.n_c;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  if (singular_values) KB_CUDA(h, cudaMemcpyAsync(singular_values, h->eig_sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (V) KB_CUDA(h, cudaMemcpyAsync(V, h->eig_Vout.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (columns)
+    for (int i = 0; i < n; ++i) columns[i] = h->h_cam_cols[i];
+  return KB_OK;
+}
 kb_status kb_get_last_svd_solve(const kb_handle* h, kb_svd_solve_result* out) {
   if (!out) return KB_ERR_INVALID_ARGUMENT;
   *out = h->last_svd;
@@ -2068,6 +2131,138 @@ kb_status kb_get_hessian_blocks(kb_handle* h, int64_t* n_blocks, int64_t* n_valu
     }
   }
   col_ptr[n_dv] = bi;
+  return KB_OK;
+}
+
+// ---- a live handle grows and shrinks by synced sets (the incremental estimator's batches) -------------------------------------
+namespace {
+void structure_changed(kb_handle* h) {
+  h->built = h->solved = h->has_backup = false;
+  ++h->state_version;
+  h->la_version = -1;
+  h->diag_residual = 0.0;
+  if (h->lm_graph) { cudaGraphExecDestroy(h->lm_graph); h->lm_graph = nullptr; }  // captured with the old sizes / addresses
+  h->lm_warm = false;
+}
+}  // namespace
+
+kb_status kb_append_set(kb_handle* h, int32_t n_views, const int32_t* view_cam, const int64_t* view_begin, const double* y_u, const double* y_v,
+                        const int32_t* corner_id, const double* set_pose) {
+  if (h->n_ranks != 1) return fail(h, KB_ERR_STATE, "kb_append_set needs a single-rank handle");
+  if (h->prefetch_pending || (h->front_u && h->front_u != h->y_u.p))
+    return fail(h, KB_ERR_STATE, "kb_append_set while the observation double buffer is in use (commit and stop prefetching first)");
+  if (n_views < 0 || !view_begin || !set_pose || (n_views > 0 && (!view_cam || !y_u || !y_v || !corner_id)))
+    return fail(h, KB_ERR_INVALID_ARGUMENT, "null argument");
+  if (h->driver_order == KB_ORDER_SINGLE && n_views > 1) return fail(h, KB_ERR_INVALID_ARGUMENT, "single-camera problem: one view per set");
+  const int64_t n_new = view_begin[n_views] - view_begin[0];
+  std::vector<char> seen((size_t)h->n_cams, 0);
+  for (int w = 0; w < n_views; ++w) {
+    if (view_cam[w] < 0 || view_cam[w] >= h->n_cams || seen[(size_t)view_cam[w]]) return fail(h, KB_ERR_INVALID_ARGUMENT, "bad or repeated camera index in the new set");
+    seen[(size_t)view_cam[w]] = 1;
+    if (view_begin[w + 1] < view_begin[w]) return fail(h, KB_ERR_INVALID_ARGUMENT, "view_begin is not monotone");
+  }
+  for (int64_t i = 0; i < n_new; ++i)
+    if (corner_id[i] < 0 || corner_id[i] >= h->d.n_target) return fail(h, KB_ERR_INVALID_ARGUMENT, "corner_id out of range");
+  if (h->n_terms_local + n_new > (int64_t)0x7fffffff) return fail(h, KB_ERR_INVALID_ARGUMENT, "more than 2^31 terms on one rank");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  KB_CUDA(h, cudaStreamSynchronize(s));
+  // observations: appended behind the existing terms (only the new ones travel)
+  const size_t n_old = (size_t)h->n_terms_local;
+  KB_CUDA(h, h->y_u.grow(n_old + (size_t)n_new, s));
+  KB_CUDA(h, h->y_v.grow(n_old + (size_t)n_new, s));
+  KB_CUDA(h, h->corner.grow(n_old + (size_t)n_new, s));
+  if (n_new > 0) {
+    std::vector<uint16_t> c16((size_t)n_new);
+    const int64_t b0 = view_begin[0];
+    for (int64_t i = 0; i < n_new; ++i) c16[(size_t)i] = (uint16_t)corner_id[b0 + i];
+    KB_CUDA(h, cudaMemcpyAsync(h->y_u.p + n_old, y_u + b0, sizeof(double) * (size_t)n_new, cudaMemcpyHostToDevice, s));
+    KB_CUDA(h, cudaMemcpyAsync(h->y_v.p + n_old, y_v + b0, sizeof(double) * (size_t)n_new, cudaMemcpyHostToDevice, s));
+    KB_CUDA(h, cudaMemcpyAsync(h->corner.p + n_old, c16.data(), sizeof(uint16_t) * (size_t)n_new, cudaMemcpyHostToDevice, s));
+    KB_CUDA(h, cudaStreamSynchronize(s));  // c16 is a local
+  }
+  // state: the new pose joins the current state, the reset point and the backup
+  const size_t S_old = (size_t)(h->set_hi - h->set_lo);
+  for (DevBuf<double>* b : {&h->set_poses, &h->init_sets, &h->bk_sets}) {
+    KB_CUDA(h, b->grow((S_old + 1) * KB_POSE_STRIDE, s));
+    KB_CUDA(h, cudaMemcpyAsync(b->p + S_old * KB_POSE_STRIDE, set_pose, sizeof(double) * KB_POSE_STRIDE, cudaMemcpyHostToDevice, s));
+  }
+  KB_CUDA(h, cudaStreamSynchronize(s));
+  // structure
+  for (int w = 0; w < n_views; ++w) {
+    h->h_view_set.push_back((int)S_old);
+    h->h_view_cam.push_back(view_cam[w]);
+    h->h_view_begin.push_back((int)(n_old + (size_t)(view_begin[w + 1] - view_begin[0])));
+  }
+  h->n_terms_local += n_new;
+  h->n_terms_global = h->n_terms_local;
+  h->set_hi += 1;
+  h->n_sets_global += 1;
+  structure_changed(h);
+  kb_status st = build_tables(h);
+  if (st != KB_OK) return st;
+  KB_CUDA(h, cudaStreamSynchronize(s));
+  return KB_OK;
+}
+
+kb_status kb_remove_last_set(kb_handle* h) {
+  if (h->n_ranks != 1) return fail(h, KB_ERR_STATE, "kb_remove_last_set needs a single-rank handle");
+  if (h->prefetch_pending || (h->front_u && h->front_u != h->y_u.p))
+    return fail(h, KB_ERR_STATE, "kb_remove_last_set while the observation double buffer is in use");
+  const int S = h->set_hi - h->set_lo;
+  if (S <= 0) return fail(h, KB_ERR_STATE, "no synced set to remove");
+  // the views of the last set must be the trailing views (true for every set that was appended, and for the per-set term order of
+  // the rig / batch drivers)
+  size_t nv = h->h_view_set.size();
+  size_t first = nv;
+  while (first > 0 && h->h_view_set[first - 1] == S - 1) --first;
+  for (size_t w = 0; w < first; ++w)
+    if (h->h_view_set[w] == S - 1) return fail(h, KB_ERR_STATE, "the views of the last synced set are not the trailing views of the problem");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int n_terms = h->h_view_begin[first];
+  h->h_view_set.resize(first);
+  h->h_view_cam.resize(first);
+  h->h_view_begin.resize(first + 1);
+  h->n_terms_local = n_terms;
+  h->n_terms_global = n_terms;
+  h->y_u.n = h->y_v.n = h->corner.n = (size_t)n_terms;  // capacity stays
+  for (DevBuf<double>* b : {&h->set_poses, &h->init_sets, &h->bk_sets}) b->n = (size_t)(S - 1) * KB_POSE_STRIDE;
+  h->set_hi -= 1;
+  h->n_sets_global -= 1;
+  structure_changed(h);
+  kb_status st = build_tables(h);
+  if (st != KB_OK) return st;
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+// ≙ OptimizationProblem::saveDesignVariables / restoreDesignVariables (IC/src/core/OptimizationProblem.cpp:260-272): what
+// IncrementalEstimator::addBatch brackets a batch with, so that a rejected batch leaves every design variable as it was
+kb_status kb_save_design_variables(kb_handle* h) {
+  KB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  KB_CUDA(h, h->sv_cam.alloc(h->cam_params.n));
+  KB_CUDA(h, h->sv_base.alloc(h->baselines.n));
+  KB_CUDA(h, h->sv_sets.alloc(h->set_poses.n));
+  KB_CUDA(h, cudaMemcpyAsync(h->sv_cam.p, h->cam_params.p, sizeof(double) * h->cam_params.n, cudaMemcpyDeviceToDevice, s));
+  if (h->baselines.n) KB_CUDA(h, cudaMemcpyAsync(h->sv_base.p, h->baselines.p, sizeof(double) * h->baselines.n, cudaMemcpyDeviceToDevice, s));
+  if (h->set_poses.n) KB_CUDA(h, cudaMemcpyAsync(h->sv_sets.p, h->set_poses.p, sizeof(double) * h->set_poses.n, cudaMemcpyDeviceToDevice, s));
+  h->saved_sets = h->set_poses.n;
+  h->has_saved = true;
+  return KB_OK;
+}
+kb_status kb_restore_design_variables(kb_handle* h) {
+  if (!h->has_saved) return fail(h, KB_ERR_STATE, "kb_restore_design_variables without kb_save_design_variables");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  KB_CUDA(h, cudaMemcpyAsync(h->cam_params.p, h->sv_cam.p, sizeof(double) * h->cam_params.n, cudaMemcpyDeviceToDevice, s));
+  if (h->baselines.n) KB_CUDA(h, cudaMemcpyAsync(h->baselines.p, h->sv_base.p, sizeof(double) * h->baselines.n, cudaMemcpyDeviceToDevice, s));
+  // the sets that existed when the state was saved (a set appended since then keeps its pose; one removed since then is gone)
+  const size_t n = std::min(h->saved_sets, h->set_poses.n);
+  if (n) KB_CUDA(h, cudaMemcpyAsync(h->set_poses.p, h->sv_sets.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  ++h->state_version;
+  h->built = h->solved = h->has_backup = false;
   return KB_OK;
 }
 

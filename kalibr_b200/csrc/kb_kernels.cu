@@ -1690,10 +1690,7 @@ __device__ __forceinline__ double eig_block_sum(double v, double* red) {
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  double s = 0.0;
-#pragma unroll
-  for (int i = 0; i < EIG_THREADS / 32; ++i) s += red[i];  // fixed order, identical in every thread
-  return s;
+  return warp_sum(red[threadIdx.x & 31]);  // EIG_THREADS / 32 == 32 partials: one butterfly, identical in every warp
 }
 
 // status_out[0]: 0 = converged, 1 = a QL iteration did not converge.  sv_out: |eigenvalues| sorted descending; V_out: [n][n] row-major,
@@ -1827,11 +1824,11 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) sym_eig_kernel(DevProblem p, d
             break;
           }
           const double ir = rsqrt(rr);
-          const double gd = d[i + 1] - pp;
+          const double gd = d[i + 1] - pp, b2 = b + b;
           e[i + 1] = rr * ir;
           sr = f * ir;
           c = g * ir;
-          const double r2 = fma(di - gd, sr, 2.0 * c * b);
+          const double r2 = fma(c, b2, (di - gd) * sr);  // (d_i - g) s + 2 c b with c and s entering side by side
           pp = sr * r2;
           d[i + 1] = gd + pp;
           g = fma(c, r2, -b);
@@ -1857,11 +1854,13 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) sym_eig_kernel(DevProblem p, d
       const int k = tid - 32, pb = buf ^ 1;
       const int m = s_m[pb], lo = s_lo[pb];
       double zi1 = Z[m * ld + k];
+      double zi = lo <= m - 1 ? Z[(m - 1) * ld + k] : 0.0;
       for (int i = m - 1; i >= lo; --i) {
-        const double zi = Z[i * ld + k];
+        const double zn = i > lo ? Z[(i - 1) * ld + k] : 0.0;  // next rotation's operand, requested before this one's store
         const double c = cs[pb][i], sr = sn[pb][i];
         Z[(i + 1) * ld + k] = sr * zi + c * zi1;
         zi1 = c * zi - sr * zi1;
+        zi = zn;
       }
       Z[lo * ld + k] = zi1;
     }

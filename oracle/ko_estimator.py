@@ -148,7 +148,7 @@ class OracleIncrementalEstimator:
         self.sv_log2_sum, self.rank_theta, self.information_gain = 0.0, -1, 0.0
 
     def _problem(self, batches, poses):
-        from kalibr_b200.problem import ORDER_RIG, Problem
+        from kalibr_b200.problem import ORDER_BATCH, Problem  # the merged incremental problem: poses, baselines, intrinsics
 
         vs, vc, vb, cid, yu, yv = [], [], [0], [], [], []
         for s, b in enumerate(batches):
@@ -157,7 +157,7 @@ class OracleIncrementalEstimator:
                 vs.append(s); vc.append(k)
                 cid.extend(c); yu.extend(u); yv.extend(v)
                 vb.append(len(cid))
-        return Problem(ORDER_RIG, self.cam_model, self.cam_params, self.baselines, np.array(poses, float).reshape(-1, 7), self.target_points,
+        return Problem(ORDER_BATCH, self.cam_model, self.cam_params, self.baselines, np.array(poses, float).reshape(-1, 7), self.target_points,
                        np.array(vs, np.int32), np.array(vc, np.int32), np.array(vb, np.int64), np.array(yu, float), np.array(yv, float),
                        np.array(cid, np.int32))
 

@@ -1,7 +1,8 @@
 // Test driver for include/kalibr_b200/calibration_tools.hpp: reads a flattened set of observations written by
 // tests/test_drivers_gpu.py, runs one of the three kalibr2 drivers on the device and prints the results as "key value..." lines.
 //   driver_main <single|stereo|rig> <problem.bin>
-//   driver_main estimator <problem.bin> <infoGainDelta>     every synced set offered to the incremental estimator, in order
+//   driver_main estimator <problem.bin> <infoGainDelta> [check]   every synced set offered to the incremental estimator, in order
+//                                                                 (check: also verifies the returned null / row spaces and covariance)
 #include <cstdio>
 #include <chrono>
 #include <cstdlib>
@@ -107,6 +108,26 @@ int main(int argc, char** argv) {
         std::memcpy(T.t, &set_poses[(size_t)s * 7 + 4], sizeof(T.t));
         auto r = estimator.addBatch(synced[(size_t)s], T);
         std::printf("batch%d %d %.17g %td %zu %.17g %.17g\n", s, r.batchAccepted ? 1 : 0, r.informationGain, r.rankTheta, r.numIterations, r.JStart, r.JFinal);
+        if (argc > 4) {  // "check": ReturnValue's bases: [obsBasis | nobsBasis] must be an orthonormal basis of the calibration block; sigma2Theta = V_r S_r^-1 V_r^T
+          const auto& O = r.obsBasis; const auto& N = r.nobsBasis;
+          const std::ptrdiff_t n = O.rows;
+          double orth = 0.0, cov = 0.0;
+          auto col = [&](std::ptrdiff_t c, std::ptrdiff_t i) { return c < O.cols ? O(i, c) : N(i, c - O.cols); };
+          for (std::ptrdiff_t a1 = 0; a1 < n; ++a1)
+            for (std::ptrdiff_t b1 = a1; b1 < n; ++b1) {
+              double d = 0.0;
+              for (std::ptrdiff_t i = 0; i < n; ++i) d += col(a1, i) * col(b1, i);
+              orth = std::max(orth, std::fabs(d - (a1 == b1 ? 1.0 : 0.0)));
+            }
+          for (std::ptrdiff_t k = 0; k < O.cols; ++k) {  // sigma2Theta v_k = v_k / sv_k on the row space
+            for (std::ptrdiff_t i = 0; i < n; ++i) {
+              double d = 0.0;
+              for (std::ptrdiff_t j = 0; j < n; ++j) d += r.sigma2Theta(i, j) * O(j, k);
+              cov = std::max(cov, std::fabs(d - O(i, k) / r.singularValues[(size_t)k]) * r.singularValues[(size_t)k]);
+            }
+          }
+          std::printf("spaces%d %td %td %td %.3e %.3e %zu %td\n", s, n, O.cols, N.cols, orth, cov, r.singularValuesScaled.size(), r.obsBasisScaled.cols);
+        }
       }
       std::printf("loop_ms %.3f\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
       std::printf("accepted %zu\n", estimator.getNumBatches());

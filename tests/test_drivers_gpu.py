@@ -136,7 +136,7 @@ def test_incremental_estimator_matches_oracle(oracle_lib, tmp_path, cfg, n_sets,
     res = [synthetic.TRUTH_PARAMS[m][1] for m in p.cam_model]
     path = str(tmp_path / "estimator.bin")
     write_problem(path, p, res)
-    code, out = run_driver("estimator", path, delta)
+    code, out = run_driver("estimator", path, delta, "check")
     assert code == 0, out
     est = ke.OracleIncrementalEstimator(oracle_lib, p.cam_model, p.cam_params, p.baselines, p.target_points, info_gain_delta=delta, check_validity=True)
     decisions = []
@@ -154,6 +154,11 @@ def test_incremental_estimator_matches_oracle(oracle_lib, tmp_path, cfg, n_sets,
         assert abs(gain - r["information_gain"]) <= 1e-6 * max(1.0, abs(r["information_gain"]))
         assert abs(j1 - r["j_final"]) <= 1e-9 * r["j_final"] and abs(j0 - r["j_start"]) <= 1e-9 * r["j_start"]
         decisions.append(bool(acc))
+        # ReturnValue's bases and covariance (IncrementalEstimator.cpp:395-417): dimensions follow the rank, [obs | nobs] is orthonormal
+        n, n_obs, n_nobs, orth, cov, n_scaled, n_obs_scaled = out[f"spaces{s}"]
+        assert int(n) == p.n_c and int(n_obs) == r["rank_theta"] and int(n_obs) + int(n_nobs) == p.n_c
+        assert orth < 1e-10 and cov < 1e-8
+        assert int(n_scaled) == p.n_c and int(n_obs_scaled) == r["rank_theta"]  # column scaling is on: the scaled system's spaces are reported too
     assert int(out["accepted"][0]) == len(est.batches) == sum(decisions)
     if delta > 1.0:
         assert not all(decisions)  # the threshold really rejects something in this sequence
