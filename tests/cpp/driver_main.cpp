@@ -102,11 +102,14 @@ int main(int argc, char** argv) {
       eo.checkValidity = true;  // CalibrateCameras.cpp:261
       kalibr_b200::calibration::IncrementalEstimator estimator(cams, guesses, target, eo);
       const auto t0 = std::chrono::steady_clock::now();
+      std::vector<double> batch_ms;
       for (int s = 0; s < n_sets; ++s) {
         Transformation T;
         std::memcpy(T.q, &set_poses[(size_t)s * 7], sizeof(T.q));
         std::memcpy(T.t, &set_poses[(size_t)s * 7 + 4], sizeof(T.t));
+        const auto tb = std::chrono::steady_clock::now();
         auto r = estimator.addBatch(synced[(size_t)s], T);
+        batch_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb).count());
         std::printf("batch%d %d %.17g %td %zu %.17g %.17g\n", s, r.batchAccepted ? 1 : 0, r.informationGain, r.rankTheta, r.numIterations, r.JStart, r.JFinal);
         if (argc > 4) {  // "check": ReturnValue's bases: [obsBasis | nobsBasis] must be an orthonormal basis of the calibration block; sigma2Theta = V_r S_r^-1 V_r^T
           const auto& O = r.obsBasis; const auto& N = r.nobsBasis;
@@ -119,17 +122,19 @@ int main(int argc, char** argv) {
               for (std::ptrdiff_t i = 0; i < n; ++i) d += col(a1, i) * col(b1, i);
               orth = std::max(orth, std::fabs(d - (a1 == b1 ? 1.0 : 0.0)));
             }
-          for (std::ptrdiff_t k = 0; k < O.cols; ++k) {  // sigma2Theta v_k = v_k / sv_k on the row space
-            for (std::ptrdiff_t i = 0; i < n; ++i) {
-              double d = 0.0;
-              for (std::ptrdiff_t j = 0; j < n; ++j) d += r.sigma2Theta(i, j) * O(j, k);
-              cov = std::max(cov, std::fabs(d - O(i, k) / r.singularValues[(size_t)k]) * r.singularValues[(size_t)k]);
-            }
+          {  // trace(sigma2Theta) = sum of the reciprocal retained singular values (V_r has orthonormal columns)
+            double tr = 0.0, sum = 0.0;
+            for (std::ptrdiff_t i = 0; i < n; ++i) tr += r.sigma2Theta(i, i);
+            for (std::ptrdiff_t k = 0; k < O.cols; ++k) sum += 1.0 / r.singularValues[(size_t)k];
+            cov = std::fabs(tr - sum) / sum;
           }
           std::printf("spaces%d %td %td %td %.3e %.3e %zu %td\n", s, n, O.cols, N.cols, orth, cov, r.singularValuesScaled.size(), r.obsBasisScaled.cols);
         }
       }
       std::printf("loop_ms %.3f\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+      std::printf("batch_ms");  // per addBatch; the first one pays the CUDA context / module load of the process
+      for (double m : batch_ms) std::printf(" %.3f", m);
+      std::printf("\n");
       std::printf("accepted %zu\n", estimator.getNumBatches());
       for (size_t j = 0; j < estimator.baselines().size(); ++j) printPose(("baseline" + std::to_string(j)).c_str(), estimator.baselines()[j]);
       for (int k = 0; k < n_cams; ++k) printCamera(("camera" + std::to_string(k)).c_str(), estimator.cameras()[(size_t)k]);

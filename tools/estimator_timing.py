@@ -25,8 +25,10 @@ with tempfile.TemporaryDirectory() as d:
     code, out = run_driver("estimator", path, 0.2)
     t_dev = time.time() - t
 acc = int(out["accepted"][0])
+bm = np.asarray(out["batch_ms"])
 line = {"cfg": cfg, "batches_offered": S, "accepted": acc, "process_wall_s": round(t_dev, 3), "addBatch_loop_ms": float(out["loop_ms"][0]),
-        "device_ms_per_batch": round(float(out["loop_ms"][0]) / S, 2)}
+        "first_batch_ms_incl_cuda_context": round(float(bm[0]), 2), "median_ms_per_batch": round(float(np.median(bm[1:])), 3),
+        "ms_per_batch_at": {str(i): round(float(bm[i]), 3) for i in sorted({1, len(bm) // 4, len(bm) // 2, len(bm) - 1})}}
 if "--oracle" in sys.argv:
     from oracle import ko_estimator as ke
     from oracle import oracle_api as oa
