@@ -332,7 +332,8 @@ class Harness:
         else:
             lo, hi = synthetic.shard_sets(sets_total, world, rank)
             S_rank, set_offset, S_total = hi - lo, lo, sets_total
-        p = synthetic.make_config(config, n_sets=S_rank, set_seed=20260000 + 100 * config + 7919 + set_offset)
+        # measurements as a corner detector delivers them: float32-representable (the reference's cv::Point2f), held as doubles
+        p = synthetic.make_config(config, n_sets=S_rank, set_seed=20260000 + 100 * config + 7919 + set_offset, float_corners=True)
         terms_total = self.sum_over_ranks(p.n_terms)
         nccl_id = None
         if world > 1:
@@ -419,46 +420,55 @@ def main():
     # ---- end-to-end arm: host buffers in, host results out, every step ----
     e2e = None
     if not args.no_e2e:
-        yu_pin = torch.from_numpy(p.y_u).pin_memory()
-        yv_pin = torch.from_numpy(p.y_v).pin_memory()
-        yu_np, yv_np = yu_pin.numpy(), yv_pin.numpy()
+        def e2e_arm(yu_host, yv_host, bytes_per_term):
+            """K steps through the public entry points with the observations in pinned HOST memory, uploaded every step, and dx fetched
+            every step.  Returns (double-buffered ms per step, isolated streamed-step ms)."""
+            yu_pin, yv_pin = torch.from_numpy(yu_host).pin_memory(), torch.from_numpy(yv_host).pin_memory()
+            yu_np, yv_np = yu_pin.numpy(), yv_pin.numpy()
 
-        def e2e_step_streamed():
-            # H2D of the observations from pinned host memory, pipelined in chunks against the fused kernel inside the
-            # library; D2H: cost, pos-def flag, dx (jcols doubles), rho, max|dx|
-            lm_step(g, fetch_dx=True, host_obs=(yu_np, yv_np))
+            def step_streamed():
+                # H2D of the observations, pipelined in chunks against the fused kernel inside the library; D2H: cost, pos-def flag,
+                # dx (jcols doubles), rho, max|dx|
+                lm_step(g, fetch_dx=True, host_obs=(yu_np, yv_np))
 
-        def e2e_step_pipelined():
-            # double buffering across steps: this step's batch was uploaded while the previous step computed; the next
-            # step's batch starts travelling now (one 16 B/term upload per step inside the timed region either way)
-            g.commit_observations()
+            def step_pipelined():
+                # double buffering across steps: this step's batch was uploaded while the previous step computed; the next step's
+                # batch starts travelling now (one upload per step inside the timed region either way)
+                g.commit_observations()
+                g.prefetch_observations(yu_np, yv_np)
+                lm_step(g, fetch_dx=True)
+
+            for _ in range(2):
+                step_streamed()
+            ms_streamed = H.timed(stream, step_streamed, k_e2e)
             g.prefetch_observations(yu_np, yv_np)
-            lm_step(g, fetch_dx=True)
+            for _ in range(2):
+                step_pipelined()
+
+            def pipelined_run():
+                for _ in range(k_e2e):
+                    step_pipelined()
+                g.commit_observations()               # the last upload is waited for inside the timed region
+                g.prefetch_observations(yu_np, yv_np)
+
+            ms = H.timed(stream, pipelined_run, 1)
+            g.commit_observations()
+            return ms / k_e2e, ms_streamed / k_e2e, int(bytes_per_term * terms_rank)
 
         k_e2e = max(3, args.steps // 2)
-        for _ in range(2):
-            e2e_step_streamed()
-        ms_streamed = H.timed(stream, e2e_step_streamed, k_e2e)
-        g.prefetch_observations(yu_np, yv_np)
-        for _ in range(2):
-            e2e_step_pipelined()
-
-        def pipelined_run():
-            for _ in range(k_e2e):
-                e2e_step_pipelined()
-            g.commit_observations()               # the last upload is waited for inside the timed region
-            g.prefetch_observations(yu_np, yv_np)
-
-        ms_e2e = H.timed(stream, pipelined_run, 1)
-        g.commit_observations()
-        e2e = {"value": terms_total * k_e2e / (ms_e2e * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(16 * terms_rank), "d2h_bytes_per_step": int(8 * g.jcols + 8 * 4 + 4),
-               "ms_per_step": ms_e2e / k_e2e, "steps": k_e2e,
-               "single_step_latency_ms": ms_streamed / k_e2e,
+        yu32, yv32 = p.y_u.astype(np.float32), p.y_v.astype(np.float32)
+        assert np.array_equal(yu32.astype(np.float64), p.y_u) and np.array_equal(yv32.astype(np.float64), p.y_v)  # exact: same values, half the bytes
+        ms64, lat64, b64 = e2e_arm(p.y_u, p.y_v, 16)
+        ms32, lat32, b32 = e2e_arm(yu32, yv32, 8)
+        e2e = {"value": terms_total / (ms32 * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": b32, "d2h_bytes_per_step": int(8 * g.jcols + 8 * 4 + 4),
+               "ms_per_step": ms32, "steps": k_e2e, "single_step_latency_ms": lat32,
+               "host_buffers": "float32 (the corner detector's type, cv::Point2f in the reference; widened exactly on the device)",
+               "f64_host_buffers": {"value": terms_total / (ms64 * 1e-3), "ms_per_step": ms64, "single_step_latency_ms": lat64, "h2d_bytes_per_step": b64},
                "note": "bytes per rank; through B200SchurLinearSystemSolver (C ABI) with pinned HOST observation buffers uploaded every step and dx fetched "
-                       "every step. value: double-buffered (kb_prefetch_observations / kb_commit_observations: the next step's upload overlaps this "
-                       "step's kernels); single_step_latency_ms: one isolated step with kb_evaluate_error_streamed (chunked upload overlapped with "
-                       "the fused kernel). Both are bounded by the 16 B/term PCIe transfer"}
+                       "every step. value: double-buffered (kb_prefetch_observations_f32 / kb_commit_observations: the next step's upload overlaps this "
+                       "step's kernels); single_step_latency_ms: one isolated step with kb_evaluate_error_streamed_f32 (chunked upload overlapped with "
+                       "the fused kernel). Both are bounded by the PCIe transfer of the measurements (8 B/term as float32, 16 B/term as float64)"}
 
     # ---- materialising linearise (HBM-bound variant), timed alone ----
     lin = None

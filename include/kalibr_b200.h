@@ -396,6 +396,13 @@ KB_API kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, con
  * host synchronisation).  The copy overlaps with whatever runs between the two calls. */
 KB_API kb_status kb_prefetch_observations(kb_handle* h, const double* y_u, const double* y_v);
 KB_API kb_status kb_commit_observations(kb_handle* h);
+/* The same three entry points for measurements held in SINGLE precision - the type a corner detector delivers (the reference keeps
+ * image points as cv::Point2f: aslam_cv/aslam_cameras/include/aslam/cameras/GridCalibrationTargetObservation.hpp) and widens to double
+ * when it builds the error terms (K2/include/kalibr2/CameraCalibrator.hpp:245-264).  Here the widening - exact - happens on the device,
+ * so half the bytes cross PCIe; results are bit-identical to passing the widened doubles. */
+KB_API kb_status kb_set_observations_f32(kb_handle* h, const float* y_u, const float* y_v);
+KB_API kb_status kb_evaluate_error_streamed_f32(kb_handle* h, const float* y_u, const float* y_v, int32_t use_m_estimator, double* out_cost);
+KB_API kb_status kb_prefetch_observations_f32(kb_handle* h, const float* y_u, const float* y_v);
 /* terms whose projection bailed out before writing y_hat (zero-weighted here) since creation */
 KB_API int64_t kb_num_invalid_terms(kb_handle* h);
 /* reset state to the initial guess given at kb_create */

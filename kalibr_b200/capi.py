@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
     "kb_set_inv_r", "kb_get_sqrt_inv_r", "kb_set_m_estimator", "kb_m_estimator_parameter", "kb_reprojection_statistics",
+    "kb_set_observations_f32", "kb_evaluate_error_streamed_f32", "kb_prefetch_observations_f32",
     "kb_append_set", "kb_remove_last_set", "kb_save_design_variables", "kb_restore_design_variables",
     "kb_set_state", "kb_set_camera_params", "kb_set_baselines", "kb_set_set_poses", "kb_set_conditioner",
     "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics", "kb_default_svd_solver_options", "kb_solve_system_svd", "kb_optimize_gauss_newton", "kb_analyze_marginal_last_build", "kb_get_last_svd_solve", "kb_get_last_svd_decomposition",
@@ -103,6 +104,9 @@ def load_library() -> C.CDLL:
     L.kb_evaluate_error_streamed.argtypes = [vp, vp, vp, C.c_int32, vp]
     L.kb_prefetch_observations.argtypes = [vp, vp, vp]
     L.kb_commit_observations.argtypes = [vp]
+    L.kb_set_observations_f32.argtypes = [vp, vp, vp]
+    L.kb_evaluate_error_streamed_f32.argtypes = [vp, vp, vp, C.c_int32, vp]
+    L.kb_prefetch_observations_f32.argtypes = [vp, vp, vp]
     L.kb_default_marginal_options.argtypes = [vp]
     L.kb_default_marginal_options.restype = None
     L.kb_analyze_marginal.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -423,18 +427,30 @@ class B200SchurLinearSystemSolver:
         d = np.ascontiguousarray(diag, np.float64)
         self._check(self._L.kb_set_conditioner(self._h, _p(d)), "kb_set_conditioner")
 
+    @staticmethod
+    def _obs_suffix(y_u, y_v):
+        """float32 arrays (the detector's precision) go through the *_f32 entry points: half the bytes over PCIe, widened on the device"""
+        if y_u.dtype == np.float32 and y_v.dtype == np.float32:
+            return "_f32"
+        if y_u.dtype == np.float64 and y_v.dtype == np.float64:
+            return ""
+        raise KalibrB200Error("observations must be two float64 or two float32 arrays")
+
     def set_observations(self, y_u: np.ndarray, y_v: np.ndarray):
-        self._check(self._L.kb_set_observations(self._h, _p(y_u), _p(y_v)), "kb_set_observations")
+        fn = getattr(self._L, "kb_set_observations" + self._obs_suffix(y_u, y_v))
+        self._check(fn(self._h, _p(y_u), _p(y_v)), "kb_set_observations")
 
     def evaluate_error_streamed(self, y_u: np.ndarray, y_v: np.ndarray, use_m_estimator: bool = True) -> float:
         """set_observations + evaluate_error with the upload pipelined against the evaluation (pass pinned host arrays)."""
         J = C.c_double(0.0)
-        self._check(self._L.kb_evaluate_error_streamed(self._h, _p(y_u), _p(y_v), 1 if use_m_estimator else 0, C.byref(J)), "kb_evaluate_error_streamed")
+        fn = getattr(self._L, "kb_evaluate_error_streamed" + self._obs_suffix(y_u, y_v))
+        self._check(fn(self._h, _p(y_u), _p(y_v), 1 if use_m_estimator else 0, C.byref(J)), "kb_evaluate_error_streamed")
         return J.value
 
     def prefetch_observations(self, y_u: np.ndarray, y_v: np.ndarray):
         """Start the upload of the NEXT batch of measurements into the back buffers (pinned host arrays, kept alive by the caller)."""
-        self._check(self._L.kb_prefetch_observations(self._h, _p(y_u), _p(y_v)), "kb_prefetch_observations")
+        fn = getattr(self._L, "kb_prefetch_observations" + self._obs_suffix(y_u, y_v))
+        self._check(fn(self._h, _p(y_u), _p(y_v)), "kb_prefetch_observations")
 
     def commit_observations(self):
         self._check(self._L.kb_commit_observations(self._h), "kb_commit_observations")

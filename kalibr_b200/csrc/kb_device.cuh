@@ -197,6 +197,8 @@ cudaError_t launch_omni_candidates(const DevProblem& p, const int* cam_views, in
                                    double* cand /*[n_views * rows][2]*/, double* out3, StreamCtx& s);
 cudaError_t launch_best_view_mask(const DevProblem& p, unsigned char* mask /*[n_views]*/, StreamCtx& s);
 cudaError_t launch_set_pose_guess(const DevProblem& p, const double* T_views, const int* ok_views, double* set_poses_out, int* set_ok, StreamCtx& s);
+// su / sv (device, n floats each; 8-byte aligned offsets) -> du / dv (doubles); offsets must be even for the vectorised path
+cudaError_t launch_widen_observations(const float* su, const float* sv, double* du, double* dv, long long n, cudaStream_t stream, long long* launches);
 int schur_num_partials(const DevProblem& p);
 size_t schur_partial_stride(const DevProblem& p);
 

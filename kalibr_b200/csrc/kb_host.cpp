@@ -145,6 +145,7 @@ struct kb_handle {
   // double-buffered observations: kb_prefetch_observations fills the back buffers on the copy stream while the front ones
   // are in use, kb_commit_observations swaps them
   DevBuf<double> y_u_back, y_v_back;
+  DevBuf<float> stage_u, stage_v;  // single-precision measurements land here and are widened on the device (the *_f32 entry points)
   double *front_u = nullptr, *front_v = nullptr, *back_u = nullptr, *back_v = nullptr;
   cudaEvent_t ev_prefetch = nullptr, ev_front_free = nullptr;
   bool prefetch_pending = false, front_free_recorded = false;
@@ -859,16 +860,59 @@ kb_status kb_evaluate_error(kb_handle* h, int32_t use_m_estimator, double* out_c
 }
 
 // kb_set_observations + kb_evaluate_error with the upload overlapped: the observations travel in KB_STREAM_CHUNKS pieces on a
-// copy stream and the fused kernel starts on each piece as soon as it has landed.
-kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const double* y_v, int32_t use_m_estimator, double* out_cost) {
+// copy stream and the fused kernel starts on each piece as soon as it has landed.  T = double, or float for measurements in the
+// detector's own precision (half the bytes over PCIe; widened exactly on the device, on the copy stream).
+}  // extern "C"
+template <typename T>
+static kb_status upload_chunk(kb_handle* h, const T* y_u, const T* y_v, int64_t lo, int64_t n, double* dst_u, double* dst_v, cudaStream_t cs);
+template <>
+kb_status upload_chunk<double>(kb_handle* h, const double* y_u, const double* y_v, int64_t lo, int64_t n, double* dst_u, double* dst_v, cudaStream_t cs) {
+  KB_CUDA(h, cudaMemcpyAsync(dst_u + lo, y_u + lo, sizeof(double) * n, cudaMemcpyHostToDevice, cs));
+  KB_CUDA(h, cudaMemcpyAsync(dst_v + lo, y_v + lo, sizeof(double) * n, cudaMemcpyHostToDevice, cs));
+  return KB_OK;
+}
+template <>
+kb_status upload_chunk<float>(kb_handle* h, const float* y_u, const float* y_v, int64_t lo, int64_t n, double* dst_u, double* dst_v, cudaStream_t cs) {
+  KB_CUDA(h, cudaMemcpyAsync(h->stage_u.p + lo, y_u + lo, sizeof(float) * n, cudaMemcpyHostToDevice, cs));
+  KB_CUDA(h, cudaMemcpyAsync(h->stage_v.p + lo, y_v + lo, sizeof(float) * n, cudaMemcpyHostToDevice, cs));
+  KB_CUDA(h, launch_widen_observations(h->stage_u.p + lo, h->stage_v.p + lo, dst_u + lo, dst_v + lo, n, cs, &h->launches));
+  return KB_OK;
+}
+template <typename T>
+static kb_status ensure_stage(kb_handle*) { return KB_OK; }
+template <>
+kb_status ensure_stage<float>(kb_handle* h) {
+  const size_t n = (size_t)std::max<int64_t>(h->n_terms_local, 1);
+  if (h->stage_u.n < n) KB_CUDA(h, h->stage_u.alloc(n));
+  if (h->stage_v.n < n) KB_CUDA(h, h->stage_v.alloc(n));
+  return KB_OK;
+}
+
+template <typename T>
+static kb_status set_observations_impl(kb_handle* h, const T* y_u, const T* y_v) {
+  if (h->n_ranks != 1 && !h->presharded)
+    return fail(h, KB_ERR_STATE, "kb_set_observations needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
+  if (!y_u || !y_v) return fail(h, KB_ERR_INVALID_ARGUMENT, "null observation array");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  kb_status st = ensure_stage<T>(h);
+  if (st != KB_OK) return st;
+  if ((st = upload_chunk<T>(h, y_u, y_v, 0, h->n_terms_local, h->front_u, h->front_v, h->stream)) != KB_OK) return st;
+  ++h->state_version;
+  return KB_OK;
+}
+
+template <typename T>
+static kb_status evaluate_error_streamed_impl(kb_handle* h, const T* y_u, const T* y_v, int32_t use_m_estimator, double* out_cost) {
   if (h->n_ranks != 1 && !h->presharded)
     return fail(h, KB_ERR_STATE, "kb_evaluate_error_streamed needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
   if (!y_u || !y_v) return fail(h, KB_ERR_INVALID_ARGUMENT, "null observation array");
   if (!h->speculative || (h->d.mest_kind != 0 && !use_m_estimator)) {
-    kb_status st = kb_set_observations(h, y_u, y_v);
+    kb_status st = set_observations_impl<T>(h, y_u, y_v);
     return st != KB_OK ? st : kb_evaluate_error(h, use_m_estimator, out_cost);
   }
   KB_CUDA(h, cudaSetDevice(h->device));
+  kb_status st = ensure_stage<T>(h);
+  if (st != KB_OK) return st;
   set_rows_mode(h, use_m_estimator);
   StreamCtx c = ctx(h);
   ++h->state_version;
@@ -877,10 +921,7 @@ kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const doub
   KB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
   for (int k = 0; k < KB_STREAM_CHUNKS; ++k) {
     const int64_t lo = h->st_chunk_term[k], n = h->st_chunk_term[k + 1] - lo;
-    if (n > 0) {
-      KB_CUDA(h, cudaMemcpyAsync(h->front_u + lo, y_u + lo, sizeof(double) * n, cudaMemcpyHostToDevice, h->copy_stream));
-      KB_CUDA(h, cudaMemcpyAsync(h->front_v + lo, y_v + lo, sizeof(double) * n, cudaMemcpyHostToDevice, h->copy_stream));
-    }
+    if (n > 0 && (st = upload_chunk<T>(h, y_u, y_v, lo, n, h->front_u, h->front_v, h->copy_stream)) != KB_OK) return st;
     KB_CUDA(h, cudaEventRecord(h->ev_chunk[k], h->copy_stream));
   }
   {
@@ -895,11 +936,18 @@ kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const doub
     if (h->px_on) {
       KB_CUDA(h, launch_px_combine_cost(h->d, h->scalars.p, 0, nullptr, nullptr, c));
     } else {
-      kb_status st = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
-      if (st != KB_OK) return st;
+      kb_status st2 = nccl_allreduce(h, h->scalars.p, 1, kNcclFloat64, kNcclSum);
+      if (st2 != KB_OK) return st2;
     }
   }
   return finish_evaluate(h, out_cost);
+}
+extern "C" {
+kb_status kb_evaluate_error_streamed(kb_handle* h, const double* y_u, const double* y_v, int32_t use_m_estimator, double* out_cost) {
+  return evaluate_error_streamed_impl<double>(h, y_u, y_v, use_m_estimator, out_cost);
+}
+kb_status kb_evaluate_error_streamed_f32(kb_handle* h, const float* y_u, const float* y_v, int32_t use_m_estimator, double* out_cost) {
+  return evaluate_error_streamed_impl<float>(h, y_u, y_v, use_m_estimator, out_cost);
 }
 
 kb_status kb_build_system(kb_handle* h, int32_t use_m_estimator) {
@@ -1664,24 +1712,20 @@ kb_status kb_reset_state(kb_handle* h) {
   return KB_OK;
 }
 
-kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v) {
-  if (h->n_ranks != 1 && !h->presharded)
-    return fail(h, KB_ERR_STATE, "kb_set_observations needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
-  if (!y_u || !y_v) return fail(h, KB_ERR_INVALID_ARGUMENT, "null observation array");
-  KB_CUDA(h, cudaSetDevice(h->device));
-  KB_CUDA(h, cudaMemcpyAsync(h->front_u, y_u, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
-  KB_CUDA(h, cudaMemcpyAsync(h->front_v, y_v, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->stream));
-  ++h->state_version;
-  return KB_OK;
-}
+kb_status kb_set_observations(kb_handle* h, const double* y_u, const double* y_v) { return set_observations_impl<double>(h, y_u, y_v); }
+kb_status kb_set_observations_f32(kb_handle* h, const float* y_u, const float* y_v) { return set_observations_impl<float>(h, y_u, y_v); }
 
+}  // extern "C"
 // Double buffering of the measurements for callers that feed a new batch per step: the upload of the NEXT batch runs on the
 // copy stream into the back buffers while the current step computes on the front buffers.
-kb_status kb_prefetch_observations(kb_handle* h, const double* y_u, const double* y_v) {
+template <typename T>
+static kb_status prefetch_observations_impl(kb_handle* h, const T* y_u, const T* y_v) {
   if (h->n_ranks != 1 && !h->presharded)
     return fail(h, KB_ERR_STATE, "kb_prefetch_observations needs a single rank or a pre-sharded problem (terms are re-packed per rank otherwise)");
   if (!y_u || !y_v) return fail(h, KB_ERR_INVALID_ARGUMENT, "null observation array");
   KB_CUDA(h, cudaSetDevice(h->device));
+  kb_status st = ensure_stage<T>(h);
+  if (st != KB_OK) return st;
   if (!h->back_u) {
     KB_CUDA(h, h->y_u_back.alloc((size_t)h->n_terms_local));
     KB_CUDA(h, h->y_v_back.alloc((size_t)h->n_terms_local));
@@ -1690,12 +1734,14 @@ kb_status kb_prefetch_observations(kb_handle* h, const double* y_u, const double
   }
   // the back buffers were the front ones until the last commit: wait for everything that was enqueued on them
   if (h->front_free_recorded) KB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_front_free, 0));
-  KB_CUDA(h, cudaMemcpyAsync(h->back_u, y_u, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->copy_stream));
-  KB_CUDA(h, cudaMemcpyAsync(h->back_v, y_v, sizeof(double) * h->n_terms_local, cudaMemcpyHostToDevice, h->copy_stream));
+  if ((st = upload_chunk<T>(h, y_u, y_v, 0, h->n_terms_local, h->back_u, h->back_v, h->copy_stream)) != KB_OK) return st;
   KB_CUDA(h, cudaEventRecord(h->ev_prefetch, h->copy_stream));
   h->prefetch_pending = true;
   return KB_OK;
 }
+extern "C" {
+kb_status kb_prefetch_observations(kb_handle* h, const double* y_u, const double* y_v) { return prefetch_observations_impl<double>(h, y_u, y_v); }
+kb_status kb_prefetch_observations_f32(kb_handle* h, const float* y_u, const float* y_v) { return prefetch_observations_impl<float>(h, y_u, y_v); }
 
 kb_status kb_commit_observations(kb_handle* h) {
   if (!h->prefetch_pending) return fail(h, KB_ERR_STATE, "kb_commit_observations without a pending kb_prefetch_observations");

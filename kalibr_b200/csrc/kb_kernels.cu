@@ -2729,6 +2729,27 @@ cudaError_t launch_lm_finish(const DevProblem& p, StreamCtx& s) {
   return cudaGetLastError();
 }
 
+// measurements that arrived in single precision (the detector's type): exact widening into the FP64 arrays the kernels read
+__global__ void __launch_bounds__(256) widen_observations_kernel(const float* __restrict__ su, const float* __restrict__ sv, double* __restrict__ du,
+                                                                 double* __restrict__ dv, long long n) {
+  const long long i2 = 2ll * (blockIdx.x * (long long)blockDim.x + threadIdx.x);  // two terms per thread: 8-byte loads, 16-byte stores
+  if (i2 + 1 < n) {
+    const float2 a = *reinterpret_cast<const float2*>(su + i2), b = *reinterpret_cast<const float2*>(sv + i2);
+    *reinterpret_cast<double2*>(du + i2) = make_double2((double)a.x, (double)a.y);
+    *reinterpret_cast<double2*>(dv + i2) = make_double2((double)b.x, (double)b.y);
+  } else if (i2 < n) {
+    du[i2] = (double)su[i2];
+    dv[i2] = (double)sv[i2];
+  }
+}
+cudaError_t launch_widen_observations(const float* su, const float* sv, double* du, double* dv, long long n, cudaStream_t stream, long long* launches) {
+  if (n <= 0) return cudaSuccess;
+  const long long threads = (n + 1) / 2;
+  widen_observations_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(su, sv, du, dv, n);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_apply_update(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int*, double* backup_cam, double* backup_base,
                                 double* backup_sets, StreamCtx& s) {
   const int n = p.n_sets > 0 ? p.n_sets : 1;

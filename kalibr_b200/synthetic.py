@@ -199,6 +199,7 @@ def make_problem(
     driver_order: int,
     seed: int,
     noise_px: float = 0.3,
+    float_corners: bool = False,
     dropout: float = 0.0,
     perturb: bool = True,
     name: str = "",
@@ -302,6 +303,11 @@ def make_problem(
     counts = keep.sum(axis=1)
     view_begin = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     corner_id = np.tile(np.arange(T, dtype=np.int32), V).reshape(V, T)[keep]
+    if float_corners:
+        # corner detectors deliver single precision (the reference keeps image points as cv::Point2f): the measurements are
+        # rounded to float32 and stored as doubles, so that they can also travel as 8 B / term (kb_*_observations_f32)
+        u_all = u_all.astype(np.float32).astype(np.float64)
+        v_all = v_all.astype(np.float32).astype(np.float64)
     y_u = u_all[keep]
     y_v = v_all[keep]
 

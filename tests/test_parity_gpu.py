@@ -399,3 +399,31 @@ def test_marginal_analysis_rank_deficient_camera(capi, oracle_lib):
     null_cols = np.abs(Vg[:, 8:]).sum(axis=1) > 1e-6
     expected = np.isin(cg, np.setdiff1d(cg, cg[:8])) if False else ~np.isin(np.arange(rg.n), np.arange(8))
     assert np.array_equal(null_cols, expected)
+
+
+def test_single_precision_observations_are_widened_exactly(capi):
+    """kb_*_observations_f32: measurements in the detector's precision (cv::Point2f in the reference) give bit-identical results to the
+    same values passed as doubles - set, streamed and prefetched."""
+    p = synthetic.make_config(3, n_sets=12, float_corners=True)
+    yu32, yv32 = p.y_u.astype(np.float32), p.y_v.astype(np.float32)
+    assert np.array_equal(yu32.astype(np.float64), p.y_u)
+    g = capi.B200SchurLinearSystemSolver(p)
+    J0, e0 = g.evaluate_error(), g.error_vector()
+    rng = np.random.default_rng(5)
+    shift = (rng.normal(0, 0.2, p.n_terms)).astype(np.float32)
+    au32, av32 = (yu32 + shift).astype(np.float32), (yv32 - shift).astype(np.float32)
+    au64, av64 = au32.astype(np.float64), av32.astype(np.float64)
+    g.set_observations(au64, av64)
+    J1, e1 = g.evaluate_error(), g.error_vector()
+    assert J1 != J0
+    g.set_observations(yu32, yv32)          # back to the original values, through the f32 path
+    assert g.evaluate_error() == J0 and np.array_equal(g.error_vector(), e0)
+    g.set_observations(au32, av32)
+    assert g.evaluate_error() == J1 and np.array_equal(g.error_vector(), e1)
+    Js = g.evaluate_error_streamed(yu32, yv32)
+    assert abs(Js - J0) <= 1e-13 * J0 and np.array_equal(g.error_vector(), e0)   # the chunked evaluation sums the cost in another order
+    g.prefetch_observations(au32, av32)
+    g.commit_observations()
+    assert g.evaluate_error() == J1 and np.array_equal(g.error_vector(), e1)
+    with pytest.raises(capi.KalibrB200Error):
+        g.set_observations(au32, av64)
