@@ -173,15 +173,16 @@ cudaError_t launch_lm_revert(const DevProblem& p, const double* backup_cam, cons
 cudaError_t launch_lm_finish(const DevProblem& p, StreamCtx& s);
 // eigen-decomposition of the reduced system in p.Sred (G, V: scratch of (n_c + 1) * n_c doubles each, V_tmp: n_c * n_c):
 // Householder + QL, then a Jacobi polish from the QL vectors.  status: int[2] = {Jacobi sweeps, QL failed}
+// V_warm (may be null): vectors of a nearby system to start the Jacobi iteration from instead of running QL; V_keep (may be null): gets V_out
 cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, double* sv_out /*[n_c]*/, double* V_out /*[n_c][n_c]*/, double* V_tmp,
-                                int* status, StreamCtx& s);
+                                int* status, const double* V_warm, double* V_keep, StreamCtx& s);
 // truncated-SVD solve of the reduced system in p.Sred (undamped Schur complement): optional column scaling from diag_h (global diagonal
 // of the camera block), eigen-decomposition (QL; plus the Jacobi polish when the system is not scaled), rank cut, x_r into p.dxc;
 // result = {rank, tolerance, gap}
 cudaError_t launch_camera_diag(const DevProblem& p, double* out /*[n_c]*/, StreamCtx& s);
 cudaError_t launch_svd_solve(const DevProblem& p, const double* diag_h, double norm_tol, int column_scaling, double eps_svd, double svd_tol,
                              double* g /*[n_c]*/, double* G, double* V, double* sv, double* V_out, double* V_tmp, int* status, double* result /*[4]*/,
-                             StreamCtx& s);
+                             const double* V_warm, double* V_keep, StreamCtx& s);
 // peer exchange consumers
 cudaError_t launch_px_reduce_system(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max /*[2]*/, int* pos_def_flag, int lm_mode, StreamCtx& s);

@@ -158,6 +158,10 @@ struct kb_handle {
   DevBuf<double> rank_slots;    // [n_ranks][4]
   DevBuf<LmCtrl> ctrl;          // control block of the device-resident LM loop (neutral flags outside kb_optimize)
   DevBuf<double> eig_G, eig_V, eig_sv, eig_Vout, eig_Vtmp;  // marginal analysis scratch / results
+  // eigenvectors of the last decomposition per system kind (0: unscaled marginal system, 1: column-scaled system of the solver): the
+  // warm start of the next one.  Every 32nd decomposition goes through QL again, which also renews the orthogonality of the vectors.
+  DevBuf<double> eig_warm[2];
+  int eig_warm_age[2] = {-1, -1};  // -1: no vectors yet
   DevBuf<int> eig_sweeps;
   DevBuf<double> trace_dev;
   LmCtrl* h_ctrl = nullptr;     // pinned
@@ -1351,6 +1355,20 @@ void kb_default_marginal_options(kb_marginal_options* o) {
   o->svd_tol = -1.0;
 }
 
+// warm start of the eigen-decomposition of system kind `kind`: the vectors of the previous one, or null (first call, every 32nd call,
+// KB_EIG_NO_WARM set).  Allocates the keep buffer.
+static const double* eig_warm_start(kb_handle* h, int kind) {
+  const size_t n = (size_t)h->d.n_c;
+  if (h->eig_warm[kind].n != n * n) {
+    if (h->eig_warm[kind].alloc(n * n) != cudaSuccess) return nullptr;
+    h->eig_warm_age[kind] = -1;
+  }
+  static const bool disabled = getenv("KB_EIG_NO_WARM") != nullptr;
+  const bool warm = !disabled && h->eig_warm_age[kind] >= 0 && h->eig_warm_age[kind] < 31;
+  h->eig_warm_age[kind] = warm ? h->eig_warm_age[kind] + 1 : 0;
+  return warm ? h->eig_warm[kind].p : nullptr;
+}
+
 static kb_status analyze_marginal_impl(kb_handle* h, const kb_marginal_options* o, kb_marginal_result* out, double* singular_values, double* V,
                                        int32_t* columns, bool rebuild) {
   if (!o || !out || !singular_values) return fail(h, KB_ERR_INVALID_ARGUMENT, "null argument");
@@ -1382,7 +1400,8 @@ static kb_status analyze_marginal_impl(kb_handle* h, const kb_marginal_options* 
   if (h->n_ranks > 1 && (st = nccl_allreduce(h, h->posdef.p, 1, kNcclInt32, kNcclMin)) != KB_OK) return st;
   {
     StageTimer t(h, 4);  // reported as "reduced_solve": the dense stage of this entry point
-    KB_CUDA(h, launch_marginal_eig(h->d, h->eig_G.p, h->eig_V.p, h->eig_sv.p, h->eig_Vout.p, h->eig_Vtmp.p, h->eig_sweeps.p, c));
+    const double* warm = eig_warm_start(h, 0);
+    KB_CUDA(h, launch_marginal_eig(h->d, h->eig_G.p, h->eig_V.p, h->eig_sv.p, h->eig_Vout.p, h->eig_Vtmp.p, h->eig_sweeps.p, warm, h->eig_warm[0].p, c));
   }
   KB_CUDA(h, cudaMemcpyAsync(h->h_posdef, h->posdef.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(singular_values, h->eig_sv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -1633,8 +1652,10 @@ kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, doub
   {
     StageTimer t(h, 4);
     const double norm_tol = std::sqrt((double)kb_jrows(h) * o->eps_norm);  // columnScalingMatrix: sqrt(A->nrow * eps)
+    const int kind = o->column_scaling ? 1 : 0;
+    const double* warm = eig_warm_start(h, kind);
     KB_CUDA(h, launch_svd_solve(h->d, h->svd_diag.p, norm_tol, o->column_scaling ? 1 : 0, o->eps_svd, o->svd_tol, h->svd_g.p, h->eig_G.p, h->eig_V.p,
-                                h->eig_sv.p, h->eig_Vout.p, h->eig_Vtmp.p, h->eig_sweeps.p, h->svd_result.p, c));
+                                h->eig_sv.p, h->eig_Vout.p, h->eig_Vtmp.p, h->eig_sweeps.p, h->svd_result.p, warm, h->eig_warm[kind].p, c));
   }
   double res[4] = {0, 0, 0, 0};
   int sweeps2[8] = {0, 0, 0, 0, 0, 0, 0, 0};

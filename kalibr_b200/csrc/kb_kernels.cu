@@ -1525,6 +1525,39 @@ __device__ __forceinline__ bool diag_block(double* __restrict__ Lp, int j0, doub
   }
   return ok;
 }
+// The same factorisation by ONE WARP (call with all 32 lanes of a warp; lanes 0..7 own the rows): right-looking, so that the
+// dependent chain per column is one reciprocal square root, one product, one shuffle and one FMA instead of a serial sweep over the
+// block by a single thread (FP64 results take ~20 cycles to come back: the serial version spends ~2.5 us per panel on this GPU).
+// Rows / columns past w are padded with the identity.  Returns false if a pivot is not positive (same in every lane).
+__device__ __forceinline__ bool diag_block_warp(double* __restrict__ Lp, int j0, int w, double* __restrict__ rd_all, int lane) {
+  const int r = lane & 7;  // lanes 8..31 shadow lanes 0..7 (no divergence around the shuffles); only lanes 0..7 store
+  double a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = (r < w && c <= r) ? Lp[(j0 + r) * (j0 + r + 1) / 2 + j0 + c] : (c == r ? 1.0 : 0.0);
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const double d = __shfl_sync(0xffffffffu, a[c], c);  // the pivot, from the lane that owns row c
+    if (c < w && !(d > 0.0)) ok = false;
+    const double rdc = rsqrt(d);
+    if (r == c) a[c] = d * rdc;          // sqrt(d)
+    else if (r > c) a[c] *= rdc;         // L[r][c]
+    if (lane == c && c < w) rd_all[j0 + c] = rdc;
+    // trailing update of this lane's row: a[j] -= L[r][c] L[j][c] for c < j <= r
+#pragma unroll
+    for (int j = c + 1; j < 8; ++j) {
+      const double ljc = __shfl_sync(0xffffffffu, a[c], j);
+      if (j <= r) a[j] = fma(-a[c], ljc, a[j]);
+    }
+  }
+  if (lane < w) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c <= lane) Lp[(j0 + lane) * (j0 + lane + 1) / 2 + j0 + c] = a[c];
+  }
+  return ok;
+}
+
 // rows below the diagonal block: x Ldd^T = a, a forward substitution per row (thread per row) with the block in registers
 template <int W>
 __device__ __forceinline__ void panel_rows(double* __restrict__ Lp, int j0, int n, const double* __restrict__ rd_all, int tid, int nthreads) {
@@ -1604,13 +1637,20 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
       const double* Bbase = Lp + tri(j0 + arow, 0);  // B fragment: L[j0 + lane/4][k0 + lane%4]
       for (int t = first_tile + warp; t < n_tiles; t += RS_THREADS / 32) {
         const double* Abase = Lp + tri(RS_NB * t + arow, 0);
-        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-        for (int k0 = 0; k0 < j0; k0 += 8) {  // two independent chains
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
+        int k0 = 0;
+        for (; k0 + 16 <= j0; k0 += 16) {  // four independent accumulator chains: the tensor pipe's result latency is what this loop waits for
+          dmma(c0, c1, Abase[k0 + acol], Bbase[k0 + acol]);
+          dmma(e0, e1, Abase[k0 + 4 + acol], Bbase[k0 + 4 + acol]);
+          dmma(f0, f1, Abase[k0 + 8 + acol], Bbase[k0 + 8 + acol]);
+          dmma(g0, g1, Abase[k0 + 12 + acol], Bbase[k0 + 12 + acol]);
+        }
+        if (k0 < j0) {  // j0 is a multiple of 8
           dmma(c0, c1, Abase[k0 + acol], Bbase[k0 + acol]);
           dmma(e0, e1, Abase[k0 + 4 + acol], Bbase[k0 + 4 + acol]);
         }
-        c0 += e0;
-        c1 += e1;
+        c0 = (c0 + e0) + (f0 + g0);
+        c1 = (c1 + e1) + (f1 + g1);
         const int row = RS_NB * t + arow, col = j0 + 2 * acol;
         if (row < n) {
           if (col <= row && col < j0 + w) Lp[tri(row, col)] -= c0;
@@ -1619,20 +1659,10 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
       }
       __syncthreads();
     }
-    // ---- 2. diagonal block (one thread, registers) ----
-    if (tid == 0) {
-      bool ok = true;
-      switch (w) {
-        case 8: ok = diag_block<8>(Lp, j0, s_rd); break;
-        case 7: ok = diag_block<7>(Lp, j0, s_rd); break;
-        case 6: ok = diag_block<6>(Lp, j0, s_rd); break;
-        case 5: ok = diag_block<5>(Lp, j0, s_rd); break;
-        case 4: ok = diag_block<4>(Lp, j0, s_rd); break;
-        case 3: ok = diag_block<3>(Lp, j0, s_rd); break;
-        case 2: ok = diag_block<2>(Lp, j0, s_rd); break;
-        default: ok = diag_block<1>(Lp, j0, s_rd); break;
-      }
-      if (!ok) s_ok = 0;
+    // ---- 2. diagonal block (one warp, a row per lane) ----
+    if (warp == 0) {
+      const bool ok = diag_block_warp(Lp, j0, w, s_rd, lane);
+      if (!ok && lane == 0) s_ok = 0;
     }
     __syncthreads();
     // ---- 3. rows below the block ----
@@ -2664,10 +2694,17 @@ cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, int lm_mod
 }
 // Eigen-decomposition of the reduced system in p.Sred: QL (always), then the Jacobi polish when `polish` (unscaled, graded systems).
 // status[0] = Jacobi sweeps of the polish (0 without it), status[1] = 1 when the QL iteration did not converge.
+// V_warm (may be null): eigenvectors of a NEARBY system (the previous solve / analysis of this handle).  The reduced system changes
+// little from one Gauss-Newton iteration or batch to the next, so the one-sided Jacobi iteration started from them converges in 2-3
+// sweeps and replaces the whole QL stage (whose rotation chain is serial); V_keep receives the new vectors for the next call.
 static cudaError_t launch_sym_eig(const DevProblem& p, double* G, double* V, double* sv_out, double* V_out, double* V_tmp, int* status, bool polish,
-                                  StreamCtx& s) {
+                                  const double* V_warm, double* V_keep, StreamCtx& s) {
   const size_t n = (size_t)p.n_c, ld = n | 1;
-  {
+  if (V_warm) {
+    polish = true;
+    cudaError_t e = cudaMemsetAsync(status + 1, 0, 5 * sizeof(int), s.stream);  // no QL stage: its status / diagnostics read 0
+    if (e != cudaSuccess) return e;
+  } else {
     const size_t bytes = sizeof(double) * 2 * n * ld;
     const size_t smem = bytes <= 200 * 1024 ? bytes : 0;
     static size_t attr_smem_dev[MAX_DEVICES] = {};
@@ -2681,16 +2718,21 @@ static cudaError_t launch_sym_eig(const DevProblem& p, double* G, double* V, dou
     const size_t smem = bytes <= 220 * 1024 ? bytes : 0;
     static size_t attr_smem_dev[MAX_DEVICES] = {};
     if (cudaError_t e = ensure_dynamic_smem(jacobi_polish_kernel, smem, attr_smem_dev); e != cudaSuccess) return e;
-    jacobi_polish_kernel<<<1, EIG_THREADS, smem, s.stream>>>(p, V_tmp, G, V, sv_out, V_out, status, smem ? 1 : 0);
+    jacobi_polish_kernel<<<1, EIG_THREADS, smem, s.stream>>>(p, V_warm ? V_warm : V_tmp, G, V, sv_out, V_out, status, smem ? 1 : 0);
     KB_LAUNCHED(s);
   } else {
     cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), s.stream);
     if (e != cudaSuccess) return e;
   }
+  if (V_keep) {
+    cudaError_t e = cudaMemcpyAsync(V_keep, V_out, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, s.stream);
+    if (e != cudaSuccess) return e;
+  }
   return cudaGetLastError();
 }
-cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, double* sv_out, double* V_out, double* V_tmp, int* status, StreamCtx& s) {
-  return launch_sym_eig(p, G, V, sv_out, V_out, V_tmp, status, true, s);
+cudaError_t launch_marginal_eig(const DevProblem& p, double* G, double* V, double* sv_out, double* V_out, double* V_tmp, int* status, const double* V_warm,
+                                double* V_keep, StreamCtx& s) {
+  return launch_sym_eig(p, G, V, sv_out, V_out, V_tmp, status, true, V_warm, V_keep, s);
 }
 cudaError_t launch_camera_diag(const DevProblem& p, double* out, StreamCtx& s) {
   camera_diag_kernel<<<1, 256, 0, s.stream>>>(p, out);
@@ -2698,11 +2740,12 @@ cudaError_t launch_camera_diag(const DevProblem& p, double* out, StreamCtx& s) {
   return cudaGetLastError();
 }
 cudaError_t launch_svd_solve(const DevProblem& p, const double* diag_h, double norm_tol, int column_scaling, double eps_svd, double svd_tol, double* g,
-                             double* G, double* V, double* sv, double* V_out, double* V_tmp, int* sweeps, double* result, StreamCtx& s) {
+                             double* G, double* V, double* sv, double* V_out, double* V_tmp, int* sweeps, double* result, const double* V_warm,
+                             double* V_keep, StreamCtx& s) {
   svd_scale_kernel<<<1, 256, 0, s.stream>>>(p, diag_h, norm_tol, column_scaling, g);
   KB_LAUNCHED(s);
   // the column-scaled system is well graded: absolute accuracy suffices (tolerance 1e-6 n sv_0); the unscaled one gets the polish
-  if (cudaError_t e = launch_sym_eig(p, G, V, sv, V_out, V_tmp, sweeps, column_scaling == 0, s); e != cudaSuccess) return e;
+  if (cudaError_t e = launch_sym_eig(p, G, V, sv, V_out, V_tmp, sweeps, column_scaling == 0, V_warm, V_keep, s); e != cudaSuccess) return e;
   svd_truncated_solve_kernel<<<1, 256, 0, s.stream>>>(p, sv, V_out, g, eps_svd, svd_tol, result);
   KB_LAUNCHED(s);
   return cudaGetLastError();
