@@ -1364,7 +1364,12 @@ static const double* eig_warm_start(kb_handle* h, int kind) {
     h->eig_warm_age[kind] = -1;
   }
   static const bool disabled = getenv("KB_EIG_NO_WARM") != nullptr;
-  const bool warm = !disabled && h->eig_warm_age[kind] >= 0 && h->eig_warm_age[kind] < 31;
+  // measured inside the estimator loop (profiles/r02_estimator_timing.md): from the previous vectors the Jacobi iteration needs 4-8
+  // sweeps (scaled system) / 10-13 (unscaled), which beats QL + polish while the columns live in shared memory (0.13 ms per sweep at
+  // n = 106) and loses once they spill to global memory (2.3 ms per sweep at n = 218): warm starts only for systems that fit
+  const size_t np = (n + 1) & ~(size_t)1;
+  const bool fits_smem = sizeof(double) * 2 * np * n <= 220 * 1024;
+  const bool warm = !disabled && fits_smem && h->eig_warm_age[kind] >= 0 && h->eig_warm_age[kind] < 31;
   h->eig_warm_age[kind] = warm ? h->eig_warm_age[kind] + 1 : 0;
   return warm ? h->eig_warm[kind].p : nullptr;
 }

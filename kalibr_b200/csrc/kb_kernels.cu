@@ -1980,9 +1980,11 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) jacobi_polish_kernel(DevProble
           if (k == 0) {
             a = np - 1;
             b = step;
-          } else {
-            a = (step + k) % (np - 1);
-            b = (step - k + (np - 1)) % (np - 1);
+          } else {  // (step + k) mod (np - 1), (step - k) mod (np - 1) without integer division: step, k < np - 1
+            a = step + k;
+            if (a >= np - 1) a -= np - 1;
+            b = step - k;
+            if (b < 0) b += np - 1;
           }
         }
         double* ga = G + (size_t)a * n;
