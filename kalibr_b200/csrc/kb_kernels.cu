@@ -1485,7 +1485,7 @@ __global__ void __launch_bounds__(256) schur_finalize_kernel(DevProblem p, const
 // reduced solve: one CTA.  Left-looking Cholesky of the augmented reduced system held packed (lower) in shared
 // memory; the augmented last row comes out as y = L^-1 b, then L^T x = y.
 // =========================================================================================================
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;  // 16 warps: one tile of the panel update per warp for n <= 128, and 16 loads in flight per thread while loading
 constexpr int RS_NB = 8;  // panel width = DMMA tile
 __device__ __forceinline__ int tri(int i, int k) { return i * (i + 1) / 2 + k; }
 
@@ -1531,6 +1531,7 @@ __device__ __forceinline__ bool diag_block(double* __restrict__ Lp, int j0, doub
 // Rows / columns past w are padded with the identity.  Returns false if a pivot is not positive (same in every lane).
 __device__ __forceinline__ bool diag_block_warp(double* __restrict__ Lp, int j0, int w, double* __restrict__ rd_all, int lane) {
   const int r = lane & 7;  // lanes 8..31 shadow lanes 0..7 (no divergence around the shuffles); only lanes 0..7 store
+  __syncwarp();            // converged from here on: a diverged warp would take the slow path of every shuffle below
   double a[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) a[c] = (r < w && c <= r) ? Lp[(j0 + r) * (j0 + r + 1) / 2 + j0 + c] : (c == r ? 1.0 : 0.0);
@@ -1593,7 +1594,18 @@ __device__ __forceinline__ void panel_rows(double* __restrict__ Lp, int j0, int 
 //   3. thread per row: L[row][panel] = A[row][panel] Ldd^-T by forward substitution.
 // Then L^T x = y panel by panel from the last: one thread solves the 8x8 triangle, all threads push the panel's x into the
 // rows above (two barriers per panel instead of one per unknown).
-__global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping_arg, int* __restrict__ pos_def_flag, int from_peers) {
+__global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping_arg, int* __restrict__ pos_def_flag, int from_peers,
+                                                                      long long* __restrict__ dbg /* KB_RS_TRACE: cycles per phase, or null */) {
+  __shared__ long long s_dbg[8];
+  if (dbg && threadIdx.x < 8) s_dbg[threadIdx.x] = 0;
+  long long t_mark = clock64();
+  auto lap = [&](int slot) {  // accumulated in shared memory: the trace must not add memory round trips to what it measures
+    if (dbg && threadIdx.x == 0) {
+      const long long t = clock64();
+      s_dbg[slot] += t - t_mark;
+      t_mark = t;
+    }
+  };
   extern __shared__ __align__(16) double Lp[];  // packed lower triangle, n_rows rows (zero padded), then rd[n_rows], x[n_rows]
   __shared__ int s_ok;
   const int n = p.n_aug, nc = p.n_c;
@@ -1614,20 +1626,45 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
     __syncthreads();
     slots = p.px.base[p.px.rank] + px_off_a(p.px, (int)(e & 1), 0);
   }
-  for (int idx = tid; idx < n * n; idx += RS_THREADS) {
-    const int i = idx / n, k = idx % n;
-    if (k > i) continue;
-    double v = 0.0;
-    if (from_peers) {
-      for (int r = 0; r < p.px.n_ranks; ++r) v += __ldcg(slots + (size_t)r * p.px.na2 + idx);
-    } else {
-      v = p.Sred[idx];
+  // lower triangle only, RS_LOAD_UNROLL independent loads in flight per thread (a dependent load per iteration exposed the full
+  // L2 latency ~190 times at n = 219: a third of the kernel)
+  {
+    constexpr int U = 8;
+    const int n_tri = n * (n + 1) / 2;
+    for (int base = tid; base < n_tri; base += RS_THREADS * U) {
+      int ii[U], kk[U];
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = base + u * RS_THREADS;
+        // row of packed index t: largest i with i (i + 1) / 2 <= t
+        int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while (i * (i + 1) / 2 > t) --i;
+        while ((i + 1) * (i + 2) / 2 <= t) ++i;
+        ii[u] = t < n_tri ? i : -1;
+        kk[u] = t - i * (i + 1) / 2;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v[u] = 0.0;
+        if (ii[u] < 0) continue;
+        const int idx = ii[u] * n + kk[u];
+        if (from_peers) {
+          for (int r = 0; r < p.px.n_ranks; ++r) v[u] += __ldcg(slots + (size_t)r * p.px.na2 + idx);
+        } else {
+          v[u] = p.Sred[idx];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (ii[u] < 0) continue;
+        Lp[base + u * RS_THREADS] = (ii[u] == kk[u] && ii[u] < nc) ? v[u] + damping : v[u];
+      }
     }
-    if (i == k && i < nc) v += damping;
-    Lp[tri(i, k)] = v;
   }
   if (tid == 0) s_ok = 1;
   __syncthreads();
+  lap(0);
   const int arow = lane >> 2, acol = lane & 3;
   for (int j0 = 0; j0 < nc; j0 += RS_NB) {
     const int w = min(RS_NB, nc - j0);
@@ -1659,12 +1696,14 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
       }
       __syncthreads();
     }
+    lap(1);
     // ---- 2. diagonal block (one warp, a row per lane) ----
     if (warp == 0) {
       const bool ok = diag_block_warp(Lp, j0, w, s_rd, lane);
       if (!ok && lane == 0) s_ok = 0;
     }
     __syncthreads();
+    lap(2);
     // ---- 3. rows below the block ----
     switch (w) {
       case 8: panel_rows<8>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
@@ -1677,6 +1716,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
       default: panel_rows<1>(Lp, j0, n, s_rd, tid, RS_THREADS); break;
     }
     __syncthreads();
+    lap(3);
   }
   if (tid == 0 && !s_ok) *pos_def_flag = 0;
   // ---- back substitution L^T x = y, y = row nc of the factor; panels from the last to the first ----
@@ -1685,12 +1725,21 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
   const int last = ((nc - 1) / RS_NB) * RS_NB;
   for (int j0 = last; j0 >= 0; j0 -= RS_NB) {
     const int w = min(RS_NB, nc - j0);
-    if (tid == 0) {  // the w x w triangle of the panel
-      for (int c = w - 1; c >= 0; --c) {
-        double v = s_x[j0 + c];
-        for (int k = c + 1; k < w; ++k) v -= Lp[tri(j0 + k, j0 + c)] * s_x[j0 + k];
-        s_x[j0 + c] = v * s_rd[j0 + c];
+    if (warp == 0) {  // the w x w triangle of the panel: lane c owns x_c and column c of the block; per step one product, one shuffle, one FMA
+      __syncwarp();
+      const int c = lane & 7;
+      double y = c < w ? s_x[j0 + c] : 0.0;
+      const double rdc = c < w ? s_rd[j0 + c] : 0.0;
+      double col[8];  // L[j0 + k][j0 + c] for k > c
+#pragma unroll
+      for (int k = 0; k < 8; ++k) col[k] = (k > c && k < w) ? Lp[tri(j0 + k, j0 + c)] : 0.0;
+#pragma unroll
+      for (int k = 7; k >= 0; --k) {
+        const double xk = __shfl_sync(0xffffffffu, y * rdc, k);  // x_k, final once every later unknown has been pushed into y_k
+        if (c == k) y = xk;
+        else if (c < k) y = fma(-col[k], xk, y);
       }
+      if (lane < w) s_x[j0 + lane] = y;
     }
     __syncthreads();
     for (int k = tid; k < j0; k += RS_THREADS) {  // y[k] -= sum_c L[j0 + c][k] x[j0 + c]
@@ -1701,6 +1750,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
     __syncthreads();
   }
   for (int i = tid; i < nc; i += RS_THREADS) p.dxc[i] = s_x[i];
+  lap(4);
+  if (dbg && tid == 0)
+    for (int i = 0; i < 5; ++i) dbg[i] = s_dbg[i];
 }
 
 // =========================================================================================================
@@ -2635,8 +2687,20 @@ cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_d
   const size_t smem = sizeof(double) * (n_rows * (n_rows + 1) / 2 + 2 * n_rows);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
   if (cudaError_t e = ensure_dynamic_smem(reduced_solve_kernel, smem, attr_smem_dev); e != cudaSuccess) return e;
-  reduced_solve_kernel<<<1, RS_THREADS, smem, s.stream>>>(p, damping, pos_def_flag, from_peers && p.px.enabled ? 1 : 0);
+  static long long* dbg = nullptr;
+  static const bool trace = getenv("KB_RS_TRACE") != nullptr;
+  if (trace && !dbg) {
+    cudaMallocManaged(&dbg, 8 * sizeof(long long));
+    cudaMemset(dbg, 0, 8 * sizeof(long long));
+  }
+  reduced_solve_kernel<<<1, RS_THREADS, smem, s.stream>>>(p, damping, pos_def_flag, from_peers && p.px.enabled ? 1 : 0, trace ? dbg : nullptr);
   KB_LAUNCHED(s);
+  if (trace) {  // experiments only: cycles per phase of this launch (load, panel update, diagonal block, panel rows, back substitution)
+    cudaStreamSynchronize(s.stream);
+    std::fprintf(stderr, "[kb trace] reduced_solve n = %d: load %lld, update %lld, diag %lld, rows %lld, backsub %lld cycles\n", p.n_aug, dbg[0], dbg[1], dbg[2],
+                 dbg[3], dbg[4]);
+    cudaMemset(dbg, 0, 8 * sizeof(long long));
+  }
   return cudaGetLastError();
 }
 
