@@ -22,12 +22,12 @@ N_D = [4, 4, 4, 0, 0, 1, 0]
 
 
 def rot_from_quat(q):
-    """rotation matrix of a unit quaternion (x, y, z, w) in the convention sm_kinematics stores poses in (Hamilton matrix of the JPL
-    quaternion: C = (w^2 - v.v) I + 2 v v^T + 2 w [v]x)"""
+    """rotation matrix of a unit quaternion (x, y, z, w) in the convention sm_kinematics stores poses in (JPL):
+    C = (w^2 - v.v) I + 2 v v^T - 2 w [v]x"""
     x, y, z, w = q
     v = np.array([x, y, z])
     vx = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]])
-    return (w * w - v @ v) * np.eye(3) + 2.0 * np.outer(v, v) + 2.0 * w * vx
+    return (w * w - v @ v) * np.eye(3) + 2.0 * np.outer(v, v) - 2.0 * w * vx
 
 
 def small_rotation_update(q, d):
@@ -39,7 +39,7 @@ def small_rotation_update(q, d):
         dq = np.concatenate([np.sin(0.5 * th) * d / th, [np.cos(0.5 * th)]])
     # quaternion product dq (+) q in the same convention: plus-matrix of dq applied to q
     x, y, z, w = dq
-    M = np.array([[w, -z, y, x], [z, w, -x, y], [-y, x, w, z], [-x, -y, -z, w]])
+    M = np.array([[w, z, -y, x], [-z, w, x, y], [y, -x, w, z], [-x, -y, -z, w]])
     out = M @ q
     return out / np.linalg.norm(out)
 
