@@ -163,6 +163,18 @@ KB_API kb_status kb_apply_state_update(kb_handle* h, double* out_max_abs_dx);
 /* ≙ Optimizer2::revertLastStateUpdate (BE/src/Optimizer2.cpp:313-318) */
 KB_API kb_status kb_revert_last_state_update(kb_handle* h);
 
+/* One iteration's worth of the calls above in one go - ≙ evaluateError, buildSystem, setConstantConditioner(lambda), solveSystem,
+ * applyStateUpdate and, if `revert`, revertLastStateUpdate (the sequence of BE/src/Optimizer2.cpp:237-249 with
+ * LevenbergMarquardtTrustRegionPolicy.cpp:72-88) - enqueued back to back with a single host synchronisation at the end, for host
+ * optimisers that only need the scalars of the iteration.  Same kernels, same results as the six separate calls. */
+typedef struct {
+  double cost;            /* J of the state the iteration started from */
+  double rho_denominator; /* dx^T (lambda dx + rhs) of its solution */
+  double max_abs_dx;
+  int32_t pos_def;
+} kb_iteration_result;
+KB_API kb_status kb_iterate(kb_handle* h, double lambda, int32_t use_m_estimator, int32_t revert, kb_iteration_result* out);
+
 /* One whole Optimizer2::optimize() (BE/src/Optimizer2.cpp:183-273) with LevenbergMarquardtTrustRegionPolicy
  * (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:50-113) driven by the host C++ mirror; state stays on the device. */
 typedef struct {

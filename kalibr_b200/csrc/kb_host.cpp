@@ -181,6 +181,7 @@ struct kb_handle {
   int semantic = 0;
   bool built = false, solved = false, has_backup = false, presharded = false;
   bool speculative = true;       // kb_evaluate_error linearises too, so that a build at the same state is free
+  bool defer_sync = false;       // inside kb_iterate: the entry points enqueue only, one synchronisation at the end
   long long state_version = 0;   // bumped whenever design variables or observations change
   long long la_version = -1;     // state the view blocks / Gram sums were computed at
   int la_rows = 0;               // DevProblem::mest_rows they were computed with
@@ -825,6 +826,7 @@ static kb_status run_linearise_assemble(kb_handle* h, bool write_e, int cost_slo
 
 static kb_status finish_evaluate(kb_handle* h, double* out_cost) {
   KB_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (h->defer_sync) return KB_OK;
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   collect_stages(h);
   if (out_cost) *out_cost = h->h_scalars[0];
@@ -1483,6 +1485,7 @@ kb_status kb_set_constant_conditioner(kb_handle* h, double lambda) {
 
 // Everything after the camera-side solution sits in dxc: back-substitution of the set poses, dx^T (lambda dx + rhs) and max|dx|
 // (combined over the ranks), the optional copy of dx to the host.  The pose factors Lv must belong to the same damping.
+static kb_status solve_post_sync(kb_handle* h);
 static kb_status solve_finish(kb_handle* h, double* dx, int32_t gather_dx) {
   StreamCtx c = ctx(h);
   {
@@ -1530,7 +1533,12 @@ static kb_status solve_finish(kb_handle* h, double* dx, int32_t gather_dx) {
       KB_CUDA(h, cudaMemcpyAsync(dx, h->dx.p, sizeof(double) * h->jcols, cudaMemcpyDeviceToHost, h->stream));
     }
   }
+  if (h->defer_sync) return KB_OK;
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return solve_post_sync(h);
+}
+
+static kb_status solve_post_sync(kb_handle* h) {
   collect_stages(h);
   if (h->n_ranks > 1 && !h->px_on) {  // combine the ranks' slots in rank order: identical on every rank
     double rho = 0.0, mx = 0.0;
@@ -1582,6 +1590,32 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
   h->solved = true;
   h->rho_lambda = h->lambda;
   if (pos_def) *pos_def = h->h_posdef[0];
+  return KB_OK;
+}
+
+// One iteration's worth of the call-by-call sequence - evaluateError, buildSystem, setConstantConditioner, solveSystem,
+// applyStateUpdate [, revertLastStateUpdate] - enqueued back to back with ONE host synchronisation at the end.
+kb_status kb_iterate(kb_handle* h, double lambda, int32_t use_m_estimator, int32_t revert, kb_iteration_result* out) {
+  h->defer_sync = true;
+  kb_status st = kb_evaluate_error(h, use_m_estimator, nullptr);
+  if (st == KB_OK) st = kb_build_system(h, use_m_estimator);
+  if (st == KB_OK) st = kb_set_constant_conditioner(h, lambda);
+  if (st == KB_OK) st = kb_solve_system(h, nullptr, 0, nullptr);
+  if (st == KB_OK) st = kb_apply_state_update(h, nullptr);
+  if (st == KB_OK && revert) st = kb_revert_last_state_update(h);
+  h->defer_sync = false;
+  if (st != KB_OK) {
+    cudaStreamSynchronize(h->stream);
+    return st;
+  }
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if ((st = solve_post_sync(h)) != KB_OK) return st;
+  if (out) {
+    out->cost = h->h_scalars[0];
+    out->rho_denominator = h->h_scalars[2];
+    out->max_abs_dx = h->h_scalars[3];
+    out->pos_def = h->h_posdef[0];
+  }
   return KB_OK;
 }
 

@@ -427,3 +427,22 @@ def test_single_precision_observations_are_widened_exactly(capi):
     assert g.evaluate_error() == J1 and np.array_equal(g.error_vector(), e1)
     with pytest.raises(capi.KalibrB200Error):
         g.set_observations(au32, av64)
+
+
+def test_iterate_equals_the_six_separate_calls(capi):
+    """kb_iterate = evaluateError, buildSystem, setConstantConditioner, solveSystem, applyStateUpdate [, revert] with one synchronisation:
+    the same scalars and the same state as the separate calls."""
+    p = make(3, 14)
+    a, b = capi.B200SchurLinearSystemSolver(p), capi.B200SchurLinearSystemSolver(p)
+    for lam, revert in [(10.0, False), (3.0, True), (1.0, False)]:
+        J = a.evaluate_error()
+        a.build_system()
+        a.set_constant_conditioner(lam)
+        _, ok = a.solve_system(fetch_dx=False)
+        rho = a.lm_rho_denominator(lam)
+        m = a.apply_state_update()
+        if revert:
+            a.revert_last_state_update()
+        cost, rho2, m2, ok2 = b.iterate(lam, revert=revert)
+        assert (cost, rho2, m2, ok2) == (J, rho, m, ok)
+        assert np.array_equal(a.camera_params(), b.camera_params()) and np.array_equal(a.set_poses(), b.set_poses())
