@@ -565,10 +565,14 @@ __device__ __forceinline__ void zero_rows(double* __restrict__ xt_lane) {
 #ifndef KB_LA_WARPS
 #define KB_LA_WARPS 8
 #endif
+#ifndef KB_LA_VARIANT
+#define KB_LA_VARIANT 0  // ablation builds only (tools/build_variants.sh): 1 = no DMMA, 2 = no projection math
+#endif
 constexpr int LA_WARPS = KB_LA_WARPS;
 constexpr int LA_THREADS = LA_WARPS * 32;
 constexpr int LA_SP_DOUBLES = 16;  // per view: C^-1 (9), -C^-1 t (3) of the set, padded
-constexpr int LA_WARP_DOUBLES = XT_WARP_DOUBLES + GRAM_TILES + 2 * LA_SP_DOUBLES;  // XT | slice Gram sum | set constants x2
+// per warp: XT | slice Gram sum | set constants x2 | [R_cw | t_cw] of the view (12) + the camera's parameters (10, padded to 12)
+constexpr int LA_WARP_DOUBLES = XT_WARP_DOUBLES + GRAM_TILES + 2 * LA_SP_DOUBLES + 24;
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -577,31 +581,55 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// one k-step pair (4 u-rows, 4 v-rows) of the Gram reduction: six DMMAs on three accumulator chains
+__device__ __forceinline__ void gram_kstep(double (&c00)[2], double (&c01)[2], double (&c11)[2], double x0, double x1, double z0, double z1) {
+  dmma(c00[0], c00[1], x0, x0);
+  dmma(c01[0], c01[1], x0, x1);
+  dmma(c11[0], c11[1], x1, x1);
+  dmma(c00[0], c00[1], z0, z0);
+  dmma(c01[0], c01[1], z0, z1);
+  dmma(c11[0], c11[1], z1, z1);
+}
+
 template <int MODEL, bool WRITE_E, bool WEIGHTED>
 __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevProblem p, const int4* __restrict__ vmeta,
                                                                             const int4* __restrict__ slices, int slice_lo, int slice_hi) {
   extern __shared__ __align__(16) double smem[];
-  double* s_target = smem;                                  // n_target*3 (rounded up to even)
-  const int target_doubles = (p.n_target * 3 + 1) & ~1;
+  // target corners, one array per coordinate (a warp's 32 consecutive corners then cost 2 wavefronts per coordinate, not 6)
+  const int tpad = (p.n_target + 1) & ~1;
+  double* s_tx = smem;
+  double* s_ty = s_tx + tpad;
+  double* s_tz = s_ty + tpad;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  double* XT = smem + target_doubles + wib * LA_WARP_DOUBLES;  // [16 cols][68]
+  double* XT = smem + 3 * tpad + wib * LA_WARP_DOUBLES;       // [16 cols][68]
   double* sG = XT + XT_WARP_DOUBLES;                           // [3][64] slice sum of the three tiles
   double* sSP = sG + GRAM_TILES;                               // [2][16] per-set constants of the current / next view (cp.async)
+  double* sC = sSP + 2 * LA_SP_DOUBLES;                        // [R_cw | t_cw] of the current view
+  double* prm = sC + 12;                                       // parameters of the slice's camera
   if (p.ctrl->done || p.ctrl->skip_eval) return;
-  for (int i = threadIdx.x; i < p.n_target * 3; i += blockDim.x) s_target[i] = p.target[i];
+  for (int i = threadIdx.x; i < p.n_target; i += blockDim.x) {
+    s_tx[i] = p.target[3 * i];
+    s_ty[i] = p.target[3 * i + 1];
+    s_tz[i] = p.target[3 * i + 2];
+  }
   __syncthreads();
 
   const int warp = blockIdx.x * LA_WARPS + wib;
   const int n_warps = gridDim.x * LA_WARPS;
   const int arow = lane >> 2, acol = lane & 3;
+  // element of [R_cw | t_cw] this lane computes per view (lanes 0..11): row tr of camT times column tj of the set's C^-1 / -C^-1 t
+  const int tl = lane < 12 ? lane : 0;
+  const int tr = tl < 9 ? tl / 3 : tl - 9;
+  const int sp_base = tl < 9 ? tl % 3 : 9, sp_stride = tl < 9 ? 3 : 1;
   for (int sl = slice_lo + warp; sl < slice_hi; sl += n_warps) {
     const int4 S = slices[sl];
     const int cam = S.z;
-    double prm[CAM_PARAM_STRIDE];
-#pragma unroll
-    for (int i = 0; i < CAM_PARAM_STRIDE; ++i) prm[i] = p.cam_params[cam * CAM_PARAM_STRIDE + i];
+    __syncwarp();
+    if (lane < CAM_PARAM_STRIDE) prm[lane] = p.cam_params[cam * CAM_PARAM_STRIDE + lane];
     for (int o = lane; o < GRAM_TILES; o += 32) sG[o] = 0.0;
+    const double ct0 = __ldg(p.camT + cam * 12 + tr * 3), ct1 = __ldg(p.camT + cam * 12 + tr * 3 + 1), ct2 = __ldg(p.camT + cam * 12 + tr * 3 + 2);
+    const double ct3 = tl < 9 ? 0.0 : __ldg(p.camT + cam * 12 + 9 + tr);
     // pipeline: metadata two views ahead (registers), per-set constants one view ahead (cp.async into shared memory),
     // observations one chunk ahead (registers), across view boundaries too
     int4 m_cur = vmeta[S.x];                                   // (view, set, begin, end)
@@ -625,16 +653,15 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
       have_pf = false;
       const int4 m_nn = (vi + 2 < S.y) ? vmeta[vi + 2] : m_nxt;
       cp_async_wait_all();
+      __syncwarp();  // the set constants have landed; every lane is done with the previous view's transform
+      {
+        const double* sp = sSP + buf * LA_SP_DOUBLES + sp_base;
+        const double v = ct0 * sp[0] + ct1 * sp[sp_stride] + ct2 * sp[2 * sp_stride] + ct3;
+        if (lane < 12) sC[lane] = v;
+      }
       __syncwarp();
       if (vi + 1 < S.y && lane < 6) cp_async_16(sSP + (buf ^ 1) * LA_SP_DOUBLES + 2 * lane, p.set_prep + (size_t)m_nxt.y * SETPREP_STRIDE + 2 * lane);
       cp_async_commit();
-      double Rcw[9], tcw[3];
-      {
-        double camT[12];  // per view from L1: not worth 24 registers across the slice
-#pragma unroll
-        for (int q = 0; q < 12; ++q) camT[q] = __ldg(p.camT + cam * 12 + q);
-        view_transform_prepped(sSP + buf * LA_SP_DOUBLES, camT, Rcw, tcw);
-      }
       double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};  // three independent DMMA chains saturate the pipe
       for (int base = b; base < e; base += 32) {
         const double cyu = yu, cyv = yv;
@@ -654,11 +681,17 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
           have_pf = true;
         }
         const int n = min(32, e - base);
-        const int kq = (n + 3) >> 2;  // DMMA k-steps per row half: a partial last chunk only spends DMMAs on rows that exist
         double e0, e1;
-        const bool valid = term_rows<MODEL, WEIGHTED>(p, prm, Rcw, tcw, s_target + 3 * ccid, cyu, cyv, XT + lane, e0, e1);
+#if KB_LA_VARIANT == 2
+        const bool valid = true;
+        e0 = cyu + s_tx[ccid]; e1 = cyv;
+#else
+        const double pt[3] = {s_tx[ccid], s_ty[ccid], s_tz[ccid]};
+        const bool valid = term_rows<MODEL, WEIGHTED>(p, prm, sC, sC + 9, pt, cyu, cyv, XT + lane, e0, e1);
+#endif
         if (cactive && !valid) atomicAdd(p.n_invalid, 1u);
         const bool keep = cactive && valid;
+        const int kq = (n + 3) >> 2;  // DMMA k-steps per row half: a partial last chunk only spends DMMAs on rows that exist
         if (__any_sync(0xffffffffu, !keep && lane < 4 * kq)) {
           if (!keep) {
             zero_rows(XT + lane);
@@ -666,24 +699,18 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
             e1 = 0.0;
           }
         }
-        if (WRITE_E && cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(-e0, -e1);
+        if (WRITE_E && cactive) reinterpret_cast<double2*>(p.e)[ci] = make_double2(neg_int(e0), neg_int(e1));
         __syncwarp();
-        // operands of k-step s + 1 are loaded before the DMMAs of k-step s are issued
         const double* xa = XT + arow * XT_LD + acol;
-        double x0 = xa[0], x1 = xa[8 * XT_LD], z0 = xa[32], z1 = xa[8 * XT_LD + 32];
+#if KB_LA_VARIANT != 1
+        if (n == 32) {  // full chunk: eight k-steps, straight-line
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          if (s >= kq) break;
-          const int sn = s < 7 ? s + 1 : 7;  // rows beyond the chunk are stale but never used
-          const double nx0 = xa[4 * sn], nx1 = xa[8 * XT_LD + 4 * sn], nz0 = xa[32 + 4 * sn], nz1 = xa[8 * XT_LD + 32 + 4 * sn];
-          dmma(c00[0], c00[1], x0, x0);
-          dmma(c01[0], c01[1], x0, x1);
-          dmma(c11[0], c11[1], x1, x1);
-          dmma(c00[0], c00[1], z0, z0);
-          dmma(c01[0], c01[1], z0, z1);
-          dmma(c11[0], c11[1], z1, z1);
-          x0 = nx0; x1 = nx1; z0 = nz0; z1 = nz1;
+          for (int s = 0; s < 8; ++s) gram_kstep(c00, c01, c11, xa[4 * s], xa[8 * XT_LD + 4 * s], xa[32 + 4 * s], xa[8 * XT_LD + 32 + 4 * s]);
+        } else {
+#pragma unroll 1
+          for (int s = 0; s < kq; ++s) gram_kstep(c00, c01, c11, xa[4 * s], xa[8 * XT_LD + 4 * s], xa[32 + 4 * s], xa[8 * XT_LD + 32 + 4 * s]);
         }
+#endif
         __syncwarp();
       }
       // ---- per view: tiles (0,0) and (0,1) row-major (the C fragment order is row-major 8x8), slice sum of all three ----
@@ -2549,8 +2576,8 @@ int la_grid_warps() { return sm_count() * 2 * LA_WARPS; }
 template <int MODEL, bool WRITE_E, bool WEIGHTED>
 static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const int4* slices, int lo, int hi, StreamCtx& s) {
   if (hi <= lo) return cudaSuccess;
-  const size_t smem = sizeof(double) * (((p.n_target * 3 + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
+  const size_t smem = sizeof(double) * (3 * ((p.n_target + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
   if (cudaError_t e = ensure_dynamic_smem(linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED>, smem, attr_smem_dev); e != cudaSuccess) return e;
   const int grid = min((hi - lo + LA_WARPS - 1) / LA_WARPS, sm_count() * 2);
   linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);

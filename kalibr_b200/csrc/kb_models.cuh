@@ -30,24 +30,37 @@ struct Linearisation {
 
 // ---- distortions ---------------------------------------------------------------------------------------
 // radtan: in/out m (normalised point), Jm = d(distorted)/d(m) (symmetric 2x2), Jk = d(distorted)/d(k1,k2,p1,p2) at m
+// sign flip on the integer pipe: the FP64 units are the bottleneck of every kernel that calls this
+__device__ __forceinline__ double neg_int(double v) { return __hiloint2double(__double2hiint(v) ^ (int)0x80000000, __double2loint(v)); }
+
 template <bool WITH_JAC>
 __device__ __forceinline__ void radtan(const double* __restrict__ k, double& mx, double& my, double Jm[2][2], double Jk[2][4]) {
+  // CAM/RadialTangentialDistortion.hpp:24-101 with the common subexpressions shared: 1 + rad = 1 + r^2 (k1 + k2 r^2),
+  // d(rad)/d(r^2) = k1 + 2 k2 r^2; the reference's sums re-associated (differences at the 1e-16 level)
   const double k1 = k[0], k2 = k[1], p1 = k[2], p2 = k[3];
+  const double tp1 = p1 + p1, tp2 = p2 + p2;
   const double x = mx, y = my;
   const double x2 = x * x, y2 = y * y, xy = x * y;
   const double rho2 = x2 + y2;
-  const double rad = k1 * rho2 + k2 * rho2 * rho2;
+  const double k2r2 = k2 * rho2;
+  const double t = k1 + k2r2;
+  const double a = fma(t, rho2, 1.0);          // 1 + rad
+  const double s3x = fma(2.0, x2, rho2);       // r^2 + 2 x^2
+  const double s3y = fma(2.0, y2, rho2);
   if (WITH_JAC) {
-    Jm[0][0] = 1.0 + rad + k1 * 2.0 * x2 + k2 * rho2 * 4.0 * x2 + 2.0 * p1 * y + 6.0 * p2 * x;
-    Jm[1][0] = k1 * 2.0 * xy + k2 * 4.0 * rho2 * xy + p1 * 2.0 * x + 2.0 * p2 * y;
+    const double dq = t + k2r2;
+    const double q = dq + dq;                  // 2 d(rad)/d(r^2)
+    Jm[0][0] = fma(3.0 * tp2, x, fma(tp1, y, fma(q, x2, a)));
+    Jm[1][0] = fma(q, xy, fma(tp1, x, tp2 * y));
     Jm[0][1] = Jm[1][0];
-    Jm[1][1] = 1.0 + rad + k1 * 2.0 * y2 + k2 * rho2 * 4.0 * y2 + 6.0 * p1 * y + 2.0 * p2 * x;
+    Jm[1][1] = fma(tp2, x, fma(3.0 * tp1, y, fma(q, y2, a)));
     const double r4 = rho2 * rho2;
-    Jk[0][0] = x * rho2; Jk[0][1] = x * r4; Jk[0][2] = 2.0 * xy;         Jk[0][3] = rho2 + 2.0 * x2;
-    Jk[1][0] = y * rho2; Jk[1][1] = y * r4; Jk[1][2] = rho2 + 2.0 * y2;  Jk[1][3] = 2.0 * xy;
+    const double txy = xy + xy;
+    Jk[0][0] = x * rho2; Jk[0][1] = x * r4; Jk[0][2] = txy; Jk[0][3] = s3x;
+    Jk[1][0] = y * rho2; Jk[1][1] = y * r4; Jk[1][2] = s3y; Jk[1][3] = txy;
   }
-  mx = x + (x * rad + 2.0 * p1 * xy + p2 * (rho2 + 2.0 * x2));
-  my = y + (y * rad + 2.0 * p2 * xy + p1 * (rho2 + 2.0 * y2));
+  mx = fma(x, a, fma(tp1, xy, p2 * s3x));
+  my = fma(y, a, fma(tp2, xy, p1 * s3y));
 }
 
 // equidistant (Kannala-Brandt).  The point Jacobian has no guard at r = 0 (NaN there, as in the reference: Q5).
@@ -151,15 +164,16 @@ struct PinholeCamera {
     if (WITH_JAC) {
       const double ju = NEG ? -fu : fu, jv = NEG ? -fv : fv;
       const double one = NEG ? -1.0 : 1.0;
-      const double rz2 = rz * rz;
-      L.Jp[0][0] = ju * Jm[0][0] * rz;
-      L.Jp[0][1] = ju * Jm[0][1] * rz;
-      L.Jp[0][2] = -ju * (p[0] * Jm[0][0] + p[1] * Jm[0][1]) * rz2;
-      L.Jp[1][0] = jv * Jm[1][0] * rz;
-      L.Jp[1][1] = jv * Jm[1][1] * rz;
-      L.Jp[1][2] = -jv * (p[0] * Jm[1][0] + p[1] * Jm[1][1]) * rz2;
-      L.Ji[0][0] = NEG ? -mx : mx; L.Ji[0][1] = 0.0; L.Ji[0][2] = one; L.Ji[0][3] = 0.0;
-      L.Ji[1][0] = 0.0; L.Ji[1][1] = NEG ? -my : my; L.Ji[1][2] = 0.0; L.Ji[1][3] = one;
+      const double jur = ju * rz, jvr = jv * rz;
+      const double ux = p[0] * rz, uy = p[1] * rz;  // the undistorted normalised point
+      L.Jp[0][0] = jur * Jm[0][0];
+      L.Jp[0][1] = jur * Jm[0][1];
+      L.Jp[0][2] = fma(-uy, L.Jp[0][1], -ux * L.Jp[0][0]);  // -ju (x Jm00 + y Jm01) / z^2
+      L.Jp[1][0] = jvr * Jm[1][0];
+      L.Jp[1][1] = jvr * Jm[1][1];
+      L.Jp[1][2] = fma(-uy, L.Jp[1][1], -ux * L.Jp[1][0]);
+      L.Ji[0][0] = NEG ? neg_int(mx) : mx; L.Ji[0][1] = 0.0; L.Ji[0][2] = one; L.Ji[0][3] = 0.0;
+      L.Ji[1][0] = 0.0; L.Ji[1][1] = NEG ? neg_int(my) : my; L.Ji[1][2] = 0.0; L.Ji[1][3] = one;
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         L.Jd[0][j] = ju * Jk[0][j];
@@ -213,8 +227,8 @@ struct OmniCamera {
       }
       L.Ji[0][0] = ju * Jm[0][0] * jxi0 + ju * Jm[0][1] * jxi1;
       L.Ji[1][0] = jv * Jm[1][0] * jxi0 + jv * Jm[1][1] * jxi1;
-      L.Ji[0][1] = NEG ? -mx : mx; L.Ji[0][2] = 0.0; L.Ji[0][3] = one; L.Ji[0][4] = 0.0;
-      L.Ji[1][1] = 0.0; L.Ji[1][2] = NEG ? -my : my; L.Ji[1][3] = 0.0; L.Ji[1][4] = one;
+      L.Ji[0][1] = NEG ? neg_int(mx) : mx; L.Ji[0][2] = 0.0; L.Ji[0][3] = one; L.Ji[0][4] = 0.0;
+      L.Ji[1][1] = 0.0; L.Ji[1][2] = NEG ? neg_int(my) : my; L.Ji[1][3] = 0.0; L.Ji[1][4] = one;
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         L.Jd[0][j] = ju * Jk[0][j];
