@@ -166,7 +166,9 @@ KB_API kb_status kb_revert_last_state_update(kb_handle* h);
 /* One iteration's worth of the calls above in one go - ≙ evaluateError, buildSystem, setConstantConditioner(lambda), solveSystem,
  * applyStateUpdate and, if `revert`, revertLastStateUpdate (the sequence of BE/src/Optimizer2.cpp:237-249 with
  * LevenbergMarquardtTrustRegionPolicy.cpp:72-88) - enqueued back to back with a single host synchronisation at the end, for host
- * optimisers that only need the scalars of the iteration.  Same kernels, same results as the six separate calls. */
+ * optimisers that only need the scalars of the iteration.  Same kernels, same results as the six separate calls.
+ * out == NULL: the iteration is only ENQUEUED (no synchronisation; several iterations can be in flight); kb_wait() then waits for
+ * everything enqueued on the handle and returns the scalars of the LAST iteration. */
 typedef struct {
   double cost;            /* J of the state the iteration started from */
   double rho_denominator; /* dx^T (lambda dx + rhs) of its solution */
@@ -174,6 +176,7 @@ typedef struct {
   int32_t pos_def;
 } kb_iteration_result;
 KB_API kb_status kb_iterate(kb_handle* h, double lambda, int32_t use_m_estimator, int32_t revert, kb_iteration_result* out);
+KB_API kb_status kb_wait(kb_handle* h, kb_iteration_result* out);
 
 /* One whole Optimizer2::optimize() (BE/src/Optimizer2.cpp:183-273) with LevenbergMarquardtTrustRegionPolicy
  * (BE/src/LevenbergMarquardtTrustRegionPolicy.cpp:50-113) driven by the host C++ mirror; state stays on the device. */
@@ -430,6 +433,9 @@ KB_API int64_t kb_kernel_launches(const kb_handle* h);
 KB_API kb_status kb_get_stage_ms(kb_handle* h, double* ms /*[KB_NUM_STAGES]*/);
 /* accumulated since the last kb_enable_stage_timing(h, 1): total ms and number of timed calls per stage */
 KB_API kb_status kb_get_stage_totals(kb_handle* h, double* total_ms /*[KB_NUM_STAGES]*/, int64_t* calls /*[KB_NUM_STAGES]*/);
+/* on = 0: off; 1: every stage; > 1: only the stages s whose bit (s + 1) is set (an event pair per timed stage sits between the
+ * kernels of an iteration, so timing fewer stages perturbs the iteration less).  Up to 64 measurements per stage may wait for the
+ * next synchronisation (kb_iterate without a result pointer). */
 KB_API kb_status kb_enable_stage_timing(kb_handle* h, int32_t on);
 KB_API void* kb_cuda_stream(kb_handle* h); /* cudaStream_t the library launches on */
 

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "kb_get_set_poses", "kb_set_observations", "kb_evaluate_error_streamed", "kb_prefetch_observations", "kb_commit_observations", "kb_peer_exchange_handle", "kb_attach_peers", "kb_default_marginal_options", "kb_analyze_marginal", "kb_num_invalid_terms", "kb_reset_state", "kb_kernel_launches", "kb_get_stage_ms",
     "kb_enable_stage_timing", "kb_get_stage_totals", "kb_cuda_stream",
     "kb_set_inv_r", "kb_get_sqrt_inv_r", "kb_set_m_estimator", "kb_m_estimator_parameter", "kb_reprojection_statistics",
-    "kb_iterate", "kb_set_observations_f32", "kb_evaluate_error_streamed_f32", "kb_prefetch_observations_f32",
+    "kb_iterate", "kb_wait", "kb_set_observations_f32", "kb_evaluate_error_streamed_f32", "kb_prefetch_observations_f32",
     "kb_append_set", "kb_remove_last_set", "kb_save_design_variables", "kb_restore_design_variables",
     "kb_set_state", "kb_set_camera_params", "kb_set_baselines", "kb_set_set_poses", "kb_set_conditioner",
     "kb_estimate_transformations", "kb_initialize_set_poses", "kb_estimate_stereo_baseline", "kb_initialize_intrinsics", "kb_default_svd_solver_options", "kb_solve_system_svd", "kb_optimize_gauss_newton", "kb_analyze_marginal_last_build", "kb_get_last_svd_solve", "kb_get_last_svd_decomposition",
@@ -92,6 +92,7 @@ def load_library() -> C.CDLL:
     L.kb_get_baselines.argtypes = [vp, vp]
     L.kb_get_set_poses.argtypes = [vp, vp]
     L.kb_iterate.argtypes = [vp, C.c_double, C.c_int32, C.c_int32, vp]
+    L.kb_wait.argtypes = [vp, vp]
     L.kb_append_set.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.kb_remove_last_set.argtypes = [vp]
     L.kb_save_design_variables.argtypes = [vp]
@@ -154,6 +155,10 @@ def nccl_unique_id() -> bytes:
     if st != KB_OK:
         raise KalibrB200Error("kb_nccl_unique_id: " + load_library().kb_last_error(None).decode())
     return buf.raw
+
+
+class _IterationResult(C.Structure):
+    _fields_ = [("cost", C.c_double), ("rho_denominator", C.c_double), ("max_abs_dx", C.c_double), ("pos_def", C.c_int32)]
 
 
 class B200SchurLinearSystemSolver:
@@ -235,15 +240,19 @@ class B200SchurLinearSystemSolver:
         self._check(self._L.kb_solve_system_svd(self._h, C.byref(o), _p(dx), 1 if gather else 0, C.byref(res), _p(sv)), "kb_solve_system_svd")
         return dx, res, sv
 
-    def iterate(self, lam: float, use_m_estimator: bool = True, revert: bool = False):
-        """evaluate + build + solve(lam) + apply [+ revert] with one host synchronisation: (cost, rho denominator, max|dx|, pos_def)."""
-        r = (C.c_double * 3)()
-
-        class _R(C.Structure):
-            _fields_ = [("cost", C.c_double), ("rho_denominator", C.c_double), ("max_abs_dx", C.c_double), ("pos_def", C.c_int32)]
-
-        out = _R()
+    def iterate(self, lam: float, use_m_estimator: bool = True, revert: bool = False, wait: bool = True):
+        """evaluate + build + solve(lam) + apply [+ revert] with one host synchronisation: (cost, rho denominator, max|dx|, pos_def).
+        wait=False only enqueues the iteration (several can be in flight); wait_iterations() then returns the last one's scalars."""
+        if not wait:
+            self._check(self._L.kb_iterate(self._h, lam, 1 if use_m_estimator else 0, 1 if revert else 0, None), "kb_iterate")
+            return None
+        out = _IterationResult()
         self._check(self._L.kb_iterate(self._h, lam, 1 if use_m_estimator else 0, 1 if revert else 0, C.byref(out)), "kb_iterate")
+        return out.cost, out.rho_denominator, out.max_abs_dx, bool(out.pos_def)
+
+    def wait_iterations(self):
+        out = _IterationResult()
+        self._check(self._L.kb_wait(self._h, C.byref(out)), "kb_wait")
         return out.cost, out.rho_denominator, out.max_abs_dx, bool(out.pos_def)
 
     def lm_rho_denominator(self, lam: float) -> float:
@@ -514,8 +523,12 @@ class B200SchurLinearSystemSolver:
     def kernel_launches(self) -> int:
         return int(self._L.kb_kernel_launches(self._h))
 
-    def enable_stage_timing(self, on: bool = True):
-        self._L.kb_enable_stage_timing(self._h, 1 if on else 0)
+    def enable_stage_timing(self, on: bool = True, stages=None):
+        """stages: names from STAGE_NAMES to time (default: all of them)"""
+        mask = 1 if on else 0
+        if on and stages is not None:
+            mask = sum(2 << STAGE_NAMES.index(n) for n in stages)
+        self._L.kb_enable_stage_timing(self._h, mask)
 
     def stage_ms(self) -> dict:
         ms = np.zeros(KB_NUM_STAGES)

@@ -108,7 +108,7 @@ struct DevProblem {
   double* dx;           // [jcols] in design-variable order (poses of other ranks stay 0)
   unsigned int* n_invalid;  // terms whose projection bailed out (Q6)
   double* rho_partial;      // [2 * max(64, back-substitution blocks)] stage-1 partials of the rho denominator / max|dx| reduction (per handle)
-  unsigned int* tickets;    // [4] zero-initialised "last block" ticket counters (finalize_gram)
+  unsigned int* tickets;    // [4] zero-initialised "last block" ticket counters ([0] finalize_gram, [1] backsub)
   LmCtrl* ctrl;             // control block (device)
   PeerXchg px;              // peer exchange (enabled after kb_attach_peers)
   // ---- weighting of the terms (kb_set_inv_r / kb_set_m_estimator) ----
@@ -158,8 +158,7 @@ cudaError_t launch_schur_finalize(const DevProblem& p, double damping, const dou
 cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_def_flag, bool from_peers, StreamCtx& s);
 int backsub_blocks(const DevProblem& p);
 cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, double lambda, int include_shared,
-                           bool with_rho, StreamCtx& s);
-cudaError_t launch_solve_scalars(const DevProblem& p, double* out2, const int* pos_def_for_exchange, const int* pos_def, int lm_mode, StreamCtx& s);
+                           double* out2, const int* pos_def_for_exchange, const int* pos_def, int lm_mode, StreamCtx& s);
 cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int* cam_cols,
                                    int include_shared, double* out2 /* [0]=sum, [1]=max|dx| */,
                                    const int* pos_def_for_exchange /* non-null: also the producer of peer exchange B */, StreamCtx& s);

@@ -181,6 +181,7 @@ struct kb_handle {
   int semantic = 0;
   bool built = false, solved = false, has_backup = false, presharded = false;
   bool speculative = true;       // kb_evaluate_error linearises too, so that a build at the same state is free
+  unsigned timing_mask = ~0u;    // stages that kb_enable_stage_timing selected
   bool defer_sync = false;       // inside kb_iterate: the entry points enqueue only, one synchronisation at the end
   long long state_version = 0;   // bumped whenever design variables or observations change
   long long la_version = -1;     // state the view blocks / Gram sums were computed at
@@ -198,11 +199,12 @@ struct kb_handle {
   NcclComm comm = nullptr;
   // ---- timing ----
   bool timing = false;
-  cudaEvent_t ev[2 * KB_NUM_STAGES] = {};
+  static constexpr int STAGE_RING = 64;          // stage measurements that may wait for a synchronisation (kb_iterate without wait)
+  cudaEvent_t ev[2 * KB_NUM_STAGES * STAGE_RING] = {};
+  long long stage_head[KB_NUM_STAGES] = {}, stage_tail[KB_NUM_STAGES] = {};  // measurements recorded / collected
   double stage_ms[KB_NUM_STAGES] = {};
   double stage_total[KB_NUM_STAGES] = {};
   long long stage_calls[KB_NUM_STAGES] = {};
-  bool stage_pending[KB_NUM_STAGES] = {};
 };
 
 namespace {
@@ -238,26 +240,30 @@ StreamCtx ctx(kb_handle* h) {
 struct StageTimer {
   kb_handle* h;
   int stage;
-  StageTimer(kb_handle* h_, int s) : h(h_), stage(s) { if (h->timing) cudaEventRecord(h->ev[2 * s], h->stream); }
+  StageTimer(kb_handle* h_, int s) : h(h_), stage(s) { if (on()) cudaEventRecord(h->ev[slot()], h->stream); }
+  bool on() const { return h->timing && ((h->timing_mask >> stage) & 1u); }
   ~StageTimer() {
-    if (h->timing) {
-      cudaEventRecord(h->ev[2 * stage + 1], h->stream);
-      h->stage_pending[stage] = true;
+    if (on()) {
+      cudaEventRecord(h->ev[slot() + 1], h->stream);
+      ++h->stage_head[stage];
     }
   }
+  int slot() const { return 2 * (stage * kb_handle::STAGE_RING + (int)(h->stage_head[stage] % kb_handle::STAGE_RING)); }
 };
 // call after a stream synchronisation: folds every finished stage measurement into the totals
 void collect_stages(kb_handle* h) {
   if (!h->timing) return;
   for (int s = 0; s < KB_NUM_STAGES; ++s) {
-    if (!h->stage_pending[s]) continue;
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, h->ev[2 * s], h->ev[2 * s + 1]) == cudaSuccess) {
-      h->stage_ms[s] = ms;
-      h->stage_total[s] += ms;
-      h->stage_calls[s] += 1;
+    for (long long i = std::max(h->stage_tail[s], h->stage_head[s] - kb_handle::STAGE_RING); i < h->stage_head[s]; ++i) {
+      const int slot = 2 * (s * kb_handle::STAGE_RING + (int)(i % kb_handle::STAGE_RING));
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, h->ev[slot], h->ev[slot + 1]) == cudaSuccess) {
+        h->stage_ms[s] = ms;
+        h->stage_total[s] += ms;
+        h->stage_calls[s] += 1;
+      }
     }
-    h->stage_pending[s] = false;
+    h->stage_tail[s] = h->stage_head[s];
   }
 }
 
@@ -585,7 +591,11 @@ static kb_status build_tables(kb_handle* h) {
   KB_CUDA(h, h->scalars.alloc(8));
   KB_CUDA(h, h->rho_partial.alloc(2 * std::max<size_t>(64, (size_t)n_local_sets / 8 + 2)));
   D.ctrl = h->ctrl.p;
-  KB_CUDA(h, h->posdef.alloc(2));
+  KB_CUDA(h, h->posdef.alloc(4));
+  {  // posdef[2] = 1 for good: the flag is re-armed by a device-to-device copy (steps may be enqueued ahead of the host)
+    static const int one = 1;
+    KB_CUDA(h, cudaMemcpyAsync(h->posdef.p + 2, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+  }
   KB_CUDA(h, h->lm_counters.alloc(KB_NUM_MODELS));
   KB_CUDA(h, cudaMemsetAsync(h->dx.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)h->jcols), s));
   KB_CUDA(h, cudaMemsetAsync(h->VB.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)n_views * VB_STRIDE), s));
@@ -659,7 +669,6 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   KB_CCUDA(cudaMallocHost((void**)&h->h_scalars, sizeof(double) * (8 + 4 * MAX_CAMS)));
   KB_CCUDA(cudaMallocHost((void**)&h->h_posdef, sizeof(int) * 2));
   KB_CCUDA(cudaMallocHost((void**)&h->h_ctrl, sizeof(LmCtrl)));
-  for (auto& e : h->ev) KB_CCUDA(cudaEventCreate(&e));
 
   // every stream / event of the handle up front (re-used for the whole life of the handle, also across kb_append_set)
   KB_CCUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -792,9 +801,15 @@ kb_status kb_get_dv_layout(const kb_handle* h, int32_t* column_base, int32_t* di
 int64_t kb_kernel_launches(const kb_handle* h) { return h->launches; }
 void* kb_cuda_stream(kb_handle* h) { return (void*)h->stream; }
 kb_status kb_enable_stage_timing(kb_handle* h, int32_t on) {
+  if (on) {  // the event ring is created on first use
+    KB_CUDA(h, cudaSetDevice(h->device));
+    for (auto& e : h->ev)
+      if (!e) KB_CUDA(h, cudaEventCreate(&e));
+  }
   h->timing = on != 0;
+  h->timing_mask = on > 1 ? (unsigned)on >> 1 : ~0u;  // on > 1: bit (s + 1) selects stage s; 1: every stage
   if (on)
-    for (int i = 0; i < KB_NUM_STAGES; ++i) { h->stage_total[i] = 0.0; h->stage_calls[i] = 0; h->stage_pending[i] = false; }
+    for (int i = 0; i < KB_NUM_STAGES; ++i) { h->stage_total[i] = 0.0; h->stage_calls[i] = 0; h->stage_tail[i] = h->stage_head[i]; }
   return KB_OK;
 }
 kb_status kb_get_stage_totals(kb_handle* h, double* total_ms, int64_t* calls) {
@@ -1395,8 +1410,7 @@ static kb_status analyze_marginal_impl(kb_handle* h, const kb_marginal_options* 
   // the undamped normal equations at the current state (or of the last build), set poses eliminated: exactly the analyzeMarginal matrix
   kb_status st = rebuild ? kb_build_system(h, 1) : KB_OK;
   if (st != KB_OK) return st;
-  h->h_posdef[0] = 1;
-  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->posdef.p + 2, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   KB_CUDA(h, launch_schur(h->d, 0.0, h->partials.p, h->n_partials, h->posdef.p, c));
   KB_CUDA(h, launch_schur_finalize(h->d, 0.0, h->partials.p, h->n_partials, true, c));
   if (h->px_on) {
@@ -1491,11 +1505,10 @@ static kb_status solve_finish(kb_handle* h, double* dx, int32_t gather_dx) {
   {
     StageTimer t(h, 5);
     // the back substitution leaves the per-block partials of dx^T (lambda dx + rhs) and max|dx| behind
-    KB_CUDA(h, launch_backsub(h->d, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->lambda, h->rank == 0 ? 1 : 0, true, c));
+    // ... and its last block adds them up, so that getLmRho / applyStateUpdate need no further pass over dx
+    KB_CUDA(h, launch_backsub(h->d, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, h->lambda, h->rank == 0 ? 1 : 0, h->scalars.p + 2, h->posdef.p, h->posdef.p, 0, c));
   }
   {
-    // ... so that getLmRho / applyStateUpdate need no further pass over dx
-    KB_CUDA(h, launch_solve_scalars(h->d, h->scalars.p + 2, h->posdef.p, h->posdef.p, 0, c));
     if (h->px_on) {
       KB_CUDA(h, launch_px_combine_solve(h->d, h->scalars.p + 2, h->posdef.p, 0, c));
     } else if (h->n_ranks > 1) {  // one packed all-reduce instead of three (min / sum / max)
@@ -1566,8 +1579,7 @@ kb_status kb_solve_system(kb_handle* h, double* dx, int32_t gather_dx, int32_t* 
   StreamCtx c = ctx(h);
   // diag(H) += lambda^2 on top of whatever earlier solves left there (BlockCholeskyLinearSystemSolver.cpp:77-86)
   const double damping = h->diag_residual + h->lambda * h->lambda;
-  h->h_posdef[0] = 1;
-  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->posdef.p + 2, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   {
     StageTimer t(h, 3);
     KB_CUDA(h, launch_schur(h->d, damping, h->partials.p, h->n_partials, h->posdef.p, c));
@@ -1608,8 +1620,13 @@ kb_status kb_iterate(kb_handle* h, double lambda, int32_t use_m_estimator, int32
     cudaStreamSynchronize(h->stream);
     return st;
   }
+  return out ? kb_wait(h, out) : KB_OK;  // out == NULL: enqueue only
+}
+
+kb_status kb_wait(kb_handle* h, kb_iteration_result* out) {
+  KB_CUDA(h, cudaSetDevice(h->device));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
-  if ((st = solve_post_sync(h)) != KB_OK) return st;
+  if (kb_status st = solve_post_sync(h); st != KB_OK) return st;
   if (out) {
     out->cost = h->h_scalars[0];
     out->rho_denominator = h->h_scalars[2];
@@ -1673,8 +1690,7 @@ kb_status kb_solve_system_svd(kb_handle* h, const kb_svd_solver_options* o, doub
     KB_CUDA(h, h->svd_result.alloc(4));
   }
   h->lambda = 0.0;  // GaussNewtonTrustRegionPolicy: no conditioner (requiresAugmentedDiagonal() == false)
-  h->h_posdef[0] = 1;
-  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->posdef.p + 2, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   kb_status st;
   {
     StageTimer t(h, 3);
@@ -1867,9 +1883,8 @@ static kb_status enqueue_lm_iteration(kb_handle* h) {
   }
   {
     StageTimer t(h, 5);
-    KB_CUDA(h, launch_backsub(D, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, -1.0, h->rank == 0 ? 1 : 0, true, c));
+    KB_CUDA(h, launch_backsub(D, h->set_col_q.p, h->set_col_t.p, h->cam_cols.p, -1.0, h->rank == 0 ? 1 : 0, h->scalars.p + 2, h->posdef.p, h->posdef.p, lm_local, c));
   }
-  KB_CUDA(h, launch_solve_scalars(D, h->scalars.p + 2, h->posdef.p, h->posdef.p, lm_local, c));
   if (h->px_on) {
     KB_CUDA(h, launch_px_combine_solve(D, h->scalars.p + 2, h->posdef.p, lm_px, c));
   } else if (h->n_ranks > 1) {
@@ -1913,8 +1928,7 @@ static kb_status optimize_on_device(kb_handle* h, const kb_optimizer_options* o,
                         h->semantic);
   // the decisions of the FIRST iteration are taken here; those of every later one by the device at the end of the iteration before
   if (!c0.done) kalibr_b200::lm_before_solve(&c0);
-  h->h_posdef[0] = 1;
-  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->h_posdef, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->posdef.p, h->posdef.p + 2, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(h->ctrl.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));  // pageable source: staged at the call
   *h->h_ctrl = c0;
   // iterations are enqueued two at a time; the host only reads the control block back to see whether the loop has ended.

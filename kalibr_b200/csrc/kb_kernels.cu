@@ -15,10 +15,10 @@
 //   reduced_solve     K3b: dense Cholesky of the reduced system            ≙ linear_solver_cholmod.h:70-112
 //   backsub           K3c: dx_v = (V_v + d I)^-1 (b_v - W_v^T dx_c)         ≙ sparse_matrix_functions.cpp:64-83
 //   rho / apply_update                                                   ≙ LevenbergMarquardtTrustRegionPolicy.cpp:107-113, Optimizer2.cpp:290-318
-//   lm_boundary (inside finalize_gram / px_combine_cost) / lm_after_solve (inside rho_stage2 / px_combine_solve) / lm_revert / lm_finish
+//   lm_boundary (inside finalize_gram / px_combine_cost) / lm_after_solve (inside backsub's last block / px_combine_solve) / lm_revert / lm_finish
 //                     device-resident LM loop: the transitions of include/kalibr_b200/lm_state_machine.h
 //                                                                       ≙ Optimizer2.cpp:215-266, LevenbergMarquardtTrustRegionPolicy.cpp:50-113
-//   px_*              NVLink peer exchange between ranks (producers are fused into schur_finalize / rho_stage2 / gram_cost)
+//   px_*              NVLink peer exchange between ranks (producers are fused into schur_finalize / backsub / finalize_gram)
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
@@ -186,6 +186,36 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ---- programmatic dependent launch -------------------------------------------------------------------------------------------
+// Every kernel of an LM iteration starts with pdl_enter(): wait until the preceding kernel of the stream has completed and its
+// writes are visible (griddepcontrol.wait; a no-op for a kernel launched without the attribute), then let the kernel that follows
+// start launching.  With launch_pdl() on the host side the CTAs of kernel N + 1 are scheduled while kernel N drains instead of
+// after it; results are unchanged because nothing is read before the wait.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+static bool pdl_enabled() {
+  static const bool on = getenv("KB_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- peer exchange primitives (kb_device.cuh: PeerXchg) -------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -286,6 +316,7 @@ __global__ void prep_kernel(DevProblem p) {
 // per synced set: inverse pose (C^-1, -C^-1 t) and P_v, shared by the views of every camera of the set
 // with_cam_prep: one extra block at the end of the grid computes the per-camera constants (prep_kernel's work) in the same launch
 __global__ void __launch_bounds__(128) set_prep_kernel(DevProblem p, int with_cam_prep) {
+  pdl_enter();
   if (p.ctrl->done || p.ctrl->skip_eval) return;
   if (with_cam_prep && blockIdx.x == gridDim.x - 1) {
     if (threadIdx.x < p.n_cams) camera_prep(p, threadIdx.x);
@@ -607,12 +638,13 @@ __global__ void __launch_bounds__(LA_THREADS, 2) linearise_assemble_kernel(DevPr
   double* sSP = sG + GRAM_TILES;                               // [2][16] per-set constants of the current / next view (cp.async)
   double* sC = sSP + 2 * LA_SP_DOUBLES;                        // [R_cw | t_cw] of the current view
   double* prm = sC + 12;                                       // parameters of the slice's camera
-  if (p.ctrl->done || p.ctrl->skip_eval) return;
-  for (int i = threadIdx.x; i < p.n_target; i += blockDim.x) {
+  for (int i = threadIdx.x; i < p.n_target; i += blockDim.x) {  // constant data: staged while the preceding kernel drains
     s_tx[i] = p.target[3 * i];
     s_ty[i] = p.target[3 * i + 1];
     s_tz[i] = p.target[3 * i + 2];
   }
+  pdl_enter();
+  if (p.ctrl->done || p.ctrl->skip_eval) return;
   __syncthreads();
 
   const int warp = blockIdx.x * LA_WARPS + wib;
@@ -969,6 +1001,7 @@ __device__ __forceinline__ double c_to_b(double c0, double c1, int ks, int arow,
 __device__ void camera_block_element(const DevProblem& p, int idx);
 // Blocks [0, n_set_blocks) reduce the sets; the remaining blocks of the grid compute the camera block U (one element per thread).
 __global__ void __launch_bounds__(SR_WARPS * 32) set_reduce_kernel(DevProblem p, int n_set_blocks) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int arow = lane >> 2, acol = lane & 3;
@@ -1091,6 +1124,7 @@ __device__ __forceinline__ void lm_boundary(LmCtrl* c, double* __restrict__ trac
 __global__ void __launch_bounds__(GRAM_TILES * FG_GROUPS) finalize_gram_kernel(DevProblem p, const int* __restrict__ cam_slice_range, int n_ranges,
                                                                                double* __restrict__ cost_out, int exchange, int lm_mode,
                                                                                double* __restrict__ trace, int* __restrict__ pos_def) {
+  pdl_enter();
   __shared__ double sh[FG_GROUPS][GRAM_TILES];
   __shared__ int s_last;
   const int k = blockIdx.x, t = threadIdx.x % GRAM_TILES, g = threadIdx.x / GRAM_TILES;
@@ -1234,6 +1268,7 @@ __device__ void camera_block_element(const DevProblem& p, int idx) {
 // exchange C consumer: total cost, summed in rank order
 // lm_mode 1 (device loop over the peer exchange): the loop boundary runs here, on the combined cost
 __global__ void px_combine_cost_kernel(DevProblem p, double* __restrict__ out, int lm_mode, double* __restrict__ trace, int* __restrict__ pos_def) {
+  pdl_enter();
   if (p.ctrl->done) return;
   if (p.ctrl->skip_eval) {
     if (lm_mode == 1) lm_boundary(p.ctrl, trace, pos_def, false);
@@ -1266,6 +1301,7 @@ __global__ void __launch_bounds__(256) px_reduce_system_kernel(DevProblem p) {
 }
 // exchange B consumer: rho denominator (sum), max|dx| (max), pos-def (min) over the ranks, in rank order
 __global__ void px_combine_solve_kernel(DevProblem p, double* __restrict__ rho_max, int* __restrict__ pos_def, int lm_mode) {
+  pdl_enter();
   if (p.ctrl->done) return;
   const unsigned long long e = px_cur_epoch(p.px, 1);
   double rho = 0.0, mx = 0.0;
@@ -1320,18 +1356,19 @@ constexpr int SC_SETS = 4;              // sets per step: K = 24 = 6 k-steps of 
 constexpr int SC_K = SC_SETS * 6;
 constexpr int SC_LD = 36;               // ld % 16 == 4 keeps the operand loads conflict-free
 
-// Per step of SC_SETS sets: the raw rows [W_v ; b_v^T] and the inverse factors L_v^-1 of the NEXT step travel with cp.async
-// straight into the other Z buffer while the DMMA phase runs on the current one; afterwards every thread turns the rows it
-// copied into Z rows in place (z = L^-1 w, a 6x6 triangular product).
+// Per step of SC_SETS sets: the raw rows [W_v ; b_v^T] and the inverse factors L_v^-1 travel with cp.async straight into a Z
+// buffer two steps ahead; one step ahead every thread turns the rows it copied into Z rows in place (z = L^-1 w, a 6x6
+// triangular product) while the DMMA phase of the current step runs.
 template <int WARPS, int MAX_PAIRS>
 __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, double* __restrict__ partials, int sets_per_cta, double damping_arg,
                                                               int* __restrict__ pos_def_flag) {
+  pdl_enter();
   extern __shared__ __align__(16) double smem[];
   const int n = p.n_aug;
   const int nt = (n + 7) >> 3;
   const int n_pad = nt * 8;
-  double* Zbuf = smem;                         // [2][n_pad][SC_LD]
-  double* sLi = smem + 2 * n_pad * SC_LD;      // [2][SC_SETS][36]
+  double* Zbuf = smem;                         // [3][n_pad][SC_LD]: reduced on / being transformed / in flight
+  double* sLi = smem + 3 * n_pad * SC_LD;      // [3][SC_SETS][36]
   if (p.ctrl->done) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int arow = lane >> 2, acol = lane & 3;
@@ -1355,7 +1392,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
     acc[q][0] = 0.0;
     acc[q][1] = 0.0;
   }
-  for (int i = tid; i < 2 * n_pad * SC_LD; i += blockDim.x) Zbuf[i] = 0.0;
+  for (int i = tid; i < 3 * n_pad * SC_LD; i += blockDim.x) Zbuf[i] = 0.0;
   const int s_lo = blockIdx.x * sets_per_cta, s_hi = min(p.n_sets, s_lo + sets_per_cta);
   {
     // the factors of this slice (the CTAs of a gridDim.y split compute the same values: identical, benign double stores)
@@ -1413,20 +1450,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
       }
     }
   };
-  if (s_lo < s_hi) {
-    fetch(Zbuf, sLi, s_lo);
+  // Three buffers, ONE barrier per step: while the tensor pipe reduces step k, the rows of step k + 1 (landed during step k - 1) are
+  // turned into Z rows and the raw rows of step k + 2 are in flight.  Half of the warps do the triangular products first and the
+  // DMMAs second, the other half the other way round, so the two kinds of FP64 work overlap on the shared pipe.
+  auto zb = [&](int k) { return Zbuf + (size_t)(k % 3) * n_pad * SC_LD; };
+  auto lb = [&](int k) { return sLi + (k % 3) * SC_SETS * 36; };
+  const int n_steps = (s_hi - s_lo + SC_SETS - 1) / SC_SETS;
+  if (n_steps > 0) {
+    fetch(zb(0), lb(0), s_lo);
+    if (n_steps > 1) fetch(zb(1), lb(1), s_lo + SC_SETS);
     cp_async_wait_all();
     __syncthreads();
-    transform(Zbuf, sLi, s_lo);
+    transform(zb(0), lb(0), s_lo);
+    __syncthreads();
   }
-  __syncthreads();
-  int buf = 0;
-  for (int s0 = s_lo; s0 < s_hi; s0 += SC_SETS) {
-    const double* Zs = Zbuf + (size_t)buf * n_pad * SC_LD;
-    double* Zn = Zbuf + (size_t)(buf ^ 1) * n_pad * SC_LD;
-    double* Ln = sLi + (buf ^ 1) * SC_SETS * 36;
-    const bool more = s0 + SC_SETS < s_hi;
-    if (more) fetch(Zn, Ln, s0 + SC_SETS);  // in flight during the DMMA phase below
+  auto reduce = [&](const double* Zs) {
 #pragma unroll
     for (int kk = 0; kk < SC_K / 4; ++kk) {
 #pragma unroll
@@ -1438,13 +1476,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
         }
       }
     }
-    if (more) {
-      cp_async_wait_all();
-      __syncthreads();  // every thread's copies (the L factors are shared) have landed
-      transform(Zn, Ln, s0 + SC_SETS);
+  };
+  for (int k = 0; k < n_steps; ++k) {
+    if (k + 2 < n_steps) fetch(zb(k + 2), lb(k + 2), s_lo + (k + 2) * SC_SETS);  // lands during this step and the next
+    if (warp & 1) {
+      reduce(zb(k));
+      if (k + 1 < n_steps) transform(zb(k + 1), lb(k + 1), s_lo + (k + 1) * SC_SETS);
+    } else {
+      if (k + 1 < n_steps) transform(zb(k + 1), lb(k + 1), s_lo + (k + 1) * SC_SETS);
+      reduce(zb(k));
     }
-    __syncthreads();
-    buf ^= 1;
+    cp_async_wait_all();  // this thread's copies of step k + 2
+    __syncthreads();      // step k + 1 is transformed, step k + 2 has landed (the L factors are shared), step k's buffer is free
   }
   double* out = partials + (size_t)blockIdx.x * n_pad * n_pad;
 #pragma unroll
@@ -1458,6 +1501,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
 
 // Sred = U - sum_partials (fixed order), symmetric, undamped; this rank's contribution to the all-reduce.
 __global__ void __launch_bounds__(256) schur_finalize_kernel(DevProblem p, const double* __restrict__ partials, int n_partials) {
+  pdl_enter();
   const int n = p.n_aug;
   const int n_pad = ((n + 7) >> 3) * 8;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1623,6 +1667,7 @@ __device__ __forceinline__ void panel_rows(double* __restrict__ Lp, int j0, int 
 // rows above (two barriers per panel instead of one per unknown).
 __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem p, double damping_arg, int* __restrict__ pos_def_flag, int from_peers,
                                                                       long long* __restrict__ dbg /* KB_RS_TRACE: cycles per phase, or null */) {
+  pdl_enter();
   __shared__ long long s_dbg[8];
   if (dbg && threadIdx.x < 8) s_dbg[threadIdx.x] = 0;
   long long t_mark = clock64();
@@ -2188,6 +2233,64 @@ __global__ void __launch_bounds__(256) svd_truncated_solve_kernel(DevProblem p, 
   }
 }
 
+constexpr int RHO_BLOCKS = 64;
+__device__ __forceinline__ void block_sum_max(double& s, double& m, double* sh_s, double* sh_m) {
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_m[threadIdx.x >> 5] = m; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    s = threadIdx.x < nw ? sh_s[threadIdx.x] : 0.0;
+    m = threadIdx.x < nw ? sh_m[threadIdx.x] : 0.0;
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+}
+// Second stage of the solve scalars, run by ONE block of 256 threads (the last block of backsub_kernel to finish): out[0] = the sum of the
+// blocks' partials of dx^T (lambda dx + rhs), out[1] = max |dx|, in a fixed order; producer of peer exchange B; lm_mode 1: thread 0
+// runs the after-solve transition of the device-resident loop (single rank).
+constexpr int RHO2_THREADS = 256;
+__device__ __forceinline__ void solve_scalars_stage2(LmCtrl* __restrict__ ctrl, const PeerXchg& px, const int* __restrict__ pos_def,
+                                                     const double* __restrict__ partial, int n, double* __restrict__ out, int lm_mode) {
+  __shared__ double sh_s[32], sh_m[32];
+  double s = 0.0, m = 0.0;
+  // fixed assignment of partials to threads, fixed order inside a thread; four independent 16-byte loads in flight per thread
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * RHO2_THREADS) {
+    double2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * RHO2_THREADS;
+      v[u] = i < n ? __ldcg(reinterpret_cast<const double2*>(partial) + i) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s += v[u].x;
+      m = fmax(m, v[u].y);
+    }
+  }
+  block_sum_max(s, m, sh_s, sh_m);
+  if (threadIdx.x == 0) {
+    out[0] = s;
+    out[1] = m;
+    if (lm_mode == 1) kalibr_b200::lm_after_solve(ctrl, s, m, pos_def[0]);
+    if (px.enabled) {  // exchange B: (rho partial, max|dx|, pos-def) into every rank's slot
+      const unsigned long long e = px_next_epoch(px, 1);
+      const double pd = (double)pos_def[0];
+      for (int r = 0; r < px.n_ranks; ++r) {
+        double* slot = px.base[r] + px_off_b(px, (int)(e & 1), px.rank);
+        slot[0] = s;
+        slot[1] = m;
+        slot[2] = pd;
+      }
+      __threadfence_system();
+      px_signal(px, 1, e);
+    }
+  }
+}
+
 // =========================================================================================================
 // back substitution for the poses + scatter of dx into design-variable order
 // =========================================================================================================
@@ -2195,8 +2298,11 @@ __global__ void __launch_bounds__(256) svd_truncated_solve_kernel(DevProblem p, 
 // camera-side part (dx_c^T b_c of this rank, + lambda |dx_c|^2 when include_shared) - stage 1 of the rho denominator for free
 __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
                                                       const int* __restrict__ cam_cols, double lambda_arg, int include_shared,
-                                                      double* __restrict__ partial) {
+                                                      double* __restrict__ partial, double* __restrict__ out2, PeerXchg px,
+                                                      const int* __restrict__ pos_def, int lm_mode) {
+  pdl_enter();
   __shared__ double sh_s[8], sh_m[8];
+  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (p.ctrl->done) return;
@@ -2266,27 +2372,20 @@ __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* _
     for (int w = 0; w < 8; ++w) { s += sh_s[w]; m = fmax(m, sh_m[w]); }  // fixed order
     partial[2 * blockIdx.x] = s;
     partial[2 * blockIdx.x + 1] = m;
+    // the last block to arrive adds the partials up (fixed order: the result does not depend on which block that is)
+    __threadfence();
+    const unsigned int ticket = atomicAdd(p.tickets + 1, 1u);
+    s_last = ticket == gridDim.x - 1;
+    if (s_last) p.tickets[1] = 0u;
   }
+  __syncthreads();
+  if (!s_last || !out2) return;
+  __threadfence();
+  solve_scalars_stage2(p.ctrl, px, pos_def, partial, (int)gridDim.x, out2, lm_mode);
 }
 
 // out[0] = sum_local dx (lambda dx + rhs) [+ lambda |dx_c|^2 once], out[1] = max |dx| over local poses and the shared block.
 // Two stages with fixed order: per-block partials, then one block.
-constexpr int RHO_BLOCKS = 64;
-__device__ __forceinline__ void block_sum_max(double& s, double& m, double* sh_s, double* sh_m) {
-  s = warp_sum(s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) { sh_s[threadIdx.x >> 5] = s; sh_m[threadIdx.x >> 5] = m; }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int nw = blockDim.x >> 5;
-    s = threadIdx.x < nw ? sh_s[threadIdx.x] : 0.0;
-    m = threadIdx.x < nw ? sh_m[threadIdx.x] : 0.0;
-    s = warp_sum(s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  }
-}
 __global__ void __launch_bounds__(256) rho_stage1_kernel(DevProblem p, double lambda_arg, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
                                                            int include_shared, double* __restrict__ partial /*[RHO_BLOCKS][2]*/) {
   __shared__ double sh_s[32], sh_m[32];
@@ -2312,37 +2411,12 @@ __global__ void __launch_bounds__(256) rho_stage1_kernel(DevProblem p, double la
   block_sum_max(s, m, sh_s, sh_m);
   if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s; partial[2 * blockIdx.x + 1] = m; }
 }
-constexpr int RHO2_THREADS = 256;
-// lm_mode 1 (single-rank device loop): thread 0 also runs the after-solve transition of the state machine on the result
+// second stage on its own (the rho query outside a solve: kb_lm_rho_denominator)
 __global__ void __launch_bounds__(RHO2_THREADS) rho_stage2_kernel(LmCtrl* __restrict__ ctrl, PeerXchg px, const int* __restrict__ pos_def,
                                                                   const double* __restrict__ partial, int n, double* __restrict__ out, int lm_mode) {
-  __shared__ double sh_s[32], sh_m[32];
   if (ctrl->done) return;
-  double s = 0.0, m = 0.0;
-  for (int i = threadIdx.x; i < n; i += RHO2_THREADS) {  // fixed assignment of partials to threads, fixed order inside a thread
-    s += partial[2 * i];
-    m = fmax(m, partial[2 * i + 1]);
-  }
-  block_sum_max(s, m, sh_s, sh_m);
-  if (threadIdx.x == 0) {
-    out[0] = s;
-    out[1] = m;
-    if (lm_mode == 1) kalibr_b200::lm_after_solve(ctrl, s, m, pos_def[0]);
-    if (px.enabled) {  // exchange B: (rho partial, max|dx|, pos-def) into every rank's slot
-      const unsigned long long e = px_next_epoch(px, 1);
-      const double pd = (double)pos_def[0];
-      for (int r = 0; r < px.n_ranks; ++r) {
-        double* slot = px.base[r] + px_off_b(px, (int)(e & 1), px.rank);
-        slot[0] = s;
-        slot[1] = m;
-        slot[2] = pd;
-      }
-      __threadfence_system();
-      px_signal(px, 1, e);
-    }
-  }
+  solve_scalars_stage2(ctrl, px, pos_def, partial, n, out, lm_mode);
 }
-
 // Multi-rank: every rank drops (rho partial, max|dx|, pos-def flag) into its own slot of a zeroed [n_ranks][4] array; ONE
 // sum all-reduce then hands every rank all slots, and the host combines them in rank order (sum / max / min).
 __global__ void pack_rank_scalars_kernel(double* __restrict__ pk, int rank, int n_ranks, const double* __restrict__ rho_max, const int* __restrict__ pos_def) {
@@ -2371,6 +2445,7 @@ __device__ __forceinline__ void update_quat(double* q, const double* dq) {
 // DesignVariableAdapter.hpp:42-55 over Projection::update / Distortion::update, all of which are parameter += delta)
 __global__ void __launch_bounds__(256) apply_update_kernel(DevProblem p, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
                                                            double* __restrict__ backup_cam, double* __restrict__ backup_base, double* __restrict__ backup_sets) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (p.ctrl->done || p.ctrl->skip_eval) return;
   // device-resident loop: a rejected step is undone lazily, here (the backup IS the state to start from) - outside the loop the flag is 0
@@ -2580,7 +2655,7 @@ static cudaError_t launch_la_model(const DevProblem& p, const int4* vmeta, const
   const size_t smem = sizeof(double) * (3 * ((p.n_target + 1) & ~1) + LA_WARPS * LA_WARP_DOUBLES);
   if (cudaError_t e = ensure_dynamic_smem(linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED>, smem, attr_smem_dev); e != cudaSuccess) return e;
   const int grid = min((hi - lo + LA_WARPS - 1) / LA_WARPS, sm_count() * 2);
-  linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED><<<grid, LA_THREADS, smem, s.stream>>>(p, vmeta, slices, lo, hi);
+  if (cudaError_t e = launch_pdl(linearise_assemble_kernel<MODEL, WRITE_E, WEIGHTED>, grid, LA_THREADS, smem, s.stream, p, vmeta, slices, lo, hi); e != cudaSuccess) return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2590,7 +2665,7 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, co
                                       bool with_cam_prep, StreamCtx& s) {
   cudaError_t e;
   if ((with_set_prep && p.n_sets > 0) || with_cam_prep) {  // per-set constants and (extra block) per-camera constants in one launch
-    set_prep_kernel<<<(with_set_prep ? (p.n_sets + 127) / 128 : 0) + (with_cam_prep ? 1 : 0), 128, 0, s.stream>>>(p, with_cam_prep ? 1 : 0);
+    if ((e = launch_pdl(set_prep_kernel, (with_set_prep ? (p.n_sets + 127) / 128 : 0) + (with_cam_prep ? 1 : 0), 128, 0, s.stream, p, with_cam_prep ? 1 : 0)) != cudaSuccess) return e;
     KB_LAUNCHED(s);
   }
   e = for_each_model_concurrently(smb, s, [&](int m, StreamCtx& c) -> cudaError_t {
@@ -2613,8 +2688,10 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, co
 // per-camera Gram sums + cost of the linearisation point (-> cost_out[0]); lm_mode 1: + the loop boundary of the device-resident loop
 cudaError_t launch_finalize_gram(const DevProblem& p, const int* cam_slice_range, int n_ranges, double* cost_out, bool exchange_cost, int lm_mode,
                                  double* trace, int* pos_def, StreamCtx& s) {
-  finalize_gram_kernel<<<p.n_cams, GRAM_TILES * FG_GROUPS, 0, s.stream>>>(p, cam_slice_range, n_ranges, cost_out, exchange_cost ? 1 : 0, lm_mode, trace,
-                                                                          pos_def);
+  if (cudaError_t e = launch_pdl(finalize_gram_kernel, p.n_cams, GRAM_TILES * FG_GROUPS, 0, s.stream, p, cam_slice_range, n_ranges, cost_out, exchange_cost ? 1 : 0, lm_mode,
+                                 trace, pos_def);
+      e != cudaSuccess)
+    return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2659,7 +2736,7 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
 cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s) {
   const int set_blocks = p.n_sets > 0 ? min((p.n_sets + SR_WARPS - 1) / SR_WARPS, sm_count() * 8) : 0;
   const int n2 = p.n_aug * p.n_aug;
-  set_reduce_kernel<<<set_blocks + (n2 + SR_WARPS * 32 - 1) / (SR_WARPS * 32), SR_WARPS * 32, 0, s.stream>>>(p, set_blocks);
+  if (cudaError_t e = launch_pdl(set_reduce_kernel, set_blocks + (n2 + SR_WARPS * 32 - 1) / (SR_WARPS * 32), SR_WARPS * 32, 0, s.stream, p, set_blocks); e != cudaSuccess) return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2683,13 +2760,15 @@ size_t schur_partial_stride(const DevProblem& p) {
 template <int WARPS, int MAX_PAIRS>
 static cudaError_t launch_schur_t(const DevProblem& p, double damping, double* partials, int n_partials, int* flag, StreamCtx& s) {
   const int n_pad = ((p.n_aug + 7) >> 3) * 8;
-  const size_t smem = sizeof(double) * (2 * (size_t)n_pad * SC_LD + 2 * SC_SETS * 36);
+  const size_t smem = sizeof(double) * (3 * (size_t)n_pad * SC_LD + 3 * SC_SETS * 36);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
   if (cudaError_t e = ensure_dynamic_smem(schur_kernel<WARPS, MAX_PAIRS>, smem, attr_smem_dev); e != cudaSuccess) return e;
   const int nt = (p.n_aug + 7) >> 3;
   const int npairs = nt * (nt + 1) / 2;
   const int gy = (npairs + WARPS * MAX_PAIRS - 1) / (WARPS * MAX_PAIRS);
-  schur_kernel<WARPS, MAX_PAIRS><<<dim3(n_partials, gy), WARPS * 32, smem, s.stream>>>(p, partials, schur_sets_per_cta(p), damping, flag);
+  if (cudaError_t e = launch_pdl(schur_kernel<WARPS, MAX_PAIRS>, dim3(n_partials, gy), WARPS * 32, smem, s.stream, p, partials, schur_sets_per_cta(p), damping, flag);
+      e != cudaSuccess)
+    return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2699,12 +2778,15 @@ cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, 
   // computed by the CTAs themselves
   const int nt = (p.n_aug + 7) >> 3;
   if (nt <= 6) return launch_schur_t<8, 3>(p, damping, partials, n_partials, flag, s);
+  static const int variant = getenv("KB_SCHUR_VARIANT") ? atoi(getenv("KB_SCHUR_VARIANT")) : 0;  // experiments
+  if (variant == 1) return launch_schur_t<16, 7>(p, damping, partials, n_partials, flag, s);
+  if (variant == 2) return launch_schur_t<12, 9>(p, damping, partials, n_partials, flag, s);
   return launch_schur_t<8, 14>(p, damping, partials, n_partials, flag, s);  // nt <= 14: one CTA per slice; larger systems: tile pairs split over gridDim.y
 }
 
 cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const double* partials, int n_partials, bool, StreamCtx& s) {
   const int n2 = p.n_aug * p.n_aug;
-  schur_finalize_kernel<<<(4 * n2 + 255) / 256, 256, 0, s.stream>>>(p, partials, n_partials);
+  if (cudaError_t e = launch_pdl(schur_finalize_kernel, (4 * n2 + 255) / 256, 256, 0, s.stream, p, partials, n_partials); e != cudaSuccess) return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2720,7 +2802,9 @@ cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_d
     cudaMallocManaged(&dbg, 8 * sizeof(long long));
     cudaMemset(dbg, 0, 8 * sizeof(long long));
   }
-  reduced_solve_kernel<<<1, RS_THREADS, smem, s.stream>>>(p, damping, pos_def_flag, from_peers && p.px.enabled ? 1 : 0, trace ? dbg : nullptr);
+  if (cudaError_t e = launch_pdl(reduced_solve_kernel, 1, RS_THREADS, smem, s.stream, p, damping, pos_def_flag, from_peers && p.px.enabled ? 1 : 0, trace ? dbg : nullptr);
+      e != cudaSuccess)
+    return e;
   KB_LAUNCHED(s);
   if (trace) {  // experiments only: cycles per phase of this launch (load, panel update, diagonal block, panel rows, back substitution)
     cudaStreamSynchronize(s.stream);
@@ -2732,25 +2816,20 @@ cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_d
 }
 
 int backsub_blocks(const DevProblem& p) { return ((p.n_sets > 0 ? p.n_sets : 1) * 32 + 255) / 256; }
-// back substitution; with_rho: its blocks also leave the stage-1 partials of the rho denominator / max|dx| in p.rho_partial, and
-// launch_solve_scalars finishes them
+// back substitution; its blocks also leave the stage-1 partials of the rho denominator / max|dx| in p.rho_partial.
+// out2 (optional) = (dx^T (lambda dx + rhs), max|dx|) of this rank, written by the last block; it is also the producer of peer
+// exchange B when pos_def_for_exchange is given; lm_mode 1: + the after-solve transition of the device-resident loop (single rank)
 cudaError_t launch_backsub(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int* cam_cols, double lambda, int include_shared,
-                           bool with_rho, StreamCtx& s) {
-  backsub_kernel<<<backsub_blocks(p), 256, 0, s.stream>>>(p, set_col_q, set_col_t, cam_cols, lambda, include_shared, with_rho ? p.rho_partial : nullptr);
-  KB_LAUNCHED(s);
-  return cudaGetLastError();
-}
-// out2 = (dx^T (lambda dx + rhs), max|dx|) of this rank from the partials launch_backsub left; producer of peer exchange B when
-// pos_def_for_exchange is given; lm_mode 1: + the after-solve transition of the device-resident loop (single rank)
-cudaError_t launch_solve_scalars(const DevProblem& p, double* out2, const int* pos_def_for_exchange, const int* pos_def, int lm_mode, StreamCtx& s) {
+                           double* out2, const int* pos_def_for_exchange, const int* pos_def, int lm_mode, StreamCtx& s) {
   PeerXchg px = p.px;
   if (!pos_def_for_exchange) px.enabled = 0;
-  rho_stage2_kernel<<<1, RHO2_THREADS, 0, s.stream>>>(p.ctrl, px, pos_def_for_exchange ? pos_def_for_exchange : pos_def, p.rho_partial, backsub_blocks(p), out2,
-                                                      lm_mode);
+  if (cudaError_t e = launch_pdl(backsub_kernel, backsub_blocks(p), 256, 0, s.stream, p, set_col_q, set_col_t, cam_cols, lambda, include_shared,
+                                 out2 ? p.rho_partial : nullptr, out2, px, pos_def_for_exchange ? pos_def_for_exchange : pos_def, lm_mode);
+      e != cudaSuccess)
+    return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
-
 cudaError_t launch_rho_denominator(const DevProblem& p, double lambda, const int* set_col_q, const int* set_col_t, const int*, int include_shared,
                                    double* out2, const int* pos_def_for_exchange, StreamCtx& s) {
   double* partial = p.rho_partial;  // per handle (kb_create): two handles on one GPU never share scratch
@@ -2776,12 +2855,12 @@ cudaError_t launch_px_reduce_system(const DevProblem& p, StreamCtx& s) {
   return cudaGetLastError();
 }
 cudaError_t launch_px_combine_solve(const DevProblem& p, double* rho_max, int* pos_def_flag, int lm_mode, StreamCtx& s) {
-  px_combine_solve_kernel<<<1, 1, 0, s.stream>>>(p, rho_max, pos_def_flag, lm_mode);
+  if (cudaError_t e = launch_pdl(px_combine_solve_kernel, 1, 1, 0, s.stream, p, rho_max, pos_def_flag, lm_mode); e != cudaSuccess) return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
 cudaError_t launch_px_combine_cost(const DevProblem& p, double* cost, int lm_mode, double* trace, int* pos_def, StreamCtx& s) {
-  px_combine_cost_kernel<<<1, 1, 0, s.stream>>>(p, cost, lm_mode, trace, pos_def);
+  if (cudaError_t e = launch_pdl(px_combine_cost_kernel, 1, 1, 0, s.stream, p, cost, lm_mode, trace, pos_def); e != cudaSuccess) return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
@@ -2889,7 +2968,7 @@ cudaError_t launch_widen_observations(const float* su, const float* sv, double* 
 cudaError_t launch_apply_update(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int*, double* backup_cam, double* backup_base,
                                 double* backup_sets, StreamCtx& s) {
   const int n = p.n_sets > 0 ? p.n_sets : 1;
-  apply_update_kernel<<<(n + 255) / 256, 256, 0, s.stream>>>(p, set_col_q, set_col_t, backup_cam, backup_base, backup_sets);
+  if (cudaError_t e = launch_pdl(apply_update_kernel, (n + 255) / 256, 256, 0, s.stream, p, set_col_q, set_col_t, backup_cam, backup_base, backup_sets); e != cudaSuccess) return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }

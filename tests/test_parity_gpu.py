@@ -446,3 +446,10 @@ def test_iterate_equals_the_six_separate_calls(capi):
         cost, rho2, m2, ok2 = b.iterate(lam, revert=revert)
         assert (cost, rho2, m2, ok2) == (J, rho, m, ok)
         assert np.array_equal(a.camera_params(), b.camera_params()) and np.array_equal(a.set_poses(), b.set_poses())
+    # enqueue-only iterations (out == NULL) followed by one kb_wait: the scalars of the LAST one, the state after all of them
+    c = capi.B200SchurLinearSystemSolver(p)
+    for lam, revert in [(10.0, False), (3.0, True)]:
+        assert c.iterate(lam, revert=revert, wait=False) is None
+    c.iterate(1.0, revert=False, wait=False)
+    assert c.wait_iterations() == (cost, rho2, m2, ok2)
+    assert np.array_equal(c.camera_params(), b.camera_params()) and np.array_equal(c.set_poses(), b.set_poses())
