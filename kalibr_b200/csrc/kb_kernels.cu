@@ -19,6 +19,9 @@
 //                     device-resident LM loop: the transitions of include/kalibr_b200/lm_state_machine.h
 //                                                                       ≙ Optimizer2.cpp:215-266, LevenbergMarquardtTrustRegionPolicy.cpp:50-113
 //   px_*              NVLink peer exchange between ranks (producers are fused into schur_finalize / backsub / finalize_gram)
+#include <algorithm>
+#include <cstring>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
@@ -1359,9 +1362,19 @@ constexpr int SC_LD = 36;               // ld % 16 == 4 keeps the operand loads 
 // Per step of SC_SETS sets: the raw rows [W_v ; b_v^T] and the inverse factors L_v^-1 travel with cp.async straight into a Z
 // buffer two steps ahead; one step ahead every thread turns the rows it copied into Z rows in place (z = L^-1 w, a 6x6
 // triangular product) while the DMMA phase of the current step runs.
-template <int WARPS, int MAX_PAIRS>
+// BLOCKED: a warp owns up to SC_UNITS rectangles of up to 4 x 4 tile pairs (SchurUnits, filled by the launcher: the upper triangle of
+// the tile grid cut into 4 x 4 macro blocks, largest first onto the least loaded warp), so the four row operands and four column
+// operands of a k-step feed up to sixteen DMMAs - the operand loads of the scattered assignment (two per DMMA) kept the LSU as busy as
+// the tensor pipe.  !BLOCKED (small systems): MAX_PAIRS scattered tile pairs per warp.
+constexpr int SC_UNITS = 2;
+constexpr int SC_MAX_SLOTS = 64;  // warps x units x gridDim.y
+struct SchurUnits {
+  unsigned char ti0[SC_MAX_SLOTS], nr[SC_MAX_SLOTS], tj0[SC_MAX_SLOTS], nc[SC_MAX_SLOTS];  // nr = 0: empty slot; ti0 == tj0: diagonal block (c >= r only)
+};
+
+template <int WARPS, int MAX_PAIRS, bool BLOCKED>
 __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, double* __restrict__ partials, int sets_per_cta, double damping_arg,
-                                                              int* __restrict__ pos_def_flag) {
+                                                              int* __restrict__ pos_def_flag, const SchurUnits units) {
   pdl_enter();
   extern __shared__ __align__(16) double smem[];
   const int n = p.n_aug;
@@ -1373,24 +1386,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int arow = lane >> 2, acol = lane & 3;
   const int npairs = nt * (nt + 1) / 2;
-  // tile pairs of this warp (upper triangle, row-major enumeration)
-  int ti[MAX_PAIRS], tj[MAX_PAIRS];
-  double acc[MAX_PAIRS][2];
+  // !BLOCKED: tile pairs of this warp (upper triangle, row-major enumeration)
+  int ti[BLOCKED ? 1 : MAX_PAIRS], tj[BLOCKED ? 1 : MAX_PAIRS];
+  double acc[BLOCKED ? 1 : MAX_PAIRS][2];
+  // BLOCKED: the warp's rectangles
+  int u_ti0[SC_UNITS], u_nr[SC_UNITS], u_tj0[SC_UNITS], u_nc[SC_UNITS];
+  double bacc[BLOCKED ? SC_UNITS : 1][4][4][2];
+  if constexpr (BLOCKED) {
 #pragma unroll
-  for (int q = 0; q < MAX_PAIRS; ++q) {
-    int pair = warp + q * WARPS + blockIdx.y * (WARPS * MAX_PAIRS);  // gridDim.y splits the tile pairs of large systems
-    int i = 0;
-    if (pair < npairs) {
-      int rem = pair;
-      while (rem >= nt - i) { rem -= nt - i; ++i; }
-      ti[q] = i;
-      tj[q] = i + rem;
-    } else {
-      ti[q] = -1;
-      tj[q] = -1;
+    for (int u = 0; u < SC_UNITS; ++u) {
+      const int slot = (blockIdx.y * WARPS + warp) * SC_UNITS + u;
+      u_ti0[u] = units.ti0[slot]; u_nr[u] = units.nr[slot]; u_tj0[u] = units.tj0[slot]; u_nc[u] = units.nc[slot];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bacc[u][r][c][0] = bacc[u][r][c][1] = 0.0;
     }
-    acc[q][0] = 0.0;
-    acc[q][1] = 0.0;
+  } else {
+#pragma unroll
+    for (int q = 0; q < MAX_PAIRS; ++q) {
+      int pair = warp + q * WARPS + blockIdx.y * (WARPS * MAX_PAIRS);  // gridDim.y splits the tile pairs of large systems
+      int i = 0;
+      if (pair < npairs) {
+        int rem = pair;
+        while (rem >= nt - i) { rem -= nt - i; ++i; }
+        ti[q] = i;
+        tj[q] = i + rem;
+      } else {
+        ti[q] = -1;
+        tj[q] = -1;
+      }
+      acc[q][0] = 0.0;
+      acc[q][1] = 0.0;
+    }
   }
   for (int i = tid; i < 3 * n_pad * SC_LD; i += blockDim.x) Zbuf[i] = 0.0;
   const int s_lo = blockIdx.x * sets_per_cta, s_hi = min(p.n_sets, s_lo + sets_per_cta);
@@ -1465,14 +1493,54 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
     __syncthreads();
   }
   auto reduce = [&](const double* Zs) {
+    if constexpr (BLOCKED) {
 #pragma unroll
-    for (int kk = 0; kk < SC_K / 4; ++kk) {
+      for (int u = 0; u < SC_UNITS; ++u) {
+        if (u_nr[u] == 0) continue;
+        const double* za = Zs + (8 * u_ti0[u] + arow) * SC_LD + acol;
+        const double* zb = Zs + (8 * u_tj0[u] + arow) * SC_LD + acol;
+        const bool diag = u_ti0[u] == u_tj0[u];
+        if (u_nr[u] == 4 && u_nc[u] == 4 && !diag) {  // full rectangle: 8 operand loads, 16 DMMAs per k-step
 #pragma unroll
-      for (int q = 0; q < MAX_PAIRS; ++q) {
-        if (ti[q] >= 0) {
-          const double a = Zs[(8 * ti[q] + arow) * SC_LD + 4 * kk + acol];
-          const double b = Zs[(8 * tj[q] + arow) * SC_LD + 4 * kk + acol];
-          dmma(acc[q][0], acc[q][1], a, b);
+          for (int kk = 0; kk < SC_K / 4; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              a[r] = za[r * 8 * SC_LD + 4 * kk];
+              b[r] = zb[r * 8 * SC_LD + 4 * kk];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) dmma(bacc[u][r][c][0], bacc[u][r][c][1], a[r], b[c]);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < SC_K / 4; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              a[r] = r < u_nr[u] ? za[r * 8 * SC_LD + 4 * kk] : 0.0;
+              b[r] = r < u_nc[u] ? zb[r * 8 * SC_LD + 4 * kk] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (r < u_nr[u] && c < u_nc[u] && (!diag || c >= r)) dmma(bacc[u][r][c][0], bacc[u][r][c][1], a[r], b[c]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < SC_K / 4; ++kk) {
+#pragma unroll
+        for (int q = 0; q < MAX_PAIRS; ++q) {
+          if (ti[q] >= 0) {
+            const double a = Zs[(8 * ti[q] + arow) * SC_LD + 4 * kk + acol];
+            const double b = Zs[(8 * tj[q] + arow) * SC_LD + 4 * kk + acol];
+            dmma(acc[q][0], acc[q][1], a, b);
+          }
         }
       }
     }
@@ -1490,11 +1558,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
     __syncthreads();      // step k + 1 is transformed, step k + 2 has landed (the L factors are shared), step k's buffer is free
   }
   double* out = partials + (size_t)blockIdx.x * n_pad * n_pad;
+  if constexpr (BLOCKED) {
 #pragma unroll
-  for (int q = 0; q < MAX_PAIRS; ++q) {
-    if (ti[q] >= 0) {
-      double* o = out + (size_t)(8 * ti[q] + arow) * n_pad + 8 * tj[q] + 2 * acol;
-      *reinterpret_cast<double2*>(o) = make_double2(acc[q][0], acc[q][1]);
+    for (int u = 0; u < SC_UNITS; ++u) {
+      const bool diag = u_ti0[u] == u_tj0[u];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (r < u_nr[u] && c < u_nc[u] && (!diag || c >= r)) {
+            double* o = out + (size_t)(8 * (u_ti0[u] + r) + arow) * n_pad + 8 * (u_tj0[u] + c) + 2 * acol;
+            *reinterpret_cast<double2*>(o) = make_double2(bacc[u][r][c][0], bacc[u][r][c][1]);
+          }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < MAX_PAIRS; ++q) {
+      if (ti[q] >= 0) {
+        double* o = out + (size_t)(8 * ti[q] + arow) * n_pad + 8 * tj[q] + 2 * acol;
+        *reinterpret_cast<double2*>(o) = make_double2(acc[q][0], acc[q][1]);
+      }
     }
   }
 }
@@ -2757,16 +2840,45 @@ size_t schur_partial_stride(const DevProblem& p) {
   return n_pad * n_pad;
 }
 
-template <int WARPS, int MAX_PAIRS>
+template <int WARPS, int MAX_PAIRS, bool BLOCKED>
 static cudaError_t launch_schur_t(const DevProblem& p, double damping, double* partials, int n_partials, int* flag, StreamCtx& s) {
   const int n_pad = ((p.n_aug + 7) >> 3) * 8;
   const size_t smem = sizeof(double) * (3 * (size_t)n_pad * SC_LD + 3 * SC_SETS * 36);
   static size_t attr_smem_dev[MAX_DEVICES] = {};
-  if (cudaError_t e = ensure_dynamic_smem(schur_kernel<WARPS, MAX_PAIRS>, smem, attr_smem_dev); e != cudaSuccess) return e;
+  if (cudaError_t e = ensure_dynamic_smem(schur_kernel<WARPS, MAX_PAIRS, BLOCKED>, smem, attr_smem_dev); e != cudaSuccess) return e;
   const int nt = (p.n_aug + 7) >> 3;
-  const int npairs = nt * (nt + 1) / 2;
-  const int gy = (npairs + WARPS * MAX_PAIRS - 1) / (WARPS * MAX_PAIRS);
-  if (cudaError_t e = launch_pdl(schur_kernel<WARPS, MAX_PAIRS>, dim3(n_partials, gy), WARPS * 32, smem, s.stream, p, partials, schur_sets_per_cta(p), damping, flag);
+  SchurUnits units;
+  std::memset(&units, 0, sizeof(units));
+  int gy;
+  if (BLOCKED) {
+    // the upper triangle of the nt x nt tile grid in 4 x 4 macro blocks, largest first onto the least loaded warp with a free slot
+    struct Blk { int ti0, nr, tj0, nc, pairs; };
+    std::vector<Blk> blocks;
+    const int ng = (nt + 3) / 4;
+    for (int g = 0; g < ng; ++g)
+      for (int h2 = g; h2 < ng; ++h2) {
+        const int nr = std::min(4, nt - 4 * g), nc = std::min(4, nt - 4 * h2);
+        blocks.push_back({4 * g, nr, 4 * h2, nc, g == h2 ? nr * (nr + 1) / 2 : nr * nc});
+      }
+    std::stable_sort(blocks.begin(), blocks.end(), [](const Blk& a, const Blk& b) { return a.pairs > b.pairs; });
+    gy = ((int)blocks.size() + WARPS * SC_UNITS - 1) / (WARPS * SC_UNITS);
+    if (gy * WARPS * SC_UNITS > SC_MAX_SLOTS) return cudaErrorInvalidValue;
+    const int nw = gy * WARPS;
+    std::vector<int> load(nw, 0), used(nw, 0);
+    for (const Blk& b : blocks) {
+      int best = -1;
+      for (int w = 0; w < nw; ++w)
+        if (used[w] < SC_UNITS && (best < 0 || load[w] < load[best])) best = w;
+      const int slot = best * SC_UNITS + used[best]++;
+      load[best] += b.pairs;
+      units.ti0[slot] = (unsigned char)b.ti0; units.nr[slot] = (unsigned char)b.nr; units.tj0[slot] = (unsigned char)b.tj0; units.nc[slot] = (unsigned char)b.nc;
+    }
+  } else {
+    const int npairs = nt * (nt + 1) / 2;
+    gy = (npairs + WARPS * MAX_PAIRS - 1) / (WARPS * MAX_PAIRS);
+  }
+  if (cudaError_t e = launch_pdl(schur_kernel<WARPS, MAX_PAIRS, BLOCKED>, dim3(n_partials, gy), WARPS * 32, smem, s.stream, p, partials, schur_sets_per_cta(p), damping, flag,
+                                 units);
       e != cudaSuccess)
     return e;
   KB_LAUNCHED(s);
@@ -2777,11 +2889,11 @@ cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, 
   // every CTA writes all of its tile pairs (zeros when it has no sets), so the partials need no clearing; the 6x6 pose factors are
   // computed by the CTAs themselves
   const int nt = (p.n_aug + 7) >> 3;
-  if (nt <= 6) return launch_schur_t<8, 3>(p, damping, partials, n_partials, flag, s);
-  static const int variant = getenv("KB_SCHUR_VARIANT") ? atoi(getenv("KB_SCHUR_VARIANT")) : 0;  // experiments
-  if (variant == 1) return launch_schur_t<16, 7>(p, damping, partials, n_partials, flag, s);
-  if (variant == 2) return launch_schur_t<12, 9>(p, damping, partials, n_partials, flag, s);
-  return launch_schur_t<8, 14>(p, damping, partials, n_partials, flag, s);  // nt <= 14: one CTA per slice; larger systems: tile pairs split over gridDim.y
+  if (nt <= 6) return launch_schur_t<8, 3, false>(p, damping, partials, n_partials, flag, s);
+  // measured (profiles/r02_schur_variants.md): up to 14 tiles a side the scattered assignment on 16 warps wins; beyond that the tile pairs
+  // no longer fit one CTA and the macro-block assignment halves the number of CTAs that redo the fetch + transform of a slice
+  if (nt <= 14) return launch_schur_t<16, 7, false>(p, damping, partials, n_partials, flag, s);
+  return launch_schur_t<8, 1, true>(p, damping, partials, n_partials, flag, s);  // 4 x 4 macro blocks of tile pairs per warp; large systems split over gridDim.y
 }
 
 cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const double* partials, int n_partials, bool, StreamCtx& s) {
