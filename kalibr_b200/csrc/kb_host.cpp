@@ -3,6 +3,8 @@
 // sequence of LinearSystemSolver (evaluate -> build -> setConditioner -> solve -> update/revert), NCCL plumbing for
 // the reduced system, and the export of the Hessian block pattern / CCS Jacobian structure for parity checks.
 // There is no CPU compute path in here: every number comes from the kernels in kb_kernels.cu.
+#include <atomic>
+#include <thread>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -682,13 +684,16 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   trace.mark("device, streams, events");
   // ---- local views / terms ----
   const int n_local_sets = h->set_hi - h->set_lo;
-  std::vector<double> yu, yv;
+  std::vector<double> yu, yv;  // only filled when the local terms are not one contiguous run of the caller's arrays
   std::vector<uint16_t> corner;
   std::vector<int>& vs = h->h_view_set;
   std::vector<int>& vc = h->h_view_cam;
   std::vector<int>& vb = h->h_view_begin;
   vb.push_back(0);
   std::vector<char> seen((size_t)n_local_sets * d->n_cams, 0);
+  std::vector<int64_t> src_begin;  // per local view: where its terms start in the caller's arrays
+  bool contiguous = true;          // the local views' term ranges follow each other in the caller's arrays
+  int64_t n_local_terms = 0;
   for (int w = 0; w < d->n_views; ++w) {
     const int k = d->view_cam[w];
     if (d->view_set[w] < 0 || d->view_set[w] >= d->n_sets || k < 0 || k >= d->n_cams) return cfail(KB_ERR_INVALID_ARGUMENT, "view index out of range");
@@ -701,18 +706,50 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     seen[(size_t)lv * d->n_cams + k] = 1;
     vs.push_back(lv);
     vc.push_back(k);
-    for (int64_t i = b; i < e; ++i) {
-      if (d->corner_id[i] < 0 || d->corner_id[i] >= d->n_target_points) return cfail(KB_ERR_INVALID_ARGUMENT, "corner_id out of range");
-      yu.push_back(d->y_u[i]);
-      yv.push_back(d->y_v[i]);
-      corner.push_back((uint16_t)d->corner_id[i]);
-    }
-    if (yu.size() > (size_t)0x7fffffff) return cfail(KB_ERR_INVALID_ARGUMENT, "more than 2^31 terms on one rank");
-    vb.push_back((int)yu.size());
+    if (!src_begin.empty() && b != src_begin.back() + (n_local_terms - vb[vb.size() - 2])) contiguous = false;
+    src_begin.push_back(b);
+    n_local_terms += e - b;
+    if (n_local_terms > (int64_t)0x7fffffff) return cfail(KB_ERR_INVALID_ARGUMENT, "more than 2^31 terms on one rank");
+    vb.push_back((int)n_local_terms);
   }
-  h->n_terms_local = (int64_t)yu.size();
-
-  h->n_terms_local = (int64_t)yu.size();
+  h->n_terms_local = n_local_terms;
+  // the observations: validated and narrowed (corner ids) / gathered (measurements, only when needed) by a few host threads
+  corner.resize((size_t)n_local_terms);
+  if (!contiguous) {
+    yu.resize((size_t)n_local_terms);
+    yv.resize((size_t)n_local_terms);
+  }
+  {
+    const int n_lv = (int)src_begin.size();
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)8, n_local_terms / 200000 + 1}));
+    std::atomic<int> bad{0};
+    auto work = [&](int t) {
+      const int lo = (int)((int64_t)n_lv * t / n_thr), hi = (int)((int64_t)n_lv * (t + 1) / n_thr);
+      for (int j = lo; j < hi; ++j) {
+        const int64_t sb = src_begin[j];
+        const int o = vb[j], cnt = vb[j + 1] - vb[j];
+        const int32_t* cid = d->corner_id + sb;
+        uint16_t* dst = corner.data() + o;
+        int flag = 0;
+        for (int i = 0; i < cnt; ++i) {
+          flag |= (cid[i] < 0) | (cid[i] >= d->n_target_points);
+          dst[i] = (uint16_t)cid[i];
+        }
+        if (flag) bad.store(1);
+        if (!contiguous && cnt > 0) {
+          std::memcpy(yu.data() + o, d->y_u + sb, sizeof(double) * (size_t)cnt);
+          std::memcpy(yv.data() + o, d->y_v + sb, sizeof(double) * (size_t)cnt);
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_thr; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    if (bad.load()) return cfail(KB_ERR_INVALID_ARGUMENT, "corner_id out of range");
+  }
+  const double* src_u = contiguous ? (src_begin.empty() ? nullptr : d->y_u + src_begin[0]) : yu.data();
+  const double* src_v = contiguous ? (src_begin.empty() ? nullptr : d->y_v + src_begin[0]) : yv.data();
   trace.mark("host copy of the structure");
   // ---- upload: observations, target, state ----
   cudaStream_t s = h->stream;
@@ -726,8 +763,12 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     const double* sp = d->set_poses + (presharded ? 0 : (size_t)KB_POSE_STRIDE * h->set_lo);
     sets.assign(sp, sp + (size_t)KB_POSE_STRIDE * n_local_sets);
   }
-  KB_CCUDA(h->y_u.upload(yu, s));
-  KB_CCUDA(h->y_v.upload(yv, s));
+  KB_CCUDA(h->y_u.alloc((size_t)n_local_terms));
+  KB_CCUDA(h->y_v.alloc((size_t)n_local_terms));
+  if (n_local_terms > 0) {  // straight from the caller's (pageable) arrays when the local terms are one contiguous run of them
+    KB_CCUDA(cudaMemcpyAsync(h->y_u.p, src_u, sizeof(double) * (size_t)n_local_terms, cudaMemcpyHostToDevice, s));
+    KB_CCUDA(cudaMemcpyAsync(h->y_v.p, src_v, sizeof(double) * (size_t)n_local_terms, cudaMemcpyHostToDevice, s));
+  }
   KB_CCUDA(h->corner.upload(corner, s));
   KB_CCUDA(h->target.upload(target, s));
   KB_CCUDA(h->cam_params.upload(cam, s));
