@@ -12,7 +12,7 @@ LIB = os.path.join(ROOT, "kalibr_b200", "libkalibr_b200.so")
 prefix = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02")
 # (file tag, substring of the mangled name)
 KERNELS = [("linearise_assemble_pinhole_radtan", "linearise_assemble_kernelILi0ELb1ELb0E"), ("linearise_materialise_pinhole_radtan", "linearise_materialise_kernelILi0ELb0E"),
-           ("set_reduce", "set_reduce_kernel"), ("schur_8x14", "schur_kernelILi8ELi14E"), ("reduced_solve", "reduced_solve_kernel"), ("sym_eig", "sym_eig_kernel")]
+           ("set_reduce", "set_reduce_kernel"), ("schur_16x7", "schur_kernelILi16ELi7ELb0E"), ("schur_blocked", "schur_kernelILi8ELi1ELb1E"), ("reduced_solve", "reduced_solve_kernel"), ("sym_eig", "sym_eig_kernel")]
 text = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 res = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", text)
