@@ -318,29 +318,38 @@ __global__ void prep_kernel(DevProblem p) {
 
 // per synced set: inverse pose (C^-1, -C^-1 t) and P_v, shared by the views of every camera of the set
 // with_cam_prep: one extra block at the end of the grid computes the per-camera constants (prep_kernel's work) in the same launch
-__global__ void __launch_bounds__(128) set_prep_kernel(DevProblem p, int with_cam_prep) {
+constexpr int SET_PREP_THREADS = 64;
+__global__ void __launch_bounds__(SET_PREP_THREADS) set_prep_kernel(DevProblem p, int with_cam_prep) {
   pdl_enter();
+  // thread per set; the 48 values of a set go through shared memory so that the block writes its rows as one coalesced run
+  __shared__ double stage[SET_PREP_THREADS][SETPREP_STRIDE + 1];
   if (p.ctrl->done || p.ctrl->skip_eval) return;
   if (with_cam_prep && blockIdx.x == gridDim.x - 1) {
     if (threadIdx.x < p.n_cams) camera_prep(p, threadIdx.x);
     return;
   }
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= p.n_sets) return;
-  const double* pose = p.set_poses + (size_t)s * POSE_STRIDE;
-  double C[9], Ci[9];
-  quat2r(pose, C);
-  inv3(C, Ci);
-  const double t[3] = {pose[4], pose[5], pose[6]};
-  const double ti[3] = {-(Ci[0] * t[0] + Ci[1] * t[1] + Ci[2] * t[2]), -(Ci[3] * t[0] + Ci[4] * t[1] + Ci[5] * t[2]), -(Ci[6] * t[0] + Ci[7] * t[1] + Ci[8] * t[2])};
-  double* o = p.set_prep + (size_t)s * SETPREP_STRIDE;
-  for (int i = 0; i < 9; ++i) o[i] = Ci[i];
-  for (int i = 0; i < 3; ++i) o[9 + i] = ti[i];
-  double bt[36], M[36], Pv[36];
-  box_times(Ci, ti, bt);
-  pose_jac(t, M);
-  mul6(bt, M, Pv);
-  for (int i = 0; i < 36; ++i) o[12 + i] = -Pv[i];
+  const int s0 = blockIdx.x * SET_PREP_THREADS;
+  const int s = s0 + threadIdx.x;
+  if (s < p.n_sets) {
+    const double* pose = p.set_poses + (size_t)s * POSE_STRIDE;
+    double C[9], Ci[9];
+    quat2r(pose, C);
+    inv3(C, Ci);
+    const double t[3] = {pose[4], pose[5], pose[6]};
+    const double ti[3] = {-(Ci[0] * t[0] + Ci[1] * t[1] + Ci[2] * t[2]), -(Ci[3] * t[0] + Ci[4] * t[1] + Ci[5] * t[2]), -(Ci[6] * t[0] + Ci[7] * t[1] + Ci[8] * t[2])};
+    double* o = stage[threadIdx.x];
+    for (int i = 0; i < 9; ++i) o[i] = Ci[i];
+    for (int i = 0; i < 3; ++i) o[9 + i] = ti[i];
+    double bt[36], M[36], Pv[36];
+    box_times(Ci, ti, bt);
+    pose_jac(t, M);
+    mul6(bt, M, Pv);
+    for (int i = 0; i < 36; ++i) o[12 + i] = -Pv[i];
+  }
+  __syncthreads();
+  const int n_here = min(SET_PREP_THREADS, p.n_sets - s0);
+  double* out = p.set_prep + (size_t)s0 * SETPREP_STRIDE;
+  for (int i = threadIdx.x; i < n_here * SETPREP_STRIDE; i += SET_PREP_THREADS) out[i] = stage[i / SETPREP_STRIDE][i % SETPREP_STRIDE];
 }
 
 // T_cam_w from the per-set inverse pose and the per-camera chain
@@ -2379,6 +2388,7 @@ __device__ __forceinline__ void solve_scalars_stage2(LmCtrl* __restrict__ ctrl, 
 // =========================================================================================================
 // partial (may be null): [gridDim.x][2] = per block (sum over its sets of dx_v^T (lambda dx_v + b_v), max |dx_v|); block 0 adds the
 // camera-side part (dx_c^T b_c of this rank, + lambda |dx_c|^2 when include_shared) - stage 1 of the rho denominator for free
+constexpr int BS_SETS = 1;  // sets per warp (4 was measured: slower, 0.046 -> 0.052 ms at 20 000 sets)
 __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* __restrict__ set_col_q, const int* __restrict__ set_col_t,
                                                       const int* __restrict__ cam_cols, double lambda_arg, int include_shared,
                                                       double* __restrict__ partial, double* __restrict__ out2, PeerXchg px,
@@ -2403,8 +2413,10 @@ __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* _
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
   }
-  const int set = gw;
-  if (set < p.n_sets) {
+  // BS_SETS consecutive sets per warp: fewer, longer-lived blocks (each block ends with a fence + ticket)
+  for (int j = 0; j < BS_SETS; ++j) {
+  const int set = gw * BS_SETS + j;
+  if (set >= p.n_sets) break;
   double acc[6] = {0, 0, 0, 0, 0, 0};
   const double* W = p.W + (size_t)set * p.n_c * 6;
   for (int i = lane; i < p.n_c; i += 32) {
@@ -2446,7 +2458,7 @@ __global__ void __launch_bounds__(256) backsub_kernel(DevProblem p, const int* _
       pm = fmax(pm, fabs(r[c]));
     }
   }
-  }
+    }
   if (!partial) return;
   if (lane == 0) { sh_s[wib] = ps; sh_m[wib] = pm; }
   __syncthreads();
@@ -2533,41 +2545,47 @@ __global__ void __launch_bounds__(256) apply_update_kernel(DevProblem p, const i
   if (p.ctrl->done || p.ctrl->skip_eval) return;
   // device-resident loop: a rejected step is undone lazily, here (the backup IS the state to start from) - outside the loop the flag is 0
   const bool restore = p.ctrl->revert != 0;
-  if (idx < p.n_sets) {
+  if (idx < p.n_sets && blockIdx.x != gridDim.x - 1) {
     double* pose = p.set_poses + (size_t)idx * POSE_STRIDE;
     double* bk = backup_sets + (size_t)idx * POSE_STRIDE;
+    const int cq = set_col_q[idx], ct = set_col_t[idx];
+    double q[POSE_STRIDE], dq[3], dt[3];
 #pragma unroll
-    for (int i = 0; i < POSE_STRIDE; ++i) {
-      if (restore) pose[i] = bk[i];
-      else bk[i] = pose[i];
+    for (int i = 0; i < POSE_STRIDE; ++i) q[i] = restore ? bk[i] : pose[i];  // all loads first: nothing below aliases them
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { dq[c] = p.dx[cq + c]; dt[c] = p.dx[ct + c]; }
+    if (!restore) {
+#pragma unroll
+      for (int i = 0; i < POSE_STRIDE; ++i) bk[i] = q[i];
     }
-    double dq[3], dt[3];
+    update_quat(q, dq);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { dq[c] = p.dx[set_col_q[idx] + c]; dt[c] = p.dx[set_col_t[idx] + c]; }
-    update_quat(pose, dq);
+    for (int c = 0; c < 3; ++c) q[4 + c] += dt[c];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) pose[4 + c] += dt[c];
+    for (int i = 0; i < POSE_STRIDE; ++i) pose[i] = q[i];
   }
-  if (blockIdx.x == 0) {
-    for (int k = threadIdx.x; k < p.n_cams; k += blockDim.x) {
-      const int PD = p.cam_P[k] + p.cam_D[k];
-      for (int c = 0; c < CAM_PARAM_STRIDE; ++c) {
-        const double v = restore ? backup_cam[k * CAM_PARAM_STRIDE + c] : p.cam_params[k * CAM_PARAM_STRIDE + c];
-        backup_cam[k * CAM_PARAM_STRIDE + c] = v;
-        p.cam_params[k * CAM_PARAM_STRIDE + c] = v;
-        if (c < PD) p.cam_params[k * CAM_PARAM_STRIDE + c] = v + p.dxc[p.intr_off[k] + c];
-      }
+  if (blockIdx.x == gridDim.x - 1) {  // the camera-side design variables: a block of their own, a thread per parameter / per baseline
+    for (int i = threadIdx.x; i < p.n_cams * CAM_PARAM_STRIDE; i += blockDim.x) {
+      const int k = i / CAM_PARAM_STRIDE, c = i - k * CAM_PARAM_STRIDE;
+      const double v = restore ? backup_cam[i] : p.cam_params[i];
+      backup_cam[i] = v;
+      p.cam_params[i] = c < p.cam_P[k] + p.cam_D[k] ? v + p.dxc[p.intr_off[k] + c] : v;
     }
     for (int j = threadIdx.x; j < p.n_cams - 1; j += blockDim.x) {
       double* b = p.baselines + j * POSE_STRIDE;
-      for (int i = 0; i < POSE_STRIDE; ++i) {
-        if (restore) b[i] = backup_base[j * POSE_STRIDE + i];
-        else backup_base[j * POSE_STRIDE + i] = b[i];
-      }
-      double dq[3];
-      for (int c = 0; c < 3; ++c) dq[c] = p.dxc[p.base_off[j] + c];
-      update_quat(b, dq);
-      for (int c = 0; c < 3; ++c) b[4 + c] += p.dxc[p.base_off[j] + 3 + c];
+      double q[POSE_STRIDE], dq[3], dt[3];
+#pragma unroll
+      for (int i = 0; i < POSE_STRIDE; ++i) q[i] = restore ? backup_base[j * POSE_STRIDE + i] : b[i];
+      const int off = p.base_off[j];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { dq[c] = p.dxc[off + c]; dt[c] = p.dxc[off + 3 + c]; }
+#pragma unroll
+      for (int i = 0; i < POSE_STRIDE; ++i) backup_base[j * POSE_STRIDE + i] = q[i];
+      update_quat(q, dq);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) q[4 + c] += dt[c];
+#pragma unroll
+      for (int i = 0; i < POSE_STRIDE; ++i) b[i] = q[i];
     }
   }
 }
@@ -2748,7 +2766,8 @@ cudaError_t launch_linearise_assemble(const DevProblem& p, const int4* vmeta, co
                                       bool with_cam_prep, StreamCtx& s) {
   cudaError_t e;
   if ((with_set_prep && p.n_sets > 0) || with_cam_prep) {  // per-set constants and (extra block) per-camera constants in one launch
-    if ((e = launch_pdl(set_prep_kernel, (with_set_prep ? (p.n_sets + 127) / 128 : 0) + (with_cam_prep ? 1 : 0), 128, 0, s.stream, p, with_cam_prep ? 1 : 0)) != cudaSuccess) return e;
+    if ((e = launch_pdl(set_prep_kernel, (with_set_prep ? (p.n_sets + SET_PREP_THREADS - 1) / SET_PREP_THREADS : 0) + (with_cam_prep ? 1 : 0), SET_PREP_THREADS, 0, s.stream, p,
+                        with_cam_prep ? 1 : 0)) != cudaSuccess) return e;
     KB_LAUNCHED(s);
   }
   e = for_each_model_concurrently(smb, s, [&](int m, StreamCtx& c) -> cudaError_t {
@@ -2799,7 +2818,7 @@ cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta,
                                          unsigned int* counters, double* jt, StreamCtx& s) {
   cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * NUM_MODELS, s.stream);
   if (e != cudaSuccess) return e;
-  set_prep_kernel<<<(p.n_sets + 127) / 128 + 1, 128, 0, s.stream>>>(p, 1);  // per-set and (last block) per-camera constants
+  set_prep_kernel<<<(p.n_sets + SET_PREP_THREADS - 1) / SET_PREP_THREADS + 1, SET_PREP_THREADS, 0, s.stream>>>(p, 1);  // per-set and (last block) per-camera constants
   KB_LAUNCHED(s);
   e = for_each_model_concurrently(smb, s, [&](int m, StreamCtx& c) -> cudaError_t {
     switch (m) {
@@ -2927,7 +2946,7 @@ cudaError_t launch_reduced_solve(const DevProblem& p, double damping, int* pos_d
   return cudaGetLastError();
 }
 
-int backsub_blocks(const DevProblem& p) { return ((p.n_sets > 0 ? p.n_sets : 1) * 32 + 255) / 256; }
+int backsub_blocks(const DevProblem& p) { return ((p.n_sets > 0 ? p.n_sets : 1) + 8 * BS_SETS - 1) / (8 * BS_SETS); }
 // back substitution; its blocks also leave the stage-1 partials of the rho denominator / max|dx| in p.rho_partial.
 // out2 (optional) = (dx^T (lambda dx + rhs), max|dx|) of this rank, written by the last block; it is also the producer of peer
 // exchange B when pos_def_for_exchange is given; lm_mode 1: + the after-solve transition of the device-resident loop (single rank)
@@ -3080,7 +3099,7 @@ cudaError_t launch_widen_observations(const float* su, const float* sv, double* 
 cudaError_t launch_apply_update(const DevProblem& p, const int* set_col_q, const int* set_col_t, const int*, double* backup_cam, double* backup_base,
                                 double* backup_sets, StreamCtx& s) {
   const int n = p.n_sets > 0 ? p.n_sets : 1;
-  if (cudaError_t e = launch_pdl(apply_update_kernel, (n + 255) / 256, 256, 0, s.stream, p, set_col_q, set_col_t, backup_cam, backup_base, backup_sets); e != cudaSuccess) return e;
+  if (cudaError_t e = launch_pdl(apply_update_kernel, (n + 255) / 256 + 1, 256, 0, s.stream, p, set_col_q, set_col_t, backup_cam, backup_base, backup_sets); e != cudaSuccess) return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
