@@ -1396,7 +1396,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
   const int arow = lane >> 2, acol = lane & 3;
   const int npairs = nt * (nt + 1) / 2;
   // !BLOCKED: tile pairs of this warp (upper triangle, row-major enumeration)
-  int ti[BLOCKED ? 1 : MAX_PAIRS], tj[BLOCKED ? 1 : MAX_PAIRS];
+  int ti[BLOCKED ? 1 : MAX_PAIRS], tj[BLOCKED ? 1 : MAX_PAIRS], offA[BLOCKED ? 1 : MAX_PAIRS], offB[BLOCKED ? 1 : MAX_PAIRS];
   double acc[BLOCKED ? 1 : MAX_PAIRS][2];
   // BLOCKED: the warp's rectangles
   int u_ti0[SC_UNITS], u_nr[SC_UNITS], u_tj0[SC_UNITS], u_nc[SC_UNITS];
@@ -1425,6 +1425,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
         ti[q] = -1;
         tj[q] = -1;
       }
+      offA[q] = (8 * max(ti[q], 0) + arow) * SC_LD + acol;
+      offB[q] = (8 * max(tj[q], 0) + arow) * SC_LD + acol;
       acc[q][0] = 0.0;
       acc[q][1] = 0.0;
     }
@@ -1437,10 +1439,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
     for (int set = s_lo + tid; set < s_hi; set += blockDim.x) pose_factor(p, set, damping, pos_def_flag);
   }
   __syncthreads();
+  // the rows this thread copies and transforms in every step: o = tid + i * blockDim  ->  (set of the step, row); computed once
+  // (the integer divisions by the runtime n were a fifth of the instructions of a step)
+  constexpr int SC_MAX_ROWS = (SC_SETS * 256 + WARPS * 32 - 1) / (WARPS * 32);  // n <= 256
+  int row_which[SC_MAX_ROWS], row_r[SC_MAX_ROWS];
+#pragma unroll
+  for (int i = 0; i < SC_MAX_ROWS; ++i) {
+    const int o = tid + i * WARPS * 32;
+    row_which[i] = o < SC_SETS * n ? o / n : -1;
+    row_r[i] = o - max(row_which[i], 0) * n;
+  }
   // raw rows of the sets [s0, s0 + SC_SETS) -> Zs, their inverse factors -> Ls  (asynchronous; rows of sets past the end are zeroed)
   auto fetch = [&](double* Zs, double* Ls, int s0) {
-    for (int o = tid; o < SC_SETS * n; o += blockDim.x) {
-      const int which = o / n, r = o - which * n;
+#pragma unroll
+    for (int i = 0; i < SC_MAX_ROWS; ++i) {
+      const int which = row_which[i], r = row_r[i];
+      if (which < 0) continue;
       const int set = s0 + which;
       double* dst = Zs + r * SC_LD + which * 6;
       if (set < s_hi) {
@@ -1453,16 +1467,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
         for (int c = 0; c < 6; ++c) dst[c] = 0.0;
       }
     }
-    for (int o = tid; o < SC_SETS * 18; o += blockDim.x) {
-      const int which = o / 18, q = o - which * 18;
+    if (tid < SC_SETS * 18) {
+      const int which = tid / 18, q = tid - which * 18;
       if (s0 + which < s_hi) cp_async_16(Ls + which * 36 + 2 * q, p.Lv + (size_t)(s0 + which) * 36 + 2 * q);
     }
     cp_async_commit();
   };
   // in place: z = Linv * w for the rows this thread fetched (same index mapping as fetch)
   auto transform = [&](double* Zs, const double* Ls, int s0) {
-    for (int o = tid; o < SC_SETS * n; o += blockDim.x) {
-      const int which = o / n, r = o - which * n;
+#pragma unroll
+    for (int i = 0; i < SC_MAX_ROWS; ++i) {
+      const int which = row_which[i], r = row_r[i];
+      if (which < 0) continue;
       const int set = s0 + which;
       if (set >= s_hi) continue;
       double* zr = Zs + r * SC_LD + which * 6;
@@ -1472,11 +1488,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
       *reinterpret_cast<double2*>(w + 2) = *reinterpret_cast<const double2*>(zr + 2);
       *reinterpret_cast<double2*>(w + 4) = *reinterpret_cast<const double2*>(zr + 4);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
+      for (int i2 = 0; i2 < 6; ++i2) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k <= i; ++k) t += Li[i * 6 + k] * w[k];
-        z[i] = t;
+        for (int k = 0; k <= i2; ++k) t += Li[i2 * 6 + k] * w[k];
+        z[i2] = t;
       }
       *reinterpret_cast<double2*>(zr) = make_double2(z[0], z[1]);
       *reinterpret_cast<double2*>(zr + 2) = make_double2(z[2], z[3]);
@@ -1545,9 +1561,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
       for (int kk = 0; kk < SC_K / 4; ++kk) {
 #pragma unroll
         for (int q = 0; q < MAX_PAIRS; ++q) {
-          if (ti[q] >= 0) {
-            const double a = Zs[(8 * ti[q] + arow) * SC_LD + 4 * kk + acol];
-            const double b = Zs[(8 * tj[q] + arow) * SC_LD + 4 * kk + acol];
+          if (ti[q] >= 0) {  // (an unpredicated loop with dummy pairs in the empty slots was measured: no faster)
+            const double a = Zs[offA[q] + 4 * kk];  // operand offsets computed once: the k-step is an immediate of the load
+            const double b = Zs[offB[q] + 4 * kk];
             dmma(acc[q][0], acc[q][1], a, b);
           }
         }
@@ -2871,27 +2887,39 @@ static cudaError_t launch_schur_t(const DevProblem& p, double damping, double* p
   int gy;
   if (BLOCKED) {
     // the upper triangle of the nt x nt tile grid in 4 x 4 macro blocks, largest first onto the least loaded warp with a free slot
-    struct Blk { int ti0, nr, tj0, nc, pairs; };
-    std::vector<Blk> blocks;
-    const int ng = (nt + 3) / 4;
-    for (int g = 0; g < ng; ++g)
-      for (int h2 = g; h2 < ng; ++h2) {
-        const int nr = std::min(4, nt - 4 * g), nc = std::min(4, nt - 4 * h2);
-        blocks.push_back({4 * g, nr, 4 * h2, nc, g == h2 ? nr * (nr + 1) / 2 : nr * nc});
+    // (computed once per system size and thread)
+    thread_local int cached_nt = -1, cached_gy = 0;
+    thread_local SchurUnits cached;
+    if (cached_nt != nt) {
+      struct Blk { int ti0, nr, tj0, nc, pairs; };
+      std::vector<Blk> blocks;
+      const int ng = (nt + 3) / 4;
+      for (int g = 0; g < ng; ++g)
+        for (int h2 = g; h2 < ng; ++h2) {
+          const int nr = std::min(4, nt - 4 * g), nc = std::min(4, nt - 4 * h2);
+          blocks.push_back({4 * g, nr, 4 * h2, nc, g == h2 ? nr * (nr + 1) / 2 : nr * nc});
+        }
+      std::stable_sort(blocks.begin(), blocks.end(), [](const Blk& a, const Blk& b) { return a.pairs > b.pairs; });
+      const int gy_new = ((int)blocks.size() + WARPS * SC_UNITS - 1) / (WARPS * SC_UNITS);
+      if (gy_new * WARPS * SC_UNITS > SC_MAX_SLOTS) return cudaErrorInvalidValue;
+      const int nw = gy_new * WARPS;
+      std::vector<int> load(nw, 0), used(nw, 0);
+      SchurUnits u;
+      std::memset(&u, 0, sizeof(u));
+      for (const Blk& b : blocks) {
+        int best = -1;
+        for (int w = 0; w < nw; ++w)
+          if (used[w] < SC_UNITS && (best < 0 || load[w] < load[best])) best = w;
+        const int slot = best * SC_UNITS + used[best]++;
+        load[best] += b.pairs;
+        u.ti0[slot] = (unsigned char)b.ti0; u.nr[slot] = (unsigned char)b.nr; u.tj0[slot] = (unsigned char)b.tj0; u.nc[slot] = (unsigned char)b.nc;
       }
-    std::stable_sort(blocks.begin(), blocks.end(), [](const Blk& a, const Blk& b) { return a.pairs > b.pairs; });
-    gy = ((int)blocks.size() + WARPS * SC_UNITS - 1) / (WARPS * SC_UNITS);
-    if (gy * WARPS * SC_UNITS > SC_MAX_SLOTS) return cudaErrorInvalidValue;
-    const int nw = gy * WARPS;
-    std::vector<int> load(nw, 0), used(nw, 0);
-    for (const Blk& b : blocks) {
-      int best = -1;
-      for (int w = 0; w < nw; ++w)
-        if (used[w] < SC_UNITS && (best < 0 || load[w] < load[best])) best = w;
-      const int slot = best * SC_UNITS + used[best]++;
-      load[best] += b.pairs;
-      units.ti0[slot] = (unsigned char)b.ti0; units.nr[slot] = (unsigned char)b.nr; units.tj0[slot] = (unsigned char)b.tj0; units.nc[slot] = (unsigned char)b.nc;
+      cached = u;
+      cached_gy = gy_new;
+      cached_nt = nt;
     }
+    units = cached;
+    gy = cached_gy;
   } else {
     const int npairs = nt * (nt + 1) / 2;
     gy = (npairs + WARPS * MAX_PAIRS - 1) / (WARPS * MAX_PAIRS);
