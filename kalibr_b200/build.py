@@ -8,7 +8,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libkalibr_b200.so")
 SOURCES = ["kb_kernels.cu", "kb_init.cu", "kb_host.cpp"]
-HEADERS = ["kb_device.cuh", "kb_models.cuh", "../../include/kalibr_b200.h", "../../include/kalibr_b200/optimizer.hpp"]
+HEADERS = ["kb_device.cuh", "kb_models.cuh", "../../include/kalibr_b200.h", "../../include/kalibr_b200/optimizer.hpp", "../../include/kalibr_b200/lm_state_machine.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

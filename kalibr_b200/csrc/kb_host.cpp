@@ -765,7 +765,34 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
   }
   KB_CCUDA(h->y_u.alloc((size_t)n_local_terms));
   KB_CCUDA(h->y_v.alloc((size_t)n_local_terms));
-  if (n_local_terms > 0) {  // straight from the caller's (pageable) arrays when the local terms are one contiguous run of them
+  // the measurements go straight from the caller's (pageable) arrays when the local terms are one contiguous run of them; large
+  // ones on two helper threads with a stream each (a pageable copy occupies its calling thread with the staging), while this thread
+  // goes on with the allocations and tables below.  The guard joins them on every path out of this function, before the handle dies.
+  struct UploadThreads {
+    std::thread t[2];
+    cudaError_t err[2] = {cudaSuccess, cudaSuccess};
+    void join() { for (auto& x : t) if (x.joinable()) x.join(); }
+    ~UploadThreads() { join(); }
+  } up;
+  if (n_local_terms > (int64_t)1 << 20) {
+    const size_t bytes = sizeof(double) * (size_t)n_local_terms;
+    const int dev = h->device;
+    double *du = h->y_u.p, *dv = h->y_v.p;
+    cudaStream_t s0 = h->copy_stream, s1 = h->model_stream[0];
+    cudaError_t* er = up.err;
+    up.t[0] = std::thread([=] {
+      cudaError_t e = cudaSetDevice(dev);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(du, src_u, bytes, cudaMemcpyHostToDevice, s0);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
+      er[0] = e;
+    });
+    up.t[1] = std::thread([=] {
+      cudaError_t e = cudaSetDevice(dev);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dv, src_v, bytes, cudaMemcpyHostToDevice, s1);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s1);
+      er[1] = e;
+    });
+  } else if (n_local_terms > 0) {
     KB_CCUDA(cudaMemcpyAsync(h->y_u.p, src_u, sizeof(double) * (size_t)n_local_terms, cudaMemcpyHostToDevice, s));
     KB_CCUDA(cudaMemcpyAsync(h->y_v.p, src_v, sizeof(double) * (size_t)n_local_terms, cudaMemcpyHostToDevice, s));
   }
@@ -824,6 +851,9 @@ kb_status kb_create(const kb_problem_desc* d, kb_handle** out) {
     int r = g_nccl.CommInitRank(&h->comm, d->n_ranks, id, d->rank);
     if (r != 0) return cfail(KB_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
   }
+  up.join();
+  KB_CCUDA(up.err[0]);
+  KB_CCUDA(up.err[1]);
   KB_CCUDA(cudaStreamSynchronize(s));
   trace.mark("nccl, synchronise");
 #undef KB_CCUDA
