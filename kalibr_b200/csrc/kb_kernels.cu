@@ -1150,7 +1150,7 @@ __global__ void __launch_bounds__(GRAM_TILES * FG_GROUPS) finalize_gram_kernel(D
     const int lo = cam_slice_range[(k * n_ranges + r) * 2], hi = cam_slice_range[(k * n_ranges + r) * 2 + 1];
     const int per = (hi - lo + FG_GROUPS - 1) / FG_GROUPS;
     const int a = lo + g * per, b = min(hi, a + per);
-#pragma unroll 8
+#pragma unroll 16
     for (int sl = a; sl < b; ++sl) s += p.gram_partial[(size_t)sl * GRAM_TILES + t];
   }
   sh[g][t] = s;
@@ -1608,25 +1608,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
 }
 
 // Sred = U - sum_partials (fixed order), symmetric, undamped; this rank's contribution to the all-reduce.
+constexpr int SF_LANES = 16;
 __global__ void __launch_bounds__(256) schur_finalize_kernel(DevProblem p, const double* __restrict__ partials, int n_partials) {
   pdl_enter();
   const int n = p.n_aug;
   const int n_pad = ((n + 7) >> 3) * 8;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int idx = t >> 2, seg = t & 3;  // four lanes per element, each a quarter of the partials; combined in a fixed order
+  // SF_LANES lanes per element, each a contiguous share of the partials (all of its loads in flight at once); combined in a fixed order
+  const int idx = t / SF_LANES, seg = t % SF_LANES;
   const int i = idx / n, j = idx - i * n;
   const bool live = idx < n * n && i <= j && !p.ctrl->done;
   // within a diagonal tile only the mma's own (i,j) entry is used for i<=j, so the result is exactly symmetric
   double s = 0.0;
   if (live) {
-    const int per = (n_partials + 3) >> 2;
+    const int per = (n_partials + SF_LANES - 1) / SF_LANES;
     const int c0 = seg * per, c1 = min(n_partials, c0 + per);
     const double* src = partials + (size_t)i * n_pad + j;
-#pragma unroll 8
+#pragma unroll 10
     for (int c = c0; c < c1; ++c) s += src[(size_t)c * n_pad * n_pad];
   }
-  s += __shfl_down_sync(0xffffffffu, s, 2);
-  s += __shfl_down_sync(0xffffffffu, s, 1);
+#pragma unroll
+  for (int o = SF_LANES / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   if (!p.px.enabled) {
     if (live && seg == 0) {
       const double v = p.U[(size_t)i * n + j] - s;
@@ -2945,7 +2947,7 @@ cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, 
 
 cudaError_t launch_schur_finalize(const DevProblem& p, double /*damping*/, const double* partials, int n_partials, bool, StreamCtx& s) {
   const int n2 = p.n_aug * p.n_aug;
-  if (cudaError_t e = launch_pdl(schur_finalize_kernel, (4 * n2 + 255) / 256, 256, 0, s.stream, p, partials, n_partials); e != cudaSuccess) return e;
+  if (cudaError_t e = launch_pdl(schur_finalize_kernel, (SF_LANES * n2 + 255) / 256, 256, 0, s.stream, p, partials, n_partials); e != cudaSuccess) return e;
   KB_LAUNCHED(s);
   return cudaGetLastError();
 }
