@@ -32,8 +32,24 @@ def attach_peers(g):
 
 ok_all = True
 use_px = os.environ.get("KB_PEER_EXCHANGE", "1") != "0" and world <= 8
-for cfg, S in [(2, 9), (3, 7), (4, 10), (5, 5), (6, 8)]:
-    p = synthetic.make_config(cfg, n_sets=S)
+
+
+def camera_major(p):
+    """the same observations with the views (and their terms) ordered by camera, then set: a rank's terms are then scattered over the
+    caller's arrays (the gather branch of kb_create instead of the straight upload)"""
+    import dataclasses
+    order = np.lexsort((p.view_set, p.view_cam))
+    cnt = np.diff(p.view_begin)[order]
+    vb = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    idx = np.concatenate([np.arange(p.view_begin[w], p.view_begin[w + 1]) for w in order]) if len(order) else np.zeros(0, np.int64)
+    return dataclasses.replace(p, view_set=p.view_set[order].copy(), view_cam=p.view_cam[order].copy(), view_begin=vb, y_u=p.y_u[idx].copy(),
+                               y_v=p.y_v[idx].copy(), corner_id=p.corner_id[idx].copy())
+
+
+for cfg, S in [(2, 9), (3, 7), (4, 10), (5, 5), (6, 8), (-3, 7)]:
+    p = synthetic.make_config(abs(cfg), n_sets=S)
+    if cfg < 0:
+        p = camera_major(p)
     g = capi.B200SchurLinearSystemSolver(p, n_ranks=world, rank=rank, nccl_id=fresh_nccl_id(), device=lr)
     if use_px:
         attach_peers(g)
