@@ -1,7 +1,9 @@
 """ctypes binding of the CPU oracle (oracle/libkalibr_oracle.so).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs, never by
-kalibr_b200/.  PARITY UNPINNED (see oracle/ko_math.hpp).
+kalibr_b200/.  PARITY: the camera models are PINNED against the reference's own code (oracle/ref_pin.cpp compiled from /root/reference
+against the stand-in headers of oracle/ref_shim/; tests/golden/reference_cameras.npz); the solver / expression-tree part is UNPINNED
+(see oracle/ko_math.hpp).
 """
 from __future__ import annotations
 
@@ -24,6 +26,40 @@ def build(force: bool = False) -> str:
     if stale:
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "libkalibr_oracle.so"], check=True)
     return _LIB_PATH
+
+
+REFERENCE_DIR = os.environ.get("KALIBR_REFERENCE", "/root/reference")
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libkalibr_ref_cameras.so")
+_ref_lib = None
+
+
+def build_reference_cameras(force: bool = False):
+    """oracle/_ref/libkalibr_ref_cameras.so: the REFERENCE's camera models compiled from the sources where they lie (oracle/ref_pin.cpp).
+    Returns the path, or None when neither the reference tree nor a built library is there (the GPU box: only prebuilt files travel)."""
+    have_ref = os.path.isdir(os.path.join(REFERENCE_DIR, "aslam_cv", "aslam_cameras"))
+    if have_ref and (force or not os.path.exists(_REF_LIB_PATH) or os.path.getmtime(os.path.join(_HERE, "ref_pin.cpp")) > os.path.getmtime(_REF_LIB_PATH)):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "REFERENCE=" + REFERENCE_DIR, "_ref/libkalibr_ref_cameras.so"], check=True)
+    return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
+
+
+def reference_camera_project(model: int, params, ph):
+    """the reference's homogeneousToKeypoint (+ point Jacobian), ...IntrinsicsJacobian, ...DistortionJacobian: same layout as camera_project"""
+    global _ref_lib
+    if _ref_lib is None:
+        path = build_reference_cameras()
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/libkalibr_ref_cameras.so is not built and the reference tree is absent")
+        _ref_lib = C.CDLL(path)
+        _ref_lib.ref_camera_project.restype = C.c_int32
+        _ref_lib.ref_camera_project.argtypes = [C.c_int32] + [C.c_void_p] * 6
+    params = np.ascontiguousarray(np.pad(np.asarray(params, np.float64), (0, 10 - len(params))))
+    ph = np.ascontiguousarray(ph, np.float64)
+    y = np.zeros(2)
+    Jp = np.zeros((2, 4))
+    Ji = np.zeros((2, 6))
+    Jd = np.zeros((2, 4))
+    ok = _ref_lib.ref_camera_project(model, _p(params), _p(ph), _p(y), _p(Jp), _p(Ji), _p(Jd))
+    return y, Jp, Ji, Jd, ok
 
 
 _lib = None
