@@ -905,6 +905,19 @@ __attribute__((visibility("default"))) void ko_quat2r(const double* q, double* R
     for (int j = 0; j < 3; ++j) R9[i * 3 + j] = R(i, j);
 }
 __attribute__((visibility("default"))) void ko_update_quat(const double* q, const double* dq, double* out) { updateQuat(q, dq, out); }
+__attribute__((visibility("default"))) void ko_box_minus(const double* p4, double* out24_rowmajor) {
+  Mat B = boxMinus(p4);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 6; ++j) out24_rowmajor[i * 6 + j] = B(i, j);
+}
+__attribute__((visibility("default"))) void ko_box_times(const double* T16_rowmajor, double* out36_rowmajor) {
+  Mat T(4, 4);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) T(i, j) = T16_rowmajor[i * 4 + j];
+  Mat B = boxTimes(T);
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) out36_rowmajor[i * 6 + j] = B(i, j);
+}
 __attribute__((visibility("default"))) void ko_inverse4(const double* M16_rowmajor, double* out16_rowmajor) {
   Mat M(4, 4);
   for (int i = 0; i < 4; ++i)

@@ -1,7 +1,7 @@
 """ctypes binding of the CPU oracle (oracle/libkalibr_oracle.so).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs, never by
-kalibr_b200/.  PARITY: the camera models are PINNED against the reference's own code (oracle/ref_pin.cpp compiled from /root/reference
+kalibr_b200/.  PARITY: the camera models and the SE(3) helpers are PINNED against the reference's own code (oracle/ref_pin.cpp compiled from /root/reference
 against the stand-in headers of oracle/ref_shim/; tests/golden/reference_cameras.npz); the solver / expression-tree part is UNPINNED
 (see oracle/ko_math.hpp).
 """
@@ -29,16 +29,16 @@ def build(force: bool = False) -> str:
 
 
 REFERENCE_DIR = os.environ.get("KALIBR_REFERENCE", "/root/reference")
-_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libkalibr_ref_cameras.so")
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libkalibr_ref.so")
 _ref_lib = None
 
 
 def build_reference_cameras(force: bool = False):
-    """oracle/_ref/libkalibr_ref_cameras.so: the REFERENCE's camera models compiled from the sources where they lie (oracle/ref_pin.cpp).
+    """oracle/_ref/libkalibr_ref.so: the REFERENCE's camera models compiled from the sources where they lie (oracle/ref_pin.cpp).
     Returns the path, or None when neither the reference tree nor a built library is there (the GPU box: only prebuilt files travel)."""
     have_ref = os.path.isdir(os.path.join(REFERENCE_DIR, "aslam_cv", "aslam_cameras"))
     if have_ref and (force or not os.path.exists(_REF_LIB_PATH) or os.path.getmtime(os.path.join(_HERE, "ref_pin.cpp")) > os.path.getmtime(_REF_LIB_PATH)):
-        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "REFERENCE=" + REFERENCE_DIR, "_ref/libkalibr_ref_cameras.so"], check=True)
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "REFERENCE=" + REFERENCE_DIR, "_ref/libkalibr_ref.so"], check=True)
     return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
 
 
@@ -48,7 +48,7 @@ def reference_camera_project(model: int, params, ph):
     if _ref_lib is None:
         path = build_reference_cameras()
         if path is None:
-            raise FileNotFoundError("oracle/_ref/libkalibr_ref_cameras.so is not built and the reference tree is absent")
+            raise FileNotFoundError("oracle/_ref/libkalibr_ref.so is not built and the reference tree is absent")
         _ref_lib = C.CDLL(path)
         _ref_lib.ref_camera_project.restype = C.c_int32
         _ref_lib.ref_camera_project.argtypes = [C.c_int32] + [C.c_void_p] * 6
@@ -60,6 +60,31 @@ def reference_camera_project(model: int, params, ph):
     Jd = np.zeros((2, 4))
     ok = _ref_lib.ref_camera_project(model, _p(params), _p(ph), _p(y), _p(Jp), _p(Ji), _p(Jd))
     return y, Jp, Ji, Jd, ok
+
+
+def reference_kinematics(name: str, *args):
+    """the reference's sm_kinematics helpers: 'quat2r'(q) -> 3x3, 'update_quat'(q, dq) -> 4, 'box_minus'(p4) -> 4x6, 'box_times'(T 4x4) -> 6x6"""
+    reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
+    a = [np.ascontiguousarray(x, np.float64) for x in args]
+    shape = {"quat2r": (3, 3), "update_quat": (4,), "box_minus": (4, 6), "box_times": (6, 6)}[name]
+    out = np.zeros(shape)
+    fn = getattr(_ref_lib, "ref_" + name)
+    fn.restype = None
+    fn.argtypes = [C.c_void_p] * (len(a) + 1)
+    fn(*[_p(x) for x in a], _p(out))
+    return out
+
+
+def kinematics(name: str, *args):
+    """the oracle's restatement of the same helpers (ko_math.hpp)"""
+    a = [np.ascontiguousarray(x, np.float64) for x in args]
+    shape = {"quat2r": (3, 3), "update_quat": (4,), "box_minus": (4, 6), "box_times": (6, 6)}[name]
+    out = np.zeros(shape)
+    fn = getattr(lib(), "ko_" + name)
+    fn.restype = None
+    fn.argtypes = [C.c_void_p] * (len(a) + 1)
+    fn(*[_p(x) for x in a], _p(out))
+    return out
 
 
 _lib = None

@@ -2,7 +2,7 @@
 // ExtendedUnifiedProjection / DoubleSphereProjection with RadialTangential / Equidistant / Fov / No distortion - compiled from the
 // sources where they lie under /root/reference (headers + src/*Distortion.cpp) against the stand-in headers of oracle/ref_shim/
 // (Eigen, Boost, OpenCV and sm_* are not in this image), behind a C entry point with the signature of the oracle's ko_camera_project.
-// Built by `make -C oracle _ref/libkalibr_ref_cameras.so` into the git-ignored oracle/_ref/; used by tests/test_reference_pin_cpu.py and
+// Built by `make -C oracle _ref/libkalibr_ref.so` into the git-ignored oracle/_ref/; used by tests/test_reference_pin_cpu.py and
 // tests/golden/make_reference_camera_golden.py to PIN the oracle's restatement of rows a11-a17 of SURVEY.md §8 against reference code:
 // homogeneousToKeypoint (value, validity flag, point Jacobian), homogeneousToKeypointIntrinsicsJacobian and
 // homogeneousToKeypointDistortionJacobian - the calls ReprojectionError and CameraDesignVariable make
@@ -16,6 +16,9 @@
 #include <aslam/cameras/PinholeProjection.hpp>
 #include <aslam/cameras/DoubleSphereProjection.hpp>
 #include <aslam/cameras/ExtendedUnifiedProjection.hpp>
+
+#include <sm/kinematics/quaternion_algebra.hpp>
+#include <sm/kinematics/transformations.hpp>
 
 #include <cstdint>
 
@@ -63,4 +66,29 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_camera_project(int
     case 6: return run(OmniProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], ru, rv), ph, y, Jp, Ji, Jd);
   }
   return -1;
+}
+
+// ---- sm_kinematics: the SE(3) helpers the expression nodes and the quaternion design variable call, from the
+// reference's own quaternion_algebra.cpp / rotations.cpp / transformations.cpp --------------------------------------------------------
+extern "C" __attribute__((visibility("default"))) void ref_quat2r(const double* q, double* R9) {
+  const Eigen::Matrix3d R = sm::kinematics::quat2r(Eigen::Vector4d(q[0], q[1], q[2], q[3]));
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R9[i * 3 + j] = R(i, j);
+}
+extern "C" __attribute__((visibility("default"))) void ref_update_quat(const double* q, const double* dq, double* out) {
+  const Eigen::Vector4d r = sm::kinematics::updateQuat(Eigen::Vector4d(q[0], q[1], q[2], q[3]), Eigen::Vector3d(dq[0], dq[1], dq[2]));
+  for (int i = 0; i < 4; ++i) out[i] = r(i);
+}
+extern "C" __attribute__((visibility("default"))) void ref_box_minus(const double* p4, double* out24_rowmajor) {
+  const Eigen::Matrix<double, 4, 6> B = sm::kinematics::boxMinus(Eigen::Vector4d(p4[0], p4[1], p4[2], p4[3]));
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 6; ++j) out24_rowmajor[i * 6 + j] = B(i, j);
+}
+extern "C" __attribute__((visibility("default"))) void ref_box_times(const double* T16_rowmajor, double* out36_rowmajor) {
+  Eigen::Matrix4d T;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) T(i, j) = T16_rowmajor[i * 4 + j];
+  const Eigen::Matrix<double, 6, 6> B = sm::kinematics::boxTimes(T);
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) out36_rowmajor[i * 6 + j] = B(i, j);
 }

@@ -1,11 +1,12 @@
-"""Golden vectors of the REFERENCE's camera models -> tests/golden/reference_cameras.npz.
+"""Golden vectors of the REFERENCE's camera models and SE(3) helpers -> tests/golden/reference_golden.npz.
 
 Needs /root/reference (read-only) in the build container: oracle/ref_pin.cpp compiles the reference's own PinholeProjection /
 OmniProjection / ExtendedUnifiedProjection / DoubleSphereProjection and *Distortion code where it lies (against the stand-in headers of
 oracle/ref_shim/) into the git-ignored oracle/_ref/, and this script records what THAT code returns for seeded inputs: keypoint, point
 Jacobian (2x4), intrinsics Jacobian, distortion Jacobian per model - on ordinary points, points behind the camera / outside the validity
-cone (where some models return before writing), negative and zero homogeneous scale, and a point on the optical axis.
-    python tests/golden/make_reference_camera_golden.py
+cone (where some models return before writing), negative and zero homogeneous scale, and a point on the optical axis; and sm_kinematics'
+quat2r, updateQuat (all its small-angle branches), boxMinus and boxTimes from the reference's quaternion_algebra.cpp / transformations.cpp.
+    python tests/golden/make_reference_golden.py
 """
 import os
 import sys
@@ -49,7 +50,22 @@ def main():
         out[f"m{model}_params"], out[f"m{model}_ph"] = P, H
         out[f"m{model}_y"], out[f"m{model}_Jp"], out[f"m{model}_Ji"], out[f"m{model}_Jd"] = np.array(Y), np.array(JP), np.array(JI), np.array(JD)
         out[f"m{model}_ok"] = np.array(OK, np.int32)
-    path = os.path.join(ROOT, "tests", "golden", "reference_cameras.npz")
+    rng = np.random.default_rng(4242)
+    Q, DQ, P4, T = [], [], [], []
+    for t in range(300):
+        q = rng.standard_normal(4)
+        q /= np.linalg.norm(q)
+        dq = rng.standard_normal(3) * [1.0, 0.3, 1e-3, 1e-5, 1e-9, 0.0][t % 6]
+        Tm = np.eye(4)
+        Tm[:3, :3] = oa.reference_kinematics("quat2r", q)
+        Tm[:3, 3] = 3.0 * rng.standard_normal(3)
+        Q.append(q); DQ.append(dq); P4.append(rng.standard_normal(4) * [1.0, 10.0, 0.1][t % 3]); T.append(Tm)
+    out["kin_q"], out["kin_dq"], out["kin_p4"], out["kin_T"] = np.array(Q), np.array(DQ), np.array(P4), np.array(T)
+    out["kin_quat2r"] = np.array([oa.reference_kinematics("quat2r", q) for q in Q])
+    out["kin_update_quat"] = np.array([oa.reference_kinematics("update_quat", q, dq) for q, dq in zip(Q, DQ)])
+    out["kin_box_minus"] = np.array([oa.reference_kinematics("box_minus", p) for p in P4])
+    out["kin_box_times"] = np.array([oa.reference_kinematics("box_times", t) for t in T])
+    path = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
 

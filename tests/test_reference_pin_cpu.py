@@ -1,12 +1,13 @@
-"""The oracle's camera models against the REFERENCE's own code.
+"""The oracle's camera models and SE(3) helpers against the REFERENCE's own code.
 
-tests/golden/reference_cameras.npz holds what the reference's PinholeProjection / OmniProjection / ExtendedUnifiedProjection /
+tests/golden/reference_golden.npz holds what the reference's PinholeProjection / OmniProjection / ExtendedUnifiedProjection /
 DoubleSphereProjection and *Distortion classes return - compiled from /root/reference by oracle/ref_pin.cpp (stand-in headers for Eigen /
-Boost / OpenCV / sm_* in oracle/ref_shim/; generator: tests/golden/make_reference_camera_golden.py).  The oracle must reproduce every
+Boost / OpenCV / sm_* in oracle/ref_shim/; generator: tests/golden/make_reference_golden.py).  The oracle must reproduce every
 value: keypoint, point Jacobian, intrinsics Jacobian, distortion Jacobian, including the points where a model returns before writing its
 outputs (quirk Q6), the NaNs of the equidistant model on the optical axis (Q5), the EUCM fu-for-fv entry (Q4) and the pinhole models'
-indifference to the sign of the homogeneous scale in the Jacobian (Q3).  This pins rows a11-a17 of SURVEY.md §8; the GPU path is
-compared with the oracle in the -m gpu suites."""
+indifference to the sign of the homogeneous scale in the Jacobian (Q3).  The same for sm_kinematics' quat2r, updateQuat, boxMinus and
+boxTimes (compiled from the reference's quaternion_algebra.cpp / transformations.cpp).  This pins rows a10 and a11-a17 of SURVEY.md §8;
+the GPU path is compared with the oracle in the -m gpu suites."""
 import os
 
 import numpy as np
@@ -14,7 +15,7 @@ import pytest
 
 from oracle import oracle_api as oa
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cameras.npz")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz")
 MODEL_NAMES = ["pinhole-radtan", "pinhole-equi", "omni-radtan", "eucm-none", "ds-none", "pinhole-fov", "omni-none"]
 # the oracle is built with the same compiler as the reference pin and follows the reference's expression order: the values agree to the
 # last bit in the build container; the bar leaves room for another compiler's choice of fused multiply-adds
@@ -46,6 +47,13 @@ def test_oracle_camera_models_reproduce_the_reference(oracle_lib, model):
         assert n_bailed > 0
 
 
+@pytest.mark.parametrize("name,args", [("quat2r", ("kin_q",)), ("update_quat", ("kin_q", "kin_dq")), ("box_minus", ("kin_p4",)), ("box_times", ("kin_T",))])
+def test_oracle_se3_helpers_reproduce_the_reference(oracle_lib, name, args):
+    g = np.load(GOLD)
+    for i in range(len(g["kin_q"])):
+        assert same(oa.kinematics(name, *[g[a][i] for a in args]), g["kin_" + name][i]), (name, i)
+
+
 def test_fixture_is_what_the_reference_returns_now(oracle_lib):
     """In the build container (reference tree present): rebuild oracle/_ref from the reference sources and check the committed fixture
     and fresh random points against it; elsewhere only the fixture test above runs."""
@@ -66,3 +74,6 @@ def test_fixture_is_what_the_reference_returns_now(oracle_lib):
             a, b = oa.camera_project(model, prm, ph), oa.reference_camera_project(model, prm, ph)
             for x, r in zip(a[:4], b[:4]):
                 assert same(x, r), (model, ph)
+    for i in range(0, len(g["kin_q"]), 5):
+        assert np.array_equal(oa.reference_kinematics("update_quat", g["kin_q"][i], g["kin_dq"][i]), g["kin_update_quat"][i])
+        assert np.array_equal(oa.reference_kinematics("box_times", g["kin_T"][i]), g["kin_box_times"][i])
