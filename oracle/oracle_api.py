@@ -75,6 +75,24 @@ def reference_kinematics(name: str, *args):
     return out
 
 
+def reference_point_chain(set_pose, baselines, p4, chain=None):
+    """the reference's expression tree of a reprojection term (oracle/ref_pin.cpp: ref_point_chain): p_c = B_{k-1} ... B_0 inverse(T_set) p_t and the
+    Jacobians of (chain @ p_c) with respect to (set q, set t, baseline 0 q, baseline 0 t, ...): returns (p_c [4], J [(1 + k) * 2, rows, 3])"""
+    reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
+    baselines = np.asarray(baselines, np.float64).reshape(-1, 7)
+    poses = np.ascontiguousarray(np.vstack([np.asarray(set_pose, np.float64).reshape(1, 7), baselines]))
+    p4 = np.ascontiguousarray(p4, np.float64)
+    rows = 4 if chain is None else int(np.asarray(chain).shape[0])
+    ch = np.ascontiguousarray(chain, np.float64) if chain is not None else np.zeros((4, 4))
+    pc = np.zeros(4)
+    J = np.zeros((2 * len(poses), rows, 3))
+    fn = _ref_lib.ref_point_chain
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn(len(baselines), _p(poses), _p(p4), 0 if chain is None else rows, _p(ch), _p(pc), _p(J))
+    return pc, J
+
+
 def kinematics(name: str, *args):
     """the oracle's restatement of the same helpers (ko_math.hpp)"""
     a = [np.ascontiguousarray(x, np.float64) for x in args]

@@ -92,3 +92,61 @@ extern "C" __attribute__((visibility("default"))) void ref_box_times(const doubl
   for (int i = 0; i < 6; ++i)
     for (int j = 0; j < 6; ++j) out36_rowmajor[i * 6 + j] = B(i, j);
 }
+
+// ---- the expression tree of a reprojection term: T_cam_w = B_{k-1} ... B_0 inverse(T_target_cam0), p_c = T_cam_w p_t,
+// built from the reference's own design variables and expression nodes exactly as K2/CalibrationTools.hpp:32-45, 405-408 and
+// K2/CameraCalibrator.hpp:213-222 build it, evaluated with HomogeneousExpression::toHomogeneous / evaluateJacobians(container, chain rule)
+// - the calls CVE/.../ReprojectionError.hpp:50-77 makes ------------------------------------------------------------------------------
+#include <aslam/backend/EuclideanPoint.hpp>
+#include <aslam/backend/HomogeneousExpression.hpp>
+#include <aslam/backend/HomogeneousPoint.hpp>
+#include <aslam/backend/JacobianContainer.hpp>
+#include <aslam/backend/RotationQuaternion.hpp>
+#include <aslam/backend/TransformationBasic.hpp>
+#include <aslam/backend/TransformationExpression.hpp>
+
+// poses7: [1 + n_base][7] = (q xyzw, t) of the set pose T_target_cam0, then of the baselines; chain (optional): rows x 4 row-major matrix the
+// Jacobians are multiplied with (the 2x4 point Jacobian of the camera); out_J: [(1 + n_base) * 2][rows][3] row-major in the order
+// (set q, set t, baseline 0 q, baseline 0 t, ...), rows = chain_rows > 0 ? chain_rows : 4.  Returns the number of Jacobian blocks written.
+extern "C" __attribute__((visibility("default"))) int32_t ref_point_chain(int32_t n_base, const double* poses7, const double* p4, int32_t chain_rows,
+                                                                          const double* chain, double* out_pc4, double* out_J) {
+  using namespace aslam::backend;
+  const int n_pose = 1 + n_base;
+  std::vector<boost::shared_ptr<RotationQuaternion>> qs;
+  std::vector<boost::shared_ptr<EuclideanPoint>> ts;
+  std::vector<boost::shared_ptr<TransformationBasic>> Ts;
+  for (int i = 0; i < n_pose; ++i) {
+    const double* p = poses7 + 7 * i;
+    qs.push_back(boost::make_shared<RotationQuaternion>(Eigen::Vector4d(p[0], p[1], p[2], p[3])));
+    qs.back()->setActive(true);
+    qs.back()->setBlockIndex(2 * i);
+    ts.push_back(boost::make_shared<EuclideanPoint>(Eigen::Vector3d(p[4], p[5], p[6])));
+    ts.back()->setActive(true);
+    ts.back()->setBlockIndex(2 * i + 1);
+    Ts.push_back(boost::make_shared<TransformationBasic>(qs.back()->toExpression(), ts.back()->toExpression()));
+  }
+  TransformationExpression T_cam_w = Ts[0]->toExpression().inverse();
+  for (int j = 0; j < n_base; ++j) T_cam_w = Ts[1 + j]->toExpression() * T_cam_w;
+  HomogeneousPoint target_point(Eigen::Vector4d(p4[0], p4[1], p4[2], p4[3]));  // not active: the target is fixed
+  HomogeneousExpression point = T_cam_w * target_point.toExpression();
+  const Eigen::Vector4d pc = point.toHomogeneous();
+  for (int i = 0; i < 4; ++i) out_pc4[i] = pc(i);
+  const int rows = chain_rows > 0 ? chain_rows : 4;
+  JacobianContainer jc(rows);
+  if (chain_rows > 0) {
+    Eigen::MatrixXd C(rows, 4);
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < 4; ++c) C(r, c) = chain[r * 4 + c];
+    point.evaluateJacobians(jc, C);
+  } else {
+    point.evaluateJacobians(jc);
+  }
+  for (int i = 0; i < 2 * n_pose * rows * 3; ++i) out_J[i] = 0.0;
+  int n = 0;
+  for (JacobianContainer::map_t::iterator it = jc.begin(); it != jc.end(); ++it, ++n) {
+    const int b = it->first->blockIndex();
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < 3; ++c) out_J[(b * rows + r) * 3 + c] = it->second(r, c);
+  }
+  return n;
+}

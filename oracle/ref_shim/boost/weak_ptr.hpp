@@ -1,0 +1,1 @@
+#include <boost/shared_ptr.hpp>

@@ -5,7 +5,10 @@ OmniProjection / ExtendedUnifiedProjection / DoubleSphereProjection and *Distort
 oracle/ref_shim/) into the git-ignored oracle/_ref/, and this script records what THAT code returns for seeded inputs: keypoint, point
 Jacobian (2x4), intrinsics Jacobian, distortion Jacobian per model - on ordinary points, points behind the camera / outside the validity
 cone (where some models return before writing), negative and zero homogeneous scale, and a point on the optical axis; and sm_kinematics'
-quat2r, updateQuat (all its small-angle branches), boxMinus and boxTimes from the reference's quaternion_algebra.cpp / transformations.cpp.
+quat2r, updateQuat (all its small-angle branches), boxMinus and boxTimes from the reference's quaternion_algebra.cpp / transformations.cpp;
+and, for two small calibration problems, the residual and the whole Jacobian row pair of every reprojection term as the reference's expression
+tree (RotationQuaternion, EuclideanPoint, TransformationBasic, the Transformation / Homogeneous expression nodes, JacobianContainer) and camera
+models produce them.
     python tests/golden/make_reference_golden.py
 """
 import os
@@ -39,8 +42,53 @@ def inputs(model, n=200, seed=0):
     return np.array(P), np.array(H)
 
 
+N_P = [4, 4, 5, 6, 6, 4, 5]
+N_D = [4, 4, 4, 0, 0, 1, 0]
+
+
+def reference_rows(p):
+    """residuals y - y_hat and the dense Jacobian rows d(y - y_hat)/d(design variables) of every term of problem p, computed by the
+    REFERENCE's code only: its expression tree (pose chain) and its camera models, combined as ReprojectionError does
+    (CVE/.../implementation/ReprojectionError.hpp:50-77: point.evaluateJacobians(container, -J), camera.evaluateJacobians(container, p));
+    the column of a design variable is p.dv_layout()'s"""
+    col, dims, labels = p.dv_layout()
+    off = {lab: int(c) for lab, c in zip(labels, col)}
+    jcols = int(col[-1] + dims[-1])
+    res, rows = np.zeros(2 * p.n_terms), np.zeros((2 * p.n_terms, jcols))
+    for w in range(len(p.view_set)):
+        v, k = int(p.view_set[w]), int(p.view_cam[w])
+        model = int(p.cam_model[k])
+        for i in range(int(p.view_begin[w]), int(p.view_begin[w + 1])):
+            p4 = np.append(p.target_points[p.corner_id[i]], 1.0)
+            pc, _ = oa.reference_point_chain(p.set_poses[v], p.baselines[:k], p4)
+            y, Jp, Ji, Jd, _ = oa.reference_camera_project(model, p.cam_params[k], pc)
+            _, Jpose = oa.reference_point_chain(p.set_poses[v], p.baselines[:k], p4, chain=-Jp)
+            r = rows[2 * i:2 * i + 2]
+            r[:, off[("set_q", v)]:off[("set_q", v)] + 3] = Jpose[0]
+            r[:, off[("set_t", v)]:off[("set_t", v)] + 3] = Jpose[1]
+            for j in range(k):
+                r[:, off[("baseline_q", j)]:off[("baseline_q", j)] + 3] = Jpose[2 + 2 * j]
+                r[:, off[("baseline_t", j)]:off[("baseline_t", j)] + 3] = Jpose[3 + 2 * j]
+            r[:, off[("proj", k)]:off[("proj", k)] + N_P[model]] = -Ji[:, :N_P[model]]
+            if N_D[model]:
+                r[:, off[("dist", k)]:off[("dist", k)] + N_D[model]] = -Jd[:, :N_D[model]]
+            res[2 * i:2 * i + 2] = np.array([p.y_u[i], p.y_v[i]]) - y
+    return res, rows
+
+
+# (tag, models, driver order, sets, seed): a rig with four different models and a batch-order problem with the remaining three
+TERM_PROBLEMS = [("rig", [0, 2, 1, 4], 2, 3, 5), ("batch", [5, 3, 6], 3, 3, 6)]
+
+
 def main():
     out = {}
+    for tag, models, order, n_sets, seed in TERM_PROBLEMS:
+        p = synthetic.make_problem(models, n_sets, order, seed=seed, dropout=0.75)
+        res, rows = reference_rows(p)
+        for name in ("cam_model", "cam_params", "baselines", "set_poses", "target_points", "view_set", "view_cam", "view_begin", "y_u", "y_v", "corner_id"):
+            out[f"term_{tag}_{name}"] = getattr(p, name)
+        out[f"term_{tag}_order"] = np.array(order)
+        out[f"term_{tag}_residuals"], out[f"term_{tag}_jacobian"] = res, rows
     for model in range(7):
         P, H = inputs(model)
         Y, JP, JI, JD, OK = [], [], [], [], []

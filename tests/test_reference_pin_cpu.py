@@ -6,8 +6,12 @@ Boost / OpenCV / sm_* in oracle/ref_shim/; generator: tests/golden/make_referenc
 value: keypoint, point Jacobian, intrinsics Jacobian, distortion Jacobian, including the points where a model returns before writing its
 outputs (quirk Q6), the NaNs of the equidistant model on the optical axis (Q5), the EUCM fu-for-fv entry (Q4) and the pinhole models'
 indifference to the sign of the homogeneous scale in the Jacobian (Q3).  The same for sm_kinematics' quat2r, updateQuat, boxMinus and
-boxTimes (compiled from the reference's quaternion_algebra.cpp / transformations.cpp).  This pins rows a10 and a11-a17 of SURVEY.md §8;
-the GPU path is compared with the oracle in the -m gpu suites."""
+boxTimes (compiled from the reference's quaternion_algebra.cpp / transformations.cpp), and for the residual and the complete Jacobian rows
+of every reprojection term of two small problems as the reference's expression tree (RotationQuaternion, EuclideanPoint, TransformationBasic,
+the Transformation / Homogeneous expression nodes, JacobianContainer: aslam_backend_expressions / aslam_backend compiled from their own
+sources) and camera models produce them, combined as ReprojectionError does.  This pins rows a3-a17 of SURVEY.md §8 (the design-variable
+ORDER of the columns, the Hessian assembly and the solver are not reference code here: they stay property-tested).  The GPU path is
+compared with the oracle in the -m gpu suites and with this fixture in tests/test_reference_pin_gpu.py."""
 import os
 
 import numpy as np
@@ -52,6 +56,40 @@ def test_oracle_se3_helpers_reproduce_the_reference(oracle_lib, name, args):
     g = np.load(GOLD)
     for i in range(len(g["kin_q"])):
         assert same(oa.kinematics(name, *[g[a][i] for a in args]), g["kin_" + name][i]), (name, i)
+
+
+def term_problem(g, tag):
+    from kalibr_b200.problem import Problem
+
+    f = lambda n: g[f"term_{tag}_{n}"]  # noqa: E731
+    return Problem(driver_order=int(f("order")), cam_model=f("cam_model"), cam_params=f("cam_params"), baselines=f("baselines"), set_poses=f("set_poses"),
+                   target_points=f("target_points"), view_set=f("view_set"), view_cam=f("view_cam"), view_begin=f("view_begin"), y_u=f("y_u"), y_v=f("y_v"),
+                   corner_id=f("corner_id"))
+
+
+def dense_from_ccs(col_ptr, row_idx, values, jcols):
+    J = np.zeros((len(col_ptr) - 1, jcols))
+    for r in range(len(col_ptr) - 1):
+        J[r, row_idx[col_ptr[r]:col_ptr[r + 1]]] = values[col_ptr[r]:col_ptr[r + 1]]
+    return J
+
+
+@pytest.mark.parametrize("tag", ["rig", "batch"])
+def test_oracle_terms_reproduce_the_reference_expression_tree(oracle_lib, tag):
+    """residual and Jacobian rows (pose chain through the expression nodes + camera part) of every term: the reference's own code vs the oracle"""
+    g = np.load(GOLD)
+    p = term_problem(g, tag)
+    o = oa.OracleProblem(p)
+    o.evaluate_error()
+    res, rows = g[f"term_{tag}_residuals"], g[f"term_{tag}_jacobian"]
+    assert np.abs(-o.error_vector() - res).max() <= 1e-12 * np.abs(p.y_u).max()  # e() = -(y - y_hat), pixels
+    J = dense_from_ccs(*o.jacobian_ccs(), o.jcols)
+    assert J.shape == rows.shape
+    assert np.array_equal(J != 0, rows != 0)  # same sparsity
+    assert (np.abs(J - rows) / np.maximum(np.abs(rows).max(axis=1, keepdims=True), 1.0)).max() <= 1e-13
+    o.build_system()
+    rhs_ref = -(rows.T @ res)  # rhs = -J^T e with the reference's J and e = y - y_hat
+    assert np.abs(o.rhs() - rhs_ref).max() <= 1e-12 * np.abs(rhs_ref).max()
 
 
 def test_fixture_is_what_the_reference_returns_now(oracle_lib):
