@@ -93,6 +93,15 @@ def reference_point_chain(set_pose, baselines, p4, chain=None):
     return pc, J
 
 
+def reference_m_estimator_weight(kind: int, squared_error: float, p0: float = 0.0, p1: float = 0.999, p2: float = 0.1) -> float:
+    """the reference's MEstimator::getWeight (BE/src/MEstimatorPolicies.cpp compiled from its own source); kinds as m_estimator_weight"""
+    reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
+    fn = _ref_lib.ref_m_estimator_weight
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_int32] + [C.c_double] * 4
+    return float(fn(kind, p0, p1, p2, squared_error))
+
+
 def kinematics(name: str, *args):
     """the oracle's restatement of the same helpers (ko_math.hpp)"""
     a = [np.ascontiguousarray(x, np.float64) for x in args]

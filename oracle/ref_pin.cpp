@@ -150,3 +150,19 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_point_chain(int32_
   }
   return n;
 }
+
+// ---- M-estimator policies: the reference's weight functions, BE/src/MEstimatorPolicies.cpp ---------------------
+// kind as kb_m_estimator: 0 none, 1 Huber(k = p0), 2 Cauchy(sigma2 = p0), 3 Geman-McClure(sigma2 = p0), 4 Blake-Zisserman(df = p0, pCut = p1,
+// wCut = p2).  (Blake-Zisserman's epsilon needs a chi-squared quantile: Boost.Math in the reference, a stand-in here - ref_shim/boost/math.)
+#include <aslam/backend/MEstimatorPolicies.hpp>
+extern "C" __attribute__((visibility("default"))) double ref_m_estimator_weight(int32_t kind, double p0, double p1, double p2, double squared_error) {
+  using namespace aslam::backend;
+  switch (kind) {
+    case 0: return NoMEstimator().getWeight(squared_error);
+    case 1: return HuberMEstimator(p0).getWeight(squared_error);
+    case 2: return CauchyMEstimator(p0).getWeight(squared_error);
+    case 3: return GemanMcClureMEstimator(p0).getWeight(squared_error);
+    case 4: return BlakeZissermanMEstimator((size_t)p0, p1, p2).getWeight(squared_error);
+  }
+  return -1.0;
+}

@@ -113,6 +113,12 @@ def main():
     out["kin_update_quat"] = np.array([oa.reference_kinematics("update_quat", q, dq) for q, dq in zip(Q, DQ)])
     out["kin_box_minus"] = np.array([oa.reference_kinematics("box_minus", p) for p in P4])
     out["kin_box_times"] = np.array([oa.reference_kinematics("box_times", t) for t in T])
+    # M-estimator weights (BE/src/MEstimatorPolicies.cpp): kind, (p0, p1, p2), squared error -> weight
+    K, PR, S, W = [], [], [], []
+    for kind, prm in ((0, (0.0, 0.0, 0.0)), (1, (1.5, 0.0, 0.0)), (1, (0.3, 0.0, 0.0)), (2, (4.0, 0.0, 0.0)), (3, (2.5, 0.0, 0.0)), (4, (2.0, 0.999, 0.1)), (4, (2.0, 0.95, 0.3))):
+        for sq in list(rng.uniform(0.0, 30.0, 60)) + [0.0, 1e-12, prm[0] ** 2, prm[0] ** 2 * (1 + 1e-9), 700.0]:
+            K.append(kind); PR.append(prm); S.append(sq); W.append(oa.reference_m_estimator_weight(kind, sq, *prm))
+    out["mest_kind"], out["mest_params"], out["mest_s"], out["mest_w"] = np.array(K, np.int32), np.array(PR), np.array(S), np.array(W)
     path = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")

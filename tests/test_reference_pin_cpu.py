@@ -92,6 +92,19 @@ def test_oracle_terms_reproduce_the_reference_expression_tree(oracle_lib, tag):
     assert np.abs(o.rhs() - rhs_ref).max() <= 1e-12 * np.abs(rhs_ref).max()
 
 
+def test_oracle_m_estimator_weights_reproduce_the_reference(oracle_lib):
+    """Huber / Cauchy / Geman-McClure / Blake-Zisserman weights of BE/src/MEstimatorPolicies.cpp (row a19); the chi-squared quantile behind
+    Blake-Zisserman's epsilon is Boost.Math in the reference and a stand-in in the pin, so that one number is also checked against scipy"""
+    g = np.load(GOLD)
+    for kind, prm, sq, w in zip(g["mest_kind"], g["mest_params"], g["mest_s"], g["mest_w"]):
+        assert abs(oa.m_estimator_weight(int(kind), float(sq), *[float(x) for x in prm]) - w) <= 1e-14 * max(abs(w), 1e-300), (kind, prm, sq)
+    from scipy.stats import chi2
+
+    eps = (1 - 0.1) / 0.1 * np.exp(-chi2.ppf(0.999, 2))
+    w = np.exp(-3.0) / (np.exp(-3.0) + eps)
+    assert abs(oa.m_estimator_weight(4, 3.0, 2.0, 0.999, 0.1) - w) <= 1e-12 * w
+
+
 def test_fixture_is_what_the_reference_returns_now(oracle_lib):
     """In the build container (reference tree present): rebuild oracle/_ref from the reference sources and check the committed fixture
     and fresh random points against it; elsewhere only the fixture test above runs."""
