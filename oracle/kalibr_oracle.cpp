@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see ko_math.hpp header).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ko_math.hpp header: parity PINNED for the per-term part against the reference's own code, UNPINNED for the rest).
 //
 // Problem construction (kalibr2 drivers), LinearSystemSolver / BlockCholesky / SparseCholesky semantics,
 // LevenbergMarquardtTrustRegionPolicy and Optimizer2, restated on the CPU behind a small C API (ko_*)

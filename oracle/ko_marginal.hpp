@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see ko_math.hpp header).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ko_math.hpp header: parity PINNED for the per-term part against the reference's own code, UNPINNED for the rest).
 //
 // Marginal analysis of the calibration block, the step the incremental estimator runs after every re-optimisation
 // (IC = aslam_incremental_calibration/incremental_calibration):

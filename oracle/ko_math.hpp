@@ -2,11 +2,15 @@
 // (kalibr_b200/).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may use anything under oracle/.
 //
-// PARITY UNPINNED: the reference (ToyotaResearchInstitute/kalibr) stores no golden vectors for this path
-//  and cannot be compiled here (needs Eigen3, Boost, SuiteSparse, OpenCV — all absent).
-// This is a CPU restatement; each function cites the reference file:line it follows.  It is pinned only
-// through the reference's own property tests re-expressed in tests/ (finite-difference Jacobians with the
-// getTestGeometry() parameter sets, H == J^T J, Schur == dense, solver-vs-solver).
+// PARITY: PINNED for the per-term part - camera models, SE(3) helpers, the expression tree of a reprojection term (residual and complete
+// Jacobian rows) and the M-estimator weights - against the REFERENCE'S OWN CODE: oracle/ref_pin.cpp compiles the reference's headers and
+// sources where they lie under /root/reference against stand-in headers for Eigen / Boost / OpenCV / sm_* (oracle/ref_shim/; none of those
+// libraries is in this image) into the git-ignored oracle/_ref/, its outputs are committed as tests/golden/reference_golden.npz and
+// tests/test_reference_pin_cpu.py holds this restatement to them (bit-identical in the build container).  UNPINNED for the rest - the
+// design-variable order, the Hessian assembly, the CHOLMOD solve with its damping quirk, the LM policy: the reference stores no golden
+// vectors for them and those sources need SuiteSparse / a thread pool / the sparse block matrix; that part is held
+// only by the reference's own property tests re-expressed in tests/ (H == J^T J, Schur == dense, solver-vs-solver) and by an
+// independent derivation (tests/independent_model.py).  Each function cites the reference file:line it follows.
 //
 // ko_math.hpp: a small heap-backed dense matrix (stands in for Eigen::MatrixXd so the CPU baseline keeps the
 // reference's per-term heap-allocation structure) and the sm_kinematics helpers.

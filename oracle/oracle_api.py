@@ -1,9 +1,10 @@
 """ctypes binding of the CPU oracle (oracle/libkalibr_oracle.so).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs, never by
-kalibr_b200/.  PARITY: the camera models and the SE(3) helpers are PINNED against the reference's own code (oracle/ref_pin.cpp compiled from /root/reference
-against the stand-in headers of oracle/ref_shim/; tests/golden/reference_cameras.npz); the solver / expression-tree part is UNPINNED
-(see oracle/ko_math.hpp).
+kalibr_b200/.  PARITY: the per-term part (camera models, SE(3) helpers, the expression tree of a reprojection term, M-estimator weights) is
+PINNED against the reference's own code (oracle/ref_pin.cpp compiled from /root/reference against the stand-in headers of oracle/ref_shim/;
+tests/golden/reference_golden.npz; tests/test_reference_pin_cpu.py); the design-variable order, Hessian assembly, solver and LM policy are
+UNPINNED (see oracle/ko_math.hpp).
 """
 from __future__ import annotations
 
