@@ -151,7 +151,11 @@ cudaError_t launch_set_reduce(const DevProblem& p, StreamCtx& s);
 cudaError_t launch_linearise_materialise(const DevProblem& p, const int4* vmeta, const int4* slices, const int* slice_model_begin,
                                          const int* bfrag_pairs /*[NUM_MODELS]*/, unsigned int* counters /*[NUM_MODELS], device*/, double* jt_values,
                                          StreamCtx& s);
-// damping / lambda arguments: a negative value means "read it from the control block" (device-resident loop)
+// damping argument: KB_DAMPING_FROM_CTRL (NaN) means "read it from the control block" (device-resident loop).  A real damping may be
+// NEGATIVE: the BlockCholesky semantic un-augments with lambda instead of lambda^2 (Q2), so after a rejected step the diagonal carries
+// lambda_old^2 - lambda_old + lambda_new^2 < 0 and the solve must see exactly that (the reference then reports "not positive definite").
+// lambda arguments: a negative value means the control block's (lambda itself is never negative)
+#define KB_DAMPING_FROM_CTRL (__builtin_nan(""))
 cudaError_t launch_schur(const DevProblem& p, double damping, double* partials, int n_partials, int* pos_def_flag, StreamCtx& s);
 cudaError_t launch_schur_finalize(const DevProblem& p, double damping, const double* partials, int n_partials, bool add_camera_block, StreamCtx& s);
 // from_peers: the kernel waits for exchange A and sums the ranks' slots itself (no launch_px_reduce_system in front)

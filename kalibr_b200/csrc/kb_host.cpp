@@ -1941,8 +1941,8 @@ static kb_status enqueue_lm_iteration(kb_handle* h) {
   }
   {
     StageTimer t(h, 3);
-    KB_CUDA(h, launch_schur(D, -1.0, h->partials.p, h->n_partials, h->posdef.p, c));
-    KB_CUDA(h, launch_schur_finalize(D, -1.0, h->partials.p, h->n_partials, true, c));
+    KB_CUDA(h, launch_schur(D, KB_DAMPING_FROM_CTRL, h->partials.p, h->n_partials, h->posdef.p, c));
+    KB_CUDA(h, launch_schur_finalize(D, KB_DAMPING_FROM_CTRL, h->partials.p, h->n_partials, true, c));
     if (!h->px_on) {
       kb_status st = nccl_allreduce(h, D.Sred, (size_t)D.n_aug * D.n_aug, kNcclFloat64, kNcclSum);
       if (st != KB_OK) return st;
@@ -1950,7 +1950,7 @@ static kb_status enqueue_lm_iteration(kb_handle* h) {
   }
   {
     StageTimer t(h, 4);
-    KB_CUDA(h, launch_reduced_solve(D, -1.0, h->posdef.p, h->px_on, c));
+    KB_CUDA(h, launch_reduced_solve(D, KB_DAMPING_FROM_CTRL, h->posdef.p, h->px_on, c));
   }
   {
     StageTimer t(h, 5);

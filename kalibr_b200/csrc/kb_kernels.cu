@@ -1435,7 +1435,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) schur_kernel(DevProblem p, doub
   const int s_lo = blockIdx.x * sets_per_cta, s_hi = min(p.n_sets, s_lo + sets_per_cta);
   {
     // the factors of this slice (the CTAs of a gridDim.y split compute the same values: identical, benign double stores)
-    const double damping = damping_arg >= 0.0 ? damping_arg : p.ctrl->damping;
+    const double damping = damping_arg == damping_arg ? damping_arg : p.ctrl->damping;  // NaN: the device loop's own (a real damping can be negative: Q2 residual)
     for (int set = s_lo + tid; set < s_hi; set += blockDim.x) pose_factor(p, set, damping, pos_def_flag);
   }
   __syncthreads();
@@ -1792,7 +1792,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) reduced_solve_kernel(DevProblem
   __shared__ int s_ok;
   const int n = p.n_aug, nc = p.n_c;
   if (p.ctrl->done) return;
-  const double damping = damping_arg >= 0.0 ? damping_arg : p.ctrl->damping;
+  const double damping = damping_arg == damping_arg ? damping_arg : p.ctrl->damping;  // NaN: the device loop's own (a real damping can be negative: Q2 residual)
   const int n_rows = ((n + RS_NB - 1) / RS_NB) * RS_NB + RS_NB;
   double* s_rd = Lp + n_rows * (n_rows + 1) / 2;
   double* s_x = s_rd + n_rows;

@@ -38,7 +38,8 @@ def build_reference_cameras(force: bool = False):
     """oracle/_ref/libkalibr_ref.so: the REFERENCE's camera models compiled from the sources where they lie (oracle/ref_pin.cpp).
     Returns the path, or None when neither the reference tree nor a built library is there (the GPU box: only prebuilt files travel)."""
     have_ref = os.path.isdir(os.path.join(REFERENCE_DIR, "aslam_cv", "aslam_cameras"))
-    if have_ref and (force or not os.path.exists(_REF_LIB_PATH) or os.path.getmtime(os.path.join(_HERE, "ref_pin.cpp")) > os.path.getmtime(_REF_LIB_PATH)):
+    srcs = [os.path.join(_HERE, f) for f in ("ref_pin.cpp", "ref_pin_optimizer.cpp")]
+    if have_ref and (force or not os.path.exists(_REF_LIB_PATH) or any(os.path.getmtime(f) > os.path.getmtime(_REF_LIB_PATH) for f in srcs)):
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "REFERENCE=" + REFERENCE_DIR, "_ref/libkalibr_ref.so"], check=True)
     return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
 
@@ -101,6 +102,36 @@ def reference_m_estimator_weight(kind: int, squared_error: float, p0: float = 0.
     fn.restype = C.c_double
     fn.argtypes = [C.c_int32] + [C.c_double] * 4
     return float(fn(kind, p0, p1, p2, squared_error))
+
+
+def reference_optimize(problem, options=None):
+    """the REFERENCE's Optimizer2::optimize (BE/src/Optimizer2.cpp, LevenbergMarquardtTrustRegionPolicy.cpp, BlockCholeskyLinearSystemSolver.cpp,
+    ErrorTerm / JacobianContainer / OptimizationProblem / SparseBlockMatrix, the expression tree and the camera models, all compiled from the
+    reference's sources: oracle/ref_pin_optimizer.cpp) on a kalibr_b200.problem.Problem, design variables in the problem's driver order.
+    Returns (dict(iterations, failed_iterations, j_start, j_final, linear_solver_failure), cam_params, baselines, set_poses)."""
+    from kalibr_b200.problem import KbOptimizerOptions
+
+    reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
+    o = options or KbOptimizerOptions.kalibr2_default()
+    p = problem
+    cp = np.array(p.cam_params, np.float64, order="C")
+    bl = np.array(p.baselines, np.float64, order="C").reshape(-1, 7)
+    sp = np.array(p.set_poses, np.float64, order="C")
+    cm, vs, vc = (np.ascontiguousarray(a, np.int32) for a in (p.cam_model, p.view_set, p.view_cam))
+    vb = np.ascontiguousarray(p.view_begin, np.int64)
+    yu, yv, tp = (np.ascontiguousarray(a, np.float64) for a in (p.y_u, p.y_v, p.target_points))
+    ci = np.ascontiguousarray(p.corner_id, np.int32)
+    out = np.zeros(8)
+    fn = _ref_lib.ref_optimize_rig
+    fn.restype = C.c_int32
+    fn.argtypes = ([C.c_int32] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 6
+                   + [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p])
+    rc = fn(len(cm), _p(cm), _p(cp), _p(bl), len(sp), _p(sp), len(tp), _p(tp), len(vs), _p(vs), _p(vc), _p(vb), _p(yu), _p(yv), _p(ci),
+            int(p.driver_order), int(o.max_iterations), float(o.convergence_delta_x), float(o.convergence_delta_j), float(o.lm_lambda_init), _p(out))
+    if rc != 0:
+        raise RuntimeError("ref_optimize_rig failed")
+    res = dict(iterations=int(out[0]), failed_iterations=int(out[1]), j_start=float(out[2]), j_final=float(out[3]), linear_solver_failure=int(out[4]))
+    return res, cp, bl, sp
 
 
 def kinematics(name: str, *args):

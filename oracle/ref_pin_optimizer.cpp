@@ -1,0 +1,214 @@
+// TEST INFRASTRUCTURE: the REFERENCE's optimiser on a small calibration problem - aslam_backend's Optimizer2, LevenbergMarquardt /
+// TrustRegionPolicy, LinearSystemSolver, BlockCholeskyLinearSystemSolver (build, conditioner, the lambda^2 / lambda damping of SURVEY.md
+// Q2), ErrorTermFs (weighting, buildHessian), JacobianContainer::evaluateHessian, OptimizationProblem and the sparse_block_matrix
+// container, all compiled from the sources where they lie under /root/reference against the stand-in headers of oracle/ref_shim/.
+// NOT reference code in this translation unit, and said so where it stands: (1) the factorisation behind LinearSolverCholmod (CHOLMOD is
+// not in the image: a dense Cholesky over the reference's own SparseBlockMatrix, ref_shim/sparse_block_matrix/linear_solver_cholmod.h);
+// (2) the glue below - the error term, which restates CVE/.../implementation/ReprojectionError.hpp:50-77 line by line over the reference's
+// projection classes and expression tree (the reference's own template needs the CameraGeometry / Frame / Image headers, i.e. OpenCV),
+// and a plain additive parameter-block design variable in place of aslam_cv_backend's DesignVariableAdapter (parameter += delta; revert).
+// The per-term arithmetic these two stand for is pinned separately against the real classes (ref_pin.cpp).  What this file pins is the
+// LOOP: iteration and failed-iteration counts, the cost per iteration, the lambda schedule, the damping quirk, the final parameters.
+#include <aslam/cameras/EquidistantDistortion.hpp>
+#include <aslam/cameras/FovDistortion.hpp>
+#include <aslam/cameras/NoDistortion.hpp>
+#include <aslam/cameras/RadialTangentialDistortion.hpp>
+#include <aslam/cameras/OmniProjection.hpp>
+#include <aslam/cameras/PinholeProjection.hpp>
+#include <aslam/cameras/DoubleSphereProjection.hpp>
+#include <aslam/cameras/ExtendedUnifiedProjection.hpp>
+
+#include <aslam/backend/BlockCholeskyLinearSystemSolver.hpp>
+#include <aslam/backend/ErrorTerm.hpp>
+#include <aslam/backend/EuclideanPoint.hpp>
+#include <aslam/backend/HomogeneousExpression.hpp>
+#include <aslam/backend/HomogeneousPoint.hpp>
+#include <aslam/backend/LevenbergMarquardtTrustRegionPolicy.hpp>
+#include <aslam/backend/OptimizationProblem.hpp>
+#include <aslam/backend/Optimizer2.hpp>
+#include <aslam/backend/RotationQuaternion.hpp>
+#include <aslam/backend/TransformationBasic.hpp>
+#include <aslam/backend/TransformationExpression.hpp>
+
+#include <cstdint>
+#include <vector>
+
+using namespace aslam::backend;
+using namespace aslam::cameras;
+
+namespace {
+// a block of parameters with the update rule of DesignVariableAdapter over Projection::update / Distortion::update (parameter += delta)
+class ParameterBlock : public DesignVariable {
+ public:
+  ParameterBlock(double* p, int n) : p_(p), n_(n), backup_(p, p + n) {}
+ protected:
+  virtual int minimalDimensionsImplementation() const { return n_; }
+  virtual void updateImplementation(const double* dp, int size) {
+    backup_.assign(p_, p_ + n_);
+    for (int i = 0; i < size && i < n_; ++i) p_[i] += dp[i];
+  }
+  virtual void revertUpdateImplementation() { for (int i = 0; i < n_; ++i) p_[i] = backup_[i]; }
+  virtual void getParametersImplementation(Eigen::MatrixXd& value) const {
+    value.resize(n_, 1);
+    for (int i = 0; i < n_; ++i) value(i, 0) = p_[i];
+  }
+  virtual void setParametersImplementation(const Eigen::MatrixXd& value) { for (int i = 0; i < n_; ++i) p_[i] = value(i, 0); }
+ private:
+  double* p_;
+  int n_;
+  std::vector<double> backup_;
+};
+
+struct CameraModel {  // parameters live here; the reference's projection object is built from them at every evaluation
+  int model;
+  double prm[10];
+  int P, D;
+  boost::shared_ptr<ParameterBlock> proj, dist;
+};
+const int N_P[7] = {4, 4, 5, 6, 6, 4, 5}, N_D[7] = {4, 4, 4, 0, 0, 1, 0};
+
+template <typename CAMERA>
+bool projectWith(const CAMERA& cam, const Eigen::Vector4d& ph, Eigen::VectorXd& y, Eigen::MatrixXd* J, Eigen::MatrixXd* Ji, Eigen::MatrixXd* Jd) {
+  if (!J) return cam.homogeneousToKeypoint(ph, y);
+  const bool ok = cam.homogeneousToKeypoint(ph, y, *J);
+  cam.homogeneousToKeypointIntrinsicsJacobian(ph, *Ji);
+  cam.homogeneousToKeypointDistortionJacobian(ph, *Jd);
+  return ok;
+}
+bool project(const CameraModel& c, const Eigen::Vector4d& ph, Eigen::VectorXd& y, Eigen::MatrixXd* J, Eigen::MatrixXd* Ji, Eigen::MatrixXd* Jd) {
+  const double* p = c.prm;
+  const int ru = 1 << 20, rv = 1 << 20;
+  switch (c.model) {
+    case 0: return projectWith(PinholeProjection<RadialTangentialDistortion>(p[0], p[1], p[2], p[3], ru, rv, RadialTangentialDistortion(p[4], p[5], p[6], p[7])), ph, y, J, Ji, Jd);
+    case 1: return projectWith(PinholeProjection<EquidistantDistortion>(p[0], p[1], p[2], p[3], ru, rv, EquidistantDistortion(p[4], p[5], p[6], p[7])), ph, y, J, Ji, Jd);
+    case 2: return projectWith(OmniProjection<RadialTangentialDistortion>(p[0], p[1], p[2], p[3], p[4], ru, rv, RadialTangentialDistortion(p[5], p[6], p[7], p[8])), ph, y, J, Ji, Jd);
+    case 3: return projectWith(ExtendedUnifiedProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], p[5], ru, rv), ph, y, J, Ji, Jd);
+    case 4: return projectWith(DoubleSphereProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], p[5], ru, rv), ph, y, J, Ji, Jd);
+    case 5: return projectWith(PinholeProjection<FovDistortion>(p[0], p[1], p[2], p[3], ru, rv, FovDistortion(p[4])), ph, y, J, Ji, Jd);
+    case 6: return projectWith(OmniProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], ru, rv), ph, y, J, Ji, Jd);
+  }
+  return false;
+}
+
+// CVE/.../implementation/ReprojectionError.hpp:50-77 over the classes above
+class ReprojectionTerm : public ErrorTermFs<2> {
+ public:
+  ReprojectionTerm(const Eigen::Vector2d& y, const HomogeneousExpression& point, CameraModel* cam) : y_(y), point_(point), cam_(cam) {
+    setInvR(Eigen::Matrix2d::Identity());
+    DesignVariable::set_t dvs;
+    point_.getDesignVariables(dvs);
+    dvs.insert(cam_->proj.get());
+    dvs.insert(cam_->dist.get());
+    setDesignVariablesIterator(dvs.begin(), dvs.end());
+  }
+ protected:
+  virtual double evaluateErrorImplementation() {
+    const Eigen::Vector4d p = point_.toHomogeneous();
+    Eigen::VectorXd hat_y(2);
+    hat_y.setZero();
+    project(*cam_, p, hat_y, 0, 0, 0);
+    setError(y_ - hat_y);
+    return error().dot(invR() * error());
+  }
+  virtual void evaluateJacobiansImplementation(JacobianContainer& jacobians) const {
+    const Eigen::Vector4d p = point_.toHomogeneous();
+    Eigen::VectorXd hat_y(2);
+    Eigen::MatrixXd J(2, 4), Ji, Jd;
+    J.setZero();
+    project(*cam_, p, hat_y, &J, &Ji, &Jd);
+    point_.evaluateJacobians(jacobians, -J);
+    // CVB/.../implementation/CameraDesignVariable.hpp: the negated intrinsics / distortion Jacobians, for the active blocks
+    if (cam_->proj->isActive()) jacobians.add(cam_->proj.get(), Eigen::MatrixXd(-Ji));
+    if (cam_->dist->isActive() && cam_->D > 0) jacobians.add(cam_->dist.get(), Eigen::MatrixXd(-Jd));
+  }
+ private:
+  Eigen::Vector2d y_;
+  HomogeneousExpression point_;
+  CameraModel* cam_;
+};
+}  // namespace
+
+// Problem in the layout of include/kalibr_b200.h (kb_problem_desc); design variables are added in the order of the driver named by
+// driver_order (kb_driver_order: 0/2 = cameras, baselines, then one pose per synced set, K2/CalibrationTools.hpp:183-300, 375-408;
+// 1 = baselines, poses, cameras, :222-262; 3 = poses, baselines, cameras, :460-491); error terms in term order.
+// out_scalars: [iterations, failedIterations, JStart, JFinal, linearSolverFailure]; state arrays are updated in place.
+extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32_t n_cams, const int32_t* cam_model, double* cam_params /*[n_cams][10]*/,
+                                                                           double* baselines /*[n_cams-1][7]*/, int32_t n_sets, double* set_poses /*[n_sets][7]*/,
+                                                                           int32_t n_target, const double* target /*[n_target][3]*/, int32_t n_views,
+                                                                           const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
+                                                                           const double* y_u, const double* y_v, const int32_t* corner_id, int32_t driver_order, int32_t max_iterations,
+                                                                           double conv_dx, double conv_dj, double lambda_init, double* out_scalars) {
+  try {
+    boost::shared_ptr<OptimizationProblem> problem(new OptimizationProblem());
+    std::vector<CameraModel> cams(n_cams);
+    auto addCameras = [&]() {
+      for (int k = 0; k < n_cams; ++k) {
+        CameraModel& c = cams[k];
+        c.model = cam_model[k];
+        c.P = N_P[c.model];
+        c.D = N_D[c.model];
+        for (int i = 0; i < 10; ++i) c.prm[i] = cam_params[k * 10 + i];
+        c.proj.reset(new ParameterBlock(c.prm, c.P));
+        c.dist.reset(new ParameterBlock(c.prm + c.P, c.D));
+        c.proj->setActive(true);
+        c.dist->setActive(true);
+        problem->addDesignVariable(c.proj);
+        problem->addDesignVariable(c.dist);
+      }
+    };
+    auto addPose = [&](const double* p, std::vector<boost::shared_ptr<RotationQuaternion>>& qs, std::vector<boost::shared_ptr<EuclideanPoint>>& ts) {
+      qs.push_back(boost::make_shared<RotationQuaternion>(Eigen::Vector4d(p[0], p[1], p[2], p[3])));
+      qs.back()->setActive(true);
+      problem->addDesignVariable(qs.back());
+      ts.push_back(boost::make_shared<EuclideanPoint>(Eigen::Vector3d(p[4], p[5], p[6])));
+      ts.back()->setActive(true);
+      problem->addDesignVariable(ts.back());
+      return boost::make_shared<TransformationBasic>(qs.back()->toExpression(), ts.back()->toExpression());
+    };
+    std::vector<boost::shared_ptr<RotationQuaternion>> bq, sq;
+    std::vector<boost::shared_ptr<EuclideanPoint>> bt, st;
+    std::vector<boost::shared_ptr<TransformationBasic>> B, S;
+    auto addBaselines = [&]() { for (int j = 0; j + 1 < n_cams; ++j) B.push_back(addPose(baselines + 7 * j, bq, bt)); };
+    auto addSets = [&]() { for (int v = 0; v < n_sets; ++v) S.push_back(addPose(set_poses + 7 * v, sq, st)); };
+    if (driver_order == 1) { addBaselines(); addSets(); addCameras(); }
+    else if (driver_order == 3) { addSets(); addBaselines(); addCameras(); }
+    else { addCameras(); addBaselines(); addSets(); }
+    std::vector<boost::shared_ptr<HomogeneousPoint>> points;
+    for (int i = 0; i < n_target; ++i) points.push_back(boost::make_shared<HomogeneousPoint>(Eigen::Vector4d(target[3 * i], target[3 * i + 1], target[3 * i + 2], 1.0)));
+    for (int w = 0; w < n_views; ++w) {
+      TransformationExpression T_cam_w = S[view_set[w]]->toExpression().inverse();
+      for (int j = 0; j < view_cam[w]; ++j) T_cam_w = B[j]->toExpression() * T_cam_w;
+      for (int64_t i = view_begin[w]; i < view_begin[w + 1]; ++i)
+        problem->addErrorTerm(boost::make_shared<ReprojectionTerm>(Eigen::Vector2d(y_u[i], y_v[i]), T_cam_w * points[corner_id[i]]->toExpression(), &cams[view_cam[w]]));
+    }
+    Optimizer2Options options;  // K2/CalibrationTools.hpp:57-66
+    options.nThreads = 1;
+    options.convergenceDeltaX = conv_dx;
+    options.convergenceDeltaJ = conv_dj;
+    options.maxIterations = max_iterations;
+    options.trustRegionPolicy = boost::make_shared<LevenbergMarquardtTrustRegionPolicy>(lambda_init);
+    options.linearSystemSolver = boost::make_shared<BlockCholeskyLinearSystemSolver>();
+    Optimizer2 optimizer(options);
+    optimizer.setProblem(problem);
+    SolutionReturnValue r = optimizer.optimize();
+    out_scalars[0] = r.iterations;
+    out_scalars[1] = r.failedIterations;
+    out_scalars[2] = r.JStart;
+    out_scalars[3] = r.JFinal;
+    out_scalars[4] = r.linearSolverFailure ? 1.0 : 0.0;
+    for (int k = 0; k < n_cams; ++k)
+      for (int i = 0; i < 10; ++i) cam_params[k * 10 + i] = cams[k].prm[i];
+    auto store = [](double* p, const boost::shared_ptr<RotationQuaternion>& q, const boost::shared_ptr<EuclideanPoint>& t) {
+      const Eigen::Vector4d qv = q->getQuaternion();
+      const Eigen::Vector3d tv = t->toEuclidean();
+      for (int i = 0; i < 4; ++i) p[i] = qv(i);
+      for (int i = 0; i < 3; ++i) p[4 + i] = tv(i);
+    };
+    for (size_t j = 0; j < bq.size(); ++j) store(baselines + 7 * j, bq[j], bt[j]);
+    for (size_t v = 0; v < sq.size(); ++v) store(set_poses + 7 * v, sq[v], st[v]);
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << "ref_optimize_rig: " << e.what() << std::endl;
+    return -1;
+  }
+}

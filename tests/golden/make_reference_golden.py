@@ -8,7 +8,10 @@ cone (where some models return before writing), negative and zero homogeneous sc
 quat2r, updateQuat (all its small-angle branches), boxMinus and boxTimes from the reference's quaternion_algebra.cpp / transformations.cpp;
 and, for two small calibration problems, the residual and the whole Jacobian row pair of every reprojection term as the reference's expression
 tree (RotationQuaternion, EuclideanPoint, TransformationBasic, the Transformation / Homogeneous expression nodes, JacobianContainer) and camera
-models produce them.
+models produce them; and, for eleven small calibration problems (all four design-variable orders, all seven models, damping seeds from
+1e-8 to 1e3, three runs with a rejected step, one that ends in the sticky linear-solver failure), what the reference's own Optimizer2 / LevenbergMarquardtTrustRegionPolicy /
+BlockCholeskyLinearSystemSolver loop returns (oracle/ref_pin_optimizer.cpp): iteration and failed-iteration counts, JStart / JFinal, the
+final design variables, and the same for runs truncated after 1, 2, ... iterations (the cost per iteration).
     python tests/golden/make_reference_golden.py
 """
 import os
@@ -80,8 +83,41 @@ def reference_rows(p):
 TERM_PROBLEMS = [("rig", [0, 2, 1, 4], 2, 3, 5), ("batch", [5, 3, 6], 3, 3, 6)]
 
 
+# (models, sets, driver order, seed, lambda_init, dropout): the reference's optimiser loop on these (see reference_optimizations); the
+# last three take a rejected step (revertLastStateUpdate, the lambda^2 / lambda damping of the solve that follows without a rebuild)
+OPT_PROBLEMS = [([0], 6, 0, 1, 10.0, 0.5), ([0, 2], 5, 1, 5, 10.0, 0.5), ([5, 3, 6], 4, 3, 6, 10.0, 0.5), ([1, 4], 5, 2, 7, 1e-4, 0.5),
+                ([0], 6, 0, 1, 1e-6, 0.5), ([2, 6], 4, 1, 9, 1e3, 0.5), ([0, 0], 5, 1, 3, 1e-8, 0.5), ([4], 6, 0, 11, 1e-7, 0.5),
+                ([2], 4, 0, 3, 1e-2, 0.6), ([4, 4], 4, 1, 4, 1e-2, 0.6), ([5, 2], 4, 3, 5, 1e-2, 0.6)]
+OPT_INPUTS = ("cam_model", "cam_params", "baselines", "set_poses", "target_points", "view_set", "view_cam", "view_begin", "y_u", "y_v", "corner_id")
+MAX_TRUNCATED = 10
+
+
+def reference_optimizations(out):
+    from kalibr_b200.problem import KbOptimizerOptions
+
+    for n, (models, n_sets, order, seed, lam0, dropout) in enumerate(OPT_PROBLEMS):
+        p = synthetic.make_problem(models, n_sets, order, seed=seed, dropout=dropout)
+        for name in OPT_INPUTS:
+            out[f"opt{n}_{name}"] = getattr(p, name)
+        out[f"opt{n}_order"], out[f"opt{n}_lambda_init"] = np.array(order), np.array(lam0)
+        opt = KbOptimizerOptions.kalibr2_default()  # K2/CalibrationTools.hpp:57-66
+        opt.lm_lambda_init = lam0
+        r, cp, bl, sp = oa.reference_optimize(p, opt)
+        out[f"opt{n}_result"] = np.array([r["iterations"], r["failed_iterations"], r["j_start"], r["j_final"], r["linear_solver_failure"]])
+        out[f"opt{n}_final_cam_params"], out[f"opt{n}_final_baselines"], out[f"opt{n}_final_set_poses"] = cp, bl, sp
+        rows = []
+        for k in range(1, min(r["iterations"], MAX_TRUNCATED) + 1):  # the run cut after k iterations: cost and counts per iteration
+            opt.max_iterations = k
+            rk = oa.reference_optimize(p, opt)[0]
+            rows.append([rk["iterations"], rk["failed_iterations"], rk["j_start"], rk["j_final"], rk["linear_solver_failure"]])
+        out[f"opt{n}_truncated"] = np.array(rows)
+        print("optimiser problem", n, models, "order", order, "lambda0", lam0, r)
+    out["opt_count"] = np.array(len(OPT_PROBLEMS))
+
+
 def main():
     out = {}
+    reference_optimizations(out)
     for tag, models, order, n_sets, seed in TERM_PROBLEMS:
         p = synthetic.make_problem(models, n_sets, order, seed=seed, dropout=0.75)
         res, rows = reference_rows(p)

@@ -135,6 +135,28 @@ def test_lm_step_sequence_matches_oracle(capi, oracle_lib, cfg, n_sets):
     assert abs(Jg2 - Jo2) <= 1e-11 * Jo2
 
 
+@pytest.mark.parametrize("cfg,n_sets,lams,pos_def", [(1, 40, (1e-3, 2e-3), True), (2, 30, (0.05, 0.02), True), (4, 12, (0.3, 0.4), True), (1, 40, (0.3, 0.4), True),
+                                                     (3, 24, (0.3, 0.4), False), (6, 8, (0.3, 0.4), False), (7, 8, (0.3, 0.4), False), (3, 24, (1e-3, 2e-3), False)])
+def test_negative_net_damping_after_a_solve_without_rebuild(capi, oracle_lib, cfg, n_sets, lams, pos_def):
+    """Q2 with lambda < 1: BlockCholesky un-augments with lambda, not lambda^2 (BlockCholeskyLinearSystemSolver.cpp:77-97), so the second solve
+    on the same built system sees diag(H) + l1^2 - l1 + l2^2, a NEGATIVE shift.  The solve must use exactly that: the same dx as the oracle
+    where the shifted system is still positive definite, "not positive definite" where it is not (the reference's sticky
+    linearSolverFailure; found by the reference pin, tests/test_reference_pin_gpu.py problem 3)."""
+    p = make(cfg, n_sets)
+    g = capi.B200SchurLinearSystemSolver(p)
+    o = oracle_lib.OracleProblem(p)
+    g.evaluate_error(); o.evaluate_error()
+    g.build_system(); o.build_system()
+    for i, lam in enumerate(lams):
+        g.set_constant_conditioner(lam); o.set_constant_conditioner(lam)
+        gdx, gok = g.solve_system()
+        odx, ook = o.solve_system()
+        assert gok == ook == (True if i == 0 else pos_def)
+        if ook:
+            assert rel_err(gdx, odx) < 1e-6
+    assert lams[0] ** 2 - lams[0] + lams[1] ** 2 < 0.0
+
+
 @pytest.mark.parametrize("cfg,n_sets", CASES)
 def test_optimize_converges_like_oracle(capi, oracle_lib, cfg, n_sets):
     p = make(cfg, n_sets)

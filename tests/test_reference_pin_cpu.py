@@ -9,8 +9,11 @@ indifference to the sign of the homogeneous scale in the Jacobian (Q3).  The sam
 boxTimes (compiled from the reference's quaternion_algebra.cpp / transformations.cpp), and for the residual and the complete Jacobian rows
 of every reprojection term of two small problems as the reference's expression tree (RotationQuaternion, EuclideanPoint, TransformationBasic,
 the Transformation / Homogeneous expression nodes, JacobianContainer: aslam_backend_expressions / aslam_backend compiled from their own
-sources) and camera models produce them, combined as ReprojectionError does.  This pins rows a3-a17 of SURVEY.md §8 (the design-variable
-ORDER of the columns, the Hessian assembly and the solver are not reference code here: they stay property-tested).  The GPU path is
+sources) and camera models produce them, combined as ReprojectionError does.  This pins rows a3-a17 of SURVEY.md §8.  Rows a1, a2, a19-a25 -
+the LOOP - are pinned by the optimiser fixture: the reference's own Optimizer2, LevenbergMarquardtTrustRegionPolicy,
+BlockCholeskyLinearSystemSolver, ErrorTermFs::buildHessian, JacobianContainer::evaluateHessian, OptimizationProblem and SparseBlockMatrix,
+compiled from their sources (oracle/ref_pin_optimizer.cpp), run on eleven small problems in all four design-variable orders; only the
+factorisation behind LinearSolverCholmod is a stand-in there (dense Cholesky; CHOLMOD is not in the image), i.e. rounding.  The GPU path is
 compared with the oracle in the -m gpu suites and with this fixture in tests/test_reference_pin_gpu.py."""
 import os
 
@@ -103,6 +106,68 @@ def test_oracle_m_estimator_weights_reproduce_the_reference(oracle_lib):
     eps = (1 - 0.1) / 0.1 * np.exp(-chi2.ppf(0.999, 2))
     w = np.exp(-3.0) / (np.exp(-3.0) + eps)
     assert abs(oa.m_estimator_weight(4, 3.0, 2.0, 0.999, 0.1) - w) <= 1e-12 * w
+
+
+def opt_problem(g, n):
+    from kalibr_b200.problem import KbOptimizerOptions, Problem
+
+    f = lambda name: g[f"opt{n}_{name}"]  # noqa: E731
+    p = Problem(driver_order=int(f("order")), cam_model=f("cam_model"), cam_params=f("cam_params"), baselines=f("baselines"), set_poses=f("set_poses"),
+                target_points=f("target_points"), view_set=f("view_set"), view_cam=f("view_cam"), view_begin=f("view_begin"), y_u=f("y_u"), y_v=f("y_v"),
+                corner_id=f("corner_id"))
+    opt = KbOptimizerOptions.kalibr2_default(device_loop=0)
+    opt.lm_lambda_init = float(f("lambda_init"))
+    return p, opt
+
+
+def check_against_reference_optimizer(g, n, solve):
+    """solve(problem, options) -> (KbSolution, cam_params, baselines, set_poses): the whole run and the runs cut after 1, 2, ... iterations
+    must walk the reference's iterations: same counts, same cost (1e-9), same final design variables (1e-6 of their scale; the
+    factorisations differ in rounding and the last accepted steps are ~1e-3 of it)"""
+    p, opt = opt_problem(g, n)
+    it, failed, j_start, j_final, lsf = g[f"opt{n}_result"]
+    sol, cp, bl, sp = solve(p, opt)
+    assert (sol.iterations, sol.failed_iterations, sol.linear_solver_failure) == (int(it), int(failed), int(lsf))
+    assert abs(sol.j_start - j_start) <= 1e-11 * j_start and abs(sol.j_final - j_final) <= 1e-9 * j_final
+    for mine, ref in ((cp, g[f"opt{n}_final_cam_params"]), (np.reshape(bl, (-1, 7)), g[f"opt{n}_final_baselines"].reshape(-1, 7)), (sp, g[f"opt{n}_final_set_poses"])):
+        if ref.size:
+            assert np.abs(np.asarray(mine) - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1.0)
+    for k, (itk, failedk, _, jk, lsfk) in enumerate(g[f"opt{n}_truncated"], start=1):
+        opt.max_iterations = k
+        s = solve(p, opt)[0]
+        assert (s.iterations, s.failed_iterations, s.linear_solver_failure) == (int(itk), int(failedk), int(lsfk)), k
+        assert abs(s.j_final - jk) <= 1e-9 * jk, k
+
+
+N_OPT = 11
+
+
+@pytest.mark.parametrize("n", range(N_OPT))
+def test_oracle_optimizer_walks_the_reference_optimizer(oracle_lib, n):
+    """rows a1, a2, a19-a25: Optimizer2::optimize with the LM policy and the BlockCholesky solver (Q1 / Q2 damping, rejected steps and
+    reverts, the sticky linear-solver failure of problem 3) - the reference's compiled loop against the oracle's restatement"""
+    g = np.load(GOLD)
+    assert int(g["opt_count"]) == N_OPT
+
+    def solve(p, opt):
+        o = oa.OracleProblem(p)
+        sol, _ = o.optimize(opt)
+        return sol, o.camera_params(), o.baselines(), o.set_poses()
+
+    check_against_reference_optimizer(g, n, solve)
+    assert sum(int(g[f"opt{i}_result"][1]) > 0 for i in range(N_OPT)) >= 4 and sum(int(g[f"opt{i}_result"][4]) for i in range(N_OPT)) >= 1
+
+
+def test_optimizer_fixture_is_what_the_reference_returns_now(oracle_lib):
+    """build container only: the reference's compiled optimiser, run again, returns the committed numbers"""
+    if oa.build_reference_cameras() is None:
+        pytest.skip("no reference tree and no prebuilt oracle/_ref here")
+    g = np.load(GOLD)
+    for n in (0, 1, 2, 8, 9):
+        p, opt = opt_problem(g, n)
+        r, cp, bl, sp = oa.reference_optimize(p, opt)
+        assert [r["iterations"], r["failed_iterations"], r["j_start"], r["j_final"], r["linear_solver_failure"]] == list(g[f"opt{n}_result"])
+        assert np.array_equal(cp, g[f"opt{n}_final_cam_params"]) and np.array_equal(sp, g[f"opt{n}_final_set_poses"])
 
 
 def test_fixture_is_what_the_reference_returns_now(oracle_lib):

@@ -34,3 +34,23 @@ def test_kernels_reproduce_the_reference_terms(capi, tag):
     s.build_system()
     rhs_ref = -(rows.T @ res)
     assert np.abs(s.rhs() - rhs_ref).max() <= 1e-9 * np.abs(rhs_ref).max()
+
+
+@pytest.mark.parametrize("device_loop", [1, 0], ids=["device-loop", "host-loop"])
+@pytest.mark.parametrize("n", range(11))
+def test_kb_optimize_walks_the_reference_optimizer(capi, n, device_loop):
+    """kb_optimize (the LM loop resident on the device, and the host-side Optimizer2 mirror over the call-by-call entry points) against what the
+    REFERENCE's own compiled Optimizer2 / LevenbergMarquardtTrustRegionPolicy / BlockCholeskyLinearSystemSolver returned for the same eleven
+    problems (tests/golden/make_reference_golden.py, oracle/ref_pin_optimizer.cpp): iteration and failed-iteration counts, the cost after every
+    iteration, the final design variables, the sticky linear-solver failure of problem 3 - without the oracle in between"""
+    from test_reference_pin_cpu import check_against_reference_optimizer
+
+    g = np.load(GOLD)
+
+    def solve(p, opt):
+        opt.device_loop = device_loop
+        s = capi.B200SchurLinearSystemSolver(p)
+        sol, _ = s.optimize(opt)
+        return sol, s.camera_params(), s.baselines(), s.set_poses()
+
+    check_against_reference_optimizer(g, n, solve)
