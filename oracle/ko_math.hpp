@@ -6,11 +6,14 @@
 // Jacobian rows) and the M-estimator weights - against the REFERENCE'S OWN CODE: oracle/ref_pin.cpp compiles the reference's headers and
 // sources where they lie under /root/reference against stand-in headers for Eigen / Boost / OpenCV / sm_* (oracle/ref_shim/; none of those
 // libraries is in this image) into the git-ignored oracle/_ref/, its outputs are committed as tests/golden/reference_golden.npz and
-// tests/test_reference_pin_cpu.py holds this restatement to them (bit-identical in the build container).  UNPINNED for the rest - the
-// design-variable order, the Hessian assembly, the CHOLMOD solve with its damping quirk, the LM policy: the reference stores no golden
-// vectors for them and those sources need SuiteSparse / a thread pool / the sparse block matrix; that part is held
-// only by the reference's own property tests re-expressed in tests/ (H == J^T J, Schur == dense, solver-vs-solver) and by an
-// independent derivation (tests/independent_model.py).  Each function cites the reference file:line it follows.
+// tests/test_reference_pin_cpu.py holds this restatement to them (bit-identical in the build container).  PINNED for the LOOP too - design-
+// variable order, ErrorTermFs::buildHessian, JacobianContainer::evaluateHessian, SparseBlockMatrix accumulation, the BlockCholesky solver's
+// damping quirk, the LM policy, Optimizer2::optimize with update / revert / sticky solver failure: oracle/ref_pin_optimizer.cpp compiles
+// those reference sources the same way and runs eleven small calibrations; counts, cost per iteration and final design variables are in the
+// same fixture (keys opt*) and the same test file holds ko_optimize to them.  UNPINNED: the CHOLMOD factorisation itself (a dense Cholesky
+// stands in for it in the pin; here an exact block-arrow Cholesky), the SparseCholesky / CCS regime and the camera design-variable adapter
+// glue (they need SuiteSparse / OpenCV): held by the reference's own property tests re-expressed in tests/ (H == J^T J, Schur == dense,
+// solver-vs-solver) and by an independent derivation (tests/independent_model.py).  Each function cites the reference file:line it follows.
 //
 // ko_math.hpp: a small heap-backed dense matrix (stands in for Eigen::MatrixXd so the CPU baseline keeps the
 // reference's per-term heap-allocation structure) and the sm_kinematics helpers.

@@ -134,6 +134,29 @@ def reference_optimize(problem, options=None):
     return res, cp, bl, sp
 
 
+def reference_time_evaluate_build(problem, n_threads: int = 4, repeats: int = 1):
+    """seconds the REFERENCE's own code (oracle/ref_pin_optimizer.cpp: ref_time_evaluate_build) spends on one Optimizer2::evaluateError and one
+    BlockCholeskyLinearSystemSolver::buildSystem of `problem`: dict(setup_s, evaluate_s, build_s, cost)"""
+    reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
+    p = problem
+    cp = np.array(p.cam_params, np.float64, order="C")
+    bl = np.array(p.baselines, np.float64, order="C").reshape(-1, 7)
+    sp = np.array(p.set_poses, np.float64, order="C")
+    cm, vs, vc = (np.ascontiguousarray(a, np.int32) for a in (p.cam_model, p.view_set, p.view_cam))
+    vb = np.ascontiguousarray(p.view_begin, np.int64)
+    yu, yv, tp = (np.ascontiguousarray(a, np.float64) for a in (p.y_u, p.y_v, p.target_points))
+    ci = np.ascontiguousarray(p.corner_id, np.int32)
+    out = np.zeros(4)
+    fn = _ref_lib.ref_time_evaluate_build
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_int32] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p]
+    rc = fn(len(cm), _p(cm), _p(cp), _p(bl), len(sp), _p(sp), len(tp), _p(tp), len(vs), _p(vs), _p(vc), _p(vb), _p(yu), _p(yv), _p(ci),
+            int(p.driver_order), int(n_threads), int(repeats), _p(out))
+    if rc != 0:
+        raise RuntimeError("ref_time_evaluate_build failed")
+    return dict(setup_s=float(out[0]), evaluate_s=float(out[1]), build_s=float(out[2]), cost=float(out[3]))
+
+
 def kinematics(name: str, *args):
     """the oracle's restatement of the same helpers (ko_math.hpp)"""
     a = [np.ascontiguousarray(x, np.float64) for x in args]

@@ -30,6 +30,7 @@
 #include <aslam/backend/TransformationBasic.hpp>
 #include <aslam/backend/TransformationExpression.hpp>
 
+#include <chrono>
 #include <cstdint>
 #include <vector>
 
@@ -131,16 +132,29 @@ class ReprojectionTerm : public ErrorTermFs<2> {
 // Problem in the layout of include/kalibr_b200.h (kb_problem_desc); design variables are added in the order of the driver named by
 // driver_order (kb_driver_order: 0/2 = cameras, baselines, then one pose per synced set, K2/CalibrationTools.hpp:183-300, 375-408;
 // 1 = baselines, poses, cameras, :222-262; 3 = poses, baselines, cameras, :460-491); error terms in term order.
-// out_scalars: [iterations, failedIterations, JStart, JFinal, linearSolverFailure]; state arrays are updated in place.
-extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32_t n_cams, const int32_t* cam_model, double* cam_params /*[n_cams][10]*/,
-                                                                           double* baselines /*[n_cams-1][7]*/, int32_t n_sets, double* set_poses /*[n_sets][7]*/,
-                                                                           int32_t n_target, const double* target /*[n_target][3]*/, int32_t n_views,
-                                                                           const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
-                                                                           const double* y_u, const double* y_v, const int32_t* corner_id, int32_t driver_order, int32_t max_iterations,
-                                                                           double conv_dx, double conv_dj, double lambda_init, double* out_scalars) {
-  try {
-    boost::shared_ptr<OptimizationProblem> problem(new OptimizationProblem());
-    std::vector<CameraModel> cams(n_cams);
+namespace {
+struct RigProblem {
+  boost::shared_ptr<OptimizationProblem> problem;
+  std::vector<CameraModel> cams;
+  std::vector<boost::shared_ptr<RotationQuaternion>> bq, sq;
+  std::vector<boost::shared_ptr<EuclideanPoint>> bt, st;
+  std::vector<boost::shared_ptr<TransformationBasic>> B, S;
+  std::vector<boost::shared_ptr<HomogeneousPoint>> points;
+
+  boost::shared_ptr<TransformationBasic> addPose(const double* p, std::vector<boost::shared_ptr<RotationQuaternion>>& qs, std::vector<boost::shared_ptr<EuclideanPoint>>& ts) {
+    qs.push_back(boost::make_shared<RotationQuaternion>(Eigen::Vector4d(p[0], p[1], p[2], p[3])));
+    qs.back()->setActive(true);
+    problem->addDesignVariable(qs.back());
+    ts.push_back(boost::make_shared<EuclideanPoint>(Eigen::Vector3d(p[4], p[5], p[6])));
+    ts.back()->setActive(true);
+    problem->addDesignVariable(ts.back());
+    return boost::make_shared<TransformationBasic>(qs.back()->toExpression(), ts.back()->toExpression());
+  }
+
+  RigProblem(int32_t n_cams, const int32_t* cam_model, const double* cam_params, const double* baselines, int32_t n_sets, const double* set_poses, int32_t n_target,
+             const double* target, int32_t n_views, const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin, const double* y_u, const double* y_v,
+             const int32_t* corner_id, int32_t driver_order)
+      : problem(new OptimizationProblem()), cams(n_cams) {
     auto addCameras = [&]() {
       for (int k = 0; k < n_cams; ++k) {
         CameraModel& c = cams[k];
@@ -156,24 +170,11 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32
         problem->addDesignVariable(c.dist);
       }
     };
-    auto addPose = [&](const double* p, std::vector<boost::shared_ptr<RotationQuaternion>>& qs, std::vector<boost::shared_ptr<EuclideanPoint>>& ts) {
-      qs.push_back(boost::make_shared<RotationQuaternion>(Eigen::Vector4d(p[0], p[1], p[2], p[3])));
-      qs.back()->setActive(true);
-      problem->addDesignVariable(qs.back());
-      ts.push_back(boost::make_shared<EuclideanPoint>(Eigen::Vector3d(p[4], p[5], p[6])));
-      ts.back()->setActive(true);
-      problem->addDesignVariable(ts.back());
-      return boost::make_shared<TransformationBasic>(qs.back()->toExpression(), ts.back()->toExpression());
-    };
-    std::vector<boost::shared_ptr<RotationQuaternion>> bq, sq;
-    std::vector<boost::shared_ptr<EuclideanPoint>> bt, st;
-    std::vector<boost::shared_ptr<TransformationBasic>> B, S;
     auto addBaselines = [&]() { for (int j = 0; j + 1 < n_cams; ++j) B.push_back(addPose(baselines + 7 * j, bq, bt)); };
     auto addSets = [&]() { for (int v = 0; v < n_sets; ++v) S.push_back(addPose(set_poses + 7 * v, sq, st)); };
     if (driver_order == 1) { addBaselines(); addSets(); addCameras(); }
     else if (driver_order == 3) { addSets(); addBaselines(); addCameras(); }
     else { addCameras(); addBaselines(); addSets(); }
-    std::vector<boost::shared_ptr<HomogeneousPoint>> points;
     for (int i = 0; i < n_target; ++i) points.push_back(boost::make_shared<HomogeneousPoint>(Eigen::Vector4d(target[3 * i], target[3 * i + 1], target[3 * i + 2], 1.0)));
     for (int w = 0; w < n_views; ++w) {
       TransformationExpression T_cam_w = S[view_set[w]]->toExpression().inverse();
@@ -181,6 +182,19 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32
       for (int64_t i = view_begin[w]; i < view_begin[w + 1]; ++i)
         problem->addErrorTerm(boost::make_shared<ReprojectionTerm>(Eigen::Vector2d(y_u[i], y_v[i]), T_cam_w * points[corner_id[i]]->toExpression(), &cams[view_cam[w]]));
     }
+  }
+};
+}  // namespace
+
+// out_scalars: [iterations, failedIterations, JStart, JFinal, linearSolverFailure]; state arrays are updated in place.
+extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32_t n_cams, const int32_t* cam_model, double* cam_params /*[n_cams][10]*/,
+                                                                           double* baselines /*[n_cams-1][7]*/, int32_t n_sets, double* set_poses /*[n_sets][7]*/,
+                                                                           int32_t n_target, const double* target /*[n_target][3]*/, int32_t n_views,
+                                                                           const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
+                                                                           const double* y_u, const double* y_v, const int32_t* corner_id, int32_t driver_order, int32_t max_iterations,
+                                                                           double conv_dx, double conv_dj, double lambda_init, double* out_scalars) {
+  try {
+    RigProblem rp(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id, driver_order);
     Optimizer2Options options;  // K2/CalibrationTools.hpp:57-66
     options.nThreads = 1;
     options.convergenceDeltaX = conv_dx;
@@ -189,7 +203,7 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32
     options.trustRegionPolicy = boost::make_shared<LevenbergMarquardtTrustRegionPolicy>(lambda_init);
     options.linearSystemSolver = boost::make_shared<BlockCholeskyLinearSystemSolver>();
     Optimizer2 optimizer(options);
-    optimizer.setProblem(problem);
+    optimizer.setProblem(rp.problem);
     SolutionReturnValue r = optimizer.optimize();
     out_scalars[0] = r.iterations;
     out_scalars[1] = r.failedIterations;
@@ -197,18 +211,62 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32
     out_scalars[3] = r.JFinal;
     out_scalars[4] = r.linearSolverFailure ? 1.0 : 0.0;
     for (int k = 0; k < n_cams; ++k)
-      for (int i = 0; i < 10; ++i) cam_params[k * 10 + i] = cams[k].prm[i];
+      for (int i = 0; i < 10; ++i) cam_params[k * 10 + i] = rp.cams[k].prm[i];
     auto store = [](double* p, const boost::shared_ptr<RotationQuaternion>& q, const boost::shared_ptr<EuclideanPoint>& t) {
       const Eigen::Vector4d qv = q->getQuaternion();
       const Eigen::Vector3d tv = t->toEuclidean();
       for (int i = 0; i < 4; ++i) p[i] = qv(i);
       for (int i = 0; i < 3; ++i) p[4 + i] = tv(i);
     };
-    for (size_t j = 0; j < bq.size(); ++j) store(baselines + 7 * j, bq[j], bt[j]);
-    for (size_t v = 0; v < sq.size(); ++v) store(set_poses + 7 * v, sq[v], st[v]);
+    for (size_t j = 0; j < rp.bq.size(); ++j) store(baselines + 7 * j, rp.bq[j], rp.bt[j]);
+    for (size_t v = 0; v < rp.sq.size(); ++v) store(set_poses + 7 * v, rp.sq[v], rp.st[v]);
     return 0;
   } catch (const std::exception& e) {
     std::cerr << "ref_optimize_rig: " << e.what() << std::endl;
+    return -1;
+  }
+}
+
+// Timing of the reference's own evaluate + build on the same problem (bench.py's cpu_baseline, kind "reference"): Optimizer2::initialize,
+// then `repeats` x { Optimizer2::evaluateError(true) (threaded over nThreads: Optimizer2.cpp:300-345), the solver's buildSystem
+// -> BlockCholeskyLinearSystemSolver::buildSystem (serial in the reference: BlockCholeskyLinearSystemSolver.cpp:57-72) }.
+// out_seconds: [problem construction + initialize, evaluate per repeat, build per repeat, cost].  The SOLVE is not timed here: the
+// factorisation behind LinearSolverCholmod is a stand-in in this build (CHOLMOD is not in the image).
+extern "C" __attribute__((visibility("default"))) int32_t ref_time_evaluate_build(int32_t n_cams, const int32_t* cam_model, const double* cam_params, const double* baselines,
+                                                                                  int32_t n_sets, const double* set_poses, int32_t n_target, const double* target,
+                                                                                  int32_t n_views, const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
+                                                                                  const double* y_u, const double* y_v, const int32_t* corner_id, int32_t driver_order,
+                                                                                  int32_t n_threads, int32_t repeats, double* out_seconds) {
+  try {
+    typedef std::chrono::steady_clock clock;
+    auto seconds = [](clock::time_point a, clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const clock::time_point t0 = clock::now();
+    RigProblem rp(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id, driver_order);
+    Optimizer2Options options;
+    options.nThreads = n_threads;
+    options.trustRegionPolicy = boost::make_shared<LevenbergMarquardtTrustRegionPolicy>(10.0);
+    options.linearSystemSolver = boost::make_shared<BlockCholeskyLinearSystemSolver>();
+    Optimizer2 optimizer(options);
+    optimizer.setProblem(rp.problem);
+    optimizer.initialize();
+    const clock::time_point t1 = clock::now();
+    double te = 0.0, tb = 0.0, J = 0.0;
+    for (int r = 0; r < repeats; ++r) {
+      const clock::time_point a = clock::now();
+      J = optimizer.evaluateError(true);
+      const clock::time_point b = clock::now();
+      optimizer.getSolver<BlockCholeskyLinearSystemSolver>()->buildSystem(n_threads, true);  // what the policy calls (LevenbergMarquardtTrustRegionPolicy.cpp:72)
+      const clock::time_point c = clock::now();
+      te += seconds(a, b);
+      tb += seconds(b, c);
+    }
+    out_seconds[0] = seconds(t0, t1);
+    out_seconds[1] = te / repeats;
+    out_seconds[2] = tb / repeats;
+    out_seconds[3] = J;
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << "ref_time_evaluate_build: " << e.what() << std::endl;
     return -1;
   }
 }
