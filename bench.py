@@ -166,24 +166,43 @@ def cpu_regimes(config, cpu_sets, steps_each, warmup=1):
                     "stage_s_per_iteration": {"evaluate": st[0] / steps, "build": st[1] / steps, "solve": st[2] / steps},
                     "problem_construction_s": build_s})
         o.close()
-    # the REFERENCE's own evaluate + build (Optimizer2::evaluateError, BlockCholeskyLinearSystemSolver::buildSystem, its expression tree,
-    # JacobianContainer and SparseBlockMatrix compiled from the reference's sources into oracle/_ref, against stand-in Eigen / Boost
+    # the REFERENCE's own evaluate + build (Optimizer2::evaluateError, then BlockCholeskyLinearSystemSolver::buildSystem or
+    # SparseCholeskyLinearSystemSolver::buildSystem with its CompressedColumnJacobianTransposeBuilder; the expression tree, JacobianContainer,
+    # SparseBlockMatrix and CompressedColumnMatrix compiled from the reference's sources into oracle/_ref, against stand-in Eigen / Boost
     # headers: oracle/ref_pin_optimizer.cpp) on the same sample, when that prebuilt library travelled here.  Its solve is not
-    # reference code in this image (no CHOLMOD), so the step takes the port's BlockCholesky solve time.  The same code that pins the
+    # reference code in this image (no CHOLMOD), so the step takes the port's solve time of the same regime.  The same code that pins the
     # oracle's numbers (tests/test_reference_pin_cpu.py) here shows the port is not a slow stand-in for it.
     if oa.build_reference_cameras() is not None:
-        port_solve = min(r["stage_s_per_iteration"]["solve"] for r in out if r["solver"] == "block")
-        try:
-            t = oa.reference_time_evaluate_build(ps, cores, max(steps_each, 1))
-            step_s = t["evaluate_s"] + t["build_s"] + port_solve
-            out.append({"regime": "BlockCholesky through the reference's own compiled evaluate + build (oracle/_ref; stand-in Eigen / Boost headers; solve time from the port)",
-                        "solver": "block", "kind": "reference", "threads": cores, "value": ps.n_terms / step_s, "unit": UNIT, "ms_per_step": 1e3 * step_s,
-                        "steps": max(steps_each, 1), "stage_s_per_iteration": {"evaluate": t["evaluate_s"], "build": t["build_s"], "solve": port_solve},
-                        "problem_construction_s": t["setup_s"]})
-        except Exception as e:  # the checker's library is optional on the box; the port regimes above always run
-            out.append({"regime": "reference's own compiled evaluate + build", "kind": "reference", "unavailable": repr(e), "value": 0.0, "solver": "block", "threads": cores})
+        for solver, kind_id, what in (("block", oa.BLOCK_CHOLESKY_KIND, "BlockCholesky (serial Hessian assembly)"),
+                                      ("sparse", oa.SPARSE_CHOLESKY_KIND, "SparseCholesky (Kalibr2's default: threaded materialisation of the compressed-column J^T)")):
+            port_solve = min(r["stage_s_per_iteration"]["solve"] for r in out if r["solver"] == solver and r.get("kind") != "reference")
+            try:
+                t = reference_evaluate_build_isolated(config, cpu_sets, cores, max(steps_each, 1), kind_id)
+                step_s = t["evaluate_s"] + t["build_s"] + port_solve
+                out.append({"regime": f"{what} through the reference's own compiled evaluate + build (oracle/_ref; stand-in Eigen / Boost headers; solve time from the port)",
+                            "solver": solver, "kind": "reference", "config": config, "threads": cores, "value": ps.n_terms / step_s, "unit": UNIT, "ms_per_step": 1e3 * step_s,
+                            "steps": max(steps_each, 1), "stage_s_per_iteration": {"evaluate": t["evaluate_s"], "build": t["build_s"], "solve": port_solve},
+                            "problem_construction_s": t["setup_s"]})
+            except Exception as e:  # the checker's library is optional on the box; the port regimes above always run
+                out.append({"regime": f"{what} through the reference's own compiled evaluate + build", "kind": "reference", "unavailable": repr(e), "value": 0.0,
+                            "solver": solver, "threads": cores})
     best = max(range(len(out)), key=lambda i: out[i]["value"])
     return out, best, ps
+
+
+def reference_evaluate_build_isolated(config, cpu_sets, threads, repeats, solver_kind):
+    """oracle/reference_timing.py in a process of its own (the reference's code over stand-in headers, threaded: a failure there must not
+    take the bench with it): dict(setup_s, evaluate_s, build_s, cost); raises when the child fails or the library is not there"""
+    import subprocess
+
+    r = subprocess.run([sys.executable, "-m", "oracle.reference_timing", str(config), str(cpu_sets), str(threads), str(repeats), str(solver_kind)],
+                       cwd=ROOT, capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        raise RuntimeError(f"oracle.reference_timing exited with {r.returncode}: {r.stderr.strip()[-200:]}")
+    t = json.loads(r.stdout.strip().splitlines()[-1])
+    if "unavailable" in t:
+        raise RuntimeError(t["unavailable"])
+    return t
 
 
 def time_cpu_regime(head, ps, steps, warmup):
@@ -192,7 +211,7 @@ def time_cpu_regime(head, ps, steps, warmup):
 
     K = max(steps, 1)
     if head.get("kind") == "reference":
-        t = oa.reference_time_evaluate_build(ps, head["threads"], K)
+        t = reference_evaluate_build_isolated(head["config"], int(ps.n_sets), head["threads"], K, oa.SPARSE_CHOLESKY_KIND if head["solver"] == "sparse" else oa.BLOCK_CHOLESKY_KIND)
         solve = head["stage_s_per_iteration"]["solve"]
         step_s = t["evaluate_s"] + t["build_s"] + solve
         return ps.n_terms / step_s, 1e3 * step_s, {"evaluate": t["evaluate_s"], "build": t["build_s"], "solve": solve}
@@ -213,7 +232,7 @@ def time_cpu_regime(head, ps, steps, warmup):
 def cpu_sample_text(config, ps, cores):
     return (f"bounded sample of the workload: cfg{config} restricted to {ps.n_sets} of its synced sets ({ps.n_terms} terms); one step = evaluate + "
             f"build + solve(lambda = 10); regimes: SparseCholesky (Kalibr2's default) / BlockCholesky semantic x 4 threads (the reference's default) / "
-            f"{cores} threads (all host cores), each through the oracle port, plus the BlockCholesky evaluate + build through the reference's own compiled code "
+            f"{cores} threads (all host cores), each through the oracle port, plus the evaluate + build of both regimes through the reference's own compiled code "
             f"(oracle/_ref, kind 'reference') when that library is present; headline = the fastest of them; throughput metric, so the sample size does not enter the unit")
 
 

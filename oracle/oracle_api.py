@@ -3,8 +3,10 @@
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs, never by
 kalibr_b200/.  PARITY: the per-term part (camera models, SE(3) helpers, the expression tree of a reprojection term, M-estimator weights) is
 PINNED against the reference's own code (oracle/ref_pin.cpp compiled from /root/reference against the stand-in headers of oracle/ref_shim/;
-tests/golden/reference_golden.npz; tests/test_reference_pin_cpu.py); the design-variable order, Hessian assembly, solver and LM policy are
-UNPINNED (see oracle/ko_math.hpp).
+tests/golden/reference_golden.npz; tests/test_reference_pin_cpu.py), and so are the design-variable order, the Hessian assembly, the
+BlockCholesky solver's damping, the LM policy and the optimiser loop (oracle/ref_pin_optimizer.cpp) and the SparseCholesky regime - the
+compressed-column J^T, its right-hand side and the loop over SparseCholeskyLinearSystemSolver (tests/golden/reference_sparse_golden.npz).
+Only the CHOLMOD factorisation itself is a stand-in there (see oracle/ko_math.hpp).
 """
 from __future__ import annotations
 
@@ -29,6 +31,8 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+BLOCK_CHOLESKY_KIND, SPARSE_CHOLESKY_KIND = 0, 1  # solver_kind of the reference-pin entry points
+
 REFERENCE_DIR = os.environ.get("KALIBR_REFERENCE", "/root/reference")
 _REF_LIB_PATH = os.path.join(_HERE, "_ref", "libkalibr_ref.so")
 _ref_lib = None
@@ -38,7 +42,7 @@ def build_reference_cameras(force: bool = False):
     """oracle/_ref/libkalibr_ref.so: the REFERENCE's camera models compiled from the sources where they lie (oracle/ref_pin.cpp).
     Returns the path, or None when neither the reference tree nor a built library is there (the GPU box: only prebuilt files travel)."""
     have_ref = os.path.isdir(os.path.join(REFERENCE_DIR, "aslam_cv", "aslam_cameras"))
-    srcs = [os.path.join(_HERE, f) for f in ("ref_pin.cpp", "ref_pin_optimizer.cpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("ref_pin.cpp", "ref_pin_optimizer.cpp", os.path.join("ref_shim", "cholmod.h"))]
     if have_ref and (force or not os.path.exists(_REF_LIB_PATH) or any(os.path.getmtime(f) > os.path.getmtime(_REF_LIB_PATH) for f in srcs)):
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "REFERENCE=" + REFERENCE_DIR, "_ref/libkalibr_ref.so"], check=True)
     return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
@@ -104,56 +108,78 @@ def reference_m_estimator_weight(kind: int, squared_error: float, p0: float = 0.
     return float(fn(kind, p0, p1, p2, squared_error))
 
 
-def reference_optimize(problem, options=None):
-    """the REFERENCE's Optimizer2::optimize (BE/src/Optimizer2.cpp, LevenbergMarquardtTrustRegionPolicy.cpp, BlockCholeskyLinearSystemSolver.cpp,
-    ErrorTerm / JacobianContainer / OptimizationProblem / SparseBlockMatrix, the expression tree and the camera models, all compiled from the
-    reference's sources: oracle/ref_pin_optimizer.cpp) on a kalibr_b200.problem.Problem, design variables in the problem's driver order.
-    Returns (dict(iterations, failed_iterations, j_start, j_final, linear_solver_failure), cam_params, baselines, set_poses)."""
+def _reference_problem_arrays(p):
+    """the arrays of a kalibr_b200.problem.Problem as the ref_* entry points of oracle/ref_pin_optimizer.cpp take them"""
+    cp = np.array(p.cam_params, np.float64, order="C")
+    bl = np.array(p.baselines, np.float64, order="C").reshape(-1, 7)
+    sp = np.array(p.set_poses, np.float64, order="C")
+    cm, vs, vc = (np.ascontiguousarray(a, np.int32) for a in (p.cam_model, p.view_set, p.view_cam))
+    vb = np.ascontiguousarray(p.view_begin, np.int64)
+    yu, yv, tp = (np.ascontiguousarray(a, np.float64) for a in (p.y_u, p.y_v, p.target_points))
+    ci = np.ascontiguousarray(p.corner_id, np.int32)
+    keep = (cp, bl, sp, cm, vs, vc, vb, yu, yv, tp, ci)
+    args = [len(cm), _p(cm), _p(cp), _p(bl), len(sp), _p(sp), len(tp), _p(tp), len(vs), _p(vs), _p(vc), _p(vb), _p(yu), _p(yv), _p(ci), int(p.driver_order)]
+    types = [C.c_int32] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 6 + [C.c_int32]
+    return keep, args, types
+
+
+def reference_optimize(problem, options=None, solver_kind: int = BLOCK_CHOLESKY_KIND, n_threads: int = 1):
+    """the REFERENCE's Optimizer2::optimize (BE/src/Optimizer2.cpp, LevenbergMarquardtTrustRegionPolicy.cpp, BlockCholeskyLinearSystemSolver.cpp
+    or - solver_kind 1 - SparseCholeskyLinearSystemSolver.cpp with CompressedColumnJacobianTransposeBuilder / CompressedColumnMatrix / the
+    Cholmod wrapper, ErrorTerm / JacobianContainer / OptimizationProblem / SparseBlockMatrix, the expression tree and the camera models, all
+    compiled from the reference's sources: oracle/ref_pin_optimizer.cpp) on a kalibr_b200.problem.Problem, design variables in the problem's
+    driver order.  Returns (dict(iterations, failed_iterations, j_start, j_final, linear_solver_failure), cam_params, baselines, set_poses)."""
     from kalibr_b200.problem import KbOptimizerOptions
 
     reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
     o = options or KbOptimizerOptions.kalibr2_default()
-    p = problem
-    cp = np.array(p.cam_params, np.float64, order="C")
-    bl = np.array(p.baselines, np.float64, order="C").reshape(-1, 7)
-    sp = np.array(p.set_poses, np.float64, order="C")
-    cm, vs, vc = (np.ascontiguousarray(a, np.int32) for a in (p.cam_model, p.view_set, p.view_cam))
-    vb = np.ascontiguousarray(p.view_begin, np.int64)
-    yu, yv, tp = (np.ascontiguousarray(a, np.float64) for a in (p.y_u, p.y_v, p.target_points))
-    ci = np.ascontiguousarray(p.corner_id, np.int32)
+    keep, args, types = _reference_problem_arrays(problem)
+    cp, bl, sp = keep[:3]
     out = np.zeros(8)
-    fn = _ref_lib.ref_optimize_rig
+    fn = _ref_lib.ref_optimize_rig_solver
     fn.restype = C.c_int32
-    fn.argtypes = ([C.c_int32] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 6
-                   + [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p])
-    rc = fn(len(cm), _p(cm), _p(cp), _p(bl), len(sp), _p(sp), len(tp), _p(tp), len(vs), _p(vs), _p(vc), _p(vb), _p(yu), _p(yv), _p(ci),
-            int(p.driver_order), int(o.max_iterations), float(o.convergence_delta_x), float(o.convergence_delta_j), float(o.lm_lambda_init), _p(out))
+    fn.argtypes = types + [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
+    rc = fn(*args, int(o.max_iterations), float(o.convergence_delta_x), float(o.convergence_delta_j), float(o.lm_lambda_init), int(solver_kind), int(n_threads), _p(out))
     if rc != 0:
-        raise RuntimeError("ref_optimize_rig failed")
+        raise RuntimeError("ref_optimize_rig_solver failed")
     res = dict(iterations=int(out[0]), failed_iterations=int(out[1]), j_start=float(out[2]), j_final=float(out[3]), linear_solver_failure=int(out[4]))
     return res, cp, bl, sp
 
 
-def reference_time_evaluate_build(problem, n_threads: int = 4, repeats: int = 1):
-    """seconds the REFERENCE's own code (oracle/ref_pin_optimizer.cpp: ref_time_evaluate_build) spends on one Optimizer2::evaluateError and one
-    BlockCholeskyLinearSystemSolver::buildSystem of `problem`: dict(setup_s, evaluate_s, build_s, cost)"""
+def reference_sparse_system(problem, lam: float = 10.0, n_threads: int = 1):
+    """the SparseCholesky regime's linear system from the REFERENCE's own classes (oracle/ref_pin_optimizer.cpp: ref_sparse_system): J^T in
+    compressed-column form as CompressedColumnJacobianTransposeBuilder<int> lays it out, the error vector, rhs = J^T e as
+    SparseCholeskyLinearSystemSolver::buildSystem forms it, and dx of one solveSystem under the constant conditioner `lam`.
+    dict(col_ptr [rows + 1] int64, row_ind int32, values, e, rhs, dx (None when the solve failed), cost, jcols)"""
     reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
-    p = problem
-    cp = np.array(p.cam_params, np.float64, order="C")
-    bl = np.array(p.baselines, np.float64, order="C").reshape(-1, 7)
-    sp = np.array(p.set_poses, np.float64, order="C")
-    cm, vs, vc = (np.ascontiguousarray(a, np.int32) for a in (p.cam_model, p.view_set, p.view_cam))
-    vb = np.ascontiguousarray(p.view_begin, np.int64)
-    yu, yv, tp = (np.ascontiguousarray(a, np.float64) for a in (p.y_u, p.y_v, p.target_points))
-    ci = np.ascontiguousarray(p.corner_id, np.int32)
-    out = np.zeros(4)
-    fn = _ref_lib.ref_time_evaluate_build
+    keep, args, types = _reference_problem_arrays(problem)
+    fn = _ref_lib.ref_sparse_system
     fn.restype = C.c_int32
-    fn.argtypes = [C.c_int32] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p]
-    rc = fn(len(cm), _p(cm), _p(cp), _p(bl), len(sp), _p(sp), len(tp), _p(tp), len(vs), _p(vs), _p(vc), _p(vb), _p(yu), _p(yv), _p(ci),
-            int(p.driver_order), int(n_threads), int(repeats), _p(out))
-    if rc != 0:
-        raise RuntimeError("ref_time_evaluate_build failed")
+    fn.argtypes = types + [C.c_int32, C.c_double] + [C.c_void_p] * 8
+    sizes = np.zeros(4, np.int64)
+    cost = np.zeros(1)
+    if fn(*args, int(n_threads), float(lam), _p(sizes), None, None, None, None, None, None, _p(cost)) != 0:
+        raise RuntimeError("ref_sparse_system failed")
+    jcols, jrows, nnz = (int(v) for v in sizes[:3])
+    col_ptr, row_ind, values = np.zeros(jrows + 1, np.int64), np.zeros(nnz, np.int32), np.zeros(nnz)
+    e, rhs, dx = np.zeros(jrows), np.zeros(jcols), np.zeros(jcols)
+    if fn(*args, int(n_threads), float(lam), _p(sizes), _p(col_ptr), _p(row_ind), _p(values), _p(e), _p(rhs), _p(dx), _p(cost)) != 0:
+        raise RuntimeError("ref_sparse_system failed")
+    return dict(col_ptr=col_ptr, row_ind=row_ind, values=values, e=e, rhs=rhs, dx=dx if sizes[3] else None, cost=float(cost[0]), jcols=jcols)
+
+
+def reference_time_evaluate_build(problem, n_threads: int = 4, repeats: int = 1, solver_kind: int = BLOCK_CHOLESKY_KIND):
+    """seconds the REFERENCE's own code (oracle/ref_pin_optimizer.cpp: ref_time_evaluate_build_solver) spends on one Optimizer2::evaluateError and
+    one buildSystem of `problem` - BlockCholeskyLinearSystemSolver's (serial Hessian assembly) or, solver_kind 1, SparseCholeskyLinearSystemSolver's
+    (Kalibr2's default: threaded materialisation of the compressed-column J^T + rhs): dict(setup_s, evaluate_s, build_s, cost)"""
+    reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
+    keep, args, types = _reference_problem_arrays(problem)
+    out = np.zeros(4)
+    fn = _ref_lib.ref_time_evaluate_build_solver
+    fn.restype = C.c_int32
+    fn.argtypes = types + [C.c_int32] * 3 + [C.c_void_p]
+    if fn(*args, int(solver_kind), int(n_threads), int(repeats), _p(out)) != 0:
+        raise RuntimeError("ref_time_evaluate_build_solver failed")
     return dict(setup_s=float(out[0]), evaluate_s=float(out[1]), build_s=float(out[2]), cost=float(out[3]))
 
 

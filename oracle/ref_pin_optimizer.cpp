@@ -9,6 +9,10 @@
 // and a plain additive parameter-block design variable in place of aslam_cv_backend's DesignVariableAdapter (parameter += delta; revert).
 // The per-term arithmetic these two stand for is pinned separately against the real classes (ref_pin.cpp).  What this file pins is the
 // LOOP: iteration and failed-iteration counts, the cost per iteration, the lambda schedule, the damping quirk, the final parameters.
+// The SparseCholesky regime (Kalibr2's default: Optimizer2.cpp:83-86) is here as well: SparseCholeskyLinearSystemSolver.cpp,
+// CompressedColumnJacobianTransposeBuilder, CompressedColumnMatrix and the reference's Cholmod wrapper compile from their sources; the
+// CHOLMOD entry points that wrapper calls are the dense extended-precision stand-in of ref_shim/cholmod.h (ref_sparse_system,
+// ref_optimize_rig_solver, ref_time_evaluate_build_solver below).
 #include <aslam/cameras/EquidistantDistortion.hpp>
 #include <aslam/cameras/FovDistortion.hpp>
 #include <aslam/cameras/NoDistortion.hpp>
@@ -19,6 +23,8 @@
 #include <aslam/cameras/ExtendedUnifiedProjection.hpp>
 
 #include <aslam/backend/BlockCholeskyLinearSystemSolver.hpp>
+#include <aslam/backend/CompressedColumnJacobianTransposeBuilder.hpp>
+#include <aslam/backend/SparseCholeskyLinearSystemSolver.hpp>
 #include <aslam/backend/ErrorTerm.hpp>
 #include <aslam/backend/EuclideanPoint.hpp>
 #include <aslam/backend/HomogeneousExpression.hpp>
@@ -187,21 +193,24 @@ struct RigProblem {
 }  // namespace
 
 // out_scalars: [iterations, failedIterations, JStart, JFinal, linearSolverFailure]; state arrays are updated in place.
-extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32_t n_cams, const int32_t* cam_model, double* cam_params /*[n_cams][10]*/,
-                                                                           double* baselines /*[n_cams-1][7]*/, int32_t n_sets, double* set_poses /*[n_sets][7]*/,
-                                                                           int32_t n_target, const double* target /*[n_target][3]*/, int32_t n_views,
-                                                                           const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
-                                                                           const double* y_u, const double* y_v, const int32_t* corner_id, int32_t driver_order, int32_t max_iterations,
-                                                                           double conv_dx, double conv_dj, double lambda_init, double* out_scalars) {
+// solver_kind: 0 = BlockCholeskyLinearSystemSolver, 1 = SparseCholeskyLinearSystemSolver (Kalibr2's default: Optimizer2.cpp:83-86; the
+// reference's own SparseCholeskyLinearSystemSolver.cpp, CompressedColumnJacobianTransposeBuilder, CompressedColumnMatrix and Cholmod
+// wrapper over the dense stand-in of ref_shim/cholmod.h).  n_threads: Optimizer2Options::nThreads (error evaluation and, for the sparse
+// solver, the Jacobian materialisation are threaded over it).
+static int32_t optimize_rig(int32_t n_cams, const int32_t* cam_model, double* cam_params, double* baselines, int32_t n_sets, double* set_poses, int32_t n_target,
+                            const double* target, int32_t n_views, const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin, const double* y_u,
+                            const double* y_v, const int32_t* corner_id, int32_t driver_order, int32_t max_iterations, double conv_dx, double conv_dj,
+                            double lambda_init, int32_t solver_kind, int32_t n_threads, double* out_scalars) {
   try {
     RigProblem rp(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id, driver_order);
     Optimizer2Options options;  // K2/CalibrationTools.hpp:57-66
-    options.nThreads = 1;
+    options.nThreads = n_threads;
     options.convergenceDeltaX = conv_dx;
     options.convergenceDeltaJ = conv_dj;
     options.maxIterations = max_iterations;
     options.trustRegionPolicy = boost::make_shared<LevenbergMarquardtTrustRegionPolicy>(lambda_init);
-    options.linearSystemSolver = boost::make_shared<BlockCholeskyLinearSystemSolver>();
+    if (solver_kind == 1) options.linearSystemSolver = boost::make_shared<SparseCholeskyLinearSystemSolver>();
+    else options.linearSystemSolver = boost::make_shared<BlockCholeskyLinearSystemSolver>();
     Optimizer2 optimizer(options);
     optimizer.setProblem(rp.problem);
     SolutionReturnValue r = optimizer.optimize();
@@ -227,35 +236,127 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32
   }
 }
 
+extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig(int32_t n_cams, const int32_t* cam_model, double* cam_params /*[n_cams][10]*/,
+                                                                           double* baselines /*[n_cams-1][7]*/, int32_t n_sets, double* set_poses /*[n_sets][7]*/,
+                                                                           int32_t n_target, const double* target /*[n_target][3]*/, int32_t n_views,
+                                                                           const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
+                                                                           const double* y_u, const double* y_v, const int32_t* corner_id, int32_t driver_order, int32_t max_iterations,
+                                                                           double conv_dx, double conv_dj, double lambda_init, double* out_scalars) {
+  return optimize_rig(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id,
+                      driver_order, max_iterations, conv_dx, conv_dj, lambda_init, 0, 1, out_scalars);
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t ref_optimize_rig_solver(int32_t n_cams, const int32_t* cam_model, double* cam_params, double* baselines,
+                                                                                  int32_t n_sets, double* set_poses, int32_t n_target, const double* target,
+                                                                                  int32_t n_views, const int32_t* view_set, const int32_t* view_cam,
+                                                                                  const int64_t* view_begin, const double* y_u, const double* y_v,
+                                                                                  const int32_t* corner_id, int32_t driver_order, int32_t max_iterations, double conv_dx,
+                                                                                  double conv_dj, double lambda_init, int32_t solver_kind, int32_t n_threads,
+                                                                                  double* out_scalars) {
+  return optimize_rig(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id,
+                      driver_order, max_iterations, conv_dx, conv_dj, lambda_init, solver_kind, n_threads, out_scalars);
+}
+
+// The SparseCholesky regime's linear system as the reference's own classes hold it: J^T in compressed-column form
+// (CompressedColumnJacobianTransposeBuilder<int> -> CompressedColumnMatrix<int>: one column per residual row, the row indices of a
+// column in the order of the term's design variables, BE/.../implementation/CompressedColumnMatrix.hpp), the weighted error vector e
+// (LinearSystemSolver::evaluateError), rhs = J^T e exactly as SparseCholeskyLinearSystemSolver::buildSystem forms it
+// (CompressedColumnMatrix::rightMultiply), and dx of one solveSystem with the constant conditioner `lambda` (the damping block is pushed
+// as extra columns of J^T, so CHOLMOD - here the dense stand-in - factorises J^T J + lambda^2 I).
+// out_sizes: [rows of J^T (= columns of J), columns of J^T (= residual rows), nnz, solve succeeded]; with col_ptr == NULL only the sizes
+// are written.  col_ptr has columns + 1 entries.
+extern "C" __attribute__((visibility("default"))) int32_t ref_sparse_system(int32_t n_cams, const int32_t* cam_model, const double* cam_params, const double* baselines,
+                                                                            int32_t n_sets, const double* set_poses, int32_t n_target, const double* target, int32_t n_views,
+                                                                            const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin, const double* y_u,
+                                                                            const double* y_v, const int32_t* corner_id, int32_t driver_order, int32_t n_threads,
+                                                                            double lambda, int64_t* out_sizes, int64_t* col_ptr, int32_t* row_ind, double* values,
+                                                                            double* e, double* rhs, double* dx, double* cost) {
+  try {
+    RigProblem rp(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id, driver_order);
+    Optimizer2Options options;
+    options.nThreads = 1;
+    options.trustRegionPolicy = boost::make_shared<LevenbergMarquardtTrustRegionPolicy>(lambda);
+    options.linearSystemSolver = boost::make_shared<SparseCholeskyLinearSystemSolver>();
+    Optimizer2 optimizer(options);
+    optimizer.setProblem(rp.problem);
+    optimizer.initialize();  // block indices, column bases, row bases; the solver's initMatrixStructure
+    optimizer.evaluateError(true);  // one serial pass first (see time_evaluate_build below), then the threaded ones
+    optimizer.getSolver<SparseCholeskyLinearSystemSolver>()->buildSystem(1, true);
+    optimizer.options().nThreads = n_threads;
+    const double J = optimizer.evaluateError(true);
+    SparseCholeskyLinearSystemSolver* solver = optimizer.getSolver<SparseCholeskyLinearSystemSolver>();
+    solver->buildSystem(n_threads, true);
+    // the same builder class the solver holds privately, on the optimiser's own design-variable and error-term lists
+    std::vector<DesignVariable*> dvs;
+    for (size_t i = 0; i < optimizer.numDesignVariables(); ++i) dvs.push_back(optimizer.designVariable(i));
+    std::vector<ErrorTerm*> errors;
+    for (size_t i = 0; i < rp.problem->numErrorTerms(); ++i) errors.push_back(rp.problem->errorTerm(i));
+    CompressedColumnJacobianTransposeBuilder<int> builder;
+    builder.initMatrixStructure(dvs, errors);
+    builder.buildSystem(n_threads, true);
+    const CompressedColumnMatrix<int>& Jt = builder.J_transpose();
+    out_sizes[0] = Jt.rows();
+    out_sizes[1] = Jt.cols();
+    out_sizes[2] = Jt.nnz();
+    out_sizes[3] = 0;
+    if (!col_ptr) return 0;
+    for (size_t c = 0; c <= Jt.cols(); ++c) col_ptr[c] = Jt.col_ptr()[c];
+    for (size_t k = 0; k < Jt.nnz(); ++k) { row_ind[k] = Jt.row_ind()[k]; values[k] = Jt.values()[k]; }
+    const Eigen::VectorXd& ev = solver->e();
+    for (int i = 0; i < ev.size(); ++i) e[i] = ev[i];
+    const Eigen::VectorXd& rv = solver->rhs();
+    for (int i = 0; i < rv.size(); ++i) rhs[i] = rv[i];
+    solver->setConstantConditioner(lambda);
+    Eigen::VectorXd x;
+    const bool ok = solver->solveSystem(x);
+    out_sizes[3] = ok ? 1 : 0;
+    if (ok) for (int i = 0; i < x.size(); ++i) dx[i] = x[i];
+    *cost = J;
+    return 0;
+  } catch (const std::exception& ex) {
+    std::cerr << "ref_sparse_system: " << ex.what() << std::endl;
+    return -1;
+  }
+}
+
 // Timing of the reference's own evaluate + build on the same problem (bench.py's cpu_baseline, kind "reference"): Optimizer2::initialize,
-// then `repeats` x { Optimizer2::evaluateError(true) (threaded over nThreads: Optimizer2.cpp:300-345), the solver's buildSystem
-// -> BlockCholeskyLinearSystemSolver::buildSystem (serial in the reference: BlockCholeskyLinearSystemSolver.cpp:57-72) }.
+// then `repeats` x { Optimizer2::evaluateError(true) (threaded over nThreads: Optimizer2.cpp:300-345), the solver's buildSystem }.
+// solver_kind 0: BlockCholeskyLinearSystemSolver::buildSystem (serial in the reference: BlockCholeskyLinearSystemSolver.cpp:57-72);
+// solver_kind 1: SparseCholeskyLinearSystemSolver::buildSystem - Kalibr2's default - the Jacobian materialisation into the
+// compressed-column J^T threaded over nThreads (CompressedColumnJacobianTransposeBuilder.hpp:59-79) + rhs = J^T e.
 // out_seconds: [problem construction + initialize, evaluate per repeat, build per repeat, cost].  The SOLVE is not timed here: the
-// factorisation behind LinearSolverCholmod is a stand-in in this build (CHOLMOD is not in the image).
-extern "C" __attribute__((visibility("default"))) int32_t ref_time_evaluate_build(int32_t n_cams, const int32_t* cam_model, const double* cam_params, const double* baselines,
-                                                                                  int32_t n_sets, const double* set_poses, int32_t n_target, const double* target,
-                                                                                  int32_t n_views, const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
-                                                                                  const double* y_u, const double* y_v, const int32_t* corner_id, int32_t driver_order,
-                                                                                  int32_t n_threads, int32_t repeats, double* out_seconds) {
+// factorisation behind the reference's CHOLMOD wrappers is a stand-in in this build (CHOLMOD is not in the image).
+// One serial evaluate + build runs first (inside the set-up time): the expression nodes cache fixed-size matrices in members while they
+// evaluate, and the threaded passes store identical values into nodes that neighbouring terms share.
+static int32_t time_evaluate_build(int32_t n_cams, const int32_t* cam_model, const double* cam_params, const double* baselines, int32_t n_sets, const double* set_poses,
+                                   int32_t n_target, const double* target, int32_t n_views, const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
+                                   const double* y_u, const double* y_v, const int32_t* corner_id, int32_t driver_order, int32_t solver_kind, int32_t n_threads,
+                                   int32_t repeats, double* out_seconds) {
   try {
     typedef std::chrono::steady_clock clock;
     auto seconds = [](clock::time_point a, clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const clock::time_point t0 = clock::now();
     RigProblem rp(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id, driver_order);
     Optimizer2Options options;
-    options.nThreads = n_threads;
+    options.nThreads = 1;
     options.trustRegionPolicy = boost::make_shared<LevenbergMarquardtTrustRegionPolicy>(10.0);
-    options.linearSystemSolver = boost::make_shared<BlockCholeskyLinearSystemSolver>();
+    if (solver_kind == 1) options.linearSystemSolver = boost::make_shared<SparseCholeskyLinearSystemSolver>();
+    else options.linearSystemSolver = boost::make_shared<BlockCholeskyLinearSystemSolver>();
     Optimizer2 optimizer(options);
     optimizer.setProblem(rp.problem);
     optimizer.initialize();
+    LinearSystemSolver* solver = solver_kind == 1 ? static_cast<LinearSystemSolver*>(optimizer.getSolver<SparseCholeskyLinearSystemSolver>())
+                                                  : static_cast<LinearSystemSolver*>(optimizer.getSolver<BlockCholeskyLinearSystemSolver>());
+    optimizer.evaluateError(true);
+    solver->buildSystem(1, true);
+    optimizer.options().nThreads = n_threads;
     const clock::time_point t1 = clock::now();
     double te = 0.0, tb = 0.0, J = 0.0;
     for (int r = 0; r < repeats; ++r) {
       const clock::time_point a = clock::now();
       J = optimizer.evaluateError(true);
       const clock::time_point b = clock::now();
-      optimizer.getSolver<BlockCholeskyLinearSystemSolver>()->buildSystem(n_threads, true);  // what the policy calls (LevenbergMarquardtTrustRegionPolicy.cpp:72)
+      solver->buildSystem(n_threads, true);  // what the policy calls (LevenbergMarquardtTrustRegionPolicy.cpp:72)
       const clock::time_point c = clock::now();
       te += seconds(a, b);
       tb += seconds(b, c);
@@ -269,4 +370,23 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_time_evaluate_buil
     std::cerr << "ref_time_evaluate_build: " << e.what() << std::endl;
     return -1;
   }
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t ref_time_evaluate_build(int32_t n_cams, const int32_t* cam_model, const double* cam_params, const double* baselines,
+                                                                                  int32_t n_sets, const double* set_poses, int32_t n_target, const double* target,
+                                                                                  int32_t n_views, const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
+                                                                                  const double* y_u, const double* y_v, const int32_t* corner_id, int32_t driver_order,
+                                                                                  int32_t n_threads, int32_t repeats, double* out_seconds) {
+  return time_evaluate_build(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id,
+                             driver_order, 0, n_threads, repeats, out_seconds);
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t ref_time_evaluate_build_solver(int32_t n_cams, const int32_t* cam_model, const double* cam_params,
+                                                                                         const double* baselines, int32_t n_sets, const double* set_poses, int32_t n_target,
+                                                                                         const double* target, int32_t n_views, const int32_t* view_set,
+                                                                                         const int32_t* view_cam, const int64_t* view_begin, const double* y_u,
+                                                                                         const double* y_v, const int32_t* corner_id, int32_t driver_order,
+                                                                                         int32_t solver_kind, int32_t n_threads, int32_t repeats, double* out_seconds) {
+  return time_evaluate_build(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id,
+                             driver_order, solver_kind, n_threads, repeats, out_seconds);
 }
