@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see ko_math.hpp header: parity PINNED against the reference's own compiled code for the per-term part and the optimiser loop, UNPINNED for the CHOLMOD factorisation / CCS regime).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ko_math.hpp header: parity PINNED against the reference's own compiled code for the per-term part, the optimiser loop and both solver regimes, UNPINNED for the CHOLMOD factorisation itself).
 //
 // Problem construction (kalibr2 drivers), LinearSystemSolver / BlockCholesky / SparseCholesky semantics,
 // LevenbergMarquardtTrustRegionPolicy and Optimizer2, restated on the CPU behind a small C API (ko_*)

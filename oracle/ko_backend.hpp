@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see ko_math.hpp header: parity PINNED against the reference's own compiled code for the per-term part and the optimiser loop, UNPINNED for the CHOLMOD factorisation / CCS regime).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ko_math.hpp header: parity PINNED against the reference's own compiled code for the per-term part, the optimiser loop and both solver regimes, UNPINNED for the CHOLMOD factorisation itself).
 //
 // aslam_backend / aslam_backend_expressions / aslam_cv_error_terms restated on the CPU, object per term,
 // heap-backed small matrices and std::map containers like the reference so that it is a fair CPU baseline.

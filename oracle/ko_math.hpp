@@ -10,9 +10,12 @@
 // variable order, ErrorTermFs::buildHessian, JacobianContainer::evaluateHessian, SparseBlockMatrix accumulation, the BlockCholesky solver's
 // damping quirk, the LM policy, Optimizer2::optimize with update / revert / sticky solver failure: oracle/ref_pin_optimizer.cpp compiles
 // those reference sources the same way and runs eleven small calibrations; counts, cost per iteration and final design variables are in the
-// same fixture (keys opt*) and the same test file holds ko_optimize to them.  UNPINNED: the CHOLMOD factorisation itself (a dense Cholesky
-// stands in for it in the pin; here an exact block-arrow Cholesky), the SparseCholesky / CCS regime and the camera design-variable adapter
-// glue (they need SuiteSparse / OpenCV): held by the reference's own property tests re-expressed in tests/ (H == J^T J, Schur == dense,
+// same fixture (keys opt*) and the same test file holds ko_optimize to them.  PINNED for the SparseCholesky regime (Kalibr2's default) as
+// well: the reference's SparseCholeskyLinearSystemSolver.cpp, CompressedColumnJacobianTransposeBuilder, CompressedColumnMatrix and Cholmod
+// wrapper compile the same way; the compressed-column J^T (layout bit for bit), e, rhs, a damped step and the eleven calibrations over that
+// solver are in tests/golden/reference_sparse_golden.npz (tests/test_reference_sparse_pin_cpu.py).  UNPINNED: the CHOLMOD factorisation
+// itself (a dense Cholesky stands in for the library in the pin; here an exact block-arrow Cholesky) and the camera design-variable
+// adapter glue (they need SuiteSparse / OpenCV): held by the reference's own property tests re-expressed in tests/ (H == J^T J, Schur == dense,
 // solver-vs-solver) and by an independent derivation (tests/independent_model.py).  Each function cites the reference file:line it follows.
 //
 // ko_math.hpp: a small heap-backed dense matrix (stands in for Eigen::MatrixXd so the CPU baseline keeps the
