@@ -14,8 +14,8 @@
 // well: the reference's SparseCholeskyLinearSystemSolver.cpp, CompressedColumnJacobianTransposeBuilder, CompressedColumnMatrix and Cholmod
 // wrapper compile the same way; the compressed-column J^T (layout bit for bit), e, rhs, a damped step and the eleven calibrations over that
 // solver are in tests/golden/reference_sparse_golden.npz (tests/test_reference_sparse_pin_cpu.py).  UNPINNED: the CHOLMOD factorisation
-// itself (a dense Cholesky stands in for the library in the pin; here an exact block-arrow Cholesky) and the camera design-variable
-// adapter glue (they need SuiteSparse / OpenCV): held by the reference's own property tests re-expressed in tests/ (H == J^T J, Schur == dense,
+// itself (a dense Cholesky stands in for the library in the pin; here an exact block-arrow Cholesky) and the few lines of glue in
+// ReprojectionError / CameraDesignVariable around the pinned pieces (they need SuiteSparse / OpenCV): held by the reference's own property tests re-expressed in tests/ (H == J^T J, Schur == dense,
 // solver-vs-solver) and by an independent derivation (tests/independent_model.py).  Each function cites the reference file:line it follows.
 //
 // ko_math.hpp: a small heap-backed dense matrix (stands in for Eigen::MatrixXd so the CPU baseline keeps the

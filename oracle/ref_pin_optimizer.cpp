@@ -4,10 +4,11 @@
 // container, all compiled from the sources where they lie under /root/reference against the stand-in headers of oracle/ref_shim/.
 // NOT reference code in this translation unit, and said so where it stands: (1) the factorisation behind LinearSolverCholmod (CHOLMOD is
 // not in the image: a dense Cholesky over the reference's own SparseBlockMatrix, ref_shim/sparse_block_matrix/linear_solver_cholmod.h);
-// (2) the glue below - the error term, which restates CVE/.../implementation/ReprojectionError.hpp:50-77 line by line over the reference's
-// projection classes and expression tree (the reference's own template needs the CameraGeometry / Frame / Image headers, i.e. OpenCV),
-// and a plain additive parameter-block design variable in place of aslam_cv_backend's DesignVariableAdapter (parameter += delta; revert).
-// The per-term arithmetic these two stand for is pinned separately against the real classes (ref_pin.cpp).  What this file pins is the
+// (2) the glue below - the error term, which restates CVE/.../implementation/ReprojectionError.hpp:50-77 and the two active-block lines of
+// CVB/.../implementation/CameraDesignVariable.hpp:39-54 line by line over the reference's projection classes and expression tree (the
+// reference's own templates need the CameraGeometry / Frame / Image headers, i.e. OpenCV).  The camera design variables themselves ARE the
+// reference's: its DesignVariableAdapter over its projection and distortion objects, created as CameraDesignVariable creates them.
+// The per-term arithmetic the glue stands for is pinned separately against the real classes (ref_pin.cpp).  What this file pins is the
 // LOOP: iteration and failed-iteration counts, the cost per iteration, the lambda schedule, the damping quirk, the final parameters.
 // The SparseCholesky regime (Kalibr2's default: Optimizer2.cpp:83-86) is here as well: SparseCholeskyLinearSystemSolver.cpp,
 // CompressedColumnJacobianTransposeBuilder, CompressedColumnMatrix and the reference's Cholmod wrapper compile from their sources; the
@@ -23,6 +24,7 @@
 #include <aslam/cameras/ExtendedUnifiedProjection.hpp>
 
 #include <aslam/backend/BlockCholeskyLinearSystemSolver.hpp>
+#include <aslam/backend/DesignVariableAdapter.hpp>
 #include <aslam/backend/CompressedColumnJacobianTransposeBuilder.hpp>
 #include <aslam/backend/SparseCholeskyLinearSystemSolver.hpp>
 #include <aslam/backend/ErrorTerm.hpp>
@@ -44,57 +46,62 @@ using namespace aslam::backend;
 using namespace aslam::cameras;
 
 namespace {
-// a block of parameters with the update rule of DesignVariableAdapter over Projection::update / Distortion::update (parameter += delta)
-class ParameterBlock : public DesignVariable {
- public:
-  ParameterBlock(double* p, int n) : p_(p), n_(n), backup_(p, p + n) {}
- protected:
-  virtual int minimalDimensionsImplementation() const { return n_; }
-  virtual void updateImplementation(const double* dp, int size) {
-    backup_.assign(p_, p_ + n_);
-    for (int i = 0; i < size && i < n_; ++i) p_[i] += dp[i];
-  }
-  virtual void revertUpdateImplementation() { for (int i = 0; i < n_; ++i) p_[i] = backup_[i]; }
-  virtual void getParametersImplementation(Eigen::MatrixXd& value) const {
-    value.resize(n_, 1);
-    for (int i = 0; i < n_; ++i) value(i, 0) = p_[i];
-  }
-  virtual void setParametersImplementation(const Eigen::MatrixXd& value) { for (int i = 0; i < n_; ++i) p_[i] = value(i, 0); }
- private:
-  double* p_;
-  int n_;
-  std::vector<double> backup_;
-};
-
-struct CameraModel {  // parameters live here; the reference's projection object is built from them at every evaluation
-  int model;
-  double prm[10];
-  int P, D;
-  boost::shared_ptr<ParameterBlock> proj, dist;
-};
 const int N_P[7] = {4, 4, 5, 6, 6, 4, 5}, N_D[7] = {4, 4, 4, 0, 0, 1, 0};
 
-template <typename CAMERA>
-bool projectWith(const CAMERA& cam, const Eigen::Vector4d& ph, Eigen::VectorXd& y, Eigen::MatrixXd* J, Eigen::MatrixXd* Ji, Eigen::MatrixXd* Jd) {
-  if (!J) return cam.homogeneousToKeypoint(ph, y);
-  const bool ok = cam.homogeneousToKeypoint(ph, y, *J);
-  cam.homogeneousToKeypointIntrinsicsJacobian(ph, *Ji);
-  cam.homogeneousToKeypointDistortionJacobian(ph, *Jd);
-  return ok;
-}
-bool project(const CameraModel& c, const Eigen::Vector4d& ph, Eigen::VectorXd& y, Eigen::MatrixXd* J, Eigen::MatrixXd* Ji, Eigen::MatrixXd* Jd) {
-  const double* p = c.prm;
-  const int ru = 1 << 20, rv = 1 << 20;
-  switch (c.model) {
-    case 0: return projectWith(PinholeProjection<RadialTangentialDistortion>(p[0], p[1], p[2], p[3], ru, rv, RadialTangentialDistortion(p[4], p[5], p[6], p[7])), ph, y, J, Ji, Jd);
-    case 1: return projectWith(PinholeProjection<EquidistantDistortion>(p[0], p[1], p[2], p[3], ru, rv, EquidistantDistortion(p[4], p[5], p[6], p[7])), ph, y, J, Ji, Jd);
-    case 2: return projectWith(OmniProjection<RadialTangentialDistortion>(p[0], p[1], p[2], p[3], p[4], ru, rv, RadialTangentialDistortion(p[5], p[6], p[7], p[8])), ph, y, J, Ji, Jd);
-    case 3: return projectWith(ExtendedUnifiedProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], p[5], ru, rv), ph, y, J, Ji, Jd);
-    case 4: return projectWith(DoubleSphereProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], p[5], ru, rv), ph, y, J, Ji, Jd);
-    case 5: return projectWith(PinholeProjection<FovDistortion>(p[0], p[1], p[2], p[3], ru, rv, FovDistortion(p[4])), ph, y, J, Ji, Jd);
-    case 6: return projectWith(OmniProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], ru, rv), ph, y, J, Ji, Jd);
+// One camera: the reference's own projection object (its distortion object inside it) and the reference's own DesignVariableAdapter over
+// each of the two, created as CVB/.../implementation/CameraDesignVariable.hpp:8-10 creates them (adapters that do not own the objects) -
+// so update (backup + Projection::update / Distortion::update), revert (setParameters(backup)), getParameters and the 0-dimensional
+// active distortion block of the models without distortion (quirk Q7) are the reference's code (BE/.../implementation/DesignVariableAdapter.hpp).
+struct CameraModel {
+  int model, P, D;
+  boost::shared_ptr<DesignVariable> proj, dist;
+  virtual ~CameraModel() {}
+  virtual bool project(const Eigen::Vector4d& ph, Eigen::VectorXd& y, Eigen::MatrixXd* J, Eigen::MatrixXd* Ji, Eigen::MatrixXd* Jd) const = 0;
+  virtual void parameters(double* prm) const = 0;  // [P projection parameters, D distortion parameters]
+};
+
+template <typename PROJECTION>
+struct CameraModelOf : public CameraModel {
+  typedef typename PROJECTION::distortion_t distortion_t;
+  PROJECTION projection;
+  CameraModelOf(int model_, const PROJECTION& p) : projection(p) {
+    model = model_;
+    P = N_P[model];
+    D = N_D[model];
+    proj.reset(new DesignVariableAdapter<PROJECTION>(&projection, false));
+    dist.reset(new DesignVariableAdapter<distortion_t>(&projection.distortion(), false));
   }
-  return false;
+  virtual bool project(const Eigen::Vector4d& ph, Eigen::VectorXd& y, Eigen::MatrixXd* J, Eigen::MatrixXd* Ji, Eigen::MatrixXd* Jd) const {
+    if (!J) return projection.homogeneousToKeypoint(ph, y);
+    const bool ok = projection.homogeneousToKeypoint(ph, y, *J);
+    projection.homogeneousToKeypointIntrinsicsJacobian(ph, *Ji);
+    projection.homogeneousToKeypointDistortionJacobian(ph, *Jd);
+    return ok;
+  }
+  virtual void parameters(double* prm) const {
+    Eigen::MatrixXd a, b;
+    projection.getParameters(a);
+    projection.distortion().getParameters(b);
+    for (int i = 0; i < P; ++i) prm[i] = a(i, 0);
+    for (int i = 0; i < D; ++i) prm[P + i] = b(i, 0);
+  }
+};
+
+template <typename PROJECTION>
+boost::shared_ptr<CameraModel> makeCameraOf(int model, const PROJECTION& p) { return boost::shared_ptr<CameraModel>(new CameraModelOf<PROJECTION>(model, p)); }
+
+boost::shared_ptr<CameraModel> makeCamera(int model, const double* p) {
+  const int ru = 1 << 20, rv = 1 << 20;
+  switch (model) {
+    case 0: return makeCameraOf(model, PinholeProjection<RadialTangentialDistortion>(p[0], p[1], p[2], p[3], ru, rv, RadialTangentialDistortion(p[4], p[5], p[6], p[7])));
+    case 1: return makeCameraOf(model, PinholeProjection<EquidistantDistortion>(p[0], p[1], p[2], p[3], ru, rv, EquidistantDistortion(p[4], p[5], p[6], p[7])));
+    case 2: return makeCameraOf(model, OmniProjection<RadialTangentialDistortion>(p[0], p[1], p[2], p[3], p[4], ru, rv, RadialTangentialDistortion(p[5], p[6], p[7], p[8])));
+    case 3: return makeCameraOf(model, ExtendedUnifiedProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], p[5], ru, rv));
+    case 4: return makeCameraOf(model, DoubleSphereProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], p[5], ru, rv));
+    case 5: return makeCameraOf(model, PinholeProjection<FovDistortion>(p[0], p[1], p[2], p[3], ru, rv, FovDistortion(p[4])));
+    case 6: return makeCameraOf(model, OmniProjection<NoDistortion>(p[0], p[1], p[2], p[3], p[4], ru, rv));
+  }
+  throw std::runtime_error("unknown camera model");
 }
 
 // CVE/.../implementation/ReprojectionError.hpp:50-77 over the classes above
@@ -113,7 +120,7 @@ class ReprojectionTerm : public ErrorTermFs<2> {
     const Eigen::Vector4d p = point_.toHomogeneous();
     Eigen::VectorXd hat_y(2);
     hat_y.setZero();
-    project(*cam_, p, hat_y, 0, 0, 0);
+    cam_->project(p, hat_y, 0, 0, 0);
     setError(y_ - hat_y);
     return error().dot(invR() * error());
   }
@@ -122,7 +129,7 @@ class ReprojectionTerm : public ErrorTermFs<2> {
     Eigen::VectorXd hat_y(2);
     Eigen::MatrixXd J(2, 4), Ji, Jd;
     J.setZero();
-    project(*cam_, p, hat_y, &J, &Ji, &Jd);
+    cam_->project(p, hat_y, &J, &Ji, &Jd);
     point_.evaluateJacobians(jacobians, -J);
     // CVB/.../implementation/CameraDesignVariable.hpp: the negated intrinsics / distortion Jacobians, for the active blocks
     if (cam_->proj->isActive()) jacobians.add(cam_->proj.get(), Eigen::MatrixXd(-Ji));
@@ -141,7 +148,7 @@ class ReprojectionTerm : public ErrorTermFs<2> {
 namespace {
 struct RigProblem {
   boost::shared_ptr<OptimizationProblem> problem;
-  std::vector<CameraModel> cams;
+  std::vector<boost::shared_ptr<CameraModel>> cams;
   std::vector<boost::shared_ptr<RotationQuaternion>> bq, sq;
   std::vector<boost::shared_ptr<EuclideanPoint>> bt, st;
   std::vector<boost::shared_ptr<TransformationBasic>> B, S;
@@ -163,17 +170,11 @@ struct RigProblem {
       : problem(new OptimizationProblem()), cams(n_cams) {
     auto addCameras = [&]() {
       for (int k = 0; k < n_cams; ++k) {
-        CameraModel& c = cams[k];
-        c.model = cam_model[k];
-        c.P = N_P[c.model];
-        c.D = N_D[c.model];
-        for (int i = 0; i < 10; ++i) c.prm[i] = cam_params[k * 10 + i];
-        c.proj.reset(new ParameterBlock(c.prm, c.P));
-        c.dist.reset(new ParameterBlock(c.prm + c.P, c.D));
-        c.proj->setActive(true);
-        c.dist->setActive(true);
-        problem->addDesignVariable(c.proj);
-        problem->addDesignVariable(c.dist);
+        cams[k] = makeCamera(cam_model[k], cam_params + k * 10);
+        cams[k]->proj->setActive(true);  // K2/CameraCalibrator.hpp:116-122: setActive(true, true, false)
+        cams[k]->dist->setActive(true);
+        problem->addDesignVariable(cams[k]->proj);
+        problem->addDesignVariable(cams[k]->dist);
       }
     };
     auto addBaselines = [&]() { for (int j = 0; j + 1 < n_cams; ++j) B.push_back(addPose(baselines + 7 * j, bq, bt)); };
@@ -186,7 +187,7 @@ struct RigProblem {
       TransformationExpression T_cam_w = S[view_set[w]]->toExpression().inverse();
       for (int j = 0; j < view_cam[w]; ++j) T_cam_w = B[j]->toExpression() * T_cam_w;
       for (int64_t i = view_begin[w]; i < view_begin[w + 1]; ++i)
-        problem->addErrorTerm(boost::make_shared<ReprojectionTerm>(Eigen::Vector2d(y_u[i], y_v[i]), T_cam_w * points[corner_id[i]]->toExpression(), &cams[view_cam[w]]));
+        problem->addErrorTerm(boost::make_shared<ReprojectionTerm>(Eigen::Vector2d(y_u[i], y_v[i]), T_cam_w * points[corner_id[i]]->toExpression(), cams[view_cam[w]].get()));
     }
   }
 };
@@ -219,8 +220,7 @@ static int32_t optimize_rig(int32_t n_cams, const int32_t* cam_model, double* ca
     out_scalars[2] = r.JStart;
     out_scalars[3] = r.JFinal;
     out_scalars[4] = r.linearSolverFailure ? 1.0 : 0.0;
-    for (int k = 0; k < n_cams; ++k)
-      for (int i = 0; i < 10; ++i) cam_params[k * 10 + i] = rp.cams[k].prm[i];
+    for (int k = 0; k < n_cams; ++k) rp.cams[k]->parameters(cam_params + k * 10);
     auto store = [](double* p, const boost::shared_ptr<RotationQuaternion>& q, const boost::shared_ptr<EuclideanPoint>& t) {
       const Eigen::Vector4d qv = q->getQuaternion();
       const Eigen::Vector3d tv = t->toEuclidean();
