@@ -108,6 +108,19 @@ def reference_m_estimator_weight(kind: int, squared_error: float, p0: float = 0.
     return float(fn(kind, p0, p1, p2, squared_error))
 
 
+def reference_set_weighting(inv_r=None, policy=None):
+    """weighting of every term of the problems the reference-pin entry points build from now on (oracle/ref_pin_optimizer.cpp:
+    ref_set_weighting): invR through the reference's ErrorTermFs<2>::setInvR, an M-estimator policy (kind, p0, p1, p2 as kb_m_estimator)
+    through ErrorTerm::setMEstimatorPolicy.  Call without arguments to go back to invR = I and no policy."""
+    reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
+    fn = _ref_lib.ref_set_weighting
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double]
+    r = None if inv_r is None else np.ascontiguousarray(inv_r, np.float64).reshape(4)
+    kind, p0, p1, p2 = (tuple(policy) + (0.0, 0.999, 0.1)[len(policy) - 1:])[:4] if policy else (0, 0.0, 0.999, 0.1)
+    fn(None if r is None else _p(r), int(kind), float(p0), float(p1), float(p2))
+
+
 def _reference_problem_arrays(p):
     """the arrays of a kalibr_b200.problem.Problem as the ref_* entry points of oracle/ref_pin_optimizer.cpp take them"""
     cp = np.array(p.cam_params, np.float64, order="C")

@@ -32,6 +32,7 @@
 #include <aslam/backend/HomogeneousExpression.hpp>
 #include <aslam/backend/HomogeneousPoint.hpp>
 #include <aslam/backend/LevenbergMarquardtTrustRegionPolicy.hpp>
+#include <aslam/backend/MEstimatorPolicies.hpp>
 #include <aslam/backend/OptimizationProblem.hpp>
 #include <aslam/backend/Optimizer2.hpp>
 #include <aslam/backend/RotationQuaternion.hpp>
@@ -104,11 +105,36 @@ boost::shared_ptr<CameraModel> makeCamera(int model, const double* p) {
   throw std::runtime_error("unknown camera model");
 }
 
+// The weighting every term of the problems built after ref_set_weighting gets: invR through ErrorTermFs<2>::setInvR (K2 passes I in the
+// batch drivers, CalibrationTools.hpp:105-108, and I / sigma^2 in CreateBatchProblem, :495-496) and an M-estimator policy through
+// ErrorTerm::setMEstimatorPolicy (BE/src/MEstimatorPolicies.cpp; kind as kb_m_estimator, see ref_m_estimator_weight in ref_pin.cpp).
+// setInvR takes the matrix square root through sm::eigen::computeMatrixSqrt = Eigen::LDLT, a STAND-IN in this build
+// (ref_shim/sm/eigen/matrix_sqrt.hpp); for invR = c I - the only form Kalibr2 passes - that square root is sqrt(c) I with no pivoting.
+struct Weighting {
+  double inv_r[4] = {1.0, 0.0, 0.0, 1.0};
+  int kind = 0;
+  double p0 = 0.0, p1 = 0.999, p2 = 0.1;
+} g_weighting;
+
+boost::shared_ptr<MEstimator> makePolicy(const Weighting& w) {
+  switch (w.kind) {
+    case 1: return boost::shared_ptr<MEstimator>(new HuberMEstimator(w.p0));
+    case 2: return boost::shared_ptr<MEstimator>(new CauchyMEstimator(w.p0));
+    case 3: return boost::shared_ptr<MEstimator>(new GemanMcClureMEstimator(w.p0));
+    case 4: return boost::shared_ptr<MEstimator>(new BlakeZissermanMEstimator((size_t)w.p0, w.p1, w.p2));
+  }
+  return boost::shared_ptr<MEstimator>();
+}
+
 // CVE/.../implementation/ReprojectionError.hpp:50-77 over the classes above
 class ReprojectionTerm : public ErrorTermFs<2> {
  public:
-  ReprojectionTerm(const Eigen::Vector2d& y, const HomogeneousExpression& point, CameraModel* cam) : y_(y), point_(point), cam_(cam) {
-    setInvR(Eigen::Matrix2d::Identity());
+  ReprojectionTerm(const Eigen::Vector2d& y, const HomogeneousExpression& point, CameraModel* cam, const boost::shared_ptr<MEstimator>& policy)
+      : y_(y), point_(point), cam_(cam) {
+    Eigen::Matrix2d invR;
+    invR(0, 0) = g_weighting.inv_r[0]; invR(0, 1) = g_weighting.inv_r[1]; invR(1, 0) = g_weighting.inv_r[2]; invR(1, 1) = g_weighting.inv_r[3];
+    setInvR(invR);
+    if (policy) setMEstimatorPolicy(policy);
     DesignVariable::set_t dvs;
     point_.getDesignVariables(dvs);
     dvs.insert(cam_->proj.get());
@@ -183,15 +209,26 @@ struct RigProblem {
     else if (driver_order == 3) { addSets(); addBaselines(); addCameras(); }
     else { addCameras(); addBaselines(); addSets(); }
     for (int i = 0; i < n_target; ++i) points.push_back(boost::make_shared<HomogeneousPoint>(Eigen::Vector4d(target[3 * i], target[3 * i + 1], target[3 * i + 2], 1.0)));
+    const boost::shared_ptr<MEstimator> policy = makePolicy(g_weighting);  // one policy object shared by all terms, as a driver would set it
     for (int w = 0; w < n_views; ++w) {
       TransformationExpression T_cam_w = S[view_set[w]]->toExpression().inverse();
       for (int j = 0; j < view_cam[w]; ++j) T_cam_w = B[j]->toExpression() * T_cam_w;
       for (int64_t i = view_begin[w]; i < view_begin[w + 1]; ++i)
-        problem->addErrorTerm(boost::make_shared<ReprojectionTerm>(Eigen::Vector2d(y_u[i], y_v[i]), T_cam_w * points[corner_id[i]]->toExpression(), cams[view_cam[w]].get()));
+        problem->addErrorTerm(boost::make_shared<ReprojectionTerm>(Eigen::Vector2d(y_u[i], y_v[i]), T_cam_w * points[corner_id[i]]->toExpression(), cams[view_cam[w]].get(), policy));
     }
   }
 };
 }  // namespace
+
+// inv_r: 2x2 row-major or NULL for the identity; kind 0 removes the policy.  Applies to every problem built afterwards.
+extern "C" __attribute__((visibility("default"))) void ref_set_weighting(const double* inv_r, int32_t kind, double p0, double p1, double p2) {
+  const double identity[4] = {1.0, 0.0, 0.0, 1.0};
+  for (int i = 0; i < 4; ++i) g_weighting.inv_r[i] = inv_r ? inv_r[i] : identity[i];
+  g_weighting.kind = kind;
+  g_weighting.p0 = p0;
+  g_weighting.p1 = p1;
+  g_weighting.p2 = p2;
+}
 
 // out_scalars: [iterations, failedIterations, JStart, JFinal, linearSolverFailure]; state arrays are updated in place.
 // solver_kind: 0 = BlockCholeskyLinearSystemSolver, 1 = SparseCholeskyLinearSystemSolver (Kalibr2's default: Optimizer2.cpp:83-86; the
