@@ -42,8 +42,7 @@ def build_reference_cameras(force: bool = False):
     """oracle/_ref/libkalibr_ref.so: the REFERENCE's camera models compiled from the sources where they lie (oracle/ref_pin.cpp).
     Returns the path, or None when neither the reference tree nor a built library is there (the GPU box: only prebuilt files travel)."""
     have_ref = os.path.isdir(os.path.join(REFERENCE_DIR, "aslam_cv", "aslam_cameras"))
-    srcs = [os.path.join(_HERE, f) for f in ("ref_pin.cpp", "ref_pin_optimizer.cpp", os.path.join("ref_shim", "cholmod.h"))]
-    if have_ref and (force or not os.path.exists(_REF_LIB_PATH) or any(os.path.getmtime(f) > os.path.getmtime(_REF_LIB_PATH) for f in srcs)):
+    if have_ref:  # make decides what is stale (the pin sources and every stand-in header under ref_shim/ are prerequisites)
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "REFERENCE=" + REFERENCE_DIR, "_ref/libkalibr_ref.so"], check=True)
     return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
 
