@@ -120,6 +120,16 @@ def reference_set_weighting(inv_r=None, policy=None):
     fn(None if r is None else _p(r), int(kind), float(p0), float(p1), float(p2))
 
 
+def reference_set_trust_region_policy(gauss_newton: bool = False):
+    """which trust-region policy reference_optimize runs from now on: the LM policy of the batch drivers (default) or
+    GaussNewtonTrustRegionPolicy, the incremental estimator's (oracle/ref_pin_optimizer.cpp: ref_set_trust_region_policy)"""
+    reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
+    fn = _ref_lib.ref_set_trust_region_policy
+    fn.restype = None
+    fn.argtypes = [C.c_int32]
+    fn(1 if gauss_newton else 0)
+
+
 def _reference_problem_arrays(p):
     """the arrays of a kalibr_b200.problem.Problem as the ref_* entry points of oracle/ref_pin_optimizer.cpp take them"""
     cp = np.array(p.cam_params, np.float64, order="C")

@@ -31,6 +31,7 @@
 #include <aslam/backend/EuclideanPoint.hpp>
 #include <aslam/backend/HomogeneousExpression.hpp>
 #include <aslam/backend/HomogeneousPoint.hpp>
+#include <aslam/backend/GaussNewtonTrustRegionPolicy.hpp>
 #include <aslam/backend/LevenbergMarquardtTrustRegionPolicy.hpp>
 #include <aslam/backend/MEstimatorPolicies.hpp>
 #include <aslam/backend/OptimizationProblem.hpp>
@@ -220,6 +221,12 @@ struct RigProblem {
 };
 }  // namespace
 
+// 0 = LevenbergMarquardtTrustRegionPolicy(lambda_init) (the batch drivers, K2/CalibrationTools.hpp:57-66), 1 = GaussNewtonTrustRegionPolicy
+// (what the incremental estimator's Optimizer2 runs: build + undamped solve every iteration, never revert); applies to the optimisations
+// started afterwards
+int g_trust_region_policy = 0;
+extern "C" __attribute__((visibility("default"))) void ref_set_trust_region_policy(int32_t kind) { g_trust_region_policy = kind; }
+
 // inv_r: 2x2 row-major or NULL for the identity; kind 0 removes the policy.  Applies to every problem built afterwards.
 extern "C" __attribute__((visibility("default"))) void ref_set_weighting(const double* inv_r, int32_t kind, double p0, double p1, double p2) {
   const double identity[4] = {1.0, 0.0, 0.0, 1.0};
@@ -246,7 +253,8 @@ static int32_t optimize_rig(int32_t n_cams, const int32_t* cam_model, double* ca
     options.convergenceDeltaX = conv_dx;
     options.convergenceDeltaJ = conv_dj;
     options.maxIterations = max_iterations;
-    options.trustRegionPolicy = boost::make_shared<LevenbergMarquardtTrustRegionPolicy>(lambda_init);
+    if (g_trust_region_policy == 1) options.trustRegionPolicy = boost::make_shared<GaussNewtonTrustRegionPolicy>();
+    else options.trustRegionPolicy = boost::make_shared<LevenbergMarquardtTrustRegionPolicy>(lambda_init);
     if (solver_kind == 1) options.linearSystemSolver = boost::make_shared<SparseCholeskyLinearSystemSolver>();
     else options.linearSystemSolver = boost::make_shared<BlockCholeskyLinearSystemSolver>();
     Optimizer2 optimizer(options);

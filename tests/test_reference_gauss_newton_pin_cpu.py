@@ -1,0 +1,87 @@
+"""The Gauss-Newton loop of the incremental estimator's optimiser against the REFERENCE's own code.
+
+tests/golden/reference_gauss_newton_golden.npz (generator: tests/golden/make_reference_gauss_newton_golden.py) holds what the reference's
+Optimizer2 returns under GaussNewtonTrustRegionPolicy (BE/src/GaussNewtonTrustRegionPolicy.cpp, BE/src/Optimizer2.cpp, compiled from their
+sources: oracle/ref_pin_optimizer.cpp) with the estimator's options on ten full-rank problems: iteration counts, the cost after every
+iteration, the final design variables.  The reference run solves with SparseCholeskyLinearSystemSolver; the estimator's own solver
+(aslam::calibration::LinearSolver: SuiteSparseQR + truncated SVD) cannot be built here, and at full rank both return the least-squares step.
+So this pins the POLICY and the LOOP of oracle/ko_estimator.py's gauss_newton_optimize (and, in tests/test_zzz_b_reference_gauss_newton_pin_gpu.py,
+of kb_optimize_gauss_newton) - and shows that the restated QR + SVD solve, with and without column scaling, with the library's and with
+kalibr2's rank tolerance, takes exactly the reference's steps when nothing is truncated.  The truncation itself stays unpinned."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ko_estimator as ke
+from oracle import oracle_api as oa
+
+GN_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_gauss_newton_golden.npz")
+N_GN = 10
+SOLVER_OPTIONS = {"plain": dict(), "column-scaling": dict(column_scaling_on=True), "kalibr2": dict(column_scaling_on=True, eps_svd=1e-6)}
+# Which problems each option set is held to.  With column scaling and the library's tolerance: all ten.  Without scaling the reduced system
+# Omega = A_r^T A_r - (A_r^T Q)(A_r^T Q)^T of problems 2 and 9 has a condition number of 2e12 / 3e10: forming it explicitly and solving it
+# through its SVD - the reference's algorithm as much as the oracle's - loses 3e-7 / 2e-8 of the cost after the first step against the
+# Cholesky solve of the fixture, so they prove nothing about the loop.  With kalibr2's tolerance (eps 1e-6) problems 2, 6 and 9 are
+# TRUNCATED (rank n_c - 1): there the estimator deliberately does not take the least-squares step the fixture holds.
+HELD = {"plain": [0, 1, 3, 4, 5, 6, 7, 8], "column-scaling": list(range(10)), "kalibr2": [0, 1, 3, 4, 5, 7, 8]}
+CASES = [(n, name) for name in SOLVER_OPTIONS for n in HELD[name]]
+
+
+def gn_problem(g, n):
+    from kalibr_b200.problem import Problem
+
+    f = lambda name: g[f"gn{n}_{name}"]  # noqa: E731
+    return Problem(driver_order=int(f("order")), cam_model=f("cam_model"), cam_params=f("cam_params"), baselines=f("baselines"), set_poses=f("set_poses"),
+                   target_points=f("target_points"), view_set=f("view_set"), view_cam=f("view_cam"), view_begin=f("view_begin"), y_u=f("y_u"), y_v=f("y_v"),
+                   corner_id=f("corner_id"))
+
+
+def check_against_reference_gauss_newton(g, n, solve):
+    """solve(problem, max_iterations) -> (iterations, failed_iterations, j_start, j_final, cam_params, baselines, set_poses)"""
+    p = gn_problem(g, n)
+    it, failed, j_start, j_final, lsf = g[f"gn{n}_result"]
+    assert failed == 0 and lsf == 0
+    its, fails, js, jf, cp, bl, sp = solve(p, 20)
+    assert (its, fails) == (int(it), 0)
+    assert abs(js - j_start) <= 1e-11 * j_start and abs(jf - j_final) <= 1e-9 * j_final
+    for mine, ref in ((cp, g[f"gn{n}_final_cam_params"]), (np.reshape(bl, (-1, 7)), g[f"gn{n}_final_baselines"].reshape(-1, 7)), (sp, g[f"gn{n}_final_set_poses"])):
+        if ref.size:
+            assert np.abs(np.asarray(mine) - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1.0)
+    for k, (itk, _, _, jk, _) in enumerate(g[f"gn{n}_truncated"], start=1):  # the run cut after k iterations: the cost per iteration
+        its, fails, _, jf = solve(p, k)[:4]
+        assert (its, fails) == (int(itk), 0) and abs(jf - jk) <= 1e-9 * jk, k
+
+
+@pytest.mark.parametrize("n,options", CASES)
+def test_oracle_gauss_newton_walks_the_reference_optimizer(oracle_lib, n, options):
+    from kalibr_b200.problem import KbOptimizerOptions
+
+    g = np.load(GN_GOLD)
+    assert int(g["gn_count"]) == N_GN
+    opt = KbOptimizerOptions.estimator_default()
+
+    def solve(p, max_iterations):
+        o = oa.OracleProblem(p, oa.SPARSE_CHOLESKY, n_threads=1)
+        r = ke.gauss_newton_optimize(o, p, SOLVER_OPTIONS[options], max_iterations=max_iterations, conv_dx=opt.convergence_delta_x, conv_dj=opt.convergence_delta_j)
+        assert r["last_solve"]["rank"] == len(ke.calibration_columns(p)[0])  # nothing truncated: the step is the least-squares step
+        return r["iterations"], 0, r["j_start"], r["j_final"], o.camera_params(), o.baselines(), o.set_poses()
+
+    check_against_reference_gauss_newton(g, n, solve)
+
+
+def test_gauss_newton_fixture_is_what_the_reference_returns_now(oracle_lib):
+    """build container only"""
+    if oa.build_reference_cameras() is None:
+        pytest.skip("no reference tree and no prebuilt oracle/_ref here")
+    from kalibr_b200.problem import KbOptimizerOptions
+
+    g = np.load(GN_GOLD)
+    oa.reference_set_trust_region_policy(True)
+    try:
+        for n in (0, 2, 3, 9):
+            r, cp, bl, sp = oa.reference_optimize(gn_problem(g, n), KbOptimizerOptions.estimator_default(), oa.SPARSE_CHOLESKY_KIND, 1)
+            assert [r["iterations"], r["failed_iterations"], r["j_start"], r["j_final"], r["linear_solver_failure"]] == list(g[f"gn{n}_result"])
+            assert np.array_equal(cp, g[f"gn{n}_final_cam_params"]) and np.array_equal(sp, g[f"gn{n}_final_set_poses"])
+    finally:
+        oa.reference_set_trust_region_policy(False)

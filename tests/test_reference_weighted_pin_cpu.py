@@ -7,7 +7,7 @@ both its solvers and Optimizer2 return for six small problems with gross outlier
 weighted compressed-column J^T, weighted e, rhs, the policy-weighted cost, a damped step, whole optimisations over the BlockCholesky and the
 SparseCholesky solver.  Stand-ins in that build: the CHOLMOD factorisation, Eigen::LDLT behind the matrix square root of invR (exact for the
 invR = c I Kalibr2 passes; case "general_huber" uses a general matrix and says so), Boost.Math's chi-squared quantile (case "blake").
-The GPU path is held to the same fixture in tests/test_zz_reference_weighted_pin_gpu.py."""
+The GPU path is held to the same fixture in tests/test_zzz_a_reference_weighted_pin_gpu.py."""
 import os
 
 import numpy as np

@@ -3,7 +3,7 @@
 compressed-column J^T, weighted e, rhs, the policy-weighted cost, one damped step, and whole optimisations over both solver semantics -
 without the oracle in between.  Rows a2 / a19 of SURVEY.md §8.
 
-(File name sorts last on purpose: written at the end of round 2 after the GPU budget of the round was spent; the oracle reproduces this
+(File name sorts after every test that HAS run on a GPU, on purpose: written at the end of round 2 after the GPU budget of the round was spent; the oracle reproduces this
 fixture to 1e-13 on the CPU and the kernels reproduce the oracle's weighted path in tests/test_weighting_gpu.py.)"""
 import numpy as np
 import pytest
