@@ -190,6 +190,30 @@ def reference_sparse_system(problem, lam: float = 10.0, n_threads: int = 1):
     return dict(col_ptr=col_ptr, row_ind=row_ind, values=values, e=e, rhs=rhs, dx=dx if sizes[3] else None, cost=float(cost[0]), jcols=jcols)
 
 
+def reference_estimator_problem(problem, options=None):
+    """the incremental estimator's MERGED problem through the REFERENCE's own containers (oracle/ref_pin_optimizer.cpp: ref_estimator_problem):
+    one aslam::calibration::OptimizationProblem per synced set filled as kalibr2's CreateBatchProblem fills it, merged by
+    IncrementalOptimizationProblem::add, ordered as IncrementalEstimator::orderMarginalizedDesignVariables orders it, then Optimizer2 with the
+    Gauss-Newton policy.  Returns (order [n_active, 4] = kind, index, column base, dimension per active design variable in the optimiser's
+    order; groups ordering as a tuple; dict of the optimisation's scalars; cam_params, baselines, set_poses)."""
+    from kalibr_b200.problem import KbOptimizerOptions
+
+    reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
+    o = options or KbOptimizerOptions.estimator_default()
+    keep, args, types = _reference_problem_arrays(problem)
+    cp, bl, sp = keep[:3]
+    order = np.full((2 * len(sp) + 4 * len(cp) + 8, 4), -7, np.int32)
+    counts = np.zeros(2, np.int32)
+    out = np.zeros(8)
+    fn = _ref_lib.ref_estimator_problem
+    fn.restype = C.c_int32
+    fn.argtypes = types[:-1] + [C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    if fn(*args[:-1], int(o.max_iterations), float(o.convergence_delta_x), float(o.convergence_delta_j), _p(order), _p(counts), _p(out)) != 0:
+        raise RuntimeError("ref_estimator_problem failed")
+    res = dict(iterations=int(out[0]), failed_iterations=int(out[1]), j_start=float(out[2]), j_final=float(out[3]), linear_solver_failure=int(out[4]))
+    return order[:counts[0]].copy(), tuple(int(c) for c in str(int(counts[1])).zfill(3)), res, cp, bl, sp
+
+
 def reference_time_evaluate_build(problem, n_threads: int = 4, repeats: int = 1, solver_kind: int = BLOCK_CHOLESKY_KIND):
     """seconds the REFERENCE's own code (oracle/ref_pin_optimizer.cpp: ref_time_evaluate_build_solver) spends on one Optimizer2::evaluateError and
     one buildSystem of `problem` - BlockCholeskyLinearSystemSolver's (serial Hessian assembly) or, solver_kind 1, SparseCholeskyLinearSystemSolver's

@@ -40,7 +40,12 @@
 #include <aslam/backend/TransformationBasic.hpp>
 #include <aslam/backend/TransformationExpression.hpp>
 
+#include <aslam/calibration/core/IncrementalOptimizationProblem.h>
+#include <aslam/calibration/core/OptimizationProblem.h>
+
+#include <algorithm>
 #include <chrono>
+#include <map>
 #include <cstdint>
 #include <vector>
 
@@ -434,4 +439,133 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_time_evaluate_buil
                                                                                          int32_t solver_kind, int32_t n_threads, int32_t repeats, double* out_seconds) {
   return time_evaluate_build(n_cams, cam_model, cam_params, baselines, n_sets, set_poses, n_target, target, n_views, view_set, view_cam, view_begin, y_u, y_v, corner_id,
                              driver_order, solver_kind, n_threads, repeats, out_seconds);
+}
+
+// The incremental estimator's MERGED problem through the reference's own containers (§8f rank 2): one
+// aslam::calibration::OptimizationProblem per synced set, filled in the order of kalibr2::tools::CreateBatchProblem
+// (K2/CalibrationTools.hpp:460-521: the set's pose q, t in group 1; the shared baselines q, t in group 0; the shared landmarks - inactive -
+// in group 2; the shared intrinsics in group 0; then the set's reprojection terms camera by camera, invR as set by ref_set_weighting),
+// merged batch by batch with IncrementalOptimizationProblem::add (IC/src/core/IncrementalOptimizationProblem.cpp:186-223) and ordered as
+// IncrementalEstimator::orderMarginalizedDesignVariables does (IC/src/core/IncrementalEstimator.cpp:550-565: the marginalised group - the
+// calibration group 0 - swapped to the end).  Optimizer2 (Gauss-Newton policy, as the estimator runs it) then enumerates the active design
+// variables of that container: out_order gets one row [kind, index, column base, dimension] per active design variable in the optimiser's
+// order (kind 0 / 1 = pose q / t of set `index`, 2 / 3 = baseline q / t, 4 / 5 = projection / distortion of camera `index`), out_counts =
+// [active design variables, groups ordering as a decimal number, e.g. 120 for {1, 2, 0}].  The optimisation's scalars and final state as
+// ref_optimize_rig.  The container classes and their ordering logic are the reference's; the fill order restates the K2 header (OpenCV /
+// ROS types in its signature keep it from compiling here).
+extern "C" __attribute__((visibility("default"))) int32_t ref_estimator_problem(int32_t n_cams, const int32_t* cam_model, double* cam_params, double* baselines,
+                                                                                int32_t n_sets, double* set_poses, int32_t n_target, const double* target, int32_t n_views,
+                                                                                const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
+                                                                                const double* y_u, const double* y_v, const int32_t* corner_id, int32_t max_iterations,
+                                                                                double conv_dx, double conv_dj, int32_t* out_order /*[<= 2 n_sets + 4 n_cams][4]*/,
+                                                                                int32_t* out_counts /*[2]*/, double* out_scalars) {
+  try {
+    namespace ic = aslam::calibration;
+    const size_t CALIBRATION_GROUP_ID = 0, TRANSFORMATION_GROUP_ID = 1, LANDMARK_GROUP_ID = 2;
+    std::vector<boost::shared_ptr<CameraModel>> cams(n_cams);
+    for (int k = 0; k < n_cams; ++k) {
+      cams[k] = makeCamera(cam_model[k], cam_params + k * 10);
+      cams[k]->proj->setActive(true);
+      cams[k]->dist->setActive(true);
+    }
+    std::vector<boost::shared_ptr<RotationQuaternion>> bq, sq;
+    std::vector<boost::shared_ptr<EuclideanPoint>> bt, st;
+    std::vector<boost::shared_ptr<TransformationBasic>> B, poses;  // kept alive: toExpression() does not own them (K2's BatchProblemStruct holds them too)
+    for (int j = 0; j + 1 < n_cams; ++j) {  // the shared baseline design variables exist before the batches (PoseDesignVariables)
+      const double* p = baselines + 7 * j;
+      bq.push_back(boost::make_shared<RotationQuaternion>(Eigen::Vector4d(p[0], p[1], p[2], p[3])));
+      bt.push_back(boost::make_shared<EuclideanPoint>(Eigen::Vector3d(p[4], p[5], p[6])));
+      bq.back()->setActive(true);
+      bt.back()->setActive(true);
+      B.push_back(boost::make_shared<TransformationBasic>(bq.back()->toExpression(), bt.back()->toExpression()));
+    }
+    std::vector<boost::shared_ptr<HomogeneousPoint>> points;  // landmarks: never set active in kalibr2
+    for (int i = 0; i < n_target; ++i) points.push_back(boost::make_shared<HomogeneousPoint>(Eigen::Vector4d(target[3 * i], target[3 * i + 1], target[3 * i + 2], 1.0)));
+    const boost::shared_ptr<MEstimator> policy = makePolicy(g_weighting);
+
+    boost::shared_ptr<ic::IncrementalOptimizationProblem> merged(new ic::IncrementalOptimizationProblem());
+    for (int v = 0; v < n_sets; ++v) {
+      boost::shared_ptr<ic::OptimizationProblem> problem(new ic::OptimizationProblem());
+      const double* p = set_poses + 7 * v;
+      sq.push_back(boost::make_shared<RotationQuaternion>(Eigen::Vector4d(p[0], p[1], p[2], p[3])));  // AddPoseDesignVariable, :31-45
+      sq.back()->setActive(true);
+      problem->addDesignVariable(sq.back(), TRANSFORMATION_GROUP_ID);
+      st.push_back(boost::make_shared<EuclideanPoint>(Eigen::Vector3d(p[4], p[5], p[6])));
+      st.back()->setActive(true);
+      problem->addDesignVariable(st.back(), TRANSFORMATION_GROUP_ID);
+      poses.push_back(boost::make_shared<TransformationBasic>(sq.back()->toExpression(), st.back()->toExpression()));
+      const boost::shared_ptr<TransformationBasic>& S = poses.back();
+      for (size_t j = 0; j < B.size(); ++j) {
+        problem->addDesignVariable(bq[j], CALIBRATION_GROUP_ID);
+        problem->addDesignVariable(bt[j], CALIBRATION_GROUP_ID);
+      }
+      for (size_t i = 0; i < points.size(); ++i) problem->addDesignVariable(points[i], LANDMARK_GROUP_ID);
+      for (int k = 0; k < n_cams; ++k) {  // AddIntrinsicDesignVariables: projection, distortion (the inactive 0-dimensional shutter block is left out)
+        problem->addDesignVariable(cams[k]->proj, CALIBRATION_GROUP_ID);
+        problem->addDesignVariable(cams[k]->dist, CALIBRATION_GROUP_ID);
+      }
+      for (int k = 0; k < n_cams; ++k)  // the set's views camera by camera
+        for (int w = 0; w < n_views; ++w) {
+          if (view_set[w] != v || view_cam[w] != k) continue;
+          TransformationExpression T_cam_w = S->toExpression().inverse();
+          for (int j = 0; j < k; ++j) T_cam_w = B[j]->toExpression() * T_cam_w;
+          for (int64_t i = view_begin[w]; i < view_begin[w + 1]; ++i)
+            problem->addErrorTerm(boost::make_shared<ReprojectionTerm>(Eigen::Vector2d(y_u[i], y_v[i]), T_cam_w * points[corner_id[i]]->toExpression(), cams[k].get(), policy));
+        }
+      merged->add(problem);
+    }
+    {  // IncrementalEstimator::orderMarginalizedDesignVariables with _margGroupId = the calibration group
+      std::vector<size_t> ordering = merged->getGroupsOrdering();
+      std::vector<size_t>::iterator it = std::find(ordering.begin(), ordering.end(), CALIBRATION_GROUP_ID);
+      if (it == ordering.end()) throw std::runtime_error("the calibration group is not in the problem");
+      if (*it != ordering.back()) {
+        std::swap(*it, ordering.back());
+        merged->setGroupsOrdering(ordering);
+      }
+    }
+    out_counts[1] = 0;
+    for (size_t g : merged->getGroupsOrdering()) out_counts[1] = out_counts[1] * 10 + (int32_t)g;
+
+    Optimizer2Options options;
+    options.nThreads = 1;
+    options.convergenceDeltaX = conv_dx;
+    options.convergenceDeltaJ = conv_dj;
+    options.maxIterations = max_iterations;
+    options.trustRegionPolicy = boost::make_shared<GaussNewtonTrustRegionPolicy>();
+    options.linearSystemSolver = boost::make_shared<SparseCholeskyLinearSystemSolver>();
+    Optimizer2 optimizer(options);
+    optimizer.setProblem(merged);
+    SolutionReturnValue r = optimizer.optimize();  // initialises: block indices and column bases stay as the optimiser assigned them
+    std::map<const DesignVariable*, std::pair<int, int>> label;
+    for (int v = 0; v < n_sets; ++v) { label[sq[v].get()] = std::make_pair(0, v); label[st[v].get()] = std::make_pair(1, v); }
+    for (size_t j = 0; j < B.size(); ++j) { label[bq[j].get()] = std::make_pair(2, (int)j); label[bt[j].get()] = std::make_pair(3, (int)j); }
+    for (int k = 0; k < n_cams; ++k) { label[cams[k]->proj.get()] = std::make_pair(4, k); label[cams[k]->dist.get()] = std::make_pair(5, k); }
+    out_counts[0] = (int32_t)optimizer.numDesignVariables();
+    for (size_t i = 0; i < optimizer.numDesignVariables(); ++i) {
+      const DesignVariable* dv = optimizer.designVariable(i);
+      const std::pair<int, int> l = label.count(dv) ? label[dv] : std::make_pair(-1, -1);
+      out_order[4 * i] = l.first;
+      out_order[4 * i + 1] = l.second;
+      out_order[4 * i + 2] = dv->columnBase();
+      out_order[4 * i + 3] = dv->minimalDimensions();
+    }
+    out_scalars[0] = r.iterations;
+    out_scalars[1] = r.failedIterations;
+    out_scalars[2] = r.JStart;
+    out_scalars[3] = r.JFinal;
+    out_scalars[4] = r.linearSolverFailure ? 1.0 : 0.0;
+    for (int k = 0; k < n_cams; ++k) cams[k]->parameters(cam_params + k * 10);
+    auto store = [](double* p, const boost::shared_ptr<RotationQuaternion>& q, const boost::shared_ptr<EuclideanPoint>& t) {
+      const Eigen::Vector4d qv = q->getQuaternion();
+      const Eigen::Vector3d tv = t->toEuclidean();
+      for (int i = 0; i < 4; ++i) p[i] = qv(i);
+      for (int i = 0; i < 3; ++i) p[4 + i] = tv(i);
+    };
+    for (size_t j = 0; j < bq.size(); ++j) store(baselines + 7 * j, bq[j], bt[j]);
+    for (size_t v = 0; v < sq.size(); ++v) store(set_poses + 7 * v, sq[v], st[v]);
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << "ref_estimator_problem: " << e.what() << std::endl;
+    return -1;
+  }
 }

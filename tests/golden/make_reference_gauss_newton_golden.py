@@ -7,6 +7,10 @@ from the reference's sources (oracle/ref_pin_optimizer.cpp, ref_set_trust_region
 SparseCholeskyLinearSystemSolver (over the dense stand-in for CHOLMOD), NOT the estimator's own aslam::calibration::LinearSolver (SuiteSparseQR
 + SVD, not buildable here): at full rank both return the least-squares step, so what this fixture pins is the POLICY and the loop - iteration
 counts, the cost after every iteration, the stopping rule, the final design variables - not the truncated-SVD solver.
+For the batch-order problems the same optimisation also runs over the estimator's MERGED problem built from the reference's own containers
+(aslam::calibration::OptimizationProblem per synced set, filled as kalibr2's CreateBatchProblem fills it; IncrementalOptimizationProblem::add;
+the groups ordering of IncrementalEstimator::orderMarginalizedDesignVariables): recorded is the order - kind, index, column base, dimension -
+in which Optimizer2 enumerates its active design variables (oracle/ref_pin_optimizer.cpp: ref_estimator_problem).
     python tests/golden/make_reference_gauss_newton_golden.py
 """
 import os
@@ -53,6 +57,16 @@ def main():
             print("Gauss-Newton problem", n, models, "order", order, r)
     finally:
         oa.reference_set_trust_region_policy(False)
+    # the estimator's MERGED problem through the reference's own containers (ref_estimator_problem): the order of the active design variables
+    # as Optimizer2 enumerates them over IncrementalOptimizationProblem, for the batch-order problems above
+    for n, (models, n_sets, order, seed) in enumerate(GN_PROBLEMS):
+        if order != 3:
+            continue
+        p = synthetic.make_problem(models, n_sets, order, seed=seed, dropout=0.5)
+        dv_order, groups, r, cp, bl, sp = oa.reference_estimator_problem(p, KbOptimizerOptions.estimator_default())
+        assert [r["iterations"], r["failed_iterations"], r["j_start"], r["j_final"], r["linear_solver_failure"]] == list(out[f"gn{n}_result"])  # the same run
+        out[f"gn{n}_estimator_order"], out[f"gn{n}_estimator_groups"] = dv_order, np.array(groups)
+        print("merged estimator problem", n, "groups ordering", groups, "active design variables", len(dv_order))
     out["gn_count"] = np.array(len(GN_PROBLEMS))
     path = os.path.join(ROOT, "tests", "golden", "reference_gauss_newton_golden.npz")
     np.savez_compressed(path, **out)

@@ -85,3 +85,28 @@ def test_gauss_newton_fixture_is_what_the_reference_returns_now(oracle_lib):
             assert np.array_equal(cp, g[f"gn{n}_final_cam_params"]) and np.array_equal(sp, g[f"gn{n}_final_set_poses"])
     finally:
         oa.reference_set_trust_region_policy(False)
+
+
+KIND = {"set_q": 0, "set_t": 1, "baseline_q": 2, "baseline_t": 3, "proj": 4, "dist": 5}
+
+
+@pytest.mark.parametrize("n", [3, 8])
+def test_batch_order_is_the_reference_estimators_merged_problem(oracle_lib, n):
+    """KB_ORDER_BATCH = the order in which the reference's Optimizer2 enumerates the active design variables of the incremental estimator's merged
+    problem: aslam::calibration::OptimizationProblem per synced set filled as kalibr2::tools::CreateBatchProblem fills it
+    (K2/CalibrationTools.hpp:460-521), IncrementalOptimizationProblem::add, the groups ordering {1, 2, 0} of
+    IncrementalEstimator::orderMarginalizedDesignVariables - all reference classes, compiled (oracle/ref_pin_optimizer.cpp: ref_estimator_problem).
+    Kind, index, column base and dimension of every block must match the layout the library and the oracle use."""
+    g = np.load(GN_GOLD)
+    p = gn_problem(g, n)
+    assert tuple(g[f"gn{n}_estimator_groups"]) == (1, 2, 0)
+    col, dims, labels = p.dv_layout()
+    mine = np.array([[KIND[lab[0]], lab[1], c, d] for lab, c, d in zip(labels, col, dims)])
+    assert np.array_equal(mine, g[f"gn{n}_estimator_order"])
+    o = oa.OracleProblem(p)
+    ocol, odims = o.dv_layout()
+    assert np.array_equal(ocol, g[f"gn{n}_estimator_order"][:, 2]) and np.array_equal(odims, g[f"gn{n}_estimator_order"][:, 3])
+    if oa.build_reference_cameras() is not None:  # build container: the reference's containers, run again
+        order, groups, r, cp, bl, sp = oa.reference_estimator_problem(p)
+        assert np.array_equal(order, g[f"gn{n}_estimator_order"]) and groups == (1, 2, 0)
+        assert [r["iterations"], r["failed_iterations"], r["j_start"], r["j_final"], r["linear_solver_failure"]] == list(g[f"gn{n}_result"])
