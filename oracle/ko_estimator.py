@@ -10,9 +10,14 @@ incremental_calibration):
 
 Third-party arithmetic: the reference factorises the pose columns with SuiteSparseQR (libsuitesparse-dev, unpinned) and takes the
 SVD of the reduced matrix with Eigen; both are replaced by numpy's dense QR / SVD, which compute the same mathematical objects
-(the orthogonal complement of the pose columns, the singular triplets of Omega).  PARITY UNPINNED for this part: the reference
-stores no expected values for it; it is pinned through properties (tests/test_estimator_cpu.py): the truncated solve equals the
-plain least-squares solution when the system has full rank, and the minimum-norm solution on the observable subspace when not.
+(the orthogonal complement of the pose columns, the singular triplets of Omega).  PARITY, part by part: PINNED against the reference's own
+compiled code are the Gauss-Newton policy and loop (tests/test_reference_gauss_newton_pin_cpu.py: Optimizer2 + GaussNewtonTrustRegionPolicy
+from their sources), the merged problem's design-variable order (same file: the reference's OptimizationProblem / IncrementalOptimizationProblem
+containers) and the decision numerics - rankTol, estimateNumericalRank, svGap, columnScalingMatrix, solveSVD
+(tests/test_reference_linalg_pin_cpu.py: IC/src/algorithms/linalg.cpp from its source).  UNPINNED: the sparse QR elimination that produces
+Omega and addBatch's accept / reject bookkeeping (they need SuiteSparseQR); those are held through properties (tests/test_estimator_cpu.py):
+the truncated solve equals the plain least-squares solution when the system has full rank, and the minimum-norm solution on the
+observable subspace when not.
 """
 from __future__ import annotations
 
@@ -44,6 +49,31 @@ def column_scaling(A, eps):
         return np.where(norm < tol, 0.0, 1.0 / norm)
 
 
+def numerical_rank(sv, eps_svd=EPS, svd_tol=-1.0):
+    """(tolerance, rank, gap) of a spectrum as LinearSolver::solve / analyzeMarginal decide them (IC/src/core/LinearSolver.cpp:427-431 over
+    IC/src/algorithms/linalg.cpp:244-282: rankTol = sv[0] * eps * n unless a tolerance is given; estimateNumericalRank counts down from the
+    smallest singular value and never goes below 1; svGap = sv[rank - 1] / sv[rank], infinite at full rank).  Pinned against the
+    reference's own functions: tests/test_reference_linalg_pin_cpu.py."""
+    sv = np.asarray(sv, float)
+    tol = svd_tol if svd_tol != -1.0 else sv[0] * eps_svd * len(sv)
+    rank = len(sv)
+    for i in range(len(sv) - 1, 0, -1):
+        if sv[i] > tol:
+            break
+        rank -= 1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gap = sv[rank - 1] / sv[rank] if rank < len(sv) else np.inf
+    return tol, rank, gap
+
+
+def svd_truncated_solve(Omega, b_r, eps_svd=EPS, svd_tol=-1.0):
+    """analyzeSVD + solveSVD (linalg.cpp:412-444): x = V_r diag(1 / sv_r) U_r^T b over the numerical rank r.  (x, sv, tolerance, rank, gap)"""
+    U, sv, Vt = np.linalg.svd(Omega)
+    tol, rank, gap = numerical_rank(sv, eps_svd, svd_tol)
+    x_r = Vt[:rank].T @ ((U[:, :rank].T @ b_r) / sv[:rank])
+    return x_r, sv, tol, rank, gap
+
+
 def linear_solver_solve(J, b, cal, rest, column_scaling_on=False, eps_norm=EPS, eps_svd=EPS, svd_tol=-1.0):
     """LinearSolver::solve: x minimising |J x - b| with the calibration block cut at the numerical rank of Omega.
     Returns (x, info) with info = dict(rank, tolerance, sv_gap, singular_values)."""
@@ -55,21 +85,12 @@ def linear_solver_solve(J, b, cal, rest, column_scaling_on=False, eps_norm=EPS, 
     Q, R = np.linalg.qr(A_l)  # thin QR of the pose columns (full column rank: every pose is observed)
     ArtQ = A_r.T @ Q
     Omega = A_r.T @ A_r - ArtQ @ ArtQ.T
-    U, sv, Vt = np.linalg.svd(Omega)
-    tol = svd_tol if svd_tol != -1.0 else sv[0] * eps_svd * len(sv)
-    rank = len(sv)
-    for i in range(len(sv) - 1, 0, -1):
-        if sv[i] > tol:
-            break
-        rank -= 1
     b_r = A_r.T @ b - ArtQ @ (Q.T @ b)
-    x_r = Vt[:rank].T @ ((U[:, :rank].T @ b_r) / sv[:rank])
+    x_r, sv, tol, rank, gap = svd_truncated_solve(Omega, b_r, eps_svd, svd_tol)
     x_l = np.linalg.solve(R, Q.T @ (b - A_r @ x_r))
     x = np.zeros(J.shape[1])
     x[rest] = G_l * x_l
     x[cal] = G_r * x_r
-    with np.errstate(divide="ignore"):
-        gap = sv[rank - 1] / sv[rank] if rank < len(sv) else np.inf
     return x, dict(rank=rank, tolerance=tol, sv_gap=gap, singular_values=sv)
 
 

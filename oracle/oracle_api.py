@@ -214,6 +214,60 @@ def reference_estimator_problem(problem, options=None):
     return order[:counts[0]].copy(), tuple(int(c) for c in str(int(counts[1])).zfill(3)), res, cp, bl, sp
 
 
+_REF_LINALG_PATH = os.path.join(_HERE, "_ref", "libkalibr_ref_linalg.so")
+_ref_linalg = None
+
+
+def reference_linalg():
+    """oracle/_ref/libkalibr_ref_linalg.so: IC/src/algorithms/linalg.cpp compiled from the reference's source (oracle/ref_pin_linalg.cpp says what
+    in it is reference code and what a stand-in); None when neither the reference tree nor a built library is there"""
+    global _ref_linalg
+    if _ref_linalg is None:
+        if os.path.isdir(os.path.join(REFERENCE_DIR, "aslam_incremental_calibration")):
+            subprocess.run(["make", "-C", _HERE, "-s", "REFERENCE=" + REFERENCE_DIR, "_ref/libkalibr_ref_linalg.so"], check=True)
+        if not os.path.exists(_REF_LINALG_PATH):
+            return None
+        _ref_linalg = C.CDLL(_REF_LINALG_PATH)
+    return _ref_linalg
+
+
+def reference_linalg_rank(sv, eps, svd_tol=-1.0):
+    """(tolerance, rank, gap) from the reference's rankTol / estimateNumericalRank / svGap"""
+    sv = np.ascontiguousarray(sv, np.float64)
+    out = np.zeros(3)
+    fn = reference_linalg().ref_linalg_rank
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p]
+    if fn(_p(sv), len(sv), float(eps), float(svd_tol), _p(out)) != 0:
+        raise RuntimeError("ref_linalg_rank failed")
+    return float(out[0]), int(out[1]), float(out[2])
+
+
+def reference_linalg_column_scaling(A, eps, eps_qr):
+    """(G, qr_tol): the reference's columnScalingMatrix (1 / column norm, 0 below sqrt(rows * eps)) and qrTol of the dense matrix A"""
+    A = np.ascontiguousarray(A, np.float64)
+    G, qr = np.zeros(A.shape[1]), np.zeros(1)
+    fn = reference_linalg().ref_linalg_column_scaling
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    if fn(_p(A), A.shape[0], A.shape[1], float(eps), float(eps_qr), _p(G), _p(qr)) != 0:
+        raise RuntimeError("ref_linalg_column_scaling failed")
+    return G, float(qr[0])
+
+
+def reference_linalg_svd_solve(Omega, b, eps, svd_tol=-1.0):
+    """the reference's analyzeSVD (SVD itself: stand-in) + rank decision + solveSVD on a dense symmetric Omega: (x, sv, tolerance, rank, gap)"""
+    Omega, b = np.ascontiguousarray(Omega, np.float64), np.ascontiguousarray(b, np.float64)
+    n = len(b)
+    sv, x, out = np.zeros(n), np.zeros(n), np.zeros(3)
+    fn = reference_linalg().ref_linalg_svd_solve
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    if fn(_p(Omega), _p(b), n, float(eps), float(svd_tol), _p(sv), _p(x), _p(out)) != 0:
+        raise RuntimeError("ref_linalg_svd_solve failed")
+    return x, sv, float(out[0]), int(out[1]), float(out[2])
+
+
 def reference_time_evaluate_build(problem, n_threads: int = 4, repeats: int = 1, solver_kind: int = BLOCK_CHOLESKY_KIND):
     """seconds the REFERENCE's own code (oracle/ref_pin_optimizer.cpp: ref_time_evaluate_build_solver) spends on one Optimizer2::evaluateError and
     one buildSystem of `problem` - BlockCholeskyLinearSystemSolver's (serial Hessian assembly) or, solver_kind 1, SparseCholeskyLinearSystemSolver's

@@ -1,5 +1,6 @@
-"""CPU tests of the oracle of the incremental estimator's numerical core (oracle/ko_estimator.py): PARITY UNPINNED for this part
-(no stored expected values in the reference), pinned through properties.
+"""CPU tests of the oracle of the incremental estimator's numerical core (oracle/ko_estimator.py) through properties - the part of it that
+has no reference pin (the QR elimination and the truncated solve as a whole; its Gauss-Newton loop, design-variable order and rank / scaling
+numerics are pinned against the reference's compiled code in tests/test_reference_gauss_newton_pin_cpu.py and test_reference_linalg_pin_cpu.py).
   IC/src/core/LinearSolver.cpp:299-463, IC/src/algorithms/linalg.cpp:128-152, 244-282, 426-443
   IC/test/algorithms/*: the reference tests its marginalisation against a dense solve in the same way
 """
