@@ -136,7 +136,7 @@ def cpu_regimes(config, cpu_sets, steps_each, warmup=1):
     SuiteSparse in the image - its evaluate + build compiled against stand-in headers is the extra "reference" regime below) on the host cores, in the reference's two solver regimes - SparseCholesky (Kalibr2's DEFAULT:
     Optimizer2.cpp:83-86; Jacobian materialisation threaded) and BlockCholesky (serial assembly) - at T = 4 threads (the reference's
     default nThreads, Optimizer2Options.hpp:16) and T = all host cores.  One step = evaluate + build + solve at lambda = 10 on a bounded
-    sample of the workload.  The HEADLINE CPU number is the fastest of the four, so that the GPU / CPU ratio is never inflated by a slow
+    sample of the workload.  The HEADLINE CPU number is the fastest of all regimes (these four and the reference-code ones below), so that the GPU / CPU ratio is never inflated by a slow
     regime: in this port the SparseCholesky solve assembles J^T J entry by entry (the reference hands J^T to CHOLMOD's supernodal
     factorisation, which is not in the image), which makes the BlockCholesky regime the faster one here.
     Returns (per-regime results sorted as CPU_REGIMES, index of the fastest, problem of the sample)."""
@@ -462,7 +462,7 @@ def main():
 
     order, models, S_cfg = synthetic.CONFIGS[args.config]
     if args.cpu_sets is None:
-        # about 10-30 s of CPU work for the four regimes: the oracle runs ~0.1-0.2 M terms/s per LM iteration
+        # about 10-30 s of CPU work for the four port regimes (the two reference-code regimes add one timed repeat each): the oracle runs ~0.1-0.2 M terms/s per LM iteration
         per_set = 120 * len(models)
         args.cpu_sets = max(8, min(S_cfg, int((400_000 if args.impl == "reference" else 200_000) / per_set)))
     if args.impl == "reference":
