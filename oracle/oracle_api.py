@@ -190,12 +190,14 @@ def reference_sparse_system(problem, lam: float = 10.0, n_threads: int = 1):
     return dict(col_ptr=col_ptr, row_ind=row_ind, values=values, e=e, rhs=rhs, dx=dx if sizes[3] else None, cost=float(cost[0]), jcols=jcols)
 
 
-def reference_estimator_problem(problem, options=None):
+def reference_estimator_problem(problem, options=None, restore_after: bool = False):
     """the incremental estimator's MERGED problem through the REFERENCE's own containers (oracle/ref_pin_optimizer.cpp: ref_estimator_problem):
     one aslam::calibration::OptimizationProblem per synced set filled as kalibr2's CreateBatchProblem fills it, merged by
     IncrementalOptimizationProblem::add, ordered as IncrementalEstimator::orderMarginalizedDesignVariables orders it, then Optimizer2 with the
     Gauss-Newton policy.  Returns (order [n_active, 4] = kind, index, column base, dimension per active design variable in the optimiser's
-    order; groups ordering as a tuple; dict of the optimisation's scalars; cam_params, baselines, set_poses)."""
+    order; groups ordering as a tuple; dict of the optimisation's scalars; cam_params, baselines, set_poses).  restore_after: the container's
+    saveDesignVariables before and restoreDesignVariables after the optimisation (the estimator's reject path): the returned state is then
+    what the reference restored."""
     from kalibr_b200.problem import KbOptimizerOptions
 
     reference_camera_project(0, [1, 1, 0, 0, 0, 0, 0, 0], [0, 0, 1, 1])  # loads the library
@@ -207,8 +209,8 @@ def reference_estimator_problem(problem, options=None):
     out = np.zeros(8)
     fn = _ref_lib.ref_estimator_problem
     fn.restype = C.c_int32
-    fn.argtypes = types[:-1] + [C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
-    if fn(*args[:-1], int(o.max_iterations), float(o.convergence_delta_x), float(o.convergence_delta_j), _p(order), _p(counts), _p(out)) != 0:
+    fn.argtypes = types[:-1] + [C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    if fn(*args[:-1], int(o.max_iterations), float(o.convergence_delta_x), float(o.convergence_delta_j), 1 if restore_after else 0, _p(order), _p(counts), _p(out)) != 0:
         raise RuntimeError("ref_estimator_problem failed")
     res = dict(iterations=int(out[0]), failed_iterations=int(out[1]), j_start=float(out[2]), j_final=float(out[3]), linear_solver_failure=int(out[4]))
     return order[:counts[0]].copy(), tuple(int(c) for c in str(int(counts[1])).zfill(3)), res, cp, bl, sp

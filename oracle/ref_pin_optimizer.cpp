@@ -457,7 +457,7 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_estimator_problem(
                                                                                 int32_t n_sets, double* set_poses, int32_t n_target, const double* target, int32_t n_views,
                                                                                 const int32_t* view_set, const int32_t* view_cam, const int64_t* view_begin,
                                                                                 const double* y_u, const double* y_v, const int32_t* corner_id, int32_t max_iterations,
-                                                                                double conv_dx, double conv_dj, int32_t* out_order /*[<= 2 n_sets + 4 n_cams][4]*/,
+                                                                                double conv_dx, double conv_dj, int32_t restore_after, int32_t* out_order /*[<= 2 n_sets + 4 n_cams][4]*/,
                                                                                 int32_t* out_counts /*[2]*/, double* out_scalars) {
   try {
     namespace ic = aslam::calibration;
@@ -535,7 +535,11 @@ extern "C" __attribute__((visibility("default"))) int32_t ref_estimator_problem(
     options.linearSystemSolver = boost::make_shared<SparseCholeskyLinearSystemSolver>();
     Optimizer2 optimizer(options);
     optimizer.setProblem(merged);
+    // restore_after: the reject path of IncrementalEstimator::addBatch (IC/src/core/IncrementalEstimator.cpp:350, 515) - the container's own
+    // saveDesignVariables before the optimisation and restoreDesignVariables after it (IncrementalOptimizationProblem.cpp:415-426)
+    if (restore_after) merged->saveDesignVariables();
     SolutionReturnValue r = optimizer.optimize();  // initialises: block indices and column bases stay as the optimiser assigned them
+    if (restore_after) merged->restoreDesignVariables();
     std::map<const DesignVariable*, std::pair<int, int>> label;
     for (int v = 0; v < n_sets; ++v) { label[sq[v].get()] = std::make_pair(0, v); label[st[v].get()] = std::make_pair(1, v); }
     for (size_t j = 0; j < B.size(); ++j) { label[bq[j].get()] = std::make_pair(2, (int)j); label[bt[j].get()] = std::make_pair(3, (int)j); }

@@ -110,3 +110,20 @@ def test_batch_order_is_the_reference_estimators_merged_problem(oracle_lib, n):
         order, groups, r, cp, bl, sp = oa.reference_estimator_problem(p)
         assert np.array_equal(order, g[f"gn{n}_estimator_order"]) and groups == (1, 2, 0)
         assert [r["iterations"], r["failed_iterations"], r["j_start"], r["j_final"], r["linear_solver_failure"]] == list(g[f"gn{n}_result"])
+
+
+def test_rejected_batch_restores_every_design_variable_bit_for_bit(oracle_lib):
+    """build container only: the reject path of IncrementalEstimator::addBatch (IC/src/core/IncrementalEstimator.cpp:350, 515) through the
+    reference's own container - saveDesignVariables before the optimisation, restoreDesignVariables after it - hands back every design
+    variable exactly as it was (getParameters / setParameters of RotationQuaternion, EuclideanPoint, DesignVariableAdapter: no
+    re-normalisation, no rounding), which is the contract of kb_save_design_variables / kb_restore_design_variables (a device-side copy;
+    tests/test_live_handle_gpu.py), and the optimisation in between is the one of the fixture."""
+    if oa.build_reference_cameras() is None:
+        pytest.skip("no reference tree and no prebuilt oracle/_ref here")
+    g = np.load(GN_GOLD)
+    for n in (3, 8):
+        p = gn_problem(g, n)
+        order, groups, r, cp, bl, sp = oa.reference_estimator_problem(p, restore_after=True)
+        assert [r["iterations"], r["failed_iterations"], r["j_start"], r["j_final"], r["linear_solver_failure"]] == list(g[f"gn{n}_result"])
+        assert np.array_equal(cp, p.cam_params) and np.array_equal(bl.reshape(-1, 7), np.reshape(p.baselines, (-1, 7))) and np.array_equal(sp, p.set_poses)
+        assert not np.array_equal(g[f"gn{n}_final_set_poses"], p.set_poses)  # the optimisation did move them
